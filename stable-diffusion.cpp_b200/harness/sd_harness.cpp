@@ -1,0 +1,578 @@
+// sd_harness.cpp -- synthetic-weight whole-model harness (C-ABI in include/sd_b200_harness.h).
+//
+// HOST code only.  It compiles the reference's own header-only graph builders and sampler
+// (included from /root/reference at build time, nothing is copied) and runs them on whichever
+// ggml backend the caller names: "CPU" (the oracle) or "B200_<i>" (this repo's plugin).
+//   UNetModelRunner            src/model/diffusion/unet.hpp:747-858
+//   AutoEncoderKL              src/model/vae/auto_encoder_kl.hpp:662-760
+//   Flux::FluxRunner           src/model/diffusion/flux.hpp
+//   sample_k_diffusion         src/runtime/denoiser.hpp:2794
+//   ClassifierFreeGuidance     src/runtime/guidance.cpp:149-178
+// Our own code here is: the synthetic RunnerWeightManager (weight_manager.h:10-17 interface),
+// seeded weight generation, the denoise callback (a minimal restatement of the lambda at
+// src/stable-diffusion.cpp:2625-2895 for the plain cond/uncond CFG case), and the C-ABI glue.
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "ggml-backend.h"
+#include "ggml.h"
+
+#include "model/diffusion/flux.hpp"
+#include "model/diffusion/unet.hpp"
+#include "model/vae/auto_encoder_kl.hpp"
+#include "runtime/denoiser.hpp"
+#include "runtime/guidance.h"
+#include "core/rng_philox.hpp"
+
+#include "../../include/sd_b200_harness.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(const std::string& msg) {
+    g_last_error = msg;
+    fprintf(stderr, "[sd_harness] error: %s\n", msg.c_str());
+    return -1;
+}
+
+// ---------------------------------------------------------------- seeded weight generation
+inline uint64_t splitmix64(uint64_t& s) {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z          = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z          = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+inline uint64_t fnv1a(const std::string& s) {
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char c : s) {
+        h ^= c;
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+// uniform in [-1, 1)
+inline float u11(uint64_t& s) {
+    return (float)((double)(splitmix64(s) >> 11) * (2.0 / 9007199254740992.0) - 1.0);
+}
+
+// Fill `n` floats: value = center + amp * U(-1,1); chunked so the stream does not depend on the
+// number of threads used.
+void fill_uniform(float* dst, int64_t n, uint64_t seed, float center, float amp) {
+    const int64_t chunk = 1 << 16;
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::atomic<int64_t> next{0};
+    auto work = [&]() {
+        for (;;) {
+            int64_t c = next.fetch_add(1);
+            if (c >= nchunks) break;
+            uint64_t s = seed ^ (0xD6E8FEB86659FD93ull * (uint64_t)(c + 1));
+            int64_t b = c * chunk, e = std::min(n, b + chunk);
+            for (int64_t i = b; i < e; ++i) dst[i] = center + amp * u11(s);
+        }
+    };
+    if (nchunks < 4) { work(); return; }
+    std::vector<std::thread> th;
+    for (unsigned i = 0; i < nt; ++i) th.emplace_back(work);
+    for (auto& t : th) t.join();
+}
+
+// ---------------------------------------------------------------- synthetic weight manager
+// All parameters live in ONE buffer on the compute backend for the whole life of the model
+// (the reference keeps weights resident too: free_compute_params=false, unet.hpp:838).
+struct SyntheticWeights : public RunnerWeightManager {
+    ggml_backend_buffer_t buffer = nullptr;
+    size_t bytes                 = 0;
+    int count                    = 0;
+
+    ~SyntheticWeights() override {
+        if (buffer) ggml_backend_buffer_free(buffer);
+    }
+    bool assign_compute_backend(const std::vector<ggml_tensor*>&, ggml_backend_t) override { return true; }
+    bool prepare_params(const std::vector<ggml_tensor*>&) override { return true; }
+    void release_compute_backend_params(const std::vector<ggml_tensor*>&) override {}
+    void release_params_backend_params(const std::vector<ggml_tensor*>&) override {}
+
+    bool materialise(ggml_backend_t backend, const std::map<std::string, ggml_tensor*>& tensors, uint64_t seed) {
+        ggml_backend_buffer_type_t buft = ggml_backend_get_default_buffer_type(backend);
+        size_t align = ggml_backend_buft_get_alignment(buft);
+        size_t total = 0;
+        for (auto& kv : tensors) {
+            size_t sz = ggml_backend_buft_get_alloc_size(buft, kv.second);
+            total += (sz + align - 1) / align * align;
+        }
+        buffer = ggml_backend_buft_alloc_buffer(buft, total + align);
+        if (!buffer) return false;
+        ggml_backend_buffer_set_usage(buffer, GGML_BACKEND_BUFFER_USAGE_WEIGHTS);
+        char* base = (char*)ggml_backend_buffer_get_base(buffer);
+        size_t off = 0;
+        std::vector<float> tmp;
+        std::vector<uint8_t> conv;
+        for (auto& kv : tensors) {
+            ggml_tensor* t = kv.second;
+            size_t sz = ggml_backend_buft_get_alloc_size(buft, t);
+            if (ggml_backend_tensor_alloc(buffer, t, base + off) != GGML_STATUS_SUCCESS) return false;
+            off += (sz + align - 1) / align * align;
+
+            const std::string& name = kv.first;
+            int64_t n = ggml_nelements(t);
+            tmp.resize(n);
+            uint64_t s = seed ^ fnv1a(name);
+            bool is_bias = name.size() >= 4 && name.compare(name.size() - 4, 4, "bias") == 0;
+            int nd = ggml_n_dims(t);
+            if (nd <= 1) {
+                // norm scales ~ 1 +- 0.1 ; biases (and other vectors) ~ +-0.05
+                bool is_scale = !is_bias && (name.find("norm") != std::string::npos || name.find("scale") != std::string::npos ||
+                                             name.find("ln_") != std::string::npos || name.find(".0.weight") != std::string::npos ||
+                                             name.find("weight") != std::string::npos);
+                if (is_scale) fill_uniform(tmp.data(), n, s, 1.0f, 0.1f);
+                else fill_uniform(tmp.data(), n, s, 0.0f, 0.05f);
+            } else {
+                // Linear [in,out] / Conv [KW,KH,IC,OC]: fan_in = prod(ne[0..nd-2]); U(+-sqrt(3/fan_in)) has variance 1/fan_in
+                int64_t fan_in = 1;
+                for (int d = 0; d < nd - 1; ++d) fan_in *= t->ne[d];
+                fill_uniform(tmp.data(), n, s, 0.0f, std::sqrt(3.0f / (float)fan_in));
+            }
+            if (t->type == GGML_TYPE_F32) {
+                ggml_backend_tensor_set(t, tmp.data(), 0, ggml_nbytes(t));
+            } else {
+                conv.resize(ggml_nbytes(t));
+                const ggml_type_traits* tt = ggml_get_type_traits(t->type);
+                if (!tt->from_float_ref) return false;
+                // quantize row by row (rows are ne[0] long)
+                int64_t nrows = n / t->ne[0];
+                size_t row_bytes = ggml_row_size(t->type, t->ne[0]);
+                for (int64_t r = 0; r < nrows; ++r)
+                    tt->from_float_ref(tmp.data() + r * t->ne[0], conv.data() + r * row_bytes, t->ne[0]);
+                ggml_backend_tensor_set(t, conv.data(), 0, ggml_nbytes(t));
+            }
+            bytes += ggml_nbytes(t);
+            count++;
+        }
+        return true;
+    }
+};
+
+enum Arch { ARCH_UNET, ARCH_VAE, ARCH_FLUX };
+
+ggml_type parse_wtype(const char* w) {
+    std::string s = w ? w : "f32";
+    if (s == "f16") return GGML_TYPE_F16;
+    if (s == "bf16") return GGML_TYPE_BF16;
+    if (s == "q8_0") return GGML_TYPE_Q8_0;
+    return GGML_TYPE_F32;
+}
+
+// graph statistics: algorithmic FLOPs per SURVEY.md 8(d)
+double graph_flops(ggml_cgraph* gf) {
+    double fl = 0;
+    int n = ggml_graph_n_nodes(gf);
+    for (int i = 0; i < n; ++i) {
+        ggml_tensor* t = ggml_graph_node(gf, i);
+        if (t->op == GGML_OP_MUL_MAT) {
+            fl += 2.0 * (double)t->src[0]->ne[0] * (double)t->ne[0] * (double)t->ne[1] * (double)t->ne[2] * (double)t->ne[3];
+        } else if (t->op == GGML_OP_FLASH_ATTN_EXT) {
+            const ggml_tensor* q = t->src[0]; const ggml_tensor* k = t->src[1]; const ggml_tensor* v = t->src[2];
+            // q [d, Lq, h, N], k [d, Lk, h_kv, N], v [dv, Lk, h_kv, N]
+            fl += 2.0 * (double)q->ne[1] * (double)k->ne[1] * (double)q->ne[2] * (double)q->ne[3] * ((double)q->ne[0] + (double)v->ne[0]);
+        } else if (t->op == GGML_OP_CONV_2D) {
+            const ggml_tensor* w = t->src[0];
+            fl += 2.0 * (double)w->ne[0] * w->ne[1] * w->ne[2] * (double)t->ne[0] * t->ne[1] * t->ne[2] * t->ne[3];
+        }
+    }
+    return fl;
+}
+
+}  // namespace
+
+struct sdh_model {
+    Arch arch;
+    std::string device;
+    ggml_backend_t backend = nullptr;
+    std::shared_ptr<SyntheticWeights> weights;
+    std::unique_ptr<UNetModelRunner> unet;
+    std::unique_ptr<AutoEncoderKL> vae;
+    std::unique_ptr<Flux::FluxRunner> flux;
+    SDVersion version = VERSION_SD1;
+    int n_threads     = 1;
+    double last_flops = 0;
+    int last_nodes    = 0;
+};
+
+namespace {
+
+sd::Tensor<float> to_sd(const sdh_tensor* t) {
+    if (!t || !t->data) return {};
+    std::vector<int64_t> shape;
+    int nd = 4;
+    while (nd > 1 && t->ne[nd - 1] == 1) nd--;
+    for (int i = 0; i < nd; ++i) shape.push_back(t->ne[i]);
+    int64_t n = 1;
+    for (auto v : shape) n *= v;
+    std::vector<float> data(t->data, t->data + n);
+    return sd::Tensor<float>(shape, std::move(data));
+}
+
+// keeps all 4 dims (x must stay 4-D even when N == 1)
+sd::Tensor<float> to_sd_nd(const sdh_tensor* t, int nd) {
+    if (!t || !t->data) return {};
+    std::vector<int64_t> shape(t->ne, t->ne + nd);
+    int64_t n = 1;
+    for (auto v : shape) n *= v;
+    std::vector<float> data(t->data, t->data + n);
+    return sd::Tensor<float>(shape, std::move(data));
+}
+
+int from_sd(const sd::Tensor<float>& s, sdh_tensor* out) {
+    if (s.empty()) return fail("model returned an empty tensor (graph_compute failed)");
+    const auto& sh = s.shape();
+    for (int i = 0; i < 4; ++i) out->ne[i] = i < (int)sh.size() ? sh[i] : 1;
+    if (out->data) memcpy(out->data, s.data(), sizeof(float) * s.numel());
+    return 0;
+}
+
+template <class BuildFn>
+std::map<std::string, ggml_type> pass1_types(BuildFn build, ggml_type wtype) {
+    // first pass with an empty storage map: discover parameter names / shapes, then ask for
+    // `wtype` on every >=2-D F32 weight (Linear weights; conv weights are already F16)
+    return {};
+}
+
+String2TensorStorage make_storage_map(const std::map<std::string, ggml_tensor*>& tensors, ggml_type wtype) {
+    String2TensorStorage m;
+    if (wtype == GGML_TYPE_F32) return m;
+    for (auto& kv : tensors) {
+        ggml_tensor* t = kv.second;
+        if (ggml_n_dims(t) != 2 || t->type != GGML_TYPE_F32) continue;
+        if (t->ne[0] % ggml_blck_size(wtype) != 0) continue;
+        TensorStorage ts(kv.first, wtype, t->ne, 2, 0);
+        m[kv.first] = ts;
+    }
+    return m;
+}
+
+ggml_backend_t init_device(const std::string& device, int n_threads) {
+    ggml_backend_dev_t dev = ggml_backend_dev_by_name(device.c_str());
+    if (!dev) return nullptr;
+    ggml_backend_t be = ggml_backend_dev_init(dev, nullptr);
+    if (!be) return nullptr;
+    if (ggml_backend_dev_type(dev) == GGML_BACKEND_DEVICE_TYPE_CPU) {
+        auto reg = ggml_backend_dev_backend_reg(dev);
+        auto fn  = (ggml_backend_set_n_threads_t)ggml_backend_reg_get_proc_address(reg, "ggml_backend_set_n_threads");
+        if (fn) fn(be, n_threads);
+    }
+    return be;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sdh_last_error(void) { return g_last_error.c_str(); }
+
+int sdh_load_backend(const char* so_path) {
+    ggml_backend_reg_t reg = ggml_backend_load(so_path);
+    if (!reg) return fail(std::string("ggml_backend_load failed for ") + so_path);
+    return (int)ggml_backend_dev_count();
+}
+
+int sdh_device_count(void) { return (int)ggml_backend_dev_count(); }
+
+const char* sdh_device_name(int index) {
+    if (index < 0 || index >= (int)ggml_backend_dev_count()) return nullptr;
+    return ggml_backend_dev_name(ggml_backend_dev_get(index));
+}
+
+sdh_model* sdh_model_create(const char* device, const char* arch, const char* wtype_s, int flags, uint64_t seed, int n_threads) {
+    std::string a = arch ? arch : "";
+    ggml_type wtype = parse_wtype(wtype_s);
+    auto m = std::make_unique<sdh_model>();
+    m->device    = device ? device : "CPU";
+    m->n_threads = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    m->backend   = init_device(m->device, m->n_threads);
+    if (!m->backend) { fail("no such device: " + m->device); return nullptr; }
+    m->weights = std::make_shared<SyntheticWeights>();
+    bool fa = flags & 1, direct = flags & 2;
+
+    std::map<std::string, ggml_tensor*> tensors;
+    if (a == "sd15_unet" || a == "sdxl_unet" || a == "unet_tiny") {
+        m->arch    = ARCH_UNET;
+        m->version = a == "sdxl_unet" ? VERSION_SDXL : (a == "unet_tiny" ? VERSION_SD1_TINY_UNET : VERSION_SD1);
+        const std::string prefix = "model.diffusion_model";
+        String2TensorStorage smap;
+        {
+            UNetModelRunner probe(m->backend, {}, prefix, m->version, m->weights);
+            std::map<std::string, ggml_tensor*> pt;
+            probe.get_param_tensors(pt, prefix);
+            smap = make_storage_map(pt, wtype);
+        }
+        m->unet = std::make_unique<UNetModelRunner>(m->backend, smap, prefix, m->version, m->weights);
+        m->unet->get_param_tensors(tensors, prefix);
+        m->unet->set_flash_attention_enabled(fa);
+        m->unet->set_conv2d_direct_enabled(direct);
+    } else if (a == "vae_decoder" || a == "vae_decoder_sdxl") {
+        m->arch    = ARCH_VAE;
+        m->version = a == "vae_decoder_sdxl" ? VERSION_SDXL : VERSION_SD1;
+        const std::string prefix = "first_stage_model";
+        String2TensorStorage smap;
+        {
+            AutoEncoderKL probe(m->backend, {}, prefix, true, false, m->version, m->weights);
+            std::map<std::string, ggml_tensor*> pt;
+            probe.get_param_tensors(pt);
+            smap = make_storage_map(pt, wtype);
+        }
+        m->vae = std::make_unique<AutoEncoderKL>(m->backend, smap, prefix, true, false, m->version, m->weights);
+        m->vae->get_param_tensors(tensors);
+        m->vae->set_flash_attention_enabled(fa);
+        m->vae->set_conv2d_direct_enabled(direct);
+    } else if (a == "flux_schnell" || a == "flux_tiny") {
+        m->arch    = ARCH_FLUX;
+        m->version = VERSION_FLUX;
+        const std::string prefix = "model.diffusion_model";
+        String2TensorStorage smap;
+        if (a == "flux_tiny") {
+            // depth is detected from weight names (flux.hpp detect_from_weights): declare 2 double + 2 single blocks
+            int64_t ne2[2] = {3072, 3072};
+            for (int i = 0; i < 2; ++i) {
+                std::string n1 = prefix + ".double_blocks." + std::to_string(i) + ".img_attn.proj.weight";
+                smap[n1] = TensorStorage(n1, wtype, ne2, 2, 0);
+                std::string n2 = prefix + ".single_blocks." + std::to_string(i) + ".modulation.lin.weight";
+                smap[n2] = TensorStorage(n2, wtype, ne2, 2, 0);
+            }
+        }
+        {
+            Flux::FluxRunner probe(m->backend, smap, prefix, m->version, m->weights);
+            std::map<std::string, ggml_tensor*> pt;
+            probe.get_param_tensors(pt, prefix);
+            String2TensorStorage typed = make_storage_map(pt, wtype);
+            for (auto& kv : typed) smap[kv.first] = kv.second;
+        }
+        m->flux = std::make_unique<Flux::FluxRunner>(m->backend, smap, prefix, m->version, m->weights);
+        m->flux->get_param_tensors(tensors, prefix);
+        m->flux->set_flash_attention_enabled(fa);
+    } else {
+        fail("unknown arch: " + a);
+        return nullptr;
+    }
+    if (!m->weights->materialise(m->backend, tensors, seed)) {
+        fail("weight allocation failed");
+        return nullptr;
+    }
+    return m.release();
+}
+
+void sdh_model_free(sdh_model* m) {
+    if (!m) return;
+    m->unet.reset();
+    m->vae.reset();
+    m->flux.reset();
+    m->weights.reset();
+    if (m->backend) ggml_backend_free(m->backend);
+    delete m;
+}
+
+size_t sdh_model_param_bytes(const sdh_model* m) { return m->weights ? m->weights->bytes : 0; }
+int sdh_model_param_count(const sdh_model* m) { return m->weights ? m->weights->count : 0; }
+
+int sdh_model_out_shape(sdh_model* m, const sdh_tensor* x, int64_t out_ne[4]) {
+    if (!m || !x) return fail("null argument");
+    for (int i = 0; i < 4; ++i) out_ne[i] = x->ne[i];
+    if (m->arch == ARCH_VAE) {
+        out_ne[0] = x->ne[0] * 8;
+        out_ne[1] = x->ne[1] * 8;
+        out_ne[2] = 3;
+    }
+    return 0;
+}
+
+static sd::Tensor<float> run_model(sdh_model* m, const sd::Tensor<float>& x, const sd::Tensor<float>& t,
+                                   const sd::Tensor<float>& ctx, const sd::Tensor<float>& y) {
+    switch (m->arch) {
+        case ARCH_UNET:
+            return m->unet->compute(m->n_threads, x, t, ctx, {}, y);
+        case ARCH_VAE:
+            return m->vae->_compute(m->n_threads, x, true);
+        case ARCH_FLUX: {
+            sd::Tensor<float> guidance;  // schnell: no guidance embed
+            return m->flux->compute(m->n_threads, x, t, ctx, {}, y, guidance);
+        }
+    }
+    return {};
+}
+
+int sdh_model_forward(sdh_model* m, const sdh_tensor* x, const sdh_tensor* timesteps, const sdh_tensor* context,
+                      const sdh_tensor* y, sdh_tensor* out, double* wall_ms) {
+    if (!m || !x || !out) return fail("null argument");
+    auto xs = to_sd_nd(x, 4);
+    auto ts = to_sd_nd(timesteps, 1);
+    auto cs = to_sd_nd(context, 3);
+    auto ys = to_sd_nd(y, 2);
+    auto t0 = std::chrono::steady_clock::now();
+    sd::Tensor<float> r = run_model(m, xs, ts, cs, ys);
+    auto t1 = std::chrono::steady_clock::now();
+    if (wall_ms) *wall_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    return from_sd(r, out);
+}
+
+static ggml_cgraph* build_only(sdh_model* m, const sd::Tensor<float>& x, const sd::Tensor<float>& t,
+                               const sd::Tensor<float>& ctx, const sd::Tensor<float>& y);
+
+int sdh_model_dump_graph(sdh_model* m, const sdh_tensor* x, const sdh_tensor* timesteps, const sdh_tensor* context,
+                         const sdh_tensor* y, const char* path) {
+    if (!m || !x) return fail("null argument");
+    auto xs = to_sd_nd(x, 4);
+    auto ts = to_sd_nd(timesteps, 1);
+    auto cs = to_sd_nd(context, 3);
+    auto ys = to_sd_nd(y, 2);
+    ggml_cgraph* gf = build_only(m, xs, ts, cs, ys);
+    if (!gf) return fail("graph build failed");
+    m->last_flops = graph_flops(gf);
+    m->last_nodes = ggml_graph_n_nodes(gf);
+    FILE* f = path ? fopen(path, "w") : nullptr;
+    if (f) {
+        int n = ggml_graph_n_nodes(gf);
+        for (int i = 0; i < n; ++i) {
+            ggml_tensor* nd = ggml_graph_node(gf, i);
+            fprintf(f, "%d %s", i, ggml_op_name(nd->op));
+            if (nd->op == GGML_OP_UNARY) fprintf(f, "(%s)", ggml_unary_op_name(ggml_get_unary_op(nd)));
+            fprintf(f, " %s [%lld,%lld,%lld,%lld] nb[%zu,%zu,%zu,%zu] fl=%d view=%d p0=%d p1=%d", ggml_type_name(nd->type),
+                    (long long)nd->ne[0], (long long)nd->ne[1], (long long)nd->ne[2], (long long)nd->ne[3], nd->nb[0], nd->nb[1],
+                    nd->nb[2], nd->nb[3], nd->flags, nd->view_src ? 1 : 0, nd->op_params[0], nd->op_params[1]);
+            for (int s = 0; s < GGML_MAX_SRC; ++s) {
+                ggml_tensor* sr = nd->src[s];
+                if (!sr) continue;
+                fprintf(f, " | %s [%lld,%lld,%lld,%lld] nb[%zu,%zu,%zu,%zu] %s%s", ggml_type_name(sr->type), (long long)sr->ne[0],
+                        (long long)sr->ne[1], (long long)sr->ne[2], (long long)sr->ne[3], sr->nb[0], sr->nb[1], sr->nb[2], sr->nb[3],
+                        ggml_op_name(sr->op), ggml_is_contiguous(sr) ? "" : " NC");
+            }
+            fprintf(f, "\n");
+        }
+        fclose(f);
+    }
+    return m->last_nodes;
+}
+
+double sdh_model_last_graph_flops(const sdh_model* m) { return m->last_flops; }
+int sdh_model_last_graph_nodes(const sdh_model* m) { return m->last_nodes; }
+
+// ---------------------------------------------------------------- scheduler + sampler
+// calculate_alphas_cumprod / refresh_compvis_denoiser_sigmas live in a .cpp of the reference
+// (src/stable-diffusion.cpp:173-186, 666-681), not in a header; these few lines restate them.
+static void init_compvis(CompVisDenoiser& d) {
+    float ls_sqrt = sqrtf(0.00085f), le_sqrt = sqrtf(0.0120f);
+    float amount = le_sqrt - ls_sqrt, product = 1.0f;
+    for (int i = 0; i < TIMESTEPS; i++) {
+        float beta = ls_sqrt + amount * ((float)i / (TIMESTEPS - 1));
+        product *= 1.0f - powf(beta, 2.0f);
+        float ac       = product;
+        d.sigmas[i]     = std::sqrt((1 - ac) / ac);
+        d.log_sigmas[i] = std::log(d.sigmas[i]);
+    }
+}
+
+int sdh_schedule(int steps, float* sigmas, float* timesteps) {
+    CompVisDenoiser d;
+    init_compvis(d);
+    std::vector<float> s = d.get_sigmas((uint32_t)steps, 0, DISCRETE_SCHEDULER, VERSION_SD1);
+    if ((int)s.size() != steps + 1) return fail("scheduler returned unexpected length");
+    for (int i = 0; i <= steps; ++i) sigmas[i] = s[i];
+    if (timesteps) for (int i = 0; i < steps; ++i) timesteps[i] = d.sigma_to_t(s[i]);
+    return 0;
+}
+
+int sdh_randn(uint64_t seed, float* dst, size_t n) {
+    PhiloxRNG rng;
+    rng.manual_seed(seed);
+    std::vector<float> v = rng.randn((uint32_t)n);
+    memcpy(dst, v.data(), n * sizeof(float));
+    return 0;
+}
+
+int sdh_sample(sdh_model* m, const char* method_s, int steps, float cfg_scale, float eta, uint64_t sampler_seed,
+               const sdh_tensor* noise, const sdh_tensor* cond, const sdh_tensor* uncond, const sdh_tensor* y_cond,
+               const sdh_tensor* y_uncond, sdh_tensor* out, float* sigmas_out, float* timesteps_out, int* n_forwards,
+               double* wall_ms) {
+    if (!m || m->arch != ARCH_UNET) return fail("sdh_sample needs a unet model");
+    auto denoiser = std::make_shared<CompVisDenoiser>();
+    init_compvis(*denoiser);
+    std::vector<float> sigmas = denoiser->get_sigmas((uint32_t)steps, 0, DISCRETE_SCHEDULER, m->version);
+    if (sigmas_out) for (size_t i = 0; i < sigmas.size(); ++i) sigmas_out[i] = sigmas[i];
+
+    sd::Tensor<float> noise_t = to_sd_nd(noise, 4);
+    sd::Tensor<float> cond_t = to_sd_nd(cond, 3), uncond_t = to_sd_nd(uncond, 3);
+    sd::Tensor<float> yc = to_sd_nd(y_cond, 2), yu = to_sd_nd(y_uncond, 2);
+    sd::Tensor<float> init_latent = sd::Tensor<float>::zeros_like(noise_t);
+    sd::Tensor<float> x_t = denoiser->noise_scaling(sigmas[0], noise_t, init_latent);  // stable-diffusion.cpp:2620-2622
+
+    auto rng = std::make_shared<PhiloxRNG>();
+    rng->manual_seed(sampler_seed);
+    sd::guidance::ClassifierFreeGuidance cfg(cfg_scale, 1.0f);
+    int forwards = 0;
+    bool failed  = false;
+
+    // minimal restatement of the denoise lambda, src/stable-diffusion.cpp:2625-2895 (plain CFG path)
+    denoise_cb_t denoise = [&](const sd::Tensor<float>& x, float sigma, int step) -> sd::guidance::GuiderOutput {
+        std::vector<float> scaling = denoiser->get_scalings(sigma);
+        float c_skip = scaling[0], c_out = scaling[1], c_in = scaling[2];
+        float t = denoiser->sigma_to_t(sigma);  // prepare_sample_timesteps, :2411-2434
+        if (timesteps_out && step >= 1 && step <= steps) timesteps_out[step - 1] = t;
+        sd::Tensor<float> timesteps_tensor({1}, std::vector<float>{t});
+        sd::Tensor<float> noised_input = x * c_in;
+        sd::Tensor<float> cond_out = run_model(m, noised_input, timesteps_tensor, cond_t, yc);  // :2811
+        forwards++;
+        if (cond_out.empty()) { failed = true; return {}; }
+        sd::Tensor<float> uncond_out;
+        if (cfg_scale != 1.0f && !uncond_t.empty()) {
+            uncond_out = run_model(m, noised_input, timesteps_tensor, uncond_t, yu);  // :2829
+            forwards++;
+            if (uncond_out.empty()) { failed = true; return {}; }
+        }
+        sd::guidance::GuidanceInput gi;
+        gi.step          = step;
+        gi.schedule_size = sigmas.size();
+        gi.pred_cond     = &cond_out;
+        gi.pred_uncond   = uncond_out.empty() ? nullptr : &uncond_out;
+        sd::guidance::GuiderOutput guided = cfg.forward(gi, {});
+        sd::guidance::GuiderOutput o;
+        o.pred = guided.pred * c_out + x * c_skip;  // :2876
+        return o;
+    };
+
+    std::string ms = method_s ? method_s : "euler_a";
+    sample_method_t method = ms == "euler" ? EULER_SAMPLE_METHOD : EULER_A_SAMPLE_METHOD;
+    auto t0 = std::chrono::steady_clock::now();
+    sd::Tensor<float> x0 = sample_k_diffusion(method, denoise, x_t, sigmas, rng, eta, false, nullptr, denoiser);
+    auto t1 = std::chrono::steady_clock::now();
+    if (wall_ms) *wall_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (n_forwards) *n_forwards = forwards;
+    if (failed || x0.empty()) return fail("sampling failed");
+    return from_sd(x0, out);
+}
+
+}  // extern "C"
+
+// build_graph entry points differ per runner; all are public in the reference
+static ggml_cgraph* build_only(sdh_model* m, const sd::Tensor<float>& x, const sd::Tensor<float>& t,
+                               const sd::Tensor<float>& ctx, const sd::Tensor<float>& y) {
+    switch (m->arch) {
+        case ARCH_UNET:
+            m->unet->reset_compute_ctx();
+            return m->unet->build_graph(x, t, ctx, {}, y);
+        case ARCH_VAE:
+            m->vae->reset_compute_ctx();
+            return m->vae->build_graph(x, true);
+        case ARCH_FLUX:
+            m->flux->reset_compute_ctx();
+            return m->flux->build_graph(x, t, ctx, {}, y);
+    }
+    return nullptr;
+}

@@ -1,0 +1,195 @@
+"""ctypes binding of the whole-model harness (include/sd_b200_harness.h).
+
+Host-side plumbing only: loads host/_ref/libsd_harness.so (the reference's unmodified graph
+builders + sampler compiled around our synthetic weight manager), registers ggml backend
+plugins by path, and exposes numpy in / numpy out calls.  No compute happens in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parents[2]
+HARNESS_SO = REPO / "host" / "_ref" / "libsd_harness.so"
+B200_SO = REPO / "stable-diffusion.cpp_b200" / "lib" / "libggml-b200.so"
+
+FLAG_FLASH_ATTN = 1
+FLAG_CONV_DIRECT = 2
+
+
+class SdhTensor(C.Structure):
+    _fields_ = [("data", C.POINTER(C.c_float)), ("ne", C.c_int64 * 4)]
+
+
+def _as_sdh(a: np.ndarray | None):
+    """numpy array in ggml order: a.shape == ne[::-1] (numpy slowest-first)."""
+    if a is None:
+        return None, None
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    t = SdhTensor()
+    t.data = a.ctypes.data_as(C.POINTER(C.c_float))
+    ne = list(a.shape[::-1]) + [1] * (4 - a.ndim)
+    for i in range(4):
+        t.ne[i] = ne[i]
+    return t, a
+
+
+class Harness:
+    _lib = None
+
+    def __init__(self):
+        if Harness._lib is None:
+            if not HARNESS_SO.exists():
+                raise RuntimeError(f"{HARNESS_SO} missing: run __graft_entry__.build() where /root/reference exists")
+            lib = C.CDLL(str(HARNESS_SO), mode=C.RTLD_GLOBAL)
+            lib.sdh_load_backend.argtypes = [C.c_char_p]
+            lib.sdh_load_backend.restype = C.c_int
+            lib.sdh_device_count.restype = C.c_int
+            lib.sdh_device_name.argtypes = [C.c_int]
+            lib.sdh_device_name.restype = C.c_char_p
+            lib.sdh_last_error.restype = C.c_char_p
+            lib.sdh_model_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_uint64, C.c_int]
+            lib.sdh_model_create.restype = C.c_void_p
+            lib.sdh_model_free.argtypes = [C.c_void_p]
+            lib.sdh_model_param_bytes.argtypes = [C.c_void_p]
+            lib.sdh_model_param_bytes.restype = C.c_size_t
+            lib.sdh_model_param_count.argtypes = [C.c_void_p]
+            lib.sdh_model_param_count.restype = C.c_int
+            P = C.POINTER(SdhTensor)
+            lib.sdh_model_out_shape.argtypes = [C.c_void_p, P, C.POINTER(C.c_int64)]
+            lib.sdh_model_forward.argtypes = [C.c_void_p, P, P, P, P, P, C.POINTER(C.c_double)]
+            lib.sdh_model_dump_graph.argtypes = [C.c_void_p, P, P, P, P, C.c_char_p]
+            lib.sdh_model_last_graph_flops.argtypes = [C.c_void_p]
+            lib.sdh_model_last_graph_flops.restype = C.c_double
+            lib.sdh_model_last_graph_nodes.argtypes = [C.c_void_p]
+            lib.sdh_sample.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_float, C.c_float, C.c_uint64, P, P, P, P, P, P,
+                                       C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+            lib.sdh_schedule.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+            lib.sdh_randn.argtypes = [C.c_uint64, C.POINTER(C.c_float), C.c_size_t]
+            Harness._lib = lib
+        self.lib = Harness._lib
+
+    # ------------------------------------------------------------------ registry
+    def load_backend(self, so_path) -> int:
+        n = self.lib.sdh_load_backend(str(so_path).encode())
+        return n
+
+    def devices(self) -> list[str]:
+        return [self.lib.sdh_device_name(i).decode() for i in range(self.lib.sdh_device_count())]
+
+    def load_b200(self) -> list[str]:
+        """Register this repo's plugin; fails loudly when the CUDA library is missing."""
+        if not B200_SO.exists():
+            raise RuntimeError(f"{B200_SO} missing: the CUDA backend was not built (no CPU fallback exists)")
+        if self.load_backend(B200_SO) < 0:
+            raise RuntimeError("libggml-b200.so failed to load: " + self.last_error())
+        devs = [d for d in self.devices() if d.startswith("B200_")]
+        if not devs:
+            raise RuntimeError("libggml-b200.so loaded but registered no device (no usable sm_100 GPU?)")
+        return devs
+
+    def last_error(self) -> str:
+        return (self.lib.sdh_last_error() or b"").decode()
+
+    # ------------------------------------------------------------------ host-side reference math
+    def schedule(self, steps: int):
+        s = np.zeros(steps + 1, np.float32)
+        t = np.zeros(steps, np.float32)
+        rc = self.lib.sdh_schedule(steps, s.ctypes.data_as(C.POINTER(C.c_float)), t.ctypes.data_as(C.POINTER(C.c_float)))
+        if rc != 0:
+            raise RuntimeError(self.last_error())
+        return s, t
+
+    def randn(self, seed: int, shape) -> np.ndarray:
+        n = int(np.prod(shape))
+        a = np.zeros(n, np.float32)
+        self.lib.sdh_randn(seed, a.ctypes.data_as(C.POINTER(C.c_float)), n)
+        return a.reshape(shape)
+
+    def model(self, device: str, arch: str, wtype: str = "f16", flags: int = 0, seed: int = 1234, n_threads: int = 0):
+        return Model(self, device, arch, wtype, flags, seed, n_threads)
+
+
+class Model:
+    def __init__(self, h: Harness, device, arch, wtype, flags, seed, n_threads):
+        self.h = h
+        self.lib = h.lib
+        self.arch = arch
+        self.ptr = self.lib.sdh_model_create(device.encode(), arch.encode(), wtype.encode(), flags, seed, n_threads)
+        if not self.ptr:
+            raise RuntimeError("sdh_model_create failed: " + h.last_error())
+
+    def close(self):
+        if self.ptr:
+            self.lib.sdh_model_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def param_bytes(self) -> int:
+        return self.lib.sdh_model_param_bytes(self.ptr)
+
+    @property
+    def param_count(self) -> int:
+        return self.lib.sdh_model_param_count(self.ptr)
+
+    def _args(self, x, t, ctx, y):
+        keep = []
+        out = []
+        for a in (x, t, ctx, y):
+            s, arr = _as_sdh(a)
+            keep.append(arr)
+            out.append(C.byref(s) if s is not None else None)
+            keep.append(s)
+        return out, keep
+
+    def forward(self, x, t=None, ctx=None, y=None):
+        """x: numpy [N,C,H,W]; t: [N]; ctx: [N,77,C]; y: [N,adm].  Returns (out, wall_ms)."""
+        (px, pt, pc, py), keep = self._args(x, t, ctx, y)
+        ne = (C.c_int64 * 4)()
+        self.lib.sdh_model_out_shape(self.ptr, px, ne)
+        out = np.empty(tuple(ne)[::-1], np.float32)
+        so, _ = _as_sdh(out)
+        so.data = out.ctypes.data_as(C.POINTER(C.c_float))
+        ms = C.c_double(0)
+        rc = self.lib.sdh_model_forward(self.ptr, px, pt, pc, py, C.byref(so), C.byref(ms))
+        if rc != 0:
+            raise RuntimeError("forward failed: " + self.h.last_error())
+        return out, ms.value
+
+    def dump_graph(self, path, x, t=None, ctx=None, y=None):
+        (px, pt, pc, py), keep = self._args(x, t, ctx, y)
+        n = self.lib.sdh_model_dump_graph(self.ptr, px, pt, pc, py, str(path).encode() if path else None)
+        if n < 0:
+            raise RuntimeError(self.h.last_error())
+        return n, self.lib.sdh_model_last_graph_flops(self.ptr)
+
+    def sample(self, noise, cond, uncond, steps=20, cfg_scale=7.0, eta=1.0, method="euler_a", sampler_seed=42,
+               y_cond=None, y_uncond=None):
+        sn, a0 = _as_sdh(noise)
+        sc, a1 = _as_sdh(cond)
+        su, a2 = _as_sdh(uncond)
+        syc, a3 = _as_sdh(y_cond)
+        syu, a4 = _as_sdh(y_uncond)
+        out = np.empty_like(a0)
+        so, _ = _as_sdh(out)
+        so.data = out.ctypes.data_as(C.POINTER(C.c_float))
+        sig = np.zeros(steps + 1, np.float32)
+        ts = np.zeros(steps, np.float32)
+        nf = C.c_int(0)
+        ms = C.c_double(0)
+        ref = lambda s: C.byref(s) if s is not None else None
+        rc = self.lib.sdh_sample(self.ptr, method.encode(), steps, cfg_scale, eta, sampler_seed, ref(sn), ref(sc), ref(su),
+                                 ref(syc), ref(syu), C.byref(so), sig.ctypes.data_as(C.POINTER(C.c_float)),
+                                 ts.ctypes.data_as(C.POINTER(C.c_float)), C.byref(nf), C.byref(ms))
+        if rc != 0:
+            raise RuntimeError("sample failed: " + self.h.last_error())
+        return out, dict(sigmas=sig, timesteps=ts, n_forwards=nf.value, wall_ms=ms.value)
