@@ -1,0 +1,91 @@
+/* ggml-b200.h -- C-ABI of libggml-b200.so, a Blackwell (sm_100a) ggml backend plugin.
+ *
+ * This is the drop-in boundary: the library is loaded by the reference's own loader
+ * (ggml/src/ggml-backend-reg.cpp:221-266, env GGML_BACKEND_PATH or ggml_backend_load(path))
+ * and from then on stable-diffusion.cpp's unchanged host code (GGMLRunner, ggml_gallocr,
+ * sample(), VAE decode) talks to it only through ggml's vtables
+ * (ggml/src/ggml-backend-impl.h:17-230).  It mirrors the public header of the reference's
+ * CUDA backend (ggml/include/ggml-cuda.h) entry for entry.
+ *
+ * Every symbol below is `extern "C"` with plain pointers / integers.  The ggml_* handle types
+ * are the reference's own opaque C structs (ggml/include/ggml-backend.h).
+ */
+#ifndef GGML_B200_H
+#define GGML_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* opaque handles of the host program (declared in ggml/include/ggml-backend.h) */
+struct ggml_backend;
+struct ggml_backend_reg;
+struct ggml_backend_buffer_type;
+typedef struct ggml_backend*             ggml_backend_t;
+typedef struct ggml_backend_reg*         ggml_backend_reg_t;
+typedef struct ggml_backend_buffer_type* ggml_backend_buffer_type_t;
+
+#define GGML_B200_NAME        "B200"
+#define GGML_B200_MAX_DEVICES 16
+
+/* ---- the two symbols the reference's dlopen loader resolves (ggml-backend-reg.cpp:231-266;
+ *      macro form GGML_BACKEND_DL_IMPL / GGML_BACKEND_DL_SCORE_IMPL, ggml-backend-impl.h:240-271) */
+
+/* Returns the static registry object (api_version == GGML_BACKEND_API_VERSION == 2). */
+ggml_backend_reg_t ggml_backend_init(void);
+/* 0 = "cannot run here" (no driver, or no compute-capability-10.0 device); otherwise 100. */
+int ggml_backend_score(void);
+
+/* ---- direct entry points (replace ggml_backend_cuda_* of ggml/include/ggml-cuda.h:25-45) */
+
+/* same object ggml_backend_init() returns                       (ggml_backend_cuda_reg, ggml-cuda.h:44) */
+ggml_backend_reg_t ggml_backend_b200_reg(void);
+/* new backend instance (own stream + workspace) on `device`; NULL on error
+ *                                                                (ggml_backend_cuda_init, ggml-cuda.h:25) */
+ggml_backend_t ggml_backend_b200_init(int device);
+/* true if `backend` was created by this library                 (ggml_backend_is_cuda, ggml-cuda.h:27) */
+int ggml_backend_is_b200(ggml_backend_t backend);
+/* device-memory buffer type of `device`                         (ggml_backend_cuda_buffer_type, ggml-cuda.h:30) */
+ggml_backend_buffer_type_t ggml_backend_b200_buffer_type(int device);
+/* pinned host buffer type for staging                           (ggml_backend_cuda_host_buffer_type, ggml-cuda.h:36) */
+ggml_backend_buffer_type_t ggml_backend_b200_host_buffer_type(void);
+/* number of usable sm_100 devices                               (ggml_backend_cuda_get_device_count, ggml-cuda.h:38) */
+int ggml_backend_b200_get_device_count(void);
+/* "NVIDIA B200 (sm_100, 148 SMs)" style text                    (ggml_backend_cuda_get_device_description, :39) */
+void ggml_backend_b200_get_device_description(int device, char* description, size_t description_size);
+/* free / total HBM in bytes                                     (ggml_backend_cuda_get_device_memory, :40) */
+void ggml_backend_b200_get_device_memory(int device, size_t* free_bytes, size_t* total_bytes);
+
+/* ---- extensions, also reachable through reg->iface.get_proc_address(reg, "<name>")
+ *      (ggml-backend-impl.h:214-224), which is how an unmodified host finds them */
+
+typedef struct ggml_b200_stats {
+    uint64_t graphs;            /* graph_compute calls                                       */
+    uint64_t kernel_launches;   /* kernels launched (all hand-written: no library dispatch) */
+    uint64_t nodes_executed;    /* ggml nodes covered                                        */
+    uint64_t fused_nodes;       /* nodes absorbed into a neighbour's kernel                  */
+    double   last_graph_ms;     /* device time of the last graph_compute (CUDA events)      */
+    double   total_graph_ms;
+    uint64_t tc_gemm_launches;  /* tcgen05 GEMM launches                                     */
+    uint64_t reserved[8];
+} ggml_b200_stats;
+
+/* copy the backend instance's counters; returns 0 on success */
+int ggml_backend_b200_get_stats(ggml_backend_t backend, ggml_b200_stats* out);
+void ggml_backend_b200_reset_stats(ggml_backend_t backend);
+
+/* Run-time options (also read once from the environment, GGML_B200_<KEY>=value):
+ *   "fusion"      1/0   graph-level fusion (0 = one kernel per ggml node; used to diff fused vs unfused)
+ *   "tc_gemm"     1/0   tcgen05 GEMM (0 = CUDA-core reference GEMM kernel, bring-up/debug only)
+ *   "timing"      1/0   record CUDA events around every graph_compute (last_graph_ms)
+ *   "cuda_graphs" 1/0   replay captured CUDA graphs for repeated identical ggml graphs
+ * returns 0 on success, -1 for an unknown key. */
+int ggml_backend_b200_set_option(ggml_backend_t backend, const char* key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGML_B200_H */

@@ -1,0 +1,46 @@
+// b200_graph.h -- per-backend-instance execution context and the graph executor entry points.
+#pragma once
+
+#include "b200_common.h"
+
+#include <string>
+#include <vector>
+
+struct ggml_cgraph;
+
+// device-memory scratch used inside one graph_compute (operand packing, split-K partials, attention scores).
+// Bump allocation; chunks are only released at the start of a later graph, after the stream has drained.
+struct b200_workspace {
+    struct chunk { char* base; size_t size; size_t used; };
+    std::vector<chunk> chunks;
+    size_t high_water = 0;   // bytes requested during the current graph
+};
+
+struct b200_context {
+    int device = 0;
+    b200_device_info info{};
+    std::string name;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t copy_event = nullptr, ev_start = nullptr, ev_stop = nullptr;
+    b200_stats stats{};
+    b200_workspace ws;
+    // options (include/ggml-b200.h: ggml_backend_b200_set_option)
+    bool opt_fusion = true;
+    bool opt_tc_gemm = true;
+    bool opt_timing = true;
+    bool opt_cuda_graphs = false;
+    bool timing_pending = false;
+
+    ~b200_context();
+};
+
+b200_context* b200_context_create(const b200_device_info& info);
+int b200_context_set_option(b200_context* ctx, const char* key, int value);
+void b200_context_finalize_timing(b200_context* ctx);
+
+// vtable back-ends
+enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph);
+bool b200_supports_op(const b200_device_info& dev, const ggml_tensor* op);
+
+// caches of derived weight layouts are keyed by device address: any host write into a range drops them
+void b200_invalidate_address_range(int device, const void* ptr, size_t size);

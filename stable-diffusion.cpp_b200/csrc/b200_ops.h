@@ -1,0 +1,72 @@
+// b200_ops.h -- launchers of the hand-written sm_100a kernels (kernels/*.cu).
+// Plain C++ signatures: raw device pointers + byte strides in b200_td, a stream, scalars.
+// Every launcher enqueues on `stream` and returns the number of kernels it launched.
+#pragma once
+
+#include "b200_common.h"
+
+// ---- elementwise.cu ------------------------------------------------------------------------
+enum b200_binop { B200_ADD = 0, B200_SUB = 1, B200_MUL = 2, B200_DIV = 3 };
+int b200_launch_binary(cudaStream_t s, int op, const b200_td& a, const b200_td& b, const b200_td& dst);
+// unary ops use ggml_unary_op numbering; p0/p1 are op parameters (unused by most)
+int b200_launch_unary(cudaStream_t s, int unary_op, const b200_td& src, const b200_td& dst);
+// extra scalar ops that are separate GGML_OPs
+enum b200_scalar_op { B200_SCALE = 0, B200_CLAMP = 1, B200_SQR = 2, B200_SQRT = 3, B200_LEAKY_RELU = 4, B200_SIN = 5, B200_COS = 6, B200_LOG = 7 };
+int b200_launch_scalar_op(cudaStream_t s, int op, const b200_td& src, const b200_td& dst, float p0, float p1);
+// strided, type-converting copy (CPY / CONT / DUP); src and dst have equal element counts
+int b200_launch_copy(cudaStream_t s, const b200_td& src, const b200_td& dst);
+int b200_launch_concat(cudaStream_t s, const b200_td& a, const b200_td& b, const b200_td& dst, int dim);
+int b200_launch_repeat(cudaStream_t s, const b200_td& src, const b200_td& dst);
+int b200_launch_pad(cudaStream_t s, const b200_td& src, const b200_td& dst, const int32_t* pads /*lp0,rp0,lp1,rp1,lp2,rp2,lp3,rp3*/, bool circular);
+int b200_launch_upscale(cudaStream_t s, const b200_td& src, const b200_td& dst, int mode_flags);
+int b200_launch_timestep_embedding(cudaStream_t s, const b200_td& src, const b200_td& dst, int dim, int max_period);
+int b200_launch_get_rows(cudaStream_t s, const b200_td& src, const b200_td& idx, const b200_td& dst);
+int b200_launch_arange(cudaStream_t s, const b200_td& dst, float start, float step);
+int b200_launch_fill(cudaStream_t s, const b200_td& dst, float value);
+int b200_launch_glu(cudaStream_t s, int glu_op, const b200_td& a, const b200_td* b, const b200_td& dst, bool swapped);
+int b200_launch_sum_rows(cudaStream_t s, const b200_td& src, const b200_td& dst, bool mean);
+// f32 -> f16/bf16 pack of a strided 2-D/4-D operand into a dense K-major matrix with K padded to kpad (zero filled)
+int b200_launch_pack_rows(cudaStream_t s, const b200_td& src, void* dst, int dst_type, int64_t kpad);
+
+// ---- norm.cu ---------------------------------------------------------------------------------
+int b200_launch_group_norm(cudaStream_t s, const b200_td& src, const b200_td& dst, int n_groups, float eps);
+enum b200_norm_kind { B200_NORM_LAYER = 0, B200_NORM_RMS = 1, B200_NORM_L2 = 2 };
+int b200_launch_norm(cudaStream_t s, int kind, const b200_td& src, const b200_td& dst, float eps);
+int b200_launch_soft_max(cudaStream_t s, const b200_td& src, const b200_td* mask, const b200_td& dst, float scale, float max_bias);
+
+// ---- im2col.cu -------------------------------------------------------------------------------
+int b200_launch_im2col(cudaStream_t s, const b200_td& src /*image*/, const b200_td& dst, int64_t KW, int64_t KH, int s0, int s1, int p0,
+                       int p1, int d0, int d1, bool is_2d);
+
+// ---- gemm_ref.cu: CUDA-core GEMM (bring-up / odd shapes) ------------------------------------------
+// dst[n][m] (f32, m fastest, ldd floats between n) = sum_k A[m][k] * B[n][k];  A,B rows K-contiguous, type f32/f16/bf16
+int b200_launch_gemm_ref(cudaStream_t s, const void* A, int a_type, int64_t lda_bytes, const void* B, int b_type, int64_t ldb_bytes,
+                         float* D, int64_t ldd, int64_t M, int64_t N, int64_t K);
+
+// ---- gemm_tc.cu: tcgen05 / TMEM / TMA GEMM -------------------------------------------------------
+struct b200_gemm_args {
+    const void* A;          // [M rows][K] K-major, element type `type` (GGML_TYPE_F16 / BF16 / F32 -> kind::f16 / kind::f16(bf16) / kind::tf32)
+    const void* B;          // [N rows][K] K-major, same element type
+    int         type;
+    int64_t     M, N, K;
+    int64_t     lda, ldb;   // row strides in ELEMENTS (multiple of 16 bytes)
+    int64_t     batch;      // number of independent problems (grid.z); strides below in elements
+    int64_t     a_batch_stride, b_batch_stride, d_batch_stride;
+    int64_t     a_bcast;    // batch index of A = z / a_bcast (ggml broadcast of src0 over src1 batches); >= 1
+    float*      D;          // [N][M] f32, M fastest (dst->data), ldd floats between consecutive n
+    int64_t     ldd;
+    const float* bias;      // optional, nullptr if none
+    int         bias_mode;  // 0 none, 1 per-m (row of A: linear bias), 2 per-n (row of B: conv bias / channel)
+    const float* residual;  // optional [N][M] like D (added after bias)
+    int64_t     ldr;
+    int         act;        // 0 none, 1 SiLU, 2 GELU(tanh)
+};
+// returns kernels launched, or -1 if the shape/alignment is not supported by the TMA path (caller falls back)
+int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g, void* workspace, size_t workspace_bytes);
+size_t b200_gemm_tc_workspace_bytes(const b200_device_info& dev, const b200_gemm_args& g);
+
+// ---- attention.cu --------------------------------------------------------------------------------
+// ggml FLASH_ATTN_EXT: q f32 [d, Lq, H, N], k f16 [d, Lk, Hkv, N], v f16 [dv, Lk, Hkv, N], mask f16 [Lk, >=Lq, ...] or null,
+// dst f32 [dv, H, Lq, N]
+int b200_launch_flash_attn(cudaStream_t s, const b200_device_info& dev, const b200_td& q, const b200_td& k, const b200_td& v,
+                           const b200_td* mask, const b200_td& dst, float scale, float max_bias, float logit_softcap);

@@ -1,0 +1,419 @@
+// gemm_tc.cu -- the dense-contraction core of the backend: D[n][m] = sum_k A[m][k] * B[n][k]
+// on Blackwell 5th-generation tensor cores.
+//
+//   * operands are K-major (exactly ggml's MUL_MAT contract: src0 = [K, M], src1 = [K, N], dst = [M, N] with M
+//     fastest, ggml/src/ggml.c:3282 / ggml-cpu.c:1406), described to the hardware by two 4-D TMA tensor maps
+//     (K, rows, batch2, batch3) so ggml's batch broadcast and strided (permuted) batches need no copies
+//   * TMA (cp.async.bulk.tensor, SWIZZLE_128B, zero OOB fill) stages 128 x BK / BN x BK tiles into a
+//     STAGES-deep shared-memory ring guarded by full/empty mbarriers
+//   * one elected thread issues tcgen05.mma (kind::f16 for F16/BF16, kind::tf32 for F32) with the f32 accumulator
+//     tile 128 x BN living in TMEM; tcgen05.commit releases ring slots and finally signals the epilogue
+//   * 4 epilogue warps read TMEM (tcgen05.ld 32x32b), apply bias / activation / residual and store coalesced
+//     along M (TMEM lane == m == ggml's fastest dst axis)
+//   * small-M/N, large-K problems (SD1.5: M=256, N=1280, K=11520 -> 20 tiles on 148 SMs) are split along K;
+//     partial tiles go to a workspace and the LAST-arriving CTA of each tile reduces them in split order
+//     (deterministic) and runs the epilogue
+//
+// Roofline: tensor pipe.  Algorithmic work = 2*M*N*K flop per launch; the 128 x BN x 64 k-block costs 2*BN cycles
+// of MMA issue at cta_group::1 (B300_MICROARCH "tcgen05 floor"), i.e. 8192 flop/cycle/SM.
+#include "../b200_ops.h"
+#include "sm100_ptx.cuh"
+
+#include <cuda_fp16.h>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+#include <string>
+#include <cstring>
+
+using namespace sm100;
+
+namespace {
+
+constexpr int BM = 128;            // UMMA M (TMEM lanes)
+constexpr int BK_BYTES = 128;      // one 128-byte swizzle atom of K per stage row
+constexpr int A_STAGE_BYTES = BM * BK_BYTES;
+
+struct GemmKParams {
+    float* D;
+    int64_t ldd, d_batch_stride;
+    int64_t M, N;
+    int num_k_blocks;
+    int splits;
+    int ne12;          // batch = i2 + ne12 * i3
+    int r2, r3;        // A batch index = (i2 / r2, i3 / r3)
+    const float* bias;
+    int bias_mode;     // 0 none, 1 per m, 2 per n
+    const float* residual;
+    int64_t ldr, r_batch_stride;
+    int act;           // 0 none, 1 silu, 2 gelu(tanh)
+    float* ws_partial; // [tile][split][BN][BM]
+    unsigned* ws_counters;
+};
+
+template <int BN> struct Cfg {
+    static constexpr int B_STAGE_BYTES = BN * BK_BYTES;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    // BN <= 128: ~96-110 KB so two CTAs share an SM (one CTA's epilogue overlaps the other's main loop)
+    static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 3 : 4);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // + alignment slack
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+__device__ __forceinline__ float epilogue_act(float v, int act) {
+    if (act == 1) return v / (1.0f + expf(-v));
+    if (act == 2) return 0.5f * v * (1.0f + tanhf(0.79788456080286535587989211986876f * v * (1.0f + 0.044715f * v * v)));
+    return v;
+}
+
+// FMT: 0 = f16, 1 = bf16, 2 = tf32 (operand format field of the instruction descriptor)
+template <int BN, int FMT>
+__global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                    const GemmKParams p) {
+    using C = Cfg<BN>;
+    constexpr int BK = FMT == 2 ? 32 : 64;     // elements per 128-byte row
+    constexpr int UMMA_K = FMT == 2 ? 8 : 16;  // 32 bytes of K per instruction
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[C::STAGES], empty_bar[C::STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ int s_is_last;
+
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int split = blockIdx.z % p.splits;
+    const int batch = blockIdx.z / p.splits;
+    const int i2 = batch % p.ne12, i3 = batch / p.ne12;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int kb0 = (int)(((int64_t)split * p.num_k_blocks) / p.splits);
+    const int kb1 = (int)(((int64_t)(split + 1) * p.num_k_blocks) / p.splits);
+    const int nkb = kb1 - kb0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {
+        tmem_alloc(&tmem_base_smem, C::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % C::STAGES;
+                const uint32_t ph = (i / C::STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+                uint8_t* sa = smem + s * C::STAGE_BYTES;
+                uint8_t* sb = sa + A_STAGE_BYTES;
+                const int k = (kb0 + i) * BK;
+                tma_load_4d(sa, &tmA, &full_bar[s], k, m0, i2 / p.r2, i3 / p.r3);
+                tma_load_4d(sb, &tmB, &full_bar[s], k, n0, i2, i3);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc(FMT, BM, BN);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % C::STAGES;
+            const uint32_t ph = (i / C::STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+                const uint64_t da = make_smem_desc_sw128(sa);
+                const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // advance 32 bytes of K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+                    if (FMT == 2) mma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    else mma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                mma_commit(&empty_bar[s]);                       // ring slot reusable once these MMAs retire
+                if (i == nkb - 1) mma_commit(&tmem_full_bar);    // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+        const int ml = q * 32 + lane;                 // row inside the tile
+        const int64_t m = (int64_t)m0 + ml;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool direct = p.splits == 1;
+        float* Dp = p.D + (int64_t)batch * p.d_batch_stride;
+        const float* Rp = p.residual ? p.residual + (int64_t)batch * p.r_batch_stride : nullptr;
+        const float bias_m = (p.bias_mode == 1 && m < p.M) ? p.bias[m] : 0.f;
+        const int64_t tile_id = ((int64_t)batch * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        float* part = direct ? nullptr : p.ws_partial + ((tile_id * p.splits + split) * BN) * BM;
+
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
+            if (direct) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int64_t n = (int64_t)n0 + c0 + j;
+                    if (m < p.M && n < p.N) {
+                        float v = __uint_as_float(r[j]) + bias_m;
+                        if (p.bias_mode == 2) v += p.bias[n];
+                        v = epilogue_act(v, p.act);
+                        if (Rp) v += Rp[n * p.ldr + m];
+                        Dp[n * p.ldd + m] = v;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) part[(c0 + j) * BM + ml] = __uint_as_float(r[j]);
+            }
+        }
+        if (!direct) {
+            // publish the partial tile, then the last CTA of this tile reduces all splits in order
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) {
+                unsigned prev = atomicAdd(&p.ws_counters[tile_id], 1u);
+                s_is_last = (prev == (unsigned)p.splits - 1);
+                if (s_is_last) p.ws_counters[tile_id] = 0;   // self-reset for the next launch
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (s_is_last) {
+                __threadfence();
+                const float* base = p.ws_partial + (tile_id * p.splits) * BN * BM;
+#pragma unroll 1
+                for (int c = 0; c < BN; ++c) {
+                    const int64_t n = (int64_t)n0 + c;
+                    if (n >= p.N) break;
+                    float v = 0.f;
+                    for (int s = 0; s < p.splits; ++s) v += __ldcg(base + ((int64_t)s * BN + c) * BM + ml);
+                    if (m < p.M) {
+                        v += bias_m;
+                        if (p.bias_mode == 2) v += p.bias[n];
+                        v = epilogue_act(v, p.act);
+                        if (Rp) v += Rp[n * p.ldr + m];
+                        Dp[n * p.ldd + m] = v;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor-map cache + launch heuristics
+// ------------------------------------------------------------------------------------------------
+struct MapKey {
+    const void* ptr;
+    int type;
+    uint64_t dims[4];
+    uint64_t strides[3];
+    uint32_t box_rows;
+    bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        const uint64_t* w = (const uint64_t*)&k;
+        uint64_t h = 1469598103934665603ull;
+        for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+        return (size_t)h;
+    }
+};
+static_assert(sizeof(MapKey) % 8 == 0, "MapKey must be padded to 8 bytes");
+
+std::mutex g_map_mutex;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+
+bool make_operand_map(CUtensorMap* out, const void* ptr, int type, int64_t K, int64_t rows, int64_t ld_elems, int64_t b2, int64_t b2_stride,
+                      int64_t b3, int64_t b3_stride, uint32_t box_rows) {
+    const int64_t es = type == GGML_TYPE_F32 ? 4 : 2;
+    MapKey key;
+    memset(&key, 0, sizeof(key));
+    key.ptr = ptr;
+    key.type = type;
+    key.dims[0] = (uint64_t)K; key.dims[1] = (uint64_t)rows; key.dims[2] = (uint64_t)b2; key.dims[3] = (uint64_t)b3;
+    key.strides[0] = (uint64_t)(ld_elems * es);
+    key.strides[1] = (uint64_t)(b2_stride * es);
+    key.strides[2] = (uint64_t)(b3_stride * es);
+    key.box_rows = box_rows;
+    {
+        std::lock_guard<std::mutex> lock(g_map_mutex);
+        auto it = g_map_cache.find(key);
+        if (it != g_map_cache.end()) { *out = it->second; return true; }
+    }
+    auto enc = b200_get_tensormap_encoder();
+    if (!enc) return false;
+    CUtensorMapDataType dt = type == GGML_TYPE_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                   : (type == GGML_TYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    cuuint64_t dims[4] = {key.dims[0], key.dims[1], key.dims[2], key.dims[3]};
+    cuuint64_t strides[3] = {key.strides[0], key.strides[1], key.strides[2]};
+    // degenerate batch dims still need legal (16-byte multiple, non-zero) strides
+    if (b2 == 1 || strides[1] == 0) strides[1] = strides[0] * dims[1];
+    if (b3 == 1 || strides[2] == 0) strides[2] = strides[1] * dims[2];
+    cuuint32_t box[4] = {(cuuint32_t)(BK_BYTES / es), box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(out, dt, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    if (g_map_cache.size() > 65536) g_map_cache.clear();
+    g_map_cache[key] = *out;
+    return true;
+}
+
+struct Plan { int bn; int splits; };
+
+Plan choose_plan(const b200_device_info& dev, const b200_gemm_args& g, int num_k_blocks) {
+    const int sms = dev.sm_count > 0 ? dev.sm_count : 148;
+    const int64_t mt = (g.M + BM - 1) / BM;
+    double best = 1e30;
+    Plan bestp{128, 1};
+    const int bns[3] = {256, 128, 64};
+    for (int bi = 0; bi < 3; ++bi) {
+        const int bn = bns[bi];
+        if (bn > 64 && g.N <= bn / 2) continue;                    // do not waste more than half of the N tile
+        const int64_t nt = (g.N + bn - 1) / bn;
+        const int64_t tiles = mt * nt * g.batch;
+        const double smem_factor = bn == 64 ? 1.5 : (bn == 128 ? 1.0 : 1.0);   // smem operand bandwidth bound at small BN
+        for (int splits = 1; splits <= 16; ++splits) {
+            if (splits > num_k_blocks) break;
+            if (splits > 1 && (num_k_blocks / splits) < 4) break;   // keep the main loop meaningful
+            const int64_t ctas = tiles * splits;
+            const double per_sm = (double)((ctas + sms - 1) / sms);
+            const double kb = (double)((num_k_blocks + splits - 1) / splits);
+            // cycles: main loop + prologue/epilogue (+ reduction traffic for split-K)
+            double cta_cycles = kb * 2.0 * bn * smem_factor + 1800.0 + 6.0 * bn + (splits > 1 ? (double)splits * bn * 4.0 + 1500.0 : 0.0);
+            double t = per_sm * cta_cycles;
+            if (t < best) { best = t; bestp = Plan{bn, splits}; }
+        }
+    }
+    return bestp;
+}
+
+template <int BN, int FMT>
+cudaError_t launch_cfg(cudaStream_t s, dim3 grid, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp) {
+    using C = Cfg<BN>;
+    static bool configured[B200_MAX_DEVICES] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    k_gemm_tc<BN, FMT><<<grid, 192, C::SMEM_BYTES, s>>>(ta, tb, kp);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t b200_gemm_tc_workspace_bytes(const b200_device_info& dev, const b200_gemm_args& g) {
+    const int64_t es = g.type == GGML_TYPE_F32 ? 4 : 2;
+    const int bk = (int)(BK_BYTES / es);
+    const int nkb = (int)((g.K + bk - 1) / bk);
+    Plan pl = choose_plan(dev, g, nkb);
+    if (pl.splits == 1) return 0;
+    const int64_t tiles = ((g.M + BM - 1) / BM) * ((g.N + pl.bn - 1) / pl.bn) * g.batch;
+    return (size_t)tiles * pl.splits * pl.bn * BM * sizeof(float);
+}
+
+// split-K arrival counters: one small zero-initialised, self-resetting array per device
+static unsigned* get_counters(int64_t n) {
+    static unsigned* ptr[B200_MAX_DEVICES] = {};
+    static int64_t cap[B200_MAX_DEVICES] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cap[dev] < n) {
+        // old array may still be in use by queued kernels: leak-free because we only grow after a device sync
+        cudaDeviceSynchronize();
+        if (ptr[dev]) cudaFree(ptr[dev]);
+        int64_t newcap = n < 65536 ? 65536 : n * 2;
+        if (cudaMalloc(&ptr[dev], newcap * sizeof(unsigned)) != cudaSuccess) { ptr[dev] = nullptr; cap[dev] = 0; return nullptr; }
+        cudaMemset(ptr[dev], 0, newcap * sizeof(unsigned));
+        cap[dev] = newcap;
+    }
+    return ptr[dev];
+}
+
+int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g, void* workspace, size_t workspace_bytes) {
+    if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return 0;
+    const int64_t es = g.type == GGML_TYPE_F32 ? 4 : 2;
+    if (g.type != GGML_TYPE_F32 && g.type != GGML_TYPE_F16 && g.type != GGML_TYPE_BF16) return -1;
+    // TMA legality: 16-byte aligned bases and strides
+    if (((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15)) return -1;
+    if ((g.lda * es) % 16 || (g.ldb * es) % 16) return -1;
+    if (g.K <= 0) return -1;
+    const int bk = (int)(BK_BYTES / es);
+    const int nkb = (int)((g.K + bk - 1) / bk);
+    Plan pl = choose_plan(dev, g, nkb);
+
+    // batch decomposition: args carry a flat batch with an A broadcast ratio; map to (i2, i3) = (batch, 1)
+    CUtensorMap ta, tb;
+    const int64_t a_batches = (g.batch + g.a_bcast - 1) / g.a_bcast;
+    if ((g.a_batch_stride * es) % 16 || (g.b_batch_stride * es) % 16) return -1;
+    if (!make_operand_map(&ta, g.A, g.type, g.K, g.M, g.lda, a_batches, g.a_batch_stride, 1, 0, BM)) return -1;
+    if (!make_operand_map(&tb, g.B, g.type, g.K, g.N, g.ldb, g.batch, g.b_batch_stride, 1, 0, (uint32_t)pl.bn)) return -1;
+
+    GemmKParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.D = g.D; kp.ldd = g.ldd; kp.d_batch_stride = g.d_batch_stride;
+    kp.M = g.M; kp.N = g.N;
+    kp.num_k_blocks = nkb;
+    kp.splits = pl.splits;
+    kp.ne12 = (int)g.batch; kp.r2 = (int)g.a_bcast; kp.r3 = 1;
+    kp.bias = g.bias; kp.bias_mode = g.bias ? g.bias_mode : 0;
+    kp.residual = g.residual; kp.ldr = g.ldr; kp.r_batch_stride = g.d_batch_stride;
+    kp.act = g.act;
+    const int64_t mt = (g.M + BM - 1) / BM, nt = (g.N + pl.bn - 1) / pl.bn;
+    if (mt > 0x7fffffff || nt > 65535 || g.batch * pl.splits > 65535) return -1;
+    if (pl.splits > 1) {
+        size_t need = (size_t)mt * nt * g.batch * pl.splits * pl.bn * BM * sizeof(float);
+        if (!workspace || workspace_bytes < need) { kp.splits = 1; pl.splits = 1; }
+        else {
+            kp.ws_partial = (float*)workspace;
+            kp.ws_counters = get_counters(mt * nt * g.batch);
+            if (!kp.ws_counters) { kp.splits = 1; pl.splits = 1; }
+        }
+    }
+    dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)(g.batch * pl.splits));
+    const int fmt = g.type == GGML_TYPE_F16 ? 0 : (g.type == GGML_TYPE_BF16 ? 1 : 2);
+    cudaError_t e = cudaErrorInvalidValue;
+#define LAUNCH(BN_)                                                          \
+    do {                                                                     \
+        if (fmt == 0) e = launch_cfg<BN_, 0>(s, grid, ta, tb, kp);           \
+        else if (fmt == 1) e = launch_cfg<BN_, 1>(s, grid, ta, tb, kp);      \
+        else e = launch_cfg<BN_, 2>(s, grid, ta, tb, kp);                    \
+    } while (0)
+    if (pl.bn == 256) LAUNCH(256);
+    else if (pl.bn == 128) LAUNCH(128);
+    else LAUNCH(64);
+#undef LAUNCH
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[ggml-b200] tcgen05 GEMM launch failed: %s\n", cudaGetErrorString(e));
+        return -1;
+    }
+    return 1;
+}

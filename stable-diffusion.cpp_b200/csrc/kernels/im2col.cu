@@ -1,0 +1,60 @@
+// im2col.cu -- GGML_OP_IM2COL for the unfused graph variant (and test-backend-ops coverage).
+// Oracle: ggml/src/ggml-cpu/ops.cpp:6426-6500 (im2col_f16) / im2col_f32: image [IW, IH, IC, N] (f32 or f16) ->
+// columns [IC*KH*KW, OW, OH, N] (f16 or f32), k = ic*KH*KW + kh*KW + kw, zero outside the image.
+// HBM-bound: algorithmic bytes = |image| read + |columns| written.  In whole-model graphs the fusion pass
+// replaces IM2COL+MUL_MAT by an implicit-GEMM kernel that never materialises the columns.
+#include "../b200_ops.h"
+
+#include <cuda_fp16.h>
+
+namespace {
+
+template <typename TS, typename TD>
+__global__ void k_im2col(const char* __restrict__ src, TD* __restrict__ dst, int64_t IW, int64_t IH, int64_t IC, int64_t N, int64_t OW, int64_t OH,
+                         int KW, int KH, int s0, int s1, int p0, int p1, int d0, int d1, int64_t nb_row, int64_t nb_ch, int64_t nb_n, int64_t total) {
+    const int64_t K = IC * KH * KW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t k = i % K, r = i / K;
+        int64_t ow = r % OW; r /= OW;
+        int64_t oh = r % OH; int64_t n = r / OH;
+        int64_t ic = k / (KH * KW);
+        int kk = (int)(k % (KH * KW));
+        int kh = kk / KW, kw = kk % KW;
+        int64_t iw = ow * s0 + (int64_t)kw * d0 - p0;
+        int64_t ih = oh * s1 + (int64_t)kh * d1 - p1;
+        float v = 0.f;
+        if (iw >= 0 && iw < IW && ih >= 0 && ih < IH) {
+            const char* p = src + n * nb_n + ic * nb_ch + ih * nb_row + iw * (int64_t)sizeof(TS);
+            v = (float)(*(const TS*)p);
+        }
+        dst[i] = (TD)v;
+    }
+}
+
+}  // namespace
+
+int b200_launch_im2col(cudaStream_t s, const b200_td& src, const b200_td& dst, int64_t KW, int64_t KH, int s0, int s1, int p0, int p1, int d0,
+                       int d1, bool is_2d) {
+    const int64_t N = is_2d ? src.ne[3] : src.ne[2];
+    const int64_t IC = is_2d ? src.ne[2] : src.ne[1];
+    const int64_t IH = is_2d ? src.ne[1] : 1;
+    const int64_t IW = src.ne[0];
+    const int64_t OH = is_2d ? dst.ne[2] : 1;
+    const int64_t OW = dst.ne[1];
+    if (!is_2d) KH = 1;
+    const int64_t nb_n = is_2d ? src.nb[3] : src.nb[2];
+    const int64_t nb_ch = is_2d ? src.nb[2] : src.nb[1];
+    const int64_t nb_row = is_2d ? src.nb[1] : 0;
+    int64_t total = IC * KH * KW * OW * OH * N;
+    if (total == 0) return 0;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffff) blocks = 0x7fffffff;
+#define IM(TS, TD) k_im2col<TS, TD><<<(unsigned)blocks, 256, 0, s>>>((const char*)src.data, (TD*)dst.data, IW, IH, IC, N, OW, OH, (int)KW, (int)KH, s0, s1, p0, p1, d0, d1, nb_row, nb_ch, nb_n, total)
+    if (src.type == GGML_TYPE_F32 && dst.type == GGML_TYPE_F16) IM(float, __half);
+    else if (src.type == GGML_TYPE_F32 && dst.type == GGML_TYPE_F32) IM(float, float);
+    else if (src.type == GGML_TYPE_F16 && dst.type == GGML_TYPE_F16) IM(__half, __half);
+    else if (src.type == GGML_TYPE_F16 && dst.type == GGML_TYPE_F32) IM(__half, float);
+    else return -1;
+#undef IM
+    return 1;
+}

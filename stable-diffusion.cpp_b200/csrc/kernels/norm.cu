@@ -1,0 +1,264 @@
+// norm.cu -- reductions along rows / groups: GROUP_NORM, NORM, RMS_NORM, L2_NORM, SOFT_MAX.
+//
+// Oracle semantics (reference CPU backend):
+//   group_norm  ggml/src/ggml-cpu/ops.cpp:4079-4152  two passes (mean, then centred variance), eps inside sqrt,
+//               group g covers channels [g*cpg, min((g+1)*cpg, C)) with cpg = ceil(C / n_groups)
+//   norm        ops.cpp (ggml_compute_forward_norm_f32): mean, centred variance, 1/sqrt(var + eps)
+//   rms_norm    ops.cpp: 1/sqrt(mean(x^2) + eps);  l2_norm: 1/max(sqrt(sum x^2), eps)
+//   soft_max    ops.cpp (ggml_compute_forward_soft_max_f32): x*scale + slope*mask, max-subtracted exp, / sum
+// All are HBM-bound (one read + one write of the tensor is the algorithmic traffic); rows/groups are kept
+// in registers or shared memory between the statistics pass and the normalise pass so HBM sees each
+// element once on the way in and once on the way out.
+#include "../b200_ops.h"
+
+#include <cuda_fp16.h>
+#include <cfloat>
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// block-wide reductions; `red` is >= 32 floats of shared memory; result broadcast to all threads
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+    if (w == 0) r = warp_sum(r);
+    if (threadIdx.x == 0) red[0] = r;
+    __syncthreads();
+    return red[0];
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = (threadIdx.x < nw) ? red[threadIdx.x] : -FLT_MAX;
+    if (w == 0) r = warp_max(r);
+    if (threadIdx.x == 0) red[0] = r;
+    __syncthreads();
+    return red[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// GROUP_NORM: one CTA per (group, batch).  The group is a contiguous run of `len` floats when the
+// tensor is contiguous (W*H*cpg); it is staged in dynamic shared memory when it fits (<= 220 KB),
+// so HBM is read once; larger groups are re-read from L2/HBM in the second and third pass.
+// ------------------------------------------------------------------------------------------
+template <bool IN_SMEM>
+__global__ void __launch_bounds__(1024) k_group_norm(const float* __restrict__ x, float* __restrict__ y, int64_t inner /*W*H*/,
+                                                     int C, int cpg, int n_groups, float eps) {
+    extern __shared__ float sbuf[];
+    __shared__ float red[32];
+    int g = blockIdx.x, n = blockIdx.y;
+    int c0 = g * cpg, c1 = min(c0 + cpg, C);
+    if (c0 >= c1) return;
+    int64_t len = (int64_t)(c1 - c0) * inner;
+    const float* xp = x + ((int64_t)n * C + c0) * inner;
+    float* yp = y + ((int64_t)n * C + c0) * inner;
+
+    float s = 0.f;
+    if (((uintptr_t)xp % 16 == 0) && (len % 4 == 0)) {
+        const float4* x4 = (const float4*)xp;
+        for (int64_t i = threadIdx.x; i < len / 4; i += blockDim.x) {
+            float4 v = x4[i];
+            if (IN_SMEM) ((float4*)sbuf)[i] = v;
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+            float v = xp[i];
+            if (IN_SMEM) sbuf[i] = v;
+            s += v;
+        }
+    }
+    float mean = block_sum(s, red) / (float)len;
+    float s2 = 0.f;
+    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+        float v = (IN_SMEM ? sbuf[i] : xp[i]) - mean;
+        s2 += v * v;
+    }
+    float var = block_sum(s2, red) / (float)len;
+    float scale = 1.0f / sqrtf(var + eps);
+    if (((uintptr_t)yp % 16 == 0) && (len % 4 == 0) && ((uintptr_t)xp % 16 == 0)) {
+        for (int64_t i = threadIdx.x; i < len / 4; i += blockDim.x) {
+            float4 v = IN_SMEM ? ((const float4*)sbuf)[i] : ((const float4*)xp)[i];
+            ((float4*)yp)[i] = make_float4((v.x - mean) * scale, (v.y - mean) * scale, (v.z - mean) * scale, (v.w - mean) * scale);
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < len; i += blockDim.x) yp[i] = ((IN_SMEM ? sbuf[i] : xp[i]) - mean) * scale;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// row norms: one CTA per row (ne0 elements, arbitrary row placement, unit stride inside the row)
+// ------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void k_row_norm(b200_td a, b200_td d, float eps) {
+    __shared__ float red[32];
+    int64_t row = blockIdx.x;
+    int64_t i1 = row % a.ne[1], r = row / a.ne[1];
+    int64_t i2 = r % a.ne[2], i3 = r / a.ne[2];
+    const float* x = (const float*)((const char*)a.data + i1 * a.nb[1] + i2 * a.nb[2] + i3 * a.nb[3]);
+    float* y = (float*)((char*)d.data + i1 * d.nb[1] + i2 * d.nb[2] + i3 * d.nb[3]);
+    int64_t n = a.ne[0];
+    // rows up to 8 elements per thread * blockDim are cached in registers
+    constexpr int MAXR = 8;
+    float v[MAXR];
+    bool cached = n <= (int64_t)MAXR * blockDim.x;
+    float s = 0.f;
+    if (cached) {
+#pragma unroll
+        for (int k = 0; k < MAXR; ++k) {
+            int64_t i = threadIdx.x + (int64_t)k * blockDim.x;
+            v[k] = i < n ? x[i] : 0.f;
+            s += (KIND == B200_NORM_LAYER) ? v[k] : v[k] * v[k];
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { float t = x[i]; s += (KIND == B200_NORM_LAYER) ? t : t * t; }
+    }
+    s = block_sum(s, red);
+    float mean = 0.f, scale;
+    if (KIND == B200_NORM_LAYER) {
+        mean = s / (float)n;
+        float s2 = 0.f;
+        if (cached) {
+#pragma unroll
+            for (int k = 0; k < MAXR; ++k) {
+                int64_t i = threadIdx.x + (int64_t)k * blockDim.x;
+                if (i < n) { float t = v[k] - mean; s2 += t * t; }
+            }
+        } else {
+            for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { float t = x[i] - mean; s2 += t * t; }
+        }
+        s2 = block_sum(s2, red);
+        scale = 1.0f / sqrtf(s2 / (float)n + eps);
+    } else if (KIND == B200_NORM_RMS) {
+        scale = 1.0f / sqrtf(s / (float)n + eps);
+    } else {
+        scale = 1.0f / fmaxf(sqrtf(s), eps);
+    }
+    if (cached) {
+#pragma unroll
+        for (int k = 0; k < MAXR; ++k) {
+            int64_t i = threadIdx.x + (int64_t)k * blockDim.x;
+            if (i < n) y[i] = (v[k] - mean) * scale;
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) y[i] = (x[i] - mean) * scale;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// SOFT_MAX: one CTA per row; the scaled+masked row lives in shared memory (ne0 floats).
+// ------------------------------------------------------------------------------------------
+template <typename TM>
+__global__ void k_soft_max(b200_td a, b200_td m, b200_td d, bool has_mask, float scale, float max_bias, float m0, float m1, uint32_t n_head_log2) {
+    extern __shared__ float srow[];
+    __shared__ float red[32];
+    int64_t row = blockIdx.x;
+    int64_t i1 = row % a.ne[1], r = row / a.ne[1];
+    int64_t i2 = r % a.ne[2], i3 = r / a.ne[2];
+    const float* x = (const float*)((const char*)a.data + i1 * a.nb[1] + i2 * a.nb[2] + i3 * a.nb[3]);
+    float* y = (float*)((char*)d.data + i1 * d.nb[1] + i2 * d.nb[2] + i3 * d.nb[3]);
+    const TM* mp = has_mask ? (const TM*)((const char*)m.data + i1 * m.nb[1] + (i2 % m.ne[2]) * m.nb[2] + (i3 % m.ne[3]) * m.nb[3]) : nullptr;
+    float slope = 1.0f;
+    if (max_bias > 0.0f) {
+        uint32_t h = (uint32_t)i2;
+        slope = h < n_head_log2 ? powf(m0, (float)(h + 1)) : powf(m1, (float)(2 * (h - n_head_log2) + 1));
+    }
+    int64_t n = a.ne[0];
+    float mx = -INFINITY;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        float v = x[i] * scale;
+        if (has_mask) v += slope * (float)mp[i];
+        srow[i] = v;
+        mx = fmaxf(mx, v);
+    }
+    mx = block_max(mx, red);
+    float s = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        float e = expf(srow[i] - mx);
+        srow[i] = e;
+        s += e;
+    }
+    s = block_sum(s, red);
+    float inv = 1.0f / s;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) y[i] = srow[i] * inv;
+}
+
+}  // namespace
+
+int b200_launch_group_norm(cudaStream_t s, const b200_td& src, const b200_td& dst, int n_groups, float eps) {
+    int64_t inner = src.ne[0] * src.ne[1];
+    int C = (int)src.ne[2];
+    int N = (int)src.ne[3];
+    if (inner * C * N == 0) return 0;
+    int cpg = (C + n_groups - 1) / n_groups;
+    size_t bytes = (size_t)cpg * inner * sizeof(float);
+    dim3 grid(n_groups, N);
+    int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(128, ((cpg * inner / 4) + 31) / 32 * 32));
+    if (bytes <= 200 * 1024) {
+        static bool attr_set[B200_MAX_DEVICES] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attr_set[dev]) {
+            cudaFuncSetAttribute(k_group_norm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_set[dev] = true;
+        }
+        k_group_norm<true><<<grid, threads, bytes, s>>>((const float*)src.data, (float*)dst.data, inner, C, cpg, n_groups, eps);
+    } else {
+        k_group_norm<false><<<grid, 1024, 0, s>>>((const float*)src.data, (float*)dst.data, inner, C, cpg, n_groups, eps);
+    }
+    return 1;
+}
+
+int b200_launch_norm(cudaStream_t s, int kind, const b200_td& src, const b200_td& dst, float eps) {
+    int64_t nrows = src.ne[1] * src.ne[2] * src.ne[3];
+    if (nrows == 0 || src.ne[0] == 0) return 0;
+    int threads = src.ne[0] >= 4096 ? 1024 : (src.ne[0] >= 1024 ? 256 : 128);
+    if (nrows > 0x7fffffff) return -1;
+    switch (kind) {
+        case B200_NORM_LAYER: k_row_norm<B200_NORM_LAYER><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps); break;
+        case B200_NORM_RMS: k_row_norm<B200_NORM_RMS><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps); break;
+        default: k_row_norm<B200_NORM_L2><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps); break;
+    }
+    return 1;
+}
+
+int b200_launch_soft_max(cudaStream_t s, const b200_td& src, const b200_td* mask, const b200_td& dst, float scale, float max_bias) {
+    int64_t nrows = src.ne[1] * src.ne[2] * src.ne[3];
+    if (nrows == 0 || src.ne[0] == 0) return 0;
+    size_t bytes = (size_t)src.ne[0] * sizeof(float);
+    if (bytes > 200 * 1024 || nrows > 0x7fffffff) return -1;
+    uint32_t n_head = (uint32_t)src.ne[2];
+    uint32_t n_head_log2 = 1u << (uint32_t)floorf(log2f((float)n_head));
+    float m0 = powf(2.0f, -(max_bias) / n_head_log2), m1 = powf(2.0f, -(max_bias / 2.0f) / n_head_log2);
+    int threads = src.ne[0] >= 2048 ? 512 : (src.ne[0] >= 256 ? 256 : 64);
+    b200_td m = mask ? *mask : src;
+    bool f16mask = mask && mask->type == GGML_TYPE_F16;
+    static bool attr_set[B200_MAX_DEVICES] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev]) {
+        cudaFuncSetAttribute(k_soft_max<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_soft_max<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set[dev] = true;
+    }
+    if (f16mask) k_soft_max<__half><<<(unsigned)nrows, threads, bytes, s>>>(src, m, dst, mask != nullptr, scale, max_bias, m0, m1, n_head_log2);
+    else k_soft_max<float><<<(unsigned)nrows, threads, bytes, s>>>(src, m, dst, mask != nullptr, scale, max_bias, m0, m1, n_head_log2);
+    return 1;
+}
