@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config, through the reference-facing boundary.
+
+Workload (config.workload = "sd15_txt2img_512_euler_a_cfg7", BASELINE.json configs[1]): SD1.5 UNet, latent 64x64x4
+(512x512 image), context 77x768, F16 weights (synthetic, seeded: no checkpoints exist offline), flash-attention graph
+variant, Euler-a sampling with CFG 7.0.  One "step" = one denoise step of one image = the TWO UNet forwards (cond +
+uncond) that the reference's sample() issues per sigma plus its host-side sampler math -- all of it the reference's own
+unmodified host code (host/_ref/libsd_harness.so), dispatching through ggml's backend vtable into libggml-b200.so.
+
+  value  denoise steps/s from DEVICE time: CUDA events on the backend stream around every graph_compute of the K timed
+         steps (inputs are resident in HBM at that point), max over ranks
+  e2e    the same K steps timed by wall clock around the reference sampler call: graph build, gallocr, H2D of x / t /
+         context, graph_compute, D2H of the eps prediction, CFG combine and Euler-a update on the host
+  N > 1  CFG batch split (north_star / SURVEY.md 8e): ranks (2i, 2i+1) evaluate cond / uncond of image i and all-gather the
+         eps prediction over NCCL (64 KB) every step; N/2 images run concurrently (N = 1: one GPU does both branches)
+  --impl reference   the reference's own CPU implementation (ggml CPU backend compiled from /root/reference into
+         oracle/_ref) on the same workload with all host threads, bounded to a few minutes
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO / "stable-diffusion.cpp_b200"))
+sys.path.insert(0, str(REPO))
+
+WORKLOAD = "sd15_txt2img_512_euler_a_cfg7"
+FLOPS_PER_FORWARD = 0.80327e12        # algorithmic, recomputed from the live graph below
+CFG_SCALE, ETA = 7.0, 1.0
+
+
+def peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), hbm=d["hbm_gbs"], src="measured")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.samples, self.stop, self.index = [], threading.Event(), index
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=3)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for i, n in enumerate(names):
+            if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples):
+                reasons.append(n)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+def inputs(h, image_index: int):
+    x = h.randn(42 + 100 * image_index, (1, 4, 64, 64))
+    cond = h.randn(43 + 100 * image_index, (1, 77, 768))
+    uncond = h.randn(44, (1, 77, 768))
+    return x, cond, uncond
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU backend on the box's host cores
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from sdb200 import Harness, FLAG_FLASH_ATTN
+    from oracle.cpu_ref import load_cpu_oracle   # allowed here: this arm times the oracle itself
+    h = Harness()
+    variant = load_cpu_oracle(h)
+    cores = os.cpu_count() or 1
+    m = h.model("CPU", "sd15_unet", "f16", 0, 1234, cores)   # non-FA graph: the reference's default, and its fastest CPU path
+    x, cond, uncond = inputs(h, 0)
+    budget_s = float(os.environ.get("SDB200_REF_BUDGET_S", "150"))
+    t0 = time.time()
+    m.sample(x, cond, uncond, steps=1, cfg_scale=CFG_SCALE, eta=ETA)          # warm-up step (also sizes the run)
+    first = time.time() - t0
+    steps = max(1, min(args.steps, int(budget_s / max(first, 1e-3))))
+    t0 = time.time()
+    _, info = m.sample(x, cond, uncond, steps=steps, cfg_scale=CFG_SCALE, eta=ETA)
+    dt = time.time() - t0
+    m.close()
+    val = steps / dt
+    line = dict(impl="reference", metric="denoise_steps_per_s", value=val, unit="steps/s", n_gpus=0, steps=steps, warmup=1,
+                ms_per_step=1e3 * dt / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16", data="synthetic",
+                config=dict(workload=WORKLOAD, weights="F16 synthetic (seed 1234)", sampler="euler_a", cfg_scale=CFG_SCALE,
+                            graph="reference default (MUL_MAT+SOFT_MAX attention)", forwards_per_step=2),
+                cpu_baseline=dict(value=val, unit="steps/s", cores=cores, kind="reference",
+                                  sample=f"{steps} full CFG denoise step(s) (2 UNet forwards each), ggml CPU backend variant '{variant}', {cores} threads; "
+                                         f"steps capped from --steps {args.steps} to fit {budget_s:.0f} s"),
+                e2e=dict(value=val, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n = args.gpus
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from sdb200 import Harness, FLAG_FLASH_ATTN
+    h = Harness()
+    devs = h.load_b200()                      # raises when libggml-b200.so is missing or no sm_100 device: no CPU fallback
+    dev = f"B200_{local}"
+    if dev not in devs:
+        raise RuntimeError(f"{dev} not registered (devices: {devs})")
+    m = h.model(dev, "sd15_unet", "f16", FLAG_FLASH_ATTN, 1234, 0)
+    image = rank // 2 if world > 1 else 0
+    role = (rank % 2) if world > 1 else -1
+    x, cond, uncond = inputs(h, image)
+    nodes, flops = m.dump_graph(None, x, np.array([999.0], np.float32), cond)
+    assert abs(flops - FLOPS_PER_FORWARD) / FLOPS_PER_FORWARD < 0.01, f"graph FLOPs {flops:.4e} differ from SURVEY.md 8d"
+
+    exchange = None
+    coll_ms = [0.0]
+    if world > 1:
+        pair = dist.new_group(ranks=[2 * (rank // 2), 2 * (rank // 2) + 1]) if world > 2 else None
+        groups = [dist.new_group(ranks=[2 * i, 2 * i + 1]) for i in range(world // 2)] if world > 2 else [None]
+        grp = groups[rank // 2] if world > 2 else None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        send = torch.empty(4 * 64 * 64, dtype=torch.float32, device="cuda")
+        recv = torch.empty(2 * 4 * 64 * 64, dtype=torch.float32, device="cuda")
+        host = torch.empty(2 * 4 * 64 * 64, dtype=torch.float32).pin_memory()
+
+        def exchange(mine: np.ndarray):
+            send.copy_(torch.from_numpy(mine), non_blocking=True)
+            ev0.record()
+            dist.all_gather_into_tensor(recv, send, group=grp)      # THE collective of this path: 64 KB eps all-gather over NVLink
+            ev1.record()
+            host.copy_(recv, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            coll_ms[0] += ev0.elapsed_time(ev1)
+            both = host.numpy()
+            return both[: mine.size], both[mine.size:]
+
+    def run(steps):
+        return m.sample(x, cond, uncond, steps=steps, cfg_scale=CFG_SCALE, eta=ETA, role=role, exchange=exchange)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    run(max(args.warmup, 3))                                   # >= 3 untimed warm-up steps (plan caches, workspace, clocks)
+    barrier()
+    s0 = m.stats()
+    coll_ms[0] = 0.0
+    with ClockSampler(local) as clk:
+        t0 = time.perf_counter()
+        out, info = run(args.steps)                            # EXACTLY K timed steps
+        barrier()
+        wall = time.perf_counter() - t0
+    s1 = m.stats()
+    dev_ms = (s1["total_graph_ms"] - s0["total_graph_ms"]) + coll_ms[0]
+    launches = s1["kernel_launches"] - s0["kernel_launches"]
+    forwards = s1["graphs"] - s0["graphs"]
+    if dist is not None:
+        t = torch.tensor([wall, dev_ms, float(launches)], dtype=torch.float64, device="cuda")
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        wall, dev_ms, launches = float(tmax[0]), float(tmax[1]), float(t[2])
+    images = max(1, world // 2) if world > 1 else 1
+    value = images * args.steps / (dev_ms / 1e3)
+    e2e = images * args.steps / wall
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): per-launch CUDA events on the launching stream, separate pass
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        pk = peaks()
+        try:
+            m.set_option("kernel_timing", 1)
+            k0 = m.stats()
+            run(2)
+            k1 = m.stats()
+            m.set_option("kernel_timing", 0)
+            gl = k1["tc_gemm_launches"] - k0["tc_gemm_launches"]
+            gf = k1["tc_gemm_flops"] - k0["tc_gemm_flops"]
+            gus = k1["tc_gemm_us"] - k0["tc_gemm_us"]
+            if gus > 0:
+                ach = gf / (gus * 1e-6) / 1e12
+                roof = dict(bound="tensor", kernel="k_gemm_tc (tcgen05.mma kind::f16/tf32, TMA, TMEM)", achieved=ach, peak=pk["bf16_sustained"],
+                            unit="TFLOP/s", frac=ach / pk["bf16_sustained"], peak_source=pk["src"] + " (sustained: kernel timed inside a long step)",
+                            launches=gl, flop_per_launch=gf / max(gl, 1), us_per_launch=gus / max(gl, 1),
+                            share_of_step_device_time=(gus / 1e3) / max((k1["total_graph_ms"] - k0["total_graph_ms"]), 1e-9), traffic=None)
+        except Exception as e:   # older plugin without kernel timing
+            roof = dict(bound="tensor", error=str(e))
+        step_tflops = 2 * flops * images * args.steps / (dev_ms / 1e3) / 1e12 / max(1, n if world > 1 else 1)
+        if n == 1 and not args.no_cpu_baseline:
+            cpu_base = cpu_baseline_leg(h)
+    m.close()
+    if rank == 0:
+        line = dict(metric="denoise_steps_per_s", value=value, unit="steps/s", n_gpus=n, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16", data="synthetic",
+                    config=dict(workload=WORKLOAD, model="SD1.5 UNet (reference UNetModelRunner, synthetic F16 weights, seed 1234)",
+                                latent="64x64x4", context="77x768", sampler="euler_a eta 1", cfg_scale=CFG_SCALE, forwards_per_step=2,
+                                graph="flash-attention variant (--diffusion-fa)", images=images,
+                                parallelism="single GPU" if world == 1 else f"CFG split: cond/uncond on GPU pairs + NCCL all-gather of eps, {images} image(s)",
+                                l2="no explicit flush: every forward streams 1.72 GB of weights (> 126 MB L2)",
+                                algorithmic_tflop_per_step=2 * flops / 1e12, step_tensor_frac_of_sustained_peak=step_tflops / peaks()["bf16_sustained"],
+                                graph_nodes=nodes),
+                    e2e=dict(value=e2e, unit="steps/s", ms_per_step=1e3 * wall / args.steps,
+                             h2d_bytes_per_step=2 * (4 * 64 * 64 * 4 + 77 * 768 * 4 + 4 + 8), d2h_bytes_per_step=2 * 4 * 64 * 64 * 4),
+                    gpu_launches=int(launches), forwards=int(forwards), clocks=clk.summary(), roofline=roof, cpu_baseline=cpu_base)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_leg(h):
+    """Bounded CPU sample: ONE full CFG denoise step (2 UNet forwards) on the reference CPU backend, all host threads."""
+    from oracle.cpu_ref import load_cpu_oracle
+    variant = load_cpu_oracle(h)
+    cores = os.cpu_count() or 1
+    m = h.model("CPU", "sd15_unet", "f16", 0, 1234, cores)
+    x, cond, uncond = inputs(h, 0)
+    t0 = time.time()
+    m.sample(x, cond, uncond, steps=1, cfg_scale=CFG_SCALE, eta=ETA)
+    dt = time.time() - t0
+    m.close()
+    return dict(value=1.0 / dt, unit="steps/s", cores=cores, kind="reference",
+                sample=f"1 full CFG denoise step (2 SD1.5 UNet forwards) on the reference ggml CPU backend ('{variant}' variant, {cores} threads), {dt:.1f} s")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

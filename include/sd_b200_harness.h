@@ -91,11 +91,53 @@ int sdh_sample(sdh_model* m, const char* method, int steps, float cfg_scale, flo
                sdh_tensor* out, float* sigmas_out, float* timesteps_out, int* n_forwards,
                double* wall_ms);
 
+/* CFG-batch split over a pair of GPUs: like sdh_sample, but this process evaluates only ONE branch per
+ * step (role 0 = cond, 1 = uncond) and calls `exchange(mine, cond_out, uncond_out, n, user)` so the caller can
+ * all-gather the eps prediction over NCCL; it must fill both outputs (n floats each) and return 0.  role < 0 or
+ * exchange == NULL degenerates to sdh_sample. */
+typedef int (*sdh_exchange_fn)(const float* mine, float* cond_out, float* uncond_out, size_t n, void* user);
+int sdh_sample_split(sdh_model* m, const char* method, int steps, float cfg_scale, float eta,
+                     uint64_t sampler_seed, const sdh_tensor* noise, const sdh_tensor* cond,
+                     const sdh_tensor* uncond, const sdh_tensor* y_cond, const sdh_tensor* y_uncond,
+                     sdh_tensor* out, float* sigmas_out, float* timesteps_out, int* n_forwards,
+                     double* wall_ms, int role, sdh_exchange_fn exchange, void* user);
+
+/* Counters of the model's backend instance when it is a B200 backend (include/ggml-b200.h ggml_b200_stats), as doubles:
+ * [0] graphs [1] kernel_launches [2] nodes_executed [3] fused_nodes [4] last_graph_ms [5] total_graph_ms
+ * [6] tc_gemm_launches [7..14] reserved (see ggml-b200.h).  Returns <0 for other backends. */
+int sdh_model_backend_stats(sdh_model* m, double* out, int n);
+/* ggml_backend_b200_set_option on the model's backend (e.g. "fusion", "tc_gemm", "kernel_timing"). */
+int sdh_model_set_backend_option(sdh_model* m, const char* key, int value);
+
 /* Scheduler-only (no model): fills sigmas[steps+1] and t[steps] = sigma_to_t(sigmas[i]). */
 int sdh_schedule(int steps, float* sigmas, float* timesteps);
 
 /* Fill `n` floats with the reference's Philox N(0,1) stream for `seed` (core/rng_philox.hpp:100). */
 int sdh_randn(uint64_t seed, float* dst, size_t n);
+
+/* Run ONE ggml op (or the small op group the reference's wrapper emits) on `device` -- the same graph the
+ * reference builds, so "CPU" gives the oracle's answer and "B200_0" ours.  Inputs are given as float32 and
+ * stored on the device in the ggml type itypes[i] (0 = F32, 1 = F16, 30 = BF16: ggml_type values).
+ *   op            inputs                       ip[]                               fp[]
+ *   mul_mat       w [K,M,..], x [K,N,..]       -                                  -
+ *   conv_2d       w [KW,KH,IC,OC], x, (bias)   s0,s1,p0,p1,d0,d1                  -      (ggml_conv_2d + bias add, ggml_extend.hpp:1131)
+ *   im2col        w, x                         s0,s1,p0,p1,d0,d1,dst_type         -
+ *   group_norm    x, (w [1,1,C,1], b), -       n_groups, silu(0/1)                eps    (ggml_extend.hpp:1502 [+ SiLU])
+ *   norm|rms_norm x                            -                                  eps
+ *   soft_max      x, (mask)                    -                                  scale, max_bias
+ *   flash_attn    q, k, v, (mask)              -                                  scale  (k, v, mask stored F16)
+ *   attention     q [C,Lq,N], k, v [C,Lk,N]    n_head, flash(0/1)                 -      (ggml_ext_attention_ext, :1349)
+ *   upscale       x                            factor, mode                       -
+ *   timestep_embedding  t [N]                  dim, max_period                    -
+ *   unary         x                            ggml_unary_op                      -
+ *   add|mul       a, b                         -                                  -
+ *   scale         x                            -                                  scale, bias
+ *   concat        a, b                         dim                                -
+ *   cont_permute  x                            ax0,ax1,ax2,ax3                    -
+ *   cpy           x                            dst_type                           -      (result read back as F32)
+ * out->ne is filled; out->data (if non-NULL) must have room for the result (call once with data=NULL to size). */
+int sdh_run_op(const char* device, const char* op, int n_in, const sdh_tensor* in, const int32_t* itypes,
+               const int32_t* ip, const float* fp, sdh_tensor* out, int n_threads);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,8 @@ b200_context::~b200_context() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     for (auto& c : ws.chunks) cudaFree(c.base);
+    for (auto& p : kt_pending) { cudaEventDestroy(p.start); cudaEventDestroy(p.stop); }
+    for (auto e : kt_free) cudaEventDestroy(e);
     if (copy_event) cudaEventDestroy(copy_event);
     if (ev_start) cudaEventDestroy(ev_start);
     if (ev_stop) cudaEventDestroy(ev_stop);
@@ -61,11 +63,15 @@ int b200_context_set_option(b200_context* ctx, const char* key, int value) {
     else if (!strcmp(key, "tc_gemm")) ctx->opt_tc_gemm = value != 0;
     else if (!strcmp(key, "timing")) ctx->opt_timing = value != 0;
     else if (!strcmp(key, "cuda_graphs")) ctx->opt_cuda_graphs = value != 0;
+    else if (!strcmp(key, "kernel_timing")) ctx->opt_kernel_timing = value != 0;
     else return -1;
     return 0;
 }
 
+static void kt_flush(b200_context* ctx);
+
 void b200_context_finalize_timing(b200_context* ctx) {
+    kt_flush(ctx);
     if (!ctx->timing_pending) return;
     cudaSetDevice(ctx->device);
     if (cudaEventSynchronize(ctx->ev_stop) == cudaSuccess) {
@@ -175,6 +181,60 @@ static bool prepare_operand(b200_context* ctx, const ggml_tensor* t, int want, o
 }
 
 // ------------------------------------------------------------------------------------------------
+// tcgen05 GEMM launch wrapper: workspace for split-K, counters, optional per-launch CUDA-event timing
+// (option "kernel_timing": the roofline numerator/denominator bench.py reports for the dominant kernel)
+// ------------------------------------------------------------------------------------------------
+static void kt_flush(b200_context* ctx) {
+    if (ctx->kt_pending.empty()) return;
+    cudaSetDevice(ctx->device);
+    for (auto& p : ctx->kt_pending) {
+        float ms = 0;
+        if (cudaEventSynchronize(p.stop) == cudaSuccess && cudaEventElapsedTime(&ms, p.start, p.stop) == cudaSuccess) {
+            ctx->kt_us += (double)ms * 1e3;
+            ctx->kt_flops += p.flops;
+        } else {
+            cudaGetLastError();
+        }
+        ctx->kt_free.push_back(p.start);
+        ctx->kt_free.push_back(p.stop);
+    }
+    ctx->kt_pending.clear();
+    ctx->stats.reserved[0] = (uint64_t)ctx->kt_flops;
+    ctx->stats.reserved[1] = (uint64_t)ctx->kt_us;
+}
+
+static cudaEvent_t kt_event(b200_context* ctx) {
+    if (!ctx->kt_free.empty()) { cudaEvent_t e = ctx->kt_free.back(); ctx->kt_free.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+static int launch_tc(b200_context* ctx, const b200_gemm_args& g) {
+    if (!ctx->opt_tc_gemm) return -1;
+    size_t wsb = b200_gemm_tc_workspace_bytes(ctx->info, g);
+    void* w = wsb ? ws_alloc(ctx, wsb) : nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->opt_kernel_timing) {
+        e0 = kt_event(ctx);
+        e1 = kt_event(ctx);
+        cudaEventRecord(e0, ctx->stream);
+    }
+    int n = b200_launch_gemm_tc(ctx->stream, ctx->info, g, w, w ? wsb : 0);
+    if (ctx->opt_kernel_timing) {
+        if (n > 0) {
+            cudaEventRecord(e1, ctx->stream);
+            ctx->kt_pending.push_back({e0, e1, 2.0 * (double)g.M * (double)g.N * (double)g.K * (double)g.batch});
+        } else {
+            ctx->kt_free.push_back(e0);
+            ctx->kt_free.push_back(e1);
+        }
+    }
+    if (n > 0) ctx->stats.tc_gemm_launches += n;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
 // MUL_MAT
 // ------------------------------------------------------------------------------------------------
 static int compute_type_for(const ggml_tensor* src0) {
@@ -219,13 +279,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst) {
         g.D = (float*)((char*)dst->data + i3 * dst->nb[3]);
         g.ldd = dst->nb[1] / 4;
         g.d_batch_stride = dst->nb[2] / 4;
-        int n = -1;
-        if (ctx->opt_tc_gemm) {
-            size_t wsb = b200_gemm_tc_workspace_bytes(ctx->info, g);
-            void* w = wsb ? ws_alloc(ctx, wsb) : nullptr;
-            n = b200_launch_gemm_tc(ctx->stream, ctx->info, g, w, w ? wsb : 0);
-            if (n > 0) ctx->stats.tc_gemm_launches += n;
-        }
+        int n = launch_tc(ctx, g);
         if (n < 0) {
             // CUDA-core reference kernel (debug option, or shapes the TMA cannot describe)
             n = 0;
@@ -291,10 +345,7 @@ static int op_flash_attn(b200_context* ctx, ggml_tensor* dst) {
         g.b_batch_stride = qa.batch_stride;
         g.a_bcast = rk;
         g.D = sbuf; g.ldd = Lk; g.d_batch_stride = Lk * Lq;
-        size_t wsb = b200_gemm_tc_workspace_bytes(ctx->info, g);
-        void* w = wsb ? ws_alloc(ctx, wsb) : nullptr;
-        n = ctx->opt_tc_gemm ? b200_launch_gemm_tc(ctx->stream, ctx->info, g, w, w ? wsb : 0) : -1;
-        if (n > 0) ctx->stats.tc_gemm_launches += n;
+        n = launch_tc(ctx, g);
         if (n < 0) {
             n = 0;
             for (int64_t h = 0; h < H; ++h)
@@ -336,10 +387,7 @@ static int op_flash_attn(b200_context* ctx, ggml_tensor* dst) {
         g.D = (float*)((char*)dst->data + i3 * dst->nb[3]);
         g.ldd = dst->nb[2] / 4;       // between consecutive queries
         g.d_batch_stride = dst->nb[1] / 4;   // between heads
-        wsb = b200_gemm_tc_workspace_bytes(ctx->info, g);
-        w = wsb ? ws_alloc(ctx, wsb) : nullptr;
-        n = ctx->opt_tc_gemm ? b200_launch_gemm_tc(ctx->stream, ctx->info, g, w, w ? wsb : 0) : -1;
-        if (n > 0) ctx->stats.tc_gemm_launches += n;
+        n = launch_tc(ctx, g);
         if (n < 0) {
             n = 0;
             for (int64_t h = 0; h < H; ++h)
@@ -575,7 +623,7 @@ static inline bool node_is_noop(const ggml_tensor* t) {
 enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
     B200_CUDA_CHECK(cudaSetDevice(ctx->device));
     // the previous graph's device time is finalised here (the host has synchronised in between: it read the result)
-    if (ctx->opt_timing && ctx->timing_pending) b200_context_finalize_timing(ctx);
+    if ((ctx->opt_timing && ctx->timing_pending) || !ctx->kt_pending.empty()) b200_context_finalize_timing(ctx);
     ws_begin_graph(ctx);
     const bool timing = ctx->opt_timing && !ctx->timing_pending;
     if (timing) cudaEventRecord(ctx->ev_start, ctx->stream);

@@ -29,7 +29,12 @@ struct b200_context {
     bool opt_tc_gemm = true;
     bool opt_timing = true;
     bool opt_cuda_graphs = false;
+    bool opt_kernel_timing = false;   // per-launch CUDA events around every tcgen05 GEMM (roofline pass only)
     bool timing_pending = false;
+    struct kt_pair { cudaEvent_t start, stop; double flops; };
+    std::vector<kt_pair> kt_pending;
+    std::vector<cudaEvent_t> kt_free;
+    double kt_us = 0, kt_flops = 0;
 
     ~b200_context();
 };

@@ -501,6 +501,40 @@ int sdh_sample(sdh_model* m, const char* method_s, int steps, float cfg_scale, f
                const sdh_tensor* noise, const sdh_tensor* cond, const sdh_tensor* uncond, const sdh_tensor* y_cond,
                const sdh_tensor* y_uncond, sdh_tensor* out, float* sigmas_out, float* timesteps_out, int* n_forwards,
                double* wall_ms) {
+    return sdh_sample_split(m, method_s, steps, cfg_scale, eta, sampler_seed, noise, cond, uncond, y_cond, y_uncond, out, sigmas_out,
+                            timesteps_out, n_forwards, wall_ms, -1, nullptr, nullptr);
+}
+
+int sdh_model_backend_stats(sdh_model* m, double* out, int n) {
+    if (!m || !out) return fail("null argument");
+    ggml_backend_dev_t dev = ggml_backend_get_device(m->backend);
+    ggml_backend_reg_t reg = dev ? ggml_backend_dev_backend_reg(dev) : nullptr;
+    typedef int (*get_stats_t)(ggml_backend_t, void*);
+    get_stats_t fn = reg ? (get_stats_t)ggml_backend_reg_get_proc_address(reg, "ggml_backend_b200_get_stats") : nullptr;
+    if (!fn) return fail("backend has no ggml_backend_b200_get_stats");
+    struct { uint64_t graphs, launches, nodes, fused; double last_ms, total_ms; uint64_t tc, reserved[8]; } s;
+    if (fn(m->backend, &s) != 0) return fail("get_stats failed");
+    double v[16] = {(double)s.graphs, (double)s.launches, (double)s.nodes, (double)s.fused, s.last_ms, s.total_ms, (double)s.tc,
+                    (double)s.reserved[0], (double)s.reserved[1], (double)s.reserved[2], (double)s.reserved[3], (double)s.reserved[4],
+                    (double)s.reserved[5], (double)s.reserved[6], (double)s.reserved[7], 0};
+    for (int i = 0; i < n && i < 16; ++i) out[i] = v[i];
+    return 0;
+}
+
+int sdh_model_set_backend_option(sdh_model* m, const char* key, int value) {
+    if (!m) return fail("null argument");
+    ggml_backend_dev_t dev = ggml_backend_get_device(m->backend);
+    ggml_backend_reg_t reg = dev ? ggml_backend_dev_backend_reg(dev) : nullptr;
+    typedef int (*set_opt_t)(ggml_backend_t, const char*, int);
+    set_opt_t fn = reg ? (set_opt_t)ggml_backend_reg_get_proc_address(reg, "ggml_backend_b200_set_option") : nullptr;
+    if (!fn) return fail("backend has no ggml_backend_b200_set_option");
+    return fn(m->backend, key, value);
+}
+
+int sdh_sample_split(sdh_model* m, const char* method_s, int steps, float cfg_scale, float eta, uint64_t sampler_seed,
+                     const sdh_tensor* noise, const sdh_tensor* cond, const sdh_tensor* uncond, const sdh_tensor* y_cond,
+                     const sdh_tensor* y_uncond, sdh_tensor* out, float* sigmas_out, float* timesteps_out, int* n_forwards,
+                     double* wall_ms, int role, sdh_exchange_fn exchange, void* user) {
     if (!m || m->arch != ARCH_UNET) return fail("sdh_sample needs a unet model");
     auto denoiser = std::make_shared<CompVisDenoiser>();
     init_compvis(*denoiser);
@@ -527,14 +561,27 @@ int sdh_sample(sdh_model* m, const char* method_s, int steps, float cfg_scale, f
         if (timesteps_out && step >= 1 && step <= steps) timesteps_out[step - 1] = t;
         sd::Tensor<float> timesteps_tensor({1}, std::vector<float>{t});
         sd::Tensor<float> noised_input = x * c_in;
-        sd::Tensor<float> cond_out = run_model(m, noised_input, timesteps_tensor, cond_t, yc);  // :2811
-        forwards++;
-        if (cond_out.empty()) { failed = true; return {}; }
-        sd::Tensor<float> uncond_out;
-        if (cfg_scale != 1.0f && !uncond_t.empty()) {
-            uncond_out = run_model(m, noised_input, timesteps_tensor, uncond_t, yu);  // :2829
+        sd::Tensor<float> cond_out, uncond_out;
+        const bool want_uncond = cfg_scale != 1.0f && !uncond_t.empty();
+        if (role < 0 || !exchange) {
+            cond_out = run_model(m, noised_input, timesteps_tensor, cond_t, yc);  // :2811
             forwards++;
-            if (uncond_out.empty()) { failed = true; return {}; }
+            if (cond_out.empty()) { failed = true; return {}; }
+            if (want_uncond) {
+                uncond_out = run_model(m, noised_input, timesteps_tensor, uncond_t, yu);  // :2829
+                forwards++;
+                if (uncond_out.empty()) { failed = true; return {}; }
+            }
+        } else {
+            // CFG batch split over a pair of GPUs: this rank evaluates ONE branch; the caller's
+            // exchange callback all-gathers the eps prediction (the "single all-gather on the latent")
+            sd::Tensor<float> mine = role == 0 ? run_model(m, noised_input, timesteps_tensor, cond_t, yc)
+                                               : run_model(m, noised_input, timesteps_tensor, uncond_t, yu);
+            forwards++;
+            if (mine.empty()) { failed = true; return {}; }
+            cond_out   = sd::Tensor<float>::zeros_like(mine);
+            uncond_out = sd::Tensor<float>::zeros_like(mine);
+            if (exchange(mine.data(), cond_out.data(), uncond_out.data(), (size_t)mine.numel(), user) != 0) { failed = true; return {}; }
         }
         sd::guidance::GuidanceInput gi;
         gi.step          = step;
@@ -575,4 +622,89 @@ static ggml_cgraph* build_only(sdh_model* m, const sd::Tensor<float>& x, const s
             return m->flux->build_graph(x, t, ctx, {}, y);
     }
     return nullptr;
+}
+
+// ---------------------------------------------------------------- single-op runner (parity tests)
+extern "C" int sdh_run_op(const char* device, const char* op_s, int n_in, const sdh_tensor* in, const int32_t* itypes, const int32_t* ip,
+                          const float* fp, sdh_tensor* out, int n_threads) {
+    std::string op = op_s ? op_s : "";
+    ggml_backend_t be = init_device(device ? device : "CPU", n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency());
+    if (!be) return fail(std::string("no such device: ") + (device ? device : "null"));
+    ggml_init_params ip0 = {ggml_tensor_overhead() * 256 + ggml_graph_overhead(), nullptr, true};
+    ggml_context* ctx = ggml_init(ip0);
+    ggml_tensor* t[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < n_in && i < 4; ++i) {
+        if (!in[i].data) continue;
+        t[i] = ggml_new_tensor_4d(ctx, (ggml_type)(itypes ? itypes[i] : 0), in[i].ne[0], in[i].ne[1], in[i].ne[2], in[i].ne[3]);
+        ggml_set_input(t[i]);
+    }
+    ggml_tensor* r = nullptr;
+    auto I = [&](int k) { return ip ? ip[k] : 0; };
+    auto F = [&](int k) { return fp ? fp[k] : 0.f; };
+    if (op == "mul_mat") r = ggml_mul_mat(ctx, t[0], t[1]);
+    else if (op == "conv_2d") {
+        r = ggml_conv_2d(ctx, t[0], t[1], I(0), I(1), I(2), I(3), I(4), I(5));
+        if (t[2]) r = ggml_add_inplace(ctx, r, t[2]);
+    } else if (op == "im2col") r = ggml_im2col(ctx, t[0], t[1], I(0), I(1), I(2), I(3), I(4), I(5), true, (ggml_type)I(6));
+    else if (op == "group_norm") {
+        r = ggml_group_norm(ctx, t[0], I(0), F(0));
+        if (t[1]) r = ggml_mul_inplace(ctx, r, t[1]);
+        if (t[2]) r = ggml_add_inplace(ctx, r, t[2]);
+        if (I(1)) r = ggml_silu_inplace(ctx, r);
+    } else if (op == "norm") r = ggml_norm(ctx, t[0], F(0));
+    else if (op == "rms_norm") r = ggml_rms_norm(ctx, t[0], F(0));
+    else if (op == "soft_max") r = ggml_soft_max_ext(ctx, t[0], t[1], F(0), F(1));
+    else if (op == "flash_attn") {
+        r = ggml_flash_attn_ext(ctx, t[0], t[1], t[2], t[3], F(0), 0.f, 0.f);
+        ggml_flash_attn_ext_set_prec(r, GGML_PREC_F32);
+    } else if (op == "attention") r = ggml_ext_attention_ext(ctx, be, t[0], t[1], t[2], I(0), nullptr, false, I(1) != 0);
+    else if (op == "upscale") r = ggml_upscale(ctx, t[0], I(0), (ggml_scale_mode)I(1));
+    else if (op == "timestep_embedding") r = ggml_timestep_embedding(ctx, t[0], I(0), I(1));
+    else if (op == "unary") r = ggml_unary(ctx, t[0], (ggml_unary_op)I(0));
+    else if (op == "add") r = ggml_add(ctx, t[0], t[1]);
+    else if (op == "mul") r = ggml_mul(ctx, t[0], t[1]);
+    else if (op == "scale") r = ggml_scale_bias(ctx, t[0], F(0), F(1));
+    else if (op == "concat") r = ggml_concat(ctx, t[0], t[1], I(0));
+    else if (op == "cont_permute") r = ggml_cont(ctx, ggml_permute(ctx, t[0], I(0), I(1), I(2), I(3)));
+    else if (op == "cpy") r = ggml_cast(ctx, t[0], (ggml_type)I(0));
+    if (!r) { ggml_free(ctx); ggml_backend_free(be); return fail("unknown op: " + op); }
+    if (r->type != GGML_TYPE_F32) r = ggml_cast(ctx, r, GGML_TYPE_F32);
+    if (!ggml_is_contiguous(r)) r = ggml_cont(ctx, r);
+    ggml_set_output(r);
+    for (int i = 0; i < 4; ++i) out->ne[i] = r->ne[i];
+    int rc = 0;
+    if (out->data) {
+        ggml_cgraph* gf = ggml_new_graph_custom(ctx, 64, false);
+        ggml_build_forward_expand(gf, r);
+        bool supported = true;
+        for (int i = 0; i < ggml_graph_n_nodes(gf); ++i)
+            if (!ggml_backend_supports_op(be, ggml_graph_node(gf, i))) {
+                supported = false;
+                rc = fail(std::string("op not supported by device: ") + ggml_op_name(ggml_graph_node(gf, i)->op));
+            }
+        ggml_backend_buffer_t buf = supported ? ggml_backend_alloc_ctx_tensors(ctx, be) : nullptr;
+        if (supported && !buf) rc = fail("buffer allocation failed");
+        if (buf) {
+            std::vector<uint8_t> conv;
+            for (int i = 0; i < 4; ++i) {
+                if (!t[i]) continue;
+                int64_t n = ggml_nelements(t[i]);
+                if (t[i]->type == GGML_TYPE_F32) ggml_backend_tensor_set(t[i], in[i].data, 0, n * 4);
+                else {
+                    conv.resize(ggml_nbytes(t[i]));
+                    const ggml_type_traits* tt = ggml_get_type_traits(t[i]->type);
+                    int64_t nrows = n / t[i]->ne[0];
+                    size_t rb = ggml_row_size(t[i]->type, t[i]->ne[0]);
+                    for (int64_t rr = 0; rr < nrows; ++rr) tt->from_float_ref(in[i].data + rr * t[i]->ne[0], conv.data() + rr * rb, t[i]->ne[0]);
+                    ggml_backend_tensor_set(t[i], conv.data(), 0, conv.size());
+                }
+            }
+            if (ggml_backend_graph_compute(be, gf) != GGML_STATUS_SUCCESS) rc = fail("graph_compute failed");
+            else ggml_backend_tensor_get(r, out->data, 0, ggml_nbytes(r));
+            ggml_backend_buffer_free(buf);
+        }
+    }
+    ggml_free(ctx);
+    ggml_backend_free(be);
+    return rc;
 }

@@ -37,6 +37,12 @@ def _as_sdh(a: np.ndarray | None):
     return t, a
 
 
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_size_t, C.c_void_p)
+
+STAT_KEYS = ("graphs", "kernel_launches", "nodes_executed", "fused_nodes", "last_graph_ms", "total_graph_ms", "tc_gemm_launches",
+             "tc_gemm_flops", "tc_gemm_us", "cuda_graph_replays", "r3", "r4", "r5", "r6", "r7")
+
+
 class Harness:
     _lib = None
 
@@ -69,6 +75,13 @@ class Harness:
                                        C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double)]
             lib.sdh_schedule.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
             lib.sdh_randn.argtypes = [C.c_uint64, C.POINTER(C.c_float), C.c_size_t]
+            lib.sdh_run_op.argtypes = [C.c_char_p, C.c_char_p, C.c_int, P, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_float), P, C.c_int]
+            lib.sdh_model_backend_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+            lib.sdh_model_set_backend_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+            lib.sdh_sample_split.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_float, C.c_float, C.c_uint64, P, P, P, P, P, P,
+                                             C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                             C.c_int, EXCHANGE_FN, C.c_void_p]
             Harness._lib = lib
         self.lib = Harness._lib
 
@@ -108,6 +121,33 @@ class Harness:
         a = np.zeros(n, np.float32)
         self.lib.sdh_randn(seed, a.ctypes.data_as(C.POINTER(C.c_float)), n)
         return a.reshape(shape)
+
+    def run_op(self, device: str, op: str, inputs, itypes=None, ip=(), fp=(), n_threads: int = 0) -> np.ndarray:
+        """Run one ggml op (sdh_run_op) on `device`.  inputs: list of numpy arrays (numpy order = reversed ggml ne) or None."""
+        GGML_TYPES = {"f32": 0, "f16": 1, "bf16": 30}
+        n = len(inputs)
+        arr = (SdhTensor * 4)()
+        keep = []
+        for i, a in enumerate(inputs):
+            if a is None:
+                continue
+            s, k = _as_sdh(a)
+            arr[i] = s
+            keep.append(k)
+        it = (C.c_int32 * 4)(*[GGML_TYPES[t] if isinstance(t, str) else int(t) for t in (list(itypes or []) + ["f32"] * 4)[:4]])
+        ipa = (C.c_int32 * 16)(*(list(ip) + [0] * 16)[:16])
+        fpa = (C.c_float * 8)(*(list(fp) + [0.0] * 8)[:8])
+        out = SdhTensor()
+        rc = self.lib.sdh_run_op(device.encode(), op.encode(), n, arr, it, ipa, fpa, C.byref(out), n_threads)
+        if rc != 0:
+            raise RuntimeError(f"run_op({op}) sizing failed: " + self.last_error())
+        shape = tuple(out.ne)[::-1]
+        res = np.empty(shape, np.float32)
+        out.data = res.ctypes.data_as(C.POINTER(C.c_float))
+        rc = self.lib.sdh_run_op(device.encode(), op.encode(), n, arr, it, ipa, fpa, C.byref(out), n_threads)
+        if rc != 0:
+            raise RuntimeError(f"run_op({op}) on {device} failed: " + self.last_error())
+        return res
 
     def model(self, device: str, arch: str, wtype: str = "f16", flags: int = 0, seed: int = 1234, n_threads: int = 0):
         return Model(self, device, arch, wtype, flags, seed, n_threads)
@@ -172,8 +212,19 @@ class Model:
             raise RuntimeError(self.h.last_error())
         return n, self.lib.sdh_model_last_graph_flops(self.ptr)
 
+    def stats(self) -> dict:
+        """Counters of the B200 backend instance behind this model (raises for other backends)."""
+        v = (C.c_double * 16)()
+        if self.lib.sdh_model_backend_stats(self.ptr, v, 16) != 0:
+            raise RuntimeError(self.h.last_error())
+        return {k: v[i] for i, k in enumerate(STAT_KEYS)}
+
+    def set_option(self, key: str, value: int):
+        if self.lib.sdh_model_set_backend_option(self.ptr, key.encode(), int(value)) != 0:
+            raise RuntimeError(f"set_option({key}) failed")
+
     def sample(self, noise, cond, uncond, steps=20, cfg_scale=7.0, eta=1.0, method="euler_a", sampler_seed=42,
-               y_cond=None, y_uncond=None):
+               y_cond=None, y_uncond=None, role=-1, exchange=None):
         sn, a0 = _as_sdh(noise)
         sc, a1 = _as_sdh(cond)
         su, a2 = _as_sdh(uncond)
@@ -187,9 +238,22 @@ class Model:
         nf = C.c_int(0)
         ms = C.c_double(0)
         ref = lambda s: C.byref(s) if s is not None else None
-        rc = self.lib.sdh_sample(self.ptr, method.encode(), steps, cfg_scale, eta, sampler_seed, ref(sn), ref(sc), ref(su),
-                                 ref(syc), ref(syu), C.byref(so), sig.ctypes.data_as(C.POINTER(C.c_float)),
-                                 ts.ctypes.data_as(C.POINTER(C.c_float)), C.byref(nf), C.byref(ms))
+        cb = EXCHANGE_FN(0)
+        if exchange is not None:
+            def _cb(mine, cond_out, uncond_out, n, user):
+                try:
+                    a = np.ctypeslib.as_array(mine, shape=(n,))
+                    c, u = exchange(a)
+                    np.ctypeslib.as_array(cond_out, shape=(n,))[:] = c
+                    np.ctypeslib.as_array(uncond_out, shape=(n,))[:] = u
+                    return 0
+                except Exception as e:  # never let an exception cross the C boundary
+                    print("exchange callback failed:", e)
+                    return -1
+            cb = EXCHANGE_FN(_cb)
+        rc = self.lib.sdh_sample_split(self.ptr, method.encode(), steps, cfg_scale, eta, sampler_seed, ref(sn), ref(sc), ref(su),
+                                       ref(syc), ref(syu), C.byref(so), sig.ctypes.data_as(C.POINTER(C.c_float)),
+                                       ts.ctypes.data_as(C.POINTER(C.c_float)), C.byref(nf), C.byref(ms), role, cb, None)
         if rc != 0:
             raise RuntimeError("sample failed: " + self.h.last_error())
         return out, dict(sigmas=sig, timesteps=ts, n_forwards=nf.value, wall_ms=ms.value)

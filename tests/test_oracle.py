@@ -1,0 +1,139 @@
+"""CPU-only tests: pin the oracle restatements (oracle/sd_oracle.c, oracle/ops_ref.py) against
+ (a) the reference's own known-answer vectors (ggml/tests/test-conv2d.cpp -> tests/golden/ggml_test_conv2d.json),
+ (b) committed outputs of the reference CPU backend / reference scheduler (tests/golden/*.npz, *.json), and
+ (c) the reference CPU backend itself (oracle/_ref), live, when it is present.
+"""
+import ctypes
+import json
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import ops_ref as R
+
+REPO = Path(__file__).resolve().parents[1]
+GOLD = REPO / "tests" / "golden"
+
+
+@pytest.fixture(scope="module")
+def c_oracle(tmp_path_factory):
+    so = REPO / "oracle" / "libsd_oracle.so"
+    src = REPO / "oracle" / "sd_oracle.c"
+    if not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-std=c11", "-o", str(so), str(src), "-lm"])
+    lib = ctypes.CDLL(str(so))
+    lib.sd_schedule.argtypes = [ctypes.c_uint32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+    lib.sd_ancestral_step.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+    return lib
+
+
+def _c_schedule(lib, steps):
+    s = np.zeros(steps + 1, np.float32)
+    t = np.zeros(steps, np.float32)
+    lib.sd_schedule(steps, s.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), t.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    return s, t
+
+
+def test_scheduler_restatement_bit_exact_vs_golden(c_oracle):
+    gold = json.loads((GOLD / "schedule_sd15.json").read_text())
+    for steps, g in gold.items():
+        s, t = _c_schedule(c_oracle, int(steps))
+        assert [f"{v:08x}" for v in s.view(np.uint32)] == g["sigmas_hex"], f"sigmas differ at steps={steps}"
+        assert [f"{v:08x}" for v in t.view(np.uint32)] == g["timesteps_hex"], f"timesteps differ at steps={steps}"
+
+
+def test_scheduler_restatement_bit_exact_vs_reference_code(c_oracle, harness):
+    """host/_ref/libsd_harness.so contains the reference's own denoiser.hpp: compare bit patterns live."""
+    for steps in (1, 3, 7, 20, 33):
+        s_ref, t_ref = harness.schedule(steps)
+        s, t = _c_schedule(c_oracle, steps)
+        assert np.array_equal(s.view(np.uint32), s_ref.view(np.uint32))
+        assert np.array_equal(t.view(np.uint32), t_ref.view(np.uint32))
+    # k-diffusion's well known SD1.x sigma_max
+    assert abs(float(harness.schedule(20)[0][0]) - 14.6146) < 1e-3
+
+
+def test_ancestral_step_properties(c_oracle):
+    d, u = ctypes.c_float(), ctypes.c_float()
+    s, _ = _c_schedule(c_oracle, 20)
+    for i in range(19):
+        c_oracle.sd_ancestral_step(float(s[i]), float(s[i + 1]), 1.0, ctypes.byref(d), ctypes.byref(u))
+        assert 0 <= u.value <= s[i + 1] and 0 <= d.value <= s[i + 1]
+        assert abs(d.value ** 2 + u.value ** 2 - float(s[i + 1]) ** 2) < 1e-4 * float(s[i + 1]) ** 2 + 1e-9
+    c_oracle.sd_ancestral_step(1.0, 0.5, 0.0, ctypes.byref(d), ctypes.byref(u))
+    assert (d.value, u.value) == (0.5, 0.0)
+
+
+def test_philox_fixture(harness):
+    g = json.loads((GOLD / "philox_seed42.json").read_text())
+    r = harness.randn(g["seed"], (g["n"],))
+    assert [f"{v:08x}" for v in r.view(np.uint32)] == g["values_hex"]
+
+
+def test_conv2d_restatement_vs_reference_known_answers():
+    g = json.loads((GOLD / "ggml_test_conv2d.json").read_text())
+    w = np.full((g["OC"], g["IC"], g["KH"], g["KW"]), g["kernel_value"], np.float32)
+    x = np.full((g["N"], g["IC"], g["IH"], g["IW"]), g["image_value"], np.float32)
+    cols = R.im2col(x, g["KH"], g["KW"], g["s"], g["s"], g["p"], g["p"], g["d"], g["d"])
+    got = cols.astype(np.float16).view(np.uint16).ravel()[:480]
+    assert np.array_equal(got, np.array(g["expected_im2col_u16"], np.uint16))
+    y = R.conv_2d(w, x, None, g["s"], g["p"], g["d"])
+    assert np.array_equal(y.ravel()[:480], np.array(g["expected_conv2d"], np.float32))   # exact: small integers x 3.75
+
+
+OPS = np.load(GOLD / "cpu_ops.npz")
+
+
+def _close(a, b, rtol, what):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    err = np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    assert err <= rtol, f"{what}: rel_l2 {err:.3e} > {rtol}"
+
+
+def test_ops_restatement_vs_committed_cpu_backend_outputs():
+    o = OPS
+    _close(R.group_norm(o["gn_x"], 32, 1e-6), o["gn_y"], 2e-6, "group_norm")
+    _close(R.silu(R.group_norm(o["gn_x"], 32, 1e-6) * o["gn_w"] + o["gn_b"]), o["gn_affine_silu_y"], 2e-6, "gn+affine+silu")
+    _close(R.norm(o["ln_x"], 1e-5), o["ln_y"], 2e-6, "norm")
+    _close(R.rms_norm(o["ln_x"], 1e-6), o["rms_y"], 2e-6, "rms_norm")
+    _close(R.soft_max(o["sm_x"], None, 0.125), o["sm_y"], 2e-6, "soft_max")
+    _close(R.mul_mat(o["mm_w"], o["mm_x"], "f32"), o["mm_f32_y"][0, 0], 2e-6, "mul_mat f32")
+    _close(R.mul_mat(o["mm_w"], o["mm_x"], "f16"), o["mm_f16_y"][0, 0], 2e-6, "mul_mat f16")
+    _close(R.mul_mat(o["mm_w"], o["mm_x"], "bf16"), o["mm_bf16_y"][0, 0], 2e-6, "mul_mat bf16")
+    _close(R.conv_2d(o["conv_w"], o["conv_x"], o["conv_b"], 1, 1, 1), o["conv_y"], 2e-6, "conv_2d")
+    _close(R.conv_2d(o["conv_w"], o["conv_x"], o["conv_b"], 2, 1, 1), o["conv_s2_y"], 2e-6, "conv_2d stride 2")
+    # the CPU flash-attention path accumulates P.V in f16 for these head sizes (ops.cpp:8620-8633): its own noise is ~1e-3
+    _close(R.flash_attn_ext(o["fa_q"], o["fa_k"], o["fa_v"], None, 40 ** -0.5), o["fa_y"], 3e-3, "flash_attn_ext")
+    _close(R.timestep_embedding(o["ts_t"], 320), o["ts_y"][0, 0], 5e-5, "timestep_embedding")   # cosf/sinf of ~1e3 rad
+    _close(R.upscale_nearest(o["up_x"], 2), o["up_y"], 0, "upscale nearest")
+    _close(R.silu(o["act_x"]), o["silu_y"], 2e-6, "silu")
+    _close(R.gelu(o["act_x"]), o["gelu_y"], 2e-3, "gelu (CPU uses an f16 table)")
+
+
+def test_restatement_vs_live_cpu_backend(cpu_oracle):
+    """Same comparison against oracle/_ref run live (fresh seeds, SD-sized channel counts)."""
+    h = cpu_oracle
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((1, 320, 16, 16)).astype(np.float32)
+    _close(R.group_norm(x, 32, 1e-6), h.run_op("CPU", "group_norm", [x], ip=[32, 0], fp=[1e-6]), 2e-6, "group_norm live")
+    w = (rng.standard_normal((64, 32, 3, 3)) / 17).astype(np.float32)
+    xc = rng.standard_normal((1, 32, 16, 16)).astype(np.float32)
+    _close(R.conv_2d(w, xc, None, 1, 1, 1), h.run_op("CPU", "conv_2d", [w, xc], ["f16", "f32"], ip=[1, 1, 1, 1, 1, 1]), 2e-6, "conv live")
+    wm = (rng.standard_normal((128, 320)) / 18).astype(np.float32)
+    xm = rng.standard_normal((77, 320)).astype(np.float32)
+    _close(R.mul_mat(wm, xm, "f16"), h.run_op("CPU", "mul_mat", [wm, xm], ["f16", "f32"])[0, 0], 2e-6, "mul_mat live")
+
+
+def test_committed_model_fixture_matches_live_cpu_backend(cpu_oracle):
+    """The whole-model fixtures are the reference CPU backend's outputs for the seeded synthetic weights."""
+    h = cpu_oracle
+    gold = np.load(GOLD / "cpu_models.npz")
+    x = h.randn(42, (1, 4, 16, 16)); ctx = h.randn(43, (1, 77, 768)); t = np.array([999.0], np.float32)
+    m = h.model("CPU", "unet_tiny", "f16", 0, 1234, 4)
+    out, _ = m.forward(x, t, ctx)
+    m.close()
+    # different CPU variants (AVX2 / AVX-512 / AMX) reduce in different orders: allow float noise, not more
+    _close(out, gold["unet_tiny_fa0"], 1e-4, "unet_tiny vs fixture")
