@@ -43,6 +43,7 @@ b200_context* b200_context_create(const b200_device_info& info) {
     ctx->opt_tc_gemm = env_flag("GGML_B200_TC_GEMM", 1) != 0;
     ctx->opt_timing = env_flag("GGML_B200_TIMING", 1) != 0;
     ctx->opt_cuda_graphs = env_flag("GGML_B200_CUDA_GRAPHS", 0) != 0;
+    ctx->opt_fused_attn = env_flag("GGML_B200_FUSED_ATTN", 1) != 0;
     return ctx;
 }
 
@@ -50,6 +51,7 @@ b200_context::~b200_context() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     for (auto& c : ws.chunks) cudaFree(c.base);
+    for (auto& kv : plans) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (auto& p : kt_pending) { cudaEventDestroy(p.start); cudaEventDestroy(p.stop); }
     for (auto e : kt_free) cudaEventDestroy(e);
     if (copy_event) cudaEventDestroy(copy_event);
@@ -64,6 +66,7 @@ int b200_context_set_option(b200_context* ctx, const char* key, int value) {
     else if (!strcmp(key, "timing")) ctx->opt_timing = value != 0;
     else if (!strcmp(key, "cuda_graphs")) ctx->opt_cuda_graphs = value != 0;
     else if (!strcmp(key, "kernel_timing")) ctx->opt_kernel_timing = value != 0;
+    else if (!strcmp(key, "fused_attn")) ctx->opt_fused_attn = value != 0;
     else return -1;
     return 0;
 }
@@ -120,6 +123,10 @@ static void* ws_alloc(b200_context* ctx, size_t bytes) {
             c.used += bytes;
             return p;
         }
+    }
+    if (ctx->capturing) {           // allocation is illegal inside stream capture: abandon the capture, caller re-runs eagerly
+        ctx->capture_overflow = true;
+        return nullptr;
     }
     size_t sz = std::max(bytes, (size_t)64 << 20);
     if (!ws.chunks.empty()) sz = std::max(sz, ws.chunks.back().size);
@@ -245,7 +252,14 @@ static int compute_type_for(const ggml_tensor* src0) {
     return GGML_TYPE_F32;
 }
 
-static int op_mul_mat(b200_context* ctx, ggml_tensor* dst) {
+// epilogue work absorbed from the nodes that follow a MUL_MAT in the graph (see try_fuse_mul_mat)
+struct mm_fusion {
+    float* out = nullptr;         // write here instead of dst->data (same [M, N, b2, b3] layout)
+    const float* bias = nullptr;  // f32 vector
+    int bias_mode = 0;            // 1: per output row m (Linear bias), 2: per n (conv bias: n == output channel)
+};
+
+static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz = nullptr) {
     const ggml_tensor* src0 = dst->src[0];
     const ggml_tensor* src1 = dst->src[1];
     int launches = 0;
@@ -276,9 +290,11 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst) {
         g.a_batch_stride = a.batch_stride;
         g.b_batch_stride = b.batch_stride;
         g.a_bcast = r2;
-        g.D = (float*)((char*)dst->data + i3 * dst->nb[3]);
+        char* out_base = fz && fz->out ? (char*)fz->out : (char*)dst->data;
+        g.D = (float*)(out_base + i3 * dst->nb[3]);
         g.ldd = dst->nb[1] / 4;
         g.d_batch_stride = dst->nb[2] / 4;
+        if (fz && fz->bias) { g.bias = fz->bias; g.bias_mode = fz->bias_mode; }
         int n = launch_tc(ctx, g);
         if (n < 0) {
             // CUDA-core reference kernel (debug option, or shapes the TMA cannot describe)
@@ -286,6 +302,19 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst) {
             for (int64_t i2 = 0; i2 < ne12; ++i2) {
                 int r = b200_launch_gemm_ref(ctx->stream, (const char*)g.A + (i2 / r2) * a.batch_stride * es, ct, a.ld * es,
                                              (const char*)g.B + i2 * b.batch_stride * es, ct, b.ld * es, g.D + i2 * g.d_batch_stride, g.ldd, M, N, K);
+                if (r < 0) return -1;
+                n += r;
+            }
+            if (fz && fz->bias) {
+                b200_td o;
+                o.data = g.D; o.type = GGML_TYPE_F32;
+                o.ne[0] = M; o.ne[1] = N; o.ne[2] = ne12; o.ne[3] = 1;
+                o.nb[0] = 4; o.nb[1] = g.ldd * 4; o.nb[2] = g.d_batch_stride * 4; o.nb[3] = o.nb[2] * ne12;
+                b200_td bv = o;
+                bv.data = (void*)fz->bias;
+                bv.ne[0] = fz->bias_mode == 1 ? M : 1; bv.ne[1] = fz->bias_mode == 2 ? N : 1; bv.ne[2] = 1; bv.ne[3] = 1;
+                bv.nb[0] = 4; bv.nb[1] = 4; bv.nb[2] = bv.nb[3] = 4 * (fz->bias_mode == 1 ? M : N);
+                int r = b200_launch_binary(ctx->stream, B200_ADD, o, bv, o);
                 if (r < 0) return -1;
                 n += r;
             }
@@ -324,12 +353,25 @@ static int op_flash_attn(b200_context* ctx, ggml_tensor* dst) {
     vt.ne[0] = v->ne[1]; vt.nb[0] = v->nb[1];
     vt.ne[1] = v->ne[0]; vt.nb[1] = v->nb[0];
     void* vbuf = ws_alloc(ctx, (size_t)(Lk_pad * dv * Hkv * NB * es));
-    float* sbuf = (float*)ws_alloc(ctx, (size_t)(Lk * Lq * H * sizeof(float)));
-    void* pbuf = ws_alloc(ctx, (size_t)(Lk_pad * Lq * H * es));
-    if (!vbuf || !sbuf || !pbuf) return -1;
+    if (!vbuf) return -1;
     int n = b200_launch_pack_rows(ctx->stream, b200_make_td(&vt), vbuf, ct, Lk_pad);
     if (n < 0) return -1;
     launches += n;
+
+    // fused single-kernel path (tcgen05 QK^T and PV, online softmax between them): f16 K/V, d == dv, d % 8 == 0, d <= 192
+    if (ctx->opt_tc_gemm && ctx->opt_fused_attn && max_bias == 0.0f && ct == GGML_TYPE_F16 && k->type == GGML_TYPE_F16) {
+        b200_td mtd;
+        if (mask) mtd = b200_make_td(mask);
+        n = b200_launch_flash_attn_fused(ctx->stream, b200_make_td(q), b200_make_td(k), vbuf, Lk_pad, b200_make_td(v), mask ? &mtd : nullptr,
+                                         b200_make_td(dst), scale);
+        if (n > 0) {
+            ctx->stats.reserved[2] += (uint64_t)n;   // fused attention launches
+            return launches + n;
+        }
+    }
+    float* sbuf = (float*)ws_alloc(ctx, (size_t)(Lk * Lq * H * sizeof(float)));
+    void* pbuf = ws_alloc(ctx, (size_t)(Lk_pad * Lq * H * es));
+    if (!sbuf || !pbuf) return -1;
 
     for (int64_t i3 = 0; i3 < NB; ++i3) {
         // S[Lk, Lq, H] = K . Q^T
@@ -620,25 +662,220 @@ static inline bool node_is_noop(const ggml_tensor* t) {
            ggml_is_empty(t);
 }
 
-enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
-    B200_CUDA_CHECK(cudaSetDevice(ctx->device));
-    // the previous graph's device time is finalised here (the host has synchronised in between: it read the result)
-    if ((ctx->opt_timing && ctx->timing_pending) || !ctx->kt_pending.empty()) b200_context_finalize_timing(ctx);
-    ws_begin_graph(ctx);
-    const bool timing = ctx->opt_timing && !ctx->timing_pending;
-    if (timing) cudaEventRecord(ctx->ev_start, ctx->stream);
+// ------------------------------------------------------------------------------------------------
+// graph identity: sd.cpp rebuilds the ggml graph on EVERY model call (ggml_extend.hpp:3066-3069) but gallocr hands out
+// the same addresses for the same topology, so (ops, shapes, strides, params, addresses) identify a repeat exactly.
+// A repeat is replayed as one CUDA graph: ~1.5k kernel launches collapse into one cudaGraphLaunch.
+// ------------------------------------------------------------------------------------------------
+static inline uint64_t mix64(uint64_t h, uint64_t v) {
+    h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xff51afd7ed558ccdull;
+    return h ^ (h >> 32);
+}
 
+static uint64_t graph_key(const ggml_cgraph* g) {
+    uint64_t h = 0x1234567ull ^ (uint64_t)g->n_nodes;
+    for (int i = 0; i < g->n_nodes; ++i) {
+        const ggml_tensor* t = g->nodes[i];
+        h = mix64(h, ((uint64_t)t->op << 32) | ((uint64_t)t->type << 16) | (uint64_t)(t->flags & 0xffff));
+        h = mix64(h, (uint64_t)(uintptr_t)t->data);
+        for (int k = 0; k < 4; ++k) h = mix64(h, (uint64_t)t->ne[k] * 0x100000001b3ull + (uint64_t)t->nb[k]);
+        const uint64_t* op = (const uint64_t*)t->op_params;
+        for (size_t k = 0; k < sizeof(t->op_params) / 8; ++k) h = mix64(h, op[k]);
+        for (int sidx = 0; sidx < GGML_MAX_SRC; ++sidx) {
+            const ggml_tensor* sr = t->src[sidx];
+            if (!sr) break;
+            h = mix64(h, (uint64_t)(uintptr_t)sr->data ^ ((uint64_t)sr->type << 56));
+            h = mix64(h, (uint64_t)sr->ne[0] ^ ((uint64_t)sr->ne[1] << 20) ^ ((uint64_t)sr->ne[2] << 40) ^ ((uint64_t)sr->nb[1] << 8) ^ ((uint64_t)sr->nb[2] << 28));
+        }
+    }
+    return h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// peephole fusion.  The reference's block wrappers emit fixed little chains of nodes around every contraction /
+// normalisation (ggml_extend.hpp:1008-1040 Linear, :1131-1171 Conv2d, :1502-1520 GroupNorm, :3897-3945 LayerNorm,
+// block.hpp:142 "+ SiLU").  Each chain below is executed as ONE kernel when the intermediate tensors have no other
+// consumer in this graph; otherwise (or with option "fusion"=0) every node runs on its own, which is also what the
+// single-node graphs of test-backend-ops exercise.
+// ------------------------------------------------------------------------------------------------
+struct fusion_state {
+    std::unordered_map<const ggml_tensor*, int> uses;   // consumer count inside this graph
+    std::vector<char> done;                             // node already covered by an earlier fused launch
+};
+
+static void count_uses(const ggml_cgraph* g, fusion_state& fs) {
+    fs.uses.reserve((size_t)g->n_nodes * 2);
+    for (int i = 0; i < g->n_nodes; ++i)
+        for (int s = 0; s < GGML_MAX_SRC; ++s) {
+            const ggml_tensor* sr = g->nodes[i]->src[s];
+            if (!sr) break;
+            fs.uses[sr]++;
+        }
+    fs.done.assign((size_t)g->n_nodes, 0);
+}
+
+static inline bool single_use(const fusion_state& fs, const ggml_tensor* t) {
+    if (t->flags & GGML_TENSOR_FLAG_OUTPUT) return false;
+    auto it = fs.uses.find(t);
+    return it != fs.uses.end() && it->second == 1;
+}
+
+static inline bool is_f32_vec(const ggml_tensor* t, int64_t n) {
+    return t && t->type == GGML_TYPE_F32 && ggml_is_contiguous(t) && ggml_nelements(t) == n;
+}
+
+static inline bool is_view_op(const ggml_tensor* t) {
+    return t->op == GGML_OP_RESHAPE || t->op == GGML_OP_VIEW || t->op == GGML_OP_PERMUTE || t->op == GGML_OP_TRANSPOSE || t->op == GGML_OP_NONE;
+}
+
+// next node index > i that does work (views and covered nodes are skipped); -1 at the end
+static inline int next_node(const ggml_cgraph* g, const fusion_state& fs, int i) {
+    for (int j = i + 1; j < g->n_nodes; ++j)
+        if (!fs.done[j] && !is_view_op(g->nodes[j]) && !ggml_is_empty(g->nodes[j])) return j;
+    return -1;
+}
+
+// does `v` reach `root` through views that keep root's memory order (same base, contiguous, same element count) and that
+// nobody else consumes?  Then a kernel may produce `v`'s value by writing root's flat buffer.
+static bool order_preserving_view_of(const fusion_state& fs, const ggml_tensor* v, const ggml_tensor* root) {
+    for (int depth = 0; depth < 8; ++depth) {
+        if (v == root) return true;
+        if (!is_view_op(v) || v->op == GGML_OP_NONE || !v->src[0]) return false;
+        if (v->data != root->data || !ggml_is_contiguous(v) || ggml_nelements(v) != ggml_nelements(root)) return false;
+        if (!single_use(fs, v->src[0])) return false;
+        v = v->src[0];
+    }
+    return false;
+}
+
+// MUL_MAT [-> views] [-> CONT of an order-preserving view] [-> views] [-> ADD bias]
+static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
+    ggml_tensor* mm = g->nodes[i];
+    if (!ggml_is_contiguous(mm) || (mm->flags & GGML_TENSOR_FLAG_OUTPUT)) return -2;
+    std::vector<int> chain;
+    const ggml_tensor* cur = mm;    // tensor whose flat buffer holds the running value
+    int j = next_node(g, fs, i);
+    if (j >= 0) {
+        ggml_tensor* c = g->nodes[j];
+        if (c->op == GGML_OP_CONT && c->type == GGML_TYPE_F32 && ggml_is_contiguous(c) && (c->flags & GGML_TENSOR_FLAG_COMPUTE) &&
+            ggml_nelements(c) == ggml_nelements(mm) && c->src[0] != mm && order_preserving_view_of(fs, c->src[0], mm) && single_use(fs, c->src[0])) {
+            chain.push_back(j);
+            cur = c;
+            j = next_node(g, fs, j);
+        }
+    }
+    mm_fusion fz;
+    fz.out = (float*)cur->data;
+    const int64_t M = mm->ne[0], N = mm->ne[1];
+    if (j >= 0) {
+        ggml_tensor* add = g->nodes[j];
+        if (add->op == GGML_OP_ADD && (add->flags & GGML_TENSOR_FLAG_COMPUTE) && add->type == GGML_TYPE_F32 && ggml_is_contiguous(add) &&
+            ggml_nelements(add) == ggml_nelements(mm) && order_preserving_view_of(fs, add->src[0], cur) &&
+            (add->data == cur->data || single_use(fs, add->src[0])) && !(cur->flags & GGML_TENSOR_FLAG_OUTPUT)) {
+            const ggml_tensor* x = add->src[0];
+            const ggml_tensor* bv = add->src[1];
+            int mode = 0;
+            // Linear bias [M] on [M, ...]; conv bias [1,1,OC,1] on [W,H,OC,1] whose GEMM view is [M = W*H, N = OC]
+            if (is_f32_vec(bv, M) && bv->ne[0] == M && x->ne[0] == M) mode = 1;
+            else if (is_f32_vec(bv, N) && bv->ne[0] == 1 && bv->ne[1] == 1 && bv->ne[2] == N && x->ne[2] == N && x->ne[0] * x->ne[1] == M && x->ne[3] == 1 &&
+                     mm->ne[2] * mm->ne[3] == 1)
+                mode = 2;
+            if (mode) {
+                fz.bias = (const float*)bv->data;
+                fz.bias_mode = mode;
+                fz.out = (float*)add->data;
+                chain.push_back(j);
+            }
+        }
+    }
+    if (chain.empty()) return -2;
+    int n = op_mul_mat(ctx, mm, &fz);
+    if (n < 0) return n;
+    for (int c : chain) fs.done[c] = 1;
+    *covered = (int)chain.size();
+    return n;
+}
+
+// GROUP_NORM -> MUL w -> ADD b [-> SILU]     /     NORM -> MUL w -> ADD b
+static int try_fuse_norm(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
+    ggml_tensor* nrm = g->nodes[i];
+    const bool group = nrm->op == GGML_OP_GROUP_NORM;
+    if (nrm->type != GGML_TYPE_F32 || !ggml_is_contiguous(nrm) || !ggml_is_contiguous(nrm->src[0])) return -2;
+    const int64_t nvec = group ? nrm->ne[2] : nrm->ne[0];
+    int j = next_node(g, fs, i);
+    if (j < 0) return -2;
+    ggml_tensor* mul = g->nodes[j];
+    if (mul->op != GGML_OP_MUL || mul->src[0] != nrm || !(mul->data == nrm->data || single_use(fs, nrm)) || !is_f32_vec(mul->src[1], nvec)) return -2;
+    if (group ? !(mul->src[1]->ne[2] == nvec) : !(mul->src[1]->ne[0] == nvec)) return -2;
+    if (!ggml_is_contiguous(mul) || mul->type != GGML_TYPE_F32) return -2;
+    int k = next_node(g, fs, j);
+    if (k < 0) return -2;
+    ggml_tensor* add = g->nodes[k];
+    if (add->op != GGML_OP_ADD || add->src[0] != mul || !(add->data == mul->data || single_use(fs, mul)) || !is_f32_vec(add->src[1], nvec)) return -2;
+    if (group ? !(add->src[1]->ne[2] == nvec) : !(add->src[1]->ne[0] == nvec)) return -2;
+    if (!ggml_is_contiguous(add) || add->type != GGML_TYPE_F32) return -2;
+    if ((nrm->flags | mul->flags) & GGML_TENSOR_FLAG_OUTPUT) return -2;
+    ggml_tensor* last = add;
+    int act = 0, ncov = 2;
+    std::vector<int> chain = {j, k};
+    if (group) {
+        int u = next_node(g, fs, k);
+        if (u >= 0 && g->nodes[u]->op == GGML_OP_UNARY && ggml_get_unary_op(g->nodes[u]) == GGML_UNARY_OP_SILU && g->nodes[u]->src[0] == add &&
+            (g->nodes[u]->data == add->data || single_use(fs, add)) && !(add->flags & GGML_TENSOR_FLAG_OUTPUT) && ggml_is_contiguous(g->nodes[u]) &&
+            g->nodes[u]->type == GGML_TYPE_F32) {
+            last = g->nodes[u];
+            act = 1;
+            chain.push_back(u);
+            ncov = 3;
+        }
+    }
+    b200_td dst = b200_make_td(last);
+    int n;
+    if (group) {
+        float eps;
+        memcpy(&eps, (const float*)nrm->op_params + 1, 4);
+        n = b200_launch_group_norm(ctx->stream, b200_make_td(nrm->src[0]), dst, ggml_get_op_params_i32(nrm, 0), eps, (const float*)mul->src[1]->data,
+                                   (const float*)add->src[1]->data, act);
+    } else {
+        float eps;
+        memcpy(&eps, nrm->op_params, 4);
+        n = b200_launch_norm(ctx->stream, B200_NORM_LAYER, b200_make_td(nrm->src[0]), dst, eps, (const float*)mul->src[1]->data,
+                             (const float*)add->src[1]->data);
+    }
+    if (n < 0) return n;
+    for (int c : chain) fs.done[c] = 1;
+    *covered = ncov;
+    return n;
+}
+
+static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, uint64_t* launches, uint64_t* nodes) {
+    fusion_state fs;
+    const bool fuse = ctx->opt_fusion && cgraph->n_nodes > 1;
+    if (fuse) count_uses(cgraph, fs);
+    else fs.done.assign((size_t)cgraph->n_nodes, 0);
     for (int i = 0; i < cgraph->n_nodes; ++i) {
         ggml_tensor* t = cgraph->nodes[i];
+        if (fs.done[i]) continue;
         if (node_is_noop(t)) continue;
         if ((t->flags & GGML_TENSOR_FLAG_COMPUTE) == 0) continue;
-        int n = run_node(ctx, t);
+        int n = -2;
+        if (fuse) {
+            int covered = 0;
+            if (t->op == GGML_OP_MUL_MAT) n = try_fuse_mul_mat(ctx, cgraph, fs, i, &covered);
+            else if (t->op == GGML_OP_GROUP_NORM || t->op == GGML_OP_NORM) n = try_fuse_norm(ctx, cgraph, fs, i, &covered);
+            if (n >= 0) {
+                ctx->stats.fused_nodes += (uint64_t)covered;
+                *nodes += (uint64_t)covered;
+            }
+        }
+        if (n == -2) n = run_node(ctx, t);
         if (n < 0) {
             GGML_LOG_ERROR("ggml-b200: node %d (%s, %s) is not executable on this backend\n", i, ggml_op_name(t->op), t->name);
             return GGML_STATUS_FAILED;
         }
-        ctx->stats.kernel_launches += (uint64_t)n;
-        ctx->stats.nodes_executed++;
+        *launches += (uint64_t)n;
+        *nodes += 1;
 #ifdef B200_DEBUG_SYNC
         {
             cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -649,6 +886,89 @@ enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
         }
 #endif
     }
+    return GGML_STATUS_SUCCESS;
+}
+
+static void drop_cuda_graphs(b200_context* ctx) {
+    for (auto& kv : ctx->plans)
+        if (kv.second.exec) { cudaGraphExecDestroy(kv.second.exec); kv.second.exec = nullptr; }
+}
+
+enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
+    B200_CUDA_CHECK(cudaSetDevice(ctx->device));
+    // the previous graph's device time is finalised here (the host has synchronised in between: it read the result)
+    if ((ctx->opt_timing && ctx->timing_pending) || !ctx->kt_pending.empty()) b200_context_finalize_timing(ctx);
+    const size_t ws_chunks_before = ctx->ws.chunks.size();
+    ws_begin_graph(ctx);
+    if (ctx->ws.chunks.size() != ws_chunks_before) {      // workspace was re-allocated: captured graphs point at freed memory
+        drop_cuda_graphs(ctx);
+        ctx->ws_generation++;
+    }
+    const bool timing = ctx->opt_timing && !ctx->timing_pending;
+    const bool want_graphs = ctx->opt_cuda_graphs && !ctx->opt_kernel_timing && cgraph->n_nodes >= 16;
+    b200_context::plan* pl = nullptr;
+    if (want_graphs) {
+        const uint64_t key = graph_key(cgraph);
+        if (ctx->plans.size() > 64) { drop_cuda_graphs(ctx); ctx->plans.clear(); }
+        pl = &ctx->plans[key];
+    }
+    if (timing) cudaEventRecord(ctx->ev_start, ctx->stream);
+    enum ggml_status st = GGML_STATUS_SUCCESS;
+    uint64_t launches = 0, nodes = 0;
+
+    if (pl && pl->exec && pl->ws_generation == ctx->ws_generation) {
+        // ---- replay
+        cudaError_t e = cudaGraphLaunch(pl->exec, ctx->stream);
+        if (e != cudaSuccess) {
+            GGML_LOG_ERROR("ggml-b200: cudaGraphLaunch failed: %s\n", cudaGetErrorString(e));
+            return GGML_STATUS_FAILED;
+        }
+        launches = pl->launches;
+        nodes = pl->nodes;
+        ctx->stats.reserved[3]++;   // CUDA-graph replays
+    } else if (pl && pl->seen >= 1 && !pl->no_capture && ctx->ws.chunks.size() <= 1) {
+        // ---- second sighting: capture while executing nothing, then launch the instantiated graph
+        ctx->capture_overflow = false;
+        ctx->capturing = true;
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            st = execute_nodes(ctx, cgraph, &launches, &nodes);
+            e = cudaStreamEndCapture(ctx->stream, &graph);
+        }
+        ctx->capturing = false;
+        bool ok = e == cudaSuccess && st == GGML_STATUS_SUCCESS && graph && !ctx->capture_overflow;
+        if (ok) {
+            cudaGraphExec_t exec = nullptr;
+            e = cudaGraphInstantiate(&exec, graph, 0);
+            ok = e == cudaSuccess && exec;
+            if (ok) {
+                pl->exec = exec;
+                pl->launches = launches;
+                pl->nodes = nodes;
+                pl->ws_generation = ctx->ws_generation;
+                e = cudaGraphLaunch(exec, ctx->stream);
+                ok = e == cudaSuccess;
+            }
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (!ok) {
+            cudaGetLastError();
+            pl->no_capture = true;
+            if (pl->exec) { cudaGraphExecDestroy(pl->exec); pl->exec = nullptr; }
+            if (st != GGML_STATUS_SUCCESS) return st;
+            // fall back to eager execution of this call
+            ws_begin_graph(ctx);
+            launches = nodes = 0;
+            st = execute_nodes(ctx, cgraph, &launches, &nodes);
+        }
+    } else {
+        st = execute_nodes(ctx, cgraph, &launches, &nodes);
+        if (pl) pl->seen++;
+    }
+    if (st != GGML_STATUS_SUCCESS) return st;
+    ctx->stats.kernel_launches += launches;
+    ctx->stats.nodes_executed += nodes;
     if (timing) {
         cudaEventRecord(ctx->ev_stop, ctx->stream);
         ctx->timing_pending = true;

@@ -4,6 +4,7 @@
 #include "b200_common.h"
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 struct ggml_cgraph;
@@ -29,12 +30,18 @@ struct b200_context {
     bool opt_tc_gemm = true;
     bool opt_timing = true;
     bool opt_cuda_graphs = false;
+    bool opt_fused_attn = true;       // single-kernel FLASH_ATTN_EXT (0 = GEMM + softmax + GEMM through workspace)
     bool opt_kernel_timing = false;   // per-launch CUDA events around every tcgen05 GEMM (roofline pass only)
     bool timing_pending = false;
     struct kt_pair { cudaEvent_t start, stop; double flops; };
     std::vector<kt_pair> kt_pending;
     std::vector<cudaEvent_t> kt_free;
     double kt_us = 0, kt_flops = 0;
+    // repeated-graph cache (CUDA graph replay)
+    struct plan { cudaGraphExec_t exec = nullptr; int seen = 0; bool no_capture = false; uint64_t launches = 0, nodes = 0, ws_generation = 0; };
+    std::unordered_map<uint64_t, plan> plans;
+    uint64_t ws_generation = 0;
+    bool capturing = false, capture_overflow = false;
 
     ~b200_context();
 };

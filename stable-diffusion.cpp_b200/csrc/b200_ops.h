@@ -29,9 +29,12 @@ int b200_launch_sum_rows(cudaStream_t s, const b200_td& src, const b200_td& dst,
 int b200_launch_pack_rows(cudaStream_t s, const b200_td& src, void* dst, int dst_type, int64_t kpad);
 
 // ---- norm.cu ---------------------------------------------------------------------------------
-int b200_launch_group_norm(cudaStream_t s, const b200_td& src, const b200_td& dst, int n_groups, float eps);
+// optional fused affine (w, b: per-channel f32, may be null) and activation (0 none, 1 SiLU)
+int b200_launch_group_norm(cudaStream_t s, const b200_td& src, const b200_td& dst, int n_groups, float eps, const float* w = nullptr,
+                           const float* b = nullptr, int act = 0);
 enum b200_norm_kind { B200_NORM_LAYER = 0, B200_NORM_RMS = 1, B200_NORM_L2 = 2 };
-int b200_launch_norm(cudaStream_t s, int kind, const b200_td& src, const b200_td& dst, float eps);
+// optional fused affine (w, b: per-column f32 of length ne0, may be null)
+int b200_launch_norm(cudaStream_t s, int kind, const b200_td& src, const b200_td& dst, float eps, const float* w = nullptr, const float* b = nullptr);
 int b200_launch_soft_max(cudaStream_t s, const b200_td& src, const b200_td* mask, const b200_td& dst, float scale, float max_bias);
 
 // ---- im2col.cu -------------------------------------------------------------------------------
@@ -68,5 +71,6 @@ size_t b200_gemm_tc_workspace_bytes(const b200_device_info& dev, const b200_gemm
 // ---- attention.cu --------------------------------------------------------------------------------
 // ggml FLASH_ATTN_EXT: q f32 [d, Lq, H, N], k f16 [d, Lk, Hkv, N], v f16 [dv, Lk, Hkv, N], mask f16 [Lk, >=Lq, ...] or null,
 // dst f32 [dv, H, Lq, N]
-int b200_launch_flash_attn(cudaStream_t s, const b200_device_info& dev, const b200_td& q, const b200_td& k, const b200_td& v,
-                           const b200_td* mask, const b200_td& dst, float scale, float max_bias, float logit_softcap);
+// vt = packed V^T f16 [Lk_pad, dv, Hkv, N]; returns -1 when the shape is outside the fused kernel's envelope
+int b200_launch_flash_attn_fused(cudaStream_t s, const b200_td& q, const b200_td& k, const void* vt, int64_t Lk_pad, const b200_td& v,
+                                 const b200_td* mask, const b200_td& dst, float scale);

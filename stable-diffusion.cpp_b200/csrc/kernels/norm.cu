@@ -60,7 +60,8 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // ------------------------------------------------------------------------------------------
 template <bool IN_SMEM>
 __global__ void __launch_bounds__(1024) k_group_norm(const float* __restrict__ x, float* __restrict__ y, int64_t inner /*W*H*/,
-                                                     int C, int cpg, int n_groups, float eps) {
+                                                     int C, int cpg, int n_groups, float eps, const float* __restrict__ gw,
+                                                     const float* __restrict__ gb, int act) {
     extern __shared__ float sbuf[];
     __shared__ float red[32];
     int g = blockIdx.x, n = blockIdx.y;
@@ -93,6 +94,18 @@ __global__ void __launch_bounds__(1024) k_group_norm(const float* __restrict__ x
     }
     float var = block_sum(s2, red) / (float)len;
     float scale = 1.0f / sqrtf(var + eps);
+    if (gw != nullptr || act != 0) {
+        // fused epilogue of the reference's GroupNorm32 block: (x - mean) * rstd * w[c] + b[c], then SiLU
+        // (ggml_extend.hpp:1502-1520 + block.hpp:142: GROUP_NORM -> MUL -> ADD -> SILU as four graph nodes)
+        for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+            const int c = c0 + (int)(i / inner);
+            float v = ((IN_SMEM ? sbuf[i] : xp[i]) - mean) * scale;
+            if (gw) v = v * gw[c] + (gb ? gb[c] : 0.f);
+            if (act == 1) v = v / (1.0f + expf(-v));
+            yp[i] = v;
+        }
+        return;
+    }
     if (((uintptr_t)yp % 16 == 0) && (len % 4 == 0) && ((uintptr_t)xp % 16 == 0)) {
         for (int64_t i = threadIdx.x; i < len / 4; i += blockDim.x) {
             float4 v = IN_SMEM ? ((const float4*)sbuf)[i] : ((const float4*)xp)[i];
@@ -107,7 +120,7 @@ __global__ void __launch_bounds__(1024) k_group_norm(const float* __restrict__ x
 // row norms: one CTA per row (ne0 elements, arbitrary row placement, unit stride inside the row)
 // ------------------------------------------------------------------------------------------
 template <int KIND>
-__global__ void k_row_norm(b200_td a, b200_td d, float eps) {
+__global__ void k_row_norm(b200_td a, b200_td d, float eps, const float* __restrict__ rw, const float* __restrict__ rb) {
     __shared__ float red[32];
     int64_t row = blockIdx.x;
     int64_t i1 = row % a.ne[1], r = row / a.ne[1];
@@ -155,10 +168,18 @@ __global__ void k_row_norm(b200_td a, b200_td d, float eps) {
 #pragma unroll
         for (int k = 0; k < MAXR; ++k) {
             int64_t i = threadIdx.x + (int64_t)k * blockDim.x;
-            if (i < n) y[i] = (v[k] - mean) * scale;
+            if (i < n) {
+                float o = (v[k] - mean) * scale;
+                if (rw) o = o * rw[i] + (rb ? rb[i] : 0.f);
+                y[i] = o;
+            }
         }
     } else {
-        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) y[i] = (x[i] - mean) * scale;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+            float o = (x[i] - mean) * scale;
+            if (rw) o = o * rw[i] + (rb ? rb[i] : 0.f);
+            y[i] = o;
+        }
     }
 }
 
@@ -202,7 +223,7 @@ __global__ void k_soft_max(b200_td a, b200_td m, b200_td d, bool has_mask, float
 
 }  // namespace
 
-int b200_launch_group_norm(cudaStream_t s, const b200_td& src, const b200_td& dst, int n_groups, float eps) {
+int b200_launch_group_norm(cudaStream_t s, const b200_td& src, const b200_td& dst, int n_groups, float eps, const float* w, const float* b, int act) {
     int64_t inner = src.ne[0] * src.ne[1];
     int C = (int)src.ne[2];
     int N = (int)src.ne[3];
@@ -219,22 +240,22 @@ int b200_launch_group_norm(cudaStream_t s, const b200_td& src, const b200_td& ds
             cudaFuncSetAttribute(k_group_norm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             attr_set[dev] = true;
         }
-        k_group_norm<true><<<grid, threads, bytes, s>>>((const float*)src.data, (float*)dst.data, inner, C, cpg, n_groups, eps);
+        k_group_norm<true><<<grid, threads, bytes, s>>>((const float*)src.data, (float*)dst.data, inner, C, cpg, n_groups, eps, w, b, act);
     } else {
-        k_group_norm<false><<<grid, 1024, 0, s>>>((const float*)src.data, (float*)dst.data, inner, C, cpg, n_groups, eps);
+        k_group_norm<false><<<grid, 1024, 0, s>>>((const float*)src.data, (float*)dst.data, inner, C, cpg, n_groups, eps, w, b, act);
     }
     return 1;
 }
 
-int b200_launch_norm(cudaStream_t s, int kind, const b200_td& src, const b200_td& dst, float eps) {
+int b200_launch_norm(cudaStream_t s, int kind, const b200_td& src, const b200_td& dst, float eps, const float* w, const float* b) {
     int64_t nrows = src.ne[1] * src.ne[2] * src.ne[3];
     if (nrows == 0 || src.ne[0] == 0) return 0;
     int threads = src.ne[0] >= 4096 ? 1024 : (src.ne[0] >= 1024 ? 256 : 128);
     if (nrows > 0x7fffffff) return -1;
     switch (kind) {
-        case B200_NORM_LAYER: k_row_norm<B200_NORM_LAYER><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps); break;
-        case B200_NORM_RMS: k_row_norm<B200_NORM_RMS><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps); break;
-        default: k_row_norm<B200_NORM_L2><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps); break;
+        case B200_NORM_LAYER: k_row_norm<B200_NORM_LAYER><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps, w, b); break;
+        case B200_NORM_RMS: k_row_norm<B200_NORM_RMS><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps, w, b); break;
+        default: k_row_norm<B200_NORM_L2><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps, w, b); break;
     }
     return 1;
 }
