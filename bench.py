@@ -104,7 +104,8 @@ def run_reference(args):
     from oracle.cpu_ref import load_cpu_oracle   # allowed here: this arm times the oracle itself
     h = Harness()
     variant = load_cpu_oracle(h)
-    cores = os.cpu_count() or 1
+    from oracle.cpu_ref import best_thread_count, usable_cores
+    cores = best_thread_count(h)          # fastest ggml thread count on this host (128 logical CPUs may sit behind a much smaller quota)
     m = h.model("CPU", "sd15_unet", "f16", 0, 1234, cores)   # non-FA graph: the reference's default, and its fastest CPU path
     x, cond, uncond = inputs(h, 0)
     budget_s = float(os.environ.get("SDB200_REF_BUDGET_S", "150"))
@@ -256,9 +257,9 @@ def run_b200(args):
 
 def cpu_baseline_leg(h):
     """Bounded CPU sample: ONE full CFG denoise step (2 UNet forwards) on the reference CPU backend, all host threads."""
-    from oracle.cpu_ref import load_cpu_oracle
+    from oracle.cpu_ref import load_cpu_oracle, best_thread_count
     variant = load_cpu_oracle(h)
-    cores = os.cpu_count() or 1
+    cores = best_thread_count(h)
     m = h.model("CPU", "sd15_unet", "f16", 0, 1234, cores)
     x, cond, uncond = inputs(h, 0)
     t0 = time.time()

@@ -20,6 +20,7 @@
 #include <memory>
 #include <string>
 #include <thread>
+#include <sched.h>
 #include <vector>
 
 #include "ggml-backend.h"
@@ -260,7 +261,27 @@ String2TensorStorage make_storage_map(const std::map<std::string, ggml_tensor*>&
     return m;
 }
 
+// default CPU thread count: affinity mask and cgroup quota aware, capped at 16 (a ggml thread pool larger than the
+// cores the container may really use spins itself ~30x slower; callers that want the maximum pass n_threads explicitly)
+int default_cpu_threads() {
+    if (const char* e = getenv("SDH_CPU_THREADS")) {
+        int v = atoi(e);
+        if (v > 0) return v;
+    }
+    int n = (int)std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = std::min(n, CPU_COUNT(&set));
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char q[64];
+        long period = 0;
+        if (fscanf(f, "%63s %ld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) n = std::min(n, std::max(1, (int)(atol(q) / period)));
+        fclose(f);
+    }
+    return std::max(1, std::min(n, 16));
+}
+
 ggml_backend_t init_device(const std::string& device, int n_threads) {
+    if (n_threads <= 0) n_threads = default_cpu_threads();
     ggml_backend_dev_t dev = ggml_backend_dev_by_name(device.c_str());
     if (!dev) return nullptr;
     ggml_backend_t be = ggml_backend_dev_init(dev, nullptr);
@@ -297,7 +318,7 @@ sdh_model* sdh_model_create(const char* device, const char* arch, const char* wt
     ggml_type wtype = parse_wtype(wtype_s);
     auto m = std::make_unique<sdh_model>();
     m->device    = device ? device : "CPU";
-    m->n_threads = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    m->n_threads = n_threads > 0 ? n_threads : default_cpu_threads();
     m->backend   = init_device(m->device, m->n_threads);
     if (!m->backend) { fail("no such device: " + m->device); return nullptr; }
     m->weights = std::make_shared<SyntheticWeights>();
@@ -628,7 +649,7 @@ static ggml_cgraph* build_only(sdh_model* m, const sd::Tensor<float>& x, const s
 extern "C" int sdh_run_op(const char* device, const char* op_s, int n_in, const sdh_tensor* in, const int32_t* itypes, const int32_t* ip,
                           const float* fp, sdh_tensor* out, int n_threads) {
     std::string op = op_s ? op_s : "";
-    ggml_backend_t be = init_device(device ? device : "CPU", n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency());
+    ggml_backend_t be = init_device(device ? device : "CPU", n_threads);
     if (!be) return fail(std::string("no such device: ") + (device ? device : "null"));
     ggml_init_params ip0 = {ggml_tensor_overhead() * 256 + ggml_graph_overhead(), nullptr, true};
     ggml_context* ctx = ggml_init(ip0);
