@@ -44,6 +44,7 @@ b200_context* b200_context_create(const b200_device_info& info) {
     ctx->opt_timing = env_flag("GGML_B200_TIMING", 1) != 0;
     ctx->opt_cuda_graphs = env_flag("GGML_B200_CUDA_GRAPHS", 0) != 0;
     ctx->opt_fused_attn = env_flag("GGML_B200_FUSED_ATTN", 1) != 0;
+    ctx->opt_implicit_conv = env_flag("GGML_B200_IMPLICIT_CONV", 1) != 0;
     return ctx;
 }
 
@@ -67,6 +68,7 @@ int b200_context_set_option(b200_context* ctx, const char* key, int value) {
     else if (!strcmp(key, "cuda_graphs")) ctx->opt_cuda_graphs = value != 0;
     else if (!strcmp(key, "kernel_timing")) ctx->opt_kernel_timing = value != 0;
     else if (!strcmp(key, "fused_attn")) ctx->opt_fused_attn = value != 0;
+    else if (!strcmp(key, "implicit_conv")) ctx->opt_implicit_conv = value != 0;
     else return -1;
     return 0;
 }
@@ -86,10 +88,6 @@ void b200_context_finalize_timing(b200_context* ctx) {
         cudaGetLastError();
     }
     ctx->timing_pending = false;
-}
-
-void b200_invalidate_address_range(int, const void*, size_t) {
-    // derived-layout caches (packed weights) are introduced together with the fused conv path; nothing cached yet
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -797,6 +795,167 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
     return n;
 }
 
+// ------------------------------------------------------------------------------------------------
+// implicit-GEMM convolution.  The reference lowers Conv2d to IM2COL(F16) -> MUL_MAT -> RESHAPE -> PERMUTE -> CONT -> ADD bias
+// (ggml.c:4732-4753, ggml_extend.hpp:1131-1171).  When the shape fits the TMA halo-tile scheme the whole chain runs as
+//   [GroupNorm statistics] -> NCHW f32 -> NHWC f16 transform (norm, affine, SiLU, nearest x2 folded in) -> tcgen05 conv GEMM
+// and the im2col matrix is never materialised.  Filters are repacked once per weight tensor ([OC][KH][KW][IC]) and cached
+// by device address; any host write into the weight buffer drops the cached copy (b200_invalidate_address_range).
+// ------------------------------------------------------------------------------------------------
+struct packed_weight { void* ptr; size_t src_bytes; int device; };
+static std::mutex g_pw_mutex;
+static std::unordered_map<const void*, packed_weight> g_packed_weights;
+
+void b200_invalidate_address_range(int device, const void* ptr, size_t size) {
+    std::lock_guard<std::mutex> lock(g_pw_mutex);
+    if (g_packed_weights.empty()) return;
+    const char* lo = (const char*)ptr;
+    const char* hi = lo + size;
+    for (auto it = g_packed_weights.begin(); it != g_packed_weights.end();) {
+        const char* a = (const char*)it->first;
+        if (it->second.device == device && a < hi && a + it->second.src_bytes > lo) {
+            cudaFree(it->second.ptr);   // implicit device synchronisation: no kernel can still be reading it
+            it = g_packed_weights.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
+
+static const void* get_packed_conv_weight(b200_context* ctx, const ggml_tensor* w, int* launches) {
+    std::lock_guard<std::mutex> lock(g_pw_mutex);
+    auto it = g_packed_weights.find(w->data);
+    if (it != g_packed_weights.end() && it->second.device == ctx->device && it->second.src_bytes == ggml_nbytes(w)) return it->second.ptr;
+    if (ctx->capturing) { ctx->capture_overflow = true; return nullptr; }
+    void* p = nullptr;
+    if (cudaMalloc(&p, ggml_nbytes(w)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    int n = b200_launch_pack_conv_weight(ctx->stream, w->data, p, (int)w->ne[0], (int)w->ne[1], w->ne[2], w->ne[3]);
+    if (n < 0) { cudaFree(p); return nullptr; }
+    *launches += n;
+    g_packed_weights[w->data] = packed_weight{p, ggml_nbytes(w), ctx->device};
+    return p;
+}
+
+struct conv_match {
+    int i_im2col = -1, i_mm = -1;
+    std::vector<int> chain;          // nodes covered besides the starting one
+    const ggml_tensor* x = nullptr;  // image [W,H,IC,N] f32
+    const ggml_tensor* w = nullptr;  // filter [KW,KH,IC,OC] f16
+    float* out = nullptr;
+    const float* bias = nullptr;
+    int64_t OW = 0, OH = 0;
+    int dil = 1;
+};
+
+// does node i (IM2COL) start a conv chain the implicit-GEMM kernel can run?  `up` = 2 when the caller feeds the image through
+// a folded nearest-x2 upsample (then x is the LOW-resolution tensor and im2col->src[1] is the UPSCALE node)
+static bool match_conv(const ggml_cgraph* g, const fusion_state& fs, int i, conv_match* m) {
+    const ggml_tensor* im = g->nodes[i];
+    if (im->op != GGML_OP_IM2COL || im->type != GGML_TYPE_F16 || !(im->flags & GGML_TENSOR_FLAG_COMPUTE)) return false;
+    const int32_t* p = im->op_params;
+    if (p[6] != 1) return false;
+    const ggml_tensor* w = im->src[0];
+    const ggml_tensor* x = im->src[1];
+    if (w->type != GGML_TYPE_F16 || !ggml_is_contiguous(w) || x->type != GGML_TYPE_F32 || !ggml_is_contiguous(x)) return false;
+    const int64_t IC = x->ne[2], N = x->ne[3], OC = w->ne[3];
+    if (w->ne[2] != IC || N != 1) return false;
+    const int64_t OW = im->ne[1], OH = im->ne[2];
+    if (OW != x->ne[0] || OH != x->ne[1]) return false;
+    if (!b200_conv_tc_supported(N, OH, OW, IC, OC, (int)w->ne[1], (int)w->ne[0], p[0], p[1], p[2], p[3], p[4], p[5])) return false;
+    if (!single_use(fs, im)) return false;
+    int j = next_node(g, fs, i);
+    if (j < 0) return false;
+    const ggml_tensor* mm = g->nodes[j];
+    if (mm->op != GGML_OP_MUL_MAT || !(mm->flags & GGML_TENSOR_FLAG_COMPUTE) || (mm->flags & GGML_TENSOR_FLAG_OUTPUT)) return false;
+    if (!order_preserving_view_of(fs, mm->src[0], im)) return false;
+    if (mm->src[0] != im && !single_use(fs, mm->src[0])) return false;
+    const ggml_tensor* wv = mm->src[1];
+    if (wv->data != w->data || wv->type != GGML_TYPE_F16 || !ggml_is_contiguous(wv) || ggml_nelements(wv) != ggml_nelements(w)) return false;
+    if (mm->ne[0] != OW * OH * N || mm->ne[1] != OC || mm->ne[2] * mm->ne[3] != 1) return false;
+    m->i_im2col = i; m->i_mm = j;
+    m->chain.push_back(j);
+    m->x = x; m->w = w; m->OW = OW; m->OH = OH; m->dil = p[4];
+    const ggml_tensor* cur = mm;
+    m->out = (float*)mm->data;
+    int k = next_node(g, fs, j);
+    if (k >= 0) {
+        const ggml_tensor* c = g->nodes[k];
+        if (c->op == GGML_OP_CONT && c->type == GGML_TYPE_F32 && ggml_is_contiguous(c) && (c->flags & GGML_TENSOR_FLAG_COMPUTE) &&
+            ggml_nelements(c) == ggml_nelements(mm) && c->src[0] != mm && order_preserving_view_of(fs, c->src[0], mm) && single_use(fs, c->src[0])) {
+            m->chain.push_back(k);
+            cur = c;
+            m->out = (float*)c->data;
+            k = next_node(g, fs, k);
+        }
+    }
+    if (k >= 0) {
+        const ggml_tensor* add = g->nodes[k];
+        if (add->op == GGML_OP_ADD && (add->flags & GGML_TENSOR_FLAG_COMPUTE) && add->type == GGML_TYPE_F32 && ggml_is_contiguous(add) &&
+            ggml_nelements(add) == ggml_nelements(mm) && order_preserving_view_of(fs, add->src[0], cur) &&
+            (add->data == cur->data || single_use(fs, add->src[0])) && !(cur->flags & GGML_TENSOR_FLAG_OUTPUT)) {
+            const ggml_tensor* bv = add->src[1];
+            if (is_f32_vec(bv, OC) && bv->ne[0] == 1 && bv->ne[1] == 1 && bv->ne[2] == OC && add->src[0]->ne[2] == OC) {
+                m->bias = (const float*)bv->data;
+                m->out = (float*)add->data;
+                m->chain.push_back(k);
+            }
+        }
+    }
+    return true;
+}
+
+struct conv_prologue {
+    const ggml_tensor* src = nullptr;   // tensor actually read (f32 NCHW); equals match.x unless a producer chain was folded in
+    int up = 1;
+    bool norm = false;
+    int n_groups = 0;
+    float eps = 0.f;
+    const float* gw = nullptr;
+    const float* gb = nullptr;
+    int act = 0;
+};
+
+static int emit_conv(b200_context* ctx, const conv_match& m, const conv_prologue& pro) {
+    int launches = 0;
+    const ggml_tensor* src = pro.src;
+    const int64_t C = src->ne[2], N = src->ne[3], H = src->ne[1], W = src->ne[0];
+    const void* wp = get_packed_conv_weight(ctx, m.w, &launches);
+    if (!wp) return -1;
+    void* shadow = ws_alloc(ctx, (size_t)(N * m.OH * m.OW * C * 2));
+    if (!shadow) return -1;
+    float* stats = nullptr;
+    if (pro.norm) {
+        stats = (float*)ws_alloc(ctx, (size_t)(N * pro.n_groups * 2 * sizeof(float)));
+        if (!stats) return -1;
+        launches += b200_launch_gn_stats(ctx->stream, (const float*)src->data, stats, N, C, H * W, pro.n_groups, pro.eps);
+    }
+    int n = b200_launch_to_nhwc_f16(ctx->stream, (const float*)src->data, shadow, N, C, H, W, pro.up, stats, pro.n_groups, pro.gw, pro.gb, pro.act);
+    if (n < 0) return -1;
+    launches += n;
+    b200_conv_args c;
+    memset(&c, 0, sizeof(c));
+    c.x_nhwc = shadow; c.w_packed = wp;
+    c.N = N; c.H = m.OH; c.W = m.OW; c.C = C; c.OC = m.w->ne[3];
+    c.KH = (int)m.w->ne[1]; c.KW = (int)m.w->ne[0];
+    c.dil = m.dil; c.pad = c.dil * (c.KH - 1) / 2;
+    c.D = m.out; c.bias = m.bias;
+    size_t wsb = b200_conv_tc_workspace_bytes(ctx->info, c);
+    void* w = wsb ? ws_alloc(ctx, wsb) : nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->opt_kernel_timing) { e0 = kt_event(ctx); e1 = kt_event(ctx); cudaEventRecord(e0, ctx->stream); }
+    n = b200_launch_conv_tc(ctx->stream, ctx->info, c, w, w ? wsb : 0);
+    if (ctx->opt_kernel_timing) {
+        if (n > 0) {
+            cudaEventRecord(e1, ctx->stream);
+            ctx->kt_pending.push_back({e0, e1, 2.0 * (double)(c.H * c.W) * (double)c.OC * (double)(c.KH * c.KW * c.C) * (double)c.N});
+        } else { ctx->kt_free.push_back(e0); ctx->kt_free.push_back(e1); }
+    }
+    if (n < 0) return -1;
+    ctx->stats.tc_gemm_launches += (uint64_t)n;
+    ctx->stats.reserved[4] += 1;   // implicit-GEMM convolutions
+    return launches + n;
+}
+
 // GROUP_NORM -> MUL w -> ADD b [-> SILU]     /     NORM -> MUL w -> ADD b
 static int try_fuse_norm(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
     ggml_tensor* nrm = g->nodes[i];
@@ -830,8 +989,32 @@ static int try_fuse_norm(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, in
             ncov = 3;
         }
     }
-    b200_td dst = b200_make_td(last);
     int n;
+    if (group && ctx->opt_tc_gemm && ctx->opt_implicit_conv && single_use(fs, last) && !(last->flags & GGML_TENSOR_FLAG_OUTPUT)) {
+        // ... -> IM2COL -> MUL_MAT ...: the normalised activation is only ever read by a convolution: never materialise it
+        int ic = next_node(g, fs, chain.back());
+        conv_match cm;
+        if (ic >= 0 && g->nodes[ic]->op == GGML_OP_IM2COL && g->nodes[ic]->src[1] == last && match_conv(g, fs, ic, &cm)) {
+            conv_prologue pro;
+            pro.src = nrm->src[0];
+            pro.norm = true;
+            pro.n_groups = ggml_get_op_params_i32(nrm, 0);
+            memcpy(&pro.eps, (const float*)nrm->op_params + 1, 4);
+            pro.gw = (const float*)mul->src[1]->data;
+            pro.gb = (const float*)add->src[1]->data;
+            pro.act = act;
+            n = emit_conv(ctx, cm, pro);
+            if (n >= 0) {
+                for (int c : chain) fs.done[c] = 1;
+                fs.done[ic] = 1;
+                for (int c : cm.chain) fs.done[c] = 1;
+                *covered = ncov + 1 + (int)cm.chain.size();
+                return n;
+            }
+            if (ctx->capture_overflow) return -1;
+        }
+    }
+    b200_td dst = b200_make_td(last);
     if (group) {
         float eps;
         memcpy(&eps, (const float*)nrm->op_params + 1, 4);
@@ -846,6 +1029,36 @@ static int try_fuse_norm(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, in
     if (n < 0) return n;
     for (int c : chain) fs.done[c] = 1;
     *covered = ncov;
+    return n;
+}
+
+// IM2COL -> ...   or   UPSCALE(nearest x2) -> IM2COL -> ...
+static int try_fuse_conv(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
+    ggml_tensor* t = g->nodes[i];
+    conv_match cm;
+    conv_prologue pro;
+    int extra = 0;
+    int ic = i;
+    if (t->op == GGML_OP_UPSCALE) {
+        const int mode = ggml_get_op_params_i32(t, 0);
+        if ((mode & 0xFF) != GGML_SCALE_MODE_NEAREST || (mode & ~0xFF)) return -2;
+        const ggml_tensor* lo = t->src[0];
+        if (lo->type != GGML_TYPE_F32 || !ggml_is_contiguous(lo) || !ggml_is_contiguous(t)) return -2;
+        if (t->ne[0] != 2 * lo->ne[0] || t->ne[1] != 2 * lo->ne[1] || t->ne[2] != lo->ne[2] || t->ne[3] != lo->ne[3]) return -2;
+        if (!single_use(fs, t)) return -2;
+        ic = next_node(g, fs, i);
+        if (ic < 0 || g->nodes[ic]->op != GGML_OP_IM2COL || g->nodes[ic]->src[1] != t) return -2;
+        pro.src = lo;
+        pro.up = 2;
+        extra = 1;
+    }
+    if (!match_conv(g, fs, ic, &cm)) return -2;
+    if (!pro.src) pro.src = cm.x;
+    int n = emit_conv(ctx, cm, pro);
+    if (n < 0) return ctx->capture_overflow ? -1 : -2;
+    if (extra) fs.done[ic] = 1;
+    for (int c : cm.chain) fs.done[c] = 1;
+    *covered = extra + (int)cm.chain.size();
     return n;
 }
 
@@ -864,6 +1077,7 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
             int covered = 0;
             if (t->op == GGML_OP_MUL_MAT) n = try_fuse_mul_mat(ctx, cgraph, fs, i, &covered);
             else if (t->op == GGML_OP_GROUP_NORM || t->op == GGML_OP_NORM) n = try_fuse_norm(ctx, cgraph, fs, i, &covered);
+            else if ((t->op == GGML_OP_IM2COL || t->op == GGML_OP_UPSCALE) && ctx->opt_tc_gemm && ctx->opt_implicit_conv) n = try_fuse_conv(ctx, cgraph, fs, i, &covered);
             if (n >= 0) {
                 ctx->stats.fused_nodes += (uint64_t)covered;
                 *nodes += (uint64_t)covered;

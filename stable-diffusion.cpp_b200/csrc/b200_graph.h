@@ -31,6 +31,7 @@ struct b200_context {
     bool opt_timing = true;
     bool opt_cuda_graphs = false;
     bool opt_fused_attn = true;       // single-kernel FLASH_ATTN_EXT (0 = GEMM + softmax + GEMM through workspace)
+    bool opt_implicit_conv = true;    // IM2COL+MUL_MAT chains as TMA halo-tile implicit GEMM (0 = materialised im2col)
     bool opt_kernel_timing = false;   // per-launch CUDA events around every tcgen05 GEMM (roofline pass only)
     bool timing_pending = false;
     struct kt_pair { cudaEvent_t start, stop; double flops; };

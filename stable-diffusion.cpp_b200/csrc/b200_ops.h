@@ -68,6 +68,26 @@ struct b200_gemm_args {
 int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g, void* workspace, size_t workspace_bytes);
 size_t b200_gemm_tc_workspace_bytes(const b200_device_info& dev, const b200_gemm_args& g);
 
+// ---- implicit-GEMM convolution (gemm_tc.cu conv mode + conv_prep.cu operand producers) ------------------------
+struct b200_conv_args {
+    const void* x_nhwc;     // f16 [N][H][W][C]   (produced by b200_launch_to_nhwc_f16)
+    const void* w_packed;   // f16 [OC][KH][KW][C] (produced by b200_launch_pack_conv_weight)
+    int64_t N, H, W, C, OC;
+    int KH, KW, pad, dil;
+    float* D;               // f32 [N][OC][H][W] == ggml [W,H,OC,N]
+    const float* bias;      // per OC or null
+    const float* residual;  // same layout as D or null
+};
+bool b200_conv_tc_supported(int64_t N, int64_t H, int64_t W, int64_t C, int64_t OC, int KH, int KW, int s0, int s1, int p0, int p1, int d0, int d1);
+size_t b200_conv_tc_workspace_bytes(const b200_device_info& dev, const b200_conv_args& c);
+int b200_launch_conv_tc(cudaStream_t s, const b200_device_info& dev, const b200_conv_args& c, void* workspace, size_t workspace_bytes);
+// stats: float2 {mean, rstd} per (image, group)
+int b200_launch_gn_stats(cudaStream_t s, const float* x, float* stats, int64_t N, int64_t C, int64_t inner, int n_groups, float eps);
+// NCHW f32 -> NHWC f16 with optional GroupNorm (stats + per-channel w, b), SiLU (act = 1) and nearest upsampling (up = 1 | 2)
+int b200_launch_to_nhwc_f16(cudaStream_t s, const float* x, void* out, int64_t N, int64_t C, int64_t H, int64_t W, int up, const float* stats,
+                            int n_groups, const float* gw, const float* gb, int act);
+int b200_launch_pack_conv_weight(cudaStream_t s, const void* w, void* out, int KW, int KH, int64_t IC, int64_t OC);
+
 // ---- attention.cu --------------------------------------------------------------------------------
 // ggml FLASH_ATTN_EXT: q f32 [d, Lq, H, N], k f16 [d, Lk, Hkv, N], v f16 [dv, Lk, Hkv, N], mask f16 [Lk, >=Lq, ...] or null,
 // dst f32 [dv, H, Lq, N]

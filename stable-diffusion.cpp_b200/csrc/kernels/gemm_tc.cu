@@ -49,6 +49,13 @@ struct GemmKParams {
     int act;           // 0 none, 1 silu, 2 gelu(tanh)
     float* ws_partial; // [tile][split][BN][BM]
     unsigned* ws_counters;
+    // implicit-GEMM convolution (conv != 0): A is an NHWC f16 image read through a 4-D map (C, W, H, N) with halo boxes;
+    // k-block kb -> filter tap kb / cblocks and 64-channel block kb % cblocks; rows of the tile are output pixels
+    int conv;
+    int conv_W;        // output width (== input width: stride 1, "same" padding)
+    int conv_KW;       // filter width (taps = KH * KW)
+    int conv_cblocks;  // IC / 64
+    int conv_pad, conv_dil;
 };
 
 template <int BN> struct Cfg {
@@ -121,8 +128,19 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
                 uint8_t* sa = smem + s * C::STAGE_BYTES;
                 uint8_t* sb = sa + A_STAGE_BYTES;
                 const int k = (kb0 + i) * BK;
-                tma_load_4d(sa, &tmA, &full_bar[s], k, m0, i2 / p.r2, i3 / p.r3);
-                tma_load_4d(sb, &tmB, &full_bar[s], k, n0, i2, i3);
+                if (p.conv) {
+                    const int kb = kb0 + i;
+                    const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
+                    const int kh = tap / p.conv_KW, kw = tap - kh * p.conv_KW;
+                    const int y0 = m0 / p.conv_W, x0 = m0 - y0 * p.conv_W;
+                    // the box {64 ch, BW, BH} lands as 128 rows of 128 bytes: row = by * BW + bx == pixel m0 + row; out-of-image
+                    // (halo / tail) coordinates are zero-filled by the TMA unit, which is exactly the conv's zero padding
+                    tma_load_4d(sa, &tmA, &full_bar[s], cb * 64, x0 + kw * p.conv_dil - p.conv_pad, y0 + kh * p.conv_dil - p.conv_pad, i2);
+                    tma_load_4d(sb, &tmB, &full_bar[s], k, n0, 0, 0);
+                } else {
+                    tma_load_4d(sa, &tmA, &full_bar[s], k, m0, i2 / p.r2, i3 / p.r3);
+                    tma_load_4d(sb, &tmB, &full_bar[s], k, n0, i2, i3);
+                }
             }
         }
     } else if (warp == 1) {
@@ -413,6 +431,85 @@ int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_
 #undef LAUNCH
     if (e != cudaSuccess) {
         fprintf(stderr, "[ggml-b200] tcgen05 GEMM launch failed: %s\n", cudaGetErrorString(e));
+        return -1;
+    }
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// implicit-GEMM convolution front end (stride 1, "same" padding, IC % 64 == 0, W | 128 or 128 | W)
+// ------------------------------------------------------------------------------------------------
+bool b200_conv_tc_supported(int64_t N, int64_t H, int64_t W, int64_t C, int64_t OC, int KH, int KW, int s0, int s1, int p0, int p1, int d0, int d1) {
+    if (s0 != 1 || s1 != 1 || d0 != d1 || p0 != p1) return false;
+    if (KH != KW || (KH != 1 && KH != 3)) return false;
+    if (p0 != d0 * (KH - 1) / 2) return false;             // output size == input size
+    if (C % 64 != 0 || C <= 0 || OC <= 0) return false;
+    if (!((W <= 128 && 128 % W == 0) || (W % 128 == 0))) return false;
+    if (N > 65535 || H * W > 0x7fffffff) return false;
+    return true;
+}
+
+size_t b200_conv_tc_workspace_bytes(const b200_device_info& dev, const b200_conv_args& c) {
+    b200_gemm_args g;
+    memset(&g, 0, sizeof(g));
+    g.type = GGML_TYPE_F16; g.M = c.H * c.W; g.N = c.OC; g.K = (int64_t)c.KH * c.KW * c.C; g.batch = c.N; g.a_bcast = 1;
+    return b200_gemm_tc_workspace_bytes(dev, g);
+}
+
+int b200_launch_conv_tc(cudaStream_t s, const b200_device_info& dev, const b200_conv_args& c, void* workspace, size_t workspace_bytes) {
+    if (!b200_conv_tc_supported(c.N, c.H, c.W, c.C, c.OC, c.KH, c.KW, 1, 1, c.pad, c.pad, c.dil, c.dil)) return -1;
+    if (((uintptr_t)c.x_nhwc & 15) || ((uintptr_t)c.w_packed & 15)) return -1;
+    b200_gemm_args g;
+    memset(&g, 0, sizeof(g));
+    g.type = GGML_TYPE_F16; g.M = c.H * c.W; g.N = c.OC; g.K = (int64_t)c.KH * c.KW * c.C; g.batch = c.N; g.a_bcast = 1;
+    const int nkb = (int)(g.K / 64);
+    Plan pl = choose_plan(dev, g, nkb);
+
+    // A: NHWC image, 4-D (C, W, H, N); box = 64 channels x BW x BH pixels with BW * BH == 128
+    const uint32_t BW = (uint32_t)(c.W < 128 ? c.W : 128), BH = 128 / BW;
+    CUtensorMap ta, tb;
+    {
+        auto enc = b200_get_tensormap_encoder();
+        if (!enc) return -1;
+        cuuint64_t dims[4] = {(cuuint64_t)c.C, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.N};
+        cuuint64_t strides[3] = {(cuuint64_t)c.C * 2, (cuuint64_t)c.W * c.C * 2, (cuuint64_t)c.H * c.W * c.C * 2};
+        cuuint32_t box[4] = {64, BW, BH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (enc(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(c.x_nhwc), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return -1;
+    }
+    if (!make_operand_map(&tb, c.w_packed, GGML_TYPE_F16, g.K, c.OC, g.K, 1, 0, 1, 0, (uint32_t)pl.bn)) return -1;
+
+    GemmKParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.D = c.D; kp.ldd = c.H * c.W; kp.d_batch_stride = c.OC * c.H * c.W;
+    kp.M = g.M; kp.N = g.N;
+    kp.num_k_blocks = nkb;
+    kp.splits = pl.splits;
+    kp.ne12 = (int)c.N; kp.r2 = 1; kp.r3 = 1;
+    kp.bias = c.bias; kp.bias_mode = c.bias ? 2 : 0;
+    kp.residual = c.residual; kp.ldr = c.H * c.W; kp.r_batch_stride = c.OC * c.H * c.W;
+    kp.act = 0;
+    kp.conv = 1; kp.conv_W = (int)c.W; kp.conv_KW = c.KW; kp.conv_cblocks = (int)(c.C / 64); kp.conv_pad = c.pad; kp.conv_dil = c.dil;
+    const int64_t mt = (g.M + BM - 1) / BM, nt = (g.N + pl.bn - 1) / pl.bn;
+    if (nt > 65535 || g.batch * pl.splits > 65535) return -1;
+    if (pl.splits > 1) {
+        size_t need = (size_t)mt * nt * g.batch * pl.splits * pl.bn * BM * sizeof(float);
+        if (!workspace || workspace_bytes < need) { kp.splits = 1; pl.splits = 1; }
+        else {
+            kp.ws_partial = (float*)workspace;
+            kp.ws_counters = get_counters(mt * nt * g.batch);
+            if (!kp.ws_counters) { kp.splits = 1; pl.splits = 1; }
+        }
+    }
+    dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)(g.batch * pl.splits));
+    cudaError_t e;
+    if (pl.bn == 256) e = launch_cfg<256, 0>(s, grid, ta, tb, kp);
+    else if (pl.bn == 128) e = launch_cfg<128, 0>(s, grid, ta, tb, kp);
+    else e = launch_cfg<64, 0>(s, grid, ta, tb, kp);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[ggml-b200] implicit-GEMM conv launch failed: %s\n", cudaGetErrorString(e));
         return -1;
     }
     return 1;

@@ -666,6 +666,18 @@ extern "C" int sdh_run_op(const char* device, const char* op_s, int n_in, const 
     else if (op == "conv_2d") {
         r = ggml_conv_2d(ctx, t[0], t[1], I(0), I(1), I(2), I(3), I(4), I(5));
         if (t[2]) r = ggml_add_inplace(ctx, r, t[2]);
+    } else if (op == "gn_silu_conv") {
+        // ResBlock prologue + conv (block.hpp:124-150): GroupNorm32 -> SiLU -> Conv2d 3x3 (x, gn_w, gn_b, conv_w)
+        ggml_tensor* hh = ggml_group_norm(ctx, t[0], I(0), F(0));
+        hh = ggml_mul_inplace(ctx, hh, t[1]);
+        hh = ggml_add_inplace(ctx, hh, t[2]);
+        if (I(1)) hh = ggml_silu_inplace(ctx, hh);
+        r = ggml_conv_2d(ctx, t[3], hh, 1, 1, I(2), I(2), 1, 1);
+    } else if (op == "upscale_conv") {
+        // UpSampleBlock (block.hpp:58-65): nearest x2 -> Conv2d 3x3 (+ bias)   (x, conv_w, bias)
+        ggml_tensor* hh = ggml_upscale(ctx, t[0], 2, GGML_SCALE_MODE_NEAREST);
+        r = ggml_conv_2d(ctx, t[1], hh, 1, 1, 1, 1, 1, 1);
+        if (t[2]) r = ggml_add_inplace(ctx, r, t[2]);
     } else if (op == "im2col") r = ggml_im2col(ctx, t[0], t[1], I(0), I(1), I(2), I(3), I(4), I(5), true, (ggml_type)I(6));
     else if (op == "group_norm") {
         r = ggml_group_norm(ctx, t[0], I(0), F(0));

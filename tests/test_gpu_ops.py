@@ -112,3 +112,33 @@ def test_small_data_movement_ops(b200):
     for uop in (10, 8):                                      # SILU, GELU (CPU GELU goes through an f16 table)
         g, c = both(b200, "unary", [f(1, 1, 64, 320)], ip=[uop])
         assert rel(g, c) < (1e-6 if uop == 10 else 2e-3)
+
+
+@pytest.mark.parametrize("C,OC,H,silu", [(320, 320, 64, 1), (640, 1280, 16, 1), (1280, 1280, 8, 1), (320, 320, 32, 0), (128, 256, 128, 1)])
+def test_resblock_prologue_plus_conv(b200, C, OC, H, silu):
+    """GROUP_NORM -> MUL -> ADD -> SILU -> IM2COL -> MUL_MAT -> RESHAPE -> PERMUTE -> CONT: one fused implicit-GEMM launch chain."""
+    x, gw, gb = f(1, C, H, H) * 2 + 0.3, 1 + 0.1 * f(1, C, 1, 1), 0.1 * f(1, C, 1, 1)
+    w = f(OC, C, 3, 3) / np.sqrt(9 * C)
+    g, c = both(b200, "gn_silu_conv", [x, gw, gb, w], ["f32", "f32", "f32", "f16"], ip=[32, silu, 1], fp=[1e-6])
+    assert rel(g, c) < 3e-4, f"rel {rel(g, c):.2e}"
+
+
+@pytest.mark.parametrize("C,OC,H", [(1280, 1280, 8), (640, 640, 32), (256, 256, 128)])
+def test_upsample_conv(b200, C, OC, H):
+    x, w, b = f(1, C, H, H), f(OC, C, 3, 3) / np.sqrt(9 * C), 0.1 * f(1, OC, 1, 1)
+    g, c = both(b200, "upscale_conv", [x, w, b], ["f32", "f16", "f32"])
+    assert rel(g, c) < 3e-4, f"rel {rel(g, c):.2e}"
+
+
+def test_implicit_conv_matches_unfused_path(b200):
+    """Same conv with fusion off (IM2COL + GEMM as separate nodes) and on (implicit GEMM): must agree to f32 summation noise."""
+    import os
+    h, dev = b200
+    w, x, b = f(640, 320, 3, 3) / 54, f(1, 320, 32, 32), 0.1 * f(1, 640, 1, 1)
+    fused = h.run_op(dev, "conv_2d", [w, x, b], ["f16", "f32", "f32"], ip=[1, 1, 1, 1, 1, 1])
+    os.environ["GGML_B200_FUSION"] = "0"
+    try:
+        plain = h.run_op(dev, "conv_2d", [w, x, b], ["f16", "f32", "f32"], ip=[1, 1, 1, 1, 1, 1])
+    finally:
+        del os.environ["GGML_B200_FUSION"]
+    assert rel(fused, plain) < 1e-5
