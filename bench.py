@@ -249,7 +249,11 @@ def run_b200(args):
                                 graph_nodes=nodes),
                     e2e=dict(value=e2e, unit="steps/s", ms_per_step=1e3 * wall / args.steps,
                              h2d_bytes_per_step=2 * (4 * 64 * 64 * 4 + 77 * 768 * 4 + 4 + 8), d2h_bytes_per_step=2 * 4 * 64 * 64 * 4),
-                    gpu_launches=int(launches), forwards=int(forwards), clocks=clk.summary(), roofline=roof, cpu_baseline=cpu_base)
+                    gpu_launches=int(launches), forwards=int(forwards), clocks=clk.summary(), roofline=roof, cpu_baseline=cpu_base,
+                    backend=dict(cuda_graph_replays=int(s1["cuda_graph_replays"] - s0["cuda_graph_replays"]),
+                                 fused_nodes=int(s1["fused_nodes"] - s0["fused_nodes"]), implicit_convs=int(s1["implicit_convs"] - s0["implicit_convs"]),
+                                 fused_attn_launches=int(s1["fused_attn_launches"] - s0["fused_attn_launches"]),
+                                 tc_gemm_launches=int(s1["tc_gemm_launches"] - s0["tc_gemm_launches"])))
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -62,6 +62,98 @@ template <int OP> __device__ __forceinline__ float binop(float a, float b) {
     return a / b;
 }
 
+// ---------------------------------------------------------------------------------------------
+// row-vectorised fast paths: tensors whose rows (dim 0) are unit-stride and 16-byte aligned but whose outer dims are
+// strided (views, permutes).  One thread per 4 elements; the (i1,i2,i3) decomposition is 32-bit and per 16 bytes, not
+// 64-bit per element like the generic kernels.
+// ---------------------------------------------------------------------------------------------
+struct rows4 {
+    uint32_t cpr;            // 4-element chunks per row
+    uint32_t ne1, ne2;       // row -> (i1, i2, i3)
+    uint32_t total;          // chunks
+};
+struct strides3 { int64_t nb1, nb2, nb3; };
+
+__device__ __forceinline__ void rows4_decode(const rows4& r, uint32_t idx, uint32_t& c, uint32_t& i1, uint32_t& i2, uint32_t& i3) {
+    uint32_t row = idx / r.cpr;
+    c = idx - row * r.cpr;
+    uint32_t t = row / r.ne1;
+    i1 = row - t * r.ne1;
+    i3 = t / r.ne2;
+    i2 = t - i3 * r.ne2;
+}
+
+template <int OP>
+__global__ void k_binary_rows4(const char* __restrict__ a, strides3 sa, const char* __restrict__ b, strides3 sb, char* __restrict__ d, strides3 sd,
+                               rows4 r) {
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < r.total; idx += gridDim.x * blockDim.x) {
+        uint32_t c, i1, i2, i3;
+        rows4_decode(r, idx, c, i1, i2, i3);
+        const float4 x = *(const float4*)(a + i1 * sa.nb1 + i2 * sa.nb2 + i3 * sa.nb3 + (int64_t)c * 16);
+        const float4 y = *(const float4*)(b + i1 * sb.nb1 + i2 * sb.nb2 + i3 * sb.nb3 + (int64_t)c * 16);
+        *(float4*)(d + i1 * sd.nb1 + i2 * sd.nb2 + i3 * sd.nb3 + (int64_t)c * 16) =
+            make_float4(binop<OP>(x.x, y.x), binop<OP>(x.y, y.y), binop<OP>(x.z, y.z), binop<OP>(x.w, y.w));
+    }
+}
+
+__global__ void k_copy_rows4(const char* __restrict__ a, strides3 sa, char* __restrict__ d, strides3 sd, rows4 r) {
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < r.total; idx += gridDim.x * blockDim.x) {
+        uint32_t c, i1, i2, i3;
+        rows4_decode(r, idx, c, i1, i2, i3);
+        *(uint4*)(d + i1 * sd.nb1 + i2 * sd.nb2 + i3 * sd.nb3 + (int64_t)c * 16) =
+            *(const uint4*)(a + i1 * sa.nb1 + i2 * sa.nb2 + i3 * sa.nb3 + (int64_t)c * 16);
+    }
+}
+
+// concat along dim >= 1 of row-contiguous 4-byte tensors: destination row -> which source, then a 16-byte copy
+__global__ void k_concat_rows4(const char* __restrict__ a, strides3 sa, const char* __restrict__ b, strides3 sb, char* __restrict__ d, strides3 sd,
+                               rows4 r, int dim, uint32_t a_ne_dim) {
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < r.total; idx += gridDim.x * blockDim.x) {
+        uint32_t c, i[4];
+        rows4_decode(r, idx, c, i[1], i[2], i[3]);
+        char* pd = d + i[1] * sd.nb1 + i[2] * sd.nb2 + i[3] * sd.nb3 + (int64_t)c * 16;
+        const char* src = a;
+        strides3 ss = sa;
+        if (i[dim] >= a_ne_dim) { i[dim] -= a_ne_dim; src = b; ss = sb; }
+        *(uint4*)pd = *(const uint4*)(src + i[1] * ss.nb1 + i[2] * ss.nb2 + i[3] * ss.nb3 + (int64_t)c * 16);
+    }
+}
+
+// f32 rows -> dense f16/bf16 [rows][kpad], 8 outputs (16 bytes) per thread; rows unit-stride and 16-byte aligned
+template <typename TD>
+__global__ void k_pack_rows8(const char* __restrict__ a, strides3 sa, TD* __restrict__ d, rows4 r /* cpr = kpad/8 */, uint32_t K) {
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < r.total; idx += gridDim.x * blockDim.x) {
+        uint32_t c, i1, i2, i3;
+        rows4_decode(r, idx, c, i1, i2, i3);
+        const float* src = (const float*)(a + i1 * sa.nb1 + i2 * sa.nb2 + i3 * sa.nb3) + c * 8;
+        float v[8];
+        if (c * 8 + 8 <= K) {
+            const float4 x = *(const float4*)src, y = *(const float4*)(src + 4);
+            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (c * 8 + k < K) ? src[k] : 0.f;
+        }
+        TD o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) stf<TD>(&o[k], v[k]);
+        *(uint4*)(d + (int64_t)idx * 8) = *(const uint4*)o;
+    }
+}
+
+inline bool rows4_ok(const b200_td& t) {
+    return t.nb[0] == 4 && t.ne[0] % 4 == 0 && (uintptr_t)t.data % 16 == 0 && t.nb[1] % 16 == 0 && t.nb[2] % 16 == 0 && t.nb[3] % 16 == 0;
+}
+inline bool make_rows4(const b200_td& shape, rows4* r) {
+    int64_t total = (shape.ne[0] / 4) * shape.ne[1] * shape.ne[2] * shape.ne[3];
+    if (total <= 0 || total >= (1ll << 31) || shape.ne[0] / 4 >= (1ll << 31) || shape.ne[1] >= (1ll << 31) || shape.ne[2] >= (1ll << 31)) return false;
+    r->cpr = (uint32_t)(shape.ne[0] / 4); r->ne1 = (uint32_t)shape.ne[1]; r->ne2 = (uint32_t)shape.ne[2]; r->total = (uint32_t)total;
+    return true;
+}
+inline strides3 st3(const b200_td& t) { return strides3{t.nb[1], t.nb[2], t.nb[3]}; }
+inline bool same_shape(const b200_td& a, const b200_td& b) { return a.ne[0] == b.ne[0] && a.ne[1] == b.ne[1] && a.ne[2] == b.ne[2] && a.ne[3] == b.ne[3]; }
+
+
 // generic: any strides, src1 broadcast by modulo (ggml_can_repeat(src1, src0))
 template <int OP, typename TA, typename TB, typename TD>
 __global__ void k_binary_generic(b200_td a, b200_td b, b200_td d, int64_t n) {
@@ -111,6 +203,13 @@ int launch_binary_op(cudaStream_t s, const b200_td& a, const b200_td& b, const b
         if (mode >= 0) {
             k_binary_f32_vec4<OP><<<grid_for(n / 4), kThreads, 0, s>>>((const float4*)a.data, (const float*)b.data, (float4*)d.data, n / 4, mode,
                                                                         d.ne[0], d.ne[0] * d.ne[1], d.ne[2]);
+            return 1;
+        }
+    }
+    if (f32 && same_shape(a, d) && same_shape(b, d) && rows4_ok(a) && rows4_ok(b) && rows4_ok(d)) {
+        rows4 r;
+        if (make_rows4(d, &r)) {
+            k_binary_rows4<OP><<<grid_for(r.total), kThreads, 0, s>>>((const char*)a.data, st3(a), (const char*)b.data, st3(b), (char*)d.data, st3(d), r);
             return 1;
         }
     }
@@ -451,6 +550,7 @@ __global__ void k_pack_rows(b200_td a, TD* __restrict__ d, int64_t kpad, int64_t
     }
 }
 
+
 }  // namespace
 
 // ================================================================================================
@@ -512,6 +612,13 @@ int b200_launch_copy(cudaStream_t s, const b200_td& a, const b200_td& d) {
             }
         }
     }
+    if (a.type == d.type && es == 4 && same_shape(a, d) && rows4_ok(a) && rows4_ok(d)) {
+        rows4 r;
+        if (make_rows4(d, &r)) {
+            k_copy_rows4<<<grid_for(r.total), kThreads, 0, s>>>((const char*)a.data, st3(a), (char*)d.data, st3(d), r);
+            return 1;
+        }
+    }
     unsigned g = grid_for(n);
 #define CP(TS, TD) k_copy_generic<TS, TD><<<g, kThreads, 0, s>>>(a, d, n)
     if (a.type == d.type) {
@@ -534,6 +641,14 @@ int b200_launch_concat(cudaStream_t s, const b200_td& a, const b200_td& b, const
     int64_t n = td_nelements(d);
     if (n == 0) return 0;
     int64_t es = type_size(d.type);
+    if (es == 4 && dim >= 1 && rows4_ok(a) && rows4_ok(b) && rows4_ok(d) && a.ne[dim] < (1ll << 31)) {
+        rows4 r;
+        if (make_rows4(d, &r)) {
+            k_concat_rows4<<<grid_for(r.total), kThreads, 0, s>>>((const char*)a.data, st3(a), (const char*)b.data, st3(b), (char*)d.data, st3(d), r, dim,
+                                                                 (uint32_t)a.ne[dim]);
+            return 1;
+        }
+    }
     if (es == 4) k_concat<uint32_t><<<grid_for(n), kThreads, 0, s>>>(a, b, d, dim, n);
     else if (es == 2) k_concat<uint16_t><<<grid_for(n), kThreads, 0, s>>>(a, b, d, dim, n);
     else return -1;
@@ -635,6 +750,17 @@ int b200_launch_pack_rows(cudaStream_t s, const b200_td& a, void* dst, int dst_t
     int64_t nrows = a.ne[1] * a.ne[2] * a.ne[3];
     int64_t n = nrows * kpad;
     if (n == 0) return 0;
+    if (a.type == GGML_TYPE_F32 && (dst_type == GGML_TYPE_F16 || dst_type == GGML_TYPE_BF16) && a.nb[0] == 4 && kpad % 8 == 0 &&
+        (uintptr_t)a.data % 16 == 0 && a.nb[1] % 16 == 0 && a.nb[2] % 16 == 0 && a.nb[3] % 16 == 0 && (uintptr_t)dst % 16 == 0 && a.ne[0] < (1ll << 31)) {
+        b200_td shape = a;
+        shape.ne[0] = kpad / 2;      // make_rows4 divides by 4: cpr = kpad / 8
+        rows4 r;
+        if (make_rows4(shape, &r)) {
+            if (dst_type == GGML_TYPE_F16) k_pack_rows8<__half><<<grid_for(r.total), kThreads, 0, s>>>((const char*)a.data, st3(a), (__half*)dst, r, (uint32_t)a.ne[0]);
+            else k_pack_rows8<__nv_bfloat16><<<grid_for(r.total), kThreads, 0, s>>>((const char*)a.data, st3(a), (__nv_bfloat16*)dst, r, (uint32_t)a.ne[0]);
+            return 1;
+        }
+    }
     unsigned g = grid_for(n);
 #define PK(TS, TD) k_pack_rows<TS, TD><<<g, kThreads, 0, s>>>(a, (TD*)dst, kpad, nrows)
     if (a.type == GGML_TYPE_F32 && dst_type == GGML_TYPE_F16) PK(float, __half);

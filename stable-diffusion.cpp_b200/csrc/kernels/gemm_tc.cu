@@ -47,8 +47,6 @@ struct GemmKParams {
     const float* residual;
     int64_t ldr, r_batch_stride;
     int act;           // 0 none, 1 silu, 2 gelu(tanh)
-    float* ws_partial; // [tile][split][BN][BM]
-    unsigned* ws_counters;
     // implicit-GEMM convolution (conv != 0): A is an NHWC f16 image read through a 4-D map (C, W, H, N) with halo boxes;
     // k-block kb -> filter tap kb / cblocks and 64-channel block kb % cblocks; rows of the tile are output pixels
     int conv;
@@ -61,8 +59,9 @@ struct GemmKParams {
 template <int BN> struct Cfg {
     static constexpr int B_STAGE_BYTES = BN * BK_BYTES;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    // BN <= 128: ~96-110 KB so two CTAs share an SM (one CTA's epilogue overlaps the other's main loop)
-    static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 3 : 4);
+    // The main loop is a latency ring (TMA issue -> data -> MMA -> commit -> slot free is ~1 us round trip), so depth is what
+    // buys bandwidth: use (almost) all 227 KB -- 8 x 24 KB, 6 x 32 KB, 4 x 48 KB -- one CTA per SM.
+    static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // + alignment slack
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
@@ -83,12 +82,11 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[C::STAGES], empty_bar[C::STAGES], tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
-    __shared__ int s_is_last;
 
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    const int split = blockIdx.z % p.splits;
+    const int split = p.splits > 1 ? (int)cluster_ctarank() : 0;   // cluster (1,1,splits): rank == blockIdx.z % splits
     const int batch = blockIdx.z / p.splits;
     const int i2 = batch % p.ne12, i3 = batch / p.ne12;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -178,8 +176,7 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
         float* Dp = p.D + (int64_t)batch * p.d_batch_stride;
         const float* Rp = p.residual ? p.residual + (int64_t)batch * p.r_batch_stride : nullptr;
         const float bias_m = (p.bias_mode == 1 && m < p.M) ? p.bias[m] : 0.f;
-        const int64_t tile_id = ((int64_t)batch * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-        float* part = direct ? nullptr : p.ws_partial + ((tile_id * p.splits + split) * BN) * BM;
+        float* sred = (float*)smem;   // [BN][BM] f32 partial tile; the operand ring is dead once tmem_full has fired
 
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -200,41 +197,51 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) part[(c0 + j) * BM + ml] = __uint_as_float(r[j]);
-            }
-        }
-        if (!direct) {
-            // publish the partial tile, then the last CTA of this tile reduces all splits in order
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (threadIdx.x == 64) {
-                unsigned prev = atomicAdd(&p.ws_counters[tile_id], 1u);
-                s_is_last = (prev == (unsigned)p.splits - 1);
-                if (s_is_last) p.ws_counters[tile_id] = 0;   // self-reset for the next launch
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (s_is_last) {
-                __threadfence();
-                const float* base = p.ws_partial + (tile_id * p.splits) * BN * BM;
-#pragma unroll 1
-                for (int c = 0; c < BN; ++c) {
-                    const int64_t n = (int64_t)n0 + c;
-                    if (n >= p.N) break;
-                    float v = 0.f;
-                    for (int s = 0; s < p.splits; ++s) v += __ldcg(base + ((int64_t)s * BN + c) * BM + ml);
-                    if (m < p.M) {
-                        v += bias_m;
-                        if (p.bias_mode == 2) v += p.bias[n];
-                        v = epilogue_act(v, p.act);
-                        if (Rp) v += Rp[n * p.ldr + m];
-                        Dp[n * p.ldd + m] = v;
-                    }
-                }
+                for (int j = 0; j < 16; ++j) sred[(c0 + j) * BM + ml] = __uint_as_float(r[j]);
             }
         }
         tc_fence_before();
     }
     __syncthreads();
+    if (p.splits > 1) {
+        // ---- split-K reduction inside the thread-block cluster: the `splits` CTAs of one output tile form a cluster
+        //      (1,1,splits); each keeps its partial tile in its own shared memory and reduces every splits-th column by
+        //      reading the peers' tiles through distributed shared memory, in rank order (deterministic), then runs the
+        //      epilogue for those columns.  No global workspace, no atomics.
+        cluster_sync_all();
+        if (warp >= 2) {
+            const int q = warp & 3;
+            const int ml = q * 32 + lane;
+            const int64_t m = (int64_t)m0 + ml;
+            float* Dp = p.D + (int64_t)batch * p.d_batch_stride;
+            const float* Rp = p.residual ? p.residual + (int64_t)batch * p.r_batch_stride : nullptr;
+            const float bias_m = (p.bias_mode == 1 && m < p.M) ? p.bias[m] : 0.f;
+            const uint32_t sred_local = smem_u32(smem);
+            uint32_t peer[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) peer[s] = s < p.splits ? dsmem_map(sred_local, (uint32_t)s) : 0u;
+#pragma unroll 1
+            for (int c = split; c < BN; c += p.splits) {
+                const int64_t n = (int64_t)n0 + c;
+                if (n >= p.N) break;
+                const uint32_t off = (uint32_t)(c * BM + ml) * 4u;
+                float part[8];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) part[s] = s < p.splits ? dsmem_ld_f32(peer[s] + off) : 0.f;
+                float v = 0.f;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) v += part[s];
+                if (m < p.M) {
+                    v += bias_m;
+                    if (p.bias_mode == 2) v += p.bias[n];
+                    v = epilogue_act(v, p.act);
+                    if (Rp) v += Rp[n * p.ldr + m];
+                    Dp[n * p.ldd + m] = v;
+                }
+            }
+        }
+        cluster_sync_all();   // nobody may exit (and release its shared memory) while a peer is still reading it
+    }
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -316,14 +323,14 @@ Plan choose_plan(const b200_device_info& dev, const b200_gemm_args& g, int num_k
         const int64_t nt = (g.N + bn - 1) / bn;
         const int64_t tiles = mt * nt * g.batch;
         const double smem_factor = bn == 64 ? 1.5 : (bn == 128 ? 1.0 : 1.0);   // smem operand bandwidth bound at small BN
-        for (int splits = 1; splits <= 16; ++splits) {
+        for (int splits = 1; splits <= 8; ++splits) {   // portable cluster size limit
             if (splits > num_k_blocks) break;
             if (splits > 1 && (num_k_blocks / splits) < 4) break;   // keep the main loop meaningful
             const int64_t ctas = tiles * splits;
             const double per_sm = (double)((ctas + sms - 1) / sms);
             const double kb = (double)((num_k_blocks + splits - 1) / splits);
             // cycles: main loop + prologue/epilogue (+ reduction traffic for split-K)
-            double cta_cycles = kb * 2.0 * bn * smem_factor + 1800.0 + 6.0 * bn + (splits > 1 ? (double)splits * bn * 4.0 + 1500.0 : 0.0);
+            double cta_cycles = kb * 2.0 * bn * smem_factor + 2500.0 + 6.0 * bn + (splits > 1 ? (double)bn * 30.0 + 2500.0 : 0.0);
             double t = per_sm * cta_cycles;
             if (t < best) { best = t; bestp = Plan{bn, splits}; }
         }
@@ -342,38 +349,26 @@ cudaError_t launch_cfg(cudaStream_t s, dim3 grid, const CUtensorMap& ta, const C
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    k_gemm_tc<BN, FMT><<<grid, 192, C::SMEM_BYTES, s>>>(ta, tb, kp);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)kp.splits;
+    cfg.attrs = attr;
+    cfg.numAttrs = kp.splits > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, FMT>, ta, tb, kp);
 }
 
 }  // namespace
 
-size_t b200_gemm_tc_workspace_bytes(const b200_device_info& dev, const b200_gemm_args& g) {
-    const int64_t es = g.type == GGML_TYPE_F32 ? 4 : 2;
-    const int bk = (int)(BK_BYTES / es);
-    const int nkb = (int)((g.K + bk - 1) / bk);
-    Plan pl = choose_plan(dev, g, nkb);
-    if (pl.splits == 1) return 0;
-    const int64_t tiles = ((g.M + BM - 1) / BM) * ((g.N + pl.bn - 1) / pl.bn) * g.batch;
-    return (size_t)tiles * pl.splits * pl.bn * BM * sizeof(float);
-}
-
-// split-K arrival counters: one small zero-initialised, self-resetting array per device
-static unsigned* get_counters(int64_t n) {
-    static unsigned* ptr[B200_MAX_DEVICES] = {};
-    static int64_t cap[B200_MAX_DEVICES] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cap[dev] < n) {
-        // old array may still be in use by queued kernels: leak-free because we only grow after a device sync
-        cudaDeviceSynchronize();
-        if (ptr[dev]) cudaFree(ptr[dev]);
-        int64_t newcap = n < 65536 ? 65536 : n * 2;
-        if (cudaMalloc(&ptr[dev], newcap * sizeof(unsigned)) != cudaSuccess) { ptr[dev] = nullptr; cap[dev] = 0; return nullptr; }
-        cudaMemset(ptr[dev], 0, newcap * sizeof(unsigned));
-        cap[dev] = newcap;
-    }
-    return ptr[dev];
+size_t b200_gemm_tc_workspace_bytes(const b200_device_info&, const b200_gemm_args&) {
+    return 0;   // split-K partials live in distributed shared memory
 }
 
 int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g, void* workspace, size_t workspace_bytes) {
@@ -407,15 +402,7 @@ int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     kp.act = g.act;
     const int64_t mt = (g.M + BM - 1) / BM, nt = (g.N + pl.bn - 1) / pl.bn;
     if (mt > 0x7fffffff || nt > 65535 || g.batch * pl.splits > 65535) return -1;
-    if (pl.splits > 1) {
-        size_t need = (size_t)mt * nt * g.batch * pl.splits * pl.bn * BM * sizeof(float);
-        if (!workspace || workspace_bytes < need) { kp.splits = 1; pl.splits = 1; }
-        else {
-            kp.ws_partial = (float*)workspace;
-            kp.ws_counters = get_counters(mt * nt * g.batch);
-            if (!kp.ws_counters) { kp.splits = 1; pl.splits = 1; }
-        }
-    }
+    (void)workspace; (void)workspace_bytes;
     dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)(g.batch * pl.splits));
     const int fmt = g.type == GGML_TYPE_F16 ? 0 : (g.type == GGML_TYPE_BF16 ? 1 : 2);
     cudaError_t e = cudaErrorInvalidValue;
@@ -494,15 +481,7 @@ int b200_launch_conv_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     kp.conv = 1; kp.conv_W = (int)c.W; kp.conv_KW = c.KW; kp.conv_cblocks = (int)(c.C / 64); kp.conv_pad = c.pad; kp.conv_dil = c.dil;
     const int64_t mt = (g.M + BM - 1) / BM, nt = (g.N + pl.bn - 1) / pl.bn;
     if (nt > 65535 || g.batch * pl.splits > 65535) return -1;
-    if (pl.splits > 1) {
-        size_t need = (size_t)mt * nt * g.batch * pl.splits * pl.bn * BM * sizeof(float);
-        if (!workspace || workspace_bytes < need) { kp.splits = 1; pl.splits = 1; }
-        else {
-            kp.ws_partial = (float*)workspace;
-            kp.ws_counters = get_counters(mt * nt * g.batch);
-            if (!kp.ws_counters) { kp.splits = 1; pl.splits = 1; }
-        }
-    }
+    (void)workspace; (void)workspace_bytes;
     dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)(g.batch * pl.splits));
     cudaError_t e;
     if (pl.bn == 256) e = launch_cfg<256, 0>(s, grid, ta, tb, kp);
