@@ -42,7 +42,7 @@ b200_context* b200_context_create(const b200_device_info& info) {
     ctx->opt_fusion = env_flag("GGML_B200_FUSION", 1) != 0;
     ctx->opt_tc_gemm = env_flag("GGML_B200_TC_GEMM", 1) != 0;
     ctx->opt_timing = env_flag("GGML_B200_TIMING", 1) != 0;
-    ctx->opt_cuda_graphs = env_flag("GGML_B200_CUDA_GRAPHS", 0) != 0;
+    ctx->opt_cuda_graphs = env_flag("GGML_B200_CUDA_GRAPHS", 1) != 0;
     ctx->opt_fused_attn = env_flag("GGML_B200_FUSED_ATTN", 1) != 0;
     ctx->opt_implicit_conv = env_flag("GGML_B200_IMPLICIT_CONV", 1) != 0;
     return ctx;

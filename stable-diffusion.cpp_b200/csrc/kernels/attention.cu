@@ -211,12 +211,13 @@ __global__ void __launch_bounds__(192, 1) k_flash_attn(const __grid_constant__ C
             float m_new = fmaxf(m_ref, mx);
             if (m_new == -INFINITY) m_new = 0.f;                  // fully masked row so far
             bool grow = (j == 0) || (m_new - m_ref > kLazyThreshold);
-            // previous P.V must have retired before P is overwritten or O is rescaled
-            if (j > 0) {
+            // previous P.V must have retired before P is overwritten or O is rescaled; the (rare) rescale needs it now,
+            // otherwise the wait is deferred until the new probabilities sit in registers so the exps overlap that MMA
+            bool waited = j == 0;
+            if (j > 0 && __any_sync(0xffffffffu, grow)) {
                 mbar_wait(&pv_done, (j - 1) & 1);
                 tc_fence_after();
-            }
-            if (j > 0 && __any_sync(0xffffffffu, grow)) {
+                waited = true;
                 const float alpha = grow ? exp2f(m_ref - m_new) : 1.0f;
                 l *= alpha;
 #pragma unroll 1
@@ -233,38 +234,40 @@ __global__ void __launch_bounds__(192, 1) k_flash_attn(const __grid_constant__ C
             if (grow) m_ref = m_new;
             // ---- pass 2: P = exp2(s - m_ref), row sum, f16 into swizzled shared memory
             float lsum = 0.f;
-#pragma unroll 1
+            uint32_t ph[BLOCK_N / 2];   // the whole P row as packed half2, kept in registers until the P buffer is free
+#pragma unroll
             for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tS + c0, v);
                 tmem_ld_wait();
-                float pv[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < 32; i += 2) {
                     const int key = kbase + c0 + i;
-                    float t = __uint_as_float(v[i]) * p.scale_log2;
-                    if (mrow && key < p.Lk) t += __half2float(mrow[key]) * p.log2e;
-                    float e = key < p.Lk ? exp2f(t - m_ref) : 0.f;
-                    pv[i] = e;
-                }
-#pragma unroll
-                for (int cch = 0; cch < 4; ++cch) {
-                    __half2 hv[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        hv[e] = __floats2half2_rn(pv[cch * 8 + e * 2], pv[cch * 8 + e * 2 + 1]);
-                        // accumulate the sum from the ROUNDED probabilities: what the tensor core multiplies is what we normalise by
-                        float2 f = __half22float2(hv[e]);
-                        lsum += f.x + f.y;
+                    float t0 = __uint_as_float(v[i]) * p.scale_log2, t1 = __uint_as_float(v[i + 1]) * p.scale_log2;
+                    if (mrow) {
+                        if (key < p.Lk) t0 += __half2float(mrow[key]) * p.log2e;
+                        if (key + 1 < p.Lk) t1 += __half2float(mrow[key + 1]) * p.log2e;
                     }
-                    const int chunk = (c0 >> 3) + cch;        // 16-byte chunk index along keys
-                    const int atom = chunk >> 3, cc = chunk & 7;
-                    uint4 val;
-                    memcpy(&val, hv, 16);
-                    *(uint4*)(sP + atom * (BLOCK_M * 128) + r * 128 + ((cc ^ (r & 7)) << 4)) = val;
+                    const float e0 = key < p.Lk ? exp2f(t0 - m_ref) : 0.f;
+                    const float e1 = key + 1 < p.Lk ? exp2f(t1 - m_ref) : 0.f;
+                    const __half2 hv = __floats2half2_rn(e0, e1);
+                    // accumulate the sum from the ROUNDED probabilities: what the tensor core multiplies is what we normalise by
+                    const float2 f = __half22float2(hv);
+                    lsum += f.x + f.y;
+                    ph[(c0 + i) >> 1] = *(const uint32_t*)&hv;
                 }
             }
             l += lsum;
+            if (!waited) {
+                mbar_wait(&pv_done, (j - 1) & 1);
+                tc_fence_after();
+            }
+#pragma unroll
+            for (int chunk = 0; chunk < BLOCK_N / 8; ++chunk) {       // 16-byte chunks of 8 keys
+                const int atom = chunk >> 3, cc = chunk & 7;
+                const uint4 val = make_uint4(ph[chunk * 4], ph[chunk * 4 + 1], ph[chunk * 4 + 2], ph[chunk * 4 + 3]);
+                *(uint4*)(sP + atom * (BLOCK_M * 128) + r * 128 + ((cc ^ (r & 7)) << 4)) = val;
+            }
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(&p_full);
@@ -336,7 +339,9 @@ int b200_launch_flash_attn_fused(cudaStream_t s, const b200_td& q, const b200_td
     if (((uintptr_t)vt & 15) || ((uintptr_t)q.data & 3)) return -1;
     if (Lq == 0 || Lk == 0) return -1;
     const int natom = (int)((d + 63) / 64);
-    const int block_n = natom == 3 ? 64 : 128;
+    // d <= 64: 64-key tiles keep a CTA at 65 KB of shared memory and 256 TMEM columns, so two CTAs share an SM and one's
+    // softmax overlaps the other's MMAs (the per-tile dependency chain S -> softmax -> P -> PV is latency bound)
+    const int block_n = natom == 2 ? 128 : 64;
     const int dv16 = (int)((dv + 15) / 16 * 16);
 
     CUtensorMap tk, tv;
@@ -365,7 +370,7 @@ int b200_launch_flash_attn_fused(cudaStream_t s, const b200_td& q, const b200_td
     p.scale_log2 = scale * p.log2e;
     dim3 grid((unsigned)((Lq + BLOCK_M - 1) / BLOCK_M), (unsigned)H, (unsigned)NB);
     if (H > 65535 || NB > 65535) return -1;
-    if (natom == 1) return launch_fa<1, 128>(s, grid, tk, tv, p);
+    if (natom == 1) return launch_fa<1, 64>(s, grid, tk, tv, p);
     if (natom == 2) return launch_fa<2, 128>(s, grid, tk, tv, p);
     return launch_fa<3, 64>(s, grid, tk, tv, p);
 }
