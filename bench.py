@@ -234,6 +234,9 @@ def run_b200(args):
         except Exception as e:   # older plugin without kernel timing
             roof = dict(bound="tensor", error=str(e))
         step_tflops = 2 * flops * images * args.steps / (dev_ms / 1e3) / 1e12 / max(1, n if world > 1 else 1)
+        vae = None
+        if n == 1 and not args.no_vae:
+            vae = vae_decode_leg(h, dev, pk)
         if n == 1 and not args.no_cpu_baseline:
             cpu_base = cpu_baseline_leg(h)
     m.close()
@@ -250,6 +253,7 @@ def run_b200(args):
                     e2e=dict(value=e2e, unit="steps/s", ms_per_step=1e3 * wall / args.steps,
                              h2d_bytes_per_step=2 * (4 * 64 * 64 * 4 + 77 * 768 * 4 + 4 + 8), d2h_bytes_per_step=2 * 4 * 64 * 64 * 4),
                     gpu_launches=int(launches), forwards=int(forwards), clocks=clk.summary(), roofline=roof, cpu_baseline=cpu_base,
+                    vae_decode=vae,
                     backend=dict(cuda_graph_replays=int(s1["cuda_graph_replays"] - s0["cuda_graph_replays"]),
                                  fused_nodes=int(s1["fused_nodes"] - s0["fused_nodes"]), implicit_convs=int(s1["implicit_convs"] - s0["implicit_convs"]),
                                  fused_attn_launches=int(s1["fused_attn_launches"] - s0["fused_attn_launches"]),
@@ -257,6 +261,32 @@ def run_b200(args):
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def vae_decode_leg(h, dev, pk):
+    """Second half of BASELINE.json's metric: AutoEncoderKL decode 64x64x4 -> 512x512x3 (reference graph, synthetic F16 weights).
+    HBM roofline per the north star: algorithmic bytes 7.27 GB (BASELINE.md section 3) / device time vs measured copy bandwidth;
+    the tensor fraction (2.515 TFLOP) is reported beside it because the fused graph crosses the ridge."""
+    m = h.model(dev, "vae_decoder", "f16", 0, 1234, 0)
+    z = h.randn(45, (1, 4, 64, 64))
+    nodes, flops = m.dump_graph(None, z)
+    for _ in range(3):
+        m.forward(z)
+    dev_ms, wall_ms = [], []
+    for _ in range(5):
+        s0 = m.stats()
+        t0 = time.perf_counter()
+        out, _ = m.forward(z)
+        wall_ms.append((time.perf_counter() - t0) * 1e3)
+        s1 = m.stats()
+        dev_ms.append(s1["total_graph_ms"] - s0["total_graph_ms"])
+    m.close()
+    d = statistics.median(dev_ms)
+    gb = 7.27
+    return dict(metric="vae_decode_ms", value=d, unit="ms", e2e_ms=statistics.median(wall_ms), workload="AutoEncoderKL decode 64x64x4 -> 512x512x3, F16 conv weights",
+                algorithmic_gb=gb, hbm_gbs=gb / (d / 1e3), hbm_frac=gb / (d / 1e3) / pk["hbm"], algorithmic_tflop=flops / 1e12,
+                tensor_tflops=flops / 1e12 / (d / 1e3), tensor_frac=flops / 1e12 / (d / 1e3) / pk["bf16_sustained"], graph_nodes=nodes,
+                finite=bool(np.isfinite(out).all()))
 
 
 def cpu_baseline_leg(h):
@@ -281,6 +311,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vae", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

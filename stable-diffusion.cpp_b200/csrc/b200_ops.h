@@ -63,6 +63,7 @@ struct b200_gemm_args {
     const float* residual;  // optional [N][M] like D (added after bias)
     int64_t     ldr;
     int         act;        // 0 none, 1 SiLU, 2 GELU(tanh)
+    void*       trace;      // optional device buffer of 8 uint64: phase timestamps of CTA (0,0,0) (tools/gemm_bench)
 };
 // returns kernels launched, or -1 if the shape/alignment is not supported by the TMA path (caller falls back)
 int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g, void* workspace, size_t workspace_bytes);

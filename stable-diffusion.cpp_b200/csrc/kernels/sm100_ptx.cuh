@@ -43,6 +43,12 @@ __device__ __forceinline__ float dsmem_ld_f32(uint32_t cluster_addr) {
     return v;
 }
 
+__device__ __forceinline__ float4 dsmem_ld_f32x4(uint32_t cluster_addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cluster_addr) : "memory");
+    return v;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

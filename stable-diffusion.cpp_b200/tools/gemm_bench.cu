@@ -1,0 +1,63 @@
+// gemm_bench.cu -- micro-benchmark of the tcgen05 GEMM / implicit-conv kernels at the SD1.5 UNet's shapes.
+// Steady state (warm L2, back-to-back launches on one stream, CUDA events), prints us / TFLOP/s per shape.
+// Tuning aid only: not part of the product path.  usage: gemm_bench [reps]
+#include "../csrc/b200_ops.h"
+#include <cuda_fp16.h>
+#include <vector>
+#include <cstring>
+
+struct Shape { const char* name; int64_t M, N, K, batch; };
+
+int main(int argc, char** argv) {
+    int reps = argc > 1 ? atoi(argv[1]) : 50;
+    cudaDeviceProp p;
+    cudaGetDeviceProperties(&p, 0);
+    b200_device_info dev{};
+    dev.id = 0; dev.sm_count = p.multiProcessorCount;
+    std::vector<Shape> shapes = {
+        {"conv 64x64 320->320 (im2col)", 4096, 320, 2880, 1}, {"conv 32x32 640->640", 1024, 640, 5760, 1}, {"conv 16x16 1280->1280", 256, 1280, 11520, 1},
+        {"conv 8x8 1280->1280", 64, 1280, 11520, 1}, {"conv 32x32 1920->640", 1024, 640, 17280, 1}, {"conv 64x64 960->320", 4096, 320, 8640, 1},
+        {"linear qkv L4096 C320", 320, 4096, 320, 1}, {"linear geglu L4096", 2560, 4096, 320, 1}, {"linear ff-out L4096", 320, 4096, 1280, 1},
+        {"linear qkv L1024 C640", 640, 1024, 640, 1}, {"linear geglu L1024", 5120, 1024, 640, 1}, {"linear ff-out L1024", 640, 1024, 2560, 1},
+        {"linear qkv L256 C1280", 1280, 256, 1280, 1}, {"linear geglu L256", 10240, 256, 1280, 1}, {"linear ff-out L256", 1280, 256, 5120, 1},
+        {"linear kv ctx77 C1280", 1280, 77, 768, 1}, {"linear kv ctx77 C320", 320, 77, 768, 1}, {"time emb", 1280, 1, 320, 1}, {"big square", 4096, 4096, 4096, 1},
+    };
+    size_t maxA = 0, maxB = 0, maxD = 0;
+    for (auto& s : shapes) { maxA = std::max(maxA, (size_t)s.M * s.K); maxB = std::max(maxB, (size_t)s.N * s.K); maxD = std::max(maxD, (size_t)s.M * s.N); }
+    __half *A, *B; float *D, *bias;
+    cudaMalloc(&A, maxA * 2); cudaMalloc(&B, maxB * 2); cudaMalloc(&D, maxD * 4); cudaMalloc(&bias, 1 << 20);
+    cudaMemset(A, 0, maxA * 2); cudaMemset(B, 0, maxB * 2); cudaMemset(bias, 0, 1 << 20);
+    unsigned long long* trace; cudaMalloc(&trace, 64);
+    cudaStream_t st; cudaStreamCreate(&st);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    printf("%-34s %8s %8s %8s | %9s %9s\n", "shape", "M", "N", "K", "us", "TFLOP/s");
+    for (auto& s : shapes) {
+        b200_gemm_args g; memset(&g, 0, sizeof(g));
+        g.A = A; g.B = B; g.type = GGML_TYPE_F16; g.M = s.M; g.N = s.N; g.K = s.K; g.lda = s.K; g.ldb = s.K; g.batch = 1; g.a_bcast = 1;
+        g.a_batch_stride = s.M * s.K; g.b_batch_stride = s.N * s.K; g.d_batch_stride = s.M * s.N; g.D = D; g.ldd = s.M; g.bias = bias; g.bias_mode = 1;
+        for (int i = 0; i < 5; ++i) b200_launch_gemm_tc(st, dev, g, nullptr, 0);
+        cudaStreamSynchronize(st);
+        cudaEventRecord(e0, st);
+        for (int i = 0; i < reps; ++i) b200_launch_gemm_tc(st, dev, g, nullptr, 0);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        double us = ms * 1e3 / reps;
+        printf("%-34s %8lld %8lld %8lld | %9.2f %9.1f", s.name, (long long)s.M, (long long)s.N, (long long)s.K, us, 2.0 * s.M * s.N * s.K / us * 1e-6);
+        // phase timestamps of CTA (0,0,0): start, setup done, first k-block landed, last k-block landed, accumulator ready, epilogue done, all warps joined, tmem freed
+        cudaMemset(trace, 0, 64);
+        g.trace = trace;
+        cudaEventRecord(e0, st);
+        b200_launch_gemm_tc(st, dev, g, nullptr, 0);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        unsigned long long t[8];
+        cudaMemcpy(t, trace, 64, cudaMemcpyDeviceToHost);
+        printf(" | single %6.2f us; cta0 ns: setup %llu, first-data %llu, mainloop %llu, acc-ready %llu, epilogue %llu, join %llu, free %llu\n", ms * 1e3,
+               t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6]);
+    }
+    cudaError_t e = cudaGetLastError();
+    printf("status: %s\n", cudaGetErrorString(e));
+    return 0;
+}

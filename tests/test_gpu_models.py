@@ -83,3 +83,31 @@ def test_no_silent_fallback_stats(b200):
     out, _ = m.forward(x, t, ctx)
     m.close()
     assert np.isfinite(out).all() and out.std() > 0
+
+
+def test_sdxl_unet_vs_live_cpu(b200):
+    """BASELINE config 3 architecture (SDXL UNet: 2816-d label embedding, transformer depth 1/2/10, 64-d heads) at a 32x32 latent."""
+    h, dev = b200
+    x = h.randn(42, (1, 4, 32, 32)); ctx = h.randn(43, (1, 77, 2048)); t = np.array([999.0], np.float32); y = h.randn(44, (1, 2816))
+    outs = {}
+    for d in (dev, "CPU"):
+        m = h.model(d, "sdxl_unet", "f16", 0, 1234, 0)
+        outs[d], _ = m.forward(x, t, ctx, y)
+        m.close()
+    assert np.isfinite(outs[dev]).all()
+    assert rel(outs[dev], outs["CPU"]) < 4e-3, f"rel_l2 {rel(outs[dev], outs['CPU']):.2e}"
+
+
+def test_flux_tiny_vs_live_cpu(b200):
+    """BASELINE config 4 architecture (Flux MMDiT: double-stream + single-stream blocks, RMSNorm(QK), RoPE, adaLN), BF16 weights,
+    2 + 2 blocks, 16x16 image tokens + 64 text tokens."""
+    h, dev = b200
+    x = h.randn(42, (1, 16, 32, 32)); ctx = h.randn(43, (1, 64, 4096)); t = np.array([1.0], np.float32); y = h.randn(44, (1, 768))
+    outs = {}
+    for d in (dev, "CPU"):
+        m = h.model(d, "flux_tiny", "bf16", 1, 1234, 0)
+        outs[d], _ = m.forward(x, t, ctx, y)
+        m.close()
+    assert np.isfinite(outs[dev]).all()
+    # bf16 weights/activations (8-bit mantissa) + the oracle's f16-accumulating flash attention: compare at bf16 noise level
+    assert rel(outs[dev], outs["CPU"]) < 3e-2, f"rel_l2 {rel(outs[dev], outs['CPU']):.2e}"
