@@ -352,7 +352,9 @@ static int op_flash_attn(b200_context* ctx, ggml_tensor* dst) {
     vt.ne[1] = v->ne[0]; vt.nb[1] = v->nb[0];
     void* vbuf = ws_alloc(ctx, (size_t)(Lk_pad * dv * Hkv * NB * es));
     if (!vbuf) return -1;
-    int n = b200_launch_pack_rows(ctx->stream, b200_make_td(&vt), vbuf, ct, Lk_pad);
+    int n = -1;
+    if (v->type == (ggml_type)ct && v->nb[0] == 2) n = b200_launch_transpose_f16(ctx->stream, b200_make_td(v), vbuf, Lk_pad);
+    if (n < 0) n = b200_launch_pack_rows(ctx->stream, b200_make_td(&vt), vbuf, ct, Lk_pad);
     if (n < 0) return -1;
     launches += n;
 
@@ -1032,6 +1034,31 @@ static int try_fuse_norm(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, in
     return n;
 }
 
+// CONT (strided f32 view) -> [order-preserving views] -> CPY to contiguous F16/BF16: one strided converting pass
+// (the K / V operands of ggml_ext_attention_ext: cont(permute(x)) followed by ggml_cast(F16), ggml_extend.hpp:1374-1406)
+static int try_fuse_cont_cast(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
+    ggml_tensor* c = g->nodes[i];
+    const ggml_tensor* src = c->src[0];
+    if (c->type != GGML_TYPE_F32 || src->type != GGML_TYPE_F32 || !ggml_is_contiguous(c) || (c->flags & GGML_TENSOR_FLAG_OUTPUT)) return -2;
+    if (src->nb[0] != 4 || c->ne[0] % 8 != 0 || !single_use(fs, c)) return -2;
+    if (src->ne[0] != c->ne[0] || src->ne[1] != c->ne[1] || src->ne[2] != c->ne[2] || src->ne[3] != c->ne[3]) return -2;
+    int j = next_node(g, fs, i);
+    if (j < 0) return -2;
+    ggml_tensor* cp = g->nodes[j];
+    if (cp->op != GGML_OP_CPY || !(cp->flags & GGML_TENSOR_FLAG_COMPUTE)) return -2;
+    const ggml_tensor* dst = cp->src[1];
+    if (!(dst->type == GGML_TYPE_F16 || dst->type == GGML_TYPE_BF16) || !ggml_is_contiguous(dst) || ggml_nelements(dst) != ggml_nelements(c)) return -2;
+    if (dst->ne[0] != c->ne[0]) return -2;   // rows must stay rows: the cast may only regroup the outer dims
+    if (!order_preserving_view_of(fs, cp->src[0], c)) return -2;
+    if (cp->src[0] != c && !single_use(fs, cp->src[0])) return -2;
+    if (((uintptr_t)src->data & 15) || (src->nb[1] & 15) || (src->nb[2] & 15) || (src->nb[3] & 15) || ((uintptr_t)dst->data & 15)) return -2;
+    int n = b200_launch_pack_rows(ctx->stream, b200_make_td(src), dst->data, (int)dst->type, c->ne[0]);
+    if (n < 0) return -2;
+    fs.done[j] = 1;
+    *covered = 1;
+    return n;
+}
+
 // IM2COL -> ...   or   UPSCALE(nearest x2) -> IM2COL -> ...
 static int try_fuse_conv(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
     ggml_tensor* t = g->nodes[i];
@@ -1078,6 +1105,7 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
             if (t->op == GGML_OP_MUL_MAT) n = try_fuse_mul_mat(ctx, cgraph, fs, i, &covered);
             else if (t->op == GGML_OP_GROUP_NORM || t->op == GGML_OP_NORM) n = try_fuse_norm(ctx, cgraph, fs, i, &covered);
             else if ((t->op == GGML_OP_IM2COL || t->op == GGML_OP_UPSCALE) && ctx->opt_tc_gemm && ctx->opt_implicit_conv) n = try_fuse_conv(ctx, cgraph, fs, i, &covered);
+            else if (t->op == GGML_OP_CONT) n = try_fuse_cont_cast(ctx, cgraph, fs, i, &covered);
             if (n >= 0) {
                 ctx->stats.fused_nodes += (uint64_t)covered;
                 *nodes += (uint64_t)covered;

@@ -28,6 +28,9 @@ int b200_launch_sum_rows(cudaStream_t s, const b200_td& src, const b200_td& dst,
 // f32 -> f16/bf16 pack of a strided 2-D/4-D operand into a dense K-major matrix with K padded to kpad (zero filled)
 int b200_launch_pack_rows(cudaStream_t s, const b200_td& src, void* dst, int dst_type, int64_t kpad);
 
+// 16-bit tiled transpose: src [d, L, b2, b3] (unit stride along d) -> dst dense [b3][b2][d rows][Lpad] (row = d index, L contiguous)
+int b200_launch_transpose_f16(cudaStream_t s, const b200_td& src, void* dst, int64_t Lpad);
+
 // ---- norm.cu ---------------------------------------------------------------------------------
 // optional fused affine (w, b: per-channel f32, may be null) and activation (0 none, 1 SiLU)
 int b200_launch_group_norm(cudaStream_t s, const b200_td& src, const b200_td& dst, int n_groups, float eps, const float* w = nullptr,

@@ -551,6 +551,26 @@ __global__ void k_pack_rows(b200_td a, TD* __restrict__ d, int64_t kpad, int64_t
 }
 
 
+// 16-bit tiled transpose through shared memory: out[z][r = d][c = l] = in[z][l][d]
+__global__ void k_transpose_16(const char* __restrict__ src, uint16_t* __restrict__ dst, int D, int L, int64_t Lpad, int64_t nb1, int64_t nb2, int64_t nb3,
+                               int ne2) {
+    __shared__ uint16_t tile[32][34];
+    const int z = blockIdx.z;
+    const int i2 = z % ne2, i3 = z / ne2;
+    const char* sb = src + i2 * nb2 + i3 * nb3;
+    uint16_t* db = dst + (int64_t)z * D * Lpad;
+    const int l0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {          // rows of the source tile: l; columns: d (contiguous)
+        const int l = l0 + k, d = d0 + threadIdx.x;
+        if (l < L && d < D) tile[k][threadIdx.x] = *(const uint16_t*)(sb + (int64_t)l * nb1 + (int64_t)d * 2);
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {          // rows of the destination tile: d; columns: l (contiguous)
+        const int d = d0 + k, l = l0 + threadIdx.x;
+        if (l < L && d < D) db[(int64_t)d * Lpad + l] = tile[threadIdx.x][k];
+    }
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -774,5 +794,15 @@ int b200_launch_pack_rows(cudaStream_t s, const b200_td& a, void* dst, int dst_t
     else if (a.type == GGML_TYPE_BF16 && dst_type == GGML_TYPE_F16) PK(__nv_bfloat16, __half);
     else return -1;
 #undef PK
+    return 1;
+}
+
+
+int b200_launch_transpose_f16(cudaStream_t s, const b200_td& src, void* dst, int64_t Lpad) {
+    const int64_t D = src.ne[0], L = src.ne[1], Z = src.ne[2] * src.ne[3];
+    if (D == 0 || L == 0 || Z == 0) return 0;
+    if (src.nb[0] != 2 || Z > 65535 || (D + 31) / 32 > 65535) return -1;
+    dim3 grid((unsigned)((L + 31) / 32), (unsigned)((D + 31) / 32), (unsigned)Z);
+    k_transpose_16<<<grid, dim3(32, 8), 0, s>>>((const char*)src.data, (uint16_t*)dst, (int)D, (int)L, Lpad, src.nb[1], src.nb[2], src.nb[3], (int)src.ne[2]);
     return 1;
 }
