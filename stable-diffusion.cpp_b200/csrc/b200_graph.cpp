@@ -156,13 +156,7 @@ static bool tma_compatible(const ggml_tensor* t) {
     return true;
 }
 
-struct operand {
-    const void* ptr;
-    int type;
-    int64_t ld;            // row stride, elements
-    int64_t batch_stride;  // dim-2 stride, elements
-    int64_t b3_stride;     // dim-3 stride, elements
-};
+using operand = b200_operand;
 
 // Bring `t` ([K, rows, b2, b3]) into a form the tcgen05 GEMM can read as type `want`: in place when possible,
 // otherwise packed (converted, K padded to 16 bytes) into workspace.  Returns false on allocation failure.
@@ -170,6 +164,13 @@ static bool prepare_operand(b200_context* ctx, const ggml_tensor* t, int want, o
     if ((int)t->type == want && tma_compatible(t)) {
         const int64_t es = fp_size(want);
         *out = operand{t->data, want, (int64_t)t->nb[1] / es, (int64_t)t->nb[2] / es, (int64_t)t->nb[3] / es};
+        return true;
+    }
+    // the same tensor node feeding several contractions (x_norm -> to_q / to_k / to_v, the text context -> 32 k/v projections) is packed
+    // once per graph execution: a ggml tensor node is a value, its buffer is not overwritten before its last consumer has run
+    auto hit = ctx->pack_cache.find(std::make_pair(t, want));
+    if (hit != ctx->pack_cache.end()) {
+        *out = hit->second;
         return true;
     }
     const int64_t es = fp_size(want);
@@ -182,6 +183,7 @@ static bool prepare_operand(b200_context* ctx, const ggml_tensor* t, int want, o
     if (n < 0) return false;
     *launches += n;
     *out = operand{buf, want, kpad, kpad * t->ne[1], kpad * t->ne[1] * t->ne[2]};
+    ctx->pack_cache[std::make_pair(t, want)] = *out;
     return true;
 }
 
@@ -1025,8 +1027,23 @@ static int try_fuse_norm(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, in
     } else {
         float eps;
         memcpy(&eps, nrm->op_params, 4);
+        // consumers that are F16/BF16-weight contractions want this activation rounded to their type (oracle: ggml-cpu.c:1430-1513):
+        // write that copy from the same kernel and hand it to prepare_operand through the pack cache
+        int want = -1;
+        if (last->ne[0] % 8 == 0 && last->ne[2] * last->ne[3] == 1) {
+            for (int u = i + 1; u < g->n_nodes && u < i + 64; ++u) {
+                const ggml_tensor* c = g->nodes[u];
+                if (c->op == GGML_OP_MUL_MAT && c->src[1] == last && (c->src[0]->type == GGML_TYPE_F16 || c->src[0]->type == GGML_TYPE_BF16)) {
+                    want = (int)c->src[0]->type;
+                    break;
+                }
+            }
+        }
+        void* shadow = nullptr;
+        if (want >= 0) shadow = ws_alloc(ctx, (size_t)(ggml_nelements(last) * 2));
         n = b200_launch_norm(ctx->stream, B200_NORM_LAYER, b200_make_td(nrm->src[0]), dst, eps, (const float*)mul->src[1]->data,
-                             (const float*)add->src[1]->data);
+                             (const float*)add->src[1]->data, shadow, want);
+        if (n >= 0 && shadow) ctx->pack_cache[std::make_pair((const ggml_tensor*)last, want)] = operand{shadow, want, last->ne[0], last->ne[0] * last->ne[1], last->ne[0] * last->ne[1]};
     }
     if (n < 0) return n;
     for (int c : chain) fs.done[c] = 1;
@@ -1091,6 +1108,7 @@ static int try_fuse_conv(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, in
 
 static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, uint64_t* launches, uint64_t* nodes) {
     fusion_state fs;
+    ctx->pack_cache.clear();
     const bool fuse = ctx->opt_fusion && cgraph->n_nodes > 1;
     if (fuse) count_uses(cgraph, fs);
     else fs.done.assign((size_t)cgraph->n_nodes, 0);

@@ -5,6 +5,8 @@
 
 #include <string>
 #include <unordered_map>
+#include <utility>
+#include <functional>
 #include <vector>
 
 struct ggml_cgraph;
@@ -15,6 +17,18 @@ struct b200_workspace {
     struct chunk { char* base; size_t size; size_t used; };
     std::vector<chunk> chunks;
     size_t high_water = 0;   // bytes requested during the current graph
+};
+
+// a contraction operand as the tcgen05 GEMM wants it: K-major rows of one element type
+struct b200_operand {
+    const void* ptr;
+    int type;
+    int64_t ld;            // row stride, elements
+    int64_t batch_stride;  // dim-2 stride, elements
+    int64_t b3_stride;     // dim-3 stride, elements
+};
+struct b200_pack_key_hash {
+    size_t operator()(const std::pair<const ggml_tensor*, int>& k) const { return std::hash<const void*>()(k.first) * 31u + (size_t)k.second; }
 };
 
 struct b200_context {
@@ -42,6 +56,8 @@ struct b200_context {
     struct plan { cudaGraphExec_t exec = nullptr; int seen = 0; bool no_capture = false; uint64_t launches = 0, nodes = 0, ws_generation = 0; };
     std::unordered_map<uint64_t, plan> plans;
     uint64_t ws_generation = 0;
+    // per-graph-execution cache of packed (type-converted) contraction operands, keyed by ggml tensor node
+    std::unordered_map<std::pair<const ggml_tensor*, int>, b200_operand, b200_pack_key_hash> pack_cache;
     bool capturing = false, capture_overflow = false;
 
     ~b200_context();

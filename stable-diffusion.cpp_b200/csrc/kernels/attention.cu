@@ -43,6 +43,12 @@ struct FaParams {
     float log2e;
 };
 
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int NATOM, int BLOCK_N> struct FaCfg {
     static constexpr int Q_BYTES = NATOM * BLOCK_M * 128;
     static constexpr int K_STAGE = NATOM * BLOCK_N * 128;
@@ -193,9 +199,10 @@ __global__ void __launch_bounds__(192, 1) k_flash_attn(const __grid_constant__ C
             const int kbase = j * BLOCK_N;
             mbar_wait(&s_full[s], (j >> 1) & 1);
             tc_fence_after();
-            // ---- pass 1: row maximum (log2 domain)
+            // ---- S row: ONE TMEM read into registers (scaled to the log2 domain, mask added, tail keys -> -inf), row maximum
+            float sv[BLOCK_N];
             float mx = -INFINITY;
-#pragma unroll 1
+#pragma unroll
             for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tS + c0, v);
@@ -205,7 +212,9 @@ __global__ void __launch_bounds__(192, 1) k_flash_attn(const __grid_constant__ C
                     const int key = kbase + c0 + i;
                     float t = __uint_as_float(v[i]) * p.scale_log2;
                     if (mrow && key < p.Lk) t += __half2float(mrow[key]) * p.log2e;
-                    if (key < p.Lk) mx = fmaxf(mx, t);
+                    t = key < p.Lk ? t : -INFINITY;
+                    sv[c0 + i] = t;
+                    mx = fmaxf(mx, t);
                 }
             }
             float m_new = fmaxf(m_ref, mx);
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(192, 1) k_flash_attn(const __grid_constant__ C
                 mbar_wait(&pv_done, (j - 1) & 1);
                 tc_fence_after();
                 waited = true;
-                const float alpha = grow ? exp2f(m_ref - m_new) : 1.0f;
+                const float alpha = grow ? fast_exp2(m_ref - m_new) : 1.0f;
                 l *= alpha;
 #pragma unroll 1
                 for (int c0 = 0; c0 < p.dv16; c0 += 16) {
@@ -236,26 +245,13 @@ __global__ void __launch_bounds__(192, 1) k_flash_attn(const __grid_constant__ C
             float lsum = 0.f;
             uint32_t ph[BLOCK_N / 2];   // the whole P row as packed half2, kept in registers until the P buffer is free
 #pragma unroll
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tS + c0, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const int key = kbase + c0 + i;
-                    float t0 = __uint_as_float(v[i]) * p.scale_log2, t1 = __uint_as_float(v[i + 1]) * p.scale_log2;
-                    if (mrow) {
-                        if (key < p.Lk) t0 += __half2float(mrow[key]) * p.log2e;
-                        if (key + 1 < p.Lk) t1 += __half2float(mrow[key + 1]) * p.log2e;
-                    }
-                    const float e0 = key < p.Lk ? exp2f(t0 - m_ref) : 0.f;
-                    const float e1 = key + 1 < p.Lk ? exp2f(t1 - m_ref) : 0.f;
-                    const __half2 hv = __floats2half2_rn(e0, e1);
-                    // accumulate the sum from the ROUNDED probabilities: what the tensor core multiplies is what we normalise by
-                    const float2 f = __half22float2(hv);
-                    lsum += f.x + f.y;
-                    ph[(c0 + i) >> 1] = *(const uint32_t*)&hv;
-                }
+            for (int i = 0; i < BLOCK_N; i += 2) {
+                const float e0 = fast_exp2(sv[i] - m_ref), e1 = fast_exp2(sv[i + 1] - m_ref);   // exp2(-inf) == 0 for masked / tail keys
+                const __half2 hv = __floats2half2_rn(e0, e1);
+                // accumulate the sum from the ROUNDED probabilities: what the tensor core multiplies is what we normalise by
+                const float2 f = __half22float2(hv);
+                lsum += f.x + f.y;
+                ph[i >> 1] = *(const uint32_t*)&hv;
             }
             l += lsum;
             if (!waited) {

@@ -12,6 +12,7 @@
 #include "../b200_ops.h"
 
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <cfloat>
 
 namespace {
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(1024) k_group_norm(const float* __restrict__ x
 // row norms: one CTA per row (ne0 elements, arbitrary row placement, unit stride inside the row)
 // ------------------------------------------------------------------------------------------
 template <int KIND>
-__global__ void k_row_norm(b200_td a, b200_td d, float eps, const float* __restrict__ rw, const float* __restrict__ rb) {
+__global__ void k_row_norm(b200_td a, b200_td d, float eps, const float* __restrict__ rw, const float* __restrict__ rb, void* out16, int out16_bf16) {
     __shared__ float red[32];
     int64_t row = blockIdx.x;
     int64_t i1 = row % a.ne[1], r = row / a.ne[1];
@@ -172,6 +173,10 @@ __global__ void k_row_norm(b200_td a, b200_td d, float eps, const float* __restr
                 float o = (v[k] - mean) * scale;
                 if (rw) o = o * rw[i] + (rb ? rb[i] : 0.f);
                 y[i] = o;
+                if (out16) {
+                    if (out16_bf16) ((__nv_bfloat16*)out16)[row * n + i] = __float2bfloat16_rn(o);
+                    else ((__half*)out16)[row * n + i] = __float2half_rn(o);
+                }
             }
         }
     } else {
@@ -179,6 +184,10 @@ __global__ void k_row_norm(b200_td a, b200_td d, float eps, const float* __restr
             float o = (x[i] - mean) * scale;
             if (rw) o = o * rw[i] + (rb ? rb[i] : 0.f);
             y[i] = o;
+            if (out16) {
+                if (out16_bf16) ((__nv_bfloat16*)out16)[row * n + i] = __float2bfloat16_rn(o);
+                else ((__half*)out16)[row * n + i] = __float2half_rn(o);
+            }
         }
     }
 }
@@ -247,15 +256,17 @@ int b200_launch_group_norm(cudaStream_t s, const b200_td& src, const b200_td& ds
     return 1;
 }
 
-int b200_launch_norm(cudaStream_t s, int kind, const b200_td& src, const b200_td& dst, float eps, const float* w, const float* b) {
+int b200_launch_norm(cudaStream_t s, int kind, const b200_td& src, const b200_td& dst, float eps, const float* w, const float* b, void* out16,
+                     int out16_type) {
+    const int bf = out16_type == GGML_TYPE_BF16 ? 1 : 0;
     int64_t nrows = src.ne[1] * src.ne[2] * src.ne[3];
     if (nrows == 0 || src.ne[0] == 0) return 0;
     int threads = src.ne[0] >= 4096 ? 1024 : (src.ne[0] >= 1024 ? 256 : 128);
     if (nrows > 0x7fffffff) return -1;
     switch (kind) {
-        case B200_NORM_LAYER: k_row_norm<B200_NORM_LAYER><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps, w, b); break;
-        case B200_NORM_RMS: k_row_norm<B200_NORM_RMS><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps, w, b); break;
-        default: k_row_norm<B200_NORM_L2><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps, w, b); break;
+        case B200_NORM_LAYER: k_row_norm<B200_NORM_LAYER><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps, w, b, out16, bf); break;
+        case B200_NORM_RMS: k_row_norm<B200_NORM_RMS><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps, w, b, out16, bf); break;
+        default: k_row_norm<B200_NORM_L2><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps, w, b, out16, bf); break;
     }
     return 1;
 }
