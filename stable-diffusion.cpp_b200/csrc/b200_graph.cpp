@@ -257,6 +257,7 @@ struct mm_fusion {
     float* out = nullptr;         // write here instead of dst->data (same [M, N, b2, b3] layout)
     const float* bias = nullptr;  // f32 vector
     int bias_mode = 0;            // 1: per output row m (Linear bias), 2: per n (conv bias: n == output channel)
+    const float* residual = nullptr;   // same [M, N] layout as out, added last
 };
 
 static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz = nullptr) {
@@ -295,6 +296,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
         g.ldd = dst->nb[1] / 4;
         g.d_batch_stride = dst->nb[2] / 4;
         if (fz && fz->bias) { g.bias = fz->bias; g.bias_mode = fz->bias_mode; }
+        if (fz && fz->residual) { g.residual = fz->residual; g.ldr = g.ldd; }
         int n = launch_tc(ctx, g);
         if (n < 0) {
             // CUDA-core reference kernel (debug option, or shapes the TMA cannot describe)
@@ -315,6 +317,17 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
                 bv.ne[0] = fz->bias_mode == 1 ? M : 1; bv.ne[1] = fz->bias_mode == 2 ? N : 1; bv.ne[2] = 1; bv.ne[3] = 1;
                 bv.nb[0] = 4; bv.nb[1] = 4; bv.nb[2] = bv.nb[3] = 4 * (fz->bias_mode == 1 ? M : N);
                 int r = b200_launch_binary(ctx->stream, B200_ADD, o, bv, o);
+                if (r < 0) return -1;
+                n += r;
+            }
+            if (fz && fz->residual) {
+                b200_td o;
+                o.data = g.D; o.type = GGML_TYPE_F32;
+                o.ne[0] = M; o.ne[1] = N; o.ne[2] = ne12; o.ne[3] = 1;
+                o.nb[0] = 4; o.nb[1] = g.ldd * 4; o.nb[2] = g.d_batch_stride * 4; o.nb[3] = o.nb[2] * ne12;
+                b200_td rv = o;
+                rv.data = (void*)fz->residual;
+                int r = b200_launch_binary(ctx->stream, B200_ADD, o, rv, o);
                 if (r < 0) return -1;
                 n += r;
             }
@@ -791,7 +804,34 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
             }
         }
     }
+    // residual: ... -> ADD(value, r) with r a same-shape tensor that already exists (the ADD is the very next work node, so r was
+    // produced before this MUL_MAT).  Read in the epilogue of the element it is added to, so in-place adds onto r are fine.
+    {
+        const int jr = chain.empty() ? next_node(g, fs, i) : next_node(g, fs, chain.back());
+        const ggml_tensor* curv = chain.empty() ? (const ggml_tensor*)mm : g->nodes[chain.back()];
+        if (jr >= 0) {
+            ggml_tensor* add = g->nodes[jr];
+            if (add->op == GGML_OP_ADD && (add->flags & GGML_TENSOR_FLAG_COMPUTE) && add->type == GGML_TYPE_F32 && ggml_is_contiguous(add) &&
+                ggml_nelements(add) == ggml_nelements(mm) && mm->ne[2] * mm->ne[3] == 1 && !(curv->flags & GGML_TENSOR_FLAG_OUTPUT)) {
+                const ggml_tensor* r = nullptr;
+                const ggml_tensor* val = nullptr;
+                if (order_preserving_view_of(fs, add->src[0], curv)) { val = add->src[0]; r = add->src[1]; }
+                else if (order_preserving_view_of(fs, add->src[1], curv)) { val = add->src[1]; r = add->src[0]; }
+                if (r && r->type == GGML_TYPE_F32 && ggml_is_contiguous(r) && ggml_nelements(r) == ggml_nelements(mm) && ggml_are_same_shape(r, add) &&
+                    (single_use(fs, val) || add->data == curv->data)) {
+                    fz.residual = (const float*)r->data;
+                    fz.out = (float*)add->data;
+                    chain.push_back(jr);
+                }
+            }
+        }
+    }
     if (chain.empty()) return -2;
+    // the fused kernel writes `out` while other CTAs may still be reading the operands: `out` must not live in memory gallocr
+    // recycled from an operand that is dead in graph order (e.g. the im2col matrix) -- run unfused then
+    auto overlaps = [](const void* a, size_t na, const void* b, size_t nb) { return (const char*)a < (const char*)b + nb && (const char*)b < (const char*)a + na; };
+    if (overlaps(fz.out, ggml_nbytes(mm), mm->src[0]->data, ggml_nbytes(mm->src[0])) || overlaps(fz.out, ggml_nbytes(mm), mm->src[1]->data, ggml_nbytes(mm->src[1])))
+        return -2;
     int n = op_mul_mat(ctx, mm, &fz);
     if (n < 0) return n;
     for (int c : chain) fs.done[c] = 1;
@@ -847,6 +887,7 @@ struct conv_match {
     const ggml_tensor* w = nullptr;  // filter [KW,KH,IC,OC] f16
     float* out = nullptr;
     const float* bias = nullptr;
+    const float* residual = nullptr;
     int64_t OW = 0, OH = 0;
     int dil = 1;
 };
@@ -902,6 +943,24 @@ static bool match_conv(const ggml_cgraph* g, const fusion_state& fs, int i, conv
                 m->bias = (const float*)bv->data;
                 m->out = (float*)add->data;
                 m->chain.push_back(k);
+                cur = add;
+                k = next_node(g, fs, k);
+            }
+        }
+    }
+    // residual add (ResBlock skip / transformer residual) read in the conv epilogue
+    if (k >= 0) {
+        const ggml_tensor* add = g->nodes[k];
+        if (add->op == GGML_OP_ADD && (add->flags & GGML_TENSOR_FLAG_COMPUTE) && add->type == GGML_TYPE_F32 && ggml_is_contiguous(add) &&
+            ggml_nelements(add) == ggml_nelements(mm) && !(cur->flags & GGML_TENSOR_FLAG_OUTPUT)) {
+            const ggml_tensor* r = nullptr;
+            const ggml_tensor* val = nullptr;
+            if (order_preserving_view_of(fs, add->src[0], cur)) { val = add->src[0]; r = add->src[1]; }
+            else if (order_preserving_view_of(fs, add->src[1], cur)) { val = add->src[1]; r = add->src[0]; }
+            if (r && r->type == GGML_TYPE_F32 && ggml_is_contiguous(r) && ggml_are_same_shape(r, add) && (single_use(fs, val) || add->data == cur->data)) {
+                m->residual = (const float*)r->data;
+                m->out = (float*)add->data;
+                m->chain.push_back(k);
             }
         }
     }
@@ -942,7 +1001,7 @@ static int emit_conv(b200_context* ctx, const conv_match& m, const conv_prologue
     c.N = N; c.H = m.OH; c.W = m.OW; c.C = C; c.OC = m.w->ne[3];
     c.KH = (int)m.w->ne[1]; c.KW = (int)m.w->ne[0];
     c.dil = m.dil; c.pad = c.dil * (c.KH - 1) / 2;
-    c.D = m.out; c.bias = m.bias;
+    c.D = m.out; c.bias = m.bias; c.residual = m.residual;
     size_t wsb = b200_conv_tc_workspace_bytes(ctx->info, c);
     void* w = wsb ? ws_alloc(ctx, wsb) : nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
