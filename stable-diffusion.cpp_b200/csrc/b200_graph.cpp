@@ -736,6 +736,10 @@ static inline bool single_use(const fusion_state& fs, const ggml_tensor* t) {
     return it != fs.uses.end() && it->second == 1;
 }
 
+static inline bool tensors_overlap(const void* a, size_t na, const void* b, size_t nb) {
+    return (const char*)a < (const char*)b + nb && (const char*)b < (const char*)a + na;
+}
+
 static inline bool is_f32_vec(const ggml_tensor* t, int64_t n) {
     return t && t->type == GGML_TYPE_F32 && ggml_is_contiguous(t) && ggml_nelements(t) == n;
 }
@@ -1077,6 +1081,9 @@ static int try_fuse_norm(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, in
             if (ctx->capture_overflow) return -1;
         }
     }
+    // the fused kernel writes `last` while reading the norm's input: identical placement is fine (each CTA owns its group / row),
+    // a partial overlap (recycled memory at another offset) is not
+    if (last->data != nrm->src[0]->data && tensors_overlap(last->data, ggml_nbytes(last), nrm->src[0]->data, ggml_nbytes(nrm->src[0]))) return -2;
     b200_td dst = b200_make_td(last);
     if (group) {
         float eps;
@@ -1128,6 +1135,9 @@ static int try_fuse_cont_cast(b200_context* ctx, ggml_cgraph* g, fusion_state& f
     if (!order_preserving_view_of(fs, cp->src[0], c)) return -2;
     if (cp->src[0] != c && !single_use(fs, cp->src[0])) return -2;
     if (((uintptr_t)src->data & 15) || (src->nb[1] & 15) || (src->nb[2] & 15) || (src->nb[3] & 15) || ((uintptr_t)dst->data & 15)) return -2;
+    // gallocr may have placed the cast's destination in the memory of the CONT's source (dead after the CONT in graph order):
+    // a single pass that reads one while writing the other would race
+    if (tensors_overlap(dst->data, ggml_nbytes(dst), src->data, ggml_nbytes(src))) return -2;
     int n = b200_launch_pack_rows(ctx->stream, b200_make_td(src), dst->data, (int)dst->type, c->ne[0]);
     if (n < 0) return -2;
     fs.done[j] = 1;
