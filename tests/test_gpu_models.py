@@ -61,16 +61,26 @@ def test_sampler_scalars_bit_exact_and_latent_close(b200):
 
 @pytest.mark.parametrize("fa", [0, 1])
 def test_sd15_unet_full_size_vs_live_cpu(b200, fa):
-    """BASELINE config 1/2 shape: SD1.5 UNet, latent 64x64x4, context 77x768, F16 weights; CPU forward takes seconds."""
+    """BASELINE config 1/2 shape: SD1.5 UNet, latent 64x64x4, context 77x768, F16 weights; CPU forward takes seconds.
+    The clean gate is the reference's default (MUL_MAT + SOFT_MAX attention) graph on the CPU: both of our graph variants must match
+    it.  The CPU's own flash-attention path accumulates P.V in f16 for these head sizes (ggml-cpu/ops.cpp:8620-8633) and sits
+    1.8e-2 away from the CPU's default graph, so against it only the oracle's noise floor can be asserted."""
     h, dev = b200
     x = h.randn(42, (1, 4, 64, 64)); ctx = h.randn(43, (1, 77, 768)); t = np.array([999.0], np.float32)
-    outs = {}
-    for d in (dev, "CPU"):
-        m = h.model(d, "sd15_unet", "f16", fa, 1234, 0)
-        outs[d], _ = m.forward(x, t, ctx)
+    m = h.model(dev, "sd15_unet", "f16", fa, 1234, 0)
+    ours, _ = m.forward(x, t, ctx)
+    m.close()
+    m = h.model("CPU", "sd15_unet", "f16", 0, 1234, 0)
+    cpu_default, _ = m.forward(x, t, ctx)
+    m.close()
+    r = rel(ours, cpu_default)
+    assert np.isfinite(ours).all() and r < 3e-3, f"vs CPU default graph: rel_l2 {r:.2e}"
+    if fa == 1:
+        m = h.model("CPU", "sd15_unet", "f16", 1, 1234, 0)
+        cpu_fa, _ = m.forward(x, t, ctx)
         m.close()
-    r = rel(outs[dev], outs["CPU"])
-    assert r < (3e-3 if fa == 0 else 2.5e-2), f"rel_l2 {r:.2e}"
+        noise = rel(cpu_fa, cpu_default)            # the oracle against itself
+        assert rel(ours, cpu_fa) < noise + 3e-3 + 3e-2, f"vs CPU FA graph: {rel(ours, cpu_fa):.2e} (oracle FA-vs-default {noise:.2e})"
 
 
 def test_no_silent_fallback_stats(b200):
