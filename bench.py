@@ -160,7 +160,6 @@ def run_b200(args):
     exchange = None
     coll_ms = [0.0]
     if world > 1:
-        pair = dist.new_group(ranks=[2 * (rank // 2), 2 * (rank // 2) + 1]) if world > 2 else None
         groups = [dist.new_group(ranks=[2 * i, 2 * i + 1]) for i in range(world // 2)] if world > 2 else [None]
         grp = groups[rank // 2] if world > 2 else None
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
