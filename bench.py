@@ -218,7 +218,8 @@ def run_b200(args):
         try:
             m.set_option("kernel_timing", 1)
             k0 = m.stats()
-            run(2)
+            # rank-0-local pass (no collective: the other ranks are not in this branch): 2 full CFG steps on this GPU alone
+            m.sample(x, cond, uncond, steps=2, cfg_scale=CFG_SCALE, eta=ETA, role=-1, exchange=None)
             k1 = m.stats()
             m.set_option("kernel_timing", 0)
             gl = k1["tc_gemm_launches"] - k0["tc_gemm_launches"]
