@@ -64,48 +64,62 @@ __global__ void __launch_bounds__(1024) k_gn_stats(const float* __restrict__ x, 
     if (threadIdx.x == 0) stats[(int64_t)n * G + g] = make_float2(mean, 1.0f / sqrtf(var + eps));
 }
 
-// grid (ceil(OH*OW / 32), C / 64, N), block (32, 8)
+// grid (ceil(OH*OW / 64), C / 64, N), block 256: a 64-channel x 64-pixel tile through shared memory.
+// Load: 16 lanes x float4 cover 64 consecutive pixels of one channel (coalesced 256 B), per-channel norm/affine constants are
+// fetched once per channel per thread.  Store: one warp writes one pixel's 64 channels = 128 contiguous bytes of the NHWC row.
+template <int UP>
 __global__ void __launch_bounds__(256) k_to_nhwc_f16(const float* __restrict__ x, __half* __restrict__ out, const float2* __restrict__ stats,
                                                      const float* __restrict__ gw, const float* __restrict__ gb, int C, int H, int W, int OH,
-                                                     int OW, int up, int cpg, int G, int act) {
-    __shared__ float tile[64][33];
+                                                     int OW, int cpg, int G, int act, int vec_ok) {
+    __shared__ float tile[64][65];
     const int n = blockIdx.z;
     const int c0 = blockIdx.y * 64;
-    const int p0 = blockIdx.x * 32;
-    const int tx = threadIdx.x, ty = threadIdx.y;
     const int64_t OHW = (int64_t)OH * OW;
-    // ---- load: tx runs over 32 consecutive output pixels (coalesced along W), ty over channels
-    const int64_t pix = (int64_t)p0 + tx;
-    int64_t src_off = 0;
-    const bool pvalid = pix < OHW;
-    if (pvalid) {
-        const int oy = (int)(pix / OW), ox = (int)(pix - (int64_t)oy * OW);
-        src_off = (int64_t)(oy / up) * W + (ox / up);
-    }
+    const int64_t p0 = (int64_t)blockIdx.x * 64;
+    const int t = threadIdx.x;
+    const int px4 = (t & 15) * 4;          // first of 4 consecutive output pixels handled by this thread
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int c = c0 + ty + k * 8;
-        float v = 0.f;
-        if (pvalid && c < C) {
-            v = x[((int64_t)n * C + c) * H * W + src_off];
-            if (stats) {
-                const float2 st = stats[(int64_t)n * G + c / cpg];
-                v = (v - st.x) * st.y;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int cl = pass * 16 + (t >> 4);
+        const int c = c0 + cl;
+        float mean = 0.f, rstd = 1.f, w = 1.f, b = 0.f;
+        if (stats) { const float2 st = stats[(int64_t)n * G + c / cpg]; mean = st.x; rstd = st.y; }
+        if (gw) { w = gw[c]; b = gb ? gb[c] : 0.f; }
+        const float* xc = x + ((int64_t)n * C + c) * H * W;
+        float v[4];
+        const int64_t p = p0 + px4;
+        if (UP == 1 && vec_ok && p + 3 < OHW) {
+            const float4 q = *(const float4*)(xc + p);     // OHW == H*W, 16-byte aligned: p % 4 == 0 and channel planes are multiples of 4 floats
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int64_t pp = p + k;
+                if (pp < OHW) {
+                    const int oy = (int)(pp / OW), ox = (int)(pp - (int64_t)oy * OW);
+                    v[k] = xc[(int64_t)(oy / UP) * W + (ox / UP)];
+                } else {
+                    v[k] = 0.f;
+                }
             }
-            if (gw) v = v * gw[c] + (gb ? gb[c] : 0.f);
-            if (act == 1) v = v / (1.0f + expf(-v));
         }
-        tile[ty + k * 8][tx] = v;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float o = (v[k] - mean) * rstd;
+            o = o * w + b;
+            if (act == 1) o = o / (1.0f + expf(-o));
+            tile[cl][px4 + k] = o;
+        }
     }
     __syncthreads();
-    // ---- store: tx runs over 32 channel pairs (64 channels = 128 contiguous bytes per pixel), ty over pixels
+    const int warp = t >> 5, lane = t & 31;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int pl = ty + k * 8;
-        const int64_t p = (int64_t)p0 + pl;
-        if (p < OHW && c0 + 2 * tx + 1 < C + 1) {
-            __half2 hv = __floats2half2_rn(tile[2 * tx][pl], tile[2 * tx + 1][pl]);
-            *(__half2*)(out + ((int64_t)n * OHW + p) * C + c0 + 2 * tx) = hv;
+    for (int k = 0; k < 8; ++k) {
+        const int pl = warp * 8 + k;
+        const int64_t p = p0 + pl;
+        if (p < OHW) {
+            const __half2 hv = __floats2half2_rn(tile[2 * lane][pl], tile[2 * lane + 1][pl]);
+            *(__half2*)(out + ((int64_t)n * OHW + p) * C + c0 + 2 * lane) = hv;
         }
     }
 }
@@ -136,10 +150,13 @@ int b200_launch_to_nhwc_f16(cudaStream_t s, const float* x, void* out, int64_t N
     if (C % 64 != 0) return -1;
     const int64_t OH = H * up, OW = W * up;
     const int cpg = n_groups > 0 ? (int)((C + n_groups - 1) / n_groups) : 1;
-    dim3 grid((unsigned)((OH * OW + 31) / 32), (unsigned)(C / 64), (unsigned)N);
-    if (grid.y > 65535 || N > 65535) return -1;
-    k_to_nhwc_f16<<<grid, dim3(32, 8), 0, s>>>(x, (__half*)out, (const float2*)stats, gw, gb, (int)C, (int)H, (int)W, (int)OH, (int)OW, up, cpg, n_groups,
-                                               act);
+    dim3 grid((unsigned)((OH * OW + 63) / 64), (unsigned)(C / 64), (unsigned)N);
+    if (grid.y > 65535 || N > 65535 || (up != 1 && up != 2)) return -1;
+    const int vec_ok = (((uintptr_t)x & 15) == 0 && ((H * W) & 3) == 0) ? 1 : 0;
+    if (up == 1)
+        k_to_nhwc_f16<1><<<grid, 256, 0, s>>>(x, (__half*)out, (const float2*)stats, gw, gb, (int)C, (int)H, (int)W, (int)OH, (int)OW, cpg, n_groups, act, vec_ok);
+    else
+        k_to_nhwc_f16<2><<<grid, 256, 0, s>>>(x, (__half*)out, (const float2*)stats, gw, gb, (int)C, (int)H, (int)W, (int)OH, (int)OW, cpg, n_groups, act, vec_ok);
     return 1;
 }
 

@@ -223,13 +223,15 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
                         if (mvalid && c0 + j < ncols) dptr[(int64_t)(c0 + j) * p.ldd] = v;
                     }
                 } else {
+                    // residual: issue all 32 loads before the first store (the compiler must assume rptr may alias dptr -- it often
+                    // does, for in-place adds -- and would otherwise serialise load -> store -> load)
+                    float rr[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) rr[j] = (mvalid && c0 + j < ncols) ? rptr[(int64_t)(c0 + j) * p.ldr] : 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        float v = __uint_as_float(r[j]) + bias_m + __shfl_sync(0xffffffffu, bn, j);
-                        if (mvalid && c0 + j < ncols) {
-                            v += rptr[(int64_t)(c0 + j) * p.ldr];
-                            dptr[(int64_t)(c0 + j) * p.ldd] = v;
-                        }
+                        const float v = __uint_as_float(r[j]) + bias_m + __shfl_sync(0xffffffffu, bn, j) + rr[j];
+                        if (mvalid && c0 + j < ncols) dptr[(int64_t)(c0 + j) * p.ldd] = v;
                     }
                 }
             }
