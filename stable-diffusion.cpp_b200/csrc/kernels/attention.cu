@@ -16,6 +16,7 @@
 //
 // Roofline: tensor pipe, 4 * Lq * Lk * d flop per head (QK^T and PV).  HBM traffic is Q + K + V + O only.
 #include "../b200_ops.h"
+#include "b200_launch.cuh"
 #include "sm100_ptx.cuh"
 
 #include <cuda_fp16.h>
@@ -98,6 +99,8 @@ __global__ void __launch_bounds__(192, 1) k_flash_attn(const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
     const uint32_t tmem_S0 = tmem_base, tmem_O = tmem_base + 2 * BLOCK_N;
+    pdl_wait();                 // on-chip setup above overlaps the predecessor's tail (b200_launch.cuh)
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
@@ -318,7 +321,7 @@ int launch_fa(cudaStream_t s, dim3 grid, const CUtensorMap& tk, const CUtensorMa
         if (cudaFuncSetAttribute(k_flash_attn<NATOM, BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) return -1;
         configured[dev] = true;
     }
-    k_flash_attn<NATOM, BLOCK_N><<<grid, 192, C::SMEM, s>>>(tk, tv, p);
+    b200_launch(k_flash_attn<NATOM, BLOCK_N>, dim3(grid), dim3(192), C::SMEM, s, tk, tv, p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -10,6 +10,7 @@
 // All three are HBM/L2 bound: the activation is read once (twice from L2 when statistics are needed) and written once
 // at half width; the 0.7 GB/forward of materialised im2col columns of the unfused graph disappear.
 #include "../b200_ops.h"
+#include "b200_launch.cuh"
 
 #include <cuda_fp16.h>
 
@@ -35,6 +36,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 
 __global__ void __launch_bounds__(1024) k_gn_stats(const float* __restrict__ x, float2* __restrict__ stats, int64_t inner, int C, int cpg, int G,
                                                    float eps) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float red[32];
     const int g = blockIdx.x, n = blockIdx.y;
     const int c0 = g * cpg, c1 = min(c0 + cpg, C);
@@ -71,6 +74,8 @@ template <int UP>
 __global__ void __launch_bounds__(256) k_to_nhwc_f16(const float* __restrict__ x, __half* __restrict__ out, const float2* __restrict__ stats,
                                                      const float* __restrict__ gw, const float* __restrict__ gb, int C, int H, int W, int OH,
                                                      int OW, int cpg, int G, int act, int vec_ok) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float tile[64][65];
     const int n = blockIdx.z;
     const int c0 = blockIdx.y * 64;
@@ -125,6 +130,8 @@ __global__ void __launch_bounds__(256) k_to_nhwc_f16(const float* __restrict__ x
 }
 
 __global__ void k_pack_conv_weight(const __half* __restrict__ w, __half* __restrict__ out, int KW, int KH, int IC, int64_t total) {
+    pdl_wait();
+    pdl_launch_dependents();
     // out[((oc * KH + kh) * KW + kw) * IC + ic] = w[((oc * IC + ic) * KH + kh) * KW + kw]
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i;
@@ -141,7 +148,7 @@ __global__ void k_pack_conv_weight(const __half* __restrict__ w, __half* __restr
 int b200_launch_gn_stats(cudaStream_t s, const float* x, float* stats, int64_t N, int64_t C, int64_t inner, int n_groups, float eps) {
     const int cpg = (int)((C + n_groups - 1) / n_groups);
     dim3 grid((unsigned)n_groups, (unsigned)N);
-    k_gn_stats<<<grid, 1024, 0, s>>>(x, (float2*)stats, inner, (int)C, cpg, n_groups, eps);
+    b200_launch(k_gn_stats, dim3(grid), dim3(1024), 0, s, x, (float2*)stats, inner, (int)C, cpg, n_groups, eps);
     return 1;
 }
 
@@ -154,9 +161,9 @@ int b200_launch_to_nhwc_f16(cudaStream_t s, const float* x, void* out, int64_t N
     if (grid.y > 65535 || N > 65535 || (up != 1 && up != 2)) return -1;
     const int vec_ok = (((uintptr_t)x & 15) == 0 && ((H * W) & 3) == 0) ? 1 : 0;
     if (up == 1)
-        k_to_nhwc_f16<1><<<grid, 256, 0, s>>>(x, (__half*)out, (const float2*)stats, gw, gb, (int)C, (int)H, (int)W, (int)OH, (int)OW, cpg, n_groups, act, vec_ok);
+        b200_launch(k_to_nhwc_f16<1>, dim3(grid), dim3(256), 0, s, x, (__half*)out, (const float2*)stats, gw, gb, (int)C, (int)H, (int)W, (int)OH, (int)OW, cpg, n_groups, act, vec_ok);
     else
-        k_to_nhwc_f16<2><<<grid, 256, 0, s>>>(x, (__half*)out, (const float2*)stats, gw, gb, (int)C, (int)H, (int)W, (int)OH, (int)OW, cpg, n_groups, act, vec_ok);
+        b200_launch(k_to_nhwc_f16<2>, dim3(grid), dim3(256), 0, s, x, (__half*)out, (const float2*)stats, gw, gb, (int)C, (int)H, (int)W, (int)OH, (int)OW, cpg, n_groups, act, vec_ok);
     return 1;
 }
 
@@ -164,6 +171,6 @@ int b200_launch_pack_conv_weight(cudaStream_t s, const void* w, void* out, int K
     const int64_t total = (int64_t)KW * KH * IC * OC;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    k_pack_conv_weight<<<(unsigned)blocks, 256, 0, s>>>((const __half*)w, (__half*)out, KW, KH, (int)IC, total);
+    b200_launch(k_pack_conv_weight, dim3((unsigned)blocks), dim3(256), 0, s, (const __half*)w, (__half*)out, KW, KH, (int)IC, total);
     return 1;
 }

@@ -9,6 +9,7 @@
 // count with 16-byte accesses on the contiguous fast paths; the strided generic paths exist for
 // coverage (test-backend-ops) and are replaced by fused producers/consumers in whole-model graphs.
 #include "../b200_ops.h"
+#include "b200_launch.cuh"
 
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -86,6 +87,8 @@ __device__ __forceinline__ void rows4_decode(const rows4& r, uint32_t idx, uint3
 template <int OP>
 __global__ void k_binary_rows4(const char* __restrict__ a, strides3 sa, const char* __restrict__ b, strides3 sb, char* __restrict__ d, strides3 sd,
                                rows4 r) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < r.total; idx += gridDim.x * blockDim.x) {
         uint32_t c, i1, i2, i3;
         rows4_decode(r, idx, c, i1, i2, i3);
@@ -97,6 +100,8 @@ __global__ void k_binary_rows4(const char* __restrict__ a, strides3 sa, const ch
 }
 
 __global__ void k_copy_rows4(const char* __restrict__ a, strides3 sa, char* __restrict__ d, strides3 sd, rows4 r) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < r.total; idx += gridDim.x * blockDim.x) {
         uint32_t c, i1, i2, i3;
         rows4_decode(r, idx, c, i1, i2, i3);
@@ -108,6 +113,8 @@ __global__ void k_copy_rows4(const char* __restrict__ a, strides3 sa, char* __re
 // concat along dim >= 1 of row-contiguous 4-byte tensors: destination row -> which source, then a 16-byte copy
 __global__ void k_concat_rows4(const char* __restrict__ a, strides3 sa, const char* __restrict__ b, strides3 sb, char* __restrict__ d, strides3 sd,
                                rows4 r, int dim, uint32_t a_ne_dim) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < r.total; idx += gridDim.x * blockDim.x) {
         uint32_t c, i[4];
         rows4_decode(r, idx, c, i[1], i[2], i[3]);
@@ -122,6 +129,8 @@ __global__ void k_concat_rows4(const char* __restrict__ a, strides3 sa, const ch
 // f32 rows -> dense f16/bf16 [rows][kpad], 8 outputs (16 bytes) per thread; rows unit-stride and 16-byte aligned
 template <typename TD>
 __global__ void k_pack_rows8(const char* __restrict__ a, strides3 sa, TD* __restrict__ d, rows4 r /* cpr = kpad/8 */, uint32_t K) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < r.total; idx += gridDim.x * blockDim.x) {
         uint32_t c, i1, i2, i3;
         rows4_decode(r, idx, c, i1, i2, i3);
@@ -157,6 +166,8 @@ inline bool same_shape(const b200_td& a, const b200_td& b) { return a.ne[0] == b
 // generic: any strides, src1 broadcast by modulo (ggml_can_repeat(src1, src0))
 template <int OP, typename TA, typename TB, typename TD>
 __global__ void k_binary_generic(b200_td a, b200_td b, b200_td d, int64_t n) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t i0 = i % d.ne[0], r = i / d.ne[0];
         int64_t i1 = r % d.ne[1];
@@ -174,6 +185,8 @@ __global__ void k_binary_generic(b200_td a, b200_td b, b200_td d, int64_t n) {
 template <int OP>
 __global__ void k_binary_f32_vec4(const float4* __restrict__ a, const float* __restrict__ b, float4* __restrict__ d, int64_t n4,
                                   int mode, int64_t ne0, int64_t inner, int64_t C) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 x = a[i], y;
         if (mode == 0) {
@@ -201,7 +214,7 @@ int launch_binary_op(cudaStream_t s, const b200_td& a, const b200_td& b, const b
         else if (nb_el == b.ne[0] && b.ne[0] == d.ne[0] && d.ne[0] % 4 == 0) mode = 1;
         else if (nb_el == b.ne[2] && b.ne[2] == d.ne[2] && (d.ne[0] * d.ne[1]) % 4 == 0) mode = 2;
         if (mode >= 0) {
-            k_binary_f32_vec4<OP><<<grid_for(n / 4), kThreads, 0, s>>>((const float4*)a.data, (const float*)b.data, (float4*)d.data, n / 4, mode,
+            b200_launch(k_binary_f32_vec4<OP>, dim3(grid_for(n / 4)), dim3(kThreads), 0, s, (const float4*)a.data, (const float*)b.data, (float4*)d.data, n / 4, mode,
                                                                         d.ne[0], d.ne[0] * d.ne[1], d.ne[2]);
             return 1;
         }
@@ -209,12 +222,12 @@ int launch_binary_op(cudaStream_t s, const b200_td& a, const b200_td& b, const b
     if (f32 && same_shape(a, d) && same_shape(b, d) && rows4_ok(a) && rows4_ok(b) && rows4_ok(d)) {
         rows4 r;
         if (make_rows4(d, &r)) {
-            k_binary_rows4<OP><<<grid_for(r.total), kThreads, 0, s>>>((const char*)a.data, st3(a), (const char*)b.data, st3(b), (char*)d.data, st3(d), r);
+            b200_launch(k_binary_rows4<OP>, dim3(grid_for(r.total)), dim3(kThreads), 0, s, (const char*)a.data, st3(a), (const char*)b.data, st3(b), (char*)d.data, st3(d), r);
             return 1;
         }
     }
     unsigned g = grid_for(n);
-#define BIN_CASE(TA, TB, TD) k_binary_generic<OP, TA, TB, TD><<<g, kThreads, 0, s>>>(a, b, d, n)
+#define BIN_CASE(TA, TB, TD) b200_launch(k_binary_generic<OP, TA, TB, TD>, dim3(g), dim3(kThreads), 0, s, a, b, d, n)
     if (f32) BIN_CASE(float, float, float);
     else if (a.type == GGML_TYPE_F16 && b.type == GGML_TYPE_F16 && d.type == GGML_TYPE_F16) BIN_CASE(__half, __half, __half);
     else if (a.type == GGML_TYPE_F32 && b.type == GGML_TYPE_F16 && d.type == GGML_TYPE_F32) BIN_CASE(float, __half, float);
@@ -269,6 +282,8 @@ __device__ __forceinline__ float apply_unary(int op, float x, float p0, float p1
 
 template <typename TS, typename TD>
 __global__ void k_unary_generic(b200_td a, b200_td d, int64_t n, UnaryParams p) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t i0 = i % d.ne[0], r = i / d.ne[0];
         int64_t i1 = r % d.ne[1];
@@ -281,6 +296,8 @@ __global__ void k_unary_generic(b200_td a, b200_td d, int64_t n, UnaryParams p) 
 }
 
 __global__ void k_unary_f32_vec4(const float4* __restrict__ a, float4* __restrict__ d, int64_t n4, UnaryParams p) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 x = a[i];
         d[i] = make_float4(apply_unary(p.op, x.x, p.p0, p.p1), apply_unary(p.op, x.y, p.p0, p.p1), apply_unary(p.op, x.z, p.p0, p.p1),
@@ -293,12 +310,12 @@ int launch_unary_impl(cudaStream_t s, const b200_td& a, const b200_td& d, UnaryP
     if (n == 0) return 0;
     if (a.type == GGML_TYPE_F32 && d.type == GGML_TYPE_F32 && td_contiguous(a, 4) && td_contiguous(d, 4) && n % 4 == 0 &&
         (uintptr_t)a.data % 16 == 0 && (uintptr_t)d.data % 16 == 0) {
-        k_unary_f32_vec4<<<grid_for(n / 4), kThreads, 0, s>>>((const float4*)a.data, (float4*)d.data, n / 4, p);
+        b200_launch(k_unary_f32_vec4, dim3(grid_for(n / 4)), dim3(kThreads), 0, s, (const float4*)a.data, (float4*)d.data, n / 4, p);
         return 1;
     }
     unsigned g = grid_for(n);
-    if (a.type == GGML_TYPE_F32 && d.type == GGML_TYPE_F32) k_unary_generic<float, float><<<g, kThreads, 0, s>>>(a, d, n, p);
-    else if (a.type == GGML_TYPE_F16 && d.type == GGML_TYPE_F16) k_unary_generic<__half, __half><<<g, kThreads, 0, s>>>(a, d, n, p);
+    if (a.type == GGML_TYPE_F32 && d.type == GGML_TYPE_F32) b200_launch(k_unary_generic<float, float>, dim3(g), dim3(kThreads), 0, s, a, d, n, p);
+    else if (a.type == GGML_TYPE_F16 && d.type == GGML_TYPE_F16) b200_launch(k_unary_generic<__half, __half>, dim3(g), dim3(kThreads), 0, s, a, d, n, p);
     else return -1;
     return 1;
 }
@@ -308,6 +325,8 @@ int launch_unary_impl(cudaStream_t s, const b200_td& a, const b200_td& d, UnaryP
 // ---------------------------------------------------------------------------------------------
 template <typename TS, typename TD>
 __global__ void k_copy_generic(b200_td a, b200_td d, int64_t n) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i;
         int64_t a0 = r % a.ne[0]; r /= a.ne[0];
@@ -324,7 +343,9 @@ __global__ void k_copy_generic(b200_td a, b200_td d, int64_t n) {
 }
 
 template <typename T>
-__global__ void k_copy_raw(b200_td a, b200_td d, int64_t n) {   // same-size raw element copy (ints, same float types)
+__global__ void k_copy_raw(b200_td a, b200_td d, int64_t n) {
+    pdl_wait();
+    pdl_launch_dependents();   // same-size raw element copy (ints, same float types)
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i;
         int64_t a0 = r % a.ne[0]; r /= a.ne[0];
@@ -343,6 +364,8 @@ __global__ void k_copy_raw(b200_td a, b200_td d, int64_t n) {   // same-size raw
 // Treats the tensor as batches of a 2-D problem: rows = dim ax (contiguous in src), cols = dim 0 (contiguous in dst).
 // Requirements: src.nb[ax] == 4; shapes identical; the other two dims are looped over by blockIdx.z.
 __global__ void k_transpose_f32(b200_td a, b200_td d, int ax, int o1, int o2) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float tile[32][33];
     int64_t z = blockIdx.z;
     int64_t j1 = z % d.ne[o1], j2 = z / d.ne[o1];
@@ -362,11 +385,15 @@ __global__ void k_transpose_f32(b200_td a, b200_td d, int ax, int o1, int o2) {
 }
 
 __global__ void k_copy_contig16(const uint4* __restrict__ a, uint4* __restrict__ d, int64_t n16) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) d[i] = a[i];
 }
 
 template <typename TD>
 __global__ void k_cvt_f32_contig(const float4* __restrict__ a, TD* __restrict__ d, int64_t n4) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 x = a[i];
         stf<TD>(d + 4 * i + 0, x.x); stf<TD>(d + 4 * i + 1, x.y); stf<TD>(d + 4 * i + 2, x.z); stf<TD>(d + 4 * i + 3, x.w);
@@ -378,6 +405,8 @@ __global__ void k_cvt_f32_contig(const float4* __restrict__ a, TD* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void k_concat(b200_td a, b200_td b, b200_td d, int dim, int64_t n) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t idx[4];
         int64_t r = i;
@@ -394,6 +423,8 @@ __global__ void k_concat(b200_td a, b200_td b, b200_td d, int dim, int64_t n) {
 
 template <typename T>
 __global__ void k_repeat(b200_td a, b200_td d, int64_t n) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i;
         int64_t i0 = r % d.ne[0]; r /= d.ne[0];
@@ -406,6 +437,8 @@ __global__ void k_repeat(b200_td a, b200_td d, int64_t n) {
 
 struct PadParams { int32_t lp[4], rp[4]; int circular; };
 __global__ void k_pad_f32(b200_td a, b200_td d, PadParams p, int64_t n) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t idx[4];
         int64_t r = i;
@@ -431,6 +464,8 @@ __global__ void k_pad_f32(b200_td a, b200_td d, PadParams p, int64_t n) {
 
 // mode 0 nearest, 1 bilinear (align_corners flag folded into sf/pixel_offset by the host like ops.cpp:7848-7860)
 __global__ void k_upscale_f32(b200_td a, b200_td d, int mode, float sf0, float sf1, float sf2, float sf3, float pixel_offset, int64_t n) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i;
         int64_t i0 = r % d.ne[0]; r /= d.ne[0];
@@ -464,6 +499,8 @@ __global__ void k_upscale_f32(b200_td a, b200_td d, int mode, float sf0, float s
 }
 
 __global__ void k_timestep_embedding(const float* __restrict__ t, char* dst, int64_t nb1, int dim, int max_period, int64_t n_t) {
+    pdl_wait();
+    pdl_launch_dependents();
     int half = dim / 2;
     int64_t i = blockIdx.y;
     if (i >= n_t) return;
@@ -481,6 +518,8 @@ __global__ void k_timestep_embedding(const float* __restrict__ t, char* dst, int
 
 template <typename TS>
 __global__ void k_get_rows(b200_td src, b200_td idx, b200_td d, int64_t n) {
+    pdl_wait();
+    pdl_launch_dependents();
     // dst[i0, r, b2, b3] = src[i0, idx[r, b2, b3], b2, b3]
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i;
@@ -494,14 +533,20 @@ __global__ void k_get_rows(b200_td src, b200_td idx, b200_td d, int64_t n) {
 }
 
 __global__ void k_arange(float* d, int64_t n, float start, float step) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = start + step * (float)i;
 }
 __global__ void k_fill(float* d, int64_t n, float v) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = v;
 }
 
 // GLU family: dst[i0] = act(a[i0]) * b[i0]   (a/b are the halves of one tensor when b == nullptr on the host side)
 __global__ void k_glu_f32(const char* a, const char* b, char* d, int64_t nc, int64_t nrows, int64_t a_nb1, int64_t b_nb1, int64_t d_nb1, int glu_op) {
+    pdl_wait();
+    pdl_launch_dependents();
     int64_t n = nc * nrows;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t c = i % nc, r = i / nc;
@@ -522,6 +567,8 @@ __global__ void k_glu_f32(const char* a, const char* b, char* d, int64_t nc, int
 
 // one warp per row
 __global__ void k_sum_rows(b200_td a, b200_td d, int64_t nrows, bool mean) {
+    pdl_wait();
+    pdl_launch_dependents();
     int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     if (row >= nrows) return;
     int lane = threadIdx.x & 31;
@@ -537,6 +584,8 @@ __global__ void k_sum_rows(b200_td a, b200_td d, int64_t nrows, bool mean) {
 // pack rows: src logical [K, R1, R2, R3] (any strides, unit stride along K not required) -> dense [R][kpad] of TD, zero padded
 template <typename TS, typename TD>
 __global__ void k_pack_rows(b200_td a, TD* __restrict__ d, int64_t kpad, int64_t nrows) {
+    pdl_wait();
+    pdl_launch_dependents();
     int64_t n = nrows * kpad;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t k = i % kpad, row = i / kpad;
@@ -554,6 +603,8 @@ __global__ void k_pack_rows(b200_td a, TD* __restrict__ d, int64_t kpad, int64_t
 // 16-bit tiled transpose through shared memory: out[z][r = d][c = l] = in[z][l][d]
 __global__ void k_transpose_16(const char* __restrict__ src, uint16_t* __restrict__ dst, int D, int L, int64_t Lpad, int64_t nb1, int64_t nb2, int64_t nb3,
                                int ne2) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ uint16_t tile[32][34];
     const int z = blockIdx.z;
     const int i2 = z % ne2, i3 = z / ne2;
@@ -603,15 +654,15 @@ int b200_launch_copy(cudaStream_t s, const b200_td& a, const b200_td& d) {
     if (a.type == d.type && ca && cd) {
         int64_t bytes = n * es;
         if (bytes % 16 == 0 && (uintptr_t)a.data % 16 == 0 && (uintptr_t)d.data % 16 == 0) {
-            k_copy_contig16<<<grid_for(bytes / 16), kThreads, 0, s>>>((const uint4*)a.data, (uint4*)d.data, bytes / 16);
+            b200_launch(k_copy_contig16, dim3(grid_for(bytes / 16)), dim3(kThreads), 0, s, (const uint4*)a.data, (uint4*)d.data, bytes / 16);
         } else {
             cudaMemcpyAsync(d.data, a.data, bytes, cudaMemcpyDeviceToDevice, s);
         }
         return 1;
     }
     if (a.type == GGML_TYPE_F32 && ca && cd && n % 4 == 0 && (uintptr_t)a.data % 16 == 0 && (d.type == GGML_TYPE_F16 || d.type == GGML_TYPE_BF16)) {
-        if (d.type == GGML_TYPE_F16) k_cvt_f32_contig<__half><<<grid_for(n / 4), kThreads, 0, s>>>((const float4*)a.data, (__half*)d.data, n / 4);
-        else k_cvt_f32_contig<__nv_bfloat16><<<grid_for(n / 4), kThreads, 0, s>>>((const float4*)a.data, (__nv_bfloat16*)d.data, n / 4);
+        if (d.type == GGML_TYPE_F16) b200_launch(k_cvt_f32_contig<__half>, dim3(grid_for(n / 4)), dim3(kThreads), 0, s, (const float4*)a.data, (__half*)d.data, n / 4);
+        else b200_launch(k_cvt_f32_contig<__nv_bfloat16>, dim3(grid_for(n / 4)), dim3(kThreads), 0, s, (const float4*)a.data, (__nv_bfloat16*)d.data, n / 4);
         return 1;
     }
     // f32 -> f32 transposing copy: dst contiguous, same shape, src unit stride on another axis
@@ -627,7 +678,7 @@ int b200_launch_copy(cudaStream_t s, const b200_td& a, const b200_td& d) {
             int64_t nz = d.ne[o1] * d.ne[o2];
             if (nz <= 65535 && (d.ne[ax] + 31) / 32 <= 65535) {
                 dim3 grid((unsigned)((d.ne[0] + 31) / 32), (unsigned)((d.ne[ax] + 31) / 32), (unsigned)nz);
-                k_transpose_f32<<<grid, dim3(32, 8), 0, s>>>(a, d, ax, o1, o2);
+                b200_launch(k_transpose_f32, dim3(grid), dim3(dim3(32, 8)), 0, s, a, d, ax, o1, o2);
                 return 1;
             }
         }
@@ -635,17 +686,17 @@ int b200_launch_copy(cudaStream_t s, const b200_td& a, const b200_td& d) {
     if (a.type == d.type && es == 4 && same_shape(a, d) && rows4_ok(a) && rows4_ok(d)) {
         rows4 r;
         if (make_rows4(d, &r)) {
-            k_copy_rows4<<<grid_for(r.total), kThreads, 0, s>>>((const char*)a.data, st3(a), (char*)d.data, st3(d), r);
+            b200_launch(k_copy_rows4, dim3(grid_for(r.total)), dim3(kThreads), 0, s, (const char*)a.data, st3(a), (char*)d.data, st3(d), r);
             return 1;
         }
     }
     unsigned g = grid_for(n);
-#define CP(TS, TD) k_copy_generic<TS, TD><<<g, kThreads, 0, s>>>(a, d, n)
+#define CP(TS, TD) b200_launch(k_copy_generic<TS, TD>, dim3(g), dim3(kThreads), 0, s, a, d, n)
     if (a.type == d.type) {
-        if (es == 4) k_copy_raw<uint32_t><<<g, kThreads, 0, s>>>(a, d, n);
-        else if (es == 2) k_copy_raw<uint16_t><<<g, kThreads, 0, s>>>(a, d, n);
-        else if (es == 1) k_copy_raw<uint8_t><<<g, kThreads, 0, s>>>(a, d, n);
-        else k_copy_raw<uint64_t><<<g, kThreads, 0, s>>>(a, d, n);
+        if (es == 4) b200_launch(k_copy_raw<uint32_t>, dim3(g), dim3(kThreads), 0, s, a, d, n);
+        else if (es == 2) b200_launch(k_copy_raw<uint16_t>, dim3(g), dim3(kThreads), 0, s, a, d, n);
+        else if (es == 1) b200_launch(k_copy_raw<uint8_t>, dim3(g), dim3(kThreads), 0, s, a, d, n);
+        else b200_launch(k_copy_raw<uint64_t>, dim3(g), dim3(kThreads), 0, s, a, d, n);
     } else if (a.type == GGML_TYPE_F32 && d.type == GGML_TYPE_F16) CP(float, __half);
     else if (a.type == GGML_TYPE_F32 && d.type == GGML_TYPE_BF16) CP(float, __nv_bfloat16);
     else if (a.type == GGML_TYPE_F16 && d.type == GGML_TYPE_F32) CP(__half, float);
@@ -664,13 +715,13 @@ int b200_launch_concat(cudaStream_t s, const b200_td& a, const b200_td& b, const
     if (es == 4 && dim >= 1 && rows4_ok(a) && rows4_ok(b) && rows4_ok(d) && a.ne[dim] < (1ll << 31)) {
         rows4 r;
         if (make_rows4(d, &r)) {
-            k_concat_rows4<<<grid_for(r.total), kThreads, 0, s>>>((const char*)a.data, st3(a), (const char*)b.data, st3(b), (char*)d.data, st3(d), r, dim,
+            b200_launch(k_concat_rows4, dim3(grid_for(r.total)), dim3(kThreads), 0, s, (const char*)a.data, st3(a), (const char*)b.data, st3(b), (char*)d.data, st3(d), r, dim,
                                                                  (uint32_t)a.ne[dim]);
             return 1;
         }
     }
-    if (es == 4) k_concat<uint32_t><<<grid_for(n), kThreads, 0, s>>>(a, b, d, dim, n);
-    else if (es == 2) k_concat<uint16_t><<<grid_for(n), kThreads, 0, s>>>(a, b, d, dim, n);
+    if (es == 4) b200_launch(k_concat<uint32_t>, dim3(grid_for(n)), dim3(kThreads), 0, s, a, b, d, dim, n);
+    else if (es == 2) b200_launch(k_concat<uint16_t>, dim3(grid_for(n)), dim3(kThreads), 0, s, a, b, d, dim, n);
     else return -1;
     return 1;
 }
@@ -679,8 +730,8 @@ int b200_launch_repeat(cudaStream_t s, const b200_td& a, const b200_td& d) {
     int64_t n = td_nelements(d);
     if (n == 0) return 0;
     int64_t es = type_size(d.type);
-    if (es == 4) k_repeat<uint32_t><<<grid_for(n), kThreads, 0, s>>>(a, d, n);
-    else if (es == 2) k_repeat<uint16_t><<<grid_for(n), kThreads, 0, s>>>(a, d, n);
+    if (es == 4) b200_launch(k_repeat<uint32_t>, dim3(grid_for(n)), dim3(kThreads), 0, s, a, d, n);
+    else if (es == 2) b200_launch(k_repeat<uint16_t>, dim3(grid_for(n)), dim3(kThreads), 0, s, a, d, n);
     else return -1;
     return 1;
 }
@@ -691,7 +742,7 @@ int b200_launch_pad(cudaStream_t s, const b200_td& a, const b200_td& d, const in
     PadParams p;
     for (int k = 0; k < 4; ++k) { p.lp[k] = pads[2 * k]; p.rp[k] = pads[2 * k + 1]; }
     p.circular = circular;
-    k_pad_f32<<<grid_for(n), kThreads, 0, s>>>(a, d, p, n);
+    b200_launch(k_pad_f32, dim3(grid_for(n)), dim3(kThreads), 0, s, a, d, p, n);
     return 1;
 }
 
@@ -707,36 +758,36 @@ int b200_launch_upscale(cudaStream_t s, const b200_td& a, const b200_td& d, int 
         sf1 = d.ne[1] > 1 && a.ne[1] > 1 ? (float)(d.ne[1] - 1) / (a.ne[1] - 1) : sf1;
     }
     int m = mode == GGML_SCALE_MODE_NEAREST ? 0 : 1;
-    k_upscale_f32<<<grid_for(n), kThreads, 0, s>>>(a, d, m, sf0, sf1, sf2, sf3, pixel_offset, n);
+    b200_launch(k_upscale_f32, dim3(grid_for(n)), dim3(kThreads), 0, s, a, d, m, sf0, sf1, sf2, sf3, pixel_offset, n);
     return 1;
 }
 
 int b200_launch_timestep_embedding(cudaStream_t s, const b200_td& src, const b200_td& d, int dim, int max_period) {
     int half = dim / 2;
     dim3 grid((unsigned)((std::max(half, 1) + 127) / 128), (unsigned)src.ne[0]);
-    k_timestep_embedding<<<grid, 128, 0, s>>>((const float*)src.data, (char*)d.data, d.nb[1], dim, max_period, src.ne[0]);
+    b200_launch(k_timestep_embedding, dim3(grid), dim3(128), 0, s, (const float*)src.data, (char*)d.data, d.nb[1], dim, max_period, src.ne[0]);
     return 1;
 }
 
 int b200_launch_get_rows(cudaStream_t s, const b200_td& src, const b200_td& idx, const b200_td& d) {
     int64_t n = td_nelements(d);
     if (n == 0) return 0;
-    if (src.type == GGML_TYPE_F32) k_get_rows<float><<<grid_for(n), kThreads, 0, s>>>(src, idx, d, n);
-    else if (src.type == GGML_TYPE_F16) k_get_rows<__half><<<grid_for(n), kThreads, 0, s>>>(src, idx, d, n);
-    else if (src.type == GGML_TYPE_BF16) k_get_rows<__nv_bfloat16><<<grid_for(n), kThreads, 0, s>>>(src, idx, d, n);
+    if (src.type == GGML_TYPE_F32) b200_launch(k_get_rows<float>, dim3(grid_for(n)), dim3(kThreads), 0, s, src, idx, d, n);
+    else if (src.type == GGML_TYPE_F16) b200_launch(k_get_rows<__half>, dim3(grid_for(n)), dim3(kThreads), 0, s, src, idx, d, n);
+    else if (src.type == GGML_TYPE_BF16) b200_launch(k_get_rows<__nv_bfloat16>, dim3(grid_for(n)), dim3(kThreads), 0, s, src, idx, d, n);
     else return -1;
     return 1;
 }
 
 int b200_launch_arange(cudaStream_t s, const b200_td& d, float start, float step) {
     int64_t n = td_nelements(d);
-    k_arange<<<grid_for(n), kThreads, 0, s>>>((float*)d.data, n, start, step);
+    b200_launch(k_arange, dim3(grid_for(n)), dim3(kThreads), 0, s, (float*)d.data, n, start, step);
     return 1;
 }
 
 int b200_launch_fill(cudaStream_t s, const b200_td& d, float v) {
     int64_t n = td_nelements(d);
-    k_fill<<<grid_for(n), kThreads, 0, s>>>((float*)d.data, n, v);
+    b200_launch(k_fill, dim3(grid_for(n)), dim3(kThreads), 0, s, (float*)d.data, n, v);
     return 1;
 }
 
@@ -755,14 +806,14 @@ int b200_launch_glu(cudaStream_t s, int glu_op, const b200_td& a, const b200_td*
         pa = pa + (swapped ? nc * 4 : 0);
         b_nb1 = a.nb[1];
     }
-    k_glu_f32<<<grid_for(nc * nrows), kThreads, 0, s>>>(pa, pb, (char*)d.data, nc, nrows, a.nb[1], b_nb1, d.nb[1], glu_op);
+    b200_launch(k_glu_f32, dim3(grid_for(nc * nrows)), dim3(kThreads), 0, s, pa, pb, (char*)d.data, nc, nrows, a.nb[1], b_nb1, d.nb[1], glu_op);
     return 1;
 }
 
 int b200_launch_sum_rows(cudaStream_t s, const b200_td& a, const b200_td& d, bool mean) {
     int64_t nrows = a.ne[1] * a.ne[2] * a.ne[3];
     if (nrows == 0) return 0;
-    k_sum_rows<<<(unsigned)((nrows + 7) / 8), 256, 0, s>>>(a, d, nrows, mean);
+    b200_launch(k_sum_rows, dim3((unsigned)((nrows + 7) / 8)), dim3(256), 0, s, a, d, nrows, mean);
     return 1;
 }
 
@@ -776,13 +827,13 @@ int b200_launch_pack_rows(cudaStream_t s, const b200_td& a, void* dst, int dst_t
         shape.ne[0] = kpad / 2;      // make_rows4 divides by 4: cpr = kpad / 8
         rows4 r;
         if (make_rows4(shape, &r)) {
-            if (dst_type == GGML_TYPE_F16) k_pack_rows8<__half><<<grid_for(r.total), kThreads, 0, s>>>((const char*)a.data, st3(a), (__half*)dst, r, (uint32_t)a.ne[0]);
-            else k_pack_rows8<__nv_bfloat16><<<grid_for(r.total), kThreads, 0, s>>>((const char*)a.data, st3(a), (__nv_bfloat16*)dst, r, (uint32_t)a.ne[0]);
+            if (dst_type == GGML_TYPE_F16) b200_launch(k_pack_rows8<__half>, dim3(grid_for(r.total)), dim3(kThreads), 0, s, (const char*)a.data, st3(a), (__half*)dst, r, (uint32_t)a.ne[0]);
+            else b200_launch(k_pack_rows8<__nv_bfloat16>, dim3(grid_for(r.total)), dim3(kThreads), 0, s, (const char*)a.data, st3(a), (__nv_bfloat16*)dst, r, (uint32_t)a.ne[0]);
             return 1;
         }
     }
     unsigned g = grid_for(n);
-#define PK(TS, TD) k_pack_rows<TS, TD><<<g, kThreads, 0, s>>>(a, (TD*)dst, kpad, nrows)
+#define PK(TS, TD) b200_launch(k_pack_rows<TS, TD>, dim3(g), dim3(kThreads), 0, s, a, (TD*)dst, kpad, nrows)
     if (a.type == GGML_TYPE_F32 && dst_type == GGML_TYPE_F16) PK(float, __half);
     else if (a.type == GGML_TYPE_F32 && dst_type == GGML_TYPE_BF16) PK(float, __nv_bfloat16);
     else if (a.type == GGML_TYPE_F32 && dst_type == GGML_TYPE_F32) PK(float, float);
@@ -803,6 +854,6 @@ int b200_launch_transpose_f16(cudaStream_t s, const b200_td& src, void* dst, int
     if (D == 0 || L == 0 || Z == 0) return 0;
     if (src.nb[0] != 2 || Z > 65535 || (D + 31) / 32 > 65535) return -1;
     dim3 grid((unsigned)((L + 31) / 32), (unsigned)((D + 31) / 32), (unsigned)Z);
-    k_transpose_16<<<grid, dim3(32, 8), 0, s>>>((const char*)src.data, (uint16_t*)dst, (int)D, (int)L, Lpad, src.nb[1], src.nb[2], src.nb[3], (int)src.ne[2]);
+    b200_launch(k_transpose_16, dim3(grid), dim3(dim3(32, 8)), 0, s, (const char*)src.data, (uint16_t*)dst, (int)D, (int)L, Lpad, src.nb[1], src.nb[2], src.nb[3], (int)src.ne[2]);
     return 1;
 }

@@ -2,6 +2,7 @@
 // cross-check for the tcgen05 kernel (option "tc_gemm"=0) and (b) for operand shapes the TMA path cannot
 // describe (rows not 16-byte aligned, K < 8).  D[n][m] = sum_k A[m][k] * B[n][k], f32 accumulate.
 #include "../b200_ops.h"
+#include "b200_launch.cuh"
 
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -18,6 +19,8 @@ constexpr int TM = 64, TN = 64, TK = 16;
 template <typename TA, typename TB>
 __global__ void __launch_bounds__(256) k_gemm_ref(const char* __restrict__ A, int64_t lda, const char* __restrict__ B, int64_t ldb,
                                                   float* __restrict__ D, int64_t ldd, int64_t M, int64_t N, int64_t K) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float sa[TK][TM + 1];
     __shared__ float sb[TK][TN + 1];
     int64_t m0 = (int64_t)blockIdx.x * TM, n0 = (int64_t)blockIdx.y * TN;
@@ -65,7 +68,7 @@ int b200_launch_gemm_ref(cudaStream_t s, const void* A, int a_type, int64_t lda_
                          int64_t ldd, int64_t M, int64_t N, int64_t K) {
     if (M == 0 || N == 0) return 0;
     dim3 grid((unsigned)((M + TM - 1) / TM), (unsigned)((N + TN - 1) / TN));
-#define G(TA, TB) k_gemm_ref<TA, TB><<<grid, 256, 0, s>>>((const char*)A, lda_bytes, (const char*)B, ldb_bytes, D, ldd, M, N, K)
+#define G(TA, TB) b200_launch(k_gemm_ref<TA, TB>, dim3(grid), dim3(256), 0, s, (const char*)A, lda_bytes, (const char*)B, ldb_bytes, D, ldd, M, N, K)
     if (a_type == GGML_TYPE_F32 && b_type == GGML_TYPE_F32) G(float, float);
     else if (a_type == GGML_TYPE_F16 && b_type == GGML_TYPE_F16) G(__half, __half);
     else if (a_type == GGML_TYPE_BF16 && b_type == GGML_TYPE_BF16) G(__nv_bfloat16, __nv_bfloat16);

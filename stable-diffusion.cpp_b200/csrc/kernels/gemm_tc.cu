@@ -17,6 +17,7 @@
 // Roofline: tensor pipe.  Algorithmic work = 2*M*N*K flop per launch; the 128 x BN x 64 k-block costs 2*BN cycles
 // of MMA issue at cta_group::1 (B300_MICROARCH "tcgen05 floor"), i.e. 8192 flop/cycle/SM.
 #include "../b200_ops.h"
+#include "b200_launch.cuh"
 #include "sm100_ptx.cuh"
 
 #include <cuda_fp16.h>
@@ -128,6 +129,9 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
     if (threadIdx.x == 0) TRACE(1);
+    // everything above is on-chip setup (barriers, TMEM, descriptor prefetch): under PDL it overlaps the predecessor's tail
+    pdl_wait();
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -432,13 +436,9 @@ cudaError_t launch_cfg(cudaStream_t s, dim3 grid, const CUtensorMap& ta, const C
     cfg.blockDim = dim3(192);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = (unsigned)kp.splits;
+    cudaLaunchAttribute attr[2];
+    cfg.numAttrs = b200_launch_attrs(attr, (unsigned)kp.splits);
     cfg.attrs = attr;
-    cfg.numAttrs = kp.splits > 1 ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, FMT>, ta, tb, kp);
 }
 

@@ -4,6 +4,7 @@
 // HBM-bound: algorithmic bytes = |image| read + |columns| written.  In whole-model graphs the fusion pass
 // replaces IM2COL+MUL_MAT by an implicit-GEMM kernel that never materialises the columns.
 #include "../b200_ops.h"
+#include "b200_launch.cuh"
 
 #include <cuda_fp16.h>
 
@@ -12,6 +13,8 @@ namespace {
 template <typename TS, typename TD>
 __global__ void k_im2col(const char* __restrict__ src, TD* __restrict__ dst, int64_t IW, int64_t IH, int64_t IC, int64_t N, int64_t OW, int64_t OH,
                          int KW, int KH, int s0, int s1, int p0, int p1, int d0, int d1, int64_t nb_row, int64_t nb_ch, int64_t nb_n, int64_t total) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int64_t K = IC * KH * KW;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t k = i % K, r = i / K;
@@ -49,7 +52,7 @@ int b200_launch_im2col(cudaStream_t s, const b200_td& src, const b200_td& dst, i
     if (total == 0) return 0;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 0x7fffffff) blocks = 0x7fffffff;
-#define IM(TS, TD) k_im2col<TS, TD><<<(unsigned)blocks, 256, 0, s>>>((const char*)src.data, (TD*)dst.data, IW, IH, IC, N, OW, OH, (int)KW, (int)KH, s0, s1, p0, p1, d0, d1, nb_row, nb_ch, nb_n, total)
+#define IM(TS, TD) b200_launch(k_im2col<TS, TD>, dim3((unsigned)blocks), dim3(256), 0, s, (const char*)src.data, (TD*)dst.data, IW, IH, IC, N, OW, OH, (int)KW, (int)KH, s0, s1, p0, p1, d0, d1, nb_row, nb_ch, nb_n, total)
     if (src.type == GGML_TYPE_F32 && dst.type == GGML_TYPE_F16) IM(float, __half);
     else if (src.type == GGML_TYPE_F32 && dst.type == GGML_TYPE_F32) IM(float, float);
     else if (src.type == GGML_TYPE_F16 && dst.type == GGML_TYPE_F16) IM(__half, __half);

@@ -10,6 +10,7 @@
 // in registers or shared memory between the statistics pass and the normalise pass so HBM sees each
 // element once on the way in and once on the way out.
 #include "../b200_ops.h"
+#include "b200_launch.cuh"
 
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -63,6 +64,8 @@ template <bool IN_SMEM>
 __global__ void __launch_bounds__(1024) k_group_norm(const float* __restrict__ x, float* __restrict__ y, int64_t inner /*W*H*/,
                                                      int C, int cpg, int n_groups, float eps, const float* __restrict__ gw,
                                                      const float* __restrict__ gb, int act) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ float sbuf[];
     __shared__ float red[32];
     int g = blockIdx.x, n = blockIdx.y;
@@ -122,6 +125,8 @@ __global__ void __launch_bounds__(1024) k_group_norm(const float* __restrict__ x
 // ------------------------------------------------------------------------------------------
 template <int KIND>
 __global__ void k_row_norm(b200_td a, b200_td d, float eps, const float* __restrict__ rw, const float* __restrict__ rb, void* out16, int out16_bf16) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float red[32];
     int64_t row = blockIdx.x;
     int64_t i1 = row % a.ne[1], r = row / a.ne[1];
@@ -197,6 +202,8 @@ __global__ void k_row_norm(b200_td a, b200_td d, float eps, const float* __restr
 // ------------------------------------------------------------------------------------------
 template <typename TM>
 __global__ void k_soft_max(b200_td a, b200_td m, b200_td d, bool has_mask, float scale, float max_bias, float m0, float m1, uint32_t n_head_log2) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ float srow[];
     __shared__ float red[32];
     int64_t row = blockIdx.x;
@@ -249,9 +256,9 @@ int b200_launch_group_norm(cudaStream_t s, const b200_td& src, const b200_td& ds
             cudaFuncSetAttribute(k_group_norm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             attr_set[dev] = true;
         }
-        k_group_norm<true><<<grid, threads, bytes, s>>>((const float*)src.data, (float*)dst.data, inner, C, cpg, n_groups, eps, w, b, act);
+        b200_launch(k_group_norm<true>, dim3(grid), dim3(threads), bytes, s, (const float*)src.data, (float*)dst.data, inner, C, cpg, n_groups, eps, w, b, act);
     } else {
-        k_group_norm<false><<<grid, 1024, 0, s>>>((const float*)src.data, (float*)dst.data, inner, C, cpg, n_groups, eps, w, b, act);
+        b200_launch(k_group_norm<false>, dim3(grid), dim3(1024), 0, s, (const float*)src.data, (float*)dst.data, inner, C, cpg, n_groups, eps, w, b, act);
     }
     return 1;
 }
@@ -264,9 +271,9 @@ int b200_launch_norm(cudaStream_t s, int kind, const b200_td& src, const b200_td
     int threads = src.ne[0] >= 4096 ? 1024 : (src.ne[0] >= 1024 ? 256 : 128);
     if (nrows > 0x7fffffff) return -1;
     switch (kind) {
-        case B200_NORM_LAYER: k_row_norm<B200_NORM_LAYER><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps, w, b, out16, bf); break;
-        case B200_NORM_RMS: k_row_norm<B200_NORM_RMS><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps, w, b, out16, bf); break;
-        default: k_row_norm<B200_NORM_L2><<<(unsigned)nrows, threads, 0, s>>>(src, dst, eps, w, b, out16, bf); break;
+        case B200_NORM_LAYER: b200_launch(k_row_norm<B200_NORM_LAYER>, dim3((unsigned)nrows), dim3(threads), 0, s, src, dst, eps, w, b, out16, bf); break;
+        case B200_NORM_RMS: b200_launch(k_row_norm<B200_NORM_RMS>, dim3((unsigned)nrows), dim3(threads), 0, s, src, dst, eps, w, b, out16, bf); break;
+        default: b200_launch(k_row_norm<B200_NORM_L2>, dim3((unsigned)nrows), dim3(threads), 0, s, src, dst, eps, w, b, out16, bf); break;
     }
     return 1;
 }
@@ -290,7 +297,7 @@ int b200_launch_soft_max(cudaStream_t s, const b200_td& src, const b200_td* mask
         cudaFuncSetAttribute(k_soft_max<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set[dev] = true;
     }
-    if (f16mask) k_soft_max<__half><<<(unsigned)nrows, threads, bytes, s>>>(src, m, dst, mask != nullptr, scale, max_bias, m0, m1, n_head_log2);
-    else k_soft_max<float><<<(unsigned)nrows, threads, bytes, s>>>(src, m, dst, mask != nullptr, scale, max_bias, m0, m1, n_head_log2);
+    if (f16mask) b200_launch(k_soft_max<__half>, dim3((unsigned)nrows), dim3(threads), bytes, s, src, m, dst, mask != nullptr, scale, max_bias, m0, m1, n_head_log2);
+    else b200_launch(k_soft_max<float>, dim3((unsigned)nrows), dim3(threads), bytes, s, src, m, dst, mask != nullptr, scale, max_bias, m0, m1, n_head_log2);
     return 1;
 }
