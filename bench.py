@@ -48,6 +48,25 @@ def peaks():
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, src="fallback")
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) per k_gemm_tc launch, averaged over the launches of the committed `ncu --set full` capture
+    (profiles/r01_ncu_full_top_kernels.json).  Offline evidence, never measured under the timed run; null when absent."""
+    p = REPO / "profiles" / "r01_ncu_full_top_kernels.json"
+    if not p.exists():
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, n = 0.0, 0
+    for row in json.loads(p.read_text()):
+        if not row.get("Kernel Name", "").startswith("k_gemm_tc"):
+            continue
+        b = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            v, u = row[key].split()
+            b += float(v) * scale[u]
+        tot, n = tot + b, n + 1
+    return dict(bytes_per_launch=tot / n, launches_sampled=n, source=str(p.relative_to(REPO))) if n else None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -230,7 +249,7 @@ def run_b200(args):
                 roof = dict(bound="tensor", kernel="k_gemm_tc (tcgen05.mma kind::f16/tf32, TMA, TMEM)", achieved=ach, peak=pk["bf16_sustained"],
                             unit="TFLOP/s", frac=ach / pk["bf16_sustained"], peak_source=pk["src"] + " (sustained: kernel timed inside a long step)",
                             launches=gl, flop_per_launch=gf / max(gl, 1), us_per_launch=gus / max(gl, 1),
-                            share_of_step_device_time=(gus / 1e3) / max((k1["total_graph_ms"] - k0["total_graph_ms"]), 1e-9), traffic=None)
+                            share_of_step_device_time=(gus / 1e3) / max((k1["total_graph_ms"] - k0["total_graph_ms"]), 1e-9), traffic=ncu_traffic())
         except Exception as e:   # older plugin without kernel timing
             roof = dict(bound="tensor", error=str(e))
         step_tflops = 2 * flops * images * args.steps / (dev_ms / 1e3) / 1e12 / max(1, n if world > 1 else 1)
