@@ -53,7 +53,7 @@ def ncu_traffic():
     (profiles/r01_ncu_full_top_kernels.json).  Offline evidence, never measured under the timed run; null when absent."""
     p = REPO / "profiles" / "r01_ncu_full_top_kernels.json"
     if not p.exists():
-        return None
+        return dict(traffic=None)
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tot, n = 0.0, 0
     for row in json.loads(p.read_text()):
@@ -64,7 +64,10 @@ def ncu_traffic():
             v, u = row[key].split()
             b += float(v) * scale[u]
         tot, n = tot + b, n + 1
-    return dict(bytes_per_launch=tot / n, launches_sampled=n, source=str(p.relative_to(REPO))) if n else None
+    if not n:
+        return dict(traffic=None)
+    return dict(traffic=tot / n, traffic_unit="bytes/launch (dram read+write, ncu --set full)", traffic_launches_sampled=n,
+                traffic_source=str(p.relative_to(REPO)))
 
 
 class ClockSampler:
@@ -177,25 +180,9 @@ def run_b200(args):
     assert abs(flops - FLOPS_PER_FORWARD) / FLOPS_PER_FORWARD < 0.01, f"graph FLOPs {flops:.4e} differ from SURVEY.md 8d"
 
     exchange = None
-    coll_ms = [0.0]
     if world > 1:
-        groups = [dist.new_group(ranks=[2 * i, 2 * i + 1]) for i in range(world // 2)] if world > 2 else [None]
-        grp = groups[rank // 2] if world > 2 else None
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        send = torch.empty(4 * 64 * 64, dtype=torch.float32, device="cuda")
-        recv = torch.empty(2 * 4 * 64 * 64, dtype=torch.float32, device="cuda")
-        host = torch.empty(2 * 4 * 64 * 64, dtype=torch.float32).pin_memory()
-
-        def exchange(mine: np.ndarray):
-            send.copy_(torch.from_numpy(mine), non_blocking=True)
-            ev0.record()
-            dist.all_gather_into_tensor(recv, send, group=grp)      # THE collective of this path: 64 KB eps all-gather over NVLink
-            ev1.record()
-            host.copy_(recv, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            coll_ms[0] += ev0.elapsed_time(ev1)
-            both = host.numpy()
-            return both[: mine.size], both[mine.size:]
+        from sdb200.cfg_split import PairExchange
+        exchange = PairExchange(dist, torch, rank, world, 4 * 64 * 64, "cuda")   # pair groups + one all-gather per step
 
     def run(steps):
         return m.sample(x, cond, uncond, steps=steps, cfg_scale=CFG_SCALE, eta=ETA, role=role, exchange=exchange)
@@ -209,14 +196,15 @@ def run_b200(args):
     run(max(args.warmup, 3))                                   # >= 3 untimed warm-up steps (plan caches, workspace, clocks)
     barrier()
     s0 = m.stats()
-    coll_ms[0] = 0.0
+    if exchange is not None:
+        exchange.coll_ms = 0.0
     with ClockSampler(local) as clk:
         t0 = time.perf_counter()
         out, info = run(args.steps)                            # EXACTLY K timed steps
         barrier()
         wall = time.perf_counter() - t0
     s1 = m.stats()
-    dev_ms = (s1["total_graph_ms"] - s0["total_graph_ms"]) + coll_ms[0]
+    dev_ms = (s1["total_graph_ms"] - s0["total_graph_ms"]) + (exchange.coll_ms if exchange is not None else 0.0)
     launches = s1["kernel_launches"] - s0["kernel_launches"]
     forwards = s1["graphs"] - s0["graphs"]
     if dist is not None:
@@ -249,7 +237,7 @@ def run_b200(args):
                 roof = dict(bound="tensor", kernel="k_gemm_tc (tcgen05.mma kind::f16/tf32, TMA, TMEM)", achieved=ach, peak=pk["bf16_sustained"],
                             unit="TFLOP/s", frac=ach / pk["bf16_sustained"], peak_source=pk["src"] + " (sustained: kernel timed inside a long step)",
                             launches=gl, flop_per_launch=gf / max(gl, 1), us_per_launch=gus / max(gl, 1),
-                            share_of_step_device_time=(gus / 1e3) / max((k1["total_graph_ms"] - k0["total_graph_ms"]), 1e-9), traffic=ncu_traffic())
+                            share_of_step_device_time=(gus / 1e3) / max((k1["total_graph_ms"] - k0["total_graph_ms"]), 1e-9), **ncu_traffic())
         except Exception as e:   # older plugin without kernel timing
             roof = dict(bound="tensor", error=str(e))
         step_tflops = 2 * flops * images * args.steps / (dev_ms / 1e3) / 1e12 / max(1, n if world > 1 else 1)
