@@ -247,6 +247,10 @@ def run_b200(args):
         if n == 1 and not args.no_cpu_baseline:
             cpu_base = cpu_baseline_leg(h)
     m.close()
+    extra = {}
+    if rank == 0 and n == 1:
+        for name in [e for e in args.extra.split(",") if e]:
+            extra[name] = extra_leg(h, dev, peaks(), name)
     if rank == 0:
         line = dict(metric="denoise_steps_per_s", value=value, unit="steps/s", n_gpus=n, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16", data="synthetic",
@@ -260,7 +264,7 @@ def run_b200(args):
                     e2e=dict(value=e2e, unit="steps/s", ms_per_step=1e3 * wall / args.steps,
                              h2d_bytes_per_step=2 * (4 * 64 * 64 * 4 + 77 * 768 * 4 + 4 + 8), d2h_bytes_per_step=2 * 4 * 64 * 64 * 4),
                     gpu_launches=int(launches), forwards=int(forwards), clocks=clk.summary(), roofline=roof, cpu_baseline=cpu_base,
-                    vae_decode=vae,
+                    vae_decode=vae, extra_workloads=extra or None,
                     backend=dict(cuda_graph_replays=int(s1["cuda_graph_replays"] - s0["cuda_graph_replays"]),
                                  fused_nodes=int(s1["fused_nodes"] - s0["fused_nodes"]), implicit_convs=int(s1["implicit_convs"] - s0["implicit_convs"]),
                                  fused_attn_launches=int(s1["fused_attn_launches"] - s0["fused_attn_launches"]),
@@ -296,6 +300,43 @@ def vae_decode_leg(h, dev, pk):
                 finite=bool(np.isfinite(out).all()))
 
 
+EXTRA = {
+    # BASELINE.json configs[2] / configs[3] shapes at one GPU (the multi-GPU layouts of those configs shard these same forwards)
+    "sdxl": dict(arch="sdxl_unet", wtype="bf16", flags=1, x=(1, 4, 128, 128), ctx=(1, 77, 2048), y=(1, 2816), t=999.0, per_step=2,
+                 workload="SDXL UNet forward, 128x128x4 latent (1024x1024), BF16 linears / F16 convs, flash-attention graph"),
+    "flux": dict(arch="flux_schnell", wtype="bf16", flags=1, x=(1, 16, 128, 128), ctx=(1, 256, 4096), y=(1, 768), t=1.0, per_step=1,
+                 workload="FLUX.1-schnell MMDiT forward, 4096 image + 256 text tokens (1024x1024), BF16 weights"),
+}
+
+
+def extra_leg(h, dev, pk, name):
+    """Forward time of a larger north-star config on ONE GPU: device ms from CUDA events around graph_compute (weights resident),
+    algorithmic FLOPs recomputed from the live ggml graph, fraction of the measured sustained bf16 peak."""
+    e = EXTRA[name]
+    t0 = time.time()
+    m = h.model(dev, e["arch"], e["wtype"], e["flags"], 1234, 0)
+    create_s = time.time() - t0
+    x = h.randn(42, e["x"]); ctx = h.randn(43, e["ctx"]); y = h.randn(44, e["y"]); t = np.array([e["t"]], np.float32)
+    nodes, flops = m.dump_graph(None, x, t, ctx, y)
+    for _ in range(3):
+        out, _ = m.forward(x, t, ctx, y)
+    dev_ms, wall_ms = [], []
+    for _ in range(5):
+        s0 = m.stats()
+        t0 = time.perf_counter()
+        out, _ = m.forward(x, t, ctx, y)
+        wall_ms.append((time.perf_counter() - t0) * 1e3)
+        s1 = m.stats()
+        dev_ms.append(s1["total_graph_ms"] - s0["total_graph_ms"])
+    launches = (s1["kernel_launches"] - s0["kernel_launches"])
+    m.close()
+    d = statistics.median(dev_ms)
+    return dict(workload=e["workload"], forward_ms=d, forward_e2e_ms=statistics.median(wall_ms), steps_per_s=1e3 / (d * e["per_step"]),
+                forwards_per_step=e["per_step"], algorithmic_tflop=flops / 1e12, tensor_tflops=flops / 1e12 / (d / 1e3),
+                tensor_frac=flops / 1e12 / (d / 1e3) / pk["bf16_sustained"], graph_nodes=nodes, launches_per_forward=int(launches),
+                finite=bool(np.isfinite(out).all()), model_create_s=create_s)
+
+
 def cpu_baseline_leg(h):
     """Bounded CPU sample: ONE full CFG denoise step (2 UNet forwards) on the reference CPU backend, all host threads."""
     from oracle.cpu_ref import load_cpu_oracle, best_thread_count
@@ -319,6 +360,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vae", action="store_true")
+    ap.add_argument("--extra", default="", help="comma list of additional single-GPU forward timings: sdxl,flux")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

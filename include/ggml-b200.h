@@ -70,7 +70,9 @@ typedef struct ggml_b200_stats {
     double   last_graph_ms;     /* device time of the last graph_compute (CUDA events)      */
     double   total_graph_ms;
     uint64_t tc_gemm_launches;  /* tcgen05 GEMM launches                                     */
-    uint64_t reserved[8];
+    uint64_t reserved[8];       /* [0] flop of the tcgen05 GEMMs timed under "kernel_timing", [1] their device time in us,
+                                   [2] fused flash-attention launches, [3] CUDA-graph replays, [4] implicit-GEMM convolutions,
+                                   [5..7] unused (0) */
 } ggml_b200_stats;
 
 /* copy the backend instance's counters; returns 0 on success */
@@ -82,6 +84,10 @@ void ggml_backend_b200_reset_stats(ggml_backend_t backend);
  *   "tc_gemm"     1/0   tcgen05 GEMM (0 = CUDA-core reference GEMM kernel, bring-up/debug only)
  *   "timing"      1/0   record CUDA events around every graph_compute (last_graph_ms)
  *   "cuda_graphs" 1/0   replay captured CUDA graphs for repeated identical ggml graphs
+ *   "kernel_timing" 1/0 CUDA events around every tcgen05 GEMM launch (roofline pass; disables graph replay while on)
+ *   "fused_attn"  1/0   single-kernel FLASH_ATTN_EXT (0 = GEMM + softmax + GEMM through workspace)
+ *   "implicit_conv" 1/0 IM2COL+MUL_MAT chains as TMA halo-tile implicit GEMM (0 = materialised im2col)
+ *   "early_weights" 1/0 GEMMs fetch the first tiles of constant weights before the programmatic-dependent-launch wait
  * returns 0 on success, -1 for an unknown key. */
 int ggml_backend_b200_set_option(ggml_backend_t backend, const char* key, int value);
 

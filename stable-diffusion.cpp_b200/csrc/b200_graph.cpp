@@ -45,6 +45,9 @@ b200_context* b200_context_create(const b200_device_info& info) {
     ctx->opt_cuda_graphs = env_flag("GGML_B200_CUDA_GRAPHS", 1) != 0;
     ctx->opt_fused_attn = env_flag("GGML_B200_FUSED_ATTN", 1) != 0;
     ctx->opt_implicit_conv = env_flag("GGML_B200_IMPLICIT_CONV", 1) != 0;
+    ctx->opt_early_weights = env_flag("GGML_B200_EARLY_WEIGHTS", 0) != 0;   // measured neutral on the SD1.5 step (profiles/r01_summary.md): off by default
+    ctx->opt_chain_fusion = env_flag("GGML_B200_CHAIN_FUSION", 1) != 0;
+    ctx->opt_gemv = env_flag("GGML_B200_GEMV", 1) != 0;
     return ctx;
 }
 
@@ -61,7 +64,11 @@ b200_context::~b200_context() {
     if (stream) cudaStreamDestroy(stream);
 }
 
+static void drop_cuda_graphs(b200_context* ctx);
+
 int b200_context_set_option(b200_context* ctx, const char* key, int value) {
+    // captured plans embody the options they were recorded under
+    if (strcmp(key, "timing") && strcmp(key, "kernel_timing")) { drop_cuda_graphs(ctx); ctx->plans.clear(); }
     if (!strcmp(key, "fusion")) ctx->opt_fusion = value != 0;
     else if (!strcmp(key, "tc_gemm")) ctx->opt_tc_gemm = value != 0;
     else if (!strcmp(key, "timing")) ctx->opt_timing = value != 0;
@@ -69,6 +76,9 @@ int b200_context_set_option(b200_context* ctx, const char* key, int value) {
     else if (!strcmp(key, "kernel_timing")) ctx->opt_kernel_timing = value != 0;
     else if (!strcmp(key, "fused_attn")) ctx->opt_fused_attn = value != 0;
     else if (!strcmp(key, "implicit_conv")) ctx->opt_implicit_conv = value != 0;
+    else if (!strcmp(key, "early_weights")) ctx->opt_early_weights = value != 0;
+    else if (!strcmp(key, "chain_fusion")) ctx->opt_chain_fusion = value != 0;
+    else if (!strcmp(key, "gemv")) ctx->opt_gemv = value != 0;
     else return -1;
     return 0;
 }
@@ -258,6 +268,8 @@ struct mm_fusion {
     const float* bias = nullptr;  // f32 vector
     int bias_mode = 0;            // 1: per output row m (Linear bias), 2: per n (conv bias: n == output channel)
     const float* residual = nullptr;   // same [M, N] layout as out, added last
+    const ggml_tensor* src1_pre = nullptr;   // activation to read instead of src[1] (same shape): the input of a unary op folded in
+    int pre_act = 0;                          // 1: SiLU applied to src1_pre on load (only the few-row GEMV path can do this)
 };
 
 static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz = nullptr) {
@@ -272,6 +284,23 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
     if (K == 0) {
         cudaMemsetAsync(dst->data, 0, ggml_nbytes(dst), ctx->stream);
         return 1;
+    }
+
+    // a handful of activation rows against in-place F16/BF16 weights (embedding MLPs): weight-streaming GEMV, no operand packing
+    {
+        const ggml_tensor* x = fz && fz->src1_pre ? fz->src1_pre : src1;
+        if (ctx->opt_gemv && ne02 * ne03 * ne12 * ne13 == 1 && N <= 4 && (src0->type == GGML_TYPE_F16 || src0->type == GGML_TYPE_BF16) &&
+            rows_unit_stride(src0) && x->type == GGML_TYPE_F32 && x->nb[0] == 4 && x->nb[1] % 4 == 0 && dst->nb[0] == 4 &&
+            b200_gemv_supported((int)src0->type, M, N, K, src0->data, (int64_t)src0->nb[1] / 2, x->data)) {
+            float* out = fz && fz->out ? fz->out : (float*)dst->data;
+            const float* bias = fz && fz->bias && fz->bias_mode == 1 ? fz->bias : nullptr;
+            if (!(fz && fz->bias && fz->bias_mode != 1)) {
+                int n = b200_launch_gemv(ctx->stream, (int)src0->type, src0->data, (int64_t)src0->nb[1] / 2, (const float*)x->data, (int64_t)x->nb[1] / 4, out,
+                                         (int64_t)dst->nb[1] / 4, M, N, K, bias, fz ? fz->residual : nullptr, (int64_t)dst->nb[1] / 4, fz ? fz->pre_act : 0);
+                if (n > 0) { ctx->stats.reserved[6] += 1; return n; }
+            }
+        }
+        if (fz && fz->src1_pre) return -2;     // only the GEMV can fold the unary op
     }
 
     operand a, b;
@@ -297,6 +326,11 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
         g.d_batch_stride = dst->nb[2] / 4;
         if (fz && fz->bias) { g.bias = fz->bias; g.bias_mode = fz->bias_mode; }
         if (fz && fz->residual) { g.residual = fz->residual; g.ldr = g.ldd; }
+        // model weights read in place are constants of the graph: their first ring-full may be fetched before the PDL wait.  Not for
+        // the first kernel of a graph_compute (its stream predecessor belongs to an earlier call, e.g. a weight update).
+        if (ctx->opt_early_weights && a.ptr == src0->data && src0->buffer && src0->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS &&
+            (ctx->launched_any || launches > 0))
+            g.early = 1;
         int n = launch_tc(ctx, g);
         if (n < 0) {
             // CUDA-core reference kernel (debug option, or shapes the TMA cannot describe)
@@ -341,7 +375,17 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
 // FLASH_ATTN_EXT (v1: tensor-core GEMMs + row softmax through workspace; the fused single-kernel
 // version replaces this for the head sizes it covers)
 // ------------------------------------------------------------------------------------------------
-static int op_flash_attn(b200_context* ctx, ggml_tensor* dst) {
+// graph-level help for the fused kernel (try_fuse_flash_attn): Q read through the strided view a skipped CONT would have copied,
+// and an f16 copy of the result for the output projection that follows
+struct fa_fusion {
+    const b200_td* q_td = nullptr;
+    ggml_tensor* q_cont = nullptr;        // the skipped CONT: executed late if the fused kernel turns the shape down
+    const ggml_tensor* shadow_act = nullptr;   // activation operand (f32 view of dst) of the next MUL_MAT
+};
+
+static int run_node(b200_context* ctx, ggml_tensor* t);
+
+static int op_flash_attn(b200_context* ctx, ggml_tensor* dst, const fa_fusion* fz = nullptr) {
     const ggml_tensor* q = dst->src[0];
     const ggml_tensor* k = dst->src[1];
     const ggml_tensor* v = dst->src[2];
@@ -358,9 +402,6 @@ static int op_flash_attn(b200_context* ctx, ggml_tensor* dst) {
     const int64_t es = 2;
     const int64_t Lk_pad = (Lk + 7) / 8 * 8;
 
-    operand qa, ka;
-    if (!prepare_operand(ctx, q, ct, &qa, &launches)) return -1;
-    if (!prepare_operand(ctx, k, ct, &ka, &launches)) return -1;
     // V^T: [Lk, dv, Hkv, NB] view of v, packed to ct with Lk padded
     ggml_tensor vt = *v;
     vt.ne[0] = v->ne[1]; vt.nb[0] = v->nb[1];
@@ -373,17 +414,38 @@ static int op_flash_attn(b200_context* ctx, ggml_tensor* dst) {
     if (n < 0) return -1;
     launches += n;
 
-    // fused single-kernel path (tcgen05 QK^T and PV, online softmax between them): f16 K/V, d == dv, d % 8 == 0, d <= 192
+    // fused single-kernel path (tcgen05 QK^T and PV, online softmax between them): f16 K/V, d == dv, d % 8 == 0, d <= 192.
+    // The kernel converts Q from f32 itself (any row stride), so no operand is packed for it.
     if (ctx->opt_tc_gemm && ctx->opt_fused_attn && max_bias == 0.0f && ct == GGML_TYPE_F16 && k->type == GGML_TYPE_F16) {
         b200_td mtd;
         if (mask) mtd = b200_make_td(mask);
-        n = b200_launch_flash_attn_fused(ctx->stream, b200_make_td(q), b200_make_td(k), vbuf, Lk_pad, b200_make_td(v), mask ? &mtd : nullptr,
-                                         b200_make_td(dst), scale);
+        void* shadow = nullptr;
+        if (fz && fz->shadow_act) shadow = ws_alloc(ctx, (size_t)ggml_nelements(dst) * 2);
+        n = b200_launch_flash_attn_fused(ctx->stream, fz && fz->q_td ? *fz->q_td : b200_make_td(q), b200_make_td(k), vbuf, Lk_pad, b200_make_td(v),
+                                         mask ? &mtd : nullptr, b200_make_td(dst), scale, shadow);
+        if (n < 0 && shadow) {
+            shadow = nullptr;
+            n = b200_launch_flash_attn_fused(ctx->stream, fz && fz->q_td ? *fz->q_td : b200_make_td(q), b200_make_td(k), vbuf, Lk_pad, b200_make_td(v),
+                                             mask ? &mtd : nullptr, b200_make_td(dst), scale, nullptr);
+        }
         if (n > 0) {
             ctx->stats.reserved[2] += (uint64_t)n;   // fused attention launches
+            if (shadow) {
+                const ggml_tensor* a = fz->shadow_act;
+                ctx->pack_cache[std::make_pair(a, (int)GGML_TYPE_F16)] = operand{shadow, GGML_TYPE_F16, a->ne[0], a->ne[0] * a->ne[1], a->ne[0] * a->ne[1] * a->ne[2]};
+            }
+            if (fz && fz->q_td) ctx->stats.reserved[5] += 1;   // Q read in place: CONT skipped
             return launches + n;
         }
     }
+    if (fz && fz->q_cont) {     // composite path reads the contiguous Q: produce it now (its source is still intact, see try_skip_q_cont)
+        n = run_node(ctx, fz->q_cont);
+        if (n < 0) return -1;
+        launches += n;
+    }
+    operand qa, ka;
+    if (!prepare_operand(ctx, q, ct, &qa, &launches)) return -1;
+    if (!prepare_operand(ctx, k, ct, &ka, &launches)) return -1;
     float* sbuf = (float*)ws_alloc(ctx, (size_t)(Lk * Lq * H * sizeof(float)));
     void* pbuf = ws_alloc(ctx, (size_t)(Lk_pad * Lq * H * es));
     if (!sbuf || !pbuf) return -1;
@@ -717,6 +779,9 @@ static uint64_t graph_key(const ggml_cgraph* g) {
 struct fusion_state {
     std::unordered_map<const ggml_tensor*, int> uses;   // consumer count inside this graph
     std::vector<char> done;                             // node already covered by an earlier fused launch
+    // FLASH_ATTN_EXT node index -> (skipped CONT node, strided descriptor the kernel reads Q through instead)
+    struct q_bypass { ggml_tensor* cont; b200_td q; };
+    std::unordered_map<int, q_bypass> fa_q;
 };
 
 static void count_uses(const ggml_cgraph* g, fusion_state& fs) {
@@ -768,8 +833,13 @@ static bool order_preserving_view_of(const fusion_state& fs, const ggml_tensor* 
     return false;
 }
 
+static inline bool overlaps_range(const void* a, size_t na, const void* b, size_t nb) {
+    return (const char*)a < (const char*)b + nb && (const char*)b < (const char*)a + na;
+}
+
 // MUL_MAT [-> views] [-> CONT of an order-preserving view] [-> views] [-> ADD bias]
-static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
+static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered, const ggml_tensor* src1_pre = nullptr,
+                            int pre_act = 0) {
     ggml_tensor* mm = g->nodes[i];
     if (!ggml_is_contiguous(mm) || (mm->flags & GGML_TENSOR_FLAG_OUTPUT)) return -2;
     std::vector<int> chain;
@@ -786,6 +856,8 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
     }
     mm_fusion fz;
     fz.out = (float*)cur->data;
+    fz.src1_pre = src1_pre;
+    fz.pre_act = pre_act;
     const int64_t M = mm->ne[0], N = mm->ne[1];
     if (j >= 0) {
         ggml_tensor* add = g->nodes[j];
@@ -830,7 +902,8 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
             }
         }
     }
-    if (chain.empty()) return -2;
+    if (chain.empty() && !src1_pre) return -2;
+    if (src1_pre && overlaps_range(fz.out, ggml_nbytes(mm), src1_pre->data, ggml_nbytes(src1_pre))) return -2;
     // the fused kernel writes `out` while other CTAs may still be reading the operands: `out` must not live in memory gallocr
     // recycled from an operand that is dead in graph order (e.g. the im2col matrix) -- run unfused then
     auto overlaps = [](const void* a, size_t na, const void* b, size_t nb) { return (const char*)a < (const char*)b + nb && (const char*)b < (const char*)a + na; };
@@ -988,6 +1061,7 @@ static int emit_conv(b200_context* ctx, const conv_match& m, const conv_prologue
     const int64_t C = src->ne[2], N = src->ne[3], H = src->ne[1], W = src->ne[0];
     const void* wp = get_packed_conv_weight(ctx, m.w, &launches);
     if (!wp) return -1;
+    const bool w_fresh = launches > 0;      // packed by a kernel of this very graph execution: not yet a constant
     void* shadow = ws_alloc(ctx, (size_t)(N * m.OH * m.OW * C * 2));
     if (!shadow) return -1;
     float* stats = nullptr;
@@ -1006,6 +1080,7 @@ static int emit_conv(b200_context* ctx, const conv_match& m, const conv_prologue
     c.KH = (int)m.w->ne[1]; c.KW = (int)m.w->ne[0];
     c.dil = m.dil; c.pad = c.dil * (c.KH - 1) / 2;
     c.D = m.out; c.bias = m.bias; c.residual = m.residual;
+    c.w_const = (ctx->opt_early_weights && !w_fresh) ? 1 : 0;     // at least the NHWC transform precedes this launch in the graph
     size_t wsb = b200_conv_tc_workspace_bytes(ctx->info, c);
     void* w = wsb ? ws_alloc(ctx, wsb) : nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1145,6 +1220,150 @@ static int try_fuse_cont_cast(b200_context* ctx, ggml_cgraph* g, fusion_state& f
     return n;
 }
 
+// `v` reaches `root` through views that keep root's flat element order (read-only alias: no consumer-count conditions)
+static bool same_order_view_of(const ggml_tensor* v, const ggml_tensor* root) {
+    for (int depth = 0; depth < 8; ++depth) {
+        if (v == root) return true;
+        if (!is_view_op(v) || v->op == GGML_OP_NONE || !v->src[0]) return false;
+        if (v->data != root->data || !ggml_is_contiguous(v) || ggml_nelements(v) != ggml_nelements(root)) return false;
+        v = v->src[0];
+    }
+    return false;
+}
+
+// memory a (possibly strided) view can touch: the whole tensor it is a view of
+static inline void base_range(const ggml_tensor* t, const char** lo, size_t* n) {
+    const ggml_tensor* b = t->view_src ? t->view_src : t;
+    *lo = (const char*)b->data;
+    *n = ggml_nbytes(b);
+}
+
+// If the next working node after j is a MUL_MAT with F16 weights whose activation operand is `produced` (f32, contiguous; possibly
+// through order-keeping views), return that operand: its producer can write the f16 copy itself and register it in the pack cache.
+static const ggml_tensor* next_mm_activation(b200_context* ctx, const ggml_cgraph* g, const fusion_state& fs, int j, const ggml_tensor* produced) {
+    if (!ctx->opt_tc_gemm || !ggml_is_contiguous(produced) || produced->type != GGML_TYPE_F32) return nullptr;
+    const int nn = next_node(g, fs, j);
+    if (nn < 0) return nullptr;
+    const ggml_tensor* mm = g->nodes[nn];
+    if (mm->op != GGML_OP_MUL_MAT || !mm->src[0] || mm->src[0]->type != GGML_TYPE_F16) return nullptr;
+    const ggml_tensor* act = mm->src[1];
+    if (!act || act->type != GGML_TYPE_F32 || !same_order_view_of(act, produced)) return nullptr;
+    if ((act->ne[0] * 2) % 16) return nullptr;
+    if (ctx->pack_cache.count(std::make_pair(act, (int)GGML_TYPE_F16))) return nullptr;
+    return act;
+}
+
+// CONT(gate half) -> GELU (in place) -> MUL(x half, .) [-> f16 operand of the next Linear]: the GEGLU tail of FeedForward
+// (src/model/common/block.hpp:194-207) as one pass over the projection output
+static int try_fuse_geglu(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
+    ggml_tensor* c = g->nodes[i];
+    const ggml_tensor* gate = c->src[0];
+    if (c->type != GGML_TYPE_F32 || gate->type != GGML_TYPE_F32 || !ggml_is_contiguous(c) || !single_use(fs, c)) return -2;
+    if (!ggml_are_same_shape(c, gate)) return -2;
+    const int j1 = next_node(g, fs, i);
+    if (j1 < 0) return -2;
+    ggml_tensor* ge = g->nodes[j1];
+    if (ge->op != GGML_OP_UNARY || ggml_get_unary_op(ge) != GGML_UNARY_OP_GELU || ge->src[0] != c || !single_use(fs, ge)) return -2;
+    if (!(ge->flags & GGML_TENSOR_FLAG_COMPUTE) || ge->type != GGML_TYPE_F32 || !ggml_is_contiguous(ge)) return -2;
+    const int j2 = next_node(g, fs, j1);
+    if (j2 < 0) return -2;
+    ggml_tensor* mul = g->nodes[j2];
+    if (mul->op != GGML_OP_MUL || !(mul->flags & GGML_TENSOR_FLAG_COMPUTE) || mul->type != GGML_TYPE_F32 || !ggml_is_contiguous(mul)) return -2;
+    const ggml_tensor* x = mul->src[0] == ge ? mul->src[1] : (mul->src[1] == ge ? mul->src[0] : nullptr);
+    if (!x || x == ge || x->type != GGML_TYPE_F32 || !ggml_are_same_shape(x, mul) || !ggml_are_same_shape(ge, mul)) return -2;
+    // one pass reads x and gate while it writes mul: the destination must not have been placed over either source
+    const char *lo; size_t nb;
+    base_range(x, &lo, &nb);
+    if (tensors_overlap(mul->data, ggml_nbytes(mul), lo, nb)) return -2;
+    base_range(gate, &lo, &nb);
+    if (tensors_overlap(mul->data, ggml_nbytes(mul), lo, nb)) return -2;
+    const ggml_tensor* act = next_mm_activation(ctx, g, fs, j2, mul);
+    void* shadow = act ? ws_alloc(ctx, (size_t)ggml_nelements(mul) * 2) : nullptr;
+    int n = b200_launch_geglu(ctx->stream, b200_make_td(x), b200_make_td(gate), b200_make_td(mul), shadow);
+    if (n < 0 && shadow) { shadow = nullptr; n = b200_launch_geglu(ctx->stream, b200_make_td(x), b200_make_td(gate), b200_make_td(mul), nullptr); }
+    if (n < 0) return -2;
+    if (shadow) ctx->pack_cache[std::make_pair(act, (int)GGML_TYPE_F16)] = operand{shadow, GGML_TYPE_F16, act->ne[0], act->ne[0] * act->ne[1], act->ne[0] * act->ne[1] * act->ne[2]};
+    fs.done[j1] = 1;
+    fs.done[j2] = 1;
+    *covered = 2;
+    return n;
+}
+
+// CONT(permute(q)) whose only consumer is the Q operand of a FLASH_ATTN_EXT (ggml_ext_attention_ext, ggml_extend.hpp:1374-1380): the
+// fused attention kernel reads Q rows through any stride, so the copy is skipped and the permuted view handed over instead --
+// provided nothing between here and the attention node (nor its output) was placed over the view's memory by the allocator.
+static int try_skip_q_cont(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i) {
+    if (!ctx->opt_tc_gemm || !ctx->opt_fused_attn) return -2;
+    ggml_tensor* c = g->nodes[i];
+    const ggml_tensor* src = c->src[0];
+    if (c->type != GGML_TYPE_F32 || src->type != GGML_TYPE_F32 || !ggml_is_contiguous(c) || !ggml_are_same_shape(c, src)) return -2;
+    if (src->nb[0] != 4 || ((uintptr_t)src->data & 3) || c->ne[0] % 8 || c->ne[0] > 192) return -2;
+    int jf = -1;
+    for (int j = i + 1; j < g->n_nodes && j < i + 32; ++j) {
+        const ggml_tensor* t = g->nodes[j];
+        if (t->op == GGML_OP_FLASH_ATTN_EXT && !fs.done[j] && same_order_view_of(t->src[0], c)) { jf = j; break; }
+    }
+    if (jf < 0) return -2;
+    ggml_tensor* fa = g->nodes[jf];
+    const ggml_tensor* q = fa->src[0];
+    if (!order_preserving_view_of(fs, q, c)) return -2;     // c and the views up to q have exactly one consumer each
+    if (q != c && !single_use(fs, q)) return -2;
+    if (fa->src[1]->type != GGML_TYPE_F16 || fa->src[2]->type != GGML_TYPE_F16 || fa->src[1]->ne[0] != fa->src[2]->ne[0]) return -2;
+    float max_bias;
+    memcpy(&max_bias, (const float*)fa->op_params + 1, sizeof(float));
+    if (max_bias != 0.0f) return -2;
+    // q is [d, Lq, H(, N)] over c's flat order: express it over src's strides
+    b200_td qt = b200_make_td(q);
+    if (q->ne[0] != c->ne[0] || q->ne[1] != c->ne[1]) return -2;
+    if (q->ne[2] == c->ne[2] && q->ne[3] == c->ne[3]) {
+        qt.nb[1] = src->nb[1]; qt.nb[2] = src->nb[2]; qt.nb[3] = src->nb[3];
+    } else if (q->ne[3] == 1 && q->ne[2] == c->ne[2] * c->ne[3] && (c->ne[3] == 1 || src->nb[3] == src->nb[2] * (size_t)c->ne[2])) {
+        qt.nb[1] = src->nb[1]; qt.nb[2] = src->nb[2]; qt.nb[3] = src->nb[2] * (size_t)q->ne[2];
+    } else {
+        return -2;
+    }
+    qt.data = src->data;
+    const char* lo; size_t nb;
+    base_range(src, &lo, &nb);
+    for (int j = i + 1; j <= jf; ++j) {
+        const ggml_tensor* t = g->nodes[j];
+        if (is_view_op(t) || ggml_is_empty(t)) continue;
+        if (tensors_overlap(t->data, ggml_nbytes(t), lo, nb)) return -2;
+        if (t->op == GGML_OP_CPY && t->src[1] && tensors_overlap(t->src[1]->data, ggml_nbytes(t->src[1]), lo, nb)) return -2;
+    }
+    fs.fa_q[jf] = fusion_state::q_bypass{c, qt};
+    return 0;
+}
+
+static int try_fuse_flash_attn(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
+    ggml_tensor* fa = g->nodes[i];
+    fa_fusion fz;
+    auto it = fs.fa_q.find(i);
+    if (it != fs.fa_q.end()) { fz.q_td = &it->second.q; fz.q_cont = it->second.cont; }
+    if (!(fa->flags & GGML_TENSOR_FLAG_OUTPUT)) fz.shadow_act = next_mm_activation(ctx, g, fs, i, fa);
+    *covered = 0;
+    return op_flash_attn(ctx, fa, &fz);
+}
+
+// SILU(emb) -> MUL_MAT(W, .) [-> ADD bias]: the per-ResBlock embedding projection (block.hpp:150-156) as one GEMV that applies
+// the SiLU while it stages the activation row
+static int try_fuse_silu_gemv(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
+    ggml_tensor* u = g->nodes[i];
+    if (!ctx->opt_gemv || ggml_get_unary_op(u) != GGML_UNARY_OP_SILU || u->type != GGML_TYPE_F32 || !single_use(fs, u)) return -2;
+    const ggml_tensor* x = u->src[0];
+    if (x->type != GGML_TYPE_F32 || !ggml_is_contiguous(x) || !ggml_is_contiguous(u) || !ggml_are_same_shape(x, u)) return -2;
+    const int j = next_node(g, fs, i);
+    if (j < 0) return -2;
+    ggml_tensor* mm = g->nodes[j];
+    if (mm->op != GGML_OP_MUL_MAT || mm->src[1] != u || !(mm->flags & GGML_TENSOR_FLAG_COMPUTE)) return -2;
+    int cov = 0;
+    const int n = try_fuse_mul_mat(ctx, g, fs, j, &cov, x, 1);
+    if (n < 0) return -2;
+    fs.done[j] = 1;
+    *covered = cov + 1;
+    return n;
+}
+
 // IM2COL -> ...   or   UPSCALE(nearest x2) -> IM2COL -> ...
 static int try_fuse_conv(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
     ggml_tensor* t = g->nodes[i];
@@ -1178,6 +1397,7 @@ static int try_fuse_conv(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, in
 static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, uint64_t* launches, uint64_t* nodes) {
     fusion_state fs;
     ctx->pack_cache.clear();
+    ctx->launched_any = false;
     const bool fuse = ctx->opt_fusion && cgraph->n_nodes > 1;
     if (fuse) count_uses(cgraph, fs);
     else fs.done.assign((size_t)cgraph->n_nodes, 0);
@@ -1192,7 +1412,12 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
             if (t->op == GGML_OP_MUL_MAT) n = try_fuse_mul_mat(ctx, cgraph, fs, i, &covered);
             else if (t->op == GGML_OP_GROUP_NORM || t->op == GGML_OP_NORM) n = try_fuse_norm(ctx, cgraph, fs, i, &covered);
             else if ((t->op == GGML_OP_IM2COL || t->op == GGML_OP_UPSCALE) && ctx->opt_tc_gemm && ctx->opt_implicit_conv) n = try_fuse_conv(ctx, cgraph, fs, i, &covered);
-            else if (t->op == GGML_OP_CONT) n = try_fuse_cont_cast(ctx, cgraph, fs, i, &covered);
+            else if (t->op == GGML_OP_CONT) {
+                n = try_fuse_cont_cast(ctx, cgraph, fs, i, &covered);
+                if (n == -2 && ctx->opt_chain_fusion) n = try_fuse_geglu(ctx, cgraph, fs, i, &covered);
+                if (n == -2 && ctx->opt_chain_fusion) n = try_skip_q_cont(ctx, cgraph, fs, i);
+            } else if (t->op == GGML_OP_UNARY && ctx->opt_chain_fusion) n = try_fuse_silu_gemv(ctx, cgraph, fs, i, &covered);
+            else if (t->op == GGML_OP_FLASH_ATTN_EXT && ctx->opt_chain_fusion) n = try_fuse_flash_attn(ctx, cgraph, fs, i, &covered);
             if (n >= 0) {
                 ctx->stats.fused_nodes += (uint64_t)covered;
                 *nodes += (uint64_t)covered;
@@ -1205,6 +1430,7 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
         }
         *launches += (uint64_t)n;
         *nodes += 1;
+        if (n > 0) ctx->launched_any = true;
 #ifdef B200_DEBUG_SYNC
         {
             cudaError_t e = cudaStreamSynchronize(ctx->stream);

@@ -46,6 +46,9 @@ struct b200_context {
     bool opt_cuda_graphs = false;
     bool opt_fused_attn = true;       // single-kernel FLASH_ATTN_EXT (0 = GEMM + softmax + GEMM through workspace)
     bool opt_implicit_conv = true;    // IM2COL+MUL_MAT chains as TMA halo-tile implicit GEMM (0 = materialised im2col)
+    bool opt_early_weights = false;   // tcgen05 GEMM fetches its first ring-full of constant weights before the PDL wait
+    bool opt_chain_fusion = true;     // GEGLU tail, Q read in place by attention, f16 operand copies written by their producers
+    bool opt_gemv = true;             // MUL_MAT with <= 4 activation rows as a weight-streaming GEMV instead of a tcgen05 tile
     bool opt_kernel_timing = false;   // per-launch CUDA events around every tcgen05 GEMM (roofline pass only)
     bool timing_pending = false;
     struct kt_pair { cudaEvent_t start, stop; double flops; };
@@ -59,6 +62,7 @@ struct b200_context {
     // per-graph-execution cache of packed (type-converted) contraction operands, keyed by ggml tensor node
     std::unordered_map<std::pair<const ggml_tensor*, int>, b200_operand, b200_pack_key_hash> pack_cache;
     bool capturing = false, capture_overflow = false;
+    bool launched_any = false;        // a kernel of the current graph execution has been launched
 
     ~b200_context();
 };

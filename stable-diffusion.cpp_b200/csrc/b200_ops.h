@@ -8,6 +8,8 @@
 // ---- elementwise.cu ------------------------------------------------------------------------
 enum b200_binop { B200_ADD = 0, B200_SUB = 1, B200_MUL = 2, B200_DIV = 3 };
 int b200_launch_binary(cudaStream_t s, int op, const b200_td& a, const b200_td& b, const b200_td& dst);
+// dst = x * gelu_tanh(gate) (f32, row-vectorisable views); optional contiguous f16 copy of dst for the contraction that follows
+int b200_launch_geglu(cudaStream_t s, const b200_td& x, const b200_td& gate, const b200_td& dst, void* dst16);
 // unary ops use ggml_unary_op numbering; p0/p1 are op parameters (unused by most)
 int b200_launch_unary(cudaStream_t s, int unary_op, const b200_td& src, const b200_td& dst);
 // extra scalar ops that are separate GGML_OPs
@@ -68,11 +70,17 @@ struct b200_gemm_args {
     const float* residual;  // optional [N][M] like D (added after bias)
     int64_t     ldr;
     int         act;        // 0 none, 1 SiLU, 2 GELU(tanh)
+    int         early;      // bit 0: A, bit 1: B is a constant (weight) operand no kernel of this graph writes -> may be fetched before the PDL wait
     void*       trace;      // optional device buffer of 8 uint64: phase timestamps of CTA (0,0,0) (tools/gemm_bench)
 };
 // returns kernels launched, or -1 if the shape/alignment is not supported by the TMA path (caller falls back)
 int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g, void* workspace, size_t workspace_bytes);
 size_t b200_gemm_tc_workspace_bytes(const b200_device_info& dev, const b200_gemm_args& g);
+
+// ---- gemv.cu: MUL_MAT with N <= 4 activation rows, F16/BF16 weights read in place; pre_act 1 = SiLU on the activation -----
+bool b200_gemv_supported(int wtype, int64_t M, int64_t N, int64_t K, const void* W, int64_t lda, const void* X);
+int b200_launch_gemv(cudaStream_t s, int wtype, const void* W, int64_t lda, const float* X, int64_t ldx, float* D, int64_t ldd, int64_t M, int64_t N,
+                     int64_t K, const float* bias, const float* residual, int64_t ldr, int pre_act);
 
 // ---- implicit-GEMM convolution (gemm_tc.cu conv mode + conv_prep.cu operand producers) ------------------------
 struct b200_conv_args {
@@ -83,6 +91,7 @@ struct b200_conv_args {
     float* D;               // f32 [N][OC][H][W] == ggml [W,H,OC,N]
     const float* bias;      // per OC or null
     const float* residual;  // same layout as D or null
+    int w_const;            // w_packed was not produced by a kernel of this graph execution (may be fetched before the PDL wait)
 };
 bool b200_conv_tc_supported(int64_t N, int64_t H, int64_t W, int64_t C, int64_t OC, int KH, int KW, int s0, int s1, int p0, int p1, int d0, int d1);
 size_t b200_conv_tc_workspace_bytes(const b200_device_info& dev, const b200_conv_args& c);
@@ -99,4 +108,4 @@ int b200_launch_pack_conv_weight(cudaStream_t s, const void* w, void* out, int K
 // dst f32 [dv, H, Lq, N]
 // vt = packed V^T f16 [Lk_pad, dv, Hkv, N]; returns -1 when the shape is outside the fused kernel's envelope
 int b200_launch_flash_attn_fused(cudaStream_t s, const b200_td& q, const b200_td& k, const void* vt, int64_t Lk_pad, const b200_td& v,
-                                 const b200_td* mask, const b200_td& dst, float scale);
+                                 const b200_td* mask, const b200_td& dst, float scale, void* dst16 = nullptr);

@@ -36,6 +36,8 @@ struct FaParams {
     int64_t q_nb1, q_nb2, q_nb3;   // bytes
     float* dst;
     int64_t dst_nb1, dst_nb2, dst_nb3;   // bytes: head, query, batch
+    __half* dst16;                       // optional f16 copy of dst, same element layout (byte strides dst_nb / 2): the operand of the
+                                         // output projection that follows, written here instead of by a separate pack kernel
     const __half* mask;
     int64_t m_nb1, m_nb2, m_nb3;
     int m_ne2, m_ne3;
@@ -276,6 +278,7 @@ __global__ void __launch_bounds__(192, 1) k_flash_attn(const __grid_constant__ C
         tc_fence_after();
         const float inv = l > 0.f ? 1.0f / l : 0.f;
         float* drow = (float*)((char*)p.dst + (int64_t)h * p.dst_nb1 + (int64_t)qi * p.dst_nb2 + (int64_t)nb * p.dst_nb3);
+        __half* drow16 = p.dst16 ? (__half*)((char*)p.dst16 + (((int64_t)h * p.dst_nb1 + (int64_t)qi * p.dst_nb2 + (int64_t)nb * p.dst_nb3) >> 1)) : nullptr;
         const int dv = p.d;
 #pragma unroll 1
         for (int c0 = 0; c0 < p.dv16; c0 += 16) {
@@ -286,6 +289,22 @@ __global__ void __launch_bounds__(192, 1) k_flash_attn(const __grid_constant__ C
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
                     if (c0 + i < dv) drow[c0 + i] = __uint_as_float(o[i]) * inv;
+                if (drow16) {
+                    if (c0 + 16 <= dv) {       // d % 8 == 0 and 16-byte aligned rows: two 16-byte stores
+                        uint32_t h[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const __half2 v = __floats2half2_rn(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+                            h[i] = *(const uint32_t*)&v;
+                        }
+                        *(uint4*)(drow16 + c0) = make_uint4(h[0], h[1], h[2], h[3]);
+                        *(uint4*)(drow16 + c0 + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < dv) drow16[c0 + i] = __float2half_rn(__uint_as_float(o[i]) * inv);
+                    }
+                }
             }
         }
         tc_fence_before();
@@ -329,7 +348,7 @@ int launch_fa(cudaStream_t s, dim3 grid, const CUtensorMap& tk, const CUtensorMa
 
 // vt: packed V^T, f16 [Lk_pad, dv, Hkv, N] dense (row stride Lk_pad elements)
 int b200_launch_flash_attn_fused(cudaStream_t s, const b200_td& q, const b200_td& k, const void* vt, int64_t Lk_pad, const b200_td& v,
-                                 const b200_td* mask, const b200_td& dst, float scale) {
+                                 const b200_td* mask, const b200_td& dst, float scale, void* dst16) {
     const int64_t d = q.ne[0], Lq = q.ne[1], H = q.ne[2], NB = q.ne[3];
     const int64_t Lk = k.ne[1], Hkv = k.ne[2], dv = v.ne[0];
     if (d != dv || d % 8 || d > 192 || k.type != GGML_TYPE_F16) return -1;
@@ -357,6 +376,9 @@ int b200_launch_flash_attn_fused(cudaStream_t s, const b200_td& q, const b200_td
     p.q_nb1 = q.nb[1]; p.q_nb2 = q.nb[2]; p.q_nb3 = q.nb[3];
     p.dst = (float*)dst.data;
     p.dst_nb1 = dst.nb[1]; p.dst_nb2 = dst.nb[2]; p.dst_nb3 = dst.nb[3];
+    // the f16 copy needs 16-byte aligned rows for its vector stores
+    p.dst16 = (dst16 && !((uintptr_t)dst16 & 15) && !(dst.nb[1] & 31) && !(dst.nb[2] & 31) && !(dst.nb[3] & 31)) ? (__half*)dst16 : nullptr;
+    if (dst16 && !p.dst16) return -1;
     if (mask) {
         p.mask = (const __half*)mask->data;
         p.m_nb1 = mask->nb[1]; p.m_nb2 = mask->nb[2]; p.m_nb3 = mask->nb[3];

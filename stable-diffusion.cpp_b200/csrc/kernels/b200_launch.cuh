@@ -45,8 +45,7 @@ inline unsigned b200_launch_attrs(cudaLaunchAttribute* attrs, unsigned cluster_z
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t b200_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;

@@ -110,6 +110,33 @@ __global__ void k_copy_rows4(const char* __restrict__ a, strides3 sa, char* __re
     }
 }
 
+// GEGLU tail of the reference's FeedForward (src/model/common/block.hpp:194-207): dst = x * gelu_tanh(gate), x and gate the two
+// halves (strided row views) of one projection output.  Replaces CONT(gate) + GELU + MUL (+ the f16 operand pack of the Linear
+// that follows, through the optional contiguous f16 shadow d16).  Arithmetic is the unfused kernels' own: f32 gelu, one multiply.
+__device__ __forceinline__ float gelu_tanh_f32(float x) {
+    return 0.5f * x * (1.0f + tanhf(0.79788456080286535587989211986876f * x * (1.0f + 0.044715f * x * x)));
+}
+__global__ void k_geglu_rows4(const char* __restrict__ a, strides3 sa, const char* __restrict__ b, strides3 sb, char* __restrict__ d, strides3 sd,
+                              __half* __restrict__ d16, rows4 r) {
+    pdl_wait();
+    pdl_launch_dependents();
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < r.total; idx += gridDim.x * blockDim.x) {
+        uint32_t c, i1, i2, i3;
+        rows4_decode(r, idx, c, i1, i2, i3);
+        const float4 x = *(const float4*)(a + i1 * sa.nb1 + i2 * sa.nb2 + i3 * sa.nb3 + (int64_t)c * 16);
+        const float4 g = *(const float4*)(b + i1 * sb.nb1 + i2 * sb.nb2 + i3 * sb.nb3 + (int64_t)c * 16);
+        const float4 y = make_float4(x.x * gelu_tanh_f32(g.x), x.y * gelu_tanh_f32(g.y), x.z * gelu_tanh_f32(g.z), x.w * gelu_tanh_f32(g.w));
+        *(float4*)(d + i1 * sd.nb1 + i2 * sd.nb2 + i3 * sd.nb3 + (int64_t)c * 16) = y;
+        if (d16) {   // dst is contiguous: chunk idx is flat element 4 * idx
+            const __half2 lo = __floats2half2_rn(y.x, y.y), hi = __floats2half2_rn(y.z, y.w);
+            uint2 u;
+            u.x = *(const uint32_t*)&lo;
+            u.y = *(const uint32_t*)&hi;
+            *(uint2*)(d16 + (size_t)idx * 4) = u;
+        }
+    }
+}
+
 // concat along dim >= 1 of row-contiguous 4-byte tensors: destination row -> which source, then a 16-byte copy
 __global__ void k_concat_rows4(const char* __restrict__ a, strides3 sa, const char* __restrict__ b, strides3 sb, char* __restrict__ d, strides3 sd,
                                rows4 r, int dim, uint32_t a_ne_dim) {
@@ -627,6 +654,18 @@ __global__ void k_transpose_16(const char* __restrict__ src, uint16_t* __restric
 // ================================================================================================
 // launchers
 // ================================================================================================
+int b200_launch_geglu(cudaStream_t s, const b200_td& x, const b200_td& gate, const b200_td& dst, void* dst16) {
+    if (x.type != GGML_TYPE_F32 || gate.type != GGML_TYPE_F32 || dst.type != GGML_TYPE_F32) return -1;
+    if (!same_shape(x, dst) || !same_shape(gate, dst) || !rows4_ok(x) || !rows4_ok(gate) || !rows4_ok(dst)) return -1;
+    if (dst16 && (!td_contiguous(dst, 4) || ((uintptr_t)dst16 & 7))) return -1;
+    rows4 r;
+    if (!make_rows4(dst, &r)) return -1;
+    if (r.total == 0) return 0;
+    b200_launch(k_geglu_rows4, dim3(grid_for(r.total)), dim3(kThreads), 0, s, (const char*)x.data, st3(x), (const char*)gate.data, st3(gate),
+                (char*)dst.data, st3(dst), (__half*)dst16, r);
+    return 1;
+}
+
 int b200_launch_binary(cudaStream_t s, int op, const b200_td& a, const b200_td& b, const b200_td& dst) {
     switch (op) {
         case B200_ADD: return launch_binary_op<B200_ADD>(s, a, b, dst);

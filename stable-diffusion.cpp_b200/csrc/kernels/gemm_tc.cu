@@ -56,6 +56,7 @@ struct GemmKParams {
     int conv_KW;       // filter width (taps = KH * KW)
     int conv_cblocks;  // IC / 64
     int conv_pad, conv_dil;
+    int early;         // operands that may be fetched before griddepcontrol.wait (bit 0 = A, bit 1 = B): constant weights
     unsigned long long* trace;   // optional: CTA (0,0,0) writes %globaltimer at its phase boundaries (tools/gemm_bench only)
 };
 
@@ -129,37 +130,52 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
     if (threadIdx.x == 0) TRACE(1);
-    // everything above is on-chip setup (barriers, TMEM, descriptor prefetch): under PDL it overlaps the predecessor's tail
-    pdl_wait();
-    pdl_launch_dependents();
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % C::STAGES;
-                const uint32_t ph = (i / C::STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
-                uint8_t* sa = smem + s * C::STAGE_BYTES;
-                uint8_t* sb = sa + A_STAGE_BYTES;
-                const int k = (kb0 + i) * BK;
-                if (p.conv) {
-                    const int kb = kb0 + i;
-                    const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
-                    const int kh = tap / p.conv_KW, kw = tap - kh * p.conv_KW;
-                    const int y0 = m0 / p.conv_W, x0 = m0 - y0 * p.conv_W;
-                    // the box {64 ch, BW, BH} lands as 128 rows of 128 bytes: row = by * BW + bx == pixel m0 + row; out-of-image
-                    // (halo / tail) coordinates are zero-filled by the TMA unit, which is exactly the conv's zero padding
-                    tma_load_4d(sa, &tmA, &full_bar[s], cb * 64, x0 + kw * p.conv_dil - p.conv_pad, y0 + kh * p.conv_dil - p.conv_pad, i2);
-                    tma_load_4d(sb, &tmB, &full_bar[s], k, n0, 0, 0);
-                } else {
-                    tma_load_4d(sa, &tmA, &full_bar[s], k, m0, i2 / p.r2, i3 / p.r3);
-                    tma_load_4d(sb, &tmB, &full_bar[s], k, n0, i2, i3);
-                }
-            }
+    // Everything above is on-chip setup (barriers, TMEM, descriptor prefetch): under PDL it overlaps the predecessor's tail.
+    // So does the first ring-full of the CONSTANT operand (p.early: bit 0 = A, bit 1 = B are model weights that no kernel of this
+    // graph writes): the producer thread issues those TMA loads BEFORE griddepcontrol.wait, which hides the cold-HBM latency of the
+    // weight stream behind the previous kernel; the activation operand follows after the wait.
+    auto issue = [&](int i, int which) {
+        const int s = i % C::STAGES;
+        uint8_t* sa = smem + s * C::STAGE_BYTES;
+        uint8_t* sb = sa + A_STAGE_BYTES;
+        const int k = (kb0 + i) * BK;
+        if (p.conv) {
+            const int kb = kb0 + i;
+            const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
+            const int kh = tap / p.conv_KW, kw = tap - kh * p.conv_KW;
+            const int y0 = m0 / p.conv_W, x0 = m0 - y0 * p.conv_W;
+            // the box {64 ch, BW, BH} lands as 128 rows of 128 bytes: row = by * BW + bx == pixel m0 + row; out-of-image
+            // (halo / tail) coordinates are zero-filled by the TMA unit, which is exactly the conv's zero padding
+            if (which & 1) tma_load_4d(sa, &tmA, &full_bar[s], cb * 64, x0 + kw * p.conv_dil - p.conv_pad, y0 + kh * p.conv_dil - p.conv_pad, i2);
+            if (which & 2) tma_load_4d(sb, &tmB, &full_bar[s], k, n0, 0, 0);
+        } else {
+            if (which & 1) tma_load_4d(sa, &tmA, &full_bar[s], k, m0, i2 / p.r2, i3 / p.r3);
+            if (which & 2) tma_load_4d(sb, &tmB, &full_bar[s], k, n0, i2, i3);
         }
-    } else if (warp == 1) {
+    };
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        const int pre = p.early ? min(nkb, C::STAGES) : 0;
+        for (int i = 0; i < pre; ++i) {
+            mbar_expect_tx(&full_bar[i], C::STAGE_BYTES);     // first pass over the ring: every slot is free
+            issue(i, p.early);
+        }
+        pdl_wait();
+        pdl_launch_dependents();
+        for (int i = 0; i < pre; ++i) issue(i, 3 & ~p.early);
+        for (int i = pre; i < nkb; ++i) {
+            const int s = i % C::STAGES;
+            const uint32_t ph = (i / C::STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+            issue(i, 3);
+        }
+    } else {
+        pdl_wait();
+        pdl_launch_dependents();
+    }
+
+    if (warp == 1) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc(FMT, BM, BN);
         for (int i = 0; i < nkb; ++i) {
@@ -184,7 +200,7 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
             }
             __syncwarp();
         }
-    } else {
+    } else if (warp >= 2) {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                       // TMEM lane quadrant this warp may access
         const int ml = q * 32 + lane;                 // row inside the tile
@@ -430,8 +446,7 @@ cudaError_t launch_cfg(cudaStream_t s, dim3 grid, const CUtensorMap& ta, const C
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(192);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
@@ -477,6 +492,7 @@ int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     kp.bias = g.bias; kp.bias_mode = g.bias ? g.bias_mode : 0;
     kp.residual = g.residual; kp.ldr = g.ldr; kp.r_batch_stride = g.d_batch_stride;
     kp.act = g.act;
+    kp.early = g.early & 3;
     kp.trace = (unsigned long long*)g.trace;
     const int64_t mt = (g.M + BM - 1) / BM, nt = (g.N + pl.bn - 1) / pl.bn;
     if (mt > 0x7fffffff || nt > 65535 || g.batch * pl.splits > 65535) return -1;
@@ -556,6 +572,7 @@ int b200_launch_conv_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     kp.bias = c.bias; kp.bias_mode = c.bias ? 2 : 0;
     kp.residual = c.residual; kp.ldr = c.H * c.W; kp.r_batch_stride = c.OC * c.H * c.W;
     kp.act = 0;
+    kp.early = c.w_const ? 2 : 0;
     kp.conv = 1; kp.conv_W = (int)c.W; kp.conv_KW = c.KW; kp.conv_cblocks = (int)(c.C / 64); kp.conv_pad = c.pad; kp.conv_dil = c.dil;
     const int64_t mt = (g.M + BM - 1) / BM, nt = (g.N + pl.bn - 1) / pl.bn;
     if (nt > 65535 || g.batch * pl.splits > 65535) return -1;

@@ -87,6 +87,25 @@ void fill_uniform(float* dst, int64_t n, uint64_t seed, float center, float amp)
     for (auto& t : th) t.join();
 }
 
+// rows [0, n) in blocks over up to 16 host threads (weight type conversion of multi-GB synthetic checkpoints)
+template <typename F>
+void parallel_rows(int64_t n, int64_t block, F fn) {
+    const int64_t nblocks = (n + block - 1) / block;
+    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::atomic<int64_t> next{0};
+    auto work = [&]() {
+        for (;;) {
+            int64_t b = next.fetch_add(1);
+            if (b >= nblocks) break;
+            fn(b * block, std::min(n, (b + 1) * block));
+        }
+    };
+    if (nblocks < 4) { work(); return; }
+    std::vector<std::thread> th;
+    for (unsigned i = 0; i < nt; ++i) th.emplace_back(work);
+    for (auto& t : th) t.join();
+}
+
 // ---------------------------------------------------------------- synthetic weight manager
 // All parameters live in ONE buffer on the compute backend for the whole life of the model
 // (the reference keeps weights resident too: free_compute_params=false, unet.hpp:838).
@@ -152,8 +171,12 @@ struct SyntheticWeights : public RunnerWeightManager {
                 // quantize row by row (rows are ne[0] long)
                 int64_t nrows = n / t->ne[0];
                 size_t row_bytes = ggml_row_size(t->type, t->ne[0]);
-                for (int64_t r = 0; r < nrows; ++r)
-                    tt->from_float_ref(tmp.data() + r * t->ne[0], conv.data() + r * row_bytes, t->ne[0]);
+                const int64_t ne0 = t->ne[0];
+                const float* srcp = tmp.data();
+                uint8_t* dstp = conv.data();
+                parallel_rows(nrows, std::max<int64_t>(1, (1 << 18) / std::max<int64_t>(ne0, 1)), [&](int64_t r0, int64_t r1) {
+                    for (int64_t r = r0; r < r1; ++r) tt->from_float_ref(srcp + r * ne0, dstp + r * row_bytes, ne0);
+                });
                 ggml_backend_tensor_set(t, conv.data(), 0, ggml_nbytes(t));
             }
             bytes += ggml_nbytes(t);

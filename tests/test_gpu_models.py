@@ -121,3 +121,27 @@ def test_flux_tiny_vs_live_cpu(b200):
     assert np.isfinite(outs[dev]).all()
     # bf16 weights/activations (8-bit mantissa) + the oracle's f16-accumulating flash attention: compare at bf16 noise level
     assert rel(outs[dev], outs["CPU"]) < 3e-2, f"rel_l2 {rel(outs[dev], outs['CPU']):.2e}"
+
+
+@pytest.mark.parametrize("arch,shape,cshape", [("unet_tiny", (1, 4, 16, 16), (1, 77, 768)), ("sd15_unet", (1, 4, 64, 64), (1, 77, 768))])
+def test_producer_side_fusions_are_bit_identical(b200, arch, shape, cshape):
+    """GEGLU tail, Q read in place by the attention kernel, f16 operand copies written by their producers and the early weight fetch
+    move work between kernels without changing one rounding: outputs must equal the unfused execution bit for bit (also across the
+    eager first call, the CUDA-graph capture and its replays)."""
+    h, dev = b200
+    x = h.randn(42, shape); ctx = h.randn(43, cshape); t = np.array([999.0], np.float32)
+    m = h.model(dev, arch, "f16", 1, 1234, 0)
+    outs = [m.forward(x, t, ctx)[0] for _ in range(3)]            # eager, capture, replay
+    st = m.stats()
+    m.set_option("chain_fusion", 0)
+    m.set_option("early_weights", 0)
+    plain = [m.forward(x, t, ctx)[0] for _ in range(2)]
+    st2 = m.stats()
+    m.set_option("fusion", 0)                                      # one kernel per ggml node
+    unfused = m.forward(x, t, ctx)[0]
+    m.close()
+    for o in outs[1:] + plain:
+        assert np.array_equal(outs[0], o)
+    assert st["kernel_launches"] / st["graphs"] < (st2["kernel_launches"] - st["kernel_launches"]) / (st2["graphs"] - st["graphs"])
+    # fusion == 0 differs only where an epilogue adds bias / residual in a different order than separate ADD nodes: rounding level
+    assert rel(outs[0], unfused) < 1e-3

@@ -53,7 +53,8 @@ def test_soft_max(b200, shape):
 
 
 @pytest.mark.parametrize("wt", ["f16", "f32", "bf16"])
-@pytest.mark.parametrize("M,N,K", [(320, 4096, 320), (2560, 1024, 640), (1280, 77, 768), (320, 64, 2880), (1280, 256, 11520), (64, 33, 40), (9, 5, 36)])
+@pytest.mark.parametrize("M,N,K", [(320, 4096, 320), (2560, 1024, 640), (1280, 77, 768), (320, 64, 2880), (1280, 256, 11520), (64, 33, 40), (9, 5, 36),
+                                   (1280, 1, 320), (320, 1, 1280), (1283, 3, 2816), (640, 4, 1280), (1280, 5, 1280)])   # N <= 4: weight-streaming GEMV
 def test_mul_mat(b200, wt, M, N, K):
     w, x = f(M, K) / np.sqrt(K), f(N, K)
     g, c = both(b200, "mul_mat", [w, x], [wt, "f32"])
