@@ -134,6 +134,72 @@ def mul_mat(w, x, wtype="f32"):
     return (x.astype(np.float64) @ w.astype(np.float64).T).astype(F32)
 
 
+# ------------------------------------------------------------------------------------------------
+# Q8_0   (block_q8_0 {f16 d; int8 qs[32]}: ggml-common.h:251-255; quantize_row_q8_0_ref / dequantize_row_q8_0: ggml-quants.c;
+#         ggml_vec_dot_q8_0_q8_0: ggml-cpu/quants.c -- sum over blocks of int32(sum q_w * q_x) * (d_w * d_x), f32 accumulation)
+# ------------------------------------------------------------------------------------------------
+def quant_q8_0(x):
+    """rows of length K (K % 32 == 0) -> (d [.., K/32] as f16-rounded f32, q [.., K/32, 32] int8).  d = amax / 127 is computed in f32 and the
+    quants use 1/d of that f32 value (NOT of the stored f16 d), exactly as quantize_row_q8_0_ref does."""
+    x = np.asarray(x, F32)
+    b = x.reshape(x.shape[:-1] + (x.shape[-1] // 32, 32))
+    amax = np.max(np.abs(b), axis=-1)
+    d = (amax / F32(127.0)).astype(F32)
+    inv = np.where(d != 0, F32(1.0) / np.where(d != 0, d, F32(1.0)), F32(0.0)).astype(F32)
+    v = (b * inv[..., None]).astype(F32)
+    q = (np.sign(v) * np.floor(np.abs(v) + F32(0.5))).astype(np.int8)      # roundf: half away from zero
+    return _f16(d), q
+
+
+def dequant_q8_0(dq):
+    d, q = dq
+    y = (q.astype(F32) * d[..., None]).astype(F32)
+    return y.reshape(y.shape[:-2] + (y.shape[-2] * 32,))
+
+
+def mul_mat_q8_0(w, x):
+    """MUL_MAT with Q8_0 weights on the CPU backend: the activation rows are quantised to Q8_0 too (ggml-cpu.c:1480-1510), then
+    per 32-block integer dot products scaled by d_w * d_x."""
+    dw, qw = quant_q8_0(w)
+    dx, qx = quant_q8_0(x)
+    sumi = np.einsum("mbk,nbk->nmb", qw.astype(np.int32), qx.astype(np.int32))
+    return np.einsum("nmb,mb,nb->nm", sumi.astype(np.float64), dw.astype(np.float64), dx.astype(np.float64)).astype(F32)
+
+
+def im2col_3d(x, IC, KD, KH, KW, s=(1, 1, 1), p=(0, 0, 0), d=(1, 1, 1), dst_f16=True):
+    """GGML_OP_IM2COL_3D (ops.cpp:6625-6709): x [N*IC, ID, IH, IW] -> [N*OD, OH, OW, IC*KD*KH*KW], k = ((ic*KD + kd)*KH + kh)*KW + kw;
+    s/p/d are (w, h, d) like the op params."""
+    NIC, ID, IH, IW = x.shape
+    N = NIC // IC
+    OW = (IW + 2 * p[0] - d[0] * (KW - 1) - 1) // s[0] + 1
+    OH = (IH + 2 * p[1] - d[1] * (KH - 1) - 1) // s[1] + 1
+    OD = (ID + 2 * p[2] - d[2] * (KD - 1) - 1) // s[2] + 1
+    xp = np.zeros((N, IC, ID + 2 * p[2], IH + 2 * p[1], IW + 2 * p[0]), F32)
+    xp[:, :, p[2]:p[2] + ID, p[1]:p[1] + IH, p[0]:p[0] + IW] = x.reshape(N, IC, ID, IH, IW)
+    cols = np.zeros((N, OD, OH, OW, IC, KD, KH, KW), F32)
+    for kd in range(KD):
+        for kh in range(KH):
+            for kw in range(KW):
+                patch = xp[:, :, kd * d[2]: kd * d[2] + (OD - 1) * s[2] + 1: s[2], kh * d[1]: kh * d[1] + (OH - 1) * s[1] + 1: s[1],
+                           kw * d[0]: kw * d[0] + (OW - 1) * s[0] + 1: s[0]]
+                cols[:, :, :, :, :, kd, kh, kw] = patch.transpose(0, 2, 3, 4, 1)
+    cols = cols.reshape(N * OD, OH, OW, IC * KD * KH * KW)
+    return _f16(cols) if dst_f16 else cols
+
+
+def conv_3d(w, x, IC, s=(1, 1, 1), p=(0, 0, 0), d=(1, 1, 1)):
+    """ggml_conv_3d (ggml.c:4809-4839): im2col_3d(F16) x F16 kernel [OC*IC, KD, KH, KW] -> [N*OC, OD, OH, OW]."""
+    OCIC, KD, KH, KW = w.shape
+    OC = OCIC // IC
+    cols = im2col_3d(x, IC, KD, KH, KW, s, p, d, dst_f16=True)
+    NOD, OH, OW, K = cols.shape
+    N = x.shape[0] // IC
+    OD = NOD // N
+    y = mul_mat(w.reshape(OC, K), cols.reshape(NOD * OH * OW, K), "f16")       # [N*OD*OH*OW, OC]
+    y = y.reshape(N, OD, OH, OW, OC).transpose(0, 4, 1, 2, 3)
+    return np.ascontiguousarray(y.reshape(N * OC, OD, OH, OW), F32)
+
+
 def conv_2d(w, x, bias=None, s=1, p=0, d=1):
     """ggml_conv_2d (ggml.c:4732-4753): im2col(F16) -> mul_mat against the F16 kernel -> [N, OC, OH, OW] (+ bias)."""
     OC, IC, KH, KW = w.shape

@@ -170,7 +170,16 @@ using operand = b200_operand;
 
 // Bring `t` ([K, rows, b2, b3]) into a form the tcgen05 GEMM can read as type `want`: in place when possible,
 // otherwise packed (converted, K padded to 16 bytes) into workspace.  Returns false on allocation failure.
+static const void* get_dequantised_weight(b200_context* ctx, const ggml_tensor* w, int* launches);
+
 static bool prepare_operand(b200_context* ctx, const ggml_tensor* t, int want, operand* out, int* launches) {
+    if (t->type == GGML_TYPE_Q8_0) {
+        if (want != GGML_TYPE_F16) return false;
+        const void* p = get_dequantised_weight(ctx, t, launches);
+        if (!p) return false;
+        *out = operand{p, GGML_TYPE_F16, t->ne[0], t->ne[0] * t->ne[1], t->ne[0] * t->ne[1] * t->ne[2]};
+        return true;
+    }
     if ((int)t->type == want && tma_compatible(t)) {
         const int64_t es = fp_size(want);
         *out = operand{t->data, want, (int64_t)t->nb[1] / es, (int64_t)t->nb[2] / es, (int64_t)t->nb[3] / es};
@@ -257,7 +266,7 @@ static int launch_tc(b200_context* ctx, const b200_gemm_args& g) {
 static int compute_type_for(const ggml_tensor* src0) {
     // the CPU oracle converts src1 to src0's vec_dot type (ggml-cpu.c:1430-1513): f16 weights -> f16 x f16 with f32
     // accumulation, bf16 -> bf16 x bf16, f32 -> f32 (here: tf32 tensor-core inputs, f32 accumulation)
-    if (src0->type == GGML_TYPE_F16) return GGML_TYPE_F16;
+    if (src0->type == GGML_TYPE_F16 || src0->type == GGML_TYPE_Q8_0) return GGML_TYPE_F16;
     if (src0->type == GGML_TYPE_BF16) return GGML_TYPE_BF16;
     return GGML_TYPE_F32;
 }
@@ -612,8 +621,12 @@ bool b200_supports_op(const b200_device_info&, const ggml_tensor* op) {
         case GGML_OP_IM2COL:
             return (s1->type == GGML_TYPE_F32 || s1->type == GGML_TYPE_F16) && (op->type == GGML_TYPE_F16 || op->type == GGML_TYPE_F32) &&
                    s1->nb[0] == ggml_type_size(s1->type) && ggml_is_contiguous(op);
+        case GGML_OP_IM2COL_3D:
+            return s1->type == GGML_TYPE_F32 && s1->nb[0] == 4 && (op->type == GGML_TYPE_F16 || op->type == GGML_TYPE_F32) && ggml_is_contiguous(op);
         case GGML_OP_MUL_MAT: {
             if (!is_f32(op) || !ggml_is_contiguous(op)) return false;
+            // Q8_0 weights (the Wan config): dequantised once per weight tensor into a cached f16 copy, then the f16 tensor-core path
+            if (s0->type == GGML_TYPE_Q8_0) return ggml_is_contiguous(s0) && s0->ne[0] % 32 == 0 && is_fp(s1) && s1->ne[2] % s0->ne[2] == 0 && s1->ne[3] % s0->ne[3] == 0;
             if (!(s0->type == GGML_TYPE_F32 || s0->type == GGML_TYPE_F16 || s0->type == GGML_TYPE_BF16)) return false;
             if (!is_fp(s1)) return false;
             if (s1->ne[2] % s0->ne[2] || s1->ne[3] % s0->ne[3]) return false;
@@ -728,6 +741,8 @@ static int run_node(b200_context* ctx, ggml_tensor* t) {
             const int32_t* p = t->op_params;
             return b200_launch_im2col(s, b200_make_td(s1), b200_make_td(t), s0->ne[0], s0->ne[1], p[0], p[1], p[2], p[3], p[4], p[5], p[6] == 1);
         }
+        case GGML_OP_IM2COL_3D:
+            return b200_launch_im2col_3d(s, b200_make_td(s1), b200_make_td(t), s0->ne[0], s0->ne[1], s0->ne[2], ggml_get_op_params_i32(t, 9), t->op_params);
         case GGML_OP_MUL_MAT: return op_mul_mat(ctx, t);
         case GGML_OP_FLASH_ATTN_EXT: return op_flash_attn(ctx, t);
         default: return -1;
@@ -957,6 +972,22 @@ static const void* get_packed_conv_weight(b200_context* ctx, const ggml_tensor* 
     return p;
 }
 
+// Q8_0 weight tensor -> contiguous f16 [K, rows, ...] copy, same cache and invalidation rule as the packed conv filters
+static const void* get_dequantised_weight(b200_context* ctx, const ggml_tensor* w, int* launches) {
+    std::lock_guard<std::mutex> lock(g_pw_mutex);
+    auto it = g_packed_weights.find(w->data);
+    if (it != g_packed_weights.end() && it->second.device == ctx->device && it->second.src_bytes == ggml_nbytes(w)) return it->second.ptr;
+    if (ctx->capturing) { ctx->capture_overflow = true; return nullptr; }
+    void* p = nullptr;
+    const int64_t n = ggml_nelements(w);
+    if (cudaMalloc(&p, (size_t)n * 2) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    int r = b200_launch_dequant_q8_0(ctx->stream, w->data, p, n / 32);
+    if (r < 0) { cudaFree(p); return nullptr; }
+    *launches += r;
+    g_packed_weights[w->data] = packed_weight{p, ggml_nbytes(w), ctx->device};
+    return p;
+}
+
 struct conv_match {
     int i_im2col = -1, i_mm = -1;
     std::vector<int> chain;          // nodes covered besides the starting one
@@ -967,6 +998,7 @@ struct conv_match {
     const float* residual = nullptr;
     int64_t OW = 0, OH = 0;
     int dil = 1;
+    bool tokens_out = false;         // 1x1 conv whose result is only consumed as tokens [OC, OW*OH]: `out` is that CONT's buffer
 };
 
 // does node i (IM2COL) start a conv chain the implicit-GEMM kernel can run?  `up` = 2 when the caller feeds the image through
@@ -1025,6 +1057,21 @@ static bool match_conv(const ggml_cgraph* g, const fusion_state& fs, int i, conv
             }
         }
     }
+    // 1x1 conv followed by the image -> token transpose (SpatialTransformer proj_in, block.hpp:548-551: PERMUTE(1,2,0,3) + CONT):
+    // computed as D[pixel][oc] = W . X^T instead, which IS the token layout -- no transpose kernel
+    if (k >= 0 && w->ne[0] == 1 && w->ne[1] == 1 && !(cur->flags & GGML_TENSOR_FLAG_OUTPUT) && single_use(fs, cur)) {
+        const ggml_tensor* c = g->nodes[k];
+        const ggml_tensor* pv = c->op == GGML_OP_CONT ? c->src[0] : nullptr;
+        if (pv && pv->op == GGML_OP_PERMUTE && pv->src[0] == cur && single_use(fs, pv) && c->type == GGML_TYPE_F32 && ggml_is_contiguous(c) &&
+            (c->flags & GGML_TENSOR_FLAG_COMPUTE) && ggml_is_contiguous(cur) && cur->ne[0] == OW && cur->ne[1] == OH && cur->ne[2] == OC && cur->ne[3] == 1 &&
+            c->ne[0] == OC && c->ne[1] == OW && c->ne[2] == OH && c->ne[3] == 1 && pv->nb[0] == cur->nb[2] && pv->nb[1] == cur->nb[0] &&
+            pv->nb[2] == cur->nb[1]) {
+            m->tokens_out = true;
+            m->out = (float*)c->data;
+            m->chain.push_back(k);
+            return true;
+        }
+    }
     // residual add (ResBlock skip / transformer residual) read in the conv epilogue
     if (k >= 0) {
         const ggml_tensor* add = g->nodes[k];
@@ -1053,26 +1100,50 @@ struct conv_prologue {
     const float* gw = nullptr;
     const float* gb = nullptr;
     int act = 0;
+    const void* ready_nhwc = nullptr;   // the NHWC f16 image already exists (tokens are NHWC): skip the transform
 };
 
 static int emit_conv(b200_context* ctx, const conv_match& m, const conv_prologue& pro) {
     int launches = 0;
     const ggml_tensor* src = pro.src;
-    const int64_t C = src->ne[2], N = src->ne[3], H = src->ne[1], W = src->ne[0];
-    const void* wp = get_packed_conv_weight(ctx, m.w, &launches);
-    if (!wp) return -1;
-    const bool w_fresh = launches > 0;      // packed by a kernel of this very graph execution: not yet a constant
-    void* shadow = ws_alloc(ctx, (size_t)(N * m.OH * m.OW * C * 2));
-    if (!shadow) return -1;
-    float* stats = nullptr;
-    if (pro.norm) {
-        stats = (float*)ws_alloc(ctx, (size_t)(N * pro.n_groups * 2 * sizeof(float)));
-        if (!stats) return -1;
-        launches += b200_launch_gn_stats(ctx->stream, (const float*)src->data, stats, N, C, H * W, pro.n_groups, pro.eps);
+    const int64_t C = m.w->ne[2], N = 1, H = m.OH / pro.up, W = m.OW / pro.up;
+    const void* wp = nullptr;
+    bool w_fresh = false;
+    if (!m.tokens_out) {
+        wp = get_packed_conv_weight(ctx, m.w, &launches);
+        if (!wp) return -1;
+        w_fresh = launches > 0;      // packed by a kernel of this very graph execution: not yet a constant
     }
-    int n = b200_launch_to_nhwc_f16(ctx->stream, (const float*)src->data, shadow, N, C, H, W, pro.up, stats, pro.n_groups, pro.gw, pro.gb, pro.act);
-    if (n < 0) return -1;
-    launches += n;
+    const void* shadow = pro.ready_nhwc;
+    if (!shadow) {
+        void* sh = ws_alloc(ctx, (size_t)(N * m.OH * m.OW * C * 2));
+        if (!sh) return -1;
+        float* stats = nullptr;
+        if (pro.norm) {
+            stats = (float*)ws_alloc(ctx, (size_t)(N * pro.n_groups * 2 * sizeof(float)));
+            if (!stats) return -1;
+            launches += b200_launch_gn_stats(ctx->stream, (const float*)src->data, stats, N, C, H * W, pro.n_groups, pro.eps);
+        }
+        int n = b200_launch_to_nhwc_f16(ctx->stream, (const float*)src->data, sh, N, C, H, W, pro.up, stats, pro.n_groups, pro.gw, pro.gb, pro.act);
+        if (n < 0) return -1;
+        launches += n;
+        shadow = sh;
+    }
+    if (m.tokens_out) {
+        // D[pixel][oc] = sum_c W[oc][c] * X[pixel][c]: the 1x1 filter [1,1,IC,OC] is already the K-major [OC][IC] operand
+        b200_gemm_args g;
+        memset(&g, 0, sizeof(g));
+        g.A = m.w->data; g.B = shadow; g.type = GGML_TYPE_F16;
+        g.M = m.w->ne[3]; g.N = m.OH * m.OW; g.K = C;
+        g.lda = C; g.ldb = C; g.batch = 1; g.a_bcast = 1;
+        g.D = m.out; g.ldd = g.M;
+        g.bias = m.bias; g.bias_mode = m.bias ? 1 : 0;
+        if (ctx->opt_early_weights && m.w->buffer && m.w->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS) g.early = 1;
+        int n = launch_tc(ctx, g);
+        if (n < 0) return -1;
+        ctx->stats.reserved[4] += 1;
+        return launches + n;
+    }
     b200_conv_args c;
     memset(&c, 0, sizeof(c));
     c.x_nhwc = shadow; c.w_packed = wp;
@@ -1085,7 +1156,7 @@ static int emit_conv(b200_context* ctx, const conv_match& m, const conv_prologue
     void* w = wsb ? ws_alloc(ctx, wsb) : nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->opt_kernel_timing) { e0 = kt_event(ctx); e1 = kt_event(ctx); cudaEventRecord(e0, ctx->stream); }
-    n = b200_launch_conv_tc(ctx->stream, ctx->info, c, w, w ? wsb : 0);
+    int n = b200_launch_conv_tc(ctx->stream, ctx->info, c, w, w ? wsb : 0);
     if (ctx->opt_kernel_timing) {
         if (n > 0) {
             cudaEventRecord(e1, ctx->stream);
@@ -1364,6 +1435,40 @@ static int try_fuse_silu_gemv(b200_context* ctx, ggml_cgraph* g, fusion_state& f
     return n;
 }
 
+// tokens [C, HW] -> PERMUTE(1,0,2,3) -> CONT -> reshape [W,H,C,1] -> 1x1 conv (SpatialTransformer proj_out, block.hpp:565-570): tokens
+// are already the NHWC image the implicit-GEMM conv reads, so the transpose and the NCHW->NHWC transform cancel: one f16 pack
+static int try_fuse_tokens_conv(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
+    if (!ctx->opt_tc_gemm || !ctx->opt_implicit_conv) return -2;
+    ggml_tensor* c = g->nodes[i];
+    const ggml_tensor* pv = c->src[0];
+    if (c->type != GGML_TYPE_F32 || !ggml_is_contiguous(c) || pv->op != GGML_OP_PERMUTE || !single_use(fs, c)) return -2;
+    const ggml_tensor* t = pv->src[0];
+    if (!t || t->type != GGML_TYPE_F32 || !ggml_is_contiguous(t) || t->ne[2] * t->ne[3] != 1) return -2;
+    if (pv->ne[0] != t->ne[1] || pv->ne[1] != t->ne[0] || pv->nb[0] != t->nb[1] || pv->nb[1] != t->nb[0] || pv->data != t->data) return -2;
+    const int64_t C = t->ne[0], HW = t->ne[1];
+    const int j = next_node(g, fs, i);
+    if (j < 0 || g->nodes[j]->op != GGML_OP_IM2COL) return -2;
+    const ggml_tensor* x = g->nodes[j]->src[1];
+    if (!x || x->ne[2] != C || x->ne[0] * x->ne[1] != HW || x->ne[3] != 1 || !order_preserving_view_of(fs, x, c)) return -2;
+    if (x != c && !single_use(fs, x)) return -2;
+    conv_match cm;
+    if (!match_conv(g, fs, j, &cm) || cm.tokens_out || cm.w->ne[0] != 1 || cm.w->ne[1] != 1 || cm.x != x) return -2;
+    if ((C * 2) % 16 || ((uintptr_t)t->data & 15)) return -2;
+    void* shadow = ws_alloc(ctx, (size_t)(HW * C * 2));
+    if (!shadow) return -1;
+    int n0 = b200_launch_pack_rows(ctx->stream, b200_make_td(t), shadow, GGML_TYPE_F16, C);
+    if (n0 < 0) return -2;
+    conv_prologue pro;
+    pro.src = x;
+    pro.ready_nhwc = shadow;
+    int n = emit_conv(ctx, cm, pro);
+    if (n < 0) return -1;     // the pack is already in the stream: do not re-run the chain differently on a half-executed state
+    fs.done[j] = 1;
+    for (int k : cm.chain) fs.done[k] = 1;
+    *covered = 1 + (int)cm.chain.size();
+    return n0 + n;
+}
+
 // IM2COL -> ...   or   UPSCALE(nearest x2) -> IM2COL -> ...
 static int try_fuse_conv(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
     ggml_tensor* t = g->nodes[i];
@@ -1415,6 +1520,7 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
             else if (t->op == GGML_OP_CONT) {
                 n = try_fuse_cont_cast(ctx, cgraph, fs, i, &covered);
                 if (n == -2 && ctx->opt_chain_fusion) n = try_fuse_geglu(ctx, cgraph, fs, i, &covered);
+                if (n == -2 && ctx->opt_chain_fusion) n = try_fuse_tokens_conv(ctx, cgraph, fs, i, &covered);
                 if (n == -2 && ctx->opt_chain_fusion) n = try_skip_q_cont(ctx, cgraph, fs, i);
             } else if (t->op == GGML_OP_UNARY && ctx->opt_chain_fusion) n = try_fuse_silu_gemv(ctx, cgraph, fs, i, &covered);
             else if (t->op == GGML_OP_FLASH_ATTN_EXT && ctx->opt_chain_fusion) n = try_fuse_flash_attn(ctx, cgraph, fs, i, &covered);
@@ -1511,8 +1617,8 @@ enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
             cudaGetLastError();
             pl->no_capture = true;
             if (pl->exec) { cudaGraphExecDestroy(pl->exec); pl->exec = nullptr; }
-            if (st != GGML_STATUS_SUCCESS) return st;
-            // fall back to eager execution of this call
+            if (st != GGML_STATUS_SUCCESS && !ctx->capture_overflow) return st;
+            // fall back to eager execution of this call (also when a node needed a one-time allocation that cannot be captured)
             ws_begin_graph(ctx);
             launches = nodes = 0;
             st = execute_nodes(ctx, cgraph, &launches, &nodes);

@@ -45,6 +45,8 @@ int b200_launch_norm(cudaStream_t s, int kind, const b200_td& src, const b200_td
 int b200_launch_soft_max(cudaStream_t s, const b200_td& src, const b200_td* mask, const b200_td& dst, float scale, float max_bias);
 
 // ---- im2col.cu -------------------------------------------------------------------------------
+// p = op_params {s0,s1,s2,p0,p1,p2,d0,d1,d2}; src [IW,IH,ID,N*IC] f32 -> dst [IC*KD*KH*KW, OW, OH, N*OD] f16|f32
+int b200_launch_im2col_3d(cudaStream_t s, const b200_td& src, const b200_td& dst, int64_t KW, int64_t KH, int64_t KD, int64_t IC, const int32_t* p);
 int b200_launch_im2col(cudaStream_t s, const b200_td& src /*image*/, const b200_td& dst, int64_t KW, int64_t KH, int s0, int s1, int p0,
                        int p1, int d0, int d1, bool is_2d);
 
@@ -76,6 +78,10 @@ struct b200_gemm_args {
 // returns kernels launched, or -1 if the shape/alignment is not supported by the TMA path (caller falls back)
 int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g, void* workspace, size_t workspace_bytes);
 size_t b200_gemm_tc_workspace_bytes(const b200_device_info& dev, const b200_gemm_args& g);
+
+// Q8_0 blocks (34 bytes: f16 scale + 32 int8, ggml-common.h:251-255) -> f16 rows [rows][K] (K % 32 == 0): the derived weight layout the
+// tensor-core GEMM reads; value = round_f16(float(d) * q), the reference's own dequantisation (ggml-quants.c dequantize_row_q8_0)
+int b200_launch_dequant_q8_0(cudaStream_t s, const void* blocks, void* out_f16, int64_t n_blocks);
 
 // ---- gemv.cu: MUL_MAT with N <= 4 activation rows, F16/BF16 weights read in place; pre_act 1 = SiLU on the activation -----
 bool b200_gemv_supported(int wtype, int64_t M, int64_t N, int64_t K, const void* W, int64_t lda, const void* X);

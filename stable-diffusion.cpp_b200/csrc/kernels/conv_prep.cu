@@ -143,7 +143,33 @@ __global__ void k_pack_conv_weight(const __half* __restrict__ w, __half* __restr
     }
 }
 
+// one thread per Q8_0 block: 2-byte scale + 32 int8 (the block is only 2-byte aligned) -> 32 f16
+__global__ void k_dequant_q8_0(const uint8_t* __restrict__ blocks, __half* __restrict__ out, int64_t n_blocks) {
+    pdl_wait();
+    pdl_launch_dependents();
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (int64_t)gridDim.x * blockDim.x) {
+        const uint8_t* blk = blocks + b * 34;
+        const float d = __half2float(*(const __half*)blk);
+        const uint16_t* q16 = (const uint16_t*)(blk + 2);
+        __half2* o = (__half2*)(out + b * 32);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint16_t two = q16[i];
+            const float a = d * (float)(int8_t)(two & 0xff), c = d * (float)(int8_t)(two >> 8);
+            o[i] = __floats2half2_rn(a, c);
+        }
+    }
+}
+
 }  // namespace
+
+int b200_launch_dequant_q8_0(cudaStream_t s, const void* blocks, void* out_f16, int64_t n_blocks) {
+    if (n_blocks <= 0) return 0;
+    int64_t nb = (n_blocks + 255) / 256;
+    if (nb > 148 * 64) nb = 148 * 64;
+    b200_launch(k_dequant_q8_0, dim3((unsigned)nb), dim3(256), 0, s, (const uint8_t*)blocks, (__half*)out_f16, n_blocks);
+    return 1;
+}
 
 int b200_launch_gn_stats(cudaStream_t s, const float* x, float* stats, int64_t N, int64_t C, int64_t inner, int n_groups, float eps) {
     const int cpg = (int)((C + n_groups - 1) / n_groups);

@@ -27,6 +27,8 @@
 #include "ggml.h"
 
 #include "model/diffusion/flux.hpp"
+#include "model/diffusion/mmdit.hpp"
+#include "model/diffusion/wan.hpp"
 #include "model/diffusion/unet.hpp"
 #include "model/vae/auto_encoder_kl.hpp"
 #include "runtime/denoiser.hpp"
@@ -186,7 +188,7 @@ struct SyntheticWeights : public RunnerWeightManager {
     }
 };
 
-enum Arch { ARCH_UNET, ARCH_VAE, ARCH_FLUX };
+enum Arch { ARCH_UNET, ARCH_VAE, ARCH_FLUX, ARCH_MMDIT, ARCH_WAN };
 
 ggml_type parse_wtype(const char* w) {
     std::string s = w ? w : "f32";
@@ -226,6 +228,8 @@ struct sdh_model {
     std::unique_ptr<UNetModelRunner> unet;
     std::unique_ptr<AutoEncoderKL> vae;
     std::unique_ptr<Flux::FluxRunner> flux;
+    std::unique_ptr<MMDiTRunner> mmdit;
+    std::unique_ptr<WAN::WanRunner> wan;
     SDVersion version = VERSION_SD1;
     int n_threads     = 1;
     double last_flops = 0;
@@ -383,12 +387,16 @@ sdh_model* sdh_model_create(const char* device, const char* arch, const char* wt
         m->version = VERSION_FLUX;
         const std::string prefix = "model.diffusion_model";
         String2TensorStorage smap;
-        if (a == "flux_tiny") {
-            // depth is detected from weight names (flux.hpp detect_from_weights): declare 2 double + 2 single blocks
+        {
+            // depth is detected from weight names (flux.hpp detect_from_weights): FLUX.1 has 19 double + 38 single blocks, the tiny
+            // variant declares 2 + 2
+            const int n_double = a == "flux_tiny" ? 2 : 19, n_single = a == "flux_tiny" ? 2 : 38;
             int64_t ne2[2] = {3072, 3072};
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < n_double; ++i) {
                 std::string n1 = prefix + ".double_blocks." + std::to_string(i) + ".img_attn.proj.weight";
                 smap[n1] = TensorStorage(n1, wtype, ne2, 2, 0);
+            }
+            for (int i = 0; i < n_single; ++i) {
                 std::string n2 = prefix + ".single_blocks." + std::to_string(i) + ".modulation.lin.weight";
                 smap[n2] = TensorStorage(n2, wtype, ne2, 2, 0);
             }
@@ -403,6 +411,42 @@ sdh_model* sdh_model_create(const char* device, const char* arch, const char* wt
         m->flux = std::make_unique<Flux::FluxRunner>(m->backend, smap, prefix, m->version, m->weights);
         m->flux->get_param_tensors(tensors, prefix);
         m->flux->set_flash_attention_enabled(fa);
+    } else if (a == "mmdit_sd3") {
+        // SD3-medium: the MMDiTConfig defaults (depth 24, hidden 1536, 2 B parameters; mmdit.hpp:16-31)
+        m->arch    = ARCH_MMDIT;
+        m->version = VERSION_SD3;
+        const std::string prefix = "model.diffusion_model";
+        String2TensorStorage smap;
+        {
+            MMDiTRunner probe(m->backend, {}, prefix, m->weights);
+            std::map<std::string, ggml_tensor*> pt;
+            probe.get_param_tensors(pt, prefix);
+            smap = make_storage_map(pt, wtype);
+        }
+        m->mmdit = std::make_unique<MMDiTRunner>(m->backend, smap, prefix, m->weights);
+        m->mmdit->get_param_tensors(tensors, prefix);
+        m->mmdit->set_flash_attention_enabled(fa);
+    } else if (a == "wan_1_3b") {
+        // Wan2.1-T2V-1.3B: 30 blocks of dim 1536 / 12 heads (wan.hpp:808-837); depth is detected from weight names
+        m->arch    = ARCH_WAN;
+        m->version = VERSION_WAN2;
+        const std::string prefix = "model.diffusion_model";
+        String2TensorStorage smap;
+        int64_t ne2[2] = {1536, 1536};
+        for (int i = 0; i < 30; ++i) {
+            std::string n1 = prefix + ".blocks." + std::to_string(i) + ".self_attn.q.weight";
+            smap[n1] = TensorStorage(n1, wtype, ne2, 2, 0);
+        }
+        {
+            WAN::WanRunner probe(m->backend, smap, prefix, m->version, m->weights);
+            std::map<std::string, ggml_tensor*> pt;
+            probe.get_param_tensors(pt, prefix);
+            String2TensorStorage typed = make_storage_map(pt, wtype);
+            for (auto& kv : typed) smap[kv.first] = kv.second;
+        }
+        m->wan = std::make_unique<WAN::WanRunner>(m->backend, smap, prefix, m->version, m->weights);
+        m->wan->get_param_tensors(tensors, prefix);
+        m->wan->set_flash_attention_enabled(fa);
     } else {
         fail("unknown arch: " + a);
         return nullptr;
@@ -419,6 +463,8 @@ void sdh_model_free(sdh_model* m) {
     m->unet.reset();
     m->vae.reset();
     m->flux.reset();
+    m->mmdit.reset();
+    m->wan.reset();
     m->weights.reset();
     if (m->backend) ggml_backend_free(m->backend);
     delete m;
@@ -449,6 +495,10 @@ static sd::Tensor<float> run_model(sdh_model* m, const sd::Tensor<float>& x, con
             sd::Tensor<float> guidance;  // schnell: no guidance embed
             return m->flux->compute(m->n_threads, x, t, ctx, {}, y, guidance);
         }
+        case ARCH_MMDIT:
+            return m->mmdit->compute(m->n_threads, x, t, ctx, y);
+        case ARCH_WAN:
+            return m->wan->compute(m->n_threads, x, t, ctx);
     }
     return {};
 }
@@ -664,6 +714,12 @@ static ggml_cgraph* build_only(sdh_model* m, const sd::Tensor<float>& x, const s
         case ARCH_FLUX:
             m->flux->reset_compute_ctx();
             return m->flux->build_graph(x, t, ctx, {}, y);
+        case ARCH_MMDIT:
+            m->mmdit->reset_compute_ctx();
+            return m->mmdit->build_graph(x, t, ctx, y);
+        case ARCH_WAN:
+            m->wan->reset_compute_ctx();
+            return m->wan->build_graph(x, t, ctx);
     }
     return nullptr;
 }
@@ -689,6 +745,9 @@ extern "C" int sdh_run_op(const char* device, const char* op_s, int n_in, const 
     else if (op == "conv_2d") {
         r = ggml_conv_2d(ctx, t[0], t[1], I(0), I(1), I(2), I(3), I(4), I(5));
         if (t[2]) r = ggml_add_inplace(ctx, r, t[2]);
+    } else if (op == "conv_3d") {
+        // w [OC*IC, KD, KH, KW], x [N*IC, ID, IH, IW]; ip = {IC, s0,s1,s2, p0,p1,p2, d0,d1,d2} (Wan patch embedding / causal 3-D convs)
+        r = ggml_conv_3d(ctx, t[0], t[1], I(0), I(1), I(2), I(3), I(4), I(5), I(6), I(7), I(8), I(9));
     } else if (op == "gn_silu_conv") {
         // ResBlock prologue + conv (block.hpp:124-150): GroupNorm32 -> SiLU -> Conv2d 3x3 (x, gn_w, gn_b, conv_w)
         ggml_tensor* hh = ggml_group_norm(ctx, t[0], I(0), F(0));

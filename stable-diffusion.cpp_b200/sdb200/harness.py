@@ -124,7 +124,7 @@ class Harness:
 
     def run_op(self, device: str, op: str, inputs, itypes=None, ip=(), fp=(), n_threads: int = 0) -> np.ndarray:
         """Run one ggml op (sdh_run_op) on `device`.  inputs: list of numpy arrays (numpy order = reversed ggml ne) or None."""
-        GGML_TYPES = {"f32": 0, "f16": 1, "bf16": 30}
+        GGML_TYPES = {"f32": 0, "f16": 1, "bf16": 30, "q8_0": 8}
         n = len(inputs)
         arr = (SdhTensor * 4)()
         keep = []

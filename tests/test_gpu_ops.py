@@ -62,6 +62,33 @@ def test_mul_mat(b200, wt, M, N, K):
     assert rel(g, c) < (2e-3 if wt == "f32" else 2e-4), f"rel {rel(g, c):.2e}"
 
 
+@pytest.mark.parametrize("M,N,K", [(1536, 192, 1536), (8960, 704, 1536), (1536, 512, 4096), (320, 3, 256), (96, 40, 64)])
+def test_mul_mat_q8_0_weights(b200, M, N, K):
+    """BASELINE config 5 data format: Q8_0 weight blocks (ggml-common.h:251-255).  The oracle also quantises the ACTIVATION rows to Q8_0
+    (ggml-cpu.c:1480-1510, vec_dot q8_0 x q8_0); this backend keeps them in f16, so the distance to the oracle is the oracle's own
+    activation-quantisation noise (~0.3 % of a row's max per element): gate at test-backend-ops' NMSE 5e-4, and check the exact
+    arithmetic separately against the f64 product of the DEQUANTISED weights."""
+    w, x = f(M, K) / np.sqrt(K), f(N, K)
+    g, c = both(b200, "mul_mat", [w, x], ["q8_0", "f32"])
+    nmse = float(np.sum((g.astype(np.float64) - c) ** 2) / np.sum(c.astype(np.float64) ** 2))
+    assert nmse < 5e-4, f"NMSE {nmse:.2e}"
+    wq = R.dequant_q8_0(R.quant_q8_0(w))
+    exact = x.astype(np.float16).astype(np.float64) @ wq.astype(np.float64).T
+    assert rel(g, exact.astype(np.float32)) < 2e-3, f"vs dequantised-weight product {rel(g, exact):.2e}"
+
+
+def test_conv_3d_patch_embedding(b200):
+    """Wan patch embedding (wan.hpp): Conv3d kernel (1,2,2) stride (1,2,2) -> IM2COL_3D + MUL_MAT + permute."""
+    IC, OC = 16, 1536
+    w, x = f(OC * IC, 1, 2, 2) / 8, f(IC, 3, 16, 16)
+    g, c = both(b200, "conv_3d", [w, x], ["f16", "f32"], ip=[IC, 2, 2, 1, 0, 0, 0, 1, 1, 1])
+    assert g.shape == c.shape and rel(g, c) < 2e-4, f"rel {rel(g, c):.2e}"
+    # causal-style 3x3x3 with padding
+    w, x = f(8 * 4, 3, 3, 3) / 10, f(4, 5, 9, 7)
+    g, c = both(b200, "conv_3d", [w, x], ["f16", "f32"], ip=[4, 1, 1, 1, 1, 1, 1, 1, 1, 1])
+    assert g.shape == c.shape and rel(g, c) < 2e-4, f"rel {rel(g, c):.2e}"
+
+
 def test_mul_mat_batched_broadcast(b200):
     w, x = f(1, 2, 64, 80) / 9, f(1, 8, 100, 80)      # ne02 = 2 broadcast over ne12 = 8 (GQA-style)
     g, c = both(b200, "mul_mat", [w, x], ["f16", "f32"])

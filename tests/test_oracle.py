@@ -125,6 +125,17 @@ def test_restatement_vs_live_cpu_backend(cpu_oracle):
     wm = (rng.standard_normal((128, 320)) / 18).astype(np.float32)
     xm = rng.standard_normal((77, 320)).astype(np.float32)
     _close(R.mul_mat(wm, xm, "f16"), h.run_op("CPU", "mul_mat", [wm, xm], ["f16", "f32"])[0, 0], 2e-6, "mul_mat live")
+    # Q8_0 weights: the CPU backend quantises the activation rows too (ggml-cpu.c:1480-1510); its SIMD quantiser rounds ties to even
+    # where the _ref restatement rounds them away from zero, so single quants may differ by one step: well under 1e-3 of the result
+    _close(R.mul_mat_q8_0(wm, xm), h.run_op("CPU", "mul_mat", [wm, xm], ["q8_0", "f32"])[0, 0], 1e-3, "mul_mat q8_0 live")
+    w3 = (rng.standard_normal((8 * 4, 3, 3, 3)) / 10).astype(np.float32)
+    x3 = rng.standard_normal((4, 5, 9, 7)).astype(np.float32)
+    _close(R.conv_3d(w3, x3, 4, (1, 1, 1), (1, 1, 1), (1, 1, 1)), h.run_op("CPU", "conv_3d", [w3, x3], ["f16", "f32"], ip=[4, 1, 1, 1, 1, 1, 1, 1, 1, 1]),
+           2e-6, "conv_3d live")
+    w3 = (rng.standard_normal((24 * 16, 1, 2, 2)) / 8).astype(np.float32)
+    x3 = rng.standard_normal((16, 3, 8, 8)).astype(np.float32)
+    _close(R.conv_3d(w3, x3, 16, (2, 2, 1), (0, 0, 0), (1, 1, 1)), h.run_op("CPU", "conv_3d", [w3, x3], ["f16", "f32"], ip=[16, 2, 2, 1, 0, 0, 0, 1, 1, 1]),
+           2e-6, "conv_3d patch embedding live")
 
 
 def test_committed_model_fixture_matches_live_cpu_backend(cpu_oracle):
