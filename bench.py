@@ -174,7 +174,7 @@ def run_b200(args):
         raise RuntimeError(f"{dev} not registered (devices: {devs})")
     m = h.model(dev, "sd15_unet", "f16", FLAG_FLASH_ATTN, 1234, 0)
     image = rank // 2 if world > 1 else 0
-    role = (rank % 2) if world > 1 else -1
+    role = (rank % 2) if world > 1 else (2 if args.cfg_batched else -1)
     x, cond, uncond = inputs(h, image)
     nodes, flops = m.dump_graph(None, x, np.array([999.0], np.float32), cond)
     assert abs(flops - FLOPS_PER_FORWARD) / FLOPS_PER_FORWARD < 0.01, f"graph FLOPs {flops:.4e} differ from SURVEY.md 8d"
@@ -226,7 +226,7 @@ def run_b200(args):
             m.set_option("kernel_timing", 1)
             k0 = m.stats()
             # rank-0-local pass (no collective: the other ranks are not in this branch): 2 full CFG steps on this GPU alone
-            m.sample(x, cond, uncond, steps=2, cfg_scale=CFG_SCALE, eta=ETA, role=-1, exchange=None)
+            m.sample(x, cond, uncond, steps=2, cfg_scale=CFG_SCALE, eta=ETA, role=2 if (world == 1 and args.cfg_batched) else -1, exchange=None)
             k1 = m.stats()
             m.set_option("kernel_timing", 0)
             gl = k1["tc_gemm_launches"] - k0["tc_gemm_launches"]
@@ -255,9 +255,9 @@ def run_b200(args):
         line = dict(metric="denoise_steps_per_s", value=value, unit="steps/s", n_gpus=n, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16", data="synthetic",
                     config=dict(workload=WORKLOAD, model="SD1.5 UNet (reference UNetModelRunner, synthetic F16 weights, seed 1234)",
-                                latent="64x64x4", context="77x768", sampler="euler_a eta 1", cfg_scale=CFG_SCALE, forwards_per_step=2,
+                                latent="64x64x4", context="77x768", sampler="euler_a eta 1", cfg_scale=CFG_SCALE, forwards_per_step=1 if (world == 1 and args.cfg_batched) else 2,
                                 graph="flash-attention variant (--diffusion-fa)", images=images,
-                                parallelism="single GPU" if world == 1 else f"CFG split: cond/uncond on GPU pairs + NCCL all-gather of eps, {images} image(s)",
+                                parallelism=("single GPU, batched CFG (one N = 2 forward per step)" if args.cfg_batched else "single GPU") if world == 1 else f"CFG split: cond/uncond on GPU pairs + NCCL all-gather of eps, {images} image(s)",
                                 l2="no explicit flush: every forward streams 1.72 GB of weights (> 126 MB L2)",
                                 algorithmic_tflop_per_step=2 * flops / 1e12, step_tensor_frac_of_sustained_peak=step_tflops / peaks()["bf16_sustained"],
                                 graph_nodes=nodes),
@@ -360,6 +360,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vae", action="store_true")
+    ap.add_argument("--cfg-batched", action="store_true",
+                    help="single GPU: evaluate cond + uncond as ONE N = 2 forward per step (caller-side CFG batching, SURVEY.md 8f-1) instead of "
+                         "the reference's two serial forwards")
     ap.add_argument("--extra", default="", help="comma list of additional single-GPU forward timings: sdxl,flux")
     args = ap.parse_args()
     if args.impl == "reference":

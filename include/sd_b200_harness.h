@@ -94,7 +94,9 @@ int sdh_sample(sdh_model* m, const char* method, int steps, float cfg_scale, flo
 /* CFG-batch split over a pair of GPUs: like sdh_sample, but this process evaluates only ONE branch per
  * step (role 0 = cond, 1 = uncond) and calls `exchange(mine, cond_out, uncond_out, n, user)` so the caller can
  * all-gather the eps prediction over NCCL; it must fill both outputs (n floats each) and return 0.  role < 0 or
- * exchange == NULL degenerates to sdh_sample. */
+ * exchange == NULL degenerates to sdh_sample.
+ * role == 2: batched CFG on ONE device -- cond and uncond evaluated as a single N = 2 forward (x [W,H,C,2], context
+ * [C,L,2], timesteps [2]); no exchange callback is used; n_forwards counts one forward per step. */
 typedef int (*sdh_exchange_fn)(const float* mine, float* cond_out, float* uncond_out, size_t n, void* user);
 int sdh_sample_split(sdh_model* m, const char* method, int steps, float cfg_scale, float eta,
                      uint64_t sampler_seed, const sdh_tensor* noise, const sdh_tensor* cond,

@@ -13,7 +13,14 @@ def main():
         lines = [l for l in f if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
     idx = [i for i, r in enumerate(rows) if "timestep" in r["Kernel Name"]]
-    seg = rows[idx[-2]:idx[-1]] if len(idx) >= 2 else rows
+    # a forward starts at its (first) k_timestep_embedding launch; Flux has two per forward (timestep + guidance/vector path), so take
+    # the last segment that is at least half as long as the longest one
+    bounds = idx + [len(rows)]
+    segs = [rows[bounds[i]:bounds[i + 1]] for i in range(len(bounds) - 1)]
+    longest = max((len(s) for s in segs), default=0)
+    full = [s for s in segs if len(s) * 2 >= longest]
+    seg = full[-2] if len(full) >= 2 else (full[-1] if full else rows)
+    title = sys.argv[3] if len(sys.argv) > 3 else "ONE SD1.5 UNet forward"
     scale = 1e-3 if rows[0]["Metric Unit"] in ("ns", "nsecond") else 1.0
     tot = sum(float(r["Metric Value"]) for r in seg) * scale
     agg = collections.defaultdict(lambda: [0, 0.0])
@@ -22,7 +29,7 @@ def main():
         n = re.sub(r"void |\(anonymous namespace\)::|<unnamed>::", "", n)
         agg[n][0] += 1
         agg[n][1] += float(r["Metric Value"]) * scale
-    out = [f"# per-kernel device time of ONE SD1.5 UNet forward (ncu launch list, cold-cache, serialised: compare SHARES)",
+    out = [f"# per-kernel device time of {title} (ncu launch list, cold-cache, serialised: compare SHARES)",
            f"source: `{path}`; launches in the forward: {len(seg)}; sum of kernel durations: {tot/1e3:.2f} ms", "",
            "| kernel | launches | total us | avg us | share |", "|---|---:|---:|---:|---:|"]
     for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):

@@ -903,7 +903,7 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
         if (jr >= 0) {
             ggml_tensor* add = g->nodes[jr];
             if (add->op == GGML_OP_ADD && (add->flags & GGML_TENSOR_FLAG_COMPUTE) && add->type == GGML_TYPE_F32 && ggml_is_contiguous(add) &&
-                ggml_nelements(add) == ggml_nelements(mm) && mm->ne[2] * mm->ne[3] == 1 && !(curv->flags & GGML_TENSOR_FLAG_OUTPUT)) {
+                ggml_nelements(add) == ggml_nelements(mm) && mm->ne[3] == 1 && !(curv->flags & GGML_TENSOR_FLAG_OUTPUT)) {
                 const ggml_tensor* r = nullptr;
                 const ggml_tensor* val = nullptr;
                 if (order_preserving_view_of(fs, add->src[0], curv)) { val = add->src[0]; r = add->src[1]; }
@@ -1012,7 +1012,7 @@ static bool match_conv(const ggml_cgraph* g, const fusion_state& fs, int i, conv
     const ggml_tensor* x = im->src[1];
     if (w->type != GGML_TYPE_F16 || !ggml_is_contiguous(w) || x->type != GGML_TYPE_F32 || !ggml_is_contiguous(x)) return false;
     const int64_t IC = x->ne[2], N = x->ne[3], OC = w->ne[3];
-    if (w->ne[2] != IC || N != 1) return false;
+    if (w->ne[2] != IC || N < 1) return false;
     const int64_t OW = im->ne[1], OH = im->ne[2];
     if (OW != x->ne[0] || OH != x->ne[1]) return false;
     if (!b200_conv_tc_supported(N, OH, OW, IC, OC, (int)w->ne[1], (int)w->ne[0], p[0], p[1], p[2], p[3], p[4], p[5])) return false;
@@ -1034,13 +1034,29 @@ static bool match_conv(const ggml_cgraph* g, const fusion_state& fs, int i, conv
     int k = next_node(g, fs, j);
     if (k >= 0) {
         const ggml_tensor* c = g->nodes[k];
-        if (c->op == GGML_OP_CONT && c->type == GGML_TYPE_F32 && ggml_is_contiguous(c) && (c->flags & GGML_TENSOR_FLAG_COMPUTE) &&
-            ggml_nelements(c) == ggml_nelements(mm) && c->src[0] != mm && order_preserving_view_of(fs, c->src[0], mm) && single_use(fs, c->src[0])) {
+        const bool cont_ok = c->op == GGML_OP_CONT && c->type == GGML_TYPE_F32 && ggml_is_contiguous(c) && (c->flags & GGML_TENSOR_FLAG_COMPUTE) &&
+                             ggml_nelements(c) == ggml_nelements(mm) && c->src[0] != mm && single_use(fs, c->src[0]);
+        bool layout_ok = false;
+        if (cont_ok && N == 1) layout_ok = order_preserving_view_of(fs, c->src[0], mm);
+        if (cont_ok && N > 1) {
+            // [OW*OH*N, OC] -> reshape [OW, OH, N, OC] -> PERMUTE(0,1,3,2) -> CONT = [OW, OH, OC, N] (ggml.c:4748-4751): exactly the
+            // per-image NCHW planes the conv kernel writes, so the permuting copy is absorbed as well
+            const ggml_tensor* pv = c->src[0];
+            const ggml_tensor* rs = pv->op == GGML_OP_PERMUTE ? pv->src[0] : nullptr;
+            layout_ok = rs && order_preserving_view_of(fs, rs, mm) && single_use(fs, rs) && rs->ne[0] == OW && rs->ne[1] == OH && rs->ne[2] == N &&
+                        rs->ne[3] == OC && pv->ne[0] == OW && pv->ne[1] == OH && pv->ne[2] == OC && pv->ne[3] == N && pv->nb[0] == rs->nb[0] &&
+                        pv->nb[1] == rs->nb[1] && pv->nb[2] == rs->nb[3] && pv->nb[3] == rs->nb[2];
+        }
+        if (layout_ok) {
             m->chain.push_back(k);
             cur = c;
             m->out = (float*)c->data;
             k = next_node(g, fs, k);
+        } else if (N > 1) {
+            return false;     // without the permuting CONT the GEMM result is not in the kernel's output layout
         }
+    } else if (N > 1) {
+        return false;
     }
     if (k >= 0) {
         const ggml_tensor* add = g->nodes[k];
@@ -1063,9 +1079,9 @@ static bool match_conv(const ggml_cgraph* g, const fusion_state& fs, int i, conv
         const ggml_tensor* c = g->nodes[k];
         const ggml_tensor* pv = c->op == GGML_OP_CONT ? c->src[0] : nullptr;
         if (pv && pv->op == GGML_OP_PERMUTE && pv->src[0] == cur && single_use(fs, pv) && c->type == GGML_TYPE_F32 && ggml_is_contiguous(c) &&
-            (c->flags & GGML_TENSOR_FLAG_COMPUTE) && ggml_is_contiguous(cur) && cur->ne[0] == OW && cur->ne[1] == OH && cur->ne[2] == OC && cur->ne[3] == 1 &&
-            c->ne[0] == OC && c->ne[1] == OW && c->ne[2] == OH && c->ne[3] == 1 && pv->nb[0] == cur->nb[2] && pv->nb[1] == cur->nb[0] &&
-            pv->nb[2] == cur->nb[1]) {
+            (c->flags & GGML_TENSOR_FLAG_COMPUTE) && ggml_is_contiguous(cur) && cur->ne[0] == OW && cur->ne[1] == OH && cur->ne[2] == OC && cur->ne[3] == N &&
+            c->ne[0] == OC && c->ne[1] == OW && c->ne[2] == OH && c->ne[3] == N && pv->nb[0] == cur->nb[2] && pv->nb[1] == cur->nb[0] &&
+            pv->nb[2] == cur->nb[1] && pv->nb[3] == cur->nb[3]) {
             m->tokens_out = true;
             m->out = (float*)c->data;
             m->chain.push_back(k);
@@ -1106,7 +1122,7 @@ struct conv_prologue {
 static int emit_conv(b200_context* ctx, const conv_match& m, const conv_prologue& pro) {
     int launches = 0;
     const ggml_tensor* src = pro.src;
-    const int64_t C = m.w->ne[2], N = 1, H = m.OH / pro.up, W = m.OW / pro.up;
+    const int64_t C = m.w->ne[2], N = m.x->ne[3], H = m.OH / pro.up, W = m.OW / pro.up;
     const void* wp = nullptr;
     bool w_fresh = false;
     if (!m.tokens_out) {
@@ -1135,7 +1151,8 @@ static int emit_conv(b200_context* ctx, const conv_match& m, const conv_prologue
         memset(&g, 0, sizeof(g));
         g.A = m.w->data; g.B = shadow; g.type = GGML_TYPE_F16;
         g.M = m.w->ne[3]; g.N = m.OH * m.OW; g.K = C;
-        g.lda = C; g.ldb = C; g.batch = 1; g.a_bcast = 1;
+        g.lda = C; g.ldb = C; g.batch = N; g.a_bcast = N;              // one filter matrix for every image of the batch
+        g.b_batch_stride = g.N * C; g.d_batch_stride = g.M * g.N;
         g.D = m.out; g.ldd = g.M;
         g.bias = m.bias; g.bias_mode = m.bias ? 1 : 0;
         if (ctx->opt_early_weights && m.w->buffer && m.w->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS) g.early = 1;
@@ -1242,7 +1259,7 @@ static int try_fuse_norm(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, in
         // consumers that are F16/BF16-weight contractions want this activation rounded to their type (oracle: ggml-cpu.c:1430-1513):
         // write that copy from the same kernel and hand it to prepare_operand through the pack cache
         int want = -1;
-        if (last->ne[0] % 8 == 0 && last->ne[2] * last->ne[3] == 1) {
+        if (last->ne[0] % 8 == 0 && ggml_is_contiguous(last)) {
             for (int u = i + 1; u < g->n_nodes && u < i + 64; ++u) {
                 const ggml_tensor* c = g->nodes[u];
                 if (c->op == GGML_OP_MUL_MAT && c->src[1] == last && (c->src[0]->type == GGML_TYPE_F16 || c->src[0]->type == GGML_TYPE_BF16)) {
@@ -1255,7 +1272,7 @@ static int try_fuse_norm(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, in
         if (want >= 0) shadow = ws_alloc(ctx, (size_t)(ggml_nelements(last) * 2));
         n = b200_launch_norm(ctx->stream, B200_NORM_LAYER, b200_make_td(nrm->src[0]), dst, eps, (const float*)mul->src[1]->data,
                              (const float*)add->src[1]->data, shadow, want);
-        if (n >= 0 && shadow) ctx->pack_cache[std::make_pair((const ggml_tensor*)last, want)] = operand{shadow, want, last->ne[0], last->ne[0] * last->ne[1], last->ne[0] * last->ne[1]};
+        if (n >= 0 && shadow) ctx->pack_cache[std::make_pair((const ggml_tensor*)last, want)] = operand{shadow, want, last->ne[0], last->ne[0] * last->ne[1], last->ne[0] * last->ne[1] * last->ne[2]};
     }
     if (n < 0) return n;
     for (int c : chain) fs.done[c] = 1;
@@ -1443,18 +1460,19 @@ static int try_fuse_tokens_conv(b200_context* ctx, ggml_cgraph* g, fusion_state&
     const ggml_tensor* pv = c->src[0];
     if (c->type != GGML_TYPE_F32 || !ggml_is_contiguous(c) || pv->op != GGML_OP_PERMUTE || !single_use(fs, c)) return -2;
     const ggml_tensor* t = pv->src[0];
-    if (!t || t->type != GGML_TYPE_F32 || !ggml_is_contiguous(t) || t->ne[2] * t->ne[3] != 1) return -2;
+    if (!t || t->type != GGML_TYPE_F32 || !ggml_is_contiguous(t) || t->ne[3] != 1) return -2;
     if (pv->ne[0] != t->ne[1] || pv->ne[1] != t->ne[0] || pv->nb[0] != t->nb[1] || pv->nb[1] != t->nb[0] || pv->data != t->data) return -2;
-    const int64_t C = t->ne[0], HW = t->ne[1];
+    if (pv->ne[2] != t->ne[2] || pv->nb[2] != t->nb[2]) return -2;
+    const int64_t C = t->ne[0], HW = t->ne[1], NB = t->ne[2];
     const int j = next_node(g, fs, i);
     if (j < 0 || g->nodes[j]->op != GGML_OP_IM2COL) return -2;
     const ggml_tensor* x = g->nodes[j]->src[1];
-    if (!x || x->ne[2] != C || x->ne[0] * x->ne[1] != HW || x->ne[3] != 1 || !order_preserving_view_of(fs, x, c)) return -2;
+    if (!x || x->ne[2] != C || x->ne[0] * x->ne[1] != HW || x->ne[3] != NB || !order_preserving_view_of(fs, x, c)) return -2;
     if (x != c && !single_use(fs, x)) return -2;
     conv_match cm;
     if (!match_conv(g, fs, j, &cm) || cm.tokens_out || cm.w->ne[0] != 1 || cm.w->ne[1] != 1 || cm.x != x) return -2;
     if ((C * 2) % 16 || ((uintptr_t)t->data & 15)) return -2;
-    void* shadow = ws_alloc(ctx, (size_t)(HW * C * 2));
+    void* shadow = ws_alloc(ctx, (size_t)(NB * HW * C * 2));
     if (!shadow) return -1;
     int n0 = b200_launch_pack_rows(ctx->stream, b200_make_td(t), shadow, GGML_TYPE_F16, C);
     if (n0 < 0) return -2;

@@ -657,7 +657,25 @@ int sdh_sample_split(sdh_model* m, const char* method_s, int steps, float cfg_sc
         sd::Tensor<float> noised_input = x * c_in;
         sd::Tensor<float> cond_out, uncond_out;
         const bool want_uncond = cfg_scale != 1.0f && !uncond_t.empty();
-        if (role < 0 || !exchange) {
+        if (role == 2 && want_uncond) {
+            // batched CFG: cond and uncond as ONE forward with N = 2 -- x [W,H,C,2], context [768,77,2],
+            // timesteps [2] (unet.hpp:535-540 takes any N) -- then split; the guidance below is unchanged
+            auto stack2 = [](const sd::Tensor<float>& a, const sd::Tensor<float>& b) {
+                if (a.empty() || b.empty()) return sd::Tensor<float>();
+                std::vector<int64_t> shape = a.shape();
+                shape.back() *= 2;
+                std::vector<float> data(a.values());
+                data.insert(data.end(), b.values().begin(), b.values().end());
+                return sd::Tensor<float>(shape, std::move(data));
+            };
+            sd::Tensor<float> both = run_model(m, stack2(noised_input, noised_input), stack2(timesteps_tensor, timesteps_tensor), stack2(cond_t, uncond_t),
+                                               stack2(yc, yu));
+            forwards++;
+            if (both.empty() || both.numel() != 2 * noised_input.numel()) { failed = true; return {}; }
+            const int64_t half = noised_input.numel();
+            cond_out   = sd::Tensor<float>(noised_input.shape(), std::vector<float>(both.data(), both.data() + half));
+            uncond_out = sd::Tensor<float>(noised_input.shape(), std::vector<float>(both.data() + half, both.data() + 2 * half));
+        } else if (role < 0 || role == 2 || !exchange) {
             cond_out = run_model(m, noised_input, timesteps_tensor, cond_t, yc);  // :2811
             forwards++;
             if (cond_out.empty()) { failed = true; return {}; }

@@ -98,3 +98,19 @@ def test_cfg_split_four_ranks_two_images(tmp_path, cpu_oracle):
         single, _ = m.sample(x, c, u, steps=2, cfg_scale=7.0, eta=1.0)
         assert np.array_equal(outs[2 * image], single), f"image {image}: split sampler differs from the single-process sampler"
     m.close()
+
+
+def test_batched_cfg_single_forward_per_step(cpu_oracle):
+    """role 2: cond + uncond as ONE N = 2 forward per step (the other way to use the CFG batch, on a single device).  Same host
+    sampler; the reference CPU backend's GEMM blocking depends on the batch, so the latent agrees to rounding noise amplified by the
+    ancestral sampler, not bit for bit."""
+    h = cpu_oracle
+    x = h.randn(42, (1, 4, 16, 16)); c = h.randn(43, (1, 77, 768)); u = h.randn(44, (1, 77, 768))
+    m = h.model("CPU", "unet_tiny", "f16", 0, 1234, 2)
+    serial, i0 = m.sample(x, c, u, steps=2, cfg_scale=7.0, eta=1.0)
+    batched, i1 = m.sample(x, c, u, steps=2, cfg_scale=7.0, eta=1.0, role=2)
+    m.close()
+    assert i0["n_forwards"] == 4 and i1["n_forwards"] == 2
+    assert np.array_equal(i0["sigmas"], i1["sigmas"]) and np.array_equal(i0["timesteps"], i1["timesteps"])
+    r = np.linalg.norm(serial - batched) / np.linalg.norm(serial)
+    assert r < 1e-2, f"rel_l2 {r:.2e}"

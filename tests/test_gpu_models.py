@@ -175,3 +175,30 @@ def test_wan_1_3b_q8_0_vs_live_cpu(b200):
         m.close()
     assert np.isfinite(outs[dev]).all() and outs[dev].shape == outs["CPU"].shape
     assert rel(outs[dev], outs["CPU"]) < 5e-2, f"rel_l2 {rel(outs[dev], outs['CPU']):.2e}"
+
+
+@pytest.mark.parametrize("arch,shape", [("unet_tiny", (1, 4, 16, 16)), ("sd15_unet", (1, 4, 64, 64))])
+def test_batched_cfg_on_device(b200, arch, shape):
+    """Batched CFG: cond and uncond as one N = 2 graph (implicit-GEMM convs, norms, attention and GEMM epilogues with a batch
+    dimension).  Forward level: each half of the N = 2 output against the N = 1 forward of the same inputs (tight) and against the CPU
+    oracle; sampler level: one guided Euler step, where CFG scale 7 amplifies any forward difference ~9x."""
+    h, dev = b200
+    x = h.randn(42, shape); c = h.randn(43, (1, 77, 768)); u = h.randn(44, (1, 77, 768)); t = np.array([999.0], np.float32)
+    m = h.model(dev, arch, "f16", 1, 1234, 0)
+    one_c, _ = m.forward(x, t, c)
+    one_u, _ = m.forward(x, t, u)
+    s0 = m.stats()
+    two, _ = m.forward(np.concatenate([x, x]), np.array([999.0, 999.0], np.float32), np.concatenate([c, u]))
+    s1 = m.stats()
+    assert two.shape == (2,) + shape[1:] and np.isfinite(two).all()
+    assert s1["implicit_convs"] - s0["implicit_convs"] > 0, "N = 2 convolutions must stay on the implicit-GEMM path"
+    assert rel(two[0:1], one_c) < 2e-3 and rel(two[1:2], one_u) < 2e-3, f"{rel(two[0:1], one_c):.2e} {rel(two[1:2], one_u):.2e}"
+    serial, i0 = m.sample(x, c, u, steps=1, cfg_scale=7.0, eta=0.0, method="euler")
+    batched, i1 = m.sample(x, c, u, steps=1, cfg_scale=7.0, eta=0.0, method="euler", role=2)
+    m.close()
+    assert i0["n_forwards"] == 2 and i1["n_forwards"] == 1
+    assert rel(batched, serial) < 2e-2, f"batched vs serial step on device: {rel(batched, serial):.2e}"
+    mc = h.model("CPU", arch, "f16", 0, 1234, 0)
+    cpu_c, _ = mc.forward(x, t, c)
+    mc.close()
+    assert rel(two[0:1], cpu_c) < 3e-3, f"batched forward vs CPU oracle: {rel(two[0:1], cpu_c):.2e}"
