@@ -48,6 +48,13 @@ def peaks():
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, src="fallback")
 
 
+LAYOUT_TEXT = {
+    "batched": "every GPU samples its own image, cond + uncond as ONE N = 2 UNet forward per step (caller-side CFG batching; no collective)",
+    "serial": "the reference's own order: two N = 1 UNet forwards per step on one GPU (stable-diffusion.cpp:2811-2836)",
+    "cfg-split": "CFG batch split over GPU pairs: rank 2i evaluates cond, rank 2i+1 uncond of image i, ONE NCCL all-gather of eps per step",
+}
+
+
 def ncu_traffic():
     """DRAM bytes (read + write) per k_gemm_tc launch, averaged over the launches of the committed `ncu --set full` capture
     (profiles/r01_ncu_full_top_kernels.json).  Offline evidence, never measured under the timed run; null when absent."""
@@ -173,19 +180,28 @@ def run_b200(args):
     if dev not in devs:
         raise RuntimeError(f"{dev} not registered (devices: {devs})")
     m = h.model(dev, "sd15_unet", "f16", FLAG_FLASH_ATTN, 1234, 0)
-    image = rank // 2 if world > 1 else 0
-    role = (rank % 2) if world > 1 else (2 if args.cfg_batched else -1)
-    x, cond, uncond = inputs(h, image)
-    nodes, flops = m.dump_graph(None, x, np.array([999.0], np.float32), cond)
+
+    # ---- layouts.  One *step* is always the cond + uncond evaluation of one image plus the reference's host sampler math.
+    #   "batched"   (default, any N): every GPU samples its own image; cond + uncond are ONE N = 2 forward per step (caller-side CFG
+    #               batching); independent units, no data-path collective
+    #   "serial"    (--cfg serial, N = 1): the reference's own order, two N = 1 forwards per step (stable-diffusion.cpp:2811-2836)
+    #   "cfg-split" (--layout cfg-split, even N): ranks (2i, 2i+1) take cond / uncond of image i and all-gather eps over NCCL
+    main_layout = "cfg-split" if (world > 1 and args.layout == "cfg-split") else ("serial" if (world == 1 and args.cfg == "serial") else "batched")
+    alt_layout = None
+    if not args.no_alt:
+        if world == 1:
+            alt_layout = "serial" if main_layout == "batched" else "batched"
+        elif world % 2 == 0:
+            alt_layout = "cfg-split" if main_layout == "batched" else "batched"
+
+    x0, cond0, _ = inputs(h, 0)
+    nodes, flops = m.dump_graph(None, x0, np.array([999.0], np.float32), cond0)
     assert abs(flops - FLOPS_PER_FORWARD) / FLOPS_PER_FORWARD < 0.01, f"graph FLOPs {flops:.4e} differ from SURVEY.md 8d"
 
-    exchange = None
-    if world > 1:
+    pair_exchange = None
+    if world > 1 and world % 2 == 0 and "cfg-split" in (main_layout, alt_layout):
         from sdb200.cfg_split import PairExchange
-        exchange = PairExchange(dist, torch, rank, world, 4 * 64 * 64, "cuda")   # pair groups + one all-gather per step
-
-    def run(steps):
-        return m.sample(x, cond, uncond, steps=steps, cfg_scale=CFG_SCALE, eta=ETA, role=role, exchange=exchange)
+        pair_exchange = PairExchange(dist, torch, rank, world, 4 * 64 * 64, "cuda")   # pair groups + one all-gather per step
 
     def barrier():
         torch.cuda.synchronize()
@@ -193,29 +209,54 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    run(max(args.warmup, 3))                                   # >= 3 untimed warm-up steps (plan caches, workspace, clocks)
-    barrier()
-    s0 = m.stats()
-    if exchange is not None:
-        exchange.coll_ms = 0.0
-    with ClockSampler(local) as clk:
+    def timed(layout, steps, warmup, sample_clocks):
+        """W untimed + exactly K timed steps in `layout`; device time = CUDA events around every graph_compute (+ the collective),
+        max over ranks; returns the whole-job numbers."""
+        if layout == "cfg-split":
+            image, role, exchange, images = rank // 2, rank % 2, pair_exchange, world // 2
+        else:
+            image, role, exchange, images = rank, (2 if layout == "batched" else -1), None, world
+        x, cond, uncond = inputs(h, image)
+
+        def run(k):
+            return m.sample(x, cond, uncond, steps=k, cfg_scale=CFG_SCALE, eta=ETA, role=role, exchange=exchange)
+
+        run(warmup)                                                # >= 3 untimed warm-up steps (plan caches, workspace, clocks)
+        barrier()
+        s0 = m.stats()
+        if exchange is not None:
+            exchange.coll_ms = 0.0
+        clk = ClockSampler(local) if sample_clocks else None
+        if clk:
+            clk.__enter__()
         t0 = time.perf_counter()
-        out, info = run(args.steps)                            # EXACTLY K timed steps
+        out, info = run(steps)                                     # EXACTLY K timed steps
         barrier()
         wall = time.perf_counter() - t0
-    s1 = m.stats()
-    dev_ms = (s1["total_graph_ms"] - s0["total_graph_ms"]) + (exchange.coll_ms if exchange is not None else 0.0)
-    launches = s1["kernel_launches"] - s0["kernel_launches"]
-    forwards = s1["graphs"] - s0["graphs"]
-    if dist is not None:
-        t = torch.tensor([wall, dev_ms, float(launches)], dtype=torch.float64, device="cuda")
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        wall, dev_ms, launches = float(tmax[0]), float(tmax[1]), float(t[2])
-    images = max(1, world // 2) if world > 1 else 1
-    value = images * args.steps / (dev_ms / 1e3)
-    e2e = images * args.steps / wall
+        if clk:
+            clk.__exit__(None, None, None)
+        s1 = m.stats()
+        dev_ms = (s1["total_graph_ms"] - s0["total_graph_ms"]) + (exchange.coll_ms if exchange is not None else 0.0)
+        launches = s1["kernel_launches"] - s0["kernel_launches"]
+        forwards = s1["graphs"] - s0["graphs"]
+        if dist is not None:
+            t = torch.tensor([wall, dev_ms, float(launches), float(forwards)], dtype=torch.float64, device="cuda")
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            wall, dev_ms, launches, forwards = float(tmax[0]), float(tmax[1]), float(t[2]), float(t[3])
+        assert np.isfinite(out).all()
+        return dict(layout=layout, images=images, value=images * steps / (dev_ms / 1e3), e2e=images * steps / wall, dev_ms=dev_ms, wall=wall,
+                    launches=launches, forwards=forwards, clk=clk, s0=s0, s1=s1,
+                    forwards_per_step=1 if layout != "serial" else 2)
+
+    W = max(args.warmup, 3)
+    main = timed(main_layout, args.steps, W, True)
+    alt = timed(alt_layout, args.steps, W, False) if alt_layout else None
+    clk, s0, s1 = main["clk"], main["s0"], main["s1"]
+    wall, dev_ms, launches, forwards, images = main["wall"], main["dev_ms"], main["launches"], main["forwards"], main["images"]
+    value, e2e = main["value"], main["e2e"]
+    x, cond, uncond = inputs(h, rank if main_layout != "cfg-split" else rank // 2)
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM): per-launch CUDA events on the launching stream, separate pass
     roof = None
@@ -226,7 +267,7 @@ def run_b200(args):
             m.set_option("kernel_timing", 1)
             k0 = m.stats()
             # rank-0-local pass (no collective: the other ranks are not in this branch): 2 full CFG steps on this GPU alone
-            m.sample(x, cond, uncond, steps=2, cfg_scale=CFG_SCALE, eta=ETA, role=2 if (world == 1 and args.cfg_batched) else -1, exchange=None)
+            m.sample(x, cond, uncond, steps=2, cfg_scale=CFG_SCALE, eta=ETA, role=-1 if main_layout == "serial" else 2, exchange=None)
             k1 = m.stats()
             m.set_option("kernel_timing", 0)
             gl = k1["tc_gemm_launches"] - k0["tc_gemm_launches"]
@@ -240,7 +281,7 @@ def run_b200(args):
                             share_of_step_device_time=(gus / 1e3) / max((k1["total_graph_ms"] - k0["total_graph_ms"]), 1e-9), **ncu_traffic())
         except Exception as e:   # older plugin without kernel timing
             roof = dict(bound="tensor", error=str(e))
-        step_tflops = 2 * flops * images * args.steps / (dev_ms / 1e3) / 1e12 / max(1, n if world > 1 else 1)
+        step_tflops = 2 * flops * images * args.steps / (dev_ms / 1e3) / 1e12 / max(1, world)
         vae = None
         if n == 1 and not args.no_vae:
             vae = vae_decode_leg(h, dev, pk)
@@ -255,15 +296,18 @@ def run_b200(args):
         line = dict(metric="denoise_steps_per_s", value=value, unit="steps/s", n_gpus=n, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16", data="synthetic",
                     config=dict(workload=WORKLOAD, model="SD1.5 UNet (reference UNetModelRunner, synthetic F16 weights, seed 1234)",
-                                latent="64x64x4", context="77x768", sampler="euler_a eta 1", cfg_scale=CFG_SCALE, forwards_per_step=1 if (world == 1 and args.cfg_batched) else 2,
+                                latent="64x64x4", context="77x768", sampler="euler_a eta 1", cfg_scale=CFG_SCALE, forwards_per_step=main["forwards_per_step"], layout=main_layout,
                                 graph="flash-attention variant (--diffusion-fa)", images=images,
-                                parallelism=("single GPU, batched CFG (one N = 2 forward per step)" if args.cfg_batched else "single GPU") if world == 1 else f"CFG split: cond/uncond on GPU pairs + NCCL all-gather of eps, {images} image(s)",
+                                parallelism=LAYOUT_TEXT[main_layout] + f"; {images} image(s) in flight on {world} GPU(s)",
                                 l2="no explicit flush: every forward streams 1.72 GB of weights (> 126 MB L2)",
                                 algorithmic_tflop_per_step=2 * flops / 1e12, step_tensor_frac_of_sustained_peak=step_tflops / peaks()["bf16_sustained"],
                                 graph_nodes=nodes),
                     e2e=dict(value=e2e, unit="steps/s", ms_per_step=1e3 * wall / args.steps,
-                             h2d_bytes_per_step=2 * (4 * 64 * 64 * 4 + 77 * 768 * 4 + 4 + 8), d2h_bytes_per_step=2 * 4 * 64 * 64 * 4),
+                             h2d_bytes_per_step=images * 2 * (4 * 64 * 64 * 4 + 77 * 768 * 4 + 4 + 8), d2h_bytes_per_step=images * 2 * 4 * 64 * 64 * 4),
                     gpu_launches=int(launches), forwards=int(forwards), clocks=clk.summary(), roofline=roof, cpu_baseline=cpu_base,
+                    alt_layout=None if alt is None else dict(layout=alt["layout"], description=LAYOUT_TEXT[alt["layout"]], value=alt["value"], unit="steps/s",
+                                                                             ms_per_step=alt["dev_ms"] / args.steps, e2e=alt["e2e"], images=alt["images"],
+                                                                             forwards_per_step=alt["forwards_per_step"], gpu_launches=int(alt["launches"])),
                     vae_decode=vae, extra_workloads=extra or None,
                     backend=dict(cuda_graph_replays=int(s1["cuda_graph_replays"] - s0["cuda_graph_replays"]),
                                  fused_nodes=int(s1["fused_nodes"] - s0["fused_nodes"]), implicit_convs=int(s1["implicit_convs"] - s0["implicit_convs"]),
@@ -360,9 +404,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vae", action="store_true")
-    ap.add_argument("--cfg-batched", action="store_true",
-                    help="single GPU: evaluate cond + uncond as ONE N = 2 forward per step (caller-side CFG batching, SURVEY.md 8f-1) instead of "
-                         "the reference's two serial forwards")
+    ap.add_argument("--cfg", default="batched", choices=["batched", "serial"],
+                    help="N = 1: cond + uncond as ONE N = 2 forward per step (default; caller-side CFG batching, SURVEY.md 8f-1) or the "
+                         "reference's two serial forwards; the other one is measured too and reported under alt_layout")
+    ap.add_argument("--layout", default="batched", choices=["batched", "cfg-split"],
+                    help="N > 1: independent images per GPU with batched CFG (default, no collective) or the CFG batch split over GPU pairs with "
+                         "one NCCL all-gather per step; the other one is reported under alt_layout")
+    ap.add_argument("--no-alt", action="store_true", help="skip the alt_layout measurement")
     ap.add_argument("--extra", default="", help="comma list of additional single-GPU forward timings: sdxl,flux")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -135,6 +135,21 @@ def mul_mat(w, x, wtype="f32"):
 
 
 # ------------------------------------------------------------------------------------------------
+# rotary embedding   (Rope::apply_rope, src/model/common/rope.hpp:966-1010, interleaved variant)
+# ------------------------------------------------------------------------------------------------
+def rope_interleaved(x, pe):
+    """x [N, L, H, d] (ggml [d, H, L, N]), pe [L, d/2, 2, 2] = [[cos, -sin], [sin, cos]] -> [N*H, L, d]:
+    out[2i + j] = x[2i] * pe[l, i, j, 0] + x[2i + 1] * pe[l, i, j, 1]; the two products are rounded to f32 before the add."""
+    x = np.asarray(x, F32)
+    pe = np.asarray(pe, F32)
+    N, L, H, d = x.shape
+    xp = x.transpose(0, 2, 1, 3).reshape(N * H, L, d // 2, 2)
+    x0, x1 = xp[..., 0:1], xp[..., 1:2]                                # [NH, L, d/2, 1]
+    out = (x0 * pe[None, :, :, :, 0]).astype(F32) + (x1 * pe[None, :, :, :, 1]).astype(F32)
+    return out.astype(F32).reshape(N * H, L, d)
+
+
+# ------------------------------------------------------------------------------------------------
 # Q8_0   (block_q8_0 {f16 d; int8 qs[32]}: ggml-common.h:251-255; quantize_row_q8_0_ref / dequantize_row_q8_0: ggml-quants.c;
 #         ggml_vec_dot_q8_0_q8_0: ggml-cpu/quants.c -- sum over blocks of int32(sum q_w * q_x) * (d_w * d_x), f32 accumulation)
 # ------------------------------------------------------------------------------------------------

@@ -1487,6 +1487,172 @@ static int try_fuse_tokens_conv(b200_context* ctx, ggml_cgraph* g, fusion_state&
     return n0 + n;
 }
 
+// Rope::apply_rope, interleaved variant (src/model/common/rope.hpp:966-1010), as emitted for every q and k of a Flux / Wan block:
+//   c1 = CONT(PERMUTE(x, 0,2,1,3))            [d, L, H, N]
+//   c2 = CONT(PERMUTE(RESHAPE(c1, [2, d/2, L, H*N]), 3,0,1,2))      even / odd split [d/2, L, H*N, 2]
+//   rep_j = REPEAT(RESHAPE(VIEW(c2, half j)))  [2, d/2, L, H*N]     pc = CONT(PERMUTE(pe, 3,0,1,2)); pe_j = VIEW(pc, half j)
+//   out = ADD(MUL(rep_0, pe_0), MUL(rep_1, pe_1))  [-> RESHAPE -> CPY F16 for k]
+// 8 working nodes, one kernel (kernels/rope.cu).  When x itself is MUL(RMS_NORM(v), w) (QKNorm) the match starts there and folds both.
+struct rope_match {
+    const ggml_tensor* x = nullptr;      // [d, H, L, N] tensor that is permuted
+    const ggml_tensor* pe = nullptr;     // [2, 2, d/2, L]
+    ggml_tensor* out = nullptr;          // the ADD node
+    std::vector<int> nodes;              // working nodes covered, excluding the starting one
+};
+
+static bool match_rope(const ggml_cgraph* g, const fusion_state& fs, int i, rope_match* m) {
+    const ggml_tensor* c1 = g->nodes[i];
+    if (c1->op != GGML_OP_CONT || c1->type != GGML_TYPE_F32 || !ggml_is_contiguous(c1) || !single_use(fs, c1)) return false;
+    const ggml_tensor* p1 = c1->src[0];
+    if (p1->op != GGML_OP_PERMUTE || !p1->src[0]) return false;
+    const ggml_tensor* x = p1->src[0];
+    const int64_t d = x->ne[0], H = x->ne[1], L = x->ne[2], N = x->ne[3];
+    if (x->type != GGML_TYPE_F32 || d % 4 || d < 4) return false;
+    if (p1->ne[0] != d || p1->ne[1] != L || p1->ne[2] != H || p1->ne[3] != N || p1->nb[0] != x->nb[0] || p1->nb[1] != x->nb[2] || p1->nb[2] != x->nb[1] ||
+        p1->nb[3] != x->nb[3] || p1->data != x->data)
+        return false;
+    auto fl = [&](const ggml_tensor* t) { return (t->flags & GGML_TENSOR_FLAG_COMPUTE) != 0; };
+    // c2: even/odd split
+    int j = next_node(g, fs, i);
+    if (j < 0) return false;
+    const ggml_tensor* c2 = g->nodes[j];
+    if (c2->op != GGML_OP_CONT || !fl(c2) || !ggml_is_contiguous(c2) || c2->ne[0] != d / 2 || c2->ne[1] != L || c2->ne[2] != H * N || c2->ne[3] != 2) return false;
+    const ggml_tensor* p2 = c2->src[0];
+    if (p2->op != GGML_OP_PERMUTE || !p2->src[0] || p2->src[0]->op != GGML_OP_RESHAPE || p2->src[0]->src[0] != c1) return false;
+    const ggml_tensor* r1 = p2->src[0];
+    if (r1->ne[0] != 2 || r1->ne[1] != d / 2 || r1->ne[2] != L || r1->ne[3] != H * N || !ggml_is_contiguous(r1)) return false;
+    if (p2->nb[0] != r1->nb[1] || p2->nb[1] != r1->nb[2] || p2->nb[2] != r1->nb[3] || p2->nb[3] != r1->nb[0]) return false;
+    m->nodes.push_back(j);
+    const size_t half = c2->nb[3];
+    auto is_half_repeat = [&](const ggml_tensor* rep, int which) {
+        if (rep->op != GGML_OP_REPEAT || !fl(rep) || !ggml_is_contiguous(rep) || rep->ne[0] != 2 || rep->ne[1] != d / 2 || rep->ne[2] != L || rep->ne[3] != H * N) return false;
+        const ggml_tensor* rs = rep->src[0];
+        if (!rs || rs->op != GGML_OP_RESHAPE || rs->ne[0] != 1 || rs->ne[1] != d / 2 || rs->ne[2] != L || rs->ne[3] != H * N) return false;
+        const ggml_tensor* v = rs->src[0];
+        if (!v || v->op != GGML_OP_VIEW || v->view_src != c2 || (const char*)v->data != (const char*)c2->data + which * half) return false;
+        return v->ne[0] == d / 2 && v->ne[1] == L && v->ne[2] == H * N && v->nb[1] == c2->nb[1] && v->nb[2] == c2->nb[2];
+    };
+    // rep_0
+    j = next_node(g, fs, j);
+    if (j < 0 || !is_half_repeat(g->nodes[j], 0) || !single_use(fs, g->nodes[j])) return false;
+    const ggml_tensor* rep0 = g->nodes[j];
+    m->nodes.push_back(j);
+    // pc = CONT(PERMUTE(pe, 3,0,1,2))
+    j = next_node(g, fs, j);
+    if (j < 0) return false;
+    const ggml_tensor* pc = g->nodes[j];
+    if (pc->op != GGML_OP_CONT || !fl(pc) || !ggml_is_contiguous(pc) || pc->src[0]->op != GGML_OP_PERMUTE) return false;
+    const ggml_tensor* pe = pc->src[0]->src[0];
+    const ggml_tensor* pp = pc->src[0];
+    if (!pe || pe->type != GGML_TYPE_F32 || !ggml_is_contiguous(pe) || pe->ne[0] != 2 || pe->ne[1] != 2 || pe->ne[2] != d / 2 || pe->ne[3] != L) return false;
+    if (pp->ne[0] != 2 || pp->ne[1] != d / 2 || pp->ne[2] != L || pp->ne[3] != 2 || pp->nb[0] != pe->nb[1] || pp->nb[1] != pe->nb[2] || pp->nb[2] != pe->nb[3] ||
+        pp->nb[3] != pe->nb[0])
+        return false;
+    m->nodes.push_back(j);
+    const size_t pe_half = pc->nb[3];
+    auto is_pe_half = [&](const ggml_tensor* v, int which) {
+        return v && v->op == GGML_OP_VIEW && v->view_src == pc && (const char*)v->data == (const char*)pc->data + which * pe_half && v->ne[0] == 2 &&
+               v->ne[1] == d / 2 && v->ne[2] == L && v->ne[3] == 1 && v->nb[1] == pc->nb[1] && v->nb[2] == pc->nb[2];
+    };
+    // m0 = MUL(rep_0, pe_0)
+    j = next_node(g, fs, j);
+    if (j < 0) return false;
+    const ggml_tensor* m0 = g->nodes[j];
+    if (m0->op != GGML_OP_MUL || !fl(m0) || m0->src[0] != rep0 || !is_pe_half(m0->src[1], 0) || !ggml_is_contiguous(m0)) return false;
+    m->nodes.push_back(j);
+    // rep_1, m1
+    j = next_node(g, fs, j);
+    if (j < 0 || !is_half_repeat(g->nodes[j], 1) || !single_use(fs, g->nodes[j])) return false;
+    const ggml_tensor* rep1 = g->nodes[j];
+    m->nodes.push_back(j);
+    j = next_node(g, fs, j);
+    if (j < 0) return false;
+    const ggml_tensor* m1 = g->nodes[j];
+    if (m1->op != GGML_OP_MUL || !fl(m1) || m1->src[0] != rep1 || !is_pe_half(m1->src[1], 1) || !ggml_is_contiguous(m1)) return false;
+    m->nodes.push_back(j);
+    j = next_node(g, fs, j);
+    if (j < 0) return false;
+    ggml_tensor* add = g->nodes[j];
+    if (add->op != GGML_OP_ADD || !fl(add) || add->src[0] != m0 || add->src[1] != m1 || !ggml_is_contiguous(add) || add->type != GGML_TYPE_F32) return false;
+    if (!single_use(fs, m0) || !single_use(fs, m1)) return false;
+    // c2 and pc feed exactly their two half views
+    auto uses = [&](const ggml_tensor* t) { auto it = fs.uses.find(t); return it == fs.uses.end() ? 0 : it->second; };
+    if (uses(c2) != 2 || uses(pc) != 2 || (c2->flags & GGML_TENSOR_FLAG_OUTPUT) || (pc->flags & GGML_TENSOR_FLAG_OUTPUT)) return false;
+    m->nodes.push_back(j);
+    m->x = x; m->pe = pe; m->out = add;
+    return true;
+}
+
+// start: the CONT of the permute (i_c1); rms != nullptr when RMS_NORM + MUL in front of it are folded in (then x = rms->src[0])
+static int emit_rope(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, const rope_match& rm, const ggml_tensor* rms, const ggml_tensor* rms_mul,
+                     int* covered) {
+    const ggml_tensor* x = rms ? rms->src[0] : rm.x;
+    const float* w = nullptr;
+    float eps = 0.f;
+    if (rms) {
+        w = (const float*)(rms_mul->src[0] == rms ? rms_mul->src[1] : rms_mul->src[0])->data;
+        memcpy(&eps, rms->op_params, sizeof(float));
+    }
+    // k: ... -> RESHAPE -> CPY to F16 (ggml_ext_attention_ext casts K, ggml_extend.hpp:1388-1392): write the f16 rows directly
+    void* out = rm.out->data;
+    int out_type = GGML_TYPE_F32;
+    int extra = -1;
+    const int jn = next_node(g, fs, rm.nodes.back());
+    if (jn >= 0 && single_use(fs, rm.out)) {
+        const ggml_tensor* cp = g->nodes[jn];
+        if (cp->op == GGML_OP_CPY && (cp->flags & GGML_TENSOR_FLAG_COMPUTE) && cp->src[1] && cp->src[1]->type == GGML_TYPE_F16 && ggml_is_contiguous(cp->src[1]) &&
+            order_preserving_view_of(fs, cp->src[0], rm.out) && (cp->src[0] == rm.out || single_use(fs, cp->src[0])) && cp->src[1]->ne[0] == x->ne[0] &&
+            ggml_nelements(cp->src[1]) == ggml_nelements(rm.out)) {
+            out = cp->src[1]->data;
+            out_type = GGML_TYPE_F16;
+            extra = jn;
+        }
+    }
+    // one pass reads x (strided view of the projection output) while writing out
+    const char* lo; size_t nb;
+    base_range(x, &lo, &nb);
+    const size_t out_bytes = (size_t)ggml_nelements(rm.out) * (out_type == GGML_TYPE_F16 ? 2 : 4);
+    if (tensors_overlap(out, out_bytes, lo, nb)) return -2;
+    if (tensors_overlap(out, out_bytes, rm.pe->data, ggml_nbytes(rm.pe))) return -2;
+    int n = b200_launch_rope(ctx->stream, b200_make_td(x), (const float*)rm.pe->data, out, out_type, w, eps);
+    if (n < 0) return -2;
+    for (int k : rm.nodes) fs.done[k] = 1;
+    if (extra >= 0) fs.done[extra] = 1;
+    *covered = (int)rm.nodes.size() + (extra >= 0 ? 1 : 0);
+    ctx->stats.reserved[7] += 1;
+    return n;
+}
+
+static int try_fuse_rope(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
+    rope_match rm;
+    if (!match_rope(g, fs, i, &rm)) return -2;
+    return emit_rope(ctx, g, fs, rm, nullptr, nullptr, covered);
+}
+
+// RMS_NORM(v) -> MUL(., w[d]) -> [rope chain]: QKNorm + RoPE of a Flux q / k (flux.hpp:213-261,279-295)
+static int try_fuse_rms_rope(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
+    const ggml_tensor* rms = g->nodes[i];
+    const ggml_tensor* v = rms->src[0];
+    if (rms->type != GGML_TYPE_F32 || v->type != GGML_TYPE_F32 || !single_use(fs, rms) || !ggml_is_contiguous(rms)) return -2;
+    const int j1 = next_node(g, fs, i);
+    if (j1 < 0) return -2;
+    const ggml_tensor* mul = g->nodes[j1];
+    if (mul->op != GGML_OP_MUL || !(mul->flags & GGML_TENSOR_FLAG_COMPUTE) || !single_use(fs, mul) || !ggml_is_contiguous(mul)) return -2;
+    const ggml_tensor* w = mul->src[0] == rms ? mul->src[1] : (mul->src[1] == rms ? mul->src[0] : nullptr);
+    if (!w || w == rms || w->type != GGML_TYPE_F32 || !ggml_is_contiguous(w) || ggml_nelements(w) != rms->ne[0] || w->ne[0] != rms->ne[0]) return -2;
+    const int j2 = next_node(g, fs, j1);
+    if (j2 < 0) return -2;
+    rope_match rm;
+    if (!match_rope(g, fs, j2, &rm) || rm.x != mul) return -2;
+    int cov = 0;
+    const int n = emit_rope(ctx, g, fs, rm, rms, mul, &cov);
+    if (n < 0) return -2;
+    fs.done[j1] = 1;
+    fs.done[j2] = 1;
+    *covered = cov + 2;
+    return n;
+}
+
 // IM2COL -> ...   or   UPSCALE(nearest x2) -> IM2COL -> ...
 static int try_fuse_conv(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
     ggml_tensor* t = g->nodes[i];
@@ -1539,8 +1705,10 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
                 n = try_fuse_cont_cast(ctx, cgraph, fs, i, &covered);
                 if (n == -2 && ctx->opt_chain_fusion) n = try_fuse_geglu(ctx, cgraph, fs, i, &covered);
                 if (n == -2 && ctx->opt_chain_fusion) n = try_fuse_tokens_conv(ctx, cgraph, fs, i, &covered);
+                if (n == -2 && ctx->opt_chain_fusion) n = try_fuse_rope(ctx, cgraph, fs, i, &covered);
                 if (n == -2 && ctx->opt_chain_fusion) n = try_skip_q_cont(ctx, cgraph, fs, i);
-            } else if (t->op == GGML_OP_UNARY && ctx->opt_chain_fusion) n = try_fuse_silu_gemv(ctx, cgraph, fs, i, &covered);
+            } else if (t->op == GGML_OP_RMS_NORM && ctx->opt_chain_fusion) n = try_fuse_rms_rope(ctx, cgraph, fs, i, &covered);
+            else if (t->op == GGML_OP_UNARY && ctx->opt_chain_fusion) n = try_fuse_silu_gemv(ctx, cgraph, fs, i, &covered);
             else if (t->op == GGML_OP_FLASH_ATTN_EXT && ctx->opt_chain_fusion) n = try_fuse_flash_attn(ctx, cgraph, fs, i, &covered);
             if (n >= 0) {
                 ctx->stats.fused_nodes += (uint64_t)covered;

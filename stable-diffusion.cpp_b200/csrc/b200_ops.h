@@ -83,6 +83,9 @@ size_t b200_gemm_tc_workspace_bytes(const b200_device_info& dev, const b200_gemm
 // tensor-core GEMM reads; value = round_f16(float(d) * q), the reference's own dequantisation (ggml-quants.c dequantize_row_q8_0)
 int b200_launch_dequant_q8_0(cudaStream_t s, const void* blocks, void* out_f16, int64_t n_blocks);
 
+// ---- rope.cu: Rope::apply_rope (interleaved) as one pass, optional RMSNorm*scale prologue, f32 or f16 rows out ------------------
+int b200_launch_rope(cudaStream_t s, const b200_td& x, const float* pe, void* out, int out_type, const float* rms_w, float eps);
+
 // ---- gemv.cu: MUL_MAT with N <= 4 activation rows, F16/BF16 weights read in place; pre_act 1 = SiLU on the activation -----
 bool b200_gemv_supported(int wtype, int64_t M, int64_t N, int64_t K, const void* W, int64_t lda, const void* X);
 int b200_launch_gemv(cudaStream_t s, int wtype, const void* W, int64_t lda, const float* X, int64_t ldx, float* D, int64_t ldd, int64_t M, int64_t N,

@@ -110,6 +110,21 @@ __global__ void k_copy_rows4(const char* __restrict__ a, strides3 sa, char* __re
     }
 }
 
+// concat along dim 0 (the single-stream Flux block glues attention and MLP halves of every token row, flux.hpp:690): destination
+// chunk -> which source row segment, then a 16-byte copy
+__global__ void k_concat_dim0_rows4(const char* __restrict__ a, strides3 sa, const char* __restrict__ b, strides3 sb, char* __restrict__ d, strides3 sd,
+                                    rows4 r, uint32_t a_chunks) {
+    pdl_wait();
+    pdl_launch_dependents();
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < r.total; idx += gridDim.x * blockDim.x) {
+        uint32_t c, i1, i2, i3;
+        rows4_decode(r, idx, c, i1, i2, i3);
+        const uint4 v = c < a_chunks ? *(const uint4*)(a + i1 * sa.nb1 + i2 * sa.nb2 + i3 * sa.nb3 + (int64_t)c * 16)
+                                     : *(const uint4*)(b + i1 * sb.nb1 + i2 * sb.nb2 + i3 * sb.nb3 + (int64_t)(c - a_chunks) * 16);
+        *(uint4*)(d + i1 * sd.nb1 + i2 * sd.nb2 + i3 * sd.nb3 + (int64_t)c * 16) = v;
+    }
+}
+
 // GEGLU tail of the reference's FeedForward (src/model/common/block.hpp:194-207): dst = x * gelu_tanh(gate), x and gate the two
 // halves (strided row views) of one projection output.  Replaces CONT(gate) + GELU + MUL (+ the f16 operand pack of the Linear
 // that follows, through the optional contiguous f16 shadow d16).  Arithmetic is the unfused kernels' own: f32 gelu, one multiply.
@@ -756,6 +771,14 @@ int b200_launch_concat(cudaStream_t s, const b200_td& a, const b200_td& b, const
         if (make_rows4(d, &r)) {
             b200_launch(k_concat_rows4, dim3(grid_for(r.total)), dim3(kThreads), 0, s, (const char*)a.data, st3(a), (const char*)b.data, st3(b), (char*)d.data, st3(d), r, dim,
                                                                  (uint32_t)a.ne[dim]);
+            return 1;
+        }
+    }
+    if (es == 4 && dim == 0 && a.ne[0] % 4 == 0 && b.ne[0] % 4 == 0 && rows4_ok(a) && rows4_ok(b) && rows4_ok(d) && a.ne[0] / 4 < (1ll << 31)) {
+        rows4 r;
+        if (make_rows4(d, &r)) {
+            b200_launch(k_concat_dim0_rows4, dim3(grid_for(r.total)), dim3(kThreads), 0, s, (const char*)a.data, st3(a), (const char*)b.data, st3(b), (char*)d.data,
+                        st3(d), r, (uint32_t)(a.ne[0] / 4));
             return 1;
         }
     }

@@ -763,6 +763,13 @@ extern "C" int sdh_run_op(const char* device, const char* op_s, int n_in, const 
     else if (op == "conv_2d") {
         r = ggml_conv_2d(ctx, t[0], t[1], I(0), I(1), I(2), I(3), I(4), I(5));
         if (t[2]) r = ggml_add_inplace(ctx, r, t[2]);
+    } else if (op == "rope") {
+        // Rope::apply_rope (rope.hpp:966-1010) on x [d, H, L, N] with pe [2, 2, d/2, L]; optional QKNorm in front (RMSNorm(eps = fp[0]) * w = t[2],
+        // flux.hpp:213-261) and the K-side cast to F16 behind (ip[0])
+        ggml_tensor* xx = t[0];
+        if (t[2]) xx = ggml_mul(ctx, ggml_rms_norm(ctx, xx, F(0)), t[2]);
+        r = Rope::apply_rope(ctx, xx, t[1], true);
+        if (I(0)) r = ggml_cast(ctx, r, GGML_TYPE_F16);
     } else if (op == "conv_3d") {
         // w [OC*IC, KD, KH, KW], x [N*IC, ID, IH, IW]; ip = {IC, s0,s1,s2, p0,p1,p2, d0,d1,d2} (Wan patch embedding / causal 3-D convs)
         r = ggml_conv_3d(ctx, t[0], t[1], I(0), I(1), I(2), I(3), I(4), I(5), I(6), I(7), I(8), I(9));

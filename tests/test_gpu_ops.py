@@ -77,6 +77,20 @@ def test_mul_mat_q8_0_weights(b200, M, N, K):
     assert rel(g, exact.astype(np.float32)) < 2e-3, f"vs dequantised-weight product {rel(g, exact):.2e}"
 
 
+@pytest.mark.parametrize("H,L,d,rms,f16out", [(24, 4352, 128, 1, 0), (24, 4352, 128, 0, 1), (3, 77, 64, 1, 1), (12, 200, 128, 0, 0)])
+def test_rope_chain(b200, H, L, d, rms, f16out):
+    """Rope::apply_rope (8 working nodes: two CONTs, two REPEATs, CONT(pe), two MULs, ADD) [+ QKNorm in front, + F16 cast behind] runs as one
+    kernel; the products are rounded separately like the unfused nodes, so the result matches the CPU to f32 rounding."""
+    x = f(1, L, H, d)
+    ang = np.random.default_rng(5).uniform(-3.1, 3.1, (L, d // 2)).astype(np.float32)
+    pe = np.stack([np.stack([np.cos(ang), -np.sin(ang)], -1), np.stack([np.sin(ang), np.cos(ang)], -1)], -2).astype(np.float32)   # [L, d/2, 2, 2]
+    w = (1 + 0.1 * f(d)).astype(np.float32) if rms else None
+    g, c = both(b200, "rope", [x, pe, w], ip=[f16out], fp=[1e-6])
+    assert rel(g, c) < (1e-3 if f16out else 3e-6), f"rel {rel(g, c):.2e}"
+    ref = R.rope_interleaved(R.rms_norm(x, 1e-6) * w if rms else x, pe)
+    assert rel(g.reshape(ref.shape), ref) < (1e-3 if f16out else 3e-6), f"vs restatement {rel(g.reshape(ref.shape), ref):.2e}"
+
+
 def test_conv_3d_patch_embedding(b200):
     """Wan patch embedding (wan.hpp): Conv3d kernel (1,2,2) stride (1,2,2) -> IM2COL_3D + MUL_MAT + permute."""
     IC, OC = 16, 1536

@@ -128,6 +128,10 @@ def test_restatement_vs_live_cpu_backend(cpu_oracle):
     # Q8_0 weights: the CPU backend quantises the activation rows too (ggml-cpu.c:1480-1510); its SIMD quantiser rounds ties to even
     # where the _ref restatement rounds them away from zero, so single quants may differ by one step: well under 1e-3 of the result
     _close(R.mul_mat_q8_0(wm, xm), h.run_op("CPU", "mul_mat", [wm, xm], ["q8_0", "f32"])[0, 0], 1e-3, "mul_mat q8_0 live")
+    xr = rng.standard_normal((1, 50, 3, 64)).astype(np.float32)
+    ang = rng.uniform(-3.1, 3.1, (50, 32)).astype(np.float32)
+    pe = np.stack([np.stack([np.cos(ang), -np.sin(ang)], -1), np.stack([np.sin(ang), np.cos(ang)], -1)], -2).astype(np.float32)
+    _close(R.rope_interleaved(xr, pe), h.run_op("CPU", "rope", [xr, pe, None]).reshape(3, 50, 64), 1e-7, "rope live")
     w3 = (rng.standard_normal((8 * 4, 3, 3, 3)) / 10).astype(np.float32)
     x3 = rng.standard_normal((4, 5, 9, 7)).astype(np.float32)
     _close(R.conv_3d(w3, x3, 4, (1, 1, 1), (1, 1, 1), (1, 1, 1)), h.run_op("CPU", "conv_3d", [w3, x3], ["f16", "f32"], ip=[4, 1, 1, 1, 1, 1, 1, 1, 1, 1]),
