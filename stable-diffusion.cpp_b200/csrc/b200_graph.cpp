@@ -1186,6 +1186,60 @@ static int emit_conv(b200_context* ctx, const conv_match& m, const conv_prologue
     return launches + n;
 }
 
+// adaLN modulation of the DiT blocks (Flux::modulate flux.hpp:413-428, MMDiT, Wan):  n = NORM(x);  m = MUL(n, scale);  a = ADD(n, m);
+// y = ADD(a, shift)  with scale / shift rows of the modulation Linear.  One row-norm launch that also writes the f16 / bf16 operand of
+// the projection that consumes y.
+static int try_fuse_modulate(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
+    ggml_tensor* nrm = g->nodes[i];
+    if (nrm->op != GGML_OP_NORM || nrm->type != GGML_TYPE_F32 || !ggml_is_contiguous(nrm) || nrm->src[0]->type != GGML_TYPE_F32 || nrm->src[0]->nb[0] != 4) return -2;
+    const int64_t C = nrm->ne[0];
+    const int j1 = next_node(g, fs, i);
+    if (j1 < 0) return -2;
+    const ggml_tensor* mul = g->nodes[j1];
+    if (mul->op != GGML_OP_MUL || !(mul->flags & GGML_TENSOR_FLAG_COMPUTE) || mul->src[0] != nrm || !is_f32_vec(mul->src[1], C) || mul->src[1]->ne[0] != C ||
+        !ggml_are_same_shape(mul, nrm) || !single_use(fs, mul))
+        return -2;
+    const int j2 = next_node(g, fs, j1);
+    if (j2 < 0) return -2;
+    const ggml_tensor* add1 = g->nodes[j2];
+    if (add1->op != GGML_OP_ADD || !(add1->flags & GGML_TENSOR_FLAG_COMPUTE) || add1->src[0] != nrm || add1->src[1] != mul || !single_use(fs, add1) ||
+        !ggml_are_same_shape(add1, nrm))
+        return -2;
+    const int j3 = next_node(g, fs, j2);
+    if (j3 < 0) return -2;
+    ggml_tensor* add2 = g->nodes[j3];
+    if (add2->op != GGML_OP_ADD || !(add2->flags & GGML_TENSOR_FLAG_COMPUTE) || add2->src[0] != add1 || !is_f32_vec(add2->src[1], C) || add2->src[1]->ne[0] != C ||
+        !ggml_are_same_shape(add2, nrm) || !ggml_is_contiguous(add2) || add2->type != GGML_TYPE_F32)
+        return -2;
+    // nrm is read by MUL and ADD only
+    auto it = fs.uses.find(nrm);
+    if (it == fs.uses.end() || it->second != 2 || (nrm->flags & GGML_TENSOR_FLAG_OUTPUT)) return -2;
+    if (add2->data != nrm->src[0]->data && tensors_overlap(add2->data, ggml_nbytes(add2), nrm->src[0]->data, ggml_nbytes(nrm->src[0]))) return -2;
+    // the modulation vectors are produced earlier in the graph: their memory must not be where we write
+    if (tensors_overlap(add2->data, ggml_nbytes(add2), mul->src[1]->data, (size_t)C * 4) || tensors_overlap(add2->data, ggml_nbytes(add2), add2->src[1]->data, (size_t)C * 4))
+        return -2;
+    float eps;
+    memcpy(&eps, nrm->op_params, 4);
+    int want = -1;
+    if (C % 8 == 0) {
+        for (int u = j3 + 1; u < g->n_nodes && u < j3 + 64; ++u) {
+            const ggml_tensor* c = g->nodes[u];
+            if (c->op == GGML_OP_MUL_MAT && c->src[1] == add2 && (c->src[0]->type == GGML_TYPE_F16 || c->src[0]->type == GGML_TYPE_BF16)) {
+                want = (int)c->src[0]->type;
+                break;
+            }
+        }
+    }
+    void* shadow = want >= 0 ? ws_alloc(ctx, (size_t)(ggml_nelements(add2) * 2)) : nullptr;
+    int n = b200_launch_norm(ctx->stream, B200_NORM_LAYER, b200_make_td(nrm->src[0]), b200_make_td(add2), eps, (const float*)mul->src[1]->data,
+                             (const float*)add2->src[1]->data, shadow, want, 1);
+    if (n < 0) return -2;
+    if (shadow) ctx->pack_cache[std::make_pair((const ggml_tensor*)add2, want)] = operand{shadow, want, add2->ne[0], add2->ne[0] * add2->ne[1], add2->ne[0] * add2->ne[1] * add2->ne[2]};
+    fs.done[j1] = 1; fs.done[j2] = 1; fs.done[j3] = 1;
+    *covered = 3;
+    return n;
+}
+
 // GROUP_NORM -> MUL w -> ADD b [-> SILU]     /     NORM -> MUL w -> ADD b
 static int try_fuse_norm(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
     ggml_tensor* nrm = g->nodes[i];
@@ -1699,7 +1753,10 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
         if (fuse) {
             int covered = 0;
             if (t->op == GGML_OP_MUL_MAT) n = try_fuse_mul_mat(ctx, cgraph, fs, i, &covered);
-            else if (t->op == GGML_OP_GROUP_NORM || t->op == GGML_OP_NORM) n = try_fuse_norm(ctx, cgraph, fs, i, &covered);
+            else if (t->op == GGML_OP_GROUP_NORM || t->op == GGML_OP_NORM) {
+                n = try_fuse_norm(ctx, cgraph, fs, i, &covered);
+                if (n == -2 && t->op == GGML_OP_NORM && ctx->opt_chain_fusion) n = try_fuse_modulate(ctx, cgraph, fs, i, &covered);
+            }
             else if ((t->op == GGML_OP_IM2COL || t->op == GGML_OP_UPSCALE) && ctx->opt_tc_gemm && ctx->opt_implicit_conv) n = try_fuse_conv(ctx, cgraph, fs, i, &covered);
             else if (t->op == GGML_OP_CONT) {
                 n = try_fuse_cont_cast(ctx, cgraph, fs, i, &covered);

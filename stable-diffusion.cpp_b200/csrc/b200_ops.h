@@ -41,7 +41,8 @@ enum b200_norm_kind { B200_NORM_LAYER = 0, B200_NORM_RMS = 1, B200_NORM_L2 = 2 }
 // optional fused affine (w, b: per-column f32 of length ne0, may be null)
 // out16 (optional): additionally write the result rounded to out16_type (F16 / BF16) as a dense [rows][ne0] matrix
 int b200_launch_norm(cudaStream_t s, int kind, const b200_td& src, const b200_td& dst, float eps, const float* w = nullptr, const float* b = nullptr,
-                     void* out16 = nullptr, int out16_type = -1);
+                     void* out16 = nullptr, int out16_type = -1, int modulate = 0);
+// modulate = 1: y = (n + n * w) + b with every step rounded (adaLN `x * (1 + scale) + shift` as the reference graph spells it: MUL, ADD, ADD)
 int b200_launch_soft_max(cudaStream_t s, const b200_td& src, const b200_td* mask, const b200_td& dst, float scale, float max_bias);
 
 // ---- im2col.cu -------------------------------------------------------------------------------

@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(1024) k_group_norm(const float* __restrict__ x
 // row norms: one CTA per row (ne0 elements, arbitrary row placement, unit stride inside the row)
 // ------------------------------------------------------------------------------------------
 template <int KIND>
-__global__ void k_row_norm(b200_td a, b200_td d, float eps, const float* __restrict__ rw, const float* __restrict__ rb, void* out16, int out16_bf16) {
+__global__ void k_row_norm(b200_td a, b200_td d, float eps, const float* __restrict__ rw, const float* __restrict__ rb, void* out16, int out16_bf16,
+                           int modulate) {
     pdl_wait();
     pdl_launch_dependents();
     __shared__ float red[32];
@@ -176,7 +177,7 @@ __global__ void k_row_norm(b200_td a, b200_td d, float eps, const float* __restr
             int64_t i = threadIdx.x + (int64_t)k * blockDim.x;
             if (i < n) {
                 float o = (v[k] - mean) * scale;
-                if (rw) o = o * rw[i] + (rb ? rb[i] : 0.f);
+                if (rw) o = modulate ? __fadd_rn(__fadd_rn(o, __fmul_rn(o, rw[i])), rb[i]) : o * rw[i] + (rb ? rb[i] : 0.f);
                 y[i] = o;
                 if (out16) {
                     if (out16_bf16) ((__nv_bfloat16*)out16)[row * n + i] = __float2bfloat16_rn(o);
@@ -187,7 +188,7 @@ __global__ void k_row_norm(b200_td a, b200_td d, float eps, const float* __restr
     } else {
         for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
             float o = (x[i] - mean) * scale;
-            if (rw) o = o * rw[i] + (rb ? rb[i] : 0.f);
+            if (rw) o = modulate ? __fadd_rn(__fadd_rn(o, __fmul_rn(o, rw[i])), rb[i]) : o * rw[i] + (rb ? rb[i] : 0.f);
             y[i] = o;
             if (out16) {
                 if (out16_bf16) ((__nv_bfloat16*)out16)[row * n + i] = __float2bfloat16_rn(o);
@@ -264,16 +265,17 @@ int b200_launch_group_norm(cudaStream_t s, const b200_td& src, const b200_td& ds
 }
 
 int b200_launch_norm(cudaStream_t s, int kind, const b200_td& src, const b200_td& dst, float eps, const float* w, const float* b, void* out16,
-                     int out16_type) {
+                     int out16_type, int modulate) {
+    if (modulate && (!w || !b)) return -1;
     const int bf = out16_type == GGML_TYPE_BF16 ? 1 : 0;
     int64_t nrows = src.ne[1] * src.ne[2] * src.ne[3];
     if (nrows == 0 || src.ne[0] == 0) return 0;
     int threads = src.ne[0] >= 4096 ? 1024 : (src.ne[0] >= 1024 ? 256 : 128);
     if (nrows > 0x7fffffff) return -1;
     switch (kind) {
-        case B200_NORM_LAYER: b200_launch(k_row_norm<B200_NORM_LAYER>, dim3((unsigned)nrows), dim3(threads), 0, s, src, dst, eps, w, b, out16, bf); break;
-        case B200_NORM_RMS: b200_launch(k_row_norm<B200_NORM_RMS>, dim3((unsigned)nrows), dim3(threads), 0, s, src, dst, eps, w, b, out16, bf); break;
-        default: b200_launch(k_row_norm<B200_NORM_L2>, dim3((unsigned)nrows), dim3(threads), 0, s, src, dst, eps, w, b, out16, bf); break;
+        case B200_NORM_LAYER: b200_launch(k_row_norm<B200_NORM_LAYER>, dim3((unsigned)nrows), dim3(threads), 0, s, src, dst, eps, w, b, out16, bf, modulate); break;
+        case B200_NORM_RMS: b200_launch(k_row_norm<B200_NORM_RMS>, dim3((unsigned)nrows), dim3(threads), 0, s, src, dst, eps, w, b, out16, bf, modulate); break;
+        default: b200_launch(k_row_norm<B200_NORM_L2>, dim3((unsigned)nrows), dim3(threads), 0, s, src, dst, eps, w, b, out16, bf, modulate); break;
     }
     return 1;
 }
