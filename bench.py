@@ -57,14 +57,15 @@ LAYOUT_TEXT = {
 
 def ncu_traffic():
     """DRAM bytes (read + write) per k_gemm_tc launch, averaged over the launches of the committed `ncu --set full` capture
-    (profiles/r01_ncu_full_top_kernels.json).  Offline evidence, never measured under the timed run; null when absent."""
-    p = REPO / "profiles" / "r01_ncu_full_top_kernels.json"
-    if not p.exists():
+    (profiles/r01_ncu_full_*.json).  Offline evidence, never measured under the timed run; null when absent."""
+    # capture of the default (batched-CFG) forward first, the serial-forward capture as fallback
+    p = next((c for c in (REPO / "profiles" / "r01_ncu_full_gemm_batched_cfg.json", REPO / "profiles" / "r01_ncu_full_top_kernels.json") if c.exists()), None)
+    if p is None:
         return dict(traffic=None)
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tot, n = 0.0, 0
     for row in json.loads(p.read_text()):
-        if not row.get("Kernel Name", "").startswith("k_gemm_tc"):
+        if "k_gemm_tc" not in row.get("Kernel Name", ""):
             continue
         b = 0.0
         for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):

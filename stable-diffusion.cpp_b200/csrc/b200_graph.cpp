@@ -277,7 +277,6 @@ struct mm_fusion {
     const float* bias = nullptr;  // f32 vector
     int bias_mode = 0;            // 1: per output row m (Linear bias), 2: per n (conv bias: n == output channel)
     const float* residual = nullptr;   // same [M, N] layout as out, added last
-    const float* mscale = nullptr;     // per-m factor between bias and residual (gate of `x + gate * Linear(...)`, flux.hpp:560-590)
     const ggml_tensor* src1_pre = nullptr;   // activation to read instead of src[1] (same shape): the input of a unary op folded in
     int pre_act = 0;                          // 1: SiLU applied to src1_pre on load (only the few-row GEMV path can do this)
 };
@@ -304,7 +303,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
             b200_gemv_supported((int)src0->type, M, N, K, src0->data, (int64_t)src0->nb[1] / 2, x->data)) {
             float* out = fz && fz->out ? fz->out : (float*)dst->data;
             const float* bias = fz && fz->bias && fz->bias_mode == 1 ? fz->bias : nullptr;
-            if (!(fz && fz->bias && fz->bias_mode != 1) && !(fz && fz->mscale)) {
+            if (!(fz && fz->bias && fz->bias_mode != 1)) {
                 int n = b200_launch_gemv(ctx->stream, (int)src0->type, src0->data, (int64_t)src0->nb[1] / 2, (const float*)x->data, (int64_t)x->nb[1] / 4, out,
                                          (int64_t)dst->nb[1] / 4, M, N, K, bias, fz ? fz->residual : nullptr, (int64_t)dst->nb[1] / 4, fz ? fz->pre_act : 0);
                 if (n > 0) { ctx->stats.reserved[6] += 1; return n; }
@@ -336,14 +335,12 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
         g.d_batch_stride = dst->nb[2] / 4;
         if (fz && fz->bias) { g.bias = fz->bias; g.bias_mode = fz->bias_mode; }
         if (fz && fz->residual) { g.residual = fz->residual; g.ldr = g.ldd; }
-        if (fz && fz->mscale) g.mscale = fz->mscale;
         // model weights read in place are constants of the graph: their first ring-full may be fetched before the PDL wait.  Not for
         // the first kernel of a graph_compute (its stream predecessor belongs to an earlier call, e.g. a weight update).
         if (ctx->opt_early_weights && a.ptr == src0->data && src0->buffer && src0->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS &&
             (ctx->launched_any || launches > 0))
             g.early = 1;
         int n = launch_tc(ctx, g);
-        if (n < 0 && fz && fz->mscale) return -2;      // only the tensor-core epilogue applies the gate: run the chain unfused
         if (n < 0) {
             // CUDA-core reference kernel (debug option, or shapes the TMA cannot describe)
             n = 0;
@@ -895,27 +892,6 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
                 fz.bias_mode = mode;
                 fz.out = (float*)add->data;
                 chain.push_back(j);
-            }
-        }
-    }
-    // gate: ... -> MUL(value, g[M]) (the adaLN gate of the DiT blocks), applied between bias and residual in the epilogue
-    {
-        const int jg = chain.empty() ? next_node(g, fs, i) : next_node(g, fs, chain.back());
-        const ggml_tensor* curv = chain.empty() ? (const ggml_tensor*)mm : g->nodes[chain.back()];
-        if (jg >= 0 && ctx->opt_chain_fusion) {
-            ggml_tensor* mul = g->nodes[jg];
-            if (mul->op == GGML_OP_MUL && (mul->flags & GGML_TENSOR_FLAG_COMPUTE) && mul->type == GGML_TYPE_F32 && ggml_is_contiguous(mul) &&
-                ggml_are_same_shape(mul, mm) && mm->ne[3] == 1 && !(curv->flags & GGML_TENSOR_FLAG_OUTPUT)) {
-                const ggml_tensor* val = nullptr;
-                const ggml_tensor* gv = nullptr;
-                if (order_preserving_view_of(fs, mul->src[0], curv)) { val = mul->src[0]; gv = mul->src[1]; }
-                else if (order_preserving_view_of(fs, mul->src[1], curv)) { val = mul->src[1]; gv = mul->src[0]; }
-                if (gv && is_f32_vec(gv, M) && gv->ne[0] == M && (single_use(fs, val) || mul->data == curv->data) &&
-                    !overlaps_range(mul->data, ggml_nbytes(mul), gv->data, (size_t)M * 4)) {
-                    fz.mscale = (const float*)gv->data;
-                    fz.out = (float*)mul->data;
-                    chain.push_back(jg);
-                }
             }
         }
     }

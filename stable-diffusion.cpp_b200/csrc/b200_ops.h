@@ -72,7 +72,6 @@ struct b200_gemm_args {
     int         bias_mode;  // 0 none, 1 per-m (row of A: linear bias), 2 per-n (row of B: conv bias / channel)
     const float* residual;  // optional [N][M] like D (added after bias)
     int64_t     ldr;
-    const float* mscale;    // optional per-m factor: D = (acc + bias) * mscale[m] + residual (gated residual of the DiT blocks)
     int         act;        // 0 none, 1 SiLU, 2 GELU(tanh)
     int         early;      // bit 0: A, bit 1: B is a constant (weight) operand no kernel of this graph writes -> may be fetched before the PDL wait
     void*       trace;      // optional device buffer of 8 uint64: phase timestamps of CTA (0,0,0) (tools/gemm_bench)

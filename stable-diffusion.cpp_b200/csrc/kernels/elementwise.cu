@@ -223,7 +223,7 @@ __global__ void k_binary_generic(b200_td a, b200_td b, b200_td d, int64_t n) {
 }
 
 // fast path: a, d contiguous f32 with identical shape; b contiguous f32 and either
-//   mode 0: same shape, mode 1: b = [ne0,1,1,1] (row vector), mode 2: b = [1,1,C,1] over inner = ne0*ne1 (channel vector)
+//   mode 0: same shape, mode 1: b = [ne0,1,1,1] (row vector), mode 2: b = [1,1,C,1|N] over inner = ne0*ne1 (channel vector, optionally per image)
 template <int OP>
 __global__ void k_binary_f32_vec4(const float4* __restrict__ a, const float* __restrict__ b, float4* __restrict__ d, int64_t n4,
                                   int mode, int64_t ne0, int64_t inner, int64_t C) {
@@ -254,10 +254,12 @@ int launch_binary_op(cudaStream_t s, const b200_td& a, const b200_td& b, const b
         int64_t nb_el = td_nelements(b);
         if (nb_el == n) mode = 0;
         else if (nb_el == b.ne[0] && b.ne[0] == d.ne[0] && d.ne[0] % 4 == 0) mode = 1;
-        else if (nb_el == b.ne[2] && b.ne[2] == d.ne[2] && (d.ne[0] * d.ne[1]) % 4 == 0) mode = 2;
+        // channel vector [1,1,C,1] over every image, or one vector per image [1,1,C,N] (the `h + emb` of a batched-CFG ResBlock): a and d are
+        // contiguous [W,H,C,N], so element i belongs to flat channel i / (W*H) = c + C*n, which is b's own flat index
+        else if (b.ne[0] == 1 && b.ne[1] == 1 && b.ne[2] == d.ne[2] && (b.ne[3] == 1 || b.ne[3] == d.ne[3]) && (d.ne[0] * d.ne[1]) % 4 == 0) mode = 2;
         if (mode >= 0) {
             b200_launch(k_binary_f32_vec4<OP>, dim3(grid_for(n / 4)), dim3(kThreads), 0, s, (const float4*)a.data, (const float*)b.data, (float4*)d.data, n / 4, mode,
-                                                                        d.ne[0], d.ne[0] * d.ne[1], d.ne[2]);
+                                                                        d.ne[0], d.ne[0] * d.ne[1], b.ne[2] * b.ne[3]);
             return 1;
         }
     }

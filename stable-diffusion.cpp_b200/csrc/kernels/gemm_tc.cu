@@ -48,7 +48,6 @@ struct GemmKParams {
     int bias_mode;     // 0 none, 1 per m, 2 per n
     const float* residual;
     int64_t ldr, r_batch_stride;
-    const float* mscale;   // optional per-m factor applied after bias, before the residual (adaLN gate: x + gate * (W y + b))
     int act;           // 0 none, 1 silu, 2 gelu(tanh)
     // implicit-GEMM convolution (conv != 0): A is an NHWC f16 image read through a 4-D map (C, W, H, N) with halo boxes;
     // k-block kb -> filter tap kb / cblocks and 64-channel block kb % cblocks; rows of the tile are output pixels
@@ -214,7 +213,6 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
         float* Dp = p.D + (int64_t)batch * p.d_batch_stride;
         const float* Rp = p.residual ? p.residual + (int64_t)batch * p.r_batch_stride : nullptr;
         const float bias_m = (p.bias_mode == 1 && m < p.M) ? p.bias[m] : 0.f;
-        const float gate_m = (p.mscale && m < p.M) ? p.mscale[m] : 1.f;     // x * 1.0f is exact: no branch in the store loops
         float* sred = (float*)smem;   // [BN][BM] f32 partial tile; the operand ring is dead once tmem_full has fired
         const int ncols = (int)min((int64_t)BN, p.N - n0);
         const bool mvalid = m < p.M;
@@ -241,7 +239,7 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
                 if (rptr == nullptr) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float v = __fmul_rn(__uint_as_float(r[j]) + bias_m + __shfl_sync(0xffffffffu, bn, j), gate_m);
+                        const float v = __uint_as_float(r[j]) + bias_m + __shfl_sync(0xffffffffu, bn, j);
                         if (mvalid && c0 + j < ncols) dptr[(int64_t)(c0 + j) * p.ldd] = v;
                     }
                 } else {
@@ -252,7 +250,7 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
                     for (int j = 0; j < 32; ++j) rr[j] = (mvalid && c0 + j < ncols) ? rptr[(int64_t)(c0 + j) * p.ldr] : 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float v = __fmul_rn(__uint_as_float(r[j]) + bias_m + __shfl_sync(0xffffffffu, bn, j), gate_m) + rr[j];
+                        const float v = __uint_as_float(r[j]) + bias_m + __shfl_sync(0xffffffffu, bn, j) + rr[j];
                         if (mvalid && c0 + j < ncols) dptr[(int64_t)(c0 + j) * p.ldd] = v;
                     }
                 }
@@ -269,7 +267,7 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
                     if (m < p.M && n < p.N) {
                         float v = __uint_as_float(r[j]) + bias_m;
                         if (p.bias_mode == 2) v += p.bias[n];
-                        v = __fmul_rn(epilogue_act(v, p.act), gate_m);
+                        v = epilogue_act(v, p.act);
                         if (Rp) v += Rp[n * p.ldr + m];
                         Dp[n * p.ldd + m] = v;
                     }
@@ -301,13 +299,6 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
                 if (mrow + 2 < p.M) bm.z = p.bias[mrow + 2];
                 if (mrow + 3 < p.M) bm.w = p.bias[mrow + 3];
             }
-            float4 gm = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (p.mscale) {
-                if (mrow + 0 < p.M) gm.x = p.mscale[mrow + 0];
-                if (mrow + 1 < p.M) gm.y = p.mscale[mrow + 1];
-                if (mrow + 2 < p.M) gm.z = p.mscale[mrow + 2];
-                if (mrow + 3 < p.M) gm.w = p.mscale[mrow + 3];
-            }
             const uint32_t sred_local = smem_u32(smem);
             uint32_t peer[8];
 #pragma unroll
@@ -328,7 +319,6 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
                 const float bn = p.bias_mode == 2 ? p.bias[n] : 0.f;
                 v.x += bm.x + bn; v.y += bm.y + bn; v.z += bm.z + bn; v.w += bm.w + bn;
                 if (p.act) { v.x = epilogue_act(v.x, p.act); v.y = epilogue_act(v.y, p.act); v.z = epilogue_act(v.z, p.act); v.w = epilogue_act(v.w, p.act); }
-                v.x = __fmul_rn(v.x, gm.x); v.y = __fmul_rn(v.y, gm.y); v.z = __fmul_rn(v.z, gm.z); v.w = __fmul_rn(v.w, gm.w);
                 float* dst = Dp + n * p.ldd + mrow;
                 if (vec_ok && (Rp == nullptr || (((p.ldr & 3) == 0) && ((((uintptr_t)Rp) & 15) == 0)))) {
                     if (Rp) { const float4 rr = *(const float4*)(Rp + n * p.ldr + mrow); v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
@@ -501,7 +491,6 @@ int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     kp.ne12 = (int)g.batch; kp.r2 = (int)g.a_bcast; kp.r3 = 1;
     kp.bias = g.bias; kp.bias_mode = g.bias ? g.bias_mode : 0;
     kp.residual = g.residual; kp.ldr = g.ldr; kp.r_batch_stride = g.d_batch_stride;
-    kp.mscale = g.mscale;
     kp.act = g.act;
     kp.early = g.early & 3;
     kp.trace = (unsigned long long*)g.trace;

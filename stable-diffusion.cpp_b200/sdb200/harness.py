@@ -14,7 +14,8 @@ import numpy as np
 
 REPO = Path(__file__).resolve().parents[2]
 HARNESS_SO = REPO / "host" / "_ref" / "libsd_harness.so"
-B200_SO = REPO / "stable-diffusion.cpp_b200" / "lib" / "libggml-b200.so"
+# SDB200_PLUGIN: A/B a differently built plugin (profiling only); the default is the in-tree build
+B200_SO = Path(os.environ.get("SDB200_PLUGIN", str(REPO / "stable-diffusion.cpp_b200" / "lib" / "libggml-b200.so")))
 
 FLAG_FLASH_ATTN = 1
 FLAG_CONV_DIRECT = 2

@@ -10,6 +10,8 @@
   cpu_ops.npz              seeded inputs and the reference CPU backend's outputs (oracle/_ref) for each hot-path op
   cpu_models.npz           reference CPU backend outputs of whole synthetic-weight models (unet_tiny fa/non-fa,
                            vae_decoder on an 8x8 latent, scheduler-driven 3-step sample)
+  cpu_models_dit.npz       (`make_golden.py dit`) the same for the larger architectures of SURVEY.md 8a: SD1.5 UNet 64x64 (default graph),
+                           SDXL UNet 32x32, flux_tiny (bf16), SD3-medium MMDiT 32x32 (f16), Wan2.1-1.3B DiT (q8_0, 3x16x16 latent)
 """
 import json
 import re
@@ -101,5 +103,39 @@ def main():
     print("golden fixtures written to", HERE)
 
 
+DIT_CASES = {
+    # key: (arch, wtype, flags, x shape, context shape, y shape or None, timestep)
+    "sd15_unet_fa0": ("sd15_unet", "f16", 0, (1, 4, 64, 64), (1, 77, 768), None, 999.0),
+    "sdxl_unet_32": ("sdxl_unet", "f16", 0, (1, 4, 32, 32), (1, 77, 2048), (1, 2816), 999.0),
+    "flux_tiny": ("flux_tiny", "bf16", 1, (1, 16, 32, 32), (1, 64, 4096), (1, 768), 1.0),
+    "mmdit_sd3": ("mmdit_sd3", "f16", 1, (1, 16, 32, 32), (1, 154, 4096), (1, 2048), 500.0),
+    "wan_1_3b": ("wan_1_3b", "q8_0", 1, (16, 3, 16, 16), (1, 512, 4096), None, 500.0),
+}
+
+
+def dit_inputs(h, key):
+    arch, wtype, flags, xs, cs, ys, t = DIT_CASES[key]
+    return h.randn(42, xs), np.array([t], np.float32), h.randn(43, cs), (h.randn(44, ys) if ys else None)
+
+
+def main_dit():
+    from sdb200 import Harness
+    from oracle.cpu_ref import load_cpu_oracle
+    h = Harness()
+    variant = load_cpu_oracle(h)
+    out = {}
+    for key, (arch, wtype, flags, *_rest) in DIT_CASES.items():
+        m = h.model("CPU", arch, wtype, flags, 1234, 8)
+        x, t, ctx, y = dit_inputs(h, key)
+        out[key], _ = m.forward(x, t, ctx, y)
+        m.close()
+        print(key, out[key].shape, float(out[key].std()), flush=True)
+    np.savez_compressed(HERE / "cpu_models_dit.npz", **out)
+    print("written with CPU variant", variant)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "dit":
+        main_dit()
+    else:
+        main()

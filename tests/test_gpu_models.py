@@ -202,3 +202,25 @@ def test_batched_cfg_on_device(b200, arch, shape):
     cpu_c, _ = mc.forward(x, t, c)
     mc.close()
     assert rel(two[0:1], cpu_c) < 3e-3, f"batched forward vs CPU oracle: {rel(two[0:1], cpu_c):.2e}"
+
+
+DIT_TOL = {"sd15_unet_fa0": 3e-3, "sdxl_unet_32": 4e-3, "flux_tiny": 3e-2, "mmdit_sd3": 2e-2, "wan_1_3b": 5e-2}
+
+
+@pytest.mark.parametrize("key", sorted(DIT_TOL))
+def test_models_vs_committed_cpu_fixtures(b200, key):
+    """The same architectures against outputs of the reference CPU backend COMMITTED under tests/golden/cpu_models_dit.npz (generated by
+    tests/golden/make_golden.py dit where /root/reference exists): parity does not depend on the CPU oracle being runnable on the box."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", GOLD / "make_golden.py")
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    h, dev = b200
+    gold = np.load(GOLD / "cpu_models_dit.npz")[key]
+    arch, wtype, flags, *_ = mg.DIT_CASES[key]
+    x, t, ctx, y = mg.dit_inputs(h, key)
+    m = h.model(dev, arch, wtype, flags, 1234, 0)
+    out, _ = m.forward(x, t, ctx, y)
+    m.close()
+    assert out.shape == gold.shape and np.isfinite(out).all()
+    assert rel(out, gold) < DIT_TOL[key], f"{key}: rel_l2 {rel(out, gold):.2e}"

@@ -148,6 +148,14 @@ def test_small_data_movement_ops(b200):
     a, b_ = f(1, 320, 8, 8), f(1, 640, 8, 8)
     g, c = both(b200, "concat", [a, b_], ip=[2])
     assert np.array_equal(g, c)
+    # dim-0 concat (single-stream Flux block) and the broadcast adds of ResBlocks: per-channel vector shared by / distinct per image
+    g, c = both(b200, "concat", [f(1, 1, 50, 3072), f(1, 1, 50, 12288)], ip=[0])
+    assert np.array_equal(g, c)
+    for bshape in ((1, 320, 1, 1), (2, 320, 1, 1)):
+        g, c = both(b200, "add", [f(2, 320, 16, 16), f(*bshape)])
+        assert np.array_equal(g, c), bshape
+        g, c = both(b200, "mul", [f(2, 320, 16, 16), f(*bshape)])
+        assert np.array_equal(g, c), bshape
     t = np.array([999.0, 500.5, 1.0], np.float32)
     g, c = both(b200, "timestep_embedding", [t], ip=[320, 10000])
     assert np.abs(g - c).max() < 2e-4                        # cosf/sinf at ~1e3 rad: libm vs CUDA differ in the last ulps of the argument reduction

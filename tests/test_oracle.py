@@ -152,3 +152,22 @@ def test_committed_model_fixture_matches_live_cpu_backend(cpu_oracle):
     m.close()
     # different CPU variants (AVX2 / AVX-512 / AMX) reduce in different orders: allow float noise, not more
     _close(out, gold["unet_tiny_fa0"], 1e-4, "unet_tiny vs fixture")
+
+
+def test_committed_dit_fixtures_match_live_cpu_backend(cpu_oracle):
+    """tests/golden/cpu_models_dit.npz really is what the reference CPU backend computes for the seeded synthetic models (the two cheap
+    ones are re-run here; blocking / SIMD variant of the host may move the last bits, hence a tolerance instead of equality)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", GOLD / "make_golden.py")
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    h = cpu_oracle
+    gold = np.load(GOLD / "cpu_models_dit.npz")
+    for key in ("flux_tiny", "wan_1_3b"):
+        arch, wtype, flags, *_ = mg.DIT_CASES[key]
+        x, t, ctx, y = mg.dit_inputs(h, key)
+        m = h.model("CPU", arch, wtype, flags, 1234, 4)
+        out, _ = m.forward(x, t, ctx, y)
+        m.close()
+        r = float(np.linalg.norm(out.astype(np.float64) - gold[key]) / np.linalg.norm(gold[key].astype(np.float64)))
+        assert r < 1e-3, f"{key}: {r:.2e}"
