@@ -72,7 +72,7 @@ typedef struct ggml_b200_stats {
     uint64_t tc_gemm_launches;  /* tcgen05 GEMM launches                                     */
     uint64_t reserved[8];       /* [0] flop of the tcgen05 GEMMs timed under "kernel_timing", [1] their device time in us,
                                    [2] fused flash-attention launches, [3] CUDA-graph replays, [4] implicit-GEMM convolutions,
-                                   [5..7] unused (0) */
+                                   [5] attention launches that read Q in place (CONT skipped), [6] few-row GEMV launches, [7] fused RoPE launches */
 } ggml_b200_stats;
 
 /* copy the backend instance's counters; returns 0 on success */
@@ -87,7 +87,9 @@ void ggml_backend_b200_reset_stats(ggml_backend_t backend);
  *   "kernel_timing" 1/0 CUDA events around every tcgen05 GEMM launch (roofline pass; disables graph replay while on)
  *   "fused_attn"  1/0   single-kernel FLASH_ATTN_EXT (0 = GEMM + softmax + GEMM through workspace)
  *   "implicit_conv" 1/0 IM2COL+MUL_MAT chains as TMA halo-tile implicit GEMM (0 = materialised im2col)
- *   "early_weights" 1/0 GEMMs fetch the first tiles of constant weights before the programmatic-dependent-launch wait
+ *   "early_weights" 1/0 GEMMs fetch the first tiles of constant weights before the programmatic-dependent-launch wait (default 0)
+ *   "chain_fusion" 1/0  producer-side fusions: GEGLU tail, Q read in place, f16 operand copies written by their producers, RoPE, adaLN
+ *   "gemv"        1/0   MUL_MAT with <= 4 activation rows as a weight-streaming GEMV
  * returns 0 on success, -1 for an unknown key. */
 int ggml_backend_b200_set_option(ggml_backend_t backend, const char* key, int value);
 

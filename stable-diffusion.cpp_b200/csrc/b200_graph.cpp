@@ -48,6 +48,7 @@ b200_context* b200_context_create(const b200_device_info& info) {
     ctx->opt_early_weights = env_flag("GGML_B200_EARLY_WEIGHTS", 0) != 0;   // measured neutral on the SD1.5 step (profiles/r01_summary.md): off by default
     ctx->opt_chain_fusion = env_flag("GGML_B200_CHAIN_FUSION", 1) != 0;
     ctx->opt_gemv = env_flag("GGML_B200_GEMV", 1) != 0;
+    ctx->opt_fold_batch = env_flag("GGML_B200_FOLD_BATCH", 0) != 0;   // written at the end of round 1, not yet measured: off by default
     return ctx;
 }
 
@@ -79,6 +80,7 @@ int b200_context_set_option(b200_context* ctx, const char* key, int value) {
     else if (!strcmp(key, "early_weights")) ctx->opt_early_weights = value != 0;
     else if (!strcmp(key, "chain_fusion")) ctx->opt_chain_fusion = value != 0;
     else if (!strcmp(key, "gemv")) ctx->opt_gemv = value != 0;
+    else if (!strcmp(key, "fold_batch")) ctx->opt_fold_batch = value != 0;
     else return -1;
     return 0;
 }
@@ -316,19 +318,28 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
     if (!prepare_operand(ctx, src0, ct, &a, &launches)) return -1;
     if (!prepare_operand(ctx, src1, ct, &b, &launches)) return -1;
 
-    for (int64_t i3 = 0; i3 < ne13; ++i3) {
+    // One weight matrix against a batch of activation matrices that lie back to back in memory (a Linear on [C, L, N] tokens of a
+    // batched-CFG graph): fold the batch into the N dimension -- fewer, fuller tiles (N = 64 + 64 fills one 128-row tile instead of
+    // two half-empty ones) and one pass over the weights instead of one per image.
+    const bool fold = ctx->opt_fold_batch && ne02 == 1 && ne03 == 1 && ne12 * ne13 > 1 && b.batch_stride == b.ld * N &&
+                      (ne13 == 1 || b.b3_stride == b.batch_stride * ne12) && dst->nb[2] == dst->nb[1] * (size_t)N &&
+                      (ne13 == 1 || dst->nb[3] == dst->nb[2] * (size_t)ne12) && !(fz && fz->bias && fz->bias_mode == 2);
+    const int64_t Ng = fold ? N * ne12 * ne13 : N;            // rows of the activation operand per GEMM
+    const int64_t nb12 = fold ? 1 : ne12, nb13 = fold ? 1 : ne13, rr2 = fold ? 1 : r2, rr3 = fold ? 1 : r3;
+
+    for (int64_t i3 = 0; i3 < nb13; ++i3) {
         const int64_t es = fp_size(ct);
         b200_gemm_args g;
         memset(&g, 0, sizeof(g));
-        g.A = (const char*)a.ptr + (i3 / r3) * a.b3_stride * es;
+        g.A = (const char*)a.ptr + (i3 / rr3) * a.b3_stride * es;
         g.B = (const char*)b.ptr + i3 * b.b3_stride * es;
         g.type = ct;
-        g.M = M; g.N = N; g.K = K;
+        g.M = M; g.N = Ng; g.K = K;
         g.lda = a.ld; g.ldb = b.ld;
-        g.batch = ne12;
+        g.batch = nb12;
         g.a_batch_stride = a.batch_stride;
         g.b_batch_stride = b.batch_stride;
-        g.a_bcast = r2;
+        g.a_bcast = rr2;
         char* out_base = fz && fz->out ? (char*)fz->out : (char*)dst->data;
         g.D = (float*)(out_base + i3 * dst->nb[3]);
         g.ldd = dst->nb[1] / 4;
@@ -344,21 +355,21 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
         if (n < 0) {
             // CUDA-core reference kernel (debug option, or shapes the TMA cannot describe)
             n = 0;
-            for (int64_t i2 = 0; i2 < ne12; ++i2) {
-                int r = b200_launch_gemm_ref(ctx->stream, (const char*)g.A + (i2 / r2) * a.batch_stride * es, ct, a.ld * es,
-                                             (const char*)g.B + i2 * b.batch_stride * es, ct, b.ld * es, g.D + i2 * g.d_batch_stride, g.ldd, M, N, K);
+            for (int64_t i2 = 0; i2 < nb12; ++i2) {
+                int r = b200_launch_gemm_ref(ctx->stream, (const char*)g.A + (i2 / rr2) * a.batch_stride * es, ct, a.ld * es,
+                                             (const char*)g.B + i2 * b.batch_stride * es, ct, b.ld * es, g.D + i2 * g.d_batch_stride, g.ldd, M, Ng, K);
                 if (r < 0) return -1;
                 n += r;
             }
             if (fz && fz->bias) {
                 b200_td o;
                 o.data = g.D; o.type = GGML_TYPE_F32;
-                o.ne[0] = M; o.ne[1] = N; o.ne[2] = ne12; o.ne[3] = 1;
-                o.nb[0] = 4; o.nb[1] = g.ldd * 4; o.nb[2] = g.d_batch_stride * 4; o.nb[3] = o.nb[2] * ne12;
+                o.ne[0] = M; o.ne[1] = Ng; o.ne[2] = nb12; o.ne[3] = 1;
+                o.nb[0] = 4; o.nb[1] = g.ldd * 4; o.nb[2] = g.d_batch_stride * 4; o.nb[3] = o.nb[2] * nb12;
                 b200_td bv = o;
                 bv.data = (void*)fz->bias;
-                bv.ne[0] = fz->bias_mode == 1 ? M : 1; bv.ne[1] = fz->bias_mode == 2 ? N : 1; bv.ne[2] = 1; bv.ne[3] = 1;
-                bv.nb[0] = 4; bv.nb[1] = 4; bv.nb[2] = bv.nb[3] = 4 * (fz->bias_mode == 1 ? M : N);
+                bv.ne[0] = fz->bias_mode == 1 ? M : 1; bv.ne[1] = fz->bias_mode == 2 ? Ng : 1; bv.ne[2] = 1; bv.ne[3] = 1;
+                bv.nb[0] = 4; bv.nb[1] = 4; bv.nb[2] = bv.nb[3] = 4 * (fz->bias_mode == 1 ? M : Ng);
                 int r = b200_launch_binary(ctx->stream, B200_ADD, o, bv, o);
                 if (r < 0) return -1;
                 n += r;
@@ -366,8 +377,8 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
             if (fz && fz->residual) {
                 b200_td o;
                 o.data = g.D; o.type = GGML_TYPE_F32;
-                o.ne[0] = M; o.ne[1] = N; o.ne[2] = ne12; o.ne[3] = 1;
-                o.nb[0] = 4; o.nb[1] = g.ldd * 4; o.nb[2] = g.d_batch_stride * 4; o.nb[3] = o.nb[2] * ne12;
+                o.ne[0] = M; o.ne[1] = Ng; o.ne[2] = nb12; o.ne[3] = 1;
+                o.nb[0] = 4; o.nb[1] = g.ldd * 4; o.nb[2] = g.d_batch_stride * 4; o.nb[3] = o.nb[2] * nb12;
                 b200_td rv = o;
                 rv.data = (void*)fz->residual;
                 int r = b200_launch_binary(ctx->stream, B200_ADD, o, rv, o);

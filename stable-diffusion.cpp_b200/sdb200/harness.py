@@ -41,7 +41,7 @@ def _as_sdh(a: np.ndarray | None):
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_size_t, C.c_void_p)
 
 STAT_KEYS = ("graphs", "kernel_launches", "nodes_executed", "fused_nodes", "last_graph_ms", "total_graph_ms", "tc_gemm_launches",
-             "tc_gemm_flops", "tc_gemm_us", "fused_attn_launches", "cuda_graph_replays", "implicit_convs", "q_read_in_place", "r6", "r7")
+             "tc_gemm_flops", "tc_gemm_us", "fused_attn_launches", "cuda_graph_replays", "implicit_convs", "q_read_in_place", "gemv_launches", "rope_launches")
 
 
 class Harness:
