@@ -93,6 +93,11 @@ void ggml_backend_b200_reset_stats(ggml_backend_t backend);
  * returns 0 on success, -1 for an unknown key. */
 int ggml_backend_b200_set_option(ggml_backend_t backend, const char* key, int value);
 
+/* ggml_backend_device_i::supports_op (ggml-backend-impl.h:186) without a device: 1 when every B200 of this backend executes `op`.
+ * Callable on a machine without a GPU -- the CPU test suite walks the reference's model graphs with it, because any 0 would make
+ * sd.cpp route that node to its CPU backend through ggml_backend_sched (src/core/ggml_extend.hpp:2198-2225). */
+int ggml_backend_b200_op_supported(const struct ggml_tensor* op);
+
 #ifdef __cplusplus
 }
 #endif

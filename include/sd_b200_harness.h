@@ -91,6 +91,13 @@ int sdh_sample(sdh_model* m, const char* method, int steps, float cfg_scale, flo
                sdh_tensor* out, float* sigmas_out, float* timesteps_out, int* n_forwards,
                double* wall_ms);
 
+/* Builds the model's graph for these inputs (nothing is computed) and asks `fn` -- e.g. ggml_backend_b200_op_supported of the plugin -- about
+ * every node: returns how many nodes `fn` rejects (0 = the whole graph runs on that backend, no ggml_backend_sched CPU fallback), or < 0
+ * on error; the first rejected node is described in `first_unsupported`. */
+typedef int (*sdh_op_supported_fn)(const struct ggml_tensor* op);
+int sdh_model_check_ops(sdh_model* m, const sdh_tensor* x, const sdh_tensor* timesteps, const sdh_tensor* context, const sdh_tensor* y,
+                        sdh_op_supported_fn fn, char* first_unsupported, size_t len);
+
 /* CFG-batch split over a pair of GPUs: like sdh_sample, but this process evaluates only ONE branch per
  * step (role 0 = cond, 1 = uncond) and calls `exchange(mine, cond_out, uncond_out, n, user)` so the caller can
  * all-gather the eps prediction over NCCL; it must fill both outputs (n floats each) and return 0.  role < 0 or

@@ -476,6 +476,7 @@ static void* b200_reg_get_proc_address(ggml_backend_reg_t, const char* name) {
     if (!strcmp(name, "ggml_backend_b200_reset_stats")) return (void*)ggml_backend_b200_reset_stats;
     if (!strcmp(name, "ggml_backend_b200_set_option")) return (void*)ggml_backend_b200_set_option;
     if (!strcmp(name, "ggml_backend_b200_init")) return (void*)ggml_backend_b200_init;
+    if (!strcmp(name, "ggml_backend_b200_op_supported")) return (void*)ggml_backend_b200_op_supported;
     // names the host probes on every registry: none of them applies to this backend
     //   ggml_backend_set_n_threads, ggml_backend_get_features, ggml_backend_split_buffer_type, ggml_backend_rpc_add_server
     return nullptr;
@@ -577,6 +578,13 @@ void ggml_backend_b200_reset_stats(ggml_backend_t backend) {
 int ggml_backend_b200_set_option(ggml_backend_t backend, const char* key, int value) {
     if (!ggml_backend_is_b200(backend) || !key) return -1;
     return b200_context_set_option((b200_context*)backend->context, key, value);
+}
+
+// the device vtable's supports_op without a device: what every B200 of this backend answers (the answer does not depend on the GPU)
+int ggml_backend_b200_op_supported(const struct ggml_tensor* op) {
+    if (!op) return 0;
+    b200_device_info info{};
+    return b200_supports_op(info, op) ? 1 : 0;
 }
 
 }  // extern "C"

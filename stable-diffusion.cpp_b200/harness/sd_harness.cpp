@@ -720,6 +720,28 @@ int sdh_sample_split(sdh_model* m, const char* method_s, int steps, float cfg_sc
 }  // extern "C"
 
 // build_graph entry points differ per runner; all are public in the reference
+int sdh_model_check_ops(sdh_model* m, const sdh_tensor* x, const sdh_tensor* timesteps, const sdh_tensor* context, const sdh_tensor* y,
+                        sdh_op_supported_fn fn, char* first_unsupported, size_t len) {
+    if (!m || !x || !fn) return fail("null argument");
+    auto xs = to_sd_nd(x, 4);
+    auto ts = to_sd_nd(timesteps, 1);
+    auto cs = to_sd_nd(context, 3);
+    auto ys = to_sd_nd(y, 2);
+    ggml_cgraph* gf = build_only(m, xs, ts, cs, ys);
+    if (!gf) return fail("graph build failed");
+    int bad = 0;
+    for (int i = 0; i < ggml_graph_n_nodes(gf); ++i) {
+        ggml_tensor* nd = ggml_graph_node(gf, i);
+        if (fn(nd)) continue;
+        if (bad == 0 && first_unsupported && len > 0)
+            snprintf(first_unsupported, len, "node %d %s %s [%lld,%lld,%lld,%lld] src0 %s", i, ggml_op_name(nd->op), ggml_type_name(nd->type), (long long)nd->ne[0],
+                     (long long)nd->ne[1], (long long)nd->ne[2], (long long)nd->ne[3], nd->src[0] ? ggml_type_name(nd->src[0]->type) : "-");
+        bad++;
+    }
+    m->last_nodes = ggml_graph_n_nodes(gf);
+    return bad;
+}
+
 static ggml_cgraph* build_only(sdh_model* m, const sd::Tensor<float>& x, const sd::Tensor<float>& t,
                                const sd::Tensor<float>& ctx, const sd::Tensor<float>& y) {
     switch (m->arch) {

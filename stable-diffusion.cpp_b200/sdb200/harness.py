@@ -213,6 +213,18 @@ class Model:
             raise RuntimeError(self.h.last_error())
         return n, self.lib.sdh_model_last_graph_flops(self.ptr)
 
+    def unsupported_nodes(self, plugin_path, x, t=None, ctx=None, y=None):
+        """How many nodes of this model's graph the B200 plugin's supports_op rejects (CPU-only check, no GPU needed)."""
+        lib = C.CDLL(str(plugin_path))
+        fn = C.cast(lib.ggml_backend_b200_op_supported, C.c_void_p)
+        (px, pt, pc, py), keep = self._args(x, t, ctx, y)
+        buf = C.create_string_buffer(256)
+        self.lib.sdh_model_check_ops.restype = C.c_int
+        n = self.lib.sdh_model_check_ops(self.ptr, px, pt, pc, py, fn, buf, C.c_size_t(256))
+        if n < 0:
+            raise RuntimeError(self.h.last_error())
+        return n, buf.value.decode()
+
     def stats(self) -> dict:
         """Counters of the B200 backend instance behind this model (raises for other backends)."""
         v = (C.c_double * 16)()

@@ -3,6 +3,7 @@ import ctypes
 import re
 from pathlib import Path
 
+import numpy as np
 import pytest
 
 REPO = Path(__file__).resolve().parents[1]
@@ -71,3 +72,28 @@ def test_product_path_has_no_cpu_fallback(harness):
     """Asking for a model on a device that does not exist must fail loudly."""
     with pytest.raises(RuntimeError):
         harness.model("B200_99", "unet_tiny", "f16", 0, 1, 1)
+
+
+@pytest.mark.parametrize("arch,wtype,flags,xs,cs,ys", [
+    ("unet_tiny", "f16", 0, (1, 4, 16, 16), (1, 77, 768), None),
+    ("unet_tiny", "f16", 1, (2, 4, 16, 16), (2, 77, 768), None),            # flash-attention graph, batched CFG (N = 2)
+    ("sd15_unet", "f16", 1, (1, 4, 64, 64), (1, 77, 768), None),
+    ("vae_decoder", "f16", 0, (1, 4, 16, 16), None, None),
+    ("flux_tiny", "bf16", 1, (1, 16, 32, 32), (1, 64, 4096), (1, 768)),
+    ("wan_1_3b", "q8_0", 1, (16, 3, 16, 16), (1, 512, 4096), None),
+])
+def test_every_graph_node_is_claimed_by_the_plugin(harness, arch, wtype, flags, xs, cs, ys):
+    """No silent CPU fallback, checked WITHOUT a GPU: build the reference's graph for each model family (on the CPU device, nothing is
+    computed) and ask the plugin's supports_op about every node.  sd.cpp switches a runner to ggml_backend_sched with a CPU fallback
+    backend as soon as one node is refused (src/core/ggml_extend.hpp:2198-2225); the north star forbids that."""
+    from sdb200 import B200_SO
+    from oracle.cpu_ref import load_cpu_oracle
+    load_cpu_oracle(harness)
+    m = harness.model("CPU", arch, wtype, flags, 1234, 2)
+    x = harness.randn(42, xs)
+    t = np.full((xs[0] if arch == "unet_tiny" else 1,), 999.0, np.float32) if cs is not None or arch != "vae_decoder" else None
+    ctx = harness.randn(43, cs) if cs else None
+    y = harness.randn(44, ys) if ys else None
+    bad, first = m.unsupported_nodes(B200_SO, x, t, ctx, y)
+    m.close()
+    assert bad == 0, f"{arch}: {bad} node(s) would fall back to the CPU, first: {first}"
