@@ -296,7 +296,7 @@ def run_b200(args):
     if rank == 0:
         line = dict(metric="denoise_steps_per_s", value=value, unit="steps/s", n_gpus=n, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16", data="synthetic",
-                    config=dict(workload=WORKLOAD, model="SD1.5 UNet (reference UNetModelRunner, synthetic F16 weights, seed 1234)",
+                    config=dict(workload=WORKLOAD, denoiser="SD1.5 UNet graph built by the reference UNetModelRunner, synthetic F16 weights (seed 1234)",
                                 latent="64x64x4", context="77x768", sampler="euler_a eta 1", cfg_scale=CFG_SCALE, forwards_per_step=main["forwards_per_step"], layout=main_layout,
                                 graph="flash-attention variant (--diffusion-fa)", images=images,
                                 parallelism=LAYOUT_TEXT[main_layout] + f"; {images} image(s) in flight on {world} GPU(s)",
