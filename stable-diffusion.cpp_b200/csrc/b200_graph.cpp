@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 // ------------------------------------------------------------------------------------------------
@@ -952,6 +953,9 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
 struct packed_weight { void* ptr; size_t src_bytes; int device; };
 static std::mutex g_pw_mutex;
 static std::unordered_map<const void*, packed_weight> g_packed_weights;
+// bumped whenever a derived weight copy is dropped: captured CUDA graphs hold raw pointers to those copies and must not be replayed
+// across such an event (a long-lived backend whose model was reloaded at the same addresses)
+static std::atomic<uint64_t> g_pw_generation{0};
 
 void b200_invalidate_address_range(int device, const void* ptr, size_t size) {
     std::lock_guard<std::mutex> lock(g_pw_mutex);
@@ -963,6 +967,7 @@ void b200_invalidate_address_range(int device, const void* ptr, size_t size) {
         if (it->second.device == device && a < hi && a + it->second.src_bytes > lo) {
             cudaFree(it->second.ptr);   // implicit device synchronisation: no kernel can still be reading it
             it = g_packed_weights.erase(it);
+            g_pw_generation.fetch_add(1, std::memory_order_relaxed);
         } else {
             ++it;
         }
@@ -1831,7 +1836,7 @@ enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
     enum ggml_status st = GGML_STATUS_SUCCESS;
     uint64_t launches = 0, nodes = 0;
 
-    if (pl && pl->exec && pl->ws_generation == ctx->ws_generation) {
+    if (pl && pl->exec && pl->ws_generation == ctx->ws_generation && pl->pw_generation == g_pw_generation.load(std::memory_order_relaxed)) {
         // ---- replay
         cudaError_t e = cudaGraphLaunch(pl->exec, ctx->stream);
         if (e != cudaSuccess) {
@@ -1842,7 +1847,9 @@ enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
         nodes = pl->nodes;
         ctx->stats.reserved[3]++;   // CUDA-graph replays
     } else if (pl && pl->seen >= 1 && !pl->no_capture && ctx->ws.chunks.size() <= 1) {
-        // ---- second sighting: capture while executing nothing, then launch the instantiated graph
+        // ---- second sighting (or a stale plan: workspace moved / derived weights dropped): capture while executing nothing, then launch
+        //      the instantiated graph
+        if (pl->exec) { cudaGraphExecDestroy(pl->exec); pl->exec = nullptr; }
         ctx->capture_overflow = false;
         ctx->capturing = true;
         cudaGraph_t graph = nullptr;
@@ -1862,6 +1869,7 @@ enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
                 pl->launches = launches;
                 pl->nodes = nodes;
                 pl->ws_generation = ctx->ws_generation;
+                pl->pw_generation = g_pw_generation.load(std::memory_order_relaxed);
                 e = cudaGraphLaunch(exec, ctx->stream);
                 ok = e == cudaSuccess;
             }

@@ -57,7 +57,7 @@ struct b200_context {
     std::vector<cudaEvent_t> kt_free;
     double kt_us = 0, kt_flops = 0;
     // repeated-graph cache (CUDA graph replay)
-    struct plan { cudaGraphExec_t exec = nullptr; int seen = 0; bool no_capture = false; uint64_t launches = 0, nodes = 0, ws_generation = 0; };
+    struct plan { cudaGraphExec_t exec = nullptr; int seen = 0; bool no_capture = false; uint64_t launches = 0, nodes = 0, ws_generation = 0, pw_generation = 0; };
     std::unordered_map<uint64_t, plan> plans;
     uint64_t ws_generation = 0;
     // per-graph-execution cache of packed (type-converted) contraction operands, keyed by ggml tensor node
