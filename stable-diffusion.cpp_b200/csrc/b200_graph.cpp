@@ -1877,7 +1877,7 @@ enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
         if (graph) cudaGraphDestroy(graph);
         if (!ok) {
             cudaGetLastError();
-            pl->no_capture = true;
+            pl->no_capture = !ctx->capture_overflow;     // an overflow is cured by the eager run below (it creates the derived weights): capture next time
             if (pl->exec) { cudaGraphExecDestroy(pl->exec); pl->exec = nullptr; }
             if (st != GGML_STATUS_SUCCESS && !ctx->capture_overflow) return st;
             // fall back to eager execution of this call (also when a node needed a one-time allocation that cannot be captured)
