@@ -49,6 +49,7 @@ b200_context* b200_context_create(const b200_device_info& info) {
     ctx->opt_early_weights = env_flag("GGML_B200_EARLY_WEIGHTS", 0) != 0;   // measured neutral on the SD1.5 step (profiles/r01_summary.md): off by default
     ctx->opt_chain_fusion = env_flag("GGML_B200_CHAIN_FUSION", 1) != 0;
     ctx->opt_gemv = env_flag("GGML_B200_GEMV", 1) != 0;
+    ctx->opt_persistent_gemm = env_flag("GGML_B200_PERSISTENT", 0) != 0;   // experimental persistent GEMM (gemm_tc_persist.cu), never run on hardware yet
     ctx->opt_fold_batch = env_flag("GGML_B200_FOLD_BATCH", 0) != 0;   // written at the end of round 1, not yet measured: off by default
     return ctx;
 }
@@ -82,6 +83,7 @@ int b200_context_set_option(b200_context* ctx, const char* key, int value) {
     else if (!strcmp(key, "chain_fusion")) ctx->opt_chain_fusion = value != 0;
     else if (!strcmp(key, "gemv")) ctx->opt_gemv = value != 0;
     else if (!strcmp(key, "fold_batch")) ctx->opt_fold_batch = value != 0;
+    else if (!strcmp(key, "persistent_gemm")) ctx->opt_persistent_gemm = value != 0;
     else return -1;
     return 0;
 }
@@ -249,7 +251,9 @@ static int launch_tc(b200_context* ctx, const b200_gemm_args& g) {
         e1 = kt_event(ctx);
         cudaEventRecord(e0, ctx->stream);
     }
-    int n = b200_launch_gemm_tc(ctx->stream, ctx->info, g, w, w ? wsb : 0);
+    int n = -1;
+    if (ctx->opt_persistent_gemm) n = b200_launch_gemm_tc_persistent(ctx->stream, ctx->info, g);   // experimental, off by default
+    if (n < 0) n = b200_launch_gemm_tc(ctx->stream, ctx->info, g, w, w ? wsb : 0);
     if (ctx->opt_kernel_timing) {
         if (n > 0) {
             cudaEventRecord(e1, ctx->stream);

@@ -50,6 +50,7 @@ struct b200_context {
     bool opt_chain_fusion = true;     // GEGLU tail, Q read in place by attention, f16 operand copies written by their producers
     bool opt_gemv = true;             // MUL_MAT with <= 4 activation rows as a weight-streaming GEMV instead of a tcgen05 tile
     bool opt_fold_batch = false;      // MUL_MAT of one weight matrix against a contiguous batch of activations runs as one GEMM with N * batch rows
+    bool opt_persistent_gemm = false; // EXPERIMENTAL persistent GEMM with double-buffered TMEM accumulators (not validated on hardware)
     bool opt_kernel_timing = false;   // per-launch CUDA events around every tcgen05 GEMM (roofline pass only)
     bool timing_pending = false;
     struct kt_pair { cudaEvent_t start, stop; double flops; };

@@ -79,6 +79,8 @@ struct b200_gemm_args {
 // returns kernels launched, or -1 if the shape/alignment is not supported by the TMA path (caller falls back)
 int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g, void* workspace, size_t workspace_bytes);
 size_t b200_gemm_tc_workspace_bytes(const b200_device_info& dev, const b200_gemm_args& g);
+// EXPERIMENTAL persistent variant (gemm_tc_persist.cu; option "persistent_gemm", off by default): 1 when launched, -1 when not applicable
+int b200_launch_gemm_tc_persistent(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g);
 
 // Q8_0 blocks (34 bytes: f16 scale + 32 int8, ggml-common.h:251-255) -> f16 rows [rows][K] (K % 32 == 0): the derived weight layout the
 // tensor-core GEMM reads; value = round_f16(float(d) * q), the reference's own dequantisation (ggml-quants.c dequantize_row_q8_0)
