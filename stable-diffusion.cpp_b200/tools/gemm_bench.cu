@@ -26,7 +26,17 @@ int main(int argc, char** argv) {
     for (auto& s : shapes) { maxA = std::max(maxA, (size_t)s.M * s.K); maxB = std::max(maxB, (size_t)s.N * s.K); maxD = std::max(maxD, (size_t)s.M * s.N); }
     __half *A, *B; float *D, *bias;
     cudaMalloc(&A, maxA * 2); cudaMalloc(&B, maxB * 2); cudaMalloc(&D, maxD * 4); cudaMalloc(&bias, 1 << 20);
-    cudaMemset(A, 0, maxA * 2); cudaMemset(B, 0, maxB * 2); cudaMemset(bias, 0, 1 << 20);
+    {   // deterministic non-trivial operands (a mismatch count against all-zero data would prove nothing)
+        std::vector<__half> h(std::max(maxA, maxB));
+        uint32_t x = 12345u;
+        for (auto& v : h) { x = x * 1664525u + 1013904223u; v = __float2half(((int)(x >> 20) % 17 - 8) / 64.0f); }
+        cudaMemcpy(A, h.data(), maxA * 2, cudaMemcpyHostToDevice);
+        for (auto& v : h) { x = x * 1664525u + 1013904223u; v = __float2half(((int)(x >> 20) % 13 - 6) / 32.0f); }
+        cudaMemcpy(B, h.data(), maxB * 2, cudaMemcpyHostToDevice);
+        std::vector<float> hb(1 << 18);
+        for (auto& v : hb) { x = x * 1664525u + 1013904223u; v = ((int)(x >> 20) % 9 - 4) / 8.0f; }
+        cudaMemcpy(bias, hb.data(), 1 << 20, cudaMemcpyHostToDevice);
+    }
     unsigned long long* trace; cudaMalloc(&trace, 64);
     cudaStream_t st; cudaStreamCreate(&st);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -44,6 +54,27 @@ int main(int argc, char** argv) {
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         double us = ms * 1e3 / reps;
         printf("%-34s %8lld %8lld %8lld | %9.2f %9.1f", s.name, (long long)s.M, (long long)s.N, (long long)s.K, us, 2.0 * s.M * s.N * s.K / us * 1e-6);
+        // experimental persistent variant (gemm_tc_persist.cu) on the same problem, with a checksum comparison against the regular kernel
+        if (getenv("GEMM_BENCH_PERSISTENT")) {
+            std::vector<float> ref((size_t)s.M * s.N), got((size_t)s.M * s.N);
+            cudaMemcpy(ref.data(), D, ref.size() * 4, cudaMemcpyDeviceToHost);
+            cudaMemsetAsync(D, 0xff, ref.size() * 4, st);
+            int ok = b200_launch_gemm_tc_persistent(st, dev, g);
+            if (ok > 0) {
+                cudaStreamSynchronize(st);
+                cudaMemcpy(got.data(), D, got.size() * 4, cudaMemcpyDeviceToHost);
+                size_t bad = 0;
+                for (size_t i = 0; i < ref.size(); ++i) bad += ref[i] != got[i];
+                cudaEventRecord(e0, st);
+                for (int i = 0; i < reps; ++i) b200_launch_gemm_tc_persistent(st, dev, g);
+                cudaEventRecord(e1, st);
+                cudaEventSynchronize(e1);
+                cudaEventElapsedTime(&ms, e0, e1);
+                printf(" | persistent %8.2f us, %zu mismatching elements", ms * 1e3 / reps, bad);
+            } else {
+                printf(" | persistent n/a");
+            }
+        }
         // phase timestamps of CTA (0,0,0): start, setup done, first k-block landed, last k-block landed, accumulator ready, epilogue done, all warps joined, tmem freed
         cudaMemset(trace, 0, 64);
         g.trace = trace;
