@@ -91,6 +91,11 @@ int sdh_sample(sdh_model* m, const char* method, int steps, float cfg_scale, flo
                sdh_tensor* out, float* sigmas_out, float* timesteps_out, int* n_forwards,
                double* wall_ms);
 
+/* The reference's VAE::decode entry (src/model/vae/vae.hpp:171-221) on a vae_decoder model: tile_size > 0 enables its host-side tiling
+ * (latent tiles of tile_size x tile_size with `overlap` in [0, 0.5], one graph_compute per tile, feathered merge on the host;
+ * SURVEY.md 8a row a16), tile_size <= 0 decodes in one piece.  out: [8W, 8H, 3, N] scaled to [0, 1] like the reference. */
+int sdh_vae_decode(sdh_model* m, const sdh_tensor* z, int tile_size, float overlap, sdh_tensor* out, double* wall_ms);
+
 /* Builds the model's graph for these inputs (nothing is computed) and asks `fn` -- e.g. ggml_backend_b200_op_supported of the plugin -- about
  * every node: returns how many nodes `fn` rejects (0 = the whole graph runs on that backend, no ggml_backend_sched CPU fallback), or < 0
  * on error; the first rejected node is described in `first_unsupported`. */

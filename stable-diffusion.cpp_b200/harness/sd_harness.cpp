@@ -520,6 +520,26 @@ int sdh_model_forward(sdh_model* m, const sdh_tensor* x, const sdh_tensor* times
 static ggml_cgraph* build_only(sdh_model* m, const sd::Tensor<float>& x, const sd::Tensor<float>& t,
                                const sd::Tensor<float>& ctx, const sd::Tensor<float>& y);
 
+// VAE::decode of the reference (src/model/vae/vae.hpp:171-221) as the txt2img path calls it: with tile_size > 0 the latent is split into
+// overlapping tiles on the HOST (sd_tiling, ggml_extend.hpp:691-951), each tile is decoded by one graph_compute on the backend, and the
+// tiles are feather-blended on the host; tile_size <= 0 decodes in one piece.  The output is the reference's [0,1]-scaled image.
+int sdh_vae_decode(sdh_model* m, const sdh_tensor* z, int tile_size, float overlap, sdh_tensor* out, double* wall_ms) {
+    if (!m || !z || !out || m->arch != ARCH_VAE) return fail("sdh_vae_decode needs a vae_decoder model");
+    auto zs = to_sd_nd(z, 4);
+    sd_tiling_params_t tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.enabled        = tile_size > 0;
+    tp.tile_size_x    = tile_size;
+    tp.tile_size_y    = tile_size;
+    tp.target_overlap = overlap;
+    auto t0 = std::chrono::steady_clock::now();
+    sd::Tensor<float> r = m->vae->decode(m->n_threads, zs, tp, false, false, false, true);
+    auto t1 = std::chrono::steady_clock::now();
+    if (wall_ms) *wall_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (r.empty()) return fail("vae decode failed");
+    return from_sd(r, out);
+}
+
 int sdh_model_dump_graph(sdh_model* m, const sdh_tensor* x, const sdh_tensor* timesteps, const sdh_tensor* context,
                          const sdh_tensor* y, const char* path) {
     if (!m || !x) return fail("null argument");

@@ -213,6 +213,21 @@ class Model:
             raise RuntimeError(self.h.last_error())
         return n, self.lib.sdh_model_last_graph_flops(self.ptr)
 
+    def vae_decode(self, z, tile_size: int = 0, overlap: float = 0.5):
+        """Reference VAE::decode (optionally with its host-side tiling) -> (image [N,3,8H,8W] in [0,1], wall_ms)."""
+        sz, keep = _as_sdh(z)
+        ne = (C.c_int64 * 4)()
+        self.lib.sdh_model_out_shape(self.ptr, C.byref(sz), ne)
+        out = np.empty(tuple(ne)[::-1], np.float32)
+        so, _ = _as_sdh(out)
+        so.data = out.ctypes.data_as(C.POINTER(C.c_float))
+        ms = C.c_double(0)
+        self.lib.sdh_vae_decode.restype = C.c_int
+        rc = self.lib.sdh_vae_decode(self.ptr, C.byref(sz), C.c_int(tile_size), C.c_float(overlap), C.byref(so), C.byref(ms))
+        if rc != 0:
+            raise RuntimeError("vae_decode failed: " + self.h.last_error())
+        return out, ms.value
+
     def unsupported_nodes(self, plugin_path, x, t=None, ctx=None, y=None):
         """How many nodes of this model's graph the B200 plugin's supports_op rejects (CPU-only check, no GPU needed)."""
         lib = C.CDLL(str(plugin_path))

@@ -171,3 +171,22 @@ def test_committed_dit_fixtures_match_live_cpu_backend(cpu_oracle):
         m.close()
         r = float(np.linalg.norm(out.astype(np.float64) - gold[key]) / np.linalg.norm(gold[key].astype(np.float64)))
         assert r < 1e-3, f"{key}: {r:.2e}"
+
+
+def test_reference_tiled_vae_decode_host_path(cpu_oracle):
+    """SURVEY.md 8a row a16: the reference's VAE::decode with its host-side tiling (vae.hpp:171-221, ggml_extend.hpp:691-951) runs through
+    the harness on any backend.  Untiled it is the plain forward scaled to [0, 1]; tiled it decodes overlapping 8x8 latent tiles (one
+    graph_compute each) and feather-blends them on the host -- deterministic, finite, and different from the untiled result because
+    GroupNorm statistics become per tile."""
+    h = cpu_oracle
+    m = h.model("CPU", "vae_decoder", "f16", 0, 1234, 4)
+    z = h.randn(45, (1, 4, 16, 16))
+    fwd, _ = m.forward(z)
+    plain, _ = m.vae_decode(z, 0)
+    tiled, _ = m.vae_decode(z, 8, 0.5)
+    tiled2, _ = m.vae_decode(z, 8, 0.5)
+    m.close()
+    assert plain.shape == (1, 3, 128, 128) and tiled.shape == plain.shape
+    assert np.allclose(plain, np.clip((fwd + 1) / 2, 0, 1), atol=1e-6)
+    assert np.isfinite(tiled).all() and tiled.min() >= 0 and tiled.max() <= 1 and np.array_equal(tiled, tiled2)
+    assert 1e-3 < np.linalg.norm(tiled - plain) / np.linalg.norm(plain) < 0.6
