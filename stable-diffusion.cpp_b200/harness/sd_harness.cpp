@@ -29,6 +29,7 @@
 #include "model/diffusion/flux.hpp"
 #include "model/diffusion/mmdit.hpp"
 #include "model/diffusion/wan.hpp"
+#include "model/te/clip.hpp"
 #include "model/diffusion/unet.hpp"
 #include "model/vae/auto_encoder_kl.hpp"
 #include "runtime/denoiser.hpp"
@@ -188,7 +189,7 @@ struct SyntheticWeights : public RunnerWeightManager {
     }
 };
 
-enum Arch { ARCH_UNET, ARCH_VAE, ARCH_FLUX, ARCH_MMDIT, ARCH_WAN };
+enum Arch { ARCH_UNET, ARCH_VAE, ARCH_FLUX, ARCH_MMDIT, ARCH_WAN, ARCH_CLIP };
 
 ggml_type parse_wtype(const char* w) {
     std::string s = w ? w : "f32";
@@ -230,6 +231,7 @@ struct sdh_model {
     std::unique_ptr<Flux::FluxRunner> flux;
     std::unique_ptr<MMDiTRunner> mmdit;
     std::unique_ptr<WAN::WanRunner> wan;
+    std::unique_ptr<CLIPTextModelRunner> clip;
     SDVersion version = VERSION_SD1;
     int n_threads     = 1;
     double last_flops = 0;
@@ -447,6 +449,21 @@ sdh_model* sdh_model_create(const char* device, const char* arch, const char* wt
         m->wan = std::make_unique<WAN::WanRunner>(m->backend, smap, prefix, m->version, m->weights);
         m->wan->get_param_tensors(tensors, prefix);
         m->wan->set_flash_attention_enabled(fa);
+    } else if (a == "clip_l") {
+        // the CLIP ViT-L/14 text encoder of SD1.x / SDXL (src/model/te/clip.hpp), the stage right before the hot path
+        m->arch    = ARCH_CLIP;
+        m->version = VERSION_SD1;
+        const std::string prefix = "cond_stage_model.transformer.text_model";
+        String2TensorStorage smap;
+        {
+            CLIPTextModelRunner probe(m->backend, {}, prefix, OPENAI_CLIP_VIT_L_14, true, false, m->weights);
+            std::map<std::string, ggml_tensor*> pt;
+            probe.get_param_tensors(pt, prefix);
+            smap = make_storage_map(pt, wtype);
+        }
+        m->clip = std::make_unique<CLIPTextModelRunner>(m->backend, smap, prefix, OPENAI_CLIP_VIT_L_14, true, false, m->weights);
+        m->clip->get_param_tensors(tensors, prefix);
+        m->clip->set_flash_attention_enabled(fa);
     } else {
         fail("unknown arch: " + a);
         return nullptr;
@@ -465,6 +482,7 @@ void sdh_model_free(sdh_model* m) {
     m->flux.reset();
     m->mmdit.reset();
     m->wan.reset();
+    m->clip.reset();
     m->weights.reset();
     if (m->backend) ggml_backend_free(m->backend);
     delete m;
@@ -476,6 +494,9 @@ int sdh_model_param_count(const sdh_model* m) { return m->weights ? m->weights->
 int sdh_model_out_shape(sdh_model* m, const sdh_tensor* x, int64_t out_ne[4]) {
     if (!m || !x) return fail("null argument");
     for (int i = 0; i < 4; ++i) out_ne[i] = x->ne[i];
+    if (m->arch == ARCH_CLIP) {      // ids [n_token, N] -> hidden states [768, n_token, N]
+        out_ne[0] = 768; out_ne[1] = x->ne[0]; out_ne[2] = x->ne[1]; out_ne[3] = 1;
+    }
     if (m->arch == ARCH_VAE) {
         out_ne[0] = x->ne[0] * 8;
         out_ne[1] = x->ne[1] * 8;
@@ -484,9 +505,17 @@ int sdh_model_out_shape(sdh_model* m, const sdh_tensor* x, int64_t out_ne[4]) {
     return 0;
 }
 
+// text-encoder input: token ids arrive as floats in x ([n_token, N, 1, 1]); CLIP wants int32 [n_token, N]
+static sd::Tensor<int32_t> token_ids(const sd::Tensor<float>& x) {
+    std::vector<int32_t> ids(x.values().begin(), x.values().end());
+    return sd::Tensor<int32_t>({x.shape()[0], x.shape()[1]}, std::move(ids));
+}
+
 static sd::Tensor<float> run_model(sdh_model* m, const sd::Tensor<float>& x, const sd::Tensor<float>& t,
                                    const sd::Tensor<float>& ctx, const sd::Tensor<float>& y) {
     switch (m->arch) {
+        case ARCH_CLIP:
+            return m->clip->compute(m->n_threads, token_ids(x), 0, nullptr, 0, false, -1, false, false, false);
         case ARCH_UNET:
             return m->unet->compute(m->n_threads, x, t, ctx, {}, y);
         case ARCH_VAE:
@@ -780,6 +809,9 @@ static ggml_cgraph* build_only(sdh_model* m, const sd::Tensor<float>& x, const s
         case ARCH_WAN:
             m->wan->reset_compute_ctx();
             return m->wan->build_graph(x, t, ctx);
+        case ARCH_CLIP:
+            m->clip->reset_compute_ctx();
+            return m->clip->build_graph(token_ids(x));
     }
     return nullptr;
 }

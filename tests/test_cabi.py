@@ -97,3 +97,21 @@ def test_every_graph_node_is_claimed_by_the_plugin(harness, arch, wtype, flags, 
     bad, first = m.unsupported_nodes(B200_SO, x, t, ctx, y)
     m.close()
     assert bad == 0, f"{arch}: {bad} node(s) would fall back to the CPU, first: {first}"
+
+
+def test_clip_text_encoder_graph_is_claimed_by_the_plugin(harness):
+    """SURVEY.md 8f-2 (the stage right before the hot path): the CLIP ViT-L/14 text encoder graph of the reference (GET_ROWS embedding lookup,
+    LayerNorm, causal-mask attention, quick-GELU MLP) consists only of ops the plugin executes -- a GPU-resident txt2img needs no CPU
+    fallback for it either."""
+    from sdb200 import B200_SO
+    from oracle.cpu_ref import load_cpu_oracle
+    load_cpu_oracle(harness)
+    m = harness.model("CPU", "clip_l", "f16", 0, 1234, 2)
+    ids = np.full((1, 1, 1, 77), 49407, np.float32)
+    ids[0, 0, 0, 0] = 49406
+    ids[0, 0, 0, 1:9] = [320, 1125, 539, 2368, 525, 1929, 267, 1662]
+    out, _ = m.forward(ids)
+    bad, first = m.unsupported_nodes(B200_SO, ids)
+    m.close()
+    assert out.shape[-2:] == (77, 768) and np.isfinite(out).all()
+    assert bad == 0, f"{bad} node(s) would fall back to the CPU, first: {first}"
