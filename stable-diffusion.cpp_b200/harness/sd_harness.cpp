@@ -32,6 +32,7 @@
 #include "model/te/clip.hpp"
 #include "model/diffusion/unet.hpp"
 #include "model/vae/auto_encoder_kl.hpp"
+#include "model/vae/wan_vae.hpp"
 #include "runtime/denoiser.hpp"
 #include "runtime/guidance.h"
 #include "core/rng_philox.hpp"
@@ -189,7 +190,7 @@ struct SyntheticWeights : public RunnerWeightManager {
     }
 };
 
-enum Arch { ARCH_UNET, ARCH_VAE, ARCH_FLUX, ARCH_MMDIT, ARCH_WAN, ARCH_CLIP };
+enum Arch { ARCH_UNET, ARCH_VAE, ARCH_FLUX, ARCH_MMDIT, ARCH_WAN, ARCH_CLIP, ARCH_WANVAE };
 
 ggml_type parse_wtype(const char* w) {
     std::string s = w ? w : "f32";
@@ -232,6 +233,7 @@ struct sdh_model {
     std::unique_ptr<MMDiTRunner> mmdit;
     std::unique_ptr<WAN::WanRunner> wan;
     std::unique_ptr<CLIPTextModelRunner> clip;
+    std::unique_ptr<WAN::WanVAERunner> wan_vae;
     SDVersion version = VERSION_SD1;
     int n_threads     = 1;
     double last_flops = 0;
@@ -449,6 +451,20 @@ sdh_model* sdh_model_create(const char* device, const char* arch, const char* wt
         m->wan = std::make_unique<WAN::WanRunner>(m->backend, smap, prefix, m->version, m->weights);
         m->wan->get_param_tensors(tensors, prefix);
         m->wan->set_flash_attention_enabled(fa);
+    } else if (a == "wan_vae_decoder") {
+        // Wan2.1 VAE decoder (causal 3-D convolutions, src/model/vae/wan_vae.hpp): latent [W, H, T, 16] -> video [8W, 8H, 4(T-1)+1, 3]
+        m->arch    = ARCH_WANVAE;
+        m->version = VERSION_WAN2;
+        const std::string prefix = "first_stage_model";
+        String2TensorStorage smap;
+        {
+            WAN::WanVAERunner probe(m->backend, {}, prefix, true, m->version, m->weights);
+            std::map<std::string, ggml_tensor*> pt;
+            probe.get_param_tensors(pt);
+            smap = make_storage_map(pt, wtype);
+        }
+        m->wan_vae = std::make_unique<WAN::WanVAERunner>(m->backend, smap, prefix, true, m->version, m->weights);
+        m->wan_vae->get_param_tensors(tensors);
     } else if (a == "clip_l") {
         // the CLIP ViT-L/14 text encoder of SD1.x / SDXL (src/model/te/clip.hpp), the stage right before the hot path
         m->arch    = ARCH_CLIP;
@@ -483,6 +499,7 @@ void sdh_model_free(sdh_model* m) {
     m->mmdit.reset();
     m->wan.reset();
     m->clip.reset();
+    m->wan_vae.reset();
     m->weights.reset();
     if (m->backend) ggml_backend_free(m->backend);
     delete m;
@@ -496,6 +513,9 @@ int sdh_model_out_shape(sdh_model* m, const sdh_tensor* x, int64_t out_ne[4]) {
     for (int i = 0; i < 4; ++i) out_ne[i] = x->ne[i];
     if (m->arch == ARCH_CLIP) {      // ids [n_token, N] -> hidden states [768, n_token, N]
         out_ne[0] = 768; out_ne[1] = x->ne[0]; out_ne[2] = x->ne[1]; out_ne[3] = 1;
+    }
+    if (m->arch == ARCH_WANVAE) {
+        out_ne[0] = x->ne[0] * 8; out_ne[1] = x->ne[1] * 8; out_ne[2] = (x->ne[2] - 1) * 4 + 1; out_ne[3] = 3;
     }
     if (m->arch == ARCH_VAE) {
         out_ne[0] = x->ne[0] * 8;
@@ -516,6 +536,16 @@ static sd::Tensor<float> run_model(sdh_model* m, const sd::Tensor<float>& x, con
     switch (m->arch) {
         case ARCH_CLIP:
             return m->clip->compute(m->n_threads, token_ids(x), 0, nullptr, 0, false, -1, false, false, false);
+        case ARCH_WANVAE: {
+            // a 4-D tensor would be taken for an image [W,H,C,N] (wan_vae.hpp:1384-1388): video latents go in as [W,H,T,C,1]
+            std::vector<int64_t> shape5 = x.shape();
+            shape5.push_back(1);
+            sd::Tensor<float> x5(shape5, std::vector<float>(x.values()));
+            sd::Tensor<float> r = m->wan_vae->_compute(m->n_threads, x5, true);
+            if (r.empty()) return r;
+            std::vector<int64_t> s4(r.shape().begin(), r.shape().begin() + 4);
+            return sd::Tensor<float>(s4, std::vector<float>(r.values()));
+        }
         case ARCH_UNET:
             return m->unet->compute(m->n_threads, x, t, ctx, {}, y);
         case ARCH_VAE:
@@ -812,6 +842,9 @@ static ggml_cgraph* build_only(sdh_model* m, const sd::Tensor<float>& x, const s
         case ARCH_CLIP:
             m->clip->reset_compute_ctx();
             return m->clip->build_graph(token_ids(x));
+        case ARCH_WANVAE:
+            m->wan_vae->reset_compute_ctx();
+            return m->wan_vae->build_graph(x, true);
     }
     return nullptr;
 }

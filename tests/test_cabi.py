@@ -83,6 +83,7 @@ def test_product_path_has_no_cpu_fallback(harness):
     ("wan_1_3b", "q8_0", 1, (16, 3, 16, 16), (1, 512, 4096), None),
     ("sdxl_unet", "bf16", 1, (1, 4, 32, 32), (1, 77, 2048), (1, 2816)),
     ("mmdit_sd3", "f16", 1, (1, 16, 32, 32), (1, 154, 4096), (1, 2048)),
+    ("wan_vae_decoder", "f16", 0, (16, 2, 8, 8), None, None),                # causal 3-D conv decoder: IM2COL_3D, PAD, RMS_NORM, CONCAT caches
 ])
 def test_every_graph_node_is_claimed_by_the_plugin(harness, arch, wtype, flags, xs, cs, ys):
     """No silent CPU fallback, checked WITHOUT a GPU: build the reference's graph for each model family (on the CPU device, nothing is
