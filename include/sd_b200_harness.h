@@ -43,8 +43,8 @@ const char* sdh_last_error(void);
 
 /* arch:    "sd15_unet" | "sdxl_unet" | "unet_tiny" | "vae_decoder" | "vae_decoder_sdxl" | "flux_schnell" | "flux_tiny" |
  *          "mmdit_sd3" (SD3-medium MMDiT) | "wan_1_3b" (Wan2.1-T2V-1.3B DiT) | "clip_l" (CLIP ViT-L/14 text encoder: x = token ids as
- *          floats [n_token, N]) | "wan_vae_decoder" (Wan causal 3-D VAE decoder: x = latent [W, H, T, 16]; graph-building / op-coverage
- *          use -- the untuned synthetic weights overflow f16 in a full forward)
+ *          floats [n_token, N]) | "wan_vae_decoder" (Wan causal 3-D VAE decoder: x = latent [W, H, T, 16]; with T > 1 the reference's
+ *          single-graph decode returns NaN from the second frame on, on its own CPU backend too, so parity is pinned on one frame)
  * wtype:   "f32" | "f16" | "bf16" | "q8_0"  (dtype of Linear weights; conv weights are always F16 as
  *           in the reference, ggml_extend.hpp:3600-3603; norm/bias are F32)
  * flags:   bit0 = flash attention graph variant (--diffusion-fa), bit1 = conv2d direct

@@ -157,7 +157,7 @@ struct SyntheticWeights : public RunnerWeightManager {
                 // norm scales ~ 1 +- 0.1 ; biases (and other vectors) ~ +-0.05
                 bool is_scale = !is_bias && (name.find("norm") != std::string::npos || name.find("scale") != std::string::npos ||
                                              name.find("ln_") != std::string::npos || name.find(".0.weight") != std::string::npos ||
-                                             name.find("weight") != std::string::npos);
+                                             name.find("weight") != std::string::npos || name.find("gamma") != std::string::npos);
                 if (is_scale) fill_uniform(tmp.data(), n, s, 1.0f, 0.1f);
                 else fill_uniform(tmp.data(), n, s, 0.0f, 0.05f);
             } else {

@@ -10,6 +10,7 @@
   cpu_ops.npz              seeded inputs and the reference CPU backend's outputs (oracle/_ref) for each hot-path op
   cpu_models.npz           reference CPU backend outputs of whole synthetic-weight models (unet_tiny fa/non-fa,
                            vae_decoder on an 8x8 latent, scheduler-driven 3-step sample)
+  cpu_wan_vae.npz          (`make_golden.py wan_vae`) Wan causal-3D VAE decoder, one latent frame
   cpu_models_dit.npz       (`make_golden.py dit`) the same for the larger architectures of SURVEY.md 8a: SD1.5 UNet 64x64 (default graph),
                            SDXL UNet 32x32, flux_tiny (bf16), SD3-medium MMDiT 32x32 (f16), Wan2.1-1.3B DiT (q8_0, 3x16x16 latent)
 """
@@ -134,8 +135,26 @@ def main_dit():
     print("written with CPU variant", variant)
 
 
+def main_wan_vae():
+    """cpu_wan_vae.npz: Wan causal-3D VAE decoder, ONE latent frame [16, 1, 8, 8] -> [3, 1, 64, 64] (with more frames the reference's
+    single-graph decode path yields NaN from the second frame on, on its own CPU backend -- wan_vae.hpp:1381 calls its chunked twin
+    "weird" too -- so only the first frame can be pinned)."""
+    from sdb200 import Harness
+    from oracle.cpu_ref import load_cpu_oracle
+    h = Harness()
+    load_cpu_oracle(h)
+    m = h.model("CPU", "wan_vae_decoder", "f16", 0, 1234, 8)
+    out, _ = m.forward(h.randn(45, (16, 1, 8, 8)))
+    m.close()
+    assert np.isfinite(out).all()
+    np.savez_compressed(HERE / "cpu_wan_vae.npz", wan_vae_1frame=out)
+    print("wan_vae_1frame", out.shape, float(out.std()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "dit":
         main_dit()
+    elif len(sys.argv) > 1 and sys.argv[1] == "wan_vae":
+        main_wan_vae()
     else:
         main()

@@ -256,3 +256,15 @@ def test_clip_text_encoder_vs_live_cpu(b200):
         m.close()
     assert np.isfinite(outs[dev]).all()
     assert rel(outs[dev], outs["CPU"]) < 3e-3, f"rel_l2 {rel(outs[dev], outs['CPU']):.2e}"
+
+
+@pytest.mark.skipif(os.environ.get("SDB200_UNVALIDATED") != "1", reason="written after the round-1 GPU budget was spent: enable once it has run on a B200")
+def test_wan_vae_decoder_vs_committed_cpu_fixture(b200):
+    """SURVEY.md 8a row a17 (VAE half): Wan causal-3D VAE decoder, one latent frame, against the committed CPU output."""
+    h, dev = b200
+    gold = np.load(GOLD / "cpu_wan_vae.npz")["wan_vae_1frame"]
+    m = h.model(dev, "wan_vae_decoder", "f16", 0, 1234, 0)
+    out, _ = m.forward(h.randn(45, (16, 1, 8, 8)))
+    m.close()
+    assert out.shape == gold.shape and np.isfinite(out).all()
+    assert rel(out, gold) < 3e-3, f"rel_l2 {rel(out, gold):.2e}"

@@ -190,3 +190,15 @@ def test_reference_tiled_vae_decode_host_path(cpu_oracle):
     assert np.allclose(plain, np.clip((fwd + 1) / 2, 0, 1), atol=1e-6)
     assert np.isfinite(tiled).all() and tiled.min() >= 0 and tiled.max() <= 1 and np.array_equal(tiled, tiled2)
     assert 1e-3 < np.linalg.norm(tiled - plain) / np.linalg.norm(plain) < 0.6
+
+
+def test_wan_vae_fixture_matches_live_cpu_backend(cpu_oracle):
+    """Wan causal-3D VAE decoder (IM2COL_3D convolutions, RMS norms, feature-cache CONCATs), one latent frame: the committed fixture is
+    the reference CPU backend's output."""
+    h = cpu_oracle
+    gold = np.load(GOLD / "cpu_wan_vae.npz")["wan_vae_1frame"]
+    m = h.model("CPU", "wan_vae_decoder", "f16", 0, 1234, 4)
+    out, _ = m.forward(h.randn(45, (16, 1, 8, 8)))
+    m.close()
+    r = float(np.linalg.norm(out.astype(np.float64) - gold) / np.linalg.norm(gold.astype(np.float64)))
+    assert out.shape == gold.shape and r < 1e-3, f"{r:.2e}"
