@@ -73,9 +73,15 @@ typedef struct ggml_b200_stats {
     uint64_t reserved[8];       /* [0] flop of the tcgen05 GEMMs timed under "kernel_timing", [1] their device time in us,
                                    [2] fused flash-attention launches, [3] CUDA-graph replays, [4] implicit-GEMM convolutions,
                                    [5] attention launches that read Q in place (CONT skipped), [6] few-row GEMV launches, [7] fused RoPE launches */
+    uint64_t ext[16];           /* [0] CUDA-core reference GEMM launches (gemm_ref.cu: must stay 0 on every model path; the parity tests assert it),
+                                   [1] host microseconds spent inside graph_compute (signature, fusion planning, launches / cudaGraphLaunch),
+                                   [2] graphs that wrote into a WEIGHTS buffer (derived weight copies dropped), [3] conv filters packed per graph
+                                   (filter computed inside the graph: no persistent copy), [4] persistent-GEMM launches, [5] 2-CTA GEMM launches,
+                                   [6] bytes of derived weight copies alive, [7] unfused (GEMM + softmax + GEMM) attention executions */
 } ggml_b200_stats;
 
-/* copy the backend instance's counters; returns 0 on success */
+/* copy the backend instance's counters; returns 0 on success.  Counters of kernels that run inside a replayed CUDA graph are
+ * accounted at every replay from the deltas recorded when the graph was captured, so they stay alive on the measured path. */
 int ggml_backend_b200_get_stats(ggml_backend_t backend, ggml_b200_stats* out);
 void ggml_backend_b200_reset_stats(ggml_backend_t backend);
 

@@ -41,7 +41,8 @@ const char* sdh_device_name(int index);
 
 const char* sdh_last_error(void);
 
-/* arch:    "sd15_unet" | "sdxl_unet" | "unet_tiny" | "vae_decoder" | "vae_decoder_sdxl" | "flux_schnell" | "flux_tiny" |
+/* arch:    "sd15_unet" | "sdxl_unet" | "unet_tiny" | "vae_decoder" | "vae_decoder_sdxl" | "flux_schnell" | "flux_tiny" | "flux_1x1" (one double + one
+ *          single block at full FLUX.1 width) |
  *          "mmdit_sd3" (SD3-medium MMDiT) | "wan_1_3b" (Wan2.1-T2V-1.3B DiT) | "clip_l" (CLIP ViT-L/14 text encoder: x = token ids as
  *          floats [n_token, N]) | "wan_vae_decoder" (Wan causal 3-D VAE decoder: x = latent [W, H, T, 16]; with T > 1 the reference's
  *          single-graph decode returns NaN from the second frame on, on its own CPU backend too, so parity is pinned on one frame)
@@ -75,6 +76,18 @@ int sdh_model_forward(sdh_model* m, const sdh_tensor* x, const sdh_tensor* times
  * Returns the node count.  Used to derive supports_op coverage and the algorithmic FLOP count. */
 int sdh_model_dump_graph(sdh_model* m, const sdh_tensor* x, const sdh_tensor* timesteps,
                          const sdh_tensor* context, const sdh_tensor* y, const char* path);
+
+/* Export the graph the reference builds for these inputs (no compute) for a host-side interpreter: <prefix>.json holds one record per
+ * tensor (op, type, ne, nb, op_params, source ids, view root + byte offset) plus the node order; <prefix>.bin holds the data of every
+ * leaf as float32 (weights read back from the backend buffer: F16 / BF16 / Q8_0 values are exact in f32; inputs from the host copies
+ * the runner is about to upload).  oracle/graph_f64.py evaluates it in float64 -- the arbiter of the whole-model parity tests.
+ * Returns the node count. */
+int sdh_model_export_graph(sdh_model* m, const sdh_tensor* x, const sdh_tensor* timesteps,
+                           const sdh_tensor* context, const sdh_tensor* y, const char* path_prefix);
+
+/* w += value for the first parameter whose name contains `name_substr` and has `n_dims` dimensions, computed as a GRAPH on the model's
+ * backend (ggml_add_inplace into the resident weight: the reference's LoRA apply, src/lora.hpp:934-937).  Returns the element count. */
+int sdh_model_add_to_weight(sdh_model* m, const char* name_substr, int n_dims, float value);
 
 /* Algorithmic FLOPs of the last graph built (sum over MUL_MAT / FLASH_ATTN_EXT / CONV_2D nodes,
  * SURVEY.md 8d), and its node counts. */
@@ -121,7 +134,7 @@ int sdh_sample_split(sdh_model* m, const char* method, int steps, float cfg_scal
 
 /* Counters of the model's backend instance when it is a B200 backend (include/ggml-b200.h ggml_b200_stats), as doubles:
  * [0] graphs [1] kernel_launches [2] nodes_executed [3] fused_nodes [4] last_graph_ms [5] total_graph_ms
- * [6] tc_gemm_launches [7..14] reserved (see ggml-b200.h).  Returns <0 for other backends. */
+ * [6] tc_gemm_launches [7..14] reserved[0..7], [15] unused, [16..31] ext[0..15] (see ggml-b200.h).  Returns <0 for other backends. */
 int sdh_model_backend_stats(sdh_model* m, double* out, int n);
 /* ggml_backend_b200_set_option on the model's backend (e.g. "fusion", "tc_gemm", "kernel_timing"). */
 int sdh_model_set_backend_option(sdh_model* m, const char* key, int value);

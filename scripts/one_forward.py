@@ -1,5 +1,5 @@
 """Run N forwards of one harness architecture on B200_0 (for `ncu` launch lists / full captures of the non-headline configs).
-usage: one_forward.py <sdxl|flux|sd15|mmdit|wan> [n_forwards]        env GGML_B200_CUDA_GRAPHS=0 keeps every launch visible"""
+usage: one_forward.py <sdxl|flux|sd15|sd15x2|mmdit|wan|vae|vae128> [n_forwards]        env GGML_B200_CUDA_GRAPHS=0 keeps every launch visible"""
 import sys
 import time
 from pathlib import Path
@@ -16,6 +16,8 @@ CASES = {
     "sdxl": ("sdxl_unet", "bf16", dict(x=(1, 4, 128, 128), ctx=(1, 77, 2048), y=(1, 2816), t=999.0)),
     "flux": ("flux_schnell", "bf16", dict(x=(1, 16, 128, 128), ctx=(1, 256, 4096), y=(1, 768), t=1.0)),
     "mmdit": ("mmdit_sd3", "f16", dict(x=(1, 16, 128, 128), ctx=(1, 154, 4096), y=(1, 2048), t=500.0)),
+    "vae": ("vae_decoder", "f16", dict(x=(1, 4, 64, 64), ctx=None, y=None, t=None)),
+    "vae128": ("vae_decoder", "f16", dict(x=(1, 4, 128, 128), ctx=None, y=None, t=None)),
     "wan": ("wan_1_3b", "q8_0", dict(x=(16, 13, 64, 64), ctx=(1, 512, 4096), y=None, t=500.0)),
 }
 
@@ -27,8 +29,8 @@ def main():
     h = Harness()
     dev = h.load_b200()[0]
     m = h.model(dev, arch, wtype, 1, 1234, 0)
-    x = h.randn(42, e["x"]); ctx = h.randn(43, e["ctx"]); y = h.randn(44, e["y"]) if e["y"] else None
-    t = np.full((e["x"][0] if name == "sd15x2" else 1,), e["t"], np.float32)
+    x = h.randn(42, e["x"]); ctx = h.randn(43, e["ctx"]) if e["ctx"] else None; y = h.randn(44, e["y"]) if e["y"] else None
+    t = np.full((e["x"][0] if name == "sd15x2" else 1,), e["t"], np.float32) if e["t"] is not None else None
     nodes, flops = m.dump_graph(None, x, t, ctx, y)
     for i in range(n):
         s0 = m.stats()

@@ -270,6 +270,8 @@ static void b200_backend_free(ggml_backend_t backend) {
 static void b200_backend_set_tensor_async(ggml_backend_t backend, ggml_tensor* tensor, const void* data, size_t offset, size_t size) {
     auto* ctx = (b200_context*)backend->context;
     B200_CUDA_CHECK(cudaSetDevice(ctx->device));
+    // a write into model weights makes derived copies (packed conv filters, dequantised Q8_0) stale, exactly like the synchronous path
+    if (tensor->buffer && tensor->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS) b200_invalidate_address_range(ctx->device, (char*)tensor->data + offset, size);
     B200_CUDA_CHECK(cudaMemcpyAsync((char*)tensor->data + offset, data, size, cudaMemcpyHostToDevice, ctx->stream));
 }
 
@@ -285,6 +287,7 @@ static bool b200_backend_cpy_tensor_async(ggml_backend_t backend_src, ggml_backe
     if (!ggml_is_contiguous(src) || !ggml_is_contiguous(dst) || ggml_nbytes(src) != ggml_nbytes(dst)) return false;
     auto* sc = (b200_context*)backend_src->context;
     auto* dc = (b200_context*)backend_dst->context;
+    if (dst->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS) b200_invalidate_address_range(dc->device, dst->data, ggml_nbytes(dst));
     if (sc == dc) {
         B200_CUDA_CHECK(cudaSetDevice(dc->device));
         B200_CUDA_CHECK(cudaMemcpyAsync(dst->data, src->data, ggml_nbytes(src), cudaMemcpyDeviceToDevice, dc->stream));

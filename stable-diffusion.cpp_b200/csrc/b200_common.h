@@ -59,6 +59,7 @@ struct b200_stats {
     double   total_graph_ms;
     uint64_t tc_gemm_launches;  // tcgen05 GEMM launches (subset of kernel_launches)
     uint64_t reserved[8];
+    uint64_t ext[16];           // see include/ggml-b200.h
 };
 
 struct b200_device_info {

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 
 // ------------------------------------------------------------------------------------------------
@@ -40,6 +41,8 @@ b200_context* b200_context_create(const b200_device_info& info) {
     cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming);
     cudaEventCreate(&ctx->ev_start);
     cudaEventCreate(&ctx->ev_stop);
+    if (cudaMalloc(&ctx->gn_counters, B200_GN_COUNTERS * sizeof(unsigned)) == cudaSuccess) cudaMemset(ctx->gn_counters, 0, B200_GN_COUNTERS * sizeof(unsigned));
+    else { cudaGetLastError(); ctx->gn_counters = nullptr; }
     ctx->opt_fusion = env_flag("GGML_B200_FUSION", 1) != 0;
     ctx->opt_tc_gemm = env_flag("GGML_B200_TC_GEMM", 1) != 0;
     ctx->opt_timing = env_flag("GGML_B200_TIMING", 1) != 0;
@@ -58,6 +61,7 @@ b200_context::~b200_context() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     for (auto& c : ws.chunks) cudaFree(c.base);
+    if (gn_counters) cudaFree(gn_counters);
     for (auto& kv : plans) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (auto& p : kt_pending) { cudaEventDestroy(p.start); cudaEventDestroy(p.stop); }
     for (auto e : kt_free) cudaEventDestroy(e);
@@ -254,6 +258,8 @@ static int launch_tc(b200_context* ctx, const b200_gemm_args& g) {
     int n = -1;
     if (ctx->opt_persistent_gemm) n = b200_launch_gemm_tc_persistent(ctx->stream, ctx->info, g);   // experimental, off by default
     if (n < 0) n = b200_launch_gemm_tc(ctx->stream, ctx->info, g, w, w ? wsb : 0);
+    else ctx->stats.ext[4] += 1;           // persistent one-CTA variant
+    if (n == 2) { n = 1; ctx->stats.ext[5] += 1; }   // CTA-pair kernel (gemm_tc2.cu)
     if (ctx->opt_kernel_timing) {
         if (n > 0) {
             cudaEventRecord(e1, ctx->stream);
@@ -365,6 +371,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
                                              (const char*)g.B + i2 * b.batch_stride * es, ct, b.ld * es, g.D + i2 * g.d_batch_stride, g.ldd, M, Ng, K);
                 if (r < 0) return -1;
                 n += r;
+                ctx->stats.ext[0] += (uint64_t)r;      // CUDA-core reference GEMM: visible to the tests (must be 0 on model paths)
             }
             if (fz && fz->bias) {
                 b200_td o;
@@ -468,6 +475,7 @@ static int op_flash_attn(b200_context* ctx, ggml_tensor* dst, const fa_fusion* f
         if (n < 0) return -1;
         launches += n;
     }
+    ctx->stats.ext[7] += 1;     // unfused attention (scores materialised)
     operand qa, ka;
     if (!prepare_operand(ctx, q, ct, &qa, &launches)) return -1;
     if (!prepare_operand(ctx, k, ct, &ka, &launches)) return -1;
@@ -495,6 +503,7 @@ static int op_flash_attn(b200_context* ctx, ggml_tensor* dst, const fa_fusion* f
             for (int64_t h = 0; h < H; ++h)
                 n += b200_launch_gemm_ref(ctx->stream, (const char*)g.A + (h / rk) * ka.batch_stride * es, ct, ka.ld * es,
                                           (const char*)g.B + h * qa.batch_stride * es, ct, qa.ld * es, sbuf + h * Lk * Lq, Lk, Lk, Lq, d);
+            ctx->stats.ext[0] += (uint64_t)n;
         }
         launches += n;
 
@@ -537,6 +546,7 @@ static int op_flash_attn(b200_context* ctx, ggml_tensor* dst, const fa_fusion* f
             for (int64_t h = 0; h < H; ++h)
                 n += b200_launch_gemm_ref(ctx->stream, (const char*)g.A + (h / rk) * g.a_batch_stride * es, ct, Lk_pad * es,
                                           (const char*)pbuf + h * g.b_batch_stride * es, ct, Lk_pad * es, g.D + h * g.d_batch_stride, g.ldd, dv, Lq, Lk);
+            ctx->stats.ext[0] += (uint64_t)n;
         }
         launches += n;
     }
@@ -781,22 +791,38 @@ static inline uint64_t mix64(uint64_t h, uint64_t v) {
     return h ^ (h >> 32);
 }
 
-static uint64_t graph_key(const ggml_cgraph* g) {
-    uint64_t h = 0x1234567ull ^ (uint64_t)g->n_nodes;
+// The identity of a graph: one record per node (op, type, flags, data address, full ne / nb, op_params) and per source (type, data
+// address, full ne / nb).  The 64-bit hash of the record array finds the plan; a hit is confirmed by comparing the arrays word for
+// word, so a hash collision or a graph that differs in any of these fields can never replay kernels recorded for another graph.
+// The same pass notes nodes that WRITE into a WEIGHTS-usage buffer (the reference's LoRA apply adds into model tensors on the runtime
+// backend, lora.hpp:934-937): derived weight copies of those ranges must be dropped (see graph_compute).
+struct weight_write { const void* ptr; size_t bytes; };
+
+static uint64_t graph_signature(const ggml_cgraph* g, std::vector<uint64_t>& sig, std::vector<weight_write>* writes) {
+    sig.clear();
+    sig.reserve((size_t)g->n_nodes * 24);
+    sig.push_back((uint64_t)g->n_nodes);
     for (int i = 0; i < g->n_nodes; ++i) {
         const ggml_tensor* t = g->nodes[i];
-        h = mix64(h, ((uint64_t)t->op << 32) | ((uint64_t)t->type << 16) | (uint64_t)(t->flags & 0xffff));
-        h = mix64(h, (uint64_t)(uintptr_t)t->data);
-        for (int k = 0; k < 4; ++k) h = mix64(h, (uint64_t)t->ne[k] * 0x100000001b3ull + (uint64_t)t->nb[k]);
+        sig.push_back(((uint64_t)t->op << 32) | ((uint64_t)t->type << 16) | (uint64_t)(t->flags & 0xffff));
+        sig.push_back((uint64_t)(uintptr_t)t->data);
+        for (int k = 0; k < 4; ++k) { sig.push_back((uint64_t)t->ne[k]); sig.push_back((uint64_t)t->nb[k]); }
         const uint64_t* op = (const uint64_t*)t->op_params;
-        for (size_t k = 0; k < sizeof(t->op_params) / 8; ++k) h = mix64(h, op[k]);
+        for (size_t k = 0; k < sizeof(t->op_params) / 8; ++k) sig.push_back(op[k]);
         for (int sidx = 0; sidx < GGML_MAX_SRC; ++sidx) {
             const ggml_tensor* sr = t->src[sidx];
             if (!sr) break;
-            h = mix64(h, (uint64_t)(uintptr_t)sr->data ^ ((uint64_t)sr->type << 56));
-            h = mix64(h, (uint64_t)sr->ne[0] ^ ((uint64_t)sr->ne[1] << 20) ^ ((uint64_t)sr->ne[2] << 40) ^ ((uint64_t)sr->nb[1] << 8) ^ ((uint64_t)sr->nb[2] << 28));
+            sig.push_back((uint64_t)(uintptr_t)sr->data ^ ((uint64_t)sr->type << 56));
+            for (int k = 0; k < 4; ++k) { sig.push_back((uint64_t)sr->ne[k]); sig.push_back((uint64_t)sr->nb[k]); }
+        }
+        if (writes && (t->flags & GGML_TENSOR_FLAG_COMPUTE) && !node_is_noop(t)) {
+            const ggml_tensor* d = (t->op == GGML_OP_CPY && t->src[1]) ? t->src[1] : t;
+            const ggml_tensor* root = d->view_src ? d->view_src : d;
+            if (root->buffer && root->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS && d->data) writes->push_back({d->data, ggml_nbytes(d)});
         }
     }
+    uint64_t h = 0x1234567ull;
+    for (uint64_t w : sig) h = mix64(h, w);
     return h;
 }
 
@@ -954,9 +980,10 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
 // and the im2col matrix is never materialised.  Filters are repacked once per weight tensor ([OC][KH][KW][IC]) and cached
 // by device address; any host write into the weight buffer drops the cached copy (b200_invalidate_address_range).
 // ------------------------------------------------------------------------------------------------
-struct packed_weight { void* ptr; size_t src_bytes; int device; };
+struct packed_weight { void* ptr; size_t src_bytes; int device; int64_t ne[4]; size_t bytes; };
 static std::mutex g_pw_mutex;
 static std::unordered_map<const void*, packed_weight> g_packed_weights;
+static std::atomic<uint64_t> g_pw_bytes{0};
 // bumped whenever a derived weight copy is dropped: captured CUDA graphs hold raw pointers to those copies and must not be replayed
 // across such an event (a long-lived backend whose model was reloaded at the same addresses)
 static std::atomic<uint64_t> g_pw_generation{0};
@@ -970,6 +997,7 @@ void b200_invalidate_address_range(int device, const void* ptr, size_t size) {
         const char* a = (const char*)it->first;
         if (it->second.device == device && a < hi && a + it->second.src_bytes > lo) {
             cudaFree(it->second.ptr);   // implicit device synchronisation: no kernel can still be reading it
+            g_pw_bytes.fetch_sub(it->second.bytes, std::memory_order_relaxed);
             it = g_packed_weights.erase(it);
             g_pw_generation.fetch_add(1, std::memory_order_relaxed);
         } else {
@@ -978,33 +1006,78 @@ void b200_invalidate_address_range(int device, const void* ptr, size_t size) {
     }
 }
 
+// A derived copy may be kept across graph executions only for a CONSTANT of the model: a leaf tensor (no op, not a graph input) that
+// lives in a WEIGHTS-usage buffer, possibly seen through views.  A filter computed inside the graph (the reference casts LoRA factors to
+// F16 at run time, lora.hpp:724-733) lives in gallocr's compute buffer, whose addresses are recycled: it is repacked on every execution.
+static bool is_constant_weight(const ggml_tensor* w) {
+    const ggml_tensor* root = w->view_src ? w->view_src : w;
+    if (root->op != GGML_OP_NONE || (root->flags & GGML_TENSOR_FLAG_INPUT)) return false;
+    return root->buffer && root->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS;
+}
+
+static bool pw_matches(const packed_weight& pw, const b200_context* ctx, const ggml_tensor* w) {
+    return pw.device == ctx->device && pw.src_bytes == ggml_nbytes(w) && pw.ne[0] == w->ne[0] && pw.ne[1] == w->ne[1] && pw.ne[2] == w->ne[2] &&
+           pw.ne[3] == w->ne[3];
+}
+
 static const void* get_packed_conv_weight(b200_context* ctx, const ggml_tensor* w, int* launches) {
+    if (!is_constant_weight(w)) {
+        void* p = ws_alloc(ctx, ggml_nbytes(w));
+        if (!p) return nullptr;
+        int n = b200_launch_pack_conv_weight(ctx->stream, w->data, p, (int)w->ne[0], (int)w->ne[1], w->ne[2], w->ne[3]);
+        if (n < 0) return nullptr;
+        *launches += n;
+        ctx->stats.ext[3] += 1;
+        return p;
+    }
     std::lock_guard<std::mutex> lock(g_pw_mutex);
     auto it = g_packed_weights.find(w->data);
-    if (it != g_packed_weights.end() && it->second.device == ctx->device && it->second.src_bytes == ggml_nbytes(w)) return it->second.ptr;
+    if (it != g_packed_weights.end() && pw_matches(it->second, ctx, w)) return it->second.ptr;
     if (ctx->capturing) { ctx->capture_overflow = true; return nullptr; }
+    if (it != g_packed_weights.end()) {      // same address, other shape / device: the old copy is stale
+        cudaFree(it->second.ptr);
+        g_pw_bytes.fetch_sub(it->second.bytes, std::memory_order_relaxed);
+        g_packed_weights.erase(it);
+        g_pw_generation.fetch_add(1, std::memory_order_relaxed);
+    }
     void* p = nullptr;
     if (cudaMalloc(&p, ggml_nbytes(w)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     int n = b200_launch_pack_conv_weight(ctx->stream, w->data, p, (int)w->ne[0], (int)w->ne[1], w->ne[2], w->ne[3]);
     if (n < 0) { cudaFree(p); return nullptr; }
     *launches += n;
-    g_packed_weights[w->data] = packed_weight{p, ggml_nbytes(w), ctx->device};
+    g_packed_weights[w->data] = packed_weight{p, ggml_nbytes(w), ctx->device, {w->ne[0], w->ne[1], w->ne[2], w->ne[3]}, ggml_nbytes(w)};
+    g_pw_bytes.fetch_add(ggml_nbytes(w), std::memory_order_relaxed);
     return p;
 }
 
 // Q8_0 weight tensor -> contiguous f16 [K, rows, ...] copy, same cache and invalidation rule as the packed conv filters
 static const void* get_dequantised_weight(b200_context* ctx, const ggml_tensor* w, int* launches) {
+    const int64_t n = ggml_nelements(w);
+    if (!is_constant_weight(w)) {
+        void* p = ws_alloc(ctx, (size_t)n * 2);
+        if (!p) return nullptr;
+        int r = b200_launch_dequant_q8_0(ctx->stream, w->data, p, n / 32);
+        if (r < 0) return nullptr;
+        *launches += r;
+        return p;
+    }
     std::lock_guard<std::mutex> lock(g_pw_mutex);
     auto it = g_packed_weights.find(w->data);
-    if (it != g_packed_weights.end() && it->second.device == ctx->device && it->second.src_bytes == ggml_nbytes(w)) return it->second.ptr;
+    if (it != g_packed_weights.end() && pw_matches(it->second, ctx, w)) return it->second.ptr;
     if (ctx->capturing) { ctx->capture_overflow = true; return nullptr; }
+    if (it != g_packed_weights.end()) {
+        cudaFree(it->second.ptr);
+        g_pw_bytes.fetch_sub(it->second.bytes, std::memory_order_relaxed);
+        g_packed_weights.erase(it);
+        g_pw_generation.fetch_add(1, std::memory_order_relaxed);
+    }
     void* p = nullptr;
-    const int64_t n = ggml_nelements(w);
     if (cudaMalloc(&p, (size_t)n * 2) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     int r = b200_launch_dequant_q8_0(ctx->stream, w->data, p, n / 32);
     if (r < 0) { cudaFree(p); return nullptr; }
     *launches += r;
-    g_packed_weights[w->data] = packed_weight{p, ggml_nbytes(w), ctx->device};
+    g_packed_weights[w->data] = packed_weight{p, ggml_nbytes(w), ctx->device, {w->ne[0], w->ne[1], w->ne[2], w->ne[3]}, (size_t)n * 2};
+    g_pw_bytes.fetch_add((size_t)n * 2, std::memory_order_relaxed);
     return p;
 }
 
@@ -1158,7 +1231,10 @@ static int emit_conv(b200_context* ctx, const conv_match& m, const conv_prologue
         if (pro.norm) {
             stats = (float*)ws_alloc(ctx, (size_t)(N * pro.n_groups * 2 * sizeof(float)));
             if (!stats) return -1;
-            launches += b200_launch_gn_stats(ctx->stream, (const float*)src->data, stats, N, C, H * W, pro.n_groups, pro.eps);
+            const size_t pb = ctx->gn_counters ? b200_gn_stats_partial_bytes(N, C, H * W, pro.n_groups) : 0;
+            void* partial = pb ? ws_alloc(ctx, pb) : nullptr;
+            if (pb && !partial) return -1;
+            launches += b200_launch_gn_stats(ctx->stream, (const float*)src->data, stats, N, C, H * W, pro.n_groups, pro.eps, partial, ctx->gn_counters);
         }
         int n = b200_launch_to_nhwc_f16(ctx->stream, (const float*)src->data, sh, N, C, H, W, pro.up, stats, pro.n_groups, pro.gw, pro.gb, pro.act);
         if (n < 0) return -1;
@@ -1194,6 +1270,7 @@ static int emit_conv(b200_context* ctx, const conv_match& m, const conv_prologue
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->opt_kernel_timing) { e0 = kt_event(ctx); e1 = kt_event(ctx); cudaEventRecord(e0, ctx->stream); }
     int n = b200_launch_conv_tc(ctx->stream, ctx->info, c, w, w ? wsb : 0);
+    if (n == 2) { n = 1; ctx->stats.ext[5] += 1; }   // CTA-pair kernel (gemm_tc2.cu)
     if (ctx->opt_kernel_timing) {
         if (n > 0) {
             cudaEventRecord(e1, ctx->stream);
@@ -1818,7 +1895,20 @@ static void drop_cuda_graphs(b200_context* ctx) {
         if (kv.second.exec) { cudaGraphExecDestroy(kv.second.exec); kv.second.exec = nullptr; }
 }
 
+// counters of kernels that run inside a replayed CUDA graph: the deltas recorded at capture are added at every replay
+static void stats_add(b200_stats& dst, const b200_stats& a, const b200_stats& b) {   // dst += a - b
+    dst.fused_nodes += a.fused_nodes - b.fused_nodes;
+    dst.tc_gemm_launches += a.tc_gemm_launches - b.tc_gemm_launches;
+    for (int i = 2; i < 8; ++i) if (i != 3) dst.reserved[i] += a.reserved[i] - b.reserved[i];
+    for (int i = 0; i < 16; ++i) if (i != 1 && i != 2 && i != 6) dst.ext[i] += a.ext[i] - b.ext[i];
+}
+
 enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
+    const auto host_t0 = std::chrono::steady_clock::now();
+    struct host_timer {
+        b200_context* c; std::chrono::steady_clock::time_point t0;
+        ~host_timer() { c->stats.ext[1] += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count(); }
+    } host_timer_guard{ctx, host_t0};
     B200_CUDA_CHECK(cudaSetDevice(ctx->device));
     // the previous graph's device time is finalised here (the host has synchronised in between: it read the result)
     if ((ctx->opt_timing && ctx->timing_pending) || !ctx->kt_pending.empty()) b200_context_finalize_timing(ctx);
@@ -1831,10 +1921,24 @@ enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
     const bool timing = ctx->opt_timing && !ctx->timing_pending;
     const bool want_graphs = ctx->opt_cuda_graphs && !ctx->opt_kernel_timing && cgraph->n_nodes >= 16;
     b200_context::plan* pl = nullptr;
-    if (want_graphs) {
-        const uint64_t key = graph_key(cgraph);
+    std::vector<weight_write> writes;
+    std::vector<uint64_t>& sig = ctx->sig_scratch;
+    const uint64_t key = graph_signature(cgraph, sig, &writes);
+    if (!writes.empty()) {
+        // this graph modifies model weights in place: derived copies (packed conv filters, dequantised Q8_0) of those ranges are stale
+        // after it -- and, for consumers later in this same graph, from the write on.  Drop them now (consumers repack in stream order)
+        // and again after the graph has been issued; such a graph is never captured.
+        for (auto& w : writes) b200_invalidate_address_range(ctx->device, w.ptr, w.bytes);
+        ctx->stats.ext[2] += 1;
+    }
+    if (want_graphs && writes.empty()) {
         if (ctx->plans.size() > 64) { drop_cuda_graphs(ctx); ctx->plans.clear(); }
         pl = &ctx->plans[key];
+        if (pl->seen > 0 && pl->sig != sig) {          // hash collision or a graph differing in a field the hash folded away
+            if (pl->exec) { cudaGraphExecDestroy(pl->exec); pl->exec = nullptr; }
+            *pl = b200_context::plan{};
+        }
+        if (pl->seen == 0) pl->sig = sig;
     }
     if (timing) cudaEventRecord(ctx->ev_start, ctx->stream);
     enum ggml_status st = GGML_STATUS_SUCCESS;
@@ -1849,6 +1953,8 @@ enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
         }
         launches = pl->launches;
         nodes = pl->nodes;
+        const b200_stats zero{};
+        stats_add(ctx->stats, pl->delta, zero);
         ctx->stats.reserved[3]++;   // CUDA-graph replays
     } else if (pl && pl->seen >= 1 && !pl->no_capture && ctx->ws.chunks.size() <= 1) {
         // ---- second sighting (or a stale plan: workspace moved / derived weights dropped): capture while executing nothing, then launch
@@ -1856,6 +1962,7 @@ enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
         if (pl->exec) { cudaGraphExecDestroy(pl->exec); pl->exec = nullptr; }
         ctx->capture_overflow = false;
         ctx->capturing = true;
+        const b200_stats before = ctx->stats;
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
         if (e == cudaSuccess) {
@@ -1874,6 +1981,8 @@ enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
                 pl->nodes = nodes;
                 pl->ws_generation = ctx->ws_generation;
                 pl->pw_generation = g_pw_generation.load(std::memory_order_relaxed);
+                pl->delta = b200_stats{};
+                stats_add(pl->delta, ctx->stats, before);
                 e = cudaGraphLaunch(exec, ctx->stream);
                 ok = e == cudaSuccess;
             }
@@ -1881,6 +1990,7 @@ enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
         if (graph) cudaGraphDestroy(graph);
         if (!ok) {
             cudaGetLastError();
+            ctx->stats = before;                         // nothing of the abandoned capture ran
             pl->no_capture = !ctx->capture_overflow;     // an overflow is cured by the eager run below (it creates the derived weights): capture next time
             if (pl->exec) { cudaGraphExecDestroy(pl->exec); pl->exec = nullptr; }
             if (st != GGML_STATUS_SUCCESS && !ctx->capture_overflow) return st;
@@ -1894,6 +2004,11 @@ enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
         if (pl) pl->seen++;
     }
     if (st != GGML_STATUS_SUCCESS) return st;
+    if (!writes.empty()) {
+        // copies made DURING this graph from pre-write values (a conv that precedes the write in graph order)
+        for (auto& w : writes) b200_invalidate_address_range(ctx->device, w.ptr, w.bytes);
+    }
+    ctx->stats.ext[6] = g_pw_bytes.load(std::memory_order_relaxed);
     ctx->stats.kernel_launches += launches;
     ctx->stats.nodes_executed += nodes;
     if (timing) {

@@ -58,11 +58,17 @@ struct b200_context {
     std::vector<cudaEvent_t> kt_free;
     double kt_us = 0, kt_flops = 0;
     // repeated-graph cache (CUDA graph replay)
-    struct plan { cudaGraphExec_t exec = nullptr; int seen = 0; bool no_capture = false; uint64_t launches = 0, nodes = 0, ws_generation = 0, pw_generation = 0; };
+    struct plan {
+        cudaGraphExec_t exec = nullptr; int seen = 0; bool no_capture = false; uint64_t launches = 0, nodes = 0, ws_generation = 0, pw_generation = 0;
+        std::vector<uint64_t> sig;     // full identity of the graph this plan was recorded for (compared word for word on a hash hit)
+        b200_stats delta{};            // counters of the kernels inside the captured graph (added at every replay)
+    };
+    std::vector<uint64_t> sig_scratch;
     std::unordered_map<uint64_t, plan> plans;
     uint64_t ws_generation = 0;
     // per-graph-execution cache of packed (type-converted) contraction operands, keyed by ggml tensor node
     std::unordered_map<std::pair<const ggml_tensor*, int>, b200_operand, b200_pack_key_hash> pack_cache;
+    unsigned* gn_counters = nullptr;   // B200_GN_COUNTERS zeroed counters of the chunked GroupNorm statistics (self-resetting)
     bool capturing = false, capture_overflow = false;
     bool launched_any = false;        // a kernel of the current graph execution has been launched
 

@@ -82,6 +82,12 @@ size_t b200_gemm_tc_workspace_bytes(const b200_device_info& dev, const b200_gemm
 // EXPERIMENTAL persistent variant (gemm_tc_persist.cu; option "persistent_gemm", off by default): 1 when launched, -1 when not applicable
 int b200_launch_gemm_tc_persistent(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g);
 
+// gemm_tc2.cu: CTA-pair (tcgen05 cta_group::2, M = 256) persistent GEMM / implicit conv with two TMEM accumulators; F16 / BF16 only.
+// bn: tile N of the pair (multiple of 16, <= 256), splits: split-K factor inside the cluster (1..4).  1 when launched, -1 when the
+// problem is outside the envelope.  The conv front end is declared after b200_conv_args below.
+int b200_launch_gemm_tc2(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g, int bn, int splits);
+double b200_gemm_tc2_model(const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int nkb, int bn, int splits);
+
 // Q8_0 blocks (34 bytes: f16 scale + 32 int8, ggml-common.h:251-255) -> f16 rows [rows][K] (K % 32 == 0): the derived weight layout the
 // tensor-core GEMM reads; value = round_f16(float(d) * q), the reference's own dequantisation (ggml-quants.c dequantize_row_q8_0)
 int b200_launch_dequant_q8_0(cudaStream_t s, const void* blocks, void* out_f16, int64_t n_blocks);
@@ -108,8 +114,14 @@ struct b200_conv_args {
 bool b200_conv_tc_supported(int64_t N, int64_t H, int64_t W, int64_t C, int64_t OC, int KH, int KW, int s0, int s1, int p0, int p1, int d0, int d1);
 size_t b200_conv_tc_workspace_bytes(const b200_device_info& dev, const b200_conv_args& c);
 int b200_launch_conv_tc(cudaStream_t s, const b200_device_info& dev, const b200_conv_args& c, void* workspace, size_t workspace_bytes);
+int b200_launch_conv_tc2(cudaStream_t s, const b200_device_info& dev, const b200_conv_args& c, int bn, int splits);
 // stats: float2 {mean, rstd} per (image, group)
-int b200_launch_gn_stats(cudaStream_t s, const float* x, float* stats, int64_t N, int64_t C, int64_t inner, int n_groups, float eps);
+// partial / counters (optional): scratch of b200_gn_stats_partial_bytes() and B200_GN_COUNTERS zero-initialised unsigneds owned by the
+// backend instance: large groups are then split over several CTAs (one read of x, deterministic merge by the last CTA)
+#define B200_GN_COUNTERS 4096
+int b200_launch_gn_stats(cudaStream_t s, const float* x, float* stats, int64_t N, int64_t C, int64_t inner, int n_groups, float eps, void* partial = nullptr,
+                         unsigned* counters = nullptr);
+size_t b200_gn_stats_partial_bytes(int64_t N, int64_t C, int64_t inner, int n_groups);
 // NCHW f32 -> NHWC f16 with optional GroupNorm (stats + per-channel w, b), SiLU (act = 1) and nearest upsampling (up = 1 | 2)
 int b200_launch_to_nhwc_f16(cudaStream_t s, const float* x, void* out, int64_t N, int64_t C, int64_t H, int64_t W, int up, const float* stats,
                             int n_groups, const float* gw, const float* gb, int act);

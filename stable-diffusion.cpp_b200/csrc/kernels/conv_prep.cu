@@ -67,6 +67,95 @@ __global__ void __launch_bounds__(1024) k_gn_stats(const float* __restrict__ x, 
     if (threadIdx.x == 0) stats[(int64_t)n * G + g] = make_float2(mean, 1.0f / sqrtf(var + eps));
 }
 
+// Chunked statistics: grid (S, G, N).  A group of the VAE decoder is 1 M floats (512 x 512 x 4 channels); one CTA per group (above)
+// leaves 116 of 148 SMs idle and reads the group twice.  Here S CTAs share a group: each keeps its chunk (<= 32 K floats) in
+// REGISTERS, computes the chunk mean and the chunk's sum of squared deviations from THAT mean (the oracle's two-pass arithmetic,
+// ops.cpp:4079-4152, per chunk), and the last CTA to finish merges the S partial (mean, M2) pairs in chunk order with the exact
+// pairwise update (Chan et al.) in double -- deterministic, one read of the activation.
+constexpr int GN2_THREADS = 512;
+constexpr int GN2_VEC = 16;                                  // float4 per thread
+constexpr int GN2_CHUNK = GN2_THREADS * GN2_VEC * 4;         // 32768 floats
+
+__device__ __forceinline__ double block_sum_d(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double r = (threadIdx.x < (GN2_THREADS >> 5)) ? red[threadIdx.x] : 0.0;
+    if (w == 0) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    if (threadIdx.x == 0) red[0] = r;
+    __syncthreads();
+    return red[0];
+}
+
+__global__ void __launch_bounds__(GN2_THREADS) k_gn_stats_chunked(const float* __restrict__ x, float2* __restrict__ stats, double2* partial,
+                                                                  unsigned* __restrict__ counters, int64_t inner, int C, int cpg, int G, int S,
+                                                                  int64_t chunk, float eps) {
+    pdl_wait();
+    pdl_launch_dependents();
+    __shared__ double red[32];
+    __shared__ int is_last;
+    const int ci = blockIdx.x, g = blockIdx.y, n = blockIdx.z;
+    const int c0 = g * cpg, c1 = min(c0 + cpg, C);
+    const int64_t len = (int64_t)(c1 - c0) * inner;
+    const float4* x4 = (const float4*)(x + ((int64_t)n * C + c0) * inner);
+    const int64_t e0 = (int64_t)ci * chunk, e1 = min(e0 + chunk, len);        // multiples of 4 (chunk % 4 == 0, len % 4 == 0)
+    const int64_t v0 = e0 >> 2, nv = (e1 - e0) >> 2;
+    float4 r[GN2_VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < GN2_VEC; ++k) {
+        const int64_t i = (int64_t)k * GN2_THREADS + threadIdx.x;
+        r[k] = i < nv ? x4[v0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (r[k].x + r[k].y) + (r[k].z + r[k].w);
+    }
+    const double cnt = (double)(e1 - e0);
+    const double mean_d = block_sum_d((double)s, red) / cnt;
+    const float mean = (float)mean_d;
+    float s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < GN2_VEC; ++k) {
+        const int64_t i = (int64_t)k * GN2_THREADS + threadIdx.x;
+        if (i < nv) {
+            const float a = r[k].x - mean, b = r[k].y - mean, c = r[k].z - mean, d = r[k].w - mean;
+            s2 += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    // sum of squared deviations from the ROUNDED mean; shift to the exact chunk mean: sum (x - m)^2 = sum (x - mf)^2 - cnt (m - mf)^2
+    double m2 = block_sum_d((double)s2, red);
+    const double dm = mean_d - (double)mean;
+    m2 -= cnt * dm * dm;
+    const int64_t ng = (int64_t)n * G + g;
+    if (threadIdx.x == 0) {
+        partial[ng * S + ci] = make_double2(mean_d, m2);
+        __threadfence();
+        const unsigned old = atomicAdd(&counters[ng], 1u);
+        is_last = (old == (unsigned)(S - 1));
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        double na = 0.0, ma = 0.0, M2 = 0.0;
+        for (int i = 0; i < S; ++i) {
+            const double* pp = (const double*)partial + 2 * (ng * S + i);
+            const double2 pb = make_double2(__ldcg(pp), __ldcg(pp + 1));     // written by other CTAs: read through L2
+            const double nb = (double)(min((int64_t)(i + 1) * chunk, len) - (int64_t)i * chunk);
+            const double nt = na + nb, delta = pb.x - ma;
+            ma += delta * nb / nt;
+            M2 += pb.y + delta * delta * na * nb / nt;
+            na = nt;
+        }
+        const float var = (float)(M2 / na);
+        stats[ng] = make_float2((float)ma, 1.0f / sqrtf(var + eps));
+        counters[ng] = 0u;            // ready for the next launch (launches of one stream are ordered)
+    }
+}
+
 // grid (ceil(OH*OW / 64), C / 64, N), block 256: a 64-channel x 64-pixel tile through shared memory.
 // Load: 16 lanes x float4 cover 64 consecutive pixels of one channel (coalesced 256 B), per-channel norm/affine constants are
 // fetched once per channel per thread.  Store: one warp writes one pixel's 64 channels = 128 contiguous bytes of the NHWC row.
@@ -171,11 +260,29 @@ int b200_launch_dequant_q8_0(cudaStream_t s, const void* blocks, void* out_f16, 
     return 1;
 }
 
-int b200_launch_gn_stats(cudaStream_t s, const float* x, float* stats, int64_t N, int64_t C, int64_t inner, int n_groups, float eps) {
+int b200_launch_gn_stats(cudaStream_t s, const float* x, float* stats, int64_t N, int64_t C, int64_t inner, int n_groups, float eps, void* partial,
+                         unsigned* counters) {
     const int cpg = (int)((C + n_groups - 1) / n_groups);
+    const int64_t len = (int64_t)cpg * inner;
+    const int64_t S = (len + GN2_CHUNK - 1) / GN2_CHUNK;
+    // chunked path: every group complete (C % cpg == 0), float4-aligned chunks, counters available
+    if (partial && counters && S >= 2 && S <= 1024 && C % cpg == 0 && (inner & 3) == 0 && (((uintptr_t)x) & 15) == 0 && N * n_groups <= B200_GN_COUNTERS && N <= 65535) {
+        int64_t chunk = (len + S - 1) / S;
+        chunk = (chunk + 3) & ~(int64_t)3;
+        dim3 grid((unsigned)S, (unsigned)n_groups, (unsigned)N);
+        b200_launch(k_gn_stats_chunked, dim3(grid), dim3(GN2_THREADS), 0, s, x, (float2*)stats, (double2*)partial, counters, inner, (int)C, cpg, n_groups, (int)S,
+                    chunk, eps);
+        return 1;
+    }
     dim3 grid((unsigned)n_groups, (unsigned)N);
     b200_launch(k_gn_stats, dim3(grid), dim3(1024), 0, s, x, (float2*)stats, inner, (int)C, cpg, n_groups, eps);
     return 1;
+}
+
+size_t b200_gn_stats_partial_bytes(int64_t N, int64_t C, int64_t inner, int n_groups) {
+    const int cpg = (int)((C + n_groups - 1) / n_groups);
+    const int64_t S = ((int64_t)cpg * inner + GN2_CHUNK - 1) / GN2_CHUNK;
+    return (size_t)(N * n_groups * S * 16);
 }
 
 int b200_launch_to_nhwc_f16(cudaStream_t s, const float* x, void* out, int64_t N, int64_t C, int64_t H, int64_t W, int up, const float* stats,

@@ -403,7 +403,7 @@ bool make_operand_map(CUtensorMap* out, const void* ptr, int type, int64_t K, in
 
 struct Plan { int bn; int splits; };
 
-Plan choose_plan(const b200_device_info& dev, const b200_gemm_args& g, int num_k_blocks) {
+Plan choose_plan(const b200_device_info& dev, const b200_gemm_args& g, int num_k_blocks, double* cycles = nullptr) {
     const int sms = dev.sm_count > 0 ? dev.sm_count : 148;
     const int64_t mt = (g.M + BM - 1) / BM;
     double best = 1e30;
@@ -432,7 +432,36 @@ Plan choose_plan(const b200_device_info& dev, const b200_gemm_args& g, int num_k
             if (t < best) { best = t; bestp = Plan{bn, splits}; }
         }
     }
+    if (cycles) *cycles = best;
     return bestp;
+}
+
+// CTA-pair kernel (gemm_tc2.cu): GGML_B200_GEMM2 = 0 never, 1 when its modelled time beats the one-CTA plan (default), 2 whenever legal
+int gemm2_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GGML_B200_GEMM2");
+        v = (e && *e) ? atoi(e) : 0;      // flipped to 1 once validated on hardware
+    }
+    return v;
+}
+
+struct Plan2 { int bn; int splits; double cycles; };
+
+Plan2 choose_plan2(const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int nkb) {
+    const int sms = dev.sm_count > 0 ? dev.sm_count : 148;
+    Plan2 best{0, 1, 1e30};
+    const int bns[] = {256, 224, 192, 160, 128, 96, 64, 48, 32};
+    for (int bn : bns) {
+        if (bn > 32 && N <= bn / 2) continue;
+        const int64_t tiles = ((M + 255) / 256) * ((N + bn - 1) / bn) * batch;
+        for (int splits = 1; splits <= 4; ++splits) {
+            if (splits > 1 && (tiles * 2 * splits > sms || nkb / splits < 4)) break;
+            const double t = b200_gemm_tc2_model(dev, M, N, batch, nkb, bn, splits);
+            if (t < best.cycles) best = Plan2{bn, splits, t};
+        }
+    }
+    return best;
 }
 
 template <int BN, int FMT>
@@ -473,7 +502,15 @@ int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     if (g.K <= 0) return -1;
     const int bk = (int)(BK_BYTES / es);
     const int nkb = (int)((g.K + bk - 1) / bk);
-    Plan pl = choose_plan(dev, g, nkb);
+    double cycles1 = 0;
+    Plan pl = choose_plan(dev, g, nkb, &cycles1);
+    if (gemm2_mode() && g.type != GGML_TYPE_F32 && !g.trace && !g.early && g.M > BM) {
+        const Plan2 p2 = choose_plan2(dev, g.M, g.N, g.batch, nkb);
+        if (p2.bn > 0 && (gemm2_mode() >= 2 || p2.cycles < cycles1)) {
+            const int r = b200_launch_gemm_tc2(s, dev, g, p2.bn, p2.splits);
+            if (r > 0) return 2;       // 2: launched on the CTA-pair kernel
+        }
+    }
 
     // batch decomposition: args carry a flat batch with an A broadcast ratio; map to (i2, i3) = (batch, 1)
     CUtensorMap ta, tb;
@@ -544,7 +581,15 @@ int b200_launch_conv_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     memset(&g, 0, sizeof(g));
     g.type = GGML_TYPE_F16; g.M = c.H * c.W; g.N = c.OC; g.K = (int64_t)c.KH * c.KW * c.C; g.batch = c.N; g.a_bcast = 1;
     const int nkb = (int)(g.K / 64);
-    Plan pl = choose_plan(dev, g, nkb);
+    double cycles1 = 0;
+    Plan pl = choose_plan(dev, g, nkb, &cycles1);
+    if (gemm2_mode() && g.M > BM && g.M % 128 == 0) {
+        const Plan2 p2 = choose_plan2(dev, g.M, g.N, g.batch, nkb);
+        if (p2.bn > 0 && (gemm2_mode() >= 2 || p2.cycles < cycles1)) {
+            const int r = b200_launch_conv_tc2(s, dev, c, p2.bn, p2.splits);
+            if (r > 0) return 2;
+        }
+    }
 
     // A: NHWC image, 4-D (C, W, H, N); box = 64 channels x BW x BH pixels with BW * BH == 128
     const uint32_t BW = (uint32_t)(c.W < 128 ? c.W : 128), BH = 128 / BW;

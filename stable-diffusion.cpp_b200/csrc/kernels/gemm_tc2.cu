@@ -1,0 +1,542 @@
+// gemm_tc2.cu -- the CTA-PAIR tcgen05 GEMM / implicit-GEMM convolution: D[n][m] = sum_k A[m][k] * B[n][k]  (F16 / BF16, f32 accumulate)
+//
+// Why a second kernel.  The one-CTA kernel (gemm_tc.cu) stages (128 + BN) x 128 B per k-block for 128 x BN x 64 MACs; on B200 the
+// L2 -> SM path (about 6300 B/clk for the whole chip, about 43 B/clk per SM when all 148 pull -- B300_MICROARCH "LTS cap") caps it
+// near 50 % of the tensor pipe and the profile of round 1 showed exactly that (profiles/r01_gemm_notes.md).  Here two CTAs of a
+// cluster (one TPC) execute ONE `tcgen05.mma.cta_group::2` of M = 256: each CTA stages its own 128 rows of A and only HALF of the B
+// tile, the tensor cores read both halves across the pair, so the bytes per MAC through L2 drop by a third (BN = 256: 85 -> 128
+// flop/B) and every B byte is fetched once per 256 output rows.
+//
+//   * persistent: grid = number of CTA pairs that fit (<= SMs / 2); each pair walks tiles t = pair, pair + P, ...
+//   * TMEM holds TWO accumulators (2 x BN columns): the MMA issuer starts the main loop of tile i + 1 while the eight epilogue warps
+//     of both CTAs drain tile i (acc_full / acc_empty mbarriers) -- the epilogue, 43 % of the warp samples in round 1, leaves the
+//     critical path whenever a pair owns more than one tile
+//   * warp roles per CTA (320 threads): warp 0 = TMA producer (each CTA loads its A rows and its half of B; completion is signalled on
+//     the LEADER CTA's full barrier: `cp.async.bulk.tensor...cta_group::2`), warp 1 = TMEM allocation (both CTAs) and, in the leader
+//     only, the single-thread MMA issue + `tcgen05.commit...multicast::cluster` that frees the ring slot in both CTAs,
+//     warps 2..9 = epilogue (two warps per TMEM lane quadrant, alternating 32-column chunks)
+//   * small-M / small-N problems with a long K: split-K inside the cluster (2, 1, splits): partial tiles stay in shared memory and
+//     are reduced through DSMEM in split order (deterministic), as in gemm_tc.cu
+//   * convolution mode: A is the NHWC f16 image read as halo boxes {64 ch, BW, BH} (zero fill = the conv's padding), B the packed
+//     filter; k-block = (tap, 64-channel block)
+//
+// Roofline: tensor pipe.  2 * M * N * K flop per launch; algorithmic bytes (M + N) * K * 2 + M * N * 4.
+#include "../b200_ops.h"
+#include "b200_launch.cuh"
+#include "sm100_ptx.cuh"
+
+#include <cuda_fp16.h>
+#include <algorithm>
+#include <cstring>
+
+using namespace sm100;
+
+namespace {
+
+constexpr int BM = 128;                 // rows of A per CTA (TMEM lanes); the pair computes 256
+constexpr int BK_BYTES = 128;
+constexpr int A_STAGE_BYTES = BM * BK_BYTES;
+constexpr int MAX_STAGES = 10;
+constexpr int NTHREADS = 320;
+
+struct G2Params {
+    float* D;
+    int64_t ldd, d_batch_stride;
+    int64_t M, N;
+    int num_k_blocks, splits;
+    int bn;                 // tile N of the pair (multiple of 16, <= 256); each CTA stages bn / 2 rows of B
+    int stages, stage_bytes;
+    int tiles_m, tiles_n, total_tiles;   // tiles_m counts 256-row pair tiles
+    int acc_stride, tmem_cols;
+    int ne12, r2;
+    const float* bias;
+    int bias_mode;          // 0 none, 1 per m, 2 per n
+    const float* residual;
+    int64_t ldr, r_batch_stride;
+    int act;
+    int conv, conv_W, conv_KW, conv_cblocks, conv_pad, conv_dil;
+};
+
+// ---- cta_group::2 flavours of the primitives in sm100_ptx.cuh
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_f16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once) on the barrier at this shared-memory offset in every CTA of `mask` when all tcgen05 ops issued so far have retired
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+// TMA tile load whose completion bytes are counted on a barrier that may live in the peer CTA (shared::cluster address)
+__device__ __forceinline__ void tma_load_4d_2cta(void* smem, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                     smem_u32(smem)),
+                 "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+__device__ __forceinline__ float act_fn(float v, int act) {
+    if (act == 1) return v / (1.0f + expf(-v));
+    if (act == 2) return 0.5f * v * (1.0f + tanhf(0.79788456080286535587989211986876f * v * (1.0f + 0.044715f * v * v)));
+    return v;
+}
+
+// FMT: 0 = f16, 1 = bf16
+template <int FMT>
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                         const G2Params p) {
+    constexpr int BK = 64, UMMA_K = 16;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();          // cluster (2, 1, splits): rank = pair rank + 2 * split
+    const uint32_t prank = crank & 1u;                 // 0: leader of the pair (issues the MMAs, owns the full / acc_empty barriers)
+    const uint32_t leader = crank & ~1u;
+    const int split = (int)(crank >> 1);
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int kb0 = (int)(((int64_t)split * p.num_k_blocks) / p.splits);
+    const int kb1 = (int)(((int64_t)(split + 1) * p.num_k_blocks) / p.splits);
+    const int nkb = kb1 - kb0;
+    const int half_bn = p.bn >> 1;
+    const uint32_t my_stage_bytes = (uint32_t)(A_STAGE_BYTES + half_bn * BK_BYTES);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 2);      // one arrive.expect_tx from the producer of each CTA of the pair (used in the leader only)
+            mbar_init(&empty_bar[s], 1);     // one multicast tcgen05.commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);      // multicast tcgen05.commit
+            mbar_init(&acc_empty[b], 16);    // eight epilogue warps of each CTA (used in the leader only)
+        }
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {
+        tmem_alloc2(&tmem_base_smem, (uint32_t)p.tmem_cols);
+        tmem_relinquish2();
+    }
+    tc_fence_before();
+    cluster_sync_all();           // barriers of every CTA of the cluster are initialised before anyone signals them remotely
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();
+    pdl_launch_dependents();
+
+    // tile -> (pair m tile, n tile, batch): m fastest, so the pairs running at one time share the B tile in L2
+    auto decode = [&](int t, int& m0, int& n0, int& batch) {
+        const int mt = t % p.tiles_m;
+        const int r = t / p.tiles_m;
+        const int nt = r % p.tiles_n;
+        batch = r / p.tiles_n;
+        m0 = mt * (2 * BM) + (int)prank * BM;      // this CTA's 128 rows
+        n0 = nt * p.bn;                            // first column of the pair's tile
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer (both CTAs) =====================
+            const uint32_t full0 = dsmem_map(smem_u32(&full_bar[0]), leader);
+            uint32_t it = 0;
+            for (int t = pair; t < p.total_tiles; t += npairs) {
+                int m0, n0, batch;
+                decode(t, m0, n0, batch);
+                const int i2 = batch % p.ne12, i3 = batch / p.ne12;
+                const int nb = n0 + (int)prank * half_bn;          // this CTA's half of the B tile
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = (int)(it % (uint32_t)p.stages);
+                    const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    const uint32_t fb = full0 + 8u * (uint32_t)s;
+                    mbar_expect_tx_cluster(fb, my_stage_bytes);
+                    uint8_t* sa = smem + (size_t)s * p.stage_bytes;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    if (p.conv) {
+                        const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
+                        const int kh = tap / p.conv_KW, kw = tap - kh * p.conv_KW;
+                        const int y0 = m0 / p.conv_W, x0 = m0 - y0 * p.conv_W;
+                        tma_load_4d_2cta(sa, &tmA, fb, cb * 64, x0 + kw * p.conv_dil - p.conv_pad, y0 + kh * p.conv_dil - p.conv_pad, i2);
+                        tma_load_4d_2cta(sb, &tmB, fb, kb * BK, nb, 0, 0);
+                    } else {
+                        tma_load_4d_2cta(sa, &tmA, fb, kb * BK, m0, i2 / p.r2, i3);
+                        tma_load_4d_2cta(sb, &tmB, fb, kb * BK, nb, i2, i3);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (prank == 0) {
+            // ===================== MMA issuer (leader CTA only) =====================
+            const uint32_t idesc = make_idesc((uint32_t)FMT, 2 * BM, (uint32_t)p.bn);
+            const uint16_t pair_mask = (uint16_t)(3u << leader);
+            uint32_t it = 0, j = 0;
+            for (int t = pair; t < p.total_tiles; t += npairs, ++j) {
+                const uint32_t buf = j & 1u, aph = (j >> 1) & 1u;
+                mbar_wait(&acc_empty[buf], aph ^ 1u);           // both CTAs have drained this accumulator (first use: free)
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * (uint32_t)p.acc_stride;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = (int)(it % (uint32_t)p.stages);
+                    const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = smem_u32(smem + (size_t)s * p.stage_bytes);
+                        const uint64_t da = make_smem_desc_sw128(sa);
+                        const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) mma_f16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        mma_commit_mc(&empty_bar[s], pair_mask);                       // ring slot reusable in BOTH CTAs
+                        if (kb == nkb - 1) mma_commit_mc(&acc_full[buf], pair_mask);   // accumulator complete (both CTAs' epilogues)
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9 of both CTAs) =====================
+        const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;             // the two warps of a quadrant alternate 32-column chunks
+        const int ml = q * 32 + lane;
+        const uint32_t acc_empty0 = dsmem_map(smem_u32(&acc_empty[0]), leader);
+        uint32_t j = 0;
+        for (int t = pair; t < p.total_tiles; t += npairs, ++j) {
+            int m0, n0, batch;
+            decode(t, m0, n0, batch);
+            const uint32_t buf = j & 1u, aph = (j >> 1) & 1u;
+            const int64_t m = (int64_t)m0 + ml;
+            const bool mvalid = m < p.M;
+            const float bias_m = (p.bias_mode == 1 && mvalid) ? p.bias[m] : 0.f;
+            const int ncols = (int)min((int64_t)p.bn, p.N - n0);
+            float* Dp = p.D + (int64_t)batch * p.d_batch_stride;
+            const float* Rp = p.residual ? p.residual + (int64_t)batch * p.r_batch_stride : nullptr;
+            mbar_wait(&acc_full[buf], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.acc_stride;
+            if (p.splits > 1) {
+                // partial tile -> own shared memory [bn][128] f32 (the operand ring is dead: every MMA of this CTA pair has retired)
+                float* sred = (float*)smem;
+#pragma unroll 1
+                for (int c0 = half * 32; c0 < p.bn; c0 += 64) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c0 + i < p.bn) sred[(c0 + i) * BM + ml] = __uint_as_float(r[i]);
+                }
+            } else if (p.act == 0) {
+                float* dptr = Dp + (int64_t)n0 * p.ldd + m;
+                const float* rptr = Rp ? Rp + (int64_t)n0 * p.ldr + m : nullptr;
+                const float* bias_n = p.bias_mode == 2 ? p.bias + n0 : nullptr;
+#pragma unroll 1
+                for (int c0 = half * 32; c0 < ncols; c0 += 64) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c0, r);
+                    const float bn = (bias_n && c0 + lane < ncols) ? bias_n[c0 + lane] : 0.f;   // lane i carries the bias of column c0 + i
+                    tmem_ld_wait();
+                    if (rptr == nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float v = __uint_as_float(r[i]) + bias_m + __shfl_sync(0xffffffffu, bn, i);
+                            if (mvalid && c0 + i < ncols) dptr[(int64_t)(c0 + i) * p.ldd] = v;
+                        }
+                    } else {
+                        float rr[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) rr[i] = (mvalid && c0 + i < ncols) ? rptr[(int64_t)(c0 + i) * p.ldr] : 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float v = __uint_as_float(r[i]) + bias_m + __shfl_sync(0xffffffffu, bn, i) + rr[i];
+                            if (mvalid && c0 + i < ncols) dptr[(int64_t)(c0 + i) * p.ldd] = v;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int c0 = half * 32; c0 < ncols; c0 += 64) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int64_t n = (int64_t)n0 + c0 + i;
+                        if (mvalid && c0 + i < ncols) {
+                            float v = __uint_as_float(r[i]) + bias_m;
+                            if (p.bias_mode == 2) v += p.bias[n];
+                            v = act_fn(v, p.act);
+                            if (Rp) v += Rp[n * p.ldr + m];
+                            Dp[n * p.ldd + m] = v;
+                        }
+                    }
+                }
+            }
+            // every tcgen05.ld of this accumulator has completed: hand it back to the MMA issuer of the pair
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty0 + 8u * buf);
+        }
+    }
+
+    if (p.splits > 1) {
+        // ---- split-K reduction across the cluster: CTA (prank, split) owns the columns [split * bn / S, (split + 1) * bn / S) of its
+        //      128 rows and sums the partial tiles of the CTAs with the same pair rank in split order (deterministic)
+        tc_fence_before();
+        cluster_sync_all();
+        if (warp >= 2) {
+            int m0, n0, batch;
+            decode(pair, m0, n0, batch);
+            const int w8 = warp - 2;
+            const int64_t mrow = (int64_t)m0 + 4 * lane;
+            float* Dp = p.D + (int64_t)batch * p.d_batch_stride;
+            const float* Rp = p.residual ? p.residual + (int64_t)batch * p.r_batch_stride : nullptr;
+            float4 bm = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias_mode == 1) {
+                if (mrow + 0 < p.M) bm.x = p.bias[mrow + 0];
+                if (mrow + 1 < p.M) bm.y = p.bias[mrow + 1];
+                if (mrow + 2 < p.M) bm.z = p.bias[mrow + 2];
+                if (mrow + 3 < p.M) bm.w = p.bias[mrow + 3];
+            }
+            const uint32_t sred_local = smem_u32(smem);
+            uint32_t peer[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) peer[s] = s < p.splits ? dsmem_map(sred_local, prank + 2u * (uint32_t)s) : 0u;
+            const int ncols = (int)min((int64_t)p.bn, p.N - n0);
+            const int cbeg = (split * p.bn) / p.splits, cend = min(((split + 1) * p.bn) / p.splits, ncols);
+            const bool vec_ok = (mrow + 3 < p.M) && ((p.ldd & 3) == 0) && ((((uintptr_t)Dp) & 15) == 0) && ((m0 & 3) == 0);
+#pragma unroll 1
+            for (int c = cbeg + w8; c < cend; c += 8) {
+                const uint32_t off = (uint32_t)(c * BM + 4 * lane) * 4u;
+                float4 part[8];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) part[s] = s < p.splits ? dsmem_ld_f32x4(peer[s] + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) { v.x += part[s].x; v.y += part[s].y; v.z += part[s].z; v.w += part[s].w; }
+                const int64_t n = (int64_t)n0 + c;
+                const float bn = p.bias_mode == 2 ? p.bias[n] : 0.f;
+                v.x += bm.x + bn; v.y += bm.y + bn; v.z += bm.z + bn; v.w += bm.w + bn;
+                if (p.act) { v.x = act_fn(v.x, p.act); v.y = act_fn(v.y, p.act); v.z = act_fn(v.z, p.act); v.w = act_fn(v.w, p.act); }
+                float* dst = Dp + n * p.ldd + mrow;
+                if (vec_ok && (Rp == nullptr || (((p.ldr & 3) == 0) && ((((uintptr_t)Rp) & 15) == 0)))) {
+                    if (Rp) { const float4 rr = *(const float4*)(Rp + n * p.ldr + mrow); v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
+                    *(float4*)dst = v;
+                } else {
+                    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (mrow + u < p.M) dst[u] = vv[u] + (Rp ? Rp[n * p.ldr + mrow + u] : 0.f);
+                }
+            }
+        }
+    }
+    // nobody may exit while a peer can still read its shared memory (DSMEM reduce, the pair's MMAs) or signal its barriers
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+bool encode_rows(CUtensorMap* out, const void* ptr, int type, int64_t K, int64_t rows, int64_t ld_elems, int64_t b2, int64_t b2_stride, uint32_t box_rows) {
+    auto enc = b200_get_tensormap_encoder();
+    if (!enc) return false;
+    CUtensorMapDataType dt = type == GGML_TYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)b2, 1};
+    cuuint64_t strides[3] = {(cuuint64_t)(ld_elems * 2), (cuuint64_t)(b2_stride * 2), 0};
+    if (b2 == 1 || strides[1] == 0) strides[1] = strides[0] * dims[1];
+    strides[2] = strides[1] * dims[2];
+    cuuint32_t box[4] = {64, box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(out, dt, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int FMT>
+cudaError_t launch2(cudaStream_t s, unsigned ctas, unsigned splits, size_t smem, const CUtensorMap& ta, const CUtensorMap& tb, const G2Params& kp) {
+    static size_t configured[B200_MAX_DEVICES] = {};
+    int d = 0;
+    cudaGetDevice(&d);
+    if (configured[d] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc2<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+        if (e != cudaSuccess) return e;
+        configured[d] = 227 * 1024;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas, 1, splits);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    unsigned n = 0;
+    if (b200_pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = 2;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = splits;
+    ++n;
+    cfg.numAttrs = n;
+    cfg.attrs = attr;
+    return cudaLaunchKernelEx(&cfg, k_gemm_tc2<FMT>, ta, tb, kp);
+}
+
+// shared by the GEMM and the conv front end: fills the tile geometry for a chosen (bn, splits)
+bool fill_geometry(G2Params& kp, const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int nkb, int bn, int splits, unsigned* ctas, size_t* smem) {
+    const int sms = dev.sm_count > 0 ? dev.sm_count : 148;
+    kp.bn = bn;
+    kp.splits = splits;
+    kp.num_k_blocks = nkb;
+    kp.stage_bytes = A_STAGE_BYTES + (bn / 2) * BK_BYTES;
+    int stages = (int)((227 * 1024 - 4096) / kp.stage_bytes);
+    stages = std::min(stages, MAX_STAGES);
+    if (splits > 1) {
+        // the partial tile [bn][128] f32 reuses the ring
+        while ((size_t)stages * kp.stage_bytes < (size_t)bn * BM * 4) ++stages;
+        if ((size_t)stages * kp.stage_bytes + 2048 > 227 * 1024 - 2048 || stages > MAX_STAGES) return false;
+    }
+    if (stages < 3) return false;
+    kp.stages = stages;
+    int cols = 32;
+    while (cols < 2 * bn) cols <<= 1;
+    if (cols > 512) return false;
+    kp.tmem_cols = cols;
+    kp.acc_stride = cols / 2;
+    const int64_t tm = (M + 2 * BM - 1) / (2 * BM), tn = (N + bn - 1) / bn;
+    const int64_t total = tm * tn * batch;
+    if (total <= 0 || total > 0x3fffffff) return false;
+    kp.tiles_m = (int)tm; kp.tiles_n = (int)tn; kp.total_tiles = (int)total;
+    int64_t pairs = total;
+    if (splits == 1) pairs = std::min<int64_t>(total, sms / 2);
+    else if (pairs * 2 * splits > 65535 * 2) return false;
+    *ctas = (unsigned)(pairs * 2);
+    *smem = (size_t)stages * kp.stage_bytes + 1024;
+    return true;
+}
+
+}  // namespace
+
+// modelled cycles of the pair kernel for (bn, splits); used by the plan choosers of gemm_tc.cu to pick between the kernels
+double b200_gemm_tc2_model(const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int nkb, int bn, int splits) {
+    const int sms = dev.sm_count > 0 ? dev.sm_count : 148;
+    const int64_t tm = (M + 255) / 256, tn = (N + bn - 1) / bn;
+    const int64_t tiles = tm * tn * batch;
+    const double kb = (double)((nkb + splits - 1) / splits);
+    const int64_t ctas = splits == 1 ? std::min<int64_t>(tiles, sms / 2) * 2 : tiles * 2 * splits;
+    const double active = (double)std::min<int64_t>(ctas, sms);
+    const double ingest = std::min(56.0, 6000.0 / active);                 // B/clk per SM: per-SM path vs. the chip-wide L2 cap
+    const double bytes = (128.0 + bn / 2.0) * 128.0;
+    const double kb_cycles = std::max(2.0 * bn, bytes / ingest);           // cta_group::2: bn / 2 clk per K = 16 MMA, four per k-block
+    const double epi = 20.0 * bn;                                          // eight epilogue warps
+    if (splits == 1) {
+        const double per_pair = (double)((tiles + (ctas / 2) - 1) / (ctas / 2));
+        // tiles of one pair overlap their epilogues with the next main loop; the last epilogue is exposed
+        return 4000.0 + per_pair * std::max(kb * kb_cycles, epi) + epi + (per_pair > 1 ? 0.0 : 0.0);
+    }
+    const double waves = (double)((ctas + sms - 1) / sms);
+    return waves * (4000.0 + kb * kb_cycles + 6.0 * bn + 2500.0 + 50.0 * bn / splits);
+}
+
+// returns 1 when launched, -1 when the problem is outside this kernel's envelope.  bn / splits <= 0: choose here.
+int b200_launch_gemm_tc2(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g, int bn, int splits) {
+    if (g.M <= 0 || g.N <= 0 || g.batch <= 0 || g.K <= 0) return -1;
+    if (g.type != GGML_TYPE_F16 && g.type != GGML_TYPE_BF16) return -1;
+    if (((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15) || (g.lda * 2) % 16 || (g.ldb * 2) % 16) return -1;
+    if ((g.a_batch_stride * 2) % 16 || (g.b_batch_stride * 2) % 16) return -1;
+    if (bn < 16 || bn > 256 || (bn & 15) || splits < 1 || splits > 4) return -1;
+    const int nkb = (int)((g.K + 63) / 64);
+    if (splits > nkb) return -1;
+    G2Params kp;
+    memset(&kp, 0, sizeof(kp));
+    unsigned ctas = 0;
+    size_t smem = 0;
+    if (!fill_geometry(kp, dev, g.M, g.N, g.batch, nkb, bn, splits, &ctas, &smem)) return -1;
+    CUtensorMap ta, tb;
+    const int64_t a_batches = (g.batch + g.a_bcast - 1) / g.a_bcast;
+    if (!encode_rows(&ta, g.A, g.type, g.K, g.M, g.lda, a_batches, g.a_batch_stride, BM)) return -1;
+    if (!encode_rows(&tb, g.B, g.type, g.K, g.N, g.ldb, g.batch, g.b_batch_stride, (uint32_t)(bn / 2))) return -1;
+    kp.D = g.D; kp.ldd = g.ldd; kp.d_batch_stride = g.d_batch_stride;
+    kp.M = g.M; kp.N = g.N;
+    kp.ne12 = (int)g.batch; kp.r2 = (int)g.a_bcast;
+    kp.bias = g.bias; kp.bias_mode = g.bias ? g.bias_mode : 0;
+    kp.residual = g.residual; kp.ldr = g.ldr; kp.r_batch_stride = g.d_batch_stride;
+    kp.act = g.act;
+    cudaError_t e = g.type == GGML_TYPE_F16 ? launch2<0>(s, ctas, (unsigned)splits, smem, ta, tb, kp) : launch2<1>(s, ctas, (unsigned)splits, smem, ta, tb, kp);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[ggml-b200] CTA-pair GEMM launch failed: %s\n", cudaGetErrorString(e));
+        cudaGetLastError();
+        return -1;
+    }
+    return 1;
+}
+
+int b200_launch_conv_tc2(cudaStream_t s, const b200_device_info& dev, const b200_conv_args& c, int bn, int splits) {
+    if (!b200_conv_tc_supported(c.N, c.H, c.W, c.C, c.OC, c.KH, c.KW, 1, 1, c.pad, c.pad, c.dil, c.dil)) return -1;
+    if (((uintptr_t)c.x_nhwc & 15) || ((uintptr_t)c.w_packed & 15)) return -1;
+    if (bn < 16 || bn > 256 || (bn & 15) || splits < 1 || splits > 4) return -1;
+    const int64_t M = c.H * c.W, K = (int64_t)c.KH * c.KW * c.C;
+    // a pair tile is 256 consecutive output pixels of one image: the image must split into whole 128-pixel boxes
+    if (M % 128 != 0) return -1;
+    const int nkb = (int)(K / 64);
+    if (splits > nkb) return -1;
+    G2Params kp;
+    memset(&kp, 0, sizeof(kp));
+    unsigned ctas = 0;
+    size_t smem = 0;
+    if (!fill_geometry(kp, dev, M, c.OC, c.N, nkb, bn, splits, &ctas, &smem)) return -1;
+    const uint32_t BW = (uint32_t)(c.W < 128 ? c.W : 128), BH = 128 / BW;
+    CUtensorMap ta, tb;
+    {
+        auto enc = b200_get_tensormap_encoder();
+        if (!enc) return -1;
+        cuuint64_t dims[4] = {(cuuint64_t)c.C, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.N};
+        cuuint64_t strides[3] = {(cuuint64_t)c.C * 2, (cuuint64_t)c.W * c.C * 2, (cuuint64_t)c.H * c.W * c.C * 2};
+        cuuint32_t box[4] = {64, BW, BH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (enc(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(c.x_nhwc), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return -1;
+    }
+    if (!encode_rows(&tb, c.w_packed, GGML_TYPE_F16, K, c.OC, K, 1, 0, (uint32_t)(bn / 2))) return -1;
+    kp.D = c.D; kp.ldd = M; kp.d_batch_stride = c.OC * M;
+    kp.M = M; kp.N = c.OC;
+    kp.ne12 = (int)c.N; kp.r2 = 1;
+    kp.bias = c.bias; kp.bias_mode = c.bias ? 2 : 0;
+    kp.residual = c.residual; kp.ldr = M; kp.r_batch_stride = c.OC * M;
+    kp.conv = 1; kp.conv_W = (int)c.W; kp.conv_KW = c.KW; kp.conv_cblocks = (int)(c.C / 64); kp.conv_pad = c.pad; kp.conv_dil = c.dil;
+    cudaError_t e = launch2<0>(s, ctas, (unsigned)splits, smem, ta, tb, kp);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[ggml-b200] CTA-pair conv launch failed: %s\n", cudaGetErrorString(e));
+        cudaGetLastError();
+        return -1;
+    }
+    return 1;
+}

@@ -17,6 +17,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
+#include <map>
 #include <memory>
 #include <string>
 #include <thread>
@@ -238,6 +240,7 @@ struct sdh_model {
     int n_threads     = 1;
     double last_flops = 0;
     int last_nodes    = 0;
+    std::map<std::string, ggml_tensor*> params;   // parameter tensors by checkpoint name (resident on the backend)
 };
 
 namespace {
@@ -386,7 +389,7 @@ sdh_model* sdh_model_create(const char* device, const char* arch, const char* wt
         m->vae->get_param_tensors(tensors);
         m->vae->set_flash_attention_enabled(fa);
         m->vae->set_conv2d_direct_enabled(direct);
-    } else if (a == "flux_schnell" || a == "flux_tiny") {
+    } else if (a == "flux_schnell" || a == "flux_tiny" || a == "flux_1x1") {
         m->arch    = ARCH_FLUX;
         m->version = VERSION_FLUX;
         const std::string prefix = "model.diffusion_model";
@@ -394,7 +397,8 @@ sdh_model* sdh_model_create(const char* device, const char* arch, const char* wt
         {
             // depth is detected from weight names (flux.hpp detect_from_weights): FLUX.1 has 19 double + 38 single blocks, the tiny
             // variant declares 2 + 2
-            const int n_double = a == "flux_tiny" ? 2 : 19, n_single = a == "flux_tiny" ? 2 : 38;
+            // flux_1x1: ONE double-stream + ONE single-stream block at the full FLUX.1 width (hidden 3072, 24 heads): full-size block parity
+            const int n_double = a == "flux_tiny" ? 2 : (a == "flux_1x1" ? 1 : 19), n_single = a == "flux_tiny" ? 2 : (a == "flux_1x1" ? 1 : 38);
             int64_t ne2[2] = {3072, 3072};
             for (int i = 0; i < n_double; ++i) {
                 std::string n1 = prefix + ".double_blocks." + std::to_string(i) + ".img_attn.proj.weight";
@@ -488,6 +492,7 @@ sdh_model* sdh_model_create(const char* device, const char* arch, const char* wt
         fail("weight allocation failed");
         return nullptr;
     }
+    m->params = tensors;
     return m.release();
 }
 
@@ -634,6 +639,135 @@ int sdh_model_dump_graph(sdh_model* m, const sdh_tensor* x, const sdh_tensor* ti
     return m->last_nodes;
 }
 
+// In-place update of a model weight THROUGH A GRAPH on the model's backend -- what the reference's LoRA apply does
+// (src/lora.hpp:934-937: ggml_add_inplace(model_tensor, updown) computed on the runtime backend): w += value for the first parameter whose
+// name contains `name_substr` and has `n_dims` dimensions.  A backend that keeps derived copies of weights must notice the write.
+int sdh_model_add_to_weight(sdh_model* m, const char* name_substr, int n_dims, float value) {
+    if (!m || !name_substr) return fail("null argument");
+    ggml_tensor* w = nullptr;
+    for (auto& kv : m->params)
+        if (kv.first.find(name_substr) != std::string::npos && ggml_n_dims(kv.second) == n_dims) { w = kv.second; break; }
+    if (!w) return fail(std::string("no parameter matches ") + name_substr);
+    ggml_init_params ip = {ggml_tensor_overhead() * 8 + ggml_graph_overhead_custom(16, false), nullptr, true};
+    ggml_context* ctx = ggml_init(ip);
+    if (!ctx) return fail("ggml_init failed");
+    ggml_tensor* delta = ggml_new_tensor_4d(ctx, GGML_TYPE_F32, w->ne[0], w->ne[1], w->ne[2], w->ne[3]);
+    ggml_tensor* r = ggml_add_inplace(ctx, w, delta);
+    ggml_cgraph* gf = ggml_new_graph_custom(ctx, 16, false);
+    ggml_build_forward_expand(gf, r);
+    int rc = 0;
+    if (!ggml_backend_supports_op(m->backend, r)) rc = fail("in-place ADD into this weight type is not supported by the device");
+    ggml_backend_buffer_t buf = rc == 0 ? ggml_backend_alloc_ctx_tensors(ctx, m->backend) : nullptr;
+    if (rc == 0 && !buf) rc = fail("buffer allocation failed");
+    if (buf) {
+        std::vector<float> v((size_t)ggml_nelements(delta), value);
+        ggml_backend_tensor_set(delta, v.data(), 0, v.size() * 4);
+        if (ggml_backend_graph_compute(m->backend, gf) != GGML_STATUS_SUCCESS) rc = fail("graph_compute failed");
+        ggml_backend_synchronize(m->backend);
+        ggml_backend_buffer_free(buf);
+    }
+    const int n = (int)std::min<int64_t>(ggml_nelements(w), 0x7fffffff);
+    ggml_free(ctx);
+    return rc == 0 ? n : rc;
+}
+
+// ---------------------------------------------------------------- graph export for the f64 arbiter (oracle/graph_f64.py)
+// The graph the reference builds for these inputs, with everything a host-side interpreter needs: per tensor op / type / ne / nb /
+// op_params / source ids / view root + offset, and the DATA of every leaf (weights read back from the backend buffer and converted to
+// f32 -- F16 / BF16 / Q8_0 values are exactly representable; inputs taken from the runner's pending host copies).
+namespace {
+struct RunnerPeek : GGMLRunner {
+    static std::map<ggml_tensor*, const void*> GGMLRunner::*inputs() { return &RunnerPeek::backend_tensor_data_map; }
+};
+GGMLRunner* runner_of(sdh_model* m) {
+    switch (m->arch) {
+        case ARCH_UNET: return m->unet.get();
+        case ARCH_VAE: return m->vae.get();
+        case ARCH_FLUX: return m->flux.get();
+        case ARCH_MMDIT: return m->mmdit.get();
+        case ARCH_WAN: return m->wan.get();
+        case ARCH_CLIP: return m->clip.get();
+        case ARCH_WANVAE: return m->wan_vae.get();
+    }
+    return nullptr;
+}
+}  // namespace
+
+int sdh_model_export_graph(sdh_model* m, const sdh_tensor* x, const sdh_tensor* timesteps, const sdh_tensor* context, const sdh_tensor* y,
+                           const char* path_prefix) {
+    if (!m || !x || !path_prefix) return fail("null argument");
+    auto xs = to_sd_nd(x, 4);
+    auto ts = to_sd_nd(timesteps, 1);
+    auto cs = to_sd_nd(context, 3);
+    auto ys = to_sd_nd(y, 2);
+    ggml_cgraph* gf = build_only(m, xs, ts, cs, ys);
+    if (!gf) return fail("graph build failed");
+    GGMLRunner* runner = runner_of(m);
+    const auto& pending = runner->*RunnerPeek::inputs();
+    std::vector<ggml_tensor*> order;
+    std::map<const ggml_tensor*, int> id;
+    std::function<void(ggml_tensor*)> visit = [&](ggml_tensor* t) {
+        if (!t || id.count(t)) return;
+        if (t->view_src) visit(t->view_src);
+        for (int s = 0; s < GGML_MAX_SRC; ++s) visit(t->src[s]);
+        id[t] = (int)order.size();
+        order.push_back(t);
+    };
+    const int n = ggml_graph_n_nodes(gf);
+    for (int i = 0; i < n; ++i) visit(ggml_graph_node(gf, i));
+    std::string jpath = std::string(path_prefix) + ".json", bpath = std::string(path_prefix) + ".bin";
+    FILE* fj = fopen(jpath.c_str(), "w");
+    FILE* fb = fopen(bpath.c_str(), "wb");
+    if (!fj || !fb) { if (fj) fclose(fj); if (fb) fclose(fb); return fail("cannot open export files"); }
+    fprintf(fj, "{\"tensors\":[\n");
+    size_t off = 0;
+    std::vector<float> f32;
+    std::vector<uint8_t> raw;
+    for (size_t k = 0; k < order.size(); ++k) {
+        ggml_tensor* t = order[k];
+        long long data_off = -1;
+        if (t->op == GGML_OP_NONE && !t->view_src) {
+            const int64_t ne = ggml_nelements(t);
+            f32.assign((size_t)ne, 0.f);
+            auto it = pending.find(t);
+            const void* src = nullptr;
+            if (it != pending.end()) src = it->second;
+            else if (t->buffer) { raw.resize(ggml_nbytes(t)); ggml_backend_tensor_get(t, raw.data(), 0, raw.size()); src = raw.data(); }
+            if (src) {
+                if (t->type == GGML_TYPE_F32) memcpy(f32.data(), src, (size_t)ne * 4);
+                else if (t->type == GGML_TYPE_I32) { const int32_t* p = (const int32_t*)src; for (int64_t i = 0; i < ne; ++i) f32[i] = (float)p[i]; }
+                else {
+                    const ggml_type_traits* tt = ggml_get_type_traits(t->type);
+                    if (!tt->to_float) { fclose(fj); fclose(fb); return fail("leaf type without to_float"); }
+                    tt->to_float(src, f32.data(), ne);
+                }
+                data_off = (long long)off;
+                fwrite(f32.data(), 4, (size_t)ne, fb);
+                off += (size_t)ne;
+            }
+        }
+        fprintf(fj, "{\"id\":%d,\"op\":\"%s\",\"uop\":\"%s\",\"type\":\"%s\",\"ne\":[%lld,%lld,%lld,%lld],\"nb\":[%zu,%zu,%zu,%zu],\"params\":[", (int)k,
+                ggml_op_name(t->op), t->op == GGML_OP_UNARY ? ggml_unary_op_name(ggml_get_unary_op(t)) : "", ggml_type_name(t->type), (long long)t->ne[0],
+                (long long)t->ne[1], (long long)t->ne[2], (long long)t->ne[3], t->nb[0], t->nb[1], t->nb[2], t->nb[3]);
+        for (int q = 0; q < 16; ++q) fprintf(fj, "%d%s", t->op_params[q], q == 15 ? "" : ",");
+        fprintf(fj, "],\"src\":[");
+        bool first = true;
+        for (int s = 0; s < GGML_MAX_SRC; ++s) {
+            if (!t->src[s]) { if (s < 4) { fprintf(fj, "%s-1", first ? "" : ","); first = false; } continue; }
+            fprintf(fj, "%s%d", first ? "" : ",", id[t->src[s]]);
+            first = false;
+        }
+        fprintf(fj, "],\"view_src\":%d,\"view_offs\":%zu,\"data\":%lld,\"name\":\"%s\",\"flags\":%d}%s\n", t->view_src ? id[t->view_src] : -1, t->view_offs, data_off,
+                t->name, t->flags, k + 1 == order.size() ? "" : ",");
+    }
+    fprintf(fj, "],\n\"nodes\":[");
+    for (int i = 0; i < n; ++i) fprintf(fj, "%d%s", id[ggml_graph_node(gf, i)], i + 1 == n ? "" : ",");
+    fprintf(fj, "],\n\"result\":%d}\n", id[ggml_graph_node(gf, n - 1)]);
+    fclose(fj);
+    fclose(fb);
+    return n;
+}
+
 double sdh_model_last_graph_flops(const sdh_model* m) { return m->last_flops; }
 int sdh_model_last_graph_nodes(const sdh_model* m) { return m->last_nodes; }
 
@@ -685,12 +819,13 @@ int sdh_model_backend_stats(sdh_model* m, double* out, int n) {
     typedef int (*get_stats_t)(ggml_backend_t, void*);
     get_stats_t fn = reg ? (get_stats_t)ggml_backend_reg_get_proc_address(reg, "ggml_backend_b200_get_stats") : nullptr;
     if (!fn) return fail("backend has no ggml_backend_b200_get_stats");
-    struct { uint64_t graphs, launches, nodes, fused; double last_ms, total_ms; uint64_t tc, reserved[8]; } s;
+    struct { uint64_t graphs, launches, nodes, fused; double last_ms, total_ms; uint64_t tc, reserved[8], ext[16]; } s;
     if (fn(m->backend, &s) != 0) return fail("get_stats failed");
-    double v[16] = {(double)s.graphs, (double)s.launches, (double)s.nodes, (double)s.fused, s.last_ms, s.total_ms, (double)s.tc,
+    double v[32] = {(double)s.graphs, (double)s.launches, (double)s.nodes, (double)s.fused, s.last_ms, s.total_ms, (double)s.tc,
                     (double)s.reserved[0], (double)s.reserved[1], (double)s.reserved[2], (double)s.reserved[3], (double)s.reserved[4],
                     (double)s.reserved[5], (double)s.reserved[6], (double)s.reserved[7], 0};
-    for (int i = 0; i < n && i < 16; ++i) out[i] = v[i];
+    for (int i = 0; i < 16; ++i) v[16 + i] = (double)s.ext[i];
+    for (int i = 0; i < n && i < 32; ++i) out[i] = v[i];
     return 0;
 }
 

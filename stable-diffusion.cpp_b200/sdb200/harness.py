@@ -41,7 +41,9 @@ def _as_sdh(a: np.ndarray | None):
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_size_t, C.c_void_p)
 
 STAT_KEYS = ("graphs", "kernel_launches", "nodes_executed", "fused_nodes", "last_graph_ms", "total_graph_ms", "tc_gemm_launches",
-             "tc_gemm_flops", "tc_gemm_us", "fused_attn_launches", "cuda_graph_replays", "implicit_convs", "q_read_in_place", "gemv_launches", "rope_launches")
+             "tc_gemm_flops", "tc_gemm_us", "fused_attn_launches", "cuda_graph_replays", "implicit_convs", "q_read_in_place", "gemv_launches", "rope_launches", "_unused",
+             "gemm_ref_launches", "host_us", "weight_write_graphs", "per_graph_filter_packs", "persistent_gemm_launches", "cta2_gemm_launches",
+             "derived_weight_bytes", "unfused_attention")
 
 
 class Harness:
@@ -69,6 +71,8 @@ class Harness:
             lib.sdh_model_out_shape.argtypes = [C.c_void_p, P, C.POINTER(C.c_int64)]
             lib.sdh_model_forward.argtypes = [C.c_void_p, P, P, P, P, P, C.POINTER(C.c_double)]
             lib.sdh_model_dump_graph.argtypes = [C.c_void_p, P, P, P, P, C.c_char_p]
+            lib.sdh_model_add_to_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_float]
+            lib.sdh_model_export_graph.argtypes = [C.c_void_p, P, P, P, P, C.c_char_p]
             lib.sdh_model_last_graph_flops.argtypes = [C.c_void_p]
             lib.sdh_model_last_graph_flops.restype = C.c_double
             lib.sdh_model_last_graph_nodes.argtypes = [C.c_void_p]
@@ -213,6 +217,21 @@ class Model:
             raise RuntimeError(self.h.last_error())
         return n, self.lib.sdh_model_last_graph_flops(self.ptr)
 
+    def add_to_weight(self, name_substr: str, n_dims: int, value: float) -> int:
+        """w += value through a graph on the model's backend (the reference's LoRA-apply pattern); returns the element count."""
+        n = self.lib.sdh_model_add_to_weight(self.ptr, name_substr.encode(), n_dims, value)
+        if n < 0:
+            raise RuntimeError(self.h.last_error())
+        return n
+
+    def export_graph(self, prefix, x, t=None, ctx=None, y=None) -> int:
+        """Write <prefix>.json / <prefix>.bin (graph structure + leaf data) for oracle/graph_f64.py; returns the node count."""
+        (px, pt, pc, py), keep = self._args(x, t, ctx, y)
+        n = self.lib.sdh_model_export_graph(self.ptr, px, pt, pc, py, str(prefix).encode())
+        if n < 0:
+            raise RuntimeError(self.h.last_error())
+        return n
+
     def vae_decode(self, z, tile_size: int = 0, overlap: float = 0.5):
         """Reference VAE::decode (optionally with its host-side tiling) -> (image [N,3,8H,8W] in [0,1], wall_ms)."""
         sz, keep = _as_sdh(z)
@@ -242,8 +261,8 @@ class Model:
 
     def stats(self) -> dict:
         """Counters of the B200 backend instance behind this model (raises for other backends)."""
-        v = (C.c_double * 16)()
-        if self.lib.sdh_model_backend_stats(self.ptr, v, 16) != 0:
+        v = (C.c_double * 32)()
+        if self.lib.sdh_model_backend_stats(self.ptr, v, 32) != 0:
             raise RuntimeError(self.h.last_error())
         return {k: v[i] for i, k in enumerate(STAT_KEYS)}
 

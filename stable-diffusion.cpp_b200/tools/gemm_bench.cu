@@ -5,11 +5,13 @@
 #include <cuda_fp16.h>
 #include <vector>
 #include <cstring>
+#include <cmath>
 
 struct Shape { const char* name; int64_t M, N, K, batch; };
 
 int main(int argc, char** argv) {
     int reps = argc > 1 ? atoi(argv[1]) : 50;
+    setenv("GGML_B200_GEMM2", "0", 1);      // the one-CTA kernel is the reference of the comparisons below
     cudaDeviceProp p;
     cudaGetDeviceProperties(&p, 0);
     b200_device_info dev{};
@@ -21,6 +23,8 @@ int main(int argc, char** argv) {
         {"linear qkv L1024 C640", 640, 1024, 640, 1}, {"linear geglu L1024", 5120, 1024, 640, 1}, {"linear ff-out L1024", 640, 1024, 2560, 1},
         {"linear qkv L256 C1280", 1280, 256, 1280, 1}, {"linear geglu L256", 10240, 256, 1280, 1}, {"linear ff-out L256", 1280, 256, 5120, 1},
         {"linear kv ctx77 C1280", 1280, 77, 768, 1}, {"linear kv ctx77 C320", 320, 77, 768, 1}, {"time emb", 1280, 1, 320, 1}, {"big square", 4096, 4096, 4096, 1},
+        {"flux qkv 4352x9216x3072", 9216, 4352, 3072, 1}, {"flux linear2 4352x3072x15360", 3072, 4352, 15360, 1}, {"vae conv 512^2 128->128 (as gemm)", 262144, 128, 1152, 1},
+        {"vae conv 256^2 256->256 (as gemm)", 65536, 256, 2304, 1}, {"sd15 conv 64x64 320 x2 (M 8192)", 8192, 320, 2880, 1},
     };
     size_t maxA = 0, maxB = 0, maxD = 0;
     for (auto& s : shapes) { maxA = std::max(maxA, (size_t)s.M * s.K); maxB = std::max(maxB, (size_t)s.N * s.K); maxD = std::max(maxD, (size_t)s.M * s.N); }
@@ -54,25 +58,35 @@ int main(int argc, char** argv) {
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         double us = ms * 1e3 / reps;
         printf("%-34s %8lld %8lld %8lld | %9.2f %9.1f", s.name, (long long)s.M, (long long)s.N, (long long)s.K, us, 2.0 * s.M * s.N * s.K / us * 1e-6);
-        // experimental persistent variant (gemm_tc_persist.cu) on the same problem, with a checksum comparison against the regular kernel
-        if (getenv("GEMM_BENCH_PERSISTENT")) {
+        // CTA-pair kernel (gemm_tc2.cu) on the same problem: a sweep over (tile N, split-K), each checked element by element against the
+        // one-CTA kernel's result
+        if (getenv("GEMM_BENCH_PAIR")) {
             std::vector<float> ref((size_t)s.M * s.N), got((size_t)s.M * s.N);
             cudaMemcpy(ref.data(), D, ref.size() * 4, cudaMemcpyDeviceToHost);
-            cudaMemsetAsync(D, 0xff, ref.size() * 4, st);
-            int ok = b200_launch_gemm_tc_persistent(st, dev, g);
-            if (ok > 0) {
-                cudaStreamSynchronize(st);
-                cudaMemcpy(got.data(), D, got.size() * 4, cudaMemcpyDeviceToHost);
-                size_t bad = 0;
-                for (size_t i = 0; i < ref.size(); ++i) bad += ref[i] != got[i];
-                cudaEventRecord(e0, st);
-                for (int i = 0; i < reps; ++i) b200_launch_gemm_tc_persistent(st, dev, g);
-                cudaEventRecord(e1, st);
-                cudaEventSynchronize(e1);
-                cudaEventElapsedTime(&ms, e0, e1);
-                printf(" | persistent %8.2f us, %zu mismatching elements", ms * 1e3 / reps, bad);
-            } else {
-                printf(" | persistent n/a");
+            const int bns[] = {256, 192, 160, 128, 96, 64};
+            printf("\n");
+            for (int bn : bns) {
+                if (bn > 64 && s.N <= bn / 2) continue;
+                for (int sp = 1; sp <= 4; ++sp) {
+                    const int64_t tiles = ((s.M + 255) / 256) * ((s.N + bn - 1) / bn);
+                    if (sp > 1 && tiles * 2 * sp > 148) continue;
+                    cudaMemsetAsync(D, 0xff, ref.size() * 4, st);
+                    int ok = b200_launch_gemm_tc2(st, dev, g, bn, sp);
+                    if (ok <= 0) continue;
+                    if (cudaStreamSynchronize(st) != cudaSuccess) { printf("   pair bn %d splits %d: FAILED %s\n", bn, sp, cudaGetErrorString(cudaGetLastError())); return 1; }
+                    cudaMemcpy(got.data(), D, got.size() * 4, cudaMemcpyDeviceToHost);
+                    size_t bad = 0; double maxd = 0;
+                    for (size_t i = 0; i < ref.size(); ++i) { if (ref[i] != got[i]) { ++bad; double d = fabs((double)ref[i] - got[i]); if (!(d <= maxd)) maxd = d; } }
+                    cudaEventRecord(e0, st);
+                    for (int i = 0; i < reps; ++i) b200_launch_gemm_tc2(st, dev, g, bn, sp);
+                    cudaEventRecord(e1, st);
+                    cudaEventSynchronize(e1);
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    const int nkb = (int)((s.K + 63) / 64);
+                    printf("   pair bn %3d splits %d: %8.2f us %7.1f TFLOP/s  model %7.2f us  mismatches %zu (max abs %.3g)\n", bn, sp, ms * 1e3 / reps,
+                           2.0 * s.M * s.N * s.K / (ms * 1e3 / reps) * 1e-6, b200_gemm_tc2_model(dev, s.M, s.N, 1, nkb, bn, sp) / 1965.0, bad, maxd);
+                    fflush(stdout);
+                }
             }
         }
         // phase timestamps of CTA (0,0,0): start, setup done, first k-block landed, last k-block landed, accumulator ready, epilogue done, all warps joined, tmem freed

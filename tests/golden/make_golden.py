@@ -11,6 +11,9 @@
   cpu_models.npz           reference CPU backend outputs of whole synthetic-weight models (unet_tiny fa/non-fa,
                            vae_decoder on an 8x8 latent, scheduler-driven 3-step sample)
   cpu_wan_vae.npz          (`make_golden.py wan_vae`) Wan causal-3D VAE decoder, one latent frame
+  truth_f64.npz            (`make_golden.py truth`) float64 evaluation (oracle/graph_f64.py) of the graphs the reference builds for unet_tiny and for
+                           the SD1.5 UNet at 64x64 (default attention graph): the arbiter of the whole-model parity tests, plus the
+                           reference CPU backend's distance to it (cpu_rel_*)
   cpu_models_dit.npz       (`make_golden.py dit`) the same for the larger architectures of SURVEY.md 8a: SD1.5 UNet 64x64 (default graph),
                            SDXL UNet 32x32, flux_tiny (bf16), SD3-medium MMDiT 32x32 (f16), Wan2.1-1.3B DiT (q8_0, 3x16x16 latent)
 """
@@ -151,8 +154,34 @@ def main_wan_vae():
     print("wan_vae_1frame", out.shape, float(out.std()))
 
 
+def main_truth():
+    """truth_f64.npz: what the graph evaluates to in exact (float64, no intermediate rounding) arithmetic, and how far the reference CPU
+    backend is from it.  SD1.5 at 64x64 takes ~2 min of numpy and ~3 GB."""
+    import tempfile
+    from sdb200 import Harness
+    from oracle.cpu_ref import load_cpu_oracle
+    from oracle.graph_f64 import evaluate
+    h = Harness()
+    load_cpu_oracle(h)
+    out = {}
+    for key, arch, shape in (("unet_tiny", "unet_tiny", (1, 4, 16, 16)), ("sd15_unet", "sd15_unet", (1, 4, 64, 64))):
+        x = h.randn(42, shape); ctx = h.randn(43, (1, 77, 768)); t = np.array([999.0], np.float32)
+        m = h.model("CPU", arch, "f16", 0, 1234, 8)
+        cpu, _ = m.forward(x, t, ctx)
+        with tempfile.TemporaryDirectory() as d:
+            m.export_graph(Path(d) / "g", x, t, ctx)
+            m.close()
+            truth = evaluate(Path(d) / "g").reshape(cpu.shape)
+        out[key] = truth
+        out["cpu_rel_" + key] = np.float64(np.linalg.norm(cpu.astype(np.float64) - truth) / np.linalg.norm(truth))
+        print(key, truth.shape, "cpu vs truth rel_l2", float(out["cpu_rel_" + key]), flush=True)
+    np.savez_compressed(HERE / "truth_f64.npz", **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "dit":
+    if len(sys.argv) > 1 and sys.argv[1] == "truth":
+        main_truth()
+    elif len(sys.argv) > 1 and sys.argv[1] == "dit":
         main_dit()
     elif len(sys.argv) > 1 and sys.argv[1] == "wan_vae":
         main_wan_vae()

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 GROUPS = {
     "elementwise": "ADD,SUB,MUL,DIV,SCALE,CLAMP,SQR,SQRT,SIN,COS,LOG,LEAKY_RELU,SILU,GELU,GELU_QUICK,RELU,SIGMOID,TANH,EXP,NEG,ABS,GELU_ERF,HARDSWISH,HARDSIGMOID,STEP,SGN,ELU",
-    "movement": "CPY,CONT,DUP,CONCAT,REPEAT,PAD,UPSCALE,TIMESTEP_EMBEDDING,GET_ROWS,ARANGE,SUM_ROWS,MEAN,IM2COL",
+    "movement": "CPY,CONT,DUP,CONCAT,REPEAT,PAD,UPSCALE,TIMESTEP_EMBEDDING,GET_ROWS,ARANGE,SUM_ROWS,MEAN,IM2COL,IM2COL_3D",
     "norms": "GROUP_NORM,NORM,RMS_NORM,L2_NORM,SOFT_MAX",
     "mul_mat": "MUL_MAT",
     "flash_attn": "FLASH_ATTN_EXT",

@@ -1,0 +1,165 @@
+"""GPU: parity AT THE CONFIGURATIONS THE NUMBERS ARE QUOTED ON (BASELINE.json configs 2-4), the float64 arbiter, the no-fallback
+assertion and the weight-write (LoRA apply) invalidation rule.
+
+Every comparison is the reference's own graph builder on both backends with byte-identical synthetic weights and inputs
+(SURVEY.md 8c).  `truth` is the float64 evaluation of the very same graph (oracle/graph_f64.py, fixture tests/golden/truth_f64.npz):
+the CPU oracle itself sits ~1e-3 away from it (f16 rounding of the contraction operands), which is why GPU-vs-CPU cannot be asked to be
+below ~1.4e-3 -- two independent roundings of that size -- while each backend on its own is at 1e-3 from the exact value."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def no_fallback(m):
+    """Every contraction of the forward(s) so far ran on the tcgen05 kernels: the CUDA-core reference GEMM never launched."""
+    st = m.stats()
+    assert st["gemm_ref_launches"] == 0, f"{int(st['gemm_ref_launches'])} CUDA-core GEMM launches on a model path"
+    return st
+
+
+# ------------------------------------------------------------------------------------------------ arbiter
+@pytest.mark.parametrize("key,arch,shape", [("unet_tiny", "unet_tiny", (1, 4, 16, 16)), ("sd15_unet", "sd15_unet", (1, 4, 64, 64))])
+def test_gpu_is_as_close_to_float64_truth_as_the_cpu_oracle(b200, key, arch, shape):
+    """|gpu - truth| <= 1.15 |cpu - truth| + 1e-4 on the reference's default graph (north_star: 1e-3 relative fp16 tolerance, measured
+    against the exact value of the graph), for both of our graph variants' shared kernels."""
+    h, dev = b200
+    gold = np.load(GOLD / "truth_f64.npz")
+    truth, cpu_rel = gold[key], float(gold["cpu_rel_" + key])
+    x = h.randn(42, shape); ctx = h.randn(43, (1, 77, 768)); t = np.array([999.0], np.float32)
+    m = h.model(dev, arch, "f16", 0, 1234, 0)
+    ours, _ = m.forward(x, t, ctx)
+    no_fallback(m)
+    m.close()
+    r = rel(ours, truth)
+    print(f"{key}: gpu vs truth {r:.3e}, cpu vs truth {cpu_rel:.3e}")
+    assert r <= 1.15 * cpu_rel + 1e-4, f"gpu vs f64 truth {r:.3e}, cpu oracle vs truth {cpu_rel:.3e}"
+    assert r < 1.3e-3
+
+
+def test_live_cpu_oracle_matches_its_committed_distance_to_truth(b200):
+    """The fixture's cpu_rel was produced by the same CPU backend build that runs here: re-derive it live for unet_tiny."""
+    h, dev = b200
+    gold = np.load(GOLD / "truth_f64.npz")
+    x = h.randn(42, (1, 4, 16, 16)); ctx = h.randn(43, (1, 77, 768)); t = np.array([999.0], np.float32)
+    m = h.model("CPU", "unet_tiny", "f16", 0, 1234, 0)
+    cpu, _ = m.forward(x, t, ctx)
+    m.close()
+    assert abs(rel(cpu, gold["unet_tiny"]) - float(gold["cpu_rel_unet_tiny"])) < 3e-4
+
+
+# ------------------------------------------------------------------------------------------------ config-size parity
+def test_vae_decode_512_vs_live_cpu(b200):
+    """BASELINE metric, second half: AutoEncoderKL decode 64x64x4 -> 512x512x3 (the size bench.py times), against the live CPU oracle."""
+    h, dev = b200
+    z = h.randn(45, (1, 4, 64, 64))
+    m = h.model(dev, "vae_decoder", "f16", 0, 1234, 0)
+    ours, _ = m.forward(z)
+    st = no_fallback(m)
+    m.close()
+    m = h.model("CPU", "vae_decoder", "f16", 0, 1234, 0)
+    cpu, _ = m.forward(z)
+    m.close()
+    assert ours.shape == (1, 3, 512, 512) and np.isfinite(ours).all()
+    r = rel(ours, cpu)
+    print(f"vae 512: rel_l2 {r:.3e}, unfused attention executions {int(st['unfused_attention'])}")
+    assert r < 2e-3, f"rel_l2 {r:.2e}"
+
+
+def test_sdxl_unet_128_bf16_vs_live_cpu(b200):
+    """BASELINE config 3 at its quoted size: SDXL UNet, 128x128x4 latent (1024x1024), BF16 linears / F16 convs.  Both of our graph
+    variants against the CPU's default graph (bf16 operands: 8-bit mantissa, so the level is bf16 rounding noise)."""
+    h, dev = b200
+    x = h.randn(42, (1, 4, 128, 128)); ctx = h.randn(43, (1, 77, 2048)); t = np.array([999.0], np.float32); y = h.randn(44, (1, 2816))
+    m = h.model("CPU", "sdxl_unet", "bf16", 0, 1234, 0)
+    cpu, _ = m.forward(x, t, ctx, y)
+    m.close()
+    for fa in (1, 0):
+        m = h.model(dev, "sdxl_unet", "bf16", fa, 1234, 0)
+        ours, _ = m.forward(x, t, ctx, y)
+        no_fallback(m)
+        m.close()
+        r = rel(ours, cpu)
+        print(f"sdxl 128 bf16 fa={fa}: rel_l2 {r:.3e}")
+        assert np.isfinite(ours).all() and r < 1.2e-2, f"fa={fa}: rel_l2 {r:.2e}"
+
+
+def test_flux_full_width_block_vs_live_cpu(b200):
+    """BASELINE config 4 at its quoted width and length: ONE double-stream + ONE single-stream FLUX.1 block (hidden 3072, 24 heads of
+    128) on 4096 image + 256 text tokens, BF16 weights, flash-attention graph."""
+    h, dev = b200
+    x = h.randn(42, (1, 16, 128, 128)); ctx = h.randn(43, (1, 256, 4096)); t = np.array([1.0], np.float32); y = h.randn(44, (1, 768))
+    outs = {}
+    for d in (dev, "CPU"):
+        m = h.model(d, "flux_1x1", "bf16", 1, 1234, 0)
+        outs[d], _ = m.forward(x, t, ctx, y)
+        if d == dev:
+            no_fallback(m)
+        m.close()
+    r = rel(outs[dev], outs["CPU"])
+    print(f"flux 1+1 full width: rel_l2 {r:.3e}")
+    assert np.isfinite(outs[dev]).all() and r < 1.5e-2, f"rel_l2 {r:.2e}"
+
+
+# ------------------------------------------------------------------------------------------------ no silent fallback
+@pytest.mark.parametrize("arch,wtype,fa,x,ctx,y,t", [
+    ("sd15_unet", "f16", 1, (1, 4, 64, 64), (1, 77, 768), None, 999.0),
+    ("sd15_unet", "f16", 0, (2, 4, 64, 64), (2, 77, 768), None, 999.0),
+    ("vae_decoder", "f16", 0, (1, 4, 32, 32), None, None, None),
+    ("flux_tiny", "bf16", 1, (1, 16, 32, 32), (1, 64, 4096), (1, 768), 1.0),
+    ("mmdit_sd3", "f16", 1, (1, 16, 32, 32), (1, 154, 4096), (1, 2048), 500.0),
+    ("wan_1_3b", "q8_0", 1, (16, 3, 16, 16), (1, 512, 4096), None, 500.0),
+])
+def test_no_cuda_core_gemm_on_any_model_path(b200, arch, wtype, fa, x, ctx, y, t):
+    """op_mul_mat / the unfused attention drop to the CUDA-core reference GEMM when the tensor-core launcher refuses a shape; a counter
+    makes that visible and it must stay 0 for every architecture of SURVEY.md 8a -- eagerly AND under CUDA-graph replay (the counters
+    of replayed graphs are accounted from the capture)."""
+    h, dev = b200
+    m = h.model(dev, arch, wtype, fa, 1234, 0)
+    xs = h.randn(42, x); cs = h.randn(43, ctx) if ctx else None; ys = h.randn(44, y) if y else None
+    ts = np.full((x[0] if arch == "sd15_unet" else 1,), t, np.float32) if t is not None else None
+    s0 = m.stats()
+    for _ in range(3):                       # eager, capture, replay
+        out, _ = m.forward(xs, ts, cs, ys)
+    st = no_fallback(m)
+    m.close()
+    assert np.isfinite(out).all()
+    assert st["tc_gemm_launches"] - s0["tc_gemm_launches"] > 0
+    if arch != "wan_1_3b":
+        assert st["cuda_graph_replays"] >= 1
+        # the replayed forward reports the same tensor-core launch count as the eager one
+        assert (st["tc_gemm_launches"] - s0["tc_gemm_launches"]) % 3 == 0
+
+
+# ------------------------------------------------------------------------------------------------ weights written by a graph
+def test_graph_write_into_conv_weight_drops_the_packed_copy(b200):
+    """The reference applies LoRA by running ggml_add_inplace INTO model tensors on the runtime backend (lora.hpp:934-937).  After one
+    forward the 3x3 filters have packed copies and the forward replays as a CUDA graph; the write must invalidate both."""
+    h, dev = b200
+    x = h.randn(42, (1, 4, 16, 16)); ctx = h.randn(43, (1, 77, 768)); t = np.array([999.0], np.float32)
+    name = "input_blocks.1.0.in_layers.2.weight"
+    outs = {}
+    for d in (dev, "CPU"):
+        m = h.model(d, "unet_tiny", "f16", 0, 1234, 0)
+        before = [m.forward(x, t, ctx)[0] for _ in range(3)][-1]      # eager, capture, replay
+        n = m.add_to_weight(name, 4, 0.01)
+        after, _ = m.forward(x, t, ctx)
+        after2, _ = m.forward(x, t, ctx)
+        if d == dev:
+            st = m.stats()
+            assert st["weight_write_graphs"] == 1
+            assert np.array_equal(after, after2)
+        m.close()
+        assert n == 320 * 320 * 9
+        outs[d] = (before, after)
+    assert rel(outs[dev][1], outs[dev][0]) > 0.1, "the weight update did not reach the convolution"
+    assert rel(outs[dev][0], outs["CPU"][0]) < 3e-3
+    assert rel(outs[dev][1], outs["CPU"][1]) < 3e-3, f"after the in-graph weight write: {rel(outs[dev][1], outs['CPU'][1]):.2e}"

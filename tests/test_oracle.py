@@ -202,3 +202,26 @@ def test_wan_vae_fixture_matches_live_cpu_backend(cpu_oracle):
     m.close()
     r = float(np.linalg.norm(out.astype(np.float64) - gold) / np.linalg.norm(gold.astype(np.float64)))
     assert out.shape == gold.shape and r < 1e-3, f"{r:.2e}"
+
+
+def test_float64_graph_interpreter_reproduces_the_committed_truth(cpu_oracle):
+    """oracle/graph_f64.py (the arbiter of the whole-model GPU parity tests) on the graph the reference builds for unet_tiny: the
+    float64 evaluation is reproducible, and the reference CPU backend sits where the fixture says it does (~1e-3: the f16 rounding of
+    the contraction operands), which is the evidence behind the GPU gates of tests/test_gpu_parity_config.py."""
+    import tempfile
+    from pathlib import Path
+    from oracle.graph_f64 import evaluate
+    h = cpu_oracle
+    gold = np.load(GOLD / "truth_f64.npz")
+    x = h.randn(42, (1, 4, 16, 16)); ctx = h.randn(43, (1, 77, 768)); t = np.array([999.0], np.float32)
+    m = h.model("CPU", "unet_tiny", "f16", 0, 1234, 0)
+    cpu, _ = m.forward(x, t, ctx)
+    with tempfile.TemporaryDirectory() as d:
+        n = m.export_graph(Path(d) / "g", x, t, ctx)
+        m.close()
+        truth = evaluate(Path(d) / "g").reshape(cpu.shape)
+    assert n > 1000
+    assert np.allclose(truth, gold["unet_tiny"], rtol=0, atol=1e-9)
+    r = float(np.linalg.norm(cpu.astype(np.float64) - truth) / np.linalg.norm(truth))
+    assert abs(r - float(gold["cpu_rel_unet_tiny"])) < 3e-4 and 3e-4 < r < 2e-3
+    assert 5e-4 < float(gold["cpu_rel_sd15_unet"]) < 1.5e-3
