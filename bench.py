@@ -51,31 +51,29 @@ def peaks():
 LAYOUT_TEXT = {
     "batched": "every GPU samples its own image, cond + uncond as ONE N = 2 UNet forward per step (caller-side CFG batching; no collective)",
     "serial": "the reference's own order: two N = 1 UNet forwards per step on one GPU (stable-diffusion.cpp:2811-2836)",
-    "cfg-split": "CFG batch split over GPU pairs: rank 2i evaluates cond, rank 2i+1 uncond of image i, ONE NCCL all-gather of eps per step",
+    "cfg-split": "CFG batch split over GPU pairs: rank 2i evaluates cond, rank 2i+1 uncond of image i; the eps prediction (64 KB) is exchanged once per "
+                 "step by device code over NVLink peer memory (stored into the partner's HBM by the output convolution's epilogue, flag handshake, "
+                 "inside the replayed CUDA graph: kernels/peer.cu) -- the north star's single all-gather on the latent, without NCCL or host staging",
 }
 
 
 def ncu_traffic():
-    """DRAM bytes (read + write) per k_gemm_tc launch, averaged over the launches of the committed `ncu --set full` capture
-    (profiles/r01_ncu_full_*.json).  Offline evidence, never measured under the timed run; null when absent."""
-    # capture of the default (batched-CFG) forward first, the serial-forward capture as fallback
-    p = next((c for c in (REPO / "profiles" / "r01_ncu_full_gemm_batched_cfg.json", REPO / "profiles" / "r01_ncu_full_top_kernels.json") if c.exists()), None)
-    if p is None:
-        return dict(traffic=None)
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    tot, n = 0.0, 0
-    for row in json.loads(p.read_text()):
-        if "k_gemm_tc" not in row.get("Kernel Name", ""):
+    """DRAM bytes (read + write) per tcgen05 GEMM launch: the sum over EVERY GEMM launch of one batched-CFG forward divided by their
+    count, from the committed whole-forward ncu metrics pass (profiles/r02_ncu_metrics_sd15_batched.json, produced by
+    scripts/ncu_kernel_table.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,...` over all launches of the forward).
+    Offline evidence, never measured under the timed run; null when absent."""
+    for name in ("r02_ncu_metrics_sd15_batched.json",):
+        p = REPO / "profiles" / name
+        if not p.exists():
             continue
-        b = 0.0
-        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            v, u = row[key].split()
-            b += float(v) * scale[u]
-        tot, n = tot + b, n + 1
-    if not n:
-        return dict(traffic=None)
-    return dict(traffic=tot / n, traffic_unit="bytes/launch (dram read+write, ncu --set full)", traffic_launches_sampled=n,
-                traffic_source=str(p.relative_to(REPO)))
+        d = json.loads(p.read_text())
+        rows = [k for k in d.get("kernels", []) if "k_gemm_tc" in k["kernel"]]
+        n = sum(k["launches"] for k in rows)
+        if n:
+            tot = sum(k["dram_bytes"] for k in rows)
+            return dict(traffic=tot / n, traffic_unit="bytes/launch (dram read+write summed over ALL GEMM launches of one forward, ncu)", traffic_launches=n,
+                        traffic_algorithmic_bytes_per_launch=d.get("gemm_algorithmic_bytes_per_launch"), traffic_source=str(p.relative_to(REPO)))
+    return dict(traffic=None)
 
 
 class ClockSampler:
@@ -187,7 +185,8 @@ def run_b200(args):
     #               batching); independent units, no data-path collective
     #   "serial"    (--cfg serial, N = 1): the reference's own order, two N = 1 forwards per step (stable-diffusion.cpp:2811-2836)
     #   "cfg-split" (--layout cfg-split, even N): ranks (2i, 2i+1) take cond / uncond of image i and all-gather eps over NCCL
-    main_layout = "cfg-split" if (world > 1 and args.layout == "cfg-split") else ("serial" if (world == 1 and args.cfg == "serial") else "batched")
+    split_ok = world > 1 and world % 2 == 0
+    main_layout = "cfg-split" if (split_ok and args.layout in ("auto", "cfg-split")) else ("serial" if (world == 1 and args.cfg == "serial") else "batched")
     alt_layout = None
     if not args.no_alt:
         if world == 1:
@@ -199,10 +198,24 @@ def run_b200(args):
     nodes, flops = m.dump_graph(None, x0, np.array([999.0], np.float32), cond0)
     assert abs(flops - FLOPS_PER_FORWARD) / FLOPS_PER_FORWARD < 0.01, f"graph FLOPs {flops:.4e} differ from SURVEY.md 8d"
 
-    pair_exchange = None
-    if world > 1 and world % 2 == 0 and "cfg-split" in (main_layout, alt_layout):
-        from sdb200.cfg_split import PairExchange
-        pair_exchange = PairExchange(dist, torch, rank, world, 4 * 64 * 64, "cuda")   # pair groups + one all-gather per step
+    # CFG split: the exchange is DEVICE code over NVLink peer memory (kernels/peer.cu) -- each rank maps its partner's mailbox once (the two
+    # 64-byte CUDA IPC handles travel over torch.distributed here, host plumbing) and from then on every forward ends with its eps
+    # prediction stored into the partner's HBM by the output convolution's epilogue + a flag handshake, inside the replayed CUDA graph
+    mailbox_ready = False
+
+    def connect_mailbox():
+        nonlocal mailbox_ready
+        if mailbox_ready:
+            return
+        mine = torch.frombuffer(bytearray(m.mailbox_create(4 * 64 * 64 * 4)), dtype=torch.uint8).clone().cuda()
+        handles = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(handles, mine)
+        m.mailbox_connect(bytes(handles[rank ^ 1].cpu().numpy().tobytes()))
+        mailbox_ready = True
+
+    def nonlocal_reset():
+        nonlocal mailbox_ready
+        mailbox_ready = False
 
     def barrier():
         torch.cuda.synchronize()
@@ -214,9 +227,14 @@ def run_b200(args):
         """W untimed + exactly K timed steps in `layout`; device time = CUDA events around every graph_compute (+ the collective),
         max over ranks; returns the whole-job numbers."""
         if layout == "cfg-split":
-            image, role, exchange, images = rank // 2, rank % 2, pair_exchange, world // 2
+            connect_mailbox()
+            image, role, images = rank // 2, rank % 2, world // 2
         else:
-            image, role, exchange, images = rank, (2 if layout == "batched" else -1), None, world
+            if mailbox_ready:
+                m.mailbox_close()
+                nonlocal_reset()
+            image, role, images = rank, (2 if layout == "batched" else -1), world
+        exchange = None
         x, cond, uncond = inputs(h, image)
 
         def run(k):
@@ -225,8 +243,6 @@ def run_b200(args):
         run(warmup)                                                # >= 3 untimed warm-up steps (plan caches, workspace, clocks)
         barrier()
         s0 = m.stats()
-        if exchange is not None:
-            exchange.coll_ms = 0.0
         clk = ClockSampler(local) if sample_clocks else None
         if clk:
             clk.__enter__()
@@ -237,7 +253,7 @@ def run_b200(args):
         if clk:
             clk.__exit__(None, None, None)
         s1 = m.stats()
-        dev_ms = (s1["total_graph_ms"] - s0["total_graph_ms"]) + (exchange.coll_ms if exchange is not None else 0.0)
+        dev_ms = s1["total_graph_ms"] - s0["total_graph_ms"]      # cfg-split: includes the in-graph exchange and the wait for the partner
         launches = s1["kernel_launches"] - s0["kernel_launches"]
         forwards = s1["graphs"] - s0["graphs"]
         if dist is not None:
@@ -254,6 +270,9 @@ def run_b200(args):
     W = max(args.warmup, 3)
     main = timed(main_layout, args.steps, W, True)
     alt = timed(alt_layout, args.steps, W, False) if alt_layout else None
+    if mailbox_ready:                 # the passes below are rank-local: no forward may wait for a partner any more
+        m.mailbox_close()
+        nonlocal_reset()
     clk, s0, s1 = main["clk"], main["s0"], main["s1"]
     wall, dev_ms, launches, forwards, images = main["wall"], main["dev_ms"], main["launches"], main["forwards"], main["images"]
     value, e2e = main["value"], main["e2e"]
@@ -276,7 +295,7 @@ def run_b200(args):
             gus = k1["tc_gemm_us"] - k0["tc_gemm_us"]
             if gus > 0:
                 ach = gf / (gus * 1e-6) / 1e12
-                roof = dict(bound="tensor", kernel="k_gemm_tc (tcgen05.mma kind::f16/tf32, TMA, TMEM)", achieved=ach, peak=pk["bf16_sustained"],
+                roof = dict(bound="tensor", kernel="k_gemm_tc / k_gemm_tc2 (tcgen05.mma kind::f16, cta_group::1 and ::2, TMA, TMEM)", achieved=ach, peak=pk["bf16_sustained"],
                             unit="TFLOP/s", frac=ach / pk["bf16_sustained"], peak_source=pk["src"] + " (sustained: kernel timed inside a long step)",
                             launches=gl, flop_per_launch=gf / max(gl, 1), us_per_launch=gus / max(gl, 1),
                             share_of_step_device_time=(gus / 1e3) / max((k1["total_graph_ms"] - k0["total_graph_ms"]), 1e-9), **ncu_traffic())
@@ -286,16 +305,19 @@ def run_b200(args):
         vae = None
         if n == 1 and not args.no_vae:
             vae = vae_decode_leg(h, dev, pk)
+            # the SDXL / Flux image size (BASELINE configs 3-4): 128x128 latent -> 1024x1024, algorithmic bytes 28.8 GB
+            vae["at_1024"] = vae_decode_leg(h, dev, pk, latent=128, gb=28.8)
         if n == 1 and not args.no_cpu_baseline:
             cpu_base = cpu_baseline_leg(h)
     m.close()
     extra = {}
     if rank == 0 and n == 1:
-        for name in [e for e in args.extra.split(",") if e]:
+        for name in [e for e in args.extra.split(",") if e and e != "none"]:
             extra[name] = extra_leg(h, dev, peaks(), name)
     if rank == 0:
         line = dict(metric="denoise_steps_per_s", value=value, unit="steps/s", n_gpus=n, steps=args.steps, warmup=max(args.warmup, 3),
-                    ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16", data="synthetic",
+                    ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling=("strong" if (main_layout == "cfg-split" and world == 2) else "weak"),
+                    vs_baseline=None, dtype="f16", data="synthetic",
                     config=dict(workload=WORKLOAD, denoiser="SD1.5 UNet graph built by the reference UNetModelRunner, synthetic F16 weights (seed 1234)",
                                 latent="64x64x4", context="77x768", sampler="euler_a eta 1", cfg_scale=CFG_SCALE, forwards_per_step=main["forwards_per_step"], layout=main_layout,
                                 graph="flash-attention variant (--diffusion-fa)", images=images,
@@ -310,7 +332,17 @@ def run_b200(args):
                                                                              ms_per_step=alt["dev_ms"] / args.steps, e2e=alt["e2e"], images=alt["images"],
                                                                              forwards_per_step=alt["forwards_per_step"], gpu_launches=int(alt["launches"])),
                     vae_decode=vae, extra_workloads=extra or None,
+                    layouts={main_layout: dict(value=value, e2e=e2e, ms_per_step=dev_ms / args.steps, e2e_ms_per_step=1e3 * wall / args.steps, is_value=True),
+                             **({alt["layout"]: dict(value=alt["value"], e2e=alt["e2e"], ms_per_step=alt["dev_ms"] / args.steps,
+                                                     e2e_ms_per_step=1e3 * alt["wall"] / args.steps, is_value=False)} if alt else {})},
+                    host=dict(backend_graph_compute_ms_per_step=(s1["host_us"] - s0["host_us"]) / 1e3 / args.steps,
+                              e2e_minus_device_ms_per_step=1e3 * wall / args.steps - dev_ms / args.steps,
+                              note="backend share = host time inside graph_compute (signature, planning, cudaGraphLaunch); the rest is the reference's "
+                                   "graph rebuild, gallocr, tensor_set/get and sampler math per model call"),
                     backend=dict(cuda_graph_replays=int(s1["cuda_graph_replays"] - s0["cuda_graph_replays"]),
+                                 gemm_ref_launches=int(s1["gemm_ref_launches"] - s0["gemm_ref_launches"]),
+                                 cta_pair_gemm_launches=int(s1["cta2_gemm_launches"] - s0["cta2_gemm_launches"]),
+                                 unfused_attention=int(s1["unfused_attention"] - s0["unfused_attention"]),
                                  fused_nodes=int(s1["fused_nodes"] - s0["fused_nodes"]), implicit_convs=int(s1["implicit_convs"] - s0["implicit_convs"]),
                                  fused_attn_launches=int(s1["fused_attn_launches"] - s0["fused_attn_launches"]),
                                  tc_gemm_launches=int(s1["tc_gemm_launches"] - s0["tc_gemm_launches"])))
@@ -319,12 +351,12 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def vae_decode_leg(h, dev, pk):
+def vae_decode_leg(h, dev, pk, latent=64, gb=7.27):
     """Second half of BASELINE.json's metric: AutoEncoderKL decode 64x64x4 -> 512x512x3 (reference graph, synthetic F16 weights).
     HBM roofline per the north star: algorithmic bytes 7.27 GB (BASELINE.md section 3) / device time vs measured copy bandwidth;
     the tensor fraction (2.515 TFLOP) is reported beside it because the fused graph crosses the ridge."""
     m = h.model(dev, "vae_decoder", "f16", 0, 1234, 0)
-    z = h.randn(45, (1, 4, 64, 64))
+    z = h.randn(45, (1, 4, latent, latent))
     nodes, flops = m.dump_graph(None, z)
     for _ in range(3):
         m.forward(z)
@@ -338,8 +370,8 @@ def vae_decode_leg(h, dev, pk):
         dev_ms.append(s1["total_graph_ms"] - s0["total_graph_ms"])
     m.close()
     d = statistics.median(dev_ms)
-    gb = 7.27
-    return dict(metric="vae_decode_ms", value=d, unit="ms", e2e_ms=statistics.median(wall_ms), workload="AutoEncoderKL decode 64x64x4 -> 512x512x3, F16 conv weights",
+    return dict(metric="vae_decode_ms", value=d, unit="ms", e2e_ms=statistics.median(wall_ms),
+                workload=f"AutoEncoderKL decode {latent}x{latent}x4 -> {8 * latent}x{8 * latent}x3, F16 conv weights",
                 algorithmic_gb=gb, hbm_gbs=gb / (d / 1e3), hbm_frac=gb / (d / 1e3) / pk["hbm"], algorithmic_tflop=flops / 1e12,
                 tensor_tflops=flops / 1e12 / (d / 1e3), tensor_frac=flops / 1e12 / (d / 1e3) / pk["bf16_sustained"], graph_nodes=nodes,
                 finite=bool(np.isfinite(out).all()))
@@ -408,11 +440,12 @@ def main():
     ap.add_argument("--cfg", default="batched", choices=["batched", "serial"],
                     help="N = 1: cond + uncond as ONE N = 2 forward per step (default; caller-side CFG batching, SURVEY.md 8f-1) or the "
                          "reference's two serial forwards; the other one is measured too and reported under alt_layout")
-    ap.add_argument("--layout", default="batched", choices=["batched", "cfg-split"],
-                    help="N > 1: independent images per GPU with batched CFG (default, no collective) or the CFG batch split over GPU pairs with "
-                         "one NCCL all-gather per step; the other one is reported under alt_layout")
+    ap.add_argument("--layout", default="auto", choices=["auto", "batched", "cfg-split"],
+                    help="N > 1: 'cfg-split' (auto at even N: the north star's layout) splits the CFG batch of one image over a GPU pair with a "
+                         "device-side exchange of eps per step; 'batched' runs independent images per GPU with batched CFG (no collective); the "
+                         "other one is reported under alt_layout")
     ap.add_argument("--no-alt", action="store_true", help="skip the alt_layout measurement")
-    ap.add_argument("--extra", default="", help="comma list of additional single-GPU forward timings: sdxl,flux")
+    ap.add_argument("--extra", default="sdxl,flux", help="comma list of additional single-GPU forward timings (N = 1 only): sdxl,flux; 'none' disables")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

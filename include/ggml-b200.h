@@ -77,7 +77,8 @@ typedef struct ggml_b200_stats {
                                    [1] host microseconds spent inside graph_compute (signature, fusion planning, launches / cudaGraphLaunch),
                                    [2] graphs that wrote into a WEIGHTS buffer (derived weight copies dropped), [3] conv filters packed per graph
                                    (filter computed inside the graph: no persistent copy), [4] persistent-GEMM launches, [5] 2-CTA GEMM launches,
-                                   [6] bytes of derived weight copies alive, [7] unfused (GEMM + softmax + GEMM) attention executions */
+                                   [6] bytes of derived weight copies alive, [7] unfused (GEMM + softmax + GEMM) attention executions,
+                                   [8] graphs that ended with a peer exchange (kernels/peer.cu) */
 } ggml_b200_stats;
 
 /* copy the backend instance's counters; returns 0 on success.  Counters of kernels that run inside a replayed CUDA graph are
@@ -98,6 +99,24 @@ void ggml_backend_b200_reset_stats(ggml_backend_t backend);
  *   "gemv"        1/0   MUL_MAT with <= 4 activation rows as a weight-streaming GEMV
  * returns 0 on success, -1 for an unknown key. */
 int ggml_backend_b200_set_option(ggml_backend_t backend, const char* key, int value);
+
+/* ---- CFG-batch split over a pair of GPUs, one process per GPU (kernels/peer.cu).  The reference offers nothing here
+ * (its sample() is serial, stable-diffusion.cpp:2811-2836); the closest reference interface is the meta backend's
+ * "ggml_backend_comm_init / _allreduce_tensor" extension pair (ggml/src/ggml-backend-meta.cpp:2207-2220), found the same way:
+ * reg->iface.get_proc_address(reg, "ggml_backend_b200_peer_mailbox_*").
+ *   create   allocates this backend's mailbox for payloads of `bytes` bytes (the eps prediction) and returns its 64-byte CUDA IPC handle
+ *   connect  maps the OTHER rank's mailbox from its handle (NULL = loopback: the rank is its own peer, a single-GPU self test).  From
+ *            then on every graph_compute whose output tensor has exactly `bytes` bytes ends with: the tensor stored into the peer's
+ *            mailbox over NVLink (by the epilogue of the convolution producing it where that is the CTA-pair kernel, by a copy kernel
+ *            otherwise), a sequence number published in the peer's flag, and a device-side wait for the peer's -- all on the backend
+ *            stream, inside the captured CUDA graph
+ *   read     synchronises the stream and copies the payload the peer stored here to `host_dst`; -2 when the peer never arrived (the
+ *            device-side wait gives up after 10 s instead of hanging the GPU)
+ * All return 0 on success. */
+int  ggml_backend_b200_peer_mailbox_create(ggml_backend_t backend, size_t bytes, void* ipc_handle_out64);
+int  ggml_backend_b200_peer_mailbox_connect(ggml_backend_t backend, const void* peer_ipc_handle64);
+int  ggml_backend_b200_peer_mailbox_read(ggml_backend_t backend, void* host_dst);
+void ggml_backend_b200_peer_mailbox_close(ggml_backend_t backend);
 
 /* ggml_backend_device_i::supports_op (ggml-backend-impl.h:186) without a device: 1 when every B200 of this backend executes `op`.
  * Callable on a machine without a GPU -- the CPU test suite walks the reference's model graphs with it, because any 0 would make

@@ -132,6 +132,14 @@ int sdh_sample_split(sdh_model* m, const char* method, int steps, float cfg_scal
                      sdh_tensor* out, float* sigmas_out, float* timesteps_out, int* n_forwards,
                      double* wall_ms, int role, sdh_exchange_fn exchange, void* user);
 
+/* CFG split with the DEVICE-SIDE exchange (include/ggml-b200.h ggml_backend_b200_peer_mailbox_*): create returns this rank's 64-byte IPC
+ * handle, connect takes the other rank's (NULL = loopback self test).  While connected, sdh_sample_split with role 0 / 1 and
+ * exchange == NULL evaluates one branch per step and takes the other branch's eps prediction from the mailbox: no callback, no NCCL,
+ * no host staging. */
+int  sdh_model_mailbox_create(sdh_model* m, size_t bytes, void* handle_out64);
+int  sdh_model_mailbox_connect(sdh_model* m, const void* peer_handle64);
+void sdh_model_mailbox_close(sdh_model* m);
+
 /* Counters of the model's backend instance when it is a B200 backend (include/ggml-b200.h ggml_b200_stats), as doubles:
  * [0] graphs [1] kernel_launches [2] nodes_executed [3] fused_nodes [4] last_graph_ms [5] total_graph_ms
  * [6] tc_gemm_launches [7..14] reserved[0..7], [15] unused, [16..31] ext[0..15] (see ggml-b200.h).  Returns <0 for other backends. */

@@ -86,6 +86,12 @@ b200_cuTensorMapEncodeTiled_t b200_get_tensormap_encoder() {
 // ------------------------------------------------------------------------------------------------
 // buffer
 // ------------------------------------------------------------------------------------------------
+static bool b200_ingest_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GGML_B200_INGEST"); v = (e && *e) ? atoi(e) != 0 : 1; }
+    return v != 0;
+}
+
 struct b200_buffer_ctx {
     int   device;
     void* base;
@@ -126,6 +132,8 @@ static void b200_buffer_set_tensor(ggml_backend_buffer_t buffer, ggml_tensor* te
     B200_CUDA_CHECK(cudaStreamSynchronize(cudaStreamPerThread));
     // derived weight layouts (packed conv filters ...) are keyed by address: writing invalidates them
     b200_invalidate_address_range(ctx->device, (char*)tensor->data + offset, size);
+    // ... and a weight uploaded in full gets its derived layout right here, at load time, not inside the first forward
+    if (buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS && offset == 0 && size == ggml_nbytes(tensor) && b200_ingest_enabled()) b200_ingest_weight(ctx->device, tensor);
 }
 
 static void b200_buffer_get_tensor(ggml_backend_buffer_t buffer, const ggml_tensor* tensor, void* data, size_t offset, size_t size) {
@@ -480,6 +488,10 @@ static void* b200_reg_get_proc_address(ggml_backend_reg_t, const char* name) {
     if (!strcmp(name, "ggml_backend_b200_set_option")) return (void*)ggml_backend_b200_set_option;
     if (!strcmp(name, "ggml_backend_b200_init")) return (void*)ggml_backend_b200_init;
     if (!strcmp(name, "ggml_backend_b200_op_supported")) return (void*)ggml_backend_b200_op_supported;
+    if (!strcmp(name, "ggml_backend_b200_peer_mailbox_create")) return (void*)ggml_backend_b200_peer_mailbox_create;
+    if (!strcmp(name, "ggml_backend_b200_peer_mailbox_connect")) return (void*)ggml_backend_b200_peer_mailbox_connect;
+    if (!strcmp(name, "ggml_backend_b200_peer_mailbox_read")) return (void*)ggml_backend_b200_peer_mailbox_read;
+    if (!strcmp(name, "ggml_backend_b200_peer_mailbox_close")) return (void*)ggml_backend_b200_peer_mailbox_close;
     // names the host probes on every registry: none of them applies to this backend
     //   ggml_backend_set_n_threads, ggml_backend_get_features, ggml_backend_split_buffer_type, ggml_backend_rpc_add_server
     return nullptr;
@@ -576,6 +588,22 @@ int ggml_backend_b200_get_stats(ggml_backend_t backend, ggml_b200_stats* out) {
 void ggml_backend_b200_reset_stats(ggml_backend_t backend) {
     if (!ggml_backend_is_b200(backend)) return;
     memset(&((b200_context*)backend->context)->stats, 0, sizeof(b200_stats));
+}
+
+int ggml_backend_b200_peer_mailbox_create(ggml_backend_t backend, size_t bytes, void* ipc_handle_out64) {
+    if (!ggml_backend_is_b200(backend)) return -1;
+    return b200_peer_create((b200_context*)backend->context, bytes, ipc_handle_out64);
+}
+int ggml_backend_b200_peer_mailbox_connect(ggml_backend_t backend, const void* peer_ipc_handle64) {
+    if (!ggml_backend_is_b200(backend)) return -1;
+    return b200_peer_connect((b200_context*)backend->context, peer_ipc_handle64);
+}
+int ggml_backend_b200_peer_mailbox_read(ggml_backend_t backend, void* host_dst) {
+    if (!ggml_backend_is_b200(backend)) return -1;
+    return b200_peer_read((b200_context*)backend->context, host_dst);
+}
+void ggml_backend_b200_peer_mailbox_close(ggml_backend_t backend) {
+    if (ggml_backend_is_b200(backend)) b200_peer_close((b200_context*)backend->context);
 }
 
 int ggml_backend_b200_set_option(ggml_backend_t backend, const char* key, int value) {

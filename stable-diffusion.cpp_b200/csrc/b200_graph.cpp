@@ -52,6 +52,7 @@ b200_context* b200_context_create(const b200_device_info& info) {
     ctx->opt_early_weights = env_flag("GGML_B200_EARLY_WEIGHTS", 0) != 0;   // measured neutral on the SD1.5 step (profiles/r01_summary.md): off by default
     ctx->opt_chain_fusion = env_flag("GGML_B200_CHAIN_FUSION", 1) != 0;
     ctx->opt_gemv = env_flag("GGML_B200_GEMV", 1) != 0;
+    ctx->opt_precise_f32 = env_flag("GGML_B200_PRECISE_F32", 1) != 0;
     ctx->opt_persistent_gemm = env_flag("GGML_B200_PERSISTENT", 0) != 0;   // experimental persistent GEMM (gemm_tc_persist.cu), never run on hardware yet
     ctx->opt_fold_batch = env_flag("GGML_B200_FOLD_BATCH", 0) != 0;   // written at the end of round 1, not yet measured: off by default
     return ctx;
@@ -62,6 +63,7 @@ b200_context::~b200_context() {
     if (stream) cudaStreamSynchronize(stream);
     for (auto& c : ws.chunks) cudaFree(c.base);
     if (gn_counters) cudaFree(gn_counters);
+    b200_peer_close(this);
     for (auto& kv : plans) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (auto& p : kt_pending) { cudaEventDestroy(p.start); cudaEventDestroy(p.stop); }
     for (auto e : kt_free) cudaEventDestroy(e);
@@ -88,6 +90,7 @@ int b200_context_set_option(b200_context* ctx, const char* key, int value) {
     else if (!strcmp(key, "gemv")) ctx->opt_gemv = value != 0;
     else if (!strcmp(key, "fold_batch")) ctx->opt_fold_batch = value != 0;
     else if (!strcmp(key, "persistent_gemm")) ctx->opt_persistent_gemm = value != 0;
+    else if (!strcmp(key, "precise_f32")) ctx->opt_precise_f32 = value != 0;
     else return -1;
     return 0;
 }
@@ -323,6 +326,67 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
             }
         }
         if (fz && fz->src1_pre) return -2;     // only the GEMV can fold the unary op
+    }
+
+    if (ct == GGML_TYPE_F32 && ctx->opt_precise_f32 && ctx->opt_tc_gemm) {
+        // F32 x F32 (attention GEMMs of the reference's default graph, F32 Linear weights): the CPU oracle computes true f32 dot products
+        // (ggml-cpu.c:1406 with vec_dot_f32); a single TF32 pass would keep 10 mantissa bits of each operand.  3xTF32: x = hi + lo with hi
+        // exactly representable in TF32; D = A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, three tensor-core passes chained through the residual
+        // input of the epilogue, small terms first.  Error ~2^-21 relative: f32 class.
+        auto split = [&](const ggml_tensor* t, operand* hi, operand* lo) -> bool {
+            const int key_hi = 1000, key_lo = 1001;
+            auto h = ctx->pack_cache.find(std::make_pair(t, key_hi));
+            auto l = ctx->pack_cache.find(std::make_pair(t, key_lo));
+            if (h != ctx->pack_cache.end() && l != ctx->pack_cache.end()) { *hi = h->second; *lo = l->second; return true; }
+            const int64_t kpad = (t->ne[0] + 3) / 4 * 4;
+            const int64_t rows = t->ne[1] * t->ne[2] * t->ne[3];
+            float* bh = (float*)ws_alloc(ctx, (size_t)(rows * kpad * 4));
+            float* bl = (float*)ws_alloc(ctx, (size_t)(rows * kpad * 4));
+            if (!bh || !bl) return false;
+            int n = b200_launch_split_tf32(ctx->stream, b200_make_td(t), bh, bl, kpad);
+            if (n < 0) return false;
+            launches += n;
+            *hi = operand{bh, GGML_TYPE_F32, kpad, kpad * t->ne[1], kpad * t->ne[1] * t->ne[2]};
+            *lo = operand{bl, GGML_TYPE_F32, kpad, kpad * t->ne[1], kpad * t->ne[1] * t->ne[2]};
+            ctx->pack_cache[std::make_pair(t, key_hi)] = *hi;
+            ctx->pack_cache[std::make_pair(t, key_lo)] = *lo;
+            return true;
+        };
+        operand ah, al, bh, bl;
+        if (src0->type == GGML_TYPE_F32 && src1->type == GGML_TYPE_F32 && split(src0, &ah, &al) && split(src1, &bh, &bl)) {
+            bool ok = true;
+            for (int64_t i3 = 0; i3 < ne13 && ok; ++i3) {
+                char* out_base = fz && fz->out ? (char*)fz->out : (char*)dst->data;
+                float* D = (float*)(out_base + i3 * dst->nb[3]);
+                const operand* As[3] = {&al, &ah, &ah};
+                const operand* Bs[3] = {&bh, &bl, &bh};
+                for (int pass = 0; pass < 3 && ok; ++pass) {
+                    b200_gemm_args g;
+                    memset(&g, 0, sizeof(g));
+                    g.A = (const char*)As[pass]->ptr + (i3 / r3) * As[pass]->b3_stride * 4;
+                    g.B = (const char*)Bs[pass]->ptr + i3 * Bs[pass]->b3_stride * 4;
+                    g.type = GGML_TYPE_F32;
+                    g.M = M; g.N = N; g.K = K;
+                    g.lda = As[pass]->ld; g.ldb = Bs[pass]->ld;
+                    g.batch = ne12;
+                    g.a_batch_stride = As[pass]->batch_stride;
+                    g.b_batch_stride = Bs[pass]->batch_stride;
+                    g.a_bcast = r2;
+                    g.D = D;
+                    g.ldd = dst->nb[1] / 4;
+                    g.d_batch_stride = dst->nb[2] / 4;
+                    g.ldr = g.ldd;
+                    if (pass == 0) { if (fz && fz->residual) g.residual = fz->residual + i3 * (dst->nb[3] / 4); }
+                    else g.residual = D;                                     // accumulate onto the previous pass (same element, same thread)
+                    if (pass == 2 && fz && fz->bias) { g.bias = fz->bias; g.bias_mode = fz->bias_mode; }
+                    const int n = launch_tc(ctx, g);
+                    if (n < 0) ok = false;
+                    else launches += n;
+                }
+            }
+            if (ok) return launches;
+            return -1;       // a half-executed chain must not be redone differently: report the failure
+        }
     }
 
     operand a, b;
@@ -1015,12 +1079,51 @@ static bool is_constant_weight(const ggml_tensor* w) {
     return root->buffer && root->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS;
 }
 
-static bool pw_matches(const packed_weight& pw, const b200_context* ctx, const ggml_tensor* w) {
-    return pw.device == ctx->device && pw.src_bytes == ggml_nbytes(w) && pw.ne[0] == w->ne[0] && pw.ne[1] == w->ne[1] && pw.ne[2] == w->ne[2] &&
-           pw.ne[3] == w->ne[3];
+static bool pw_matches_dev(const packed_weight& pw, int device, const ggml_tensor* w) {
+    return pw.device == device && pw.src_bytes == ggml_nbytes(w) && pw.ne[0] == w->ne[0] && pw.ne[1] == w->ne[1] && pw.ne[2] == w->ne[2] && pw.ne[3] == w->ne[3];
+}
+
+// creates (or finds) the persistent derived copy of a constant weight: kind 0 = packed conv filter [OC][KH][KW][IC], kind 1 = Q8_0 -> f16 rows.
+// `may_allocate` is false inside a stream capture.  Caller holds no lock.
+static const void* derived_weight(int device, cudaStream_t stream, const ggml_tensor* w, int kind, bool may_allocate, int* launches, bool* overflow) {
+    std::lock_guard<std::mutex> lock(g_pw_mutex);
+    auto it = g_packed_weights.find(w->data);
+    if (it != g_packed_weights.end() && pw_matches_dev(it->second, device, w)) return it->second.ptr;
+    if (!may_allocate) { if (overflow) *overflow = true; return nullptr; }
+    if (it != g_packed_weights.end()) {      // same address, other shape / device: the old copy is stale
+        cudaFree(it->second.ptr);
+        g_pw_bytes.fetch_sub(it->second.bytes, std::memory_order_relaxed);
+        g_packed_weights.erase(it);
+        g_pw_generation.fetch_add(1, std::memory_order_relaxed);
+    }
+    const size_t bytes = kind == 0 ? ggml_nbytes(w) : (size_t)ggml_nelements(w) * 2;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    int n = kind == 0 ? b200_launch_pack_conv_weight(stream, w->data, p, (int)w->ne[0], (int)w->ne[1], w->ne[2], w->ne[3])
+                      : b200_launch_dequant_q8_0(stream, w->data, p, ggml_nelements(w) / 32);
+    if (n < 0) { cudaFree(p); return nullptr; }
+    if (launches) *launches += n;
+    g_packed_weights[w->data] = packed_weight{p, ggml_nbytes(w), device, {w->ne[0], w->ne[1], w->ne[2], w->ne[3]}, bytes};
+    g_pw_bytes.fetch_add(bytes, std::memory_order_relaxed);
+    return p;
+}
+
+// SURVEY.md 8f-3, weight ingest: called by the buffer's set_tensor for WEIGHTS-usage buffers once a tensor has been uploaded in full.
+// Conv filters (F16, 4-D, 3x3) get their K-major [OC][KH][KW][IC] copy and Q8_0 matrices their f16 rows HERE, at load time, instead of
+// by a kernel inside the first forward that meets them; 1x1 filters and F16 / BF16 matrices already are the layout the TMA reads.
+void b200_ingest_weight(int device, const ggml_tensor* w) {
+    if (!w || !w->data || w->view_src) return;
+    int kind = -1;
+    if (w->type == GGML_TYPE_F16 && ggml_n_dims(w) == 4 && w->ne[0] == w->ne[1] && w->ne[0] == 3 && w->ne[2] % 64 == 0 && ggml_is_contiguous(w)) kind = 0;
+    else if (w->type == GGML_TYPE_Q8_0 && ggml_n_dims(w) >= 2 && ggml_is_contiguous(w)) kind = 1;
+    if (kind < 0) return;
+    derived_weight(device, cudaStreamPerThread, w, kind, true, nullptr, nullptr);
+    cudaStreamSynchronize(cudaStreamPerThread);
 }
 
 static const void* get_packed_conv_weight(b200_context* ctx, const ggml_tensor* w, int* launches) {
+    // a 1x1 filter [1,1,IC,OC] IS the K-major [OC][IC] operand: read in place
+    if (w->ne[0] == 1 && w->ne[1] == 1 && ggml_is_contiguous(w)) return w->data;
     if (!is_constant_weight(w)) {
         void* p = ws_alloc(ctx, ggml_nbytes(w));
         if (!p) return nullptr;
@@ -1030,23 +1133,9 @@ static const void* get_packed_conv_weight(b200_context* ctx, const ggml_tensor* 
         ctx->stats.ext[3] += 1;
         return p;
     }
-    std::lock_guard<std::mutex> lock(g_pw_mutex);
-    auto it = g_packed_weights.find(w->data);
-    if (it != g_packed_weights.end() && pw_matches(it->second, ctx, w)) return it->second.ptr;
-    if (ctx->capturing) { ctx->capture_overflow = true; return nullptr; }
-    if (it != g_packed_weights.end()) {      // same address, other shape / device: the old copy is stale
-        cudaFree(it->second.ptr);
-        g_pw_bytes.fetch_sub(it->second.bytes, std::memory_order_relaxed);
-        g_packed_weights.erase(it);
-        g_pw_generation.fetch_add(1, std::memory_order_relaxed);
-    }
-    void* p = nullptr;
-    if (cudaMalloc(&p, ggml_nbytes(w)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    int n = b200_launch_pack_conv_weight(ctx->stream, w->data, p, (int)w->ne[0], (int)w->ne[1], w->ne[2], w->ne[3]);
-    if (n < 0) { cudaFree(p); return nullptr; }
-    *launches += n;
-    g_packed_weights[w->data] = packed_weight{p, ggml_nbytes(w), ctx->device, {w->ne[0], w->ne[1], w->ne[2], w->ne[3]}, ggml_nbytes(w)};
-    g_pw_bytes.fetch_add(ggml_nbytes(w), std::memory_order_relaxed);
+    bool overflow = false;
+    const void* p = derived_weight(ctx->device, ctx->stream, w, 0, !ctx->capturing, launches, &overflow);
+    if (overflow) ctx->capture_overflow = true;
     return p;
 }
 
@@ -1061,23 +1150,9 @@ static const void* get_dequantised_weight(b200_context* ctx, const ggml_tensor* 
         *launches += r;
         return p;
     }
-    std::lock_guard<std::mutex> lock(g_pw_mutex);
-    auto it = g_packed_weights.find(w->data);
-    if (it != g_packed_weights.end() && pw_matches(it->second, ctx, w)) return it->second.ptr;
-    if (ctx->capturing) { ctx->capture_overflow = true; return nullptr; }
-    if (it != g_packed_weights.end()) {
-        cudaFree(it->second.ptr);
-        g_pw_bytes.fetch_sub(it->second.bytes, std::memory_order_relaxed);
-        g_packed_weights.erase(it);
-        g_pw_generation.fetch_add(1, std::memory_order_relaxed);
-    }
-    void* p = nullptr;
-    if (cudaMalloc(&p, (size_t)n * 2) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    int r = b200_launch_dequant_q8_0(ctx->stream, w->data, p, n / 32);
-    if (r < 0) { cudaFree(p); return nullptr; }
-    *launches += r;
-    g_packed_weights[w->data] = packed_weight{p, ggml_nbytes(w), ctx->device, {w->ne[0], w->ne[1], w->ne[2], w->ne[3]}, (size_t)n * 2};
-    g_pw_bytes.fetch_add((size_t)n * 2, std::memory_order_relaxed);
+    bool overflow = false;
+    const void* p = derived_weight(ctx->device, ctx->stream, w, 1, !ctx->capturing, launches, &overflow);
+    if (overflow) ctx->capture_overflow = true;
     return p;
 }
 
@@ -1265,12 +1340,18 @@ static int emit_conv(b200_context* ctx, const conv_match& m, const conv_prologue
     c.dil = m.dil; c.pad = c.dil * (c.KH - 1) / 2;
     c.D = m.out; c.bias = m.bias; c.residual = m.residual;
     c.w_const = (ctx->opt_early_weights && !w_fresh) ? 1 : 0;     // at least the NHWC transform precedes this launch in the graph
+    const bool want_peer = ctx->peer.connected && ctx->peer_out && (const void*)m.out == ctx->peer_out && N == 1;
+    if (want_peer) {       // compute + collective in one kernel: the epilogue also stores into the peer GPU's mailbox
+        c.D2 = (float*)ctx->peer.remote;
+        c.d2_seq = ctx->peer.seq(ctx->peer.mailbox);
+        c.d2_slot_floats = (int64_t)(ctx->peer.slot_bytes / 4);
+    }
     size_t wsb = b200_conv_tc_workspace_bytes(ctx->info, c);
     void* w = wsb ? ws_alloc(ctx, wsb) : nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->opt_kernel_timing) { e0 = kt_event(ctx); e1 = kt_event(ctx); cudaEventRecord(e0, ctx->stream); }
     int n = b200_launch_conv_tc(ctx->stream, ctx->info, c, w, w ? wsb : 0);
-    if (n == 2) { n = 1; ctx->stats.ext[5] += 1; }   // CTA-pair kernel (gemm_tc2.cu)
+    if (n == 2) { n = 1; ctx->stats.ext[5] += 1; if (want_peer) ctx->peer_fused = true; }   // CTA-pair kernel (gemm_tc2.cu)
     if (ctx->opt_kernel_timing) {
         if (n > 0) {
             cudaEventRecord(e1, ctx->stream);
@@ -1838,6 +1919,18 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
     fusion_state fs;
     ctx->pack_cache.clear();
     ctx->launched_any = false;
+    ctx->peer_out = nullptr;
+    ctx->peer_fused = false;
+    ctx->graph_pushed = false;
+    if (ctx->peer.connected) {
+        // the tensor to exchange: the graph's last OUTPUT node, when it has exactly the mailbox's payload size (the eps prediction)
+        for (int i = cgraph->n_nodes - 1; i >= 0; --i) {
+            const ggml_tensor* t = cgraph->nodes[i];
+            if (!(t->flags & GGML_TENSOR_FLAG_OUTPUT)) continue;
+            if (t->type == GGML_TYPE_F32 && ggml_is_contiguous(t) && ggml_nbytes(t) == ctx->peer.bytes) ctx->peer_out = t->data;
+            break;
+        }
+    }
     const bool fuse = ctx->opt_fusion && cgraph->n_nodes > 1;
     if (fuse) count_uses(cgraph, fs);
     else fs.done.assign((size_t)cgraph->n_nodes, 0);
@@ -1887,7 +1980,90 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
         }
 #endif
     }
+    if (ctx->peer_out) {
+        auto& pr = ctx->peer;
+        if (!ctx->peer_fused) {
+            if (b200_launch_peer_push(ctx->stream, ctx->peer_out, pr.remote, pr.seq(pr.mailbox), pr.bytes, pr.slot_bytes) < 0) return GGML_STATUS_FAILED;
+            *launches += 1;
+        }
+        b200_launch_peer_signal_wait(ctx->stream, pr.seq(pr.mailbox), pr.flag(pr.remote), pr.flag(pr.mailbox), pr.err(pr.mailbox), 10.0);
+        *launches += 1;
+        ctx->graph_pushed = true;
+    }
     return GGML_STATUS_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CFG-split exchange: mailbox life cycle (device code in kernels/peer.cu)
+// ------------------------------------------------------------------------------------------------
+int b200_peer_create(b200_context* ctx, size_t bytes, void* ipc_handle_out64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!ctx || bytes == 0 || (bytes & 15)) return -1;
+    cudaSetDevice(ctx->device);
+    b200_peer_close(ctx);
+    auto& pr = ctx->peer;
+    pr.bytes = bytes;
+    pr.slot_bytes = (bytes + 255) & ~(size_t)255;
+    const size_t total = 2 * pr.slot_bytes + 512;
+    if (cudaMalloc(&pr.mailbox, total) != cudaSuccess) { cudaGetLastError(); pr.mailbox = nullptr; return -1; }
+    cudaMemset(pr.mailbox, 0, total);
+    cudaDeviceSynchronize();
+    if (ipc_handle_out64) {
+        cudaIpcMemHandle_t h;
+        if (cudaIpcGetMemHandle(&h, pr.mailbox) != cudaSuccess) { cudaGetLastError(); memset(ipc_handle_out64, 0, 64); }
+        else memcpy(ipc_handle_out64, &h, 64);
+    }
+    return 0;
+}
+
+int b200_peer_connect(b200_context* ctx, const void* peer_ipc_handle64) {
+    if (!ctx || !ctx->peer.mailbox) return -1;
+    cudaSetDevice(ctx->device);
+    auto& pr = ctx->peer;
+    if (!peer_ipc_handle64) {
+        pr.remote = pr.mailbox;          // loopback: the rank is its own peer (single-GPU self test of the protocol)
+        pr.ipc = false;
+    } else {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, peer_ipc_handle64, 64);
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            fprintf(stderr, "[ggml-b200] cudaIpcOpenMemHandle failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+            return -1;
+        }
+        pr.remote = (char*)p;
+        pr.ipc = true;
+    }
+    pr.pushes = 0;
+    pr.connected = true;
+    drop_cuda_graphs(ctx);              // plans captured without the exchange must not be replayed
+    ctx->plans.clear();
+    return 0;
+}
+
+int b200_peer_read(b200_context* ctx, void* host_dst) {
+    if (!ctx || !ctx->peer.connected || !host_dst || ctx->peer.pushes == 0) return -1;
+    cudaSetDevice(ctx->device);
+    auto& pr = ctx->peer;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); return -1; }
+    unsigned err = 0;
+    cudaMemcpy(&err, pr.err(pr.mailbox), 4, cudaMemcpyDeviceToHost);
+    if (err) { fprintf(stderr, "[ggml-b200] peer exchange %u timed out: the other rank never arrived\n", err); return -2; }
+    const size_t slot = (size_t)(pr.pushes & 1);
+    return cudaMemcpy(host_dst, pr.mailbox + slot * pr.slot_bytes, pr.bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+
+void b200_peer_close(b200_context* ctx) {
+    if (!ctx) return;
+    auto& pr = ctx->peer;
+    if (pr.mailbox || pr.remote) {
+        cudaSetDevice(ctx->device);
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        if (pr.ipc && pr.remote) cudaIpcCloseMemHandle(pr.remote);
+        if (pr.mailbox) cudaFree(pr.mailbox);
+        if (pr.connected) { drop_cuda_graphs(ctx); ctx->plans.clear(); }
+    }
+    pr = b200_context::peer_state{};
 }
 
 static void drop_cuda_graphs(b200_context* ctx) {
@@ -1956,6 +2132,7 @@ enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
         const b200_stats zero{};
         stats_add(ctx->stats, pl->delta, zero);
         ctx->stats.reserved[3]++;   // CUDA-graph replays
+        ctx->graph_pushed = pl->pushed;
     } else if (pl && pl->seen >= 1 && !pl->no_capture && ctx->ws.chunks.size() <= 1) {
         // ---- second sighting (or a stale plan: workspace moved / derived weights dropped): capture while executing nothing, then launch
         //      the instantiated graph
@@ -1983,6 +2160,7 @@ enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
                 pl->pw_generation = g_pw_generation.load(std::memory_order_relaxed);
                 pl->delta = b200_stats{};
                 stats_add(pl->delta, ctx->stats, before);
+                pl->pushed = ctx->graph_pushed;
                 e = cudaGraphLaunch(exec, ctx->stream);
                 ok = e == cudaSuccess;
             }
@@ -2009,6 +2187,7 @@ enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
         for (auto& w : writes) b200_invalidate_address_range(ctx->device, w.ptr, w.bytes);
     }
     ctx->stats.ext[6] = g_pw_bytes.load(std::memory_order_relaxed);
+    if (ctx->graph_pushed) { ctx->peer.pushes++; ctx->stats.ext[8] += 1; }
     ctx->stats.kernel_launches += launches;
     ctx->stats.nodes_executed += nodes;
     if (timing) {

@@ -51,6 +51,7 @@ struct b200_context {
     bool opt_gemv = true;             // MUL_MAT with <= 4 activation rows as a weight-streaming GEMV instead of a tcgen05 tile
     bool opt_fold_batch = false;      // MUL_MAT of one weight matrix against a contiguous batch of activations runs as one GEMM with N * batch rows
     bool opt_persistent_gemm = false; // EXPERIMENTAL persistent GEMM with double-buffered TMEM accumulators (not validated on hardware)
+    bool opt_precise_f32 = true;      // F32 x F32 MUL_MAT as 3xTF32 (hi/lo operand split, three tensor-core passes): f32-class accuracy like the CPU oracle's f32 dot
     bool opt_kernel_timing = false;   // per-launch CUDA events around every tcgen05 GEMM (roofline pass only)
     bool timing_pending = false;
     struct kt_pair { cudaEvent_t start, stop; double flops; };
@@ -62,12 +63,27 @@ struct b200_context {
         cudaGraphExec_t exec = nullptr; int seen = 0; bool no_capture = false; uint64_t launches = 0, nodes = 0, ws_generation = 0, pw_generation = 0;
         std::vector<uint64_t> sig;     // full identity of the graph this plan was recorded for (compared word for word on a hash hit)
         b200_stats delta{};            // counters of the kernels inside the captured graph (added at every replay)
+        bool pushed = false;           // the captured graph ends with a peer push (kernels/peer.cu)
     };
     std::vector<uint64_t> sig_scratch;
     std::unordered_map<uint64_t, plan> plans;
     uint64_t ws_generation = 0;
     // per-graph-execution cache of packed (type-converted) contraction operands, keyed by ggml tensor node
     std::unordered_map<std::pair<const ggml_tensor*, int>, b200_operand, b200_pack_key_hash> pack_cache;
+    // CFG-split exchange over NVLink peer memory (kernels/peer.cu; include/ggml-b200.h ggml_backend_b200_peer_*)
+    struct peer_state {
+        bool connected = false, ipc = false;
+        size_t bytes = 0, slot_bytes = 0;
+        char* mailbox = nullptr;        // own: [slot 0 | slot 1 | flag @ 2*slot | seq @ +128 | err @ +256]
+        char* remote = nullptr;         // the peer's mailbox mapped here (== mailbox in loopback mode)
+        uint64_t pushes = 0;            // pushes issued so far (host count; selects the slot to read)
+        unsigned* flag(char* base) const { return (unsigned*)(base + 2 * slot_bytes); }
+        unsigned* seq(char* base) const { return (unsigned*)(base + 2 * slot_bytes + 128); }
+        unsigned* err(char* base) const { return (unsigned*)(base + 2 * slot_bytes + 256); }
+    } peer;
+    const void* peer_out = nullptr;     // data pointer of the current graph's output tensor when it is to be pushed to the peer
+    bool peer_fused = false;            // ... and its producer has already stored it there (fused epilogue)
+    bool graph_pushed = false;          // the graph executed last contained a push
     unsigned* gn_counters = nullptr;   // B200_GN_COUNTERS zeroed counters of the chunked GroupNorm statistics (self-resetting)
     bool capturing = false, capture_overflow = false;
     bool launched_any = false;        // a kernel of the current graph execution has been launched
@@ -85,3 +101,11 @@ bool b200_supports_op(const b200_device_info& dev, const ggml_tensor* op);
 
 // caches of derived weight layouts are keyed by device address: any host write into a range drops them
 void b200_invalidate_address_range(int device, const void* ptr, size_t size);
+// weight ingest: derive the layouts the kernels read (packed 3x3 conv filters, Q8_0 -> f16 rows) when a weight is uploaded
+void b200_ingest_weight(int device, const ggml_tensor* w);
+
+// CFG-split exchange (kernels/peer.cu)
+int b200_peer_create(b200_context* ctx, size_t bytes, void* ipc_handle_out64);
+int b200_peer_connect(b200_context* ctx, const void* peer_ipc_handle64);   // nullptr: loopback (single-GPU self test)
+int b200_peer_read(b200_context* ctx, void* host_dst);
+void b200_peer_close(b200_context* ctx);

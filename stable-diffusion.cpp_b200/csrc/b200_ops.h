@@ -30,6 +30,9 @@ int b200_launch_sum_rows(cudaStream_t s, const b200_td& src, const b200_td& dst,
 // f32 -> f16/bf16 pack of a strided 2-D/4-D operand into a dense K-major matrix with K padded to kpad (zero filled)
 int b200_launch_pack_rows(cudaStream_t s, const b200_td& src, void* dst, int dst_type, int64_t kpad);
 
+// 3xTF32: f32 [K, rows, b2, b3] (any strides) -> hi / lo dense [rows][kpad] f32 (x = hi + lo, hi exactly representable in TF32)
+int b200_launch_split_tf32(cudaStream_t s, const b200_td& a, float* hi, float* lo, int64_t kpad);
+
 // 16-bit tiled transpose: src [d, L, b2, b3] (unit stride along d) -> dst dense [b3][b2][d rows][Lpad] (row = d index, L contiguous)
 int b200_launch_transpose_f16(cudaStream_t s, const b200_td& src, void* dst, int64_t Lpad);
 
@@ -110,6 +113,11 @@ struct b200_conv_args {
     const float* bias;      // per OC or null
     const float* residual;  // same layout as D or null
     int w_const;            // w_packed was not produced by a kernel of this graph execution (may be fetched before the PDL wait)
+    // optional second destination over NVLink (kernels/peer.cu): every output element is also stored at
+    // D2 + ((*d2_seq + 1) & 1) * d2_slot_floats + (its offset in D).  Honoured by the CTA-pair kernel only (launcher returns 2).
+    float* D2;
+    const unsigned* d2_seq;
+    int64_t d2_slot_floats;
 };
 bool b200_conv_tc_supported(int64_t N, int64_t H, int64_t W, int64_t C, int64_t OC, int KH, int KW, int s0, int s1, int p0, int p1, int d0, int d1);
 size_t b200_conv_tc_workspace_bytes(const b200_device_info& dev, const b200_conv_args& c);
@@ -126,6 +134,10 @@ size_t b200_gn_stats_partial_bytes(int64_t N, int64_t C, int64_t inner, int n_gr
 int b200_launch_to_nhwc_f16(cudaStream_t s, const float* x, void* out, int64_t N, int64_t C, int64_t H, int64_t W, int up, const float* stats,
                             int n_groups, const float* gw, const float* gb, int act);
 int b200_launch_pack_conv_weight(cudaStream_t s, const void* w, void* out, int KW, int KH, int64_t IC, int64_t OC);
+
+// ---- peer.cu: CFG-split exchange over NVLink peer memory -------------------------------------------------------------------------
+int b200_launch_peer_push(cudaStream_t s, const void* src, void* peer_base, const unsigned* seq, size_t bytes, size_t slot_bytes);
+int b200_launch_peer_signal_wait(cudaStream_t s, unsigned* my_seq, unsigned* peer_flag, const unsigned* my_flag, unsigned* my_err, double timeout_s);
 
 // ---- attention.cu --------------------------------------------------------------------------------
 // ggml FLASH_ATTN_EXT: q f32 [d, Lq, H, N], k f16 [d, Lk, Hkv, N], v f16 [dv, Lk, Hkv, N], mask f16 [Lk, >=Lq, ...] or null,

@@ -644,6 +644,27 @@ __global__ void k_pack_rows(b200_td a, TD* __restrict__ d, int64_t kpad, int64_t
 }
 
 
+// f32 operand -> (hi, lo) pair for the 3xTF32 contraction: hi = x with the 13 low mantissa bits cleared (exactly representable in TF32,
+// whatever rounding the tensor core applies to its inputs), lo = x - hi (exact in f32).  Dense [rows][kpad] f32 each, K zero padded.
+template <typename TS>
+__global__ void k_split_tf32(b200_td a, float* __restrict__ hi, float* __restrict__ lo, int64_t kpad, int64_t nrows) {
+    pdl_wait();
+    pdl_launch_dependents();
+    int64_t n = nrows * kpad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t k = i % kpad, row = i / kpad;
+        float v = 0.f;
+        if (k < a.ne[0]) {
+            int64_t i1 = row % a.ne[1], r = row / a.ne[1];
+            int64_t i2 = r % a.ne[2], i3 = r / a.ne[2];
+            v = ldf<TS>((const char*)a.data + k * a.nb[0] + i1 * a.nb[1] + i2 * a.nb[2] + i3 * a.nb[3]);
+        }
+        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        hi[i] = h;
+        lo[i] = v - h;
+    }
+}
+
 // 16-bit tiled transpose through shared memory: out[z][r = d][c = l] = in[z][l][d]
 __global__ void k_transpose_16(const char* __restrict__ src, uint16_t* __restrict__ dst, int D, int L, int64_t Lpad, int64_t nb1, int64_t nb2, int64_t nb3,
                                int ne2) {
@@ -912,6 +933,15 @@ int b200_launch_pack_rows(cudaStream_t s, const b200_td& a, void* dst, int dst_t
     return 1;
 }
 
+
+int b200_launch_split_tf32(cudaStream_t s, const b200_td& a, float* hi, float* lo, int64_t kpad) {
+    const int64_t nrows = a.ne[1] * a.ne[2] * a.ne[3];
+    const int64_t n = nrows * kpad;
+    if (n == 0) return 0;
+    if (a.type != GGML_TYPE_F32) return -1;
+    b200_launch(k_split_tf32<float>, dim3(grid_for(n)), dim3(kThreads), 0, s, a, hi, lo, kpad, nrows);
+    return 1;
+}
 
 int b200_launch_transpose_f16(cudaStream_t s, const b200_td& src, void* dst, int64_t Lpad) {
     const int64_t D = src.ne[0], L = src.ne[1], Z = src.ne[2] * src.ne[3];

@@ -446,17 +446,29 @@ int gemm2_mode() {
     return v;
 }
 
+int gemm_log() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GGML_B200_GEMM_LOG"); v = (e && *e) ? atoi(e) : 0; }
+    return v;
+}
+
 struct Plan2 { int bn; int splits; double cycles; };
 
 Plan2 choose_plan2(const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int nkb) {
     const int sms = dev.sm_count > 0 ? dev.sm_count : 148;
     Plan2 best{0, 1, 1e30};
     const int bns[] = {256, 224, 192, 160, 128, 96, 64, 48, 32};
+    // tuning overrides (scripts/tune_gemm.py): restrict the candidates to one tile width / split factor
+    static int force_bn = -1, force_splits = -1;
+    if (force_bn < 0) { const char* e = getenv("GGML_B200_GEMM2_BN"); force_bn = (e && *e) ? atoi(e) : 0; }
+    if (force_splits < 0) { const char* e = getenv("GGML_B200_GEMM2_SPLITS"); force_splits = (e && *e) ? atoi(e) : 0; }
     for (int bn : bns) {
+        if (force_bn && bn != force_bn && !(N <= force_bn / 2 && bn < force_bn)) continue;
         if (bn > 32 && N <= bn / 2) continue;
         const int64_t tiles = ((M + 255) / 256) * ((N + bn - 1) / bn) * batch;
         for (int splits = 1; splits <= 4; ++splits) {
             if (splits > 1 && (tiles * 2 * splits > sms || nkb / splits < 4)) break;
+            if (force_splits && splits != force_splits && !(splits == 1 && (tiles * 2 * force_splits > sms || nkb / force_splits < 4))) continue;
             const double t = b200_gemm_tc2_model(dev, M, N, batch, nkb, bn, splits);
             if (t < best.cycles) best = Plan2{bn, splits, t};
         }
@@ -508,7 +520,10 @@ int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_
         const Plan2 p2 = choose_plan2(dev, g.M, g.N, g.batch, nkb);
         if (p2.bn > 0 && (gemm2_mode() >= 2 || p2.cycles < cycles1)) {
             const int r = b200_launch_gemm_tc2(s, dev, g, p2.bn, p2.splits);
-            if (r > 0) return 2;       // 2: launched on the CTA-pair kernel
+            if (r > 0) {
+                if (gemm_log()) fprintf(stderr, "GEMMLOG pair gemm M %lld N %lld K %lld batch %lld bn %d splits %d model1 %.0f model2 %.0f\n", (long long)g.M, (long long)g.N, (long long)g.K, (long long)g.batch, p2.bn, p2.splits, cycles1, p2.cycles);
+                return 2;       // 2: launched on the CTA-pair kernel
+            }
         }
     }
 
@@ -535,6 +550,7 @@ int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     if (mt > 0x7fffffff || nt > 65535 || g.batch * pl.splits > 65535) return -1;
     (void)workspace; (void)workspace_bytes;
     dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)(g.batch * pl.splits));
+    if (gemm_log()) fprintf(stderr, "GEMMLOG one gemm M %lld N %lld K %lld batch %lld bn %d splits %d model1 %.0f\n", (long long)g.M, (long long)g.N, (long long)g.K, (long long)g.batch, pl.bn, pl.splits, cycles1);
     const int fmt = g.type == GGML_TYPE_F16 ? 0 : (g.type == GGML_TYPE_BF16 ? 1 : 2);
     cudaError_t e = cudaErrorInvalidValue;
 #define LAUNCH(BN_)                                                          \
@@ -583,11 +599,14 @@ int b200_launch_conv_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     const int nkb = (int)(g.K / 64);
     double cycles1 = 0;
     Plan pl = choose_plan(dev, g, nkb, &cycles1);
-    if (gemm2_mode() && g.M > BM && g.M % 128 == 0) {
+    if ((gemm2_mode() || c.D2) && g.M > BM && g.M % 128 == 0) {
         const Plan2 p2 = choose_plan2(dev, g.M, g.N, g.batch, nkb);
-        if (p2.bn > 0 && (gemm2_mode() >= 2 || p2.cycles < cycles1)) {
+        if (p2.bn > 0 && (gemm2_mode() >= 2 || c.D2 || p2.cycles < cycles1)) {
             const int r = b200_launch_conv_tc2(s, dev, c, p2.bn, p2.splits);
-            if (r > 0) return 2;
+            if (r > 0) {
+                if (gemm_log()) fprintf(stderr, "GEMMLOG pair conv M %lld N %lld K %lld batch %lld bn %d splits %d model1 %.0f model2 %.0f\n", (long long)g.M, (long long)g.N, (long long)g.K, (long long)g.batch, p2.bn, p2.splits, cycles1, p2.cycles);
+                return 2;
+            }
         }
     }
 
@@ -623,6 +642,7 @@ int b200_launch_conv_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     if (nt > 65535 || g.batch * pl.splits > 65535) return -1;
     (void)workspace; (void)workspace_bytes;
     dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)(g.batch * pl.splits));
+    if (gemm_log()) fprintf(stderr, "GEMMLOG one conv M %lld N %lld K %lld batch %lld bn %d splits %d model1 %.0f\n", (long long)g.M, (long long)g.N, (long long)g.K, (long long)g.batch, pl.bn, pl.splits, cycles1);
     cudaError_t e;
     if (pl.bn == 256) e = launch_cfg<256, 0>(s, grid, ta, tb, kp);
     else if (pl.bn == 128) e = launch_cfg<128, 0>(s, grid, ta, tb, kp);

@@ -55,6 +55,9 @@ struct G2Params {
     int64_t ldr, r_batch_stride;
     int act;
     int conv, conv_W, conv_KW, conv_cblocks, conv_pad, conv_dil;
+    float* D2;                // optional mirror of D in the PEER GPU's memory (NVLink mapping, kernels/peer.cu); slot chosen by *d2_seq
+    const unsigned* d2_seq;
+    int64_t d2_slot;
 };
 
 // ---- cta_group::2 flavours of the primitives in sm100_ptx.cuh
@@ -233,6 +236,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
             const int ncols = (int)min((int64_t)p.bn, p.N - n0);
             float* Dp = p.D + (int64_t)batch * p.d_batch_stride;
             const float* Rp = p.residual ? p.residual + (int64_t)batch * p.r_batch_stride : nullptr;
+            // fused collective: the same element also goes to the peer GPU (offset of D's element inside the mailbox slot)
+            const int64_t d2off = p.D2 ? (p.D2 - p.D) + (int64_t)((*p.d2_seq + 1u) & 1u) * p.d2_slot : 0;
             mbar_wait(&acc_full[buf], aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.acc_stride;
@@ -262,7 +267,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const float v = __uint_as_float(r[i]) + bias_m + __shfl_sync(0xffffffffu, bn, i);
-                            if (mvalid && c0 + i < ncols) dptr[(int64_t)(c0 + i) * p.ldd] = v;
+                            if (mvalid && c0 + i < ncols) {
+                                dptr[(int64_t)(c0 + i) * p.ldd] = v;
+                                if (p.D2) dptr[(int64_t)(c0 + i) * p.ldd + d2off] = v;
+                            }
                         }
                     } else {
                         float rr[32];
@@ -271,7 +279,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const float v = __uint_as_float(r[i]) + bias_m + __shfl_sync(0xffffffffu, bn, i) + rr[i];
-                            if (mvalid && c0 + i < ncols) dptr[(int64_t)(c0 + i) * p.ldd] = v;
+                            if (mvalid && c0 + i < ncols) {
+                                dptr[(int64_t)(c0 + i) * p.ldd] = v;
+                                if (p.D2) dptr[(int64_t)(c0 + i) * p.ldd + d2off] = v;
+                            }
                         }
                     }
                 }
@@ -290,6 +301,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                             v = act_fn(v, p.act);
                             if (Rp) v += Rp[n * p.ldr + m];
                             Dp[n * p.ldd + m] = v;
+                            if (p.D2) Dp[n * p.ldd + m + d2off] = v;
                         }
                     }
                 }
@@ -327,6 +339,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
             const int ncols = (int)min((int64_t)p.bn, p.N - n0);
             const int cbeg = (split * p.bn) / p.splits, cend = min(((split + 1) * p.bn) / p.splits, ncols);
             const bool vec_ok = (mrow + 3 < p.M) && ((p.ldd & 3) == 0) && ((((uintptr_t)Dp) & 15) == 0) && ((m0 & 3) == 0);
+            const int64_t d2off = p.D2 ? (p.D2 - p.D) + (int64_t)((*p.d2_seq + 1u) & 1u) * p.d2_slot : 0;
 #pragma unroll 1
             for (int c = cbeg + w8; c < cend; c += 8) {
                 const uint32_t off = (uint32_t)(c * BM + 4 * lane) * 4u;
@@ -344,11 +357,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                 if (vec_ok && (Rp == nullptr || (((p.ldr & 3) == 0) && ((((uintptr_t)Rp) & 15) == 0)))) {
                     if (Rp) { const float4 rr = *(const float4*)(Rp + n * p.ldr + mrow); v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
                     *(float4*)dst = v;
+                    if (p.D2) {
+                        if ((d2off & 3) == 0) *(float4*)(dst + d2off) = v;
+                        else { dst[d2off] = v.x; dst[d2off + 1] = v.y; dst[d2off + 2] = v.z; dst[d2off + 3] = v.w; }
+                    }
                 } else {
                     const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (mrow + u < p.M) dst[u] = vv[u] + (Rp ? Rp[n * p.ldr + mrow + u] : 0.f);
+                        if (mrow + u < p.M) {
+                            const float o = vv[u] + (Rp ? Rp[n * p.ldr + mrow + u] : 0.f);
+                            dst[u] = o;
+                            if (p.D2) dst[u + d2off] = o;
+                        }
                 }
             }
         }
@@ -531,6 +552,7 @@ int b200_launch_conv_tc2(cudaStream_t s, const b200_device_info& dev, const b200
     kp.ne12 = (int)c.N; kp.r2 = 1;
     kp.bias = c.bias; kp.bias_mode = c.bias ? 2 : 0;
     kp.residual = c.residual; kp.ldr = M; kp.r_batch_stride = c.OC * M;
+    kp.D2 = c.D2; kp.d2_seq = c.d2_seq; kp.d2_slot = c.d2_slot_floats;
     kp.conv = 1; kp.conv_W = (int)c.W; kp.conv_KW = c.KW; kp.conv_cblocks = (int)(c.C / 64); kp.conv_pad = c.pad; kp.conv_dil = c.dil;
     cudaError_t e = launch2<0>(s, ctas, (unsigned)splits, smem, ta, tb, kp);
     if (e != cudaSuccess) {

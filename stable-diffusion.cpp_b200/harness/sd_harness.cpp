@@ -241,6 +241,7 @@ struct sdh_model {
     double last_flops = 0;
     int last_nodes    = 0;
     std::map<std::string, ggml_tensor*> params;   // parameter tensors by checkpoint name (resident on the backend)
+    bool mailbox = false;                          // the backend's peer mailbox is connected (CFG split over NVLink)
 };
 
 namespace {
@@ -829,6 +830,33 @@ int sdh_model_backend_stats(sdh_model* m, double* out, int n) {
     return 0;
 }
 
+// CFG-split exchange through the backend's peer mailbox (include/ggml-b200.h ggml_backend_b200_peer_mailbox_*)
+static void* b200_proc(sdh_model* m, const char* name) {
+    ggml_backend_dev_t dev = ggml_backend_get_device(m->backend);
+    ggml_backend_reg_t reg = dev ? ggml_backend_dev_backend_reg(dev) : nullptr;
+    return reg ? ggml_backend_reg_get_proc_address(reg, name) : nullptr;
+}
+int sdh_model_mailbox_create(sdh_model* m, size_t bytes, void* handle_out64) {
+    if (!m) return fail("null argument");
+    auto fn = (int (*)(ggml_backend_t, size_t, void*))b200_proc(m, "ggml_backend_b200_peer_mailbox_create");
+    if (!fn) return fail("backend has no peer mailbox");
+    return fn(m->backend, bytes, handle_out64) == 0 ? 0 : fail("mailbox create failed");
+}
+int sdh_model_mailbox_connect(sdh_model* m, const void* peer_handle64) {
+    if (!m) return fail("null argument");
+    auto fn = (int (*)(ggml_backend_t, const void*))b200_proc(m, "ggml_backend_b200_peer_mailbox_connect");
+    if (!fn) return fail("backend has no peer mailbox");
+    if (fn(m->backend, peer_handle64) != 0) return fail("mailbox connect failed");
+    m->mailbox = true;
+    return 0;
+}
+void sdh_model_mailbox_close(sdh_model* m) {
+    if (!m) return;
+    auto fn = (void (*)(ggml_backend_t))b200_proc(m, "ggml_backend_b200_peer_mailbox_close");
+    if (fn) fn(m->backend);
+    m->mailbox = false;
+}
+
 int sdh_model_set_backend_option(sdh_model* m, const char* key, int value) {
     if (!m) return fail("null argument");
     ggml_backend_dev_t dev = ggml_backend_get_device(m->backend);
@@ -889,6 +917,19 @@ int sdh_sample_split(sdh_model* m, const char* method_s, int steps, float cfg_sc
             const int64_t half = noised_input.numel();
             cond_out   = sd::Tensor<float>(noised_input.shape(), std::vector<float>(both.data(), both.data() + half));
             uncond_out = sd::Tensor<float>(noised_input.shape(), std::vector<float>(both.data() + half, both.data() + 2 * half));
+        } else if ((role == 0 || role == 1) && !exchange && m->mailbox) {
+            // CFG batch split, device-side exchange: this rank evaluates ONE branch; the backend stores the eps prediction into the
+            // peer GPU's mailbox over NVLink at the end of the forward and waits for the peer's (kernels/peer.cu).  The host only reads
+            // its own result (as always) and the peer's payload from the local mailbox.
+            sd::Tensor<float> mine = role == 0 ? run_model(m, noised_input, timesteps_tensor, cond_t, yc)
+                                               : run_model(m, noised_input, timesteps_tensor, uncond_t, yu);
+            forwards++;
+            if (mine.empty()) { failed = true; return {}; }
+            sd::Tensor<float> other = sd::Tensor<float>::zeros_like(mine);
+            auto rd = (int (*)(ggml_backend_t, void*))b200_proc(m, "ggml_backend_b200_peer_mailbox_read");
+            if (!rd || rd(m->backend, other.data()) != 0) { failed = true; return {}; }
+            cond_out   = role == 0 ? mine : other;
+            uncond_out = role == 0 ? other : mine;
         } else if (role < 0 || role == 2 || !exchange) {
             cond_out = run_model(m, noised_input, timesteps_tensor, cond_t, yc);  // :2811
             forwards++;

@@ -43,7 +43,7 @@ EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C
 STAT_KEYS = ("graphs", "kernel_launches", "nodes_executed", "fused_nodes", "last_graph_ms", "total_graph_ms", "tc_gemm_launches",
              "tc_gemm_flops", "tc_gemm_us", "fused_attn_launches", "cuda_graph_replays", "implicit_convs", "q_read_in_place", "gemv_launches", "rope_launches", "_unused",
              "gemm_ref_launches", "host_us", "weight_write_graphs", "per_graph_filter_packs", "persistent_gemm_launches", "cta2_gemm_launches",
-             "derived_weight_bytes", "unfused_attention")
+             "derived_weight_bytes", "unfused_attention", "peer_exchanges")
 
 
 class Harness:
@@ -71,6 +71,9 @@ class Harness:
             lib.sdh_model_out_shape.argtypes = [C.c_void_p, P, C.POINTER(C.c_int64)]
             lib.sdh_model_forward.argtypes = [C.c_void_p, P, P, P, P, P, C.POINTER(C.c_double)]
             lib.sdh_model_dump_graph.argtypes = [C.c_void_p, P, P, P, P, C.c_char_p]
+            lib.sdh_model_mailbox_create.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+            lib.sdh_model_mailbox_connect.argtypes = [C.c_void_p, C.c_void_p]
+            lib.sdh_model_mailbox_close.argtypes = [C.c_void_p]
             lib.sdh_model_add_to_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_float]
             lib.sdh_model_export_graph.argtypes = [C.c_void_p, P, P, P, P, C.c_char_p]
             lib.sdh_model_last_graph_flops.argtypes = [C.c_void_p]
@@ -216,6 +219,22 @@ class Model:
         if n < 0:
             raise RuntimeError(self.h.last_error())
         return n, self.lib.sdh_model_last_graph_flops(self.ptr)
+
+    def mailbox_create(self, nbytes: int) -> bytes:
+        """Allocate the backend's peer mailbox for payloads of nbytes; returns the 64-byte CUDA IPC handle to hand to the other rank."""
+        buf = C.create_string_buffer(64)
+        if self.lib.sdh_model_mailbox_create(self.ptr, nbytes, buf) != 0:
+            raise RuntimeError(self.h.last_error())
+        return buf.raw
+
+    def mailbox_connect(self, peer_handle: bytes | None):
+        """Map the other rank's mailbox (None: loopback self test); from now on sample(role=0|1, exchange=None) exchanges on the device."""
+        buf = C.create_string_buffer(peer_handle, 64) if peer_handle is not None else None
+        if self.lib.sdh_model_mailbox_connect(self.ptr, buf) != 0:
+            raise RuntimeError(self.h.last_error())
+
+    def mailbox_close(self):
+        self.lib.sdh_model_mailbox_close(self.ptr)
 
     def add_to_weight(self, name_substr: str, n_dims: int, value: float) -> int:
         """w += value through a graph on the model's backend (the reference's LoRA-apply pattern); returns the element count."""

@@ -74,6 +74,24 @@ def test_vae_decode_512_vs_live_cpu(b200):
     assert r < 2e-3, f"rel_l2 {r:.2e}"
 
 
+def test_vae_decode_1024_vs_live_cpu(b200):
+    """BASELINE configs 3-4 image size: 128x128x4 -> 1024x1024x3; the mid-block attention (one head, d = 512, L = 16384) runs as
+    tensor-core GEMM + softmax + GEMM (outside the fused kernel's head-size envelope; 5 % of the decode)."""
+    h, dev = b200
+    z = h.randn(45, (1, 4, 128, 128))
+    m = h.model(dev, "vae_decoder", "f16", 0, 1234, 0)
+    ours, _ = m.forward(z)
+    st = no_fallback(m)
+    m.close()
+    m = h.model("CPU", "vae_decoder", "f16", 0, 1234, 0)
+    cpu, _ = m.forward(z)
+    m.close()
+    assert ours.shape == (1, 3, 1024, 1024) and np.isfinite(ours).all()
+    r = rel(ours, cpu)
+    print(f"vae 1024: rel_l2 {r:.3e}")
+    assert r < 2e-3, f"rel_l2 {r:.2e}"
+
+
 def test_sdxl_unet_128_bf16_vs_live_cpu(b200):
     """BASELINE config 3 at its quoted size: SDXL UNet, 128x128x4 latent (1024x1024), BF16 linears / F16 convs.  Both of our graph
     variants against the CPU's default graph (bf16 operands: 8-bit mantissa, so the level is bf16 rounding noise)."""
