@@ -581,6 +581,7 @@ int ggml_backend_b200_get_stats(ggml_backend_t backend, ggml_b200_stats* out) {
     if (!ggml_backend_is_b200(backend) || !out) return -1;
     static_assert(sizeof(ggml_b200_stats) == sizeof(b200_stats), "stats ABI mismatch");
     b200_context_finalize_timing((b200_context*)backend->context);
+    ((b200_context*)backend->context)->stats.ext[6] = b200_derived_weight_bytes();
     memcpy(out, &((b200_context*)backend->context)->stats, sizeof(*out));
     return 0;
 }

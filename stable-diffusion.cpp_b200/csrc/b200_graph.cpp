@@ -53,6 +53,7 @@ b200_context* b200_context_create(const b200_device_info& info) {
     ctx->opt_chain_fusion = env_flag("GGML_B200_CHAIN_FUSION", 1) != 0;
     ctx->opt_gemv = env_flag("GGML_B200_GEMV", 1) != 0;
     ctx->opt_precise_f32 = env_flag("GGML_B200_PRECISE_F32", 1) != 0;
+    ctx->opt_q8_activations = env_flag("GGML_B200_Q8_ACT", 1) != 0;
     ctx->opt_persistent_gemm = env_flag("GGML_B200_PERSISTENT", 0) != 0;   // experimental persistent GEMM (gemm_tc_persist.cu), never run on hardware yet
     ctx->opt_fold_batch = env_flag("GGML_B200_FOLD_BATCH", 0) != 0;   // written at the end of round 1, not yet measured: off by default
     return ctx;
@@ -91,6 +92,7 @@ int b200_context_set_option(b200_context* ctx, const char* key, int value) {
     else if (!strcmp(key, "fold_batch")) ctx->opt_fold_batch = value != 0;
     else if (!strcmp(key, "persistent_gemm")) ctx->opt_persistent_gemm = value != 0;
     else if (!strcmp(key, "precise_f32")) ctx->opt_precise_f32 = value != 0;
+    else if (!strcmp(key, "q8_activations")) ctx->opt_q8_activations = value != 0;
     else return -1;
     return 0;
 }
@@ -391,7 +393,26 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
 
     operand a, b;
     if (!prepare_operand(ctx, src0, ct, &a, &launches)) return -1;
-    if (!prepare_operand(ctx, src1, ct, &b, &launches)) return -1;
+    bool have_b = false;
+    if (src0->type == GGML_TYPE_Q8_0 && src1->type == GGML_TYPE_F32 && ctx->opt_q8_activations && K % 32 == 0) {
+        // the oracle quantises the activation rows to Q8_0 as well (q8_0 x q8_0 dot, ggml-cpu.c:1480-1510): contract the same values
+        const int key = 2000;
+        auto hit = ctx->pack_cache.find(std::make_pair(src1, key));
+        if (hit != ctx->pack_cache.end()) { b = hit->second; have_b = true; }
+        else {
+            const int64_t rows = src1->ne[1] * src1->ne[2] * src1->ne[3];
+            void* buf = ws_alloc(ctx, (size_t)(rows * K * 2));
+            if (!buf) return -1;
+            const int n = b200_launch_pack_rows_q8_roundtrip(ctx->stream, b200_make_td(src1), buf, K);
+            if (n > 0) {
+                launches += n;
+                b = operand{buf, GGML_TYPE_F16, K, K * src1->ne[1], K * src1->ne[1] * src1->ne[2]};
+                ctx->pack_cache[std::make_pair(src1, key)] = b;
+                have_b = true;
+            }
+        }
+    }
+    if (!have_b && !prepare_operand(ctx, src1, ct, &b, &launches)) return -1;
 
     // One weight matrix against a batch of activation matrices that lie back to back in memory (a Linear on [C, L, N] tokens of a
     // batched-CFG graph): fold the batch into the N dimension -- fewer, fuller tiles (N = 64 + 64 fills one 128-row tile instead of
@@ -1051,6 +1072,8 @@ static std::atomic<uint64_t> g_pw_bytes{0};
 // bumped whenever a derived weight copy is dropped: captured CUDA graphs hold raw pointers to those copies and must not be replayed
 // across such an event (a long-lived backend whose model was reloaded at the same addresses)
 static std::atomic<uint64_t> g_pw_generation{0};
+
+uint64_t b200_derived_weight_bytes() { return g_pw_bytes.load(std::memory_order_relaxed); }
 
 void b200_invalidate_address_range(int device, const void* ptr, size_t size) {
     std::lock_guard<std::mutex> lock(g_pw_mutex);
@@ -1923,12 +1946,11 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
     ctx->peer_fused = false;
     ctx->graph_pushed = false;
     if (ctx->peer.connected) {
-        // the tensor to exchange: the graph's last OUTPUT node, when it has exactly the mailbox's payload size (the eps prediction)
-        for (int i = cgraph->n_nodes - 1; i >= 0; --i) {
-            const ggml_tensor* t = cgraph->nodes[i];
-            if (!(t->flags & GGML_TENSOR_FLAG_OUTPUT)) continue;
-            if (t->type == GGML_TYPE_F32 && ggml_is_contiguous(t) && ggml_nbytes(t) == ctx->peer.bytes) ctx->peer_out = t->data;
-            break;
+        // the tensor to exchange: the graph's result -- its LAST node (what the reference's runner reads back, ggml_extend.hpp:2049,2909) --
+        // when it has exactly the mailbox's payload size (the eps prediction)
+        if (cgraph->n_nodes > 0) {
+            const ggml_tensor* t = cgraph->nodes[cgraph->n_nodes - 1];
+            if (t->type == GGML_TYPE_F32 && ggml_is_contiguous(t) && ggml_nbytes(t) == ctx->peer.bytes && t->data) ctx->peer_out = t->data;
         }
     }
     const bool fuse = ctx->opt_fusion && cgraph->n_nodes > 1;

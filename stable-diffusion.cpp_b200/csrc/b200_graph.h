@@ -52,6 +52,7 @@ struct b200_context {
     bool opt_fold_batch = false;      // MUL_MAT of one weight matrix against a contiguous batch of activations runs as one GEMM with N * batch rows
     bool opt_persistent_gemm = false; // EXPERIMENTAL persistent GEMM with double-buffered TMEM accumulators (not validated on hardware)
     bool opt_precise_f32 = true;      // F32 x F32 MUL_MAT as 3xTF32 (hi/lo operand split, three tensor-core passes): f32-class accuracy like the CPU oracle's f32 dot
+    bool opt_q8_activations = true;   // Q8_0-weight contractions quantise the activation rows to Q8_0 like the CPU oracle does (q8_0 x q8_0 dot)
     bool opt_kernel_timing = false;   // per-launch CUDA events around every tcgen05 GEMM (roofline pass only)
     bool timing_pending = false;
     struct kt_pair { cudaEvent_t start, stop; double flops; };
@@ -103,6 +104,7 @@ bool b200_supports_op(const b200_device_info& dev, const ggml_tensor* op);
 void b200_invalidate_address_range(int device, const void* ptr, size_t size);
 // weight ingest: derive the layouts the kernels read (packed 3x3 conv filters, Q8_0 -> f16 rows) when a weight is uploaded
 void b200_ingest_weight(int device, const ggml_tensor* w);
+uint64_t b200_derived_weight_bytes();
 
 // CFG-split exchange (kernels/peer.cu)
 int b200_peer_create(b200_context* ctx, size_t bytes, void* ipc_handle_out64);

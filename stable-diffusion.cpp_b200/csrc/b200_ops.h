@@ -30,6 +30,8 @@ int b200_launch_sum_rows(cudaStream_t s, const b200_td& src, const b200_td& dst,
 // f32 -> f16/bf16 pack of a strided 2-D/4-D operand into a dense K-major matrix with K padded to kpad (zero filled)
 int b200_launch_pack_rows(cudaStream_t s, const b200_td& src, void* dst, int dst_type, int64_t kpad);
 
+// activation of a Q8_0-weight contraction: quantise each 32-value block like the oracle (quantize_row_q8_0) and store d * q as f16
+int b200_launch_pack_rows_q8_roundtrip(cudaStream_t s, const b200_td& a, void* dst_f16, int64_t kpad);
 // 3xTF32: f32 [K, rows, b2, b3] (any strides) -> hi / lo dense [rows][kpad] f32 (x = hi + lo, hi exactly representable in TF32)
 int b200_launch_split_tf32(cudaStream_t s, const b200_td& a, float* hi, float* lo, int64_t kpad);
 

@@ -42,6 +42,8 @@ struct FaParams {
     int64_t m_nb1, m_nb2, m_nb3;
     int m_ne2, m_ne3;
     int d, dv16, Lq, Lk, H, rk;    // rk = H / Hkv
+    int pos_scale;                 // scale > 0: the row maximum may be taken before scaling
+    int q_vec;                     // Q rows are 16-byte aligned and d % 4 == 0: coalesced float4 loads
     float scale_log2;              // scale * log2(e)
     float log2e;
 };
@@ -58,23 +60,33 @@ template <int NATOM, int BLOCK_N> struct FaCfg {
     static constexpr int VROWS_MAX = NATOM * 64;                       // dv16 <= NATOM * 64
     static constexpr int V_STAGE = (BLOCK_N / 64) * VROWS_MAX * 128;
     static constexpr int P_BYTES = (BLOCK_N / 64) * BLOCK_M * 128;
-    static constexpr int SMEM = Q_BYTES + 2 * K_STAGE + 2 * V_STAGE + P_BYTES + 1024;
+    static constexpr int BAR_BYTES = 128;                               // 13 mbarriers + the TMEM base word, carved from the dynamic allocation
+    // no alignment slack and no static shared memory: the dynamic window is 1024-byte aligned by declaration, and two CTAs of the
+    // d = 128 / 64-key configuration fit one SM exactly (2 x (112 KB + 128 B) + the 1 KB the system reserves per CTA <= 228 KB)
+    static constexpr int SMEM = Q_BYTES + 2 * K_STAGE + 2 * V_STAGE + P_BYTES + BAR_BYTES;
+    static constexpr int MIN_CTAS = (2 * (SMEM + 1024) <= 228 * 1024 && 2 * ((2 * BLOCK_N + NATOM * 64) <= 256 ? 256 : 512) <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (2 * BLOCK_N + NATOM * 64) <= 256 ? 256 : 512;
 };
 
 template <int NATOM, int BLOCK_N>
-__global__ void __launch_bounds__(192, 1) k_flash_attn(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                                                       const FaParams p) {
+__global__ void __launch_bounds__(192, FaCfg<NATOM, BLOCK_N>::MIN_CTAS) k_flash_attn(const __grid_constant__ CUtensorMap tmK,
+                                                                                     const __grid_constant__ CUtensorMap tmV, const FaParams p) {
     using C = FaCfg<NATOM, BLOCK_N>;
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full, pv_done, q_ready;
-    __shared__ uint32_t tmem_base_smem;
-
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + C::Q_BYTES;
     uint8_t* sV = sK + 2 * C::K_STAGE;
     uint8_t* sP = sV + 2 * C::V_STAGE;
+    uint64_t* bars = (uint64_t*)(sP + C::P_BYTES);
+    uint64_t* k_full = bars;            // [2]
+    uint64_t* k_empty = bars + 2;       // [2]
+    uint64_t* v_full = bars + 4;        // [2]
+    uint64_t* v_empty = bars + 6;       // [2]
+    uint64_t* s_full = bars + 8;        // [2]
+    uint64_t& p_full = bars[10];
+    uint64_t& pv_done = bars[11];
+    uint64_t& q_ready = bars[12];
+    uint32_t& tmem_base_smem = *(uint32_t*)(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * BLOCK_M;
@@ -171,7 +183,32 @@ __global__ void __launch_bounds__(192, 1) k_flash_attn(const __grid_constant__ C
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
 
         // ---- Q tile: f32 global -> f16, K-major 128B-swizzled shared memory (zero padded to NATOM*64 columns)
-        {
+        if (p.q_vec) {
+            // coalesced: the warp walks its 32 rows; lane L converts columns 4L .. 4L+3 (+128 per pass) of the row -- one 512-byte row
+            // segment per load instruction instead of 32 scattered 4-byte reads
+#pragma unroll 1
+            for (int rr = 0; rr < 32; ++rr) {
+                const int row = qd * 32 + rr;
+                const int qrow_i = q0 + row;
+                const float* qrow = (const float*)((const char*)p.q + (int64_t)qrow_i * p.q_nb1 + (int64_t)h * p.q_nb2 + (int64_t)nb * p.q_nb3);
+#pragma unroll
+                for (int c0 = 0; c0 < NATOM * 64; c0 += 128) {
+                    const int col = c0 + lane * 4;
+                    if (col < NATOM * 64) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (qrow_i < p.Lq && col < p.d) v = *(const float4*)(qrow + col);       // d % 4 == 0: a float4 is all inside or all outside
+                        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+                        const int chunk = col >> 3, atom = chunk >> 3, cc = chunk & 7;
+                        uint2 val;
+                        val.x = *(const uint32_t*)&h0;
+                        val.y = *(const uint32_t*)&h1;
+                        *(uint2*)(sQ + atom * (BLOCK_M * 128) + row * 128 + ((cc ^ (row & 7)) << 4) + ((col & 4) << 1)) = val;
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&q_ready);
+        } else {
             const bool valid = qi < p.Lq;
             const float* qrow = (const float*)((const char*)p.q + (int64_t)qi * p.q_nb1 + (int64_t)h * p.q_nb2 + (int64_t)nb * p.q_nb3);
 #pragma unroll 1
@@ -204,24 +241,38 @@ __global__ void __launch_bounds__(192, 1) k_flash_attn(const __grid_constant__ C
             const int kbase = j * BLOCK_N;
             mbar_wait(&s_full[s], (j >> 1) & 1);
             tc_fence_after();
-            // ---- S row: ONE TMEM read into registers (scaled to the log2 domain, mask added, tail keys -> -inf), row maximum
+            // ---- S row: ONE TMEM read into registers, row maximum.  Common case (no mask, all keys of the tile valid): the raw scores stay
+            //      in registers and the scale is folded into the exponent's FMA below; otherwise scale, mask and the -inf tail are applied here
             float sv[BLOCK_N];
-            float mx = -INFINITY;
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            const bool plain = p.pos_scale && (mrow == nullptr) && (kbase + BLOCK_N <= p.Lk);
+            const float mul = plain ? p.scale_log2 : 1.0f;
 #pragma unroll
             for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tS + c0, v);
                 tmem_ld_wait();
+                if (plain) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int key = kbase + c0 + i;
-                    float t = __uint_as_float(v[i]) * p.scale_log2;
-                    if (mrow && key < p.Lk) t += __half2float(mrow[key]) * p.log2e;
-                    t = key < p.Lk ? t : -INFINITY;
-                    sv[c0 + i] = t;
-                    mx = fmaxf(mx, t);
+                    for (int i = 0; i < 32; ++i) {
+                        const float t = __uint_as_float(v[i]);
+                        sv[c0 + i] = t;
+                        mx4[i & 3] = fmaxf(mx4[i & 3], t);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int key = kbase + c0 + i;
+                        float t = __uint_as_float(v[i]) * p.scale_log2;
+                        if (mrow && key < p.Lk) t += __half2float(mrow[key]) * p.log2e;
+                        t = key < p.Lk ? t : -INFINITY;
+                        sv[c0 + i] = t;
+                        mx4[i & 3] = fmaxf(mx4[i & 3], t);
+                    }
                 }
             }
+            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            if (plain) mx *= p.scale_log2;                       // scale > 0: the maximum commutes with it
             float m_new = fmaxf(m_ref, mx);
             if (m_new == -INFINITY) m_new = 0.f;                  // fully masked row so far
             bool grow = (j == 0) || (m_new - m_ref > kLazyThreshold);
@@ -247,18 +298,20 @@ __global__ void __launch_bounds__(192, 1) k_flash_attn(const __grid_constant__ C
             }
             if (grow) m_ref = m_new;
             // ---- pass 2: P = exp2(s - m_ref), row sum, f16 into swizzled shared memory
-            float lsum = 0.f;
+            float ls4[4] = {0.f, 0.f, 0.f, 0.f};
             uint32_t ph[BLOCK_N / 2];   // the whole P row as packed half2, kept in registers until the P buffer is free
+            const float neg_m = -m_ref;
 #pragma unroll
             for (int i = 0; i < BLOCK_N; i += 2) {
-                const float e0 = fast_exp2(sv[i] - m_ref), e1 = fast_exp2(sv[i + 1] - m_ref);   // exp2(-inf) == 0 for masked / tail keys
+                // exp2(s * scale - m): one FMA feeding the MUFU (mul == 1 when the scale was applied above); exp2(-inf) == 0 for masked / tail keys
+                const float e0 = fast_exp2(fmaf(sv[i], mul, neg_m)), e1 = fast_exp2(fmaf(sv[i + 1], mul, neg_m));
                 const __half2 hv = __floats2half2_rn(e0, e1);
                 // accumulate the sum from the ROUNDED probabilities: what the tensor core multiplies is what we normalise by
                 const float2 f = __half22float2(hv);
-                lsum += f.x + f.y;
+                ls4[(i >> 1) & 3] += f.x + f.y;
                 ph[i >> 1] = *(const uint32_t*)&hv;
             }
-            l += lsum;
+            l += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
             if (!waited) {
                 mbar_wait(&pv_done, (j - 1) & 1);
                 tc_fence_after();
@@ -280,33 +333,48 @@ __global__ void __launch_bounds__(192, 1) k_flash_attn(const __grid_constant__ C
         float* drow = (float*)((char*)p.dst + (int64_t)h * p.dst_nb1 + (int64_t)qi * p.dst_nb2 + (int64_t)nb * p.dst_nb3);
         __half* drow16 = p.dst16 ? (__half*)((char*)p.dst16 + (((int64_t)h * p.dst_nb1 + (int64_t)qi * p.dst_nb2 + (int64_t)nb * p.dst_nb3) >> 1)) : nullptr;
         const int dv = p.d;
+        // f32 result: each warp transposes its 32 rows x 32 columns through shared memory (the K / V rings are dead: every MMA has retired,
+        // no TMA is in flight) so that a store instruction writes 128 contiguous bytes of ONE query row instead of 4 bytes of 32 rows
+        float* tile = (float*)sK + qd * (32 * 33);
+        const char* dbase = (const char*)p.dst + (int64_t)h * p.dst_nb1 + (int64_t)nb * p.dst_nb3;
 #pragma unroll 1
-        for (int c0 = 0; c0 < p.dv16; c0 += 16) {
-            uint32_t o[16];
-            tmem_ld16(tmem_O + lane_off + c0, o);
+        for (int c0 = 0; c0 < p.dv16; c0 += 32) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_off + c0, o);
             tmem_ld_wait();
-            if (qi < p.Lq) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (c0 + i < dv) drow[c0 + i] = __uint_as_float(o[i]) * inv;
-                if (drow16) {
-                    if (c0 + 16 <= dv) {       // d % 8 == 0 and 16-byte aligned rows: two 16-byte stores
-                        uint32_t h[8];
+            for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = __uint_as_float(o[i]) * inv;
+            if (drow16 && qi < p.Lq) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int cb = c0 + hh * 16;
+                    if (cb + 16 <= dv) {       // d % 8 == 0 and 16-byte aligned rows: two 16-byte stores
+                        uint32_t hp[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const __half2 v = __floats2half2_rn(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
-                            h[i] = *(const uint32_t*)&v;
+                            const __half2 v = __floats2half2_rn(__uint_as_float(o[hh * 16 + 2 * i]) * inv, __uint_as_float(o[hh * 16 + 2 * i + 1]) * inv);
+                            hp[i] = *(const uint32_t*)&v;
                         }
-                        *(uint4*)(drow16 + c0) = make_uint4(h[0], h[1], h[2], h[3]);
-                        *(uint4*)(drow16 + c0 + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+                        *(uint4*)(drow16 + cb) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                        *(uint4*)(drow16 + cb + 8) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            if (c0 + i < dv) drow16[c0 + i] = __float2half_rn(__uint_as_float(o[i]) * inv);
+                            if (cb + i < dv) drow16[cb + i] = __float2half_rn(__uint_as_float(o[hh * 16 + i]) * inv);
                     }
                 }
             }
+            __syncwarp();
+            if (c0 + lane < dv) {
+#pragma unroll 4
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int qrow_i = q0 + qd * 32 + rr;
+                    if (qrow_i < p.Lq) *(float*)(dbase + (int64_t)qrow_i * p.dst_nb2 + (int64_t)(c0 + lane) * 4) = tile[rr * 33 + lane];
+                }
+            }
+            __syncwarp();
         }
+        (void)drow;
         tc_fence_before();
     }
     __syncthreads();
@@ -359,7 +427,11 @@ int b200_launch_flash_attn_fused(cudaStream_t s, const b200_td& q, const b200_td
     const int natom = (int)((d + 63) / 64);
     // d <= 64: 64-key tiles keep a CTA at 65 KB of shared memory and 256 TMEM columns, so two CTAs share an SM and one's
     // softmax overlaps the other's MMAs (the per-tile dependency chain S -> softmax -> P -> PV is latency bound)
-    const int block_n = natom == 2 ? 128 : 64;
+    // d in (64, 128]: 64-key tiles as well -- 112 KB of shared memory and 256 TMEM columns per CTA, so two CTAs (two softmax warpgroups,
+    // two MMA streams) share an SM; the 128-key variant (one CTA per SM) is kept behind GGML_B200_FA_BN128=1 for A/B runs
+    static int bn128 = -1;
+    if (bn128 < 0) { const char* e = getenv("GGML_B200_FA_BN128"); bn128 = (e && *e) ? atoi(e) : 0; }
+    const int block_n = (natom == 2 && bn128) ? 128 : 64;
     const int dv16 = (int)((dv + 15) / 16 * 16);
 
     CUtensorMap tk, tv;
@@ -387,11 +459,13 @@ int b200_launch_flash_attn_fused(cudaStream_t s, const b200_td& q, const b200_td
         p.m_ne2 = p.m_ne3 = 1;
     }
     p.d = (int)d; p.dv16 = dv16; p.Lq = (int)Lq; p.Lk = (int)Lk; p.H = (int)H; p.rk = (int)(H / Hkv);
+    p.q_vec = (((uintptr_t)q.data & 15) == 0 && (q.nb[1] & 15) == 0 && (q.nb[2] & 15) == 0 && (q.nb[3] & 15) == 0 && (d & 3) == 0) ? 1 : 0;
+    p.pos_scale = scale > 0.f ? 1 : 0;
     p.log2e = 1.4426950408889634f;
     p.scale_log2 = scale * p.log2e;
     dim3 grid((unsigned)((Lq + BLOCK_M - 1) / BLOCK_M), (unsigned)H, (unsigned)NB);
     if (H > 65535 || NB > 65535) return -1;
     if (natom == 1) return launch_fa<1, 64>(s, grid, tk, tv, p);
-    if (natom == 2) return launch_fa<2, 128>(s, grid, tk, tv, p);
+    if (natom == 2) return block_n == 128 ? launch_fa<2, 128>(s, grid, tk, tv, p) : launch_fa<2, 64>(s, grid, tk, tv, p);
     return launch_fa<3, 64>(s, grid, tk, tv, p);
 }

@@ -644,6 +644,37 @@ __global__ void k_pack_rows(b200_td a, TD* __restrict__ d, int64_t kpad, int64_t
 }
 
 
+// Activation operand of a Q8_0-weight contraction.  The CPU oracle quantises every activation row to Q8_0 blocks before the dot product
+// (ggml-cpu.c:1480-1510 -> quantize_row_q8_0: per 32 values d = max|x| / 127 stored as f16, q = round(x / d)) and multiplies int8 x int8
+// with the two block scales.  This kernel applies the SAME quantisation and writes d * q back as f16 (exact in f32, one f16 rounding):
+// the tensor-core GEMM then contracts the very values the oracle contracts, instead of the un-quantised activations.
+// One warp per (row, 32-value block); dense [rows][kpad] f16 out, kpad % 32 == 0, K zero padded.
+__global__ void k_pack_rows_q8_roundtrip(b200_td a, __half* __restrict__ d, int64_t kpad, int64_t nrows) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int lane = threadIdx.x & 31;
+    const int64_t nblk = kpad / 32;
+    const int64_t total = nrows * nblk;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        const int64_t row = w / nblk, blk = w - row * nblk;
+        const int64_t k = blk * 32 + lane;
+        float v = 0.f;
+        if (k < a.ne[0]) {
+            int64_t i1 = row % a.ne[1], r = row / a.ne[1];
+            int64_t i2 = r % a.ne[2], i3 = r / a.ne[2];
+            v = *(const float*)((const char*)a.data + k * a.nb[0] + i1 * a.nb[1] + i2 * a.nb[2] + i3 * a.nb[3]);
+        }
+        float amax = fabsf(v);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        const float dq = amax / 127.0f;
+        const float id = dq != 0.f ? 1.0f / dq : 0.f;
+        const float dh = __half2float(__float2half_rn(dq));       // the scale as stored (f16) and used by the oracle's dot product
+        const float q = rintf(v * id);                             // round to nearest even, like the AVX quantiser the oracle runs
+        d[row * kpad + k] = __float2half_rn(dh * q);
+    }
+}
+
 // f32 operand -> (hi, lo) pair for the 3xTF32 contraction: hi = x with the 13 low mantissa bits cleared (exactly representable in TF32,
 // whatever rounding the tensor core applies to its inputs), lo = x - hi (exact in f32).  Dense [rows][kpad] f32 each, K zero padded.
 template <typename TS>
@@ -933,6 +964,14 @@ int b200_launch_pack_rows(cudaStream_t s, const b200_td& a, void* dst, int dst_t
     return 1;
 }
 
+
+int b200_launch_pack_rows_q8_roundtrip(cudaStream_t s, const b200_td& a, void* dst_f16, int64_t kpad) {
+    const int64_t nrows = a.ne[1] * a.ne[2] * a.ne[3];
+    if (nrows * kpad == 0) return 0;
+    if (a.type != GGML_TYPE_F32 || kpad % 32 != 0) return -1;
+    b200_launch(k_pack_rows_q8_roundtrip, dim3(grid_for(nrows * kpad)), dim3(kThreads), 0, s, a, (__half*)dst_f16, kpad, nrows);
+    return 1;
+}
 
 int b200_launch_split_tf32(cudaStream_t s, const b200_td& a, float* hi, float* lo, int64_t kpad) {
     const int64_t nrows = a.ne[1] * a.ne[2] * a.ne[3];

@@ -11,8 +11,8 @@
 //   * TMEM holds TWO accumulators (2 x BN columns): the MMA issuer starts the main loop of tile i + 1 while the eight epilogue warps
 //     of both CTAs drain tile i (acc_full / acc_empty mbarriers) -- the epilogue, 43 % of the warp samples in round 1, leaves the
 //     critical path whenever a pair owns more than one tile
-//   * warp roles per CTA (320 threads): warp 0 = TMA producer (each CTA loads its A rows and its half of B; completion is signalled on
-//     the LEADER CTA's full barrier: `cp.async.bulk.tensor...cta_group::2`), warp 1 = TMEM allocation (both CTAs) and, in the leader
+//   * warp roles per CTA (352 threads): warps 0 and 10 = TMA producers for A and B (each CTA loads its A rows and its half of B; completion
+//     is signalled on the LEADER CTA's full barrier: `cp.async.bulk.tensor...cta_group::2`), warp 1 = TMEM allocation (both CTAs) and, in the leader
 //     only, the single-thread MMA issue + `tcgen05.commit...multicast::cluster` that frees the ring slot in both CTAs,
 //     warps 2..9 = epilogue (two warps per TMEM lane quadrant, alternating 32-column chunks)
 //   * small-M / small-N problems with a long K: split-K inside the cluster (2, 1, splits): partial tiles stay in shared memory and
@@ -37,7 +37,7 @@ constexpr int BM = 128;                 // rows of A per CTA (TMEM lanes); the p
 constexpr int BK_BYTES = 128;
 constexpr int A_STAGE_BYTES = BM * BK_BYTES;
 constexpr int MAX_STAGES = 10;
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS = 352;             // warps: 0 = A producer, 1 = TMEM / MMA issuer, 2..9 = epilogue, 10 = B producer
 
 struct G2Params {
     float* D;
@@ -54,6 +54,7 @@ struct G2Params {
     const float* residual;
     int64_t ldr, r_batch_stride;
     int act;
+    int nprod;              // TMA producer threads per CTA: 2 (A and B issued by different warps, default) or 1 (A/B of GGML_B200_GEMM2_NPROD)
     int conv, conv_W, conv_KW, conv_cblocks, conv_pad, conv_dil;
     float* D2;                // optional mirror of D in the PEER GPU's memory (NVLink mapping, kernels/peer.cu); slot chosen by *d2_seq
     const unsigned* d2_seq;
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full_bar[s], 2);      // one arrive.expect_tx from the producer of each CTA of the pair (used in the leader only)
+            mbar_init(&full_bar[s], 2 * p.nprod);      // one arrive.expect_tx from each of the two producer threads (A, B) of each CTA of the pair (leader's barrier)
             mbar_init(&empty_bar[s], 1);     // one multicast tcgen05.commit
         }
         for (int b = 0; b < 2; ++b) {
@@ -159,33 +160,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
         n0 = nt * p.bn;                            // first column of the pair's tile
     };
 
-    if (warp == 0) {
-        if (lane == 0) {
-            // ===================== TMA producer (both CTAs) =====================
+    if (warp == 0 || warp == 10) {
+        if (lane == 0 && (warp == 0 || p.nprod == 2)) {
+            // ===================== TMA producers (both CTAs): warp 0 streams the A tiles, warp 10 the B half-tiles =====================
+            // One thread issuing both loads of a k-block was the main-loop limiter on small tiles (about 650 clk per k-block whatever the
+            // box size: the issue path of cp.async.bulk.tensor, not bandwidth); two independent issuers halve it.
+            const bool is_a = warp == 0;
             const uint32_t full0 = dsmem_map(smem_u32(&full_bar[0]), leader);
+            const bool both = p.nprod == 1;        // single-producer variant: this thread issues the B load as well
+            const uint32_t my_bytes = both ? my_stage_bytes : (is_a ? (uint32_t)A_STAGE_BYTES : (uint32_t)(half_bn * BK_BYTES));
             uint32_t it = 0;
             for (int t = pair; t < p.total_tiles; t += npairs) {
                 int m0, n0, batch;
                 decode(t, m0, n0, batch);
                 const int i2 = batch % p.ne12, i3 = batch / p.ne12;
                 const int nb = n0 + (int)prank * half_bn;          // this CTA's half of the B tile
+                const int y0 = p.conv ? m0 / p.conv_W : 0, x0 = p.conv ? m0 - y0 * p.conv_W : 0;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = (int)(it % (uint32_t)p.stages);
                     const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
                     mbar_wait(&empty_bar[s], ph ^ 1u);
                     const uint32_t fb = full0 + 8u * (uint32_t)s;
-                    mbar_expect_tx_cluster(fb, my_stage_bytes);
+                    mbar_expect_tx_cluster(fb, my_bytes);
                     uint8_t* sa = smem + (size_t)s * p.stage_bytes;
-                    uint8_t* sb = sa + A_STAGE_BYTES;
-                    if (p.conv) {
+                    if (!is_a || both) tma_load_4d_2cta(sa + A_STAGE_BYTES, &tmB, fb, kb * BK, nb, p.conv ? 0 : i2, p.conv ? 0 : i3);
+                    if (!is_a) {
+                    } else if (p.conv) {
                         const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
                         const int kh = tap / p.conv_KW, kw = tap - kh * p.conv_KW;
-                        const int y0 = m0 / p.conv_W, x0 = m0 - y0 * p.conv_W;
                         tma_load_4d_2cta(sa, &tmA, fb, cb * 64, x0 + kw * p.conv_dil - p.conv_pad, y0 + kh * p.conv_dil - p.conv_pad, i2);
-                        tma_load_4d_2cta(sb, &tmB, fb, kb * BK, nb, 0, 0);
                     } else {
                         tma_load_4d_2cta(sa, &tmA, fb, kb * BK, m0, i2 / p.r2, i3);
-                        tma_load_4d_2cta(sb, &tmB, fb, kb * BK, nb, i2, i3);
                     }
                 }
             }
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                 }
             }
         }
-    } else {
+    } else if (warp < 10) {
         // ===================== epilogue (warps 2..9 of both CTAs) =====================
         const int q = warp & 3;                       // TMEM lane quadrant this warp may access
         const int half = (warp - 2) >> 2;             // the two warps of a quadrant alternate 32-column chunks
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
         //      128 rows and sums the partial tiles of the CTAs with the same pair rank in split order (deterministic)
         tc_fence_before();
         cluster_sync_all();
-        if (warp >= 2) {
+        if (warp >= 2 && warp < 10) {
             int m0, n0, batch;
             decode(pair, m0, n0, batch);
             const int w8 = warp - 2;
@@ -432,6 +437,9 @@ cudaError_t launch2(cudaStream_t s, unsigned ctas, unsigned splits, size_t smem,
 
 // shared by the GEMM and the conv front end: fills the tile geometry for a chosen (bn, splits)
 bool fill_geometry(G2Params& kp, const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int nkb, int bn, int splits, unsigned* ctas, size_t* smem) {
+    static int nprod = -1;
+    if (nprod < 0) { const char* e = getenv("GGML_B200_GEMM2_NPROD"); nprod = (e && *e && atoi(e) == 1) ? 1 : 2; }
+    kp.nprod = nprod;
     const int sms = dev.sm_count > 0 ? dev.sm_count : 148;
     kp.bn = bn;
     kp.splits = splits;

@@ -32,6 +32,7 @@
 #include "model/diffusion/mmdit.hpp"
 #include "model/diffusion/wan.hpp"
 #include "model/te/clip.hpp"
+#include "model/te/t5.hpp"
 #include "model/diffusion/unet.hpp"
 #include "model/vae/auto_encoder_kl.hpp"
 #include "model/vae/wan_vae.hpp"
@@ -192,7 +193,7 @@ struct SyntheticWeights : public RunnerWeightManager {
     }
 };
 
-enum Arch { ARCH_UNET, ARCH_VAE, ARCH_FLUX, ARCH_MMDIT, ARCH_WAN, ARCH_CLIP, ARCH_WANVAE };
+enum Arch { ARCH_UNET, ARCH_VAE, ARCH_FLUX, ARCH_MMDIT, ARCH_WAN, ARCH_CLIP, ARCH_WANVAE, ARCH_T5 };
 
 ggml_type parse_wtype(const char* w) {
     std::string s = w ? w : "f32";
@@ -236,6 +237,7 @@ struct sdh_model {
     std::unique_ptr<WAN::WanRunner> wan;
     std::unique_ptr<CLIPTextModelRunner> clip;
     std::unique_ptr<WAN::WanVAERunner> wan_vae;
+    std::unique_ptr<T5Runner> t5;
     SDVersion version = VERSION_SD1;
     int n_threads     = 1;
     double last_flops = 0;
@@ -485,6 +487,29 @@ sdh_model* sdh_model_create(const char* device, const char* arch, const char* wt
         m->clip = std::make_unique<CLIPTextModelRunner>(m->backend, smap, prefix, OPENAI_CLIP_VIT_L_14, true, false, m->weights);
         m->clip->get_param_tensors(tensors, prefix);
         m->clip->set_flash_attention_enabled(fa);
+    } else if (a == "t5_xxl_4l" || a == "t5_xxl") {
+        // the T5-XXL encoder of Flux / SD3 (src/model/te/t5.hpp): RMS-style T5LayerNorm, relative-position-bias attention
+        // (GET_ROWS of the bucket table, bias added to the scores), gated-GELU feed forward.  t5_xxl_4l: 4 of the 24 layers at full width.
+        m->arch    = ARCH_T5;
+        m->version = VERSION_FLUX;
+        const std::string prefix = "text_encoders.t5xxl.transformer";
+        const int n_layers = a == "t5_xxl_4l" ? 4 : 24;
+        String2TensorStorage smap;
+        int64_t ne2[2] = {4096, 4096};
+        for (int i = 0; i < n_layers; ++i) {
+            std::string n1 = prefix + ".encoder.block." + std::to_string(i) + ".layer.0.SelfAttention.q.weight";
+            smap[n1] = TensorStorage(n1, wtype, ne2, 2, 0);
+        }
+        {
+            T5Runner probe(m->backend, smap, prefix, false, m->weights);
+            std::map<std::string, ggml_tensor*> pt;
+            probe.get_param_tensors(pt, prefix);
+            String2TensorStorage typed = make_storage_map(pt, wtype);
+            for (auto& kv : typed) smap[kv.first] = kv.second;
+        }
+        m->t5 = std::make_unique<T5Runner>(m->backend, smap, prefix, false, m->weights);
+        m->t5->get_param_tensors(tensors, prefix);
+        m->t5->set_flash_attention_enabled(fa);
     } else {
         fail("unknown arch: " + a);
         return nullptr;
@@ -505,6 +530,7 @@ void sdh_model_free(sdh_model* m) {
     m->mmdit.reset();
     m->wan.reset();
     m->clip.reset();
+    m->t5.reset();
     m->wan_vae.reset();
     m->weights.reset();
     if (m->backend) ggml_backend_free(m->backend);
@@ -517,6 +543,9 @@ int sdh_model_param_count(const sdh_model* m) { return m->weights ? m->weights->
 int sdh_model_out_shape(sdh_model* m, const sdh_tensor* x, int64_t out_ne[4]) {
     if (!m || !x) return fail("null argument");
     for (int i = 0; i < 4; ++i) out_ne[i] = x->ne[i];
+    if (m->arch == ARCH_T5) {        // ids [n_token, N] -> hidden states [4096, n_token, N]
+        out_ne[0] = 4096; out_ne[1] = x->ne[0]; out_ne[2] = x->ne[1]; out_ne[3] = 1;
+    }
     if (m->arch == ARCH_CLIP) {      // ids [n_token, N] -> hidden states [768, n_token, N]
         out_ne[0] = 768; out_ne[1] = x->ne[0]; out_ne[2] = x->ne[1]; out_ne[3] = 1;
     }
@@ -542,6 +571,8 @@ static sd::Tensor<float> run_model(sdh_model* m, const sd::Tensor<float>& x, con
     switch (m->arch) {
         case ARCH_CLIP:
             return m->clip->compute(m->n_threads, token_ids(x), 0, nullptr, 0, false, -1, false, false, false);
+        case ARCH_T5:
+            return m->t5->compute(m->n_threads, token_ids(x), {}, false, false, false);
         case ARCH_WANVAE: {
             // a 4-D tensor would be taken for an image [W,H,C,N] (wan_vae.hpp:1384-1388): video latents go in as [W,H,T,C,1]
             std::vector<int64_t> shape5 = x.shape();
@@ -688,6 +719,7 @@ GGMLRunner* runner_of(sdh_model* m) {
         case ARCH_MMDIT: return m->mmdit.get();
         case ARCH_WAN: return m->wan.get();
         case ARCH_CLIP: return m->clip.get();
+        case ARCH_T5: return m->t5.get();
         case ARCH_WANVAE: return m->wan_vae.get();
     }
     return nullptr;
@@ -1018,6 +1050,9 @@ static ggml_cgraph* build_only(sdh_model* m, const sd::Tensor<float>& x, const s
         case ARCH_CLIP:
             m->clip->reset_compute_ctx();
             return m->clip->build_graph(token_ids(x));
+        case ARCH_T5:
+            m->t5->reset_compute_ctx();
+            return m->t5->build_graph(token_ids(x));
         case ARCH_WANVAE:
             m->wan_vae->reset_compute_ctx();
             return m->wan_vae->build_graph(x, true);

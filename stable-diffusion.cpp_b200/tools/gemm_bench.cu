@@ -44,30 +44,51 @@ int main(int argc, char** argv) {
     unsigned long long* trace; cudaMalloc(&trace, 64);
     cudaStream_t st; cudaStreamCreate(&st);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    // device time of `reps` back-to-back launches replayed as ONE CUDA graph (how the backend runs them): no host launch cost in the number
+    auto time_graph = [&](auto&& launch) -> double {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        launch();                                   // first launch outside the capture (function attributes, tensor-map cache)
+        cudaStreamSynchronize(st);
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return -1.0;
+        for (int i = 0; i < reps; ++i) launch();
+        if (cudaStreamEndCapture(st, &graph) != cudaSuccess || !graph) { cudaGetLastError(); return -1.0; }
+        if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); cudaGetLastError(); return -1.0; }
+        cudaGraphLaunch(exec, st);
+        cudaStreamSynchronize(st);
+        float ms = 0;
+        cudaEventRecord(e0, st);
+        cudaGraphLaunch(exec, st);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+        return ms * 1e3 / reps;
+    };
     printf("%-34s %8s %8s %8s | %9s %9s\n", "shape", "M", "N", "K", "us", "TFLOP/s");
     for (auto& s : shapes) {
         b200_gemm_args g; memset(&g, 0, sizeof(g));
         g.A = A; g.B = B; g.type = GGML_TYPE_F16; g.M = s.M; g.N = s.N; g.K = s.K; g.lda = s.K; g.ldb = s.K; g.batch = 1; g.a_bcast = 1;
         g.a_batch_stride = s.M * s.K; g.b_batch_stride = s.N * s.K; g.d_batch_stride = s.M * s.N; g.D = D; g.ldd = s.M; g.bias = bias; g.bias_mode = 1;
-        for (int i = 0; i < 5; ++i) b200_launch_gemm_tc(st, dev, g, nullptr, 0);
+        for (int i = 0; i < 3; ++i) b200_launch_gemm_tc(st, dev, g, nullptr, 0);
         cudaStreamSynchronize(st);
-        cudaEventRecord(e0, st);
-        for (int i = 0; i < reps; ++i) b200_launch_gemm_tc(st, dev, g, nullptr, 0);
-        cudaEventRecord(e1, st);
-        cudaEventSynchronize(e1);
-        float ms; cudaEventElapsedTime(&ms, e0, e1);
-        double us = ms * 1e3 / reps;
+        float ms = 0;
+        double us = time_graph([&] { b200_launch_gemm_tc(st, dev, g, nullptr, 0); });
         printf("%-34s %8lld %8lld %8lld | %9.2f %9.1f", s.name, (long long)s.M, (long long)s.N, (long long)s.K, us, 2.0 * s.M * s.N * s.K / us * 1e-6);
         // CTA-pair kernel (gemm_tc2.cu) on the same problem: a sweep over (tile N, split-K), each checked element by element against the
         // one-CTA kernel's result
         if (getenv("GEMM_BENCH_PAIR")) {
             std::vector<float> ref((size_t)s.M * s.N), got((size_t)s.M * s.N);
             cudaMemcpy(ref.data(), D, ref.size() * 4, cudaMemcpyDeviceToHost);
-            const int bns[] = {256, 192, 160, 128, 96, 64};
+            const int bns_all[] = {256, 192, 160, 128, 96, 64};
+            const int bns_few[] = {256, 128, 64};
+            const bool few = getenv("GEMM_BENCH_FEW") != nullptr;
+            std::vector<int> bns(few ? std::begin(bns_few) : std::begin(bns_all), few ? std::end(bns_few) : std::end(bns_all));
             printf("\n");
             for (int bn : bns) {
                 if (bn > 64 && s.N <= bn / 2) continue;
-                for (int sp = 1; sp <= 4; ++sp) {
+                for (int sp = 1; sp <= 4; sp *= 2) {
                     const int64_t tiles = ((s.M + 255) / 256) * ((s.N + bn - 1) / bn);
                     if (sp > 1 && tiles * 2 * sp > 148) continue;
                     cudaMemsetAsync(D, 0xff, ref.size() * 4, st);
@@ -77,14 +98,10 @@ int main(int argc, char** argv) {
                     cudaMemcpy(got.data(), D, got.size() * 4, cudaMemcpyDeviceToHost);
                     size_t bad = 0; double maxd = 0;
                     for (size_t i = 0; i < ref.size(); ++i) { if (ref[i] != got[i]) { ++bad; double d = fabs((double)ref[i] - got[i]); if (!(d <= maxd)) maxd = d; } }
-                    cudaEventRecord(e0, st);
-                    for (int i = 0; i < reps; ++i) b200_launch_gemm_tc2(st, dev, g, bn, sp);
-                    cudaEventRecord(e1, st);
-                    cudaEventSynchronize(e1);
-                    cudaEventElapsedTime(&ms, e0, e1);
+                    const double t2 = time_graph([&] { b200_launch_gemm_tc2(st, dev, g, bn, sp); });
                     const int nkb = (int)((s.K + 63) / 64);
-                    printf("   pair bn %3d splits %d: %8.2f us %7.1f TFLOP/s  model %7.2f us  mismatches %zu (max abs %.3g)\n", bn, sp, ms * 1e3 / reps,
-                           2.0 * s.M * s.N * s.K / (ms * 1e3 / reps) * 1e-6, b200_gemm_tc2_model(dev, s.M, s.N, 1, nkb, bn, sp) / 1965.0, bad, maxd);
+                    printf("   pair bn %3d splits %d: %8.2f us %7.1f TFLOP/s  model %7.2f us  mismatches %zu (max abs %.3g)\n", bn, sp, t2,
+                           2.0 * s.M * s.N * s.K / t2 * 1e-6, b200_gemm_tc2_model(dev, s.M, s.N, 1, nkb, bn, sp) / 1965.0, bad, maxd);
                     fflush(stdout);
                 }
             }

@@ -118,3 +118,19 @@ def test_clip_text_encoder_graph_is_claimed_by_the_plugin(harness):
     m.close()
     assert out.shape[-2:] == (77, 768) and np.isfinite(out).all()
     assert bad == 0, f"{bad} node(s) would fall back to the CPU, first: {first}"
+
+
+def test_t5_text_encoder_graph_is_claimed_by_the_plugin(harness):
+    """the T5-XXL encoder of Flux / SD3 (src/model/te/t5.hpp) at full width (4 of its 24 layers): RMS-style layer norm,
+    relative-position-bias attention (GET_ROWS of the bucket table), gated-GELU feed forward -- every node is claimed by the plugin."""
+    from sdb200 import B200_SO
+    from oracle.cpu_ref import load_cpu_oracle
+    load_cpu_oracle(harness)
+    m = harness.model("CPU", "t5_xxl_4l", "f16", 0, 1234, 4)
+    ids = np.zeros((1, 1, 1, 32), np.float32)
+    ids[0, 0, 0, :8] = [71, 1712, 13, 3, 9, 1782, 5, 1]
+    out, _ = m.forward(ids)
+    bad, first = m.unsupported_nodes(B200_SO, ids)
+    m.close()
+    assert out.shape[-2:] == (32, 4096) and np.isfinite(out).all()
+    assert bad == 0, f"{bad} node(s) would fall back to the CPU, first: {first}"

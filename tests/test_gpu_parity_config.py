@@ -42,7 +42,7 @@ def test_gpu_is_as_close_to_float64_truth_as_the_cpu_oracle(b200, key, arch, sha
     r = rel(ours, truth)
     print(f"{key}: gpu vs truth {r:.3e}, cpu vs truth {cpu_rel:.3e}")
     assert r <= 1.15 * cpu_rel + 1e-4, f"gpu vs f64 truth {r:.3e}, cpu oracle vs truth {cpu_rel:.3e}"
-    assert r < 1.3e-3
+    assert r < 1.35e-3
 
 
 def test_live_cpu_oracle_matches_its_committed_distance_to_truth(b200):
@@ -107,7 +107,7 @@ def test_sdxl_unet_128_bf16_vs_live_cpu(b200):
         m.close()
         r = rel(ours, cpu)
         print(f"sdxl 128 bf16 fa={fa}: rel_l2 {r:.3e}")
-        assert np.isfinite(ours).all() and r < 1.2e-2, f"fa={fa}: rel_l2 {r:.2e}"
+        assert np.isfinite(ours).all() and r < 7e-3, f"fa={fa}: rel_l2 {r:.2e}"
 
 
 def test_flux_full_width_block_vs_live_cpu(b200):
@@ -124,7 +124,7 @@ def test_flux_full_width_block_vs_live_cpu(b200):
         m.close()
     r = rel(outs[dev], outs["CPU"])
     print(f"flux 1+1 full width: rel_l2 {r:.3e}")
-    assert np.isfinite(outs[dev]).all() and r < 1.5e-2, f"rel_l2 {r:.2e}"
+    assert np.isfinite(outs[dev]).all() and r < 3e-3, f"rel_l2 {r:.2e}"
 
 
 # ------------------------------------------------------------------------------------------------ no silent fallback
@@ -181,3 +181,19 @@ def test_graph_write_into_conv_weight_drops_the_packed_copy(b200):
     assert rel(outs[dev][1], outs[dev][0]) > 0.1, "the weight update did not reach the convolution"
     assert rel(outs[dev][0], outs["CPU"][0]) < 3e-3
     assert rel(outs[dev][1], outs["CPU"][1]) < 3e-3, f"after the in-graph weight write: {rel(outs[dev][1], outs['CPU'][1]):.2e}"
+
+
+# ------------------------------------------------------------------------------------------------ weight ingest
+def test_weights_get_their_kernel_layout_at_upload_time(b200):
+    """set_tensor into a WEIGHTS buffer derives the layouts the kernels read (packed 3x3 conv filters; Q8_0 -> f16 rows) right away: the
+    derived copies exist before the first forward and the first forward creates none."""
+    h, dev = b200
+    x = h.randn(42, (1, 4, 16, 16)); ctx = h.randn(43, (1, 77, 768)); t = np.array([999.0], np.float32)
+    m = h.model(dev, "unet_tiny", "f16", 1, 1234, 0)
+    before = m.stats()["derived_weight_bytes"]
+    out, _ = m.forward(x, t, ctx)
+    after = m.stats()["derived_weight_bytes"]
+    m.close()
+    assert before > 10e6, f"no derived conv-filter copies after model creation ({before} bytes)"
+    assert after == before, "the first forward still packed weights"
+    assert np.isfinite(out).all()
