@@ -420,14 +420,12 @@ Plan choose_plan(const b200_device_info& dev, const b200_gemm_args& g, int num_k
             const int64_t ctas = tiles * splits;
             const double per_sm = (double)((ctas + sms - 1) / sms);
             const double kb = (double)((num_k_blocks + splits - 1) / splits);
-            // Measured model (tools/gemm_bench, B200): a 1-CTA main loop is bound by the SM's L2 ingest (~64 B/clk, ~80 % achieved),
-            // not by the MMA: (128 + bn) x 128 B per k-block; the shared L2 (~4700 B/clk) caps the sum over active SMs.
-            const double active = (double)(ctas < sms ? ctas : sms);
-            const double ingest = std::min(64.0 * 0.8, 4700.0 / active);
-            const double kb_cycles = std::max(2.0 * bn, (128.0 + bn) * 128.0 / ingest);
-            // fixed: setup + first data + accumulator hand-off + teardown ~ 3500 clk; epilogue ~ 35 clk per column (direct) or
-            // smem staging + cluster barrier + DSMEM reduce of bn / splits columns
-            double cta_cycles = kb * kb_cycles + 3500.0 + (splits > 1 ? 8.0 * bn + 2500.0 + 80.0 * bn / splits : 35.0 * bn);
+            // Measured model (tools/gemm_bench, B200; profiles/r02_gemm_model.md): a main loop is bound by the SM's ingest port -- ~43 B/clk
+            // from L2 through TMA per SM, alone or with all 148 busy -- not by the MMA: (128 + bn) x 128 B per k-block
+            const double kb_cycles = std::max(2.0 * bn, (128.0 + bn) * 128.0 / 43.0);
+            // fixed: setup + first data + accumulator hand-off + teardown ~ 5500 clk; epilogue ~ 35 clk per column (four warps, direct) or
+            // smem staging + cluster barriers + DSMEM reduce (~17 B/clk: bn x 512 B per CTA)
+            double cta_cycles = kb * kb_cycles + 5500.0 + (splits > 1 ? 8.0 * bn + 1500.0 + 31.0 * bn : 35.0 * bn);
             double t = per_sm * cta_cycles;
             if (t < best) { best = t; bestp = Plan{bn, splits}; }
         }
@@ -441,7 +439,7 @@ int gemm2_mode() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("GGML_B200_GEMM2");
-        v = (e && *e) ? atoi(e) : 0;      // flipped to 1 once validated on hardware
+        v = (e && *e) ? atoi(e) : 1;      // validated on B200: 275 / 275 shape x plan combinations element-exact vs the one-CTA kernel, full GPU suite green when forced
     }
     return v;
 }
@@ -466,7 +464,7 @@ Plan2 choose_plan2(const b200_device_info& dev, int64_t M, int64_t N, int64_t ba
         if (force_bn && bn != force_bn && !(N <= force_bn / 2 && bn < force_bn)) continue;
         if (bn > 32 && N <= bn / 2) continue;
         const int64_t tiles = ((M + 255) / 256) * ((N + bn - 1) / bn) * batch;
-        for (int splits = 1; splits <= 4; ++splits) {
+        for (int splits = 1; splits <= 4; splits *= 2) {
             if (splits > 1 && (tiles * 2 * splits > sms || nkb / splits < 4)) break;
             if (force_splits && splits != force_splits && !(splits == 1 && (tiles * 2 * force_splits > sms || nkb / force_splits < 4))) continue;
             const double t = b200_gemm_tc2_model(dev, M, N, batch, nkb, bn, splits);
@@ -599,9 +597,11 @@ int b200_launch_conv_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     const int nkb = (int)(g.K / 64);
     double cycles1 = 0;
     Plan pl = choose_plan(dev, g, nkb, &cycles1);
-    if ((gemm2_mode() || c.D2) && g.M > BM && g.M % 128 == 0) {
+    // (a peer destination c.D2 does not influence the choice: the serial and the split sampler must run the very same plans to stay
+    //  bit-identical; when this launch ends up on the one-CTA kernel the executor pushes the tensor with kernels/peer.cu instead)
+    if (gemm2_mode() && g.M > BM && g.M % 128 == 0) {
         const Plan2 p2 = choose_plan2(dev, g.M, g.N, g.batch, nkb);
-        if (p2.bn > 0 && (gemm2_mode() >= 2 || c.D2 || p2.cycles < cycles1)) {
+        if (p2.bn > 0 && (gemm2_mode() >= 2 || p2.cycles < cycles1)) {
             const int r = b200_launch_conv_tc2(s, dev, c, p2.bn, p2.splits);
             if (r > 0) {
                 if (gemm_log()) fprintf(stderr, "GEMMLOG pair conv M %lld N %lld K %lld batch %lld bn %d splits %d model1 %.0f model2 %.0f\n", (long long)g.M, (long long)g.N, (long long)g.K, (long long)g.batch, p2.bn, p2.splits, cycles1, p2.cycles);

@@ -54,6 +54,8 @@ struct G2Params {
     const float* residual;
     int64_t ldr, r_batch_stride;
     int act;
+    int vec_epi;            // staged epilogue: the 4 warps of a column group transpose 32 columns x 128 rows through shared memory and store 512 B per column
+    int stage_off;          // byte offset of the two 16 KB staging tiles behind the operand ring
     int nprod;              // TMA producer threads per CTA: 2 (A and B issued by different warps, default) or 1 (A/B of GGML_B200_GEMM2_NPROD)
     int conv, conv_W, conv_KW, conv_cblocks, conv_pad, conv_dil;
     float* D2;                // optional mirror of D in the PEER GPU's memory (NVLink mapping, kernels/peer.cu); slot chosen by *d2_seq
@@ -258,6 +260,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                     for (int i = 0; i < 32; ++i)
                         if (c0 + i < p.bn) sred[(c0 + i) * BM + ml] = __uint_as_float(r[i]);
                 }
+            } else if (p.act == 0 && p.vec_epi) {
+                // Staged stores.  A thread owns one accumulator ROW (TMEM lane), but memory wants a column's 128 consecutive rows in one
+                // piece: the four warps of this column group write a 32-column chunk to shared memory as [column][row], then every warp
+                // streams 8 of the columns with 16 bytes per lane -- one store instruction = 512 contiguous bytes (and the residual is read
+                // the same way), instead of 4 x 128 B scattered over four instructions per column.
+                float* stage = (float*)(smem + p.stage_off) + half * (32 * BM);
+                const int wq = (warp - 2) & 3;
+                const int64_t mrow = (int64_t)m0 + 4 * lane;
+                const bool rvalid = mrow < p.M;                           // M % 4 == 0 on this path
+                float4 bm4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias_mode == 1 && rvalid) bm4 = *(const float4*)(p.bias + mrow);
+#pragma unroll 1
+                for (int c0 = half * 32; c0 < ncols; c0 += 64) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) stage[i * BM + ml] = __uint_as_float(r[i]);
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int col = wq * 8 + jj, n = c0 + col;
+                        if (n < ncols && rvalid) {
+                            float4 v = *(const float4*)(stage + col * BM + 4 * lane);
+                            const float bn = p.bias_mode == 2 ? p.bias[n0 + n] : 0.f;
+                            v.x += bm4.x + bn; v.y += bm4.y + bn; v.z += bm4.z + bn; v.w += bm4.w + bn;
+                            const int64_t off = (int64_t)(n0 + n) * p.ldd + mrow;
+                            if (Rp) {
+                                const float4 rr = *(const float4*)(Rp + (int64_t)(n0 + n) * p.ldr + mrow);
+                                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+                            }
+                            *(float4*)(Dp + off) = v;
+                            if (p.D2) *(float4*)(Dp + off + d2off) = v;
+                        }
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                }
             } else if (p.act == 0) {
                 float* dptr = Dp + (int64_t)n0 * p.ldd + m;
                 const float* rptr = Rp ? Rp + (int64_t)n0 * p.ldr + m : nullptr;
@@ -435,6 +474,18 @@ cudaError_t launch2(cudaStream_t s, unsigned ctas, unsigned splits, size_t smem,
     return cudaLaunchKernelEx(&cfg, k_gemm_tc2<FMT>, ta, tb, kp);
 }
 
+// may the epilogue use 16-byte stores along m?  (GGML_B200_GEMM2_VEC_EPI=0 keeps the per-row path for A/B runs)
+int vec_epilogue_ok(const G2Params& kp, int splits) {
+    static int en = -1;
+    if (en < 0) { const char* e = getenv("GGML_B200_GEMM2_VEC_EPI"); en = (e && *e) ? atoi(e) : 1; }
+    if (!en || splits != 1 || kp.act != 0) return 0;
+    if ((kp.M & 3) || (kp.ldd & 3) || (kp.d_batch_stride & 3) || ((uintptr_t)kp.D & 15)) return 0;
+    if (kp.residual && ((kp.ldr & 3) || (kp.r_batch_stride & 3) || ((uintptr_t)kp.residual & 15))) return 0;
+    if (kp.bias_mode == 1 && ((uintptr_t)kp.bias & 15)) return 0;
+    if (kp.D2 && (((uintptr_t)kp.D2 & 15) || (kp.d2_slot & 3))) return 0;
+    return 1;
+}
+
 // shared by the GEMM and the conv front end: fills the tile geometry for a chosen (bn, splits)
 bool fill_geometry(G2Params& kp, const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int nkb, int bn, int splits, unsigned* ctas, size_t* smem) {
     static int nprod = -1;
@@ -445,7 +496,8 @@ bool fill_geometry(G2Params& kp, const b200_device_info& dev, int64_t M, int64_t
     kp.splits = splits;
     kp.num_k_blocks = nkb;
     kp.stage_bytes = A_STAGE_BYTES + (bn / 2) * BK_BYTES;
-    int stages = (int)((227 * 1024 - 4096) / kp.stage_bytes);
+    const int stage_tiles = splits == 1 ? 2 * 32 * BM * 4 : 0;        // two 16 KB staging tiles of the vectorised epilogue
+    int stages = (int)((227 * 1024 - 4096 - stage_tiles) / kp.stage_bytes);
     stages = std::min(stages, MAX_STAGES);
     if (splits > 1) {
         // the partial tile [bn][128] f32 reuses the ring
@@ -467,31 +519,38 @@ bool fill_geometry(G2Params& kp, const b200_device_info& dev, int64_t M, int64_t
     if (splits == 1) pairs = std::min<int64_t>(total, sms / 2);
     else if (pairs * 2 * splits > 65535 * 2) return false;
     *ctas = (unsigned)(pairs * 2);
-    *smem = (size_t)stages * kp.stage_bytes + 1024;
+    kp.stage_off = stages * kp.stage_bytes;
+    *smem = (size_t)stages * kp.stage_bytes + stage_tiles + 1024;
     return true;
 }
 
 }  // namespace
 
-// modelled cycles of the pair kernel for (bn, splits); used by the plan choosers of gemm_tc.cu to pick between the kernels
+// Modelled cycles of the pair kernel for (bn, splits); used by the plan choosers of gemm_tc.cu to pick between the kernels.
+// Calibrated on B200 with tools/gemm_bench (profiles/r02_gemm_model.md).  The quantity that decides everything below the MMA floor is
+// the SM's ingest port: one SM takes ~43 B/clk from L2 through TMA whether it runs alone or with 147 others (the "6300 B/clk chip
+// cap" is 148 such ports), so a CTA's main loop costs (bytes it stages) / 43 clk and small problems are won by spreading the operand
+// bytes over as many SMs as possible -- not by bigger tiles.
 double b200_gemm_tc2_model(const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int nkb, int bn, int splits) {
     const int sms = dev.sm_count > 0 ? dev.sm_count : 148;
     const int64_t tm = (M + 255) / 256, tn = (N + bn - 1) / bn;
     const int64_t tiles = tm * tn * batch;
     const double kb = (double)((nkb + splits - 1) / splits);
-    const int64_t ctas = splits == 1 ? std::min<int64_t>(tiles, sms / 2) * 2 : tiles * 2 * splits;
-    const double active = (double)std::min<int64_t>(ctas, sms);
-    const double ingest = std::min(56.0, 6000.0 / active);                 // B/clk per SM: per-SM path vs. the chip-wide L2 cap
+    const double ingest = 43.0;                                            // B/clk per SM
     const double bytes = (128.0 + bn / 2.0) * 128.0;
     const double kb_cycles = std::max(2.0 * bn, bytes / ingest);           // cta_group::2: bn / 2 clk per K = 16 MMA, four per k-block
-    const double epi = 20.0 * bn;                                          // eight epilogue warps
+    const double epi = 18.0 * bn + 600.0;                                  // eight epilogue warps: TMEM -> registers -> coalesced f32 stores
     if (splits == 1) {
-        const double per_pair = (double)((tiles + (ctas / 2) - 1) / (ctas / 2));
-        // tiles of one pair overlap their epilogues with the next main loop; the last epilogue is exposed
-        return 4000.0 + per_pair * std::max(kb * kb_cycles, epi) + epi + (per_pair > 1 ? 0.0 : 0.0);
+        const int64_t pairs = std::min<int64_t>(tiles, sms / 2);
+        const double per_pair = (double)((tiles + pairs - 1) / pairs);
+        // tiles of one pair overlap their epilogue with the next main loop (two TMEM accumulators); the last epilogue is exposed
+        return 5500.0 + per_pair * std::max(kb * kb_cycles, epi) + epi;
     }
-    const double waves = (double)((ctas + sms - 1) / sms);
-    return waves * (4000.0 + kb * kb_cycles + 6.0 * bn + 2500.0 + 50.0 * bn / splits);
+    // split-K: every cluster owns one tile; the partial tiles are reduced through DSMEM (~17 B/clk per CTA): bn * 128 * 4 B per CTA
+    const int csize = 2 * splits;
+    const int64_t max_clusters = csize == 4 ? 36 : (csize == 6 ? 20 : 13);   // concurrent clusters the GPCs (16-20 SMs each) can host
+    const double waves = (double)((tiles + max_clusters - 1) / max_clusters);
+    return waves * (6500.0 + kb * kb_cycles + 31.0 * bn + 900.0);
 }
 
 // returns 1 when launched, -1 when the problem is outside this kernel's envelope.  bn / splits <= 0: choose here.
@@ -518,6 +577,7 @@ int b200_launch_gemm_tc2(cudaStream_t s, const b200_device_info& dev, const b200
     kp.bias = g.bias; kp.bias_mode = g.bias ? g.bias_mode : 0;
     kp.residual = g.residual; kp.ldr = g.ldr; kp.r_batch_stride = g.d_batch_stride;
     kp.act = g.act;
+    kp.vec_epi = vec_epilogue_ok(kp, splits);
     cudaError_t e = g.type == GGML_TYPE_F16 ? launch2<0>(s, ctas, (unsigned)splits, smem, ta, tb, kp) : launch2<1>(s, ctas, (unsigned)splits, smem, ta, tb, kp);
     if (e != cudaSuccess) {
         fprintf(stderr, "[ggml-b200] CTA-pair GEMM launch failed: %s\n", cudaGetErrorString(e));
@@ -561,6 +621,7 @@ int b200_launch_conv_tc2(cudaStream_t s, const b200_device_info& dev, const b200
     kp.bias = c.bias; kp.bias_mode = c.bias ? 2 : 0;
     kp.residual = c.residual; kp.ldr = M; kp.r_batch_stride = c.OC * M;
     kp.D2 = c.D2; kp.d2_seq = c.d2_seq; kp.d2_slot = c.d2_slot_floats;
+    kp.vec_epi = vec_epilogue_ok(kp, splits);
     kp.conv = 1; kp.conv_W = (int)c.W; kp.conv_KW = c.KW; kp.conv_cblocks = (int)(c.C / 64); kp.conv_pad = c.pad; kp.conv_dil = c.dil;
     cudaError_t e = launch2<0>(s, ctas, (unsigned)splits, smem, ta, tb, kp);
     if (e != cudaSuccess) {
