@@ -14,6 +14,7 @@ CASES = {
     "sd15": ("sd15_unet", "f16", dict(x=(1, 4, 64, 64), ctx=(1, 77, 768), y=None, t=999.0)),
     "sd15x2": ("sd15_unet", "f16", dict(x=(2, 4, 64, 64), ctx=(2, 77, 768), y=None, t=999.0)),
     "sdxl": ("sdxl_unet", "bf16", dict(x=(1, 4, 128, 128), ctx=(1, 77, 2048), y=(1, 2816), t=999.0)),
+    "flux1": ("flux_1x1", "bf16", dict(x=(1, 16, 128, 128), ctx=(1, 256, 4096), y=(1, 768), t=1.0)),
     "flux": ("flux_schnell", "bf16", dict(x=(1, 16, 128, 128), ctx=(1, 256, 4096), y=(1, 768), t=1.0)),
     "mmdit": ("mmdit_sd3", "f16", dict(x=(1, 16, 128, 128), ctx=(1, 154, 4096), y=(1, 2048), t=500.0)),
     "vae": ("vae_decoder", "f16", dict(x=(1, 4, 64, 64), ctx=None, y=None, t=None)),

@@ -67,7 +67,9 @@ int main(int argc, char** argv) {
         return ms * 1e3 / reps;
     };
     printf("%-34s %8s %8s %8s | %9s %9s\n", "shape", "M", "N", "K", "us", "TFLOP/s");
+    const char* only = getenv("GEMM_BENCH_ONLY");      // substring filter on the shape name
     for (auto& s : shapes) {
+        if (only && !strstr(s.name, only)) continue;
         b200_gemm_args g; memset(&g, 0, sizeof(g));
         g.A = A; g.B = B; g.type = GGML_TYPE_F16; g.M = s.M; g.N = s.N; g.K = s.K; g.lda = s.K; g.ldb = s.K; g.batch = 1; g.a_bcast = 1;
         g.a_batch_stride = s.M * s.K; g.b_batch_stride = s.N * s.K; g.d_batch_stride = s.M * s.N; g.D = D; g.ldd = s.M; g.bias = bias; g.bias_mode = 1;
