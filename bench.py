@@ -336,9 +336,13 @@ def run_b200(args):
                              **({alt["layout"]: dict(value=alt["value"], e2e=alt["e2e"], ms_per_step=alt["dev_ms"] / args.steps,
                                                      e2e_ms_per_step=1e3 * alt["wall"] / args.steps, is_value=False)} if alt else {})},
                     host=dict(backend_graph_compute_ms_per_step=(s1["host_us"] - s0["host_us"]) / 1e3 / args.steps,
+                              set_tensor_ms_per_step=(s1["host_set_us"] - s0["host_set_us"]) / 1e3 / args.steps,
+                              get_tensor_incl_device_wait_ms_per_step=(s1["host_get_us"] - s0["host_get_us"]) / 1e3 / args.steps,
+                              outside_backend_ms_per_step=(s1["host_outside_us"] - s0["host_outside_us"]) / 1e3 / args.steps,
                               e2e_minus_device_ms_per_step=1e3 * wall / args.steps - dev_ms / args.steps,
-                              note="backend share = host time inside graph_compute (signature, planning, cudaGraphLaunch); the rest is the reference's "
-                                   "graph rebuild, gallocr, tensor_set/get and sampler math per model call"),
+                              note="attribution at the plugin boundary: outside_backend = host time between two vtable calls (the reference's graph rebuild, "
+                                   "gallocr, sampler math), set/get = inside the buffer vtable (get includes waiting for the device), "
+                                   "backend_graph_compute = host side of graph_compute (signature, cudaGraphLaunch)"),
                     backend=dict(cuda_graph_replays=int(s1["cuda_graph_replays"] - s0["cuda_graph_replays"]),
                                  gemm_ref_launches=int(s1["gemm_ref_launches"] - s0["gemm_ref_launches"]),
                                  cta_pair_gemm_launches=int(s1["cta2_gemm_launches"] - s0["cta2_gemm_launches"]),

@@ -78,7 +78,10 @@ typedef struct ggml_b200_stats {
                                    [2] graphs that wrote into a WEIGHTS buffer (derived weight copies dropped), [3] conv filters packed per graph
                                    (filter computed inside the graph: no persistent copy), [4] persistent-GEMM launches, [5] 2-CTA GEMM launches,
                                    [6] bytes of derived weight copies alive, [7] unfused (GEMM + softmax + GEMM) attention executions,
-                                   [8] graphs that ended with a peer exchange (kernels/peer.cu) */
+                                   [8] graphs that ended with a peer exchange (kernels/peer.cu),
+                                   [9..12] host microseconds at the plugin boundary, process-wide: inside set_tensor, inside get_tensor (includes
+                                   waiting for the device), inside graph_compute (host side), and OUTSIDE the backend between two boundary
+                                   calls (the host's own work: graph rebuild, gallocr, sampler) */
 } ggml_b200_stats;
 
 /* copy the backend instance's counters; returns 0 on success.  Counters of kernels that run inside a replayed CUDA graph are

@@ -127,6 +127,8 @@ static void b200_buffer_memset_tensor(ggml_backend_buffer_t buffer, ggml_tensor*
 
 static void b200_buffer_set_tensor(ggml_backend_buffer_t buffer, ggml_tensor* tensor, const void* data, size_t offset, size_t size) {
     auto* ctx = (b200_buffer_ctx*)buffer->context;
+    b200_boundary_clock::enter();
+    struct leave_guard { ~leave_guard() { b200_boundary_clock::leave(0); } } leave_guard_;
     B200_CUDA_CHECK(cudaSetDevice(ctx->device));
     B200_CUDA_CHECK(cudaMemcpyAsync((char*)tensor->data + offset, data, size, cudaMemcpyHostToDevice, cudaStreamPerThread));
     B200_CUDA_CHECK(cudaStreamSynchronize(cudaStreamPerThread));
@@ -138,6 +140,8 @@ static void b200_buffer_set_tensor(ggml_backend_buffer_t buffer, ggml_tensor* te
 
 static void b200_buffer_get_tensor(ggml_backend_buffer_t buffer, const ggml_tensor* tensor, void* data, size_t offset, size_t size) {
     auto* ctx = (b200_buffer_ctx*)buffer->context;
+    b200_boundary_clock::enter();
+    struct leave_guard { ~leave_guard() { b200_boundary_clock::leave(1); } } leave_guard_;
     B200_CUDA_CHECK(cudaSetDevice(ctx->device));
     B200_CUDA_CHECK(cudaMemcpyAsync(data, (const char*)tensor->data + offset, size, cudaMemcpyDeviceToHost, cudaStreamPerThread));
     B200_CUDA_CHECK(cudaStreamSynchronize(cudaStreamPerThread));
@@ -582,6 +586,7 @@ int ggml_backend_b200_get_stats(ggml_backend_t backend, ggml_b200_stats* out) {
     static_assert(sizeof(ggml_b200_stats) == sizeof(b200_stats), "stats ABI mismatch");
     b200_context_finalize_timing((b200_context*)backend->context);
     ((b200_context*)backend->context)->stats.ext[6] = b200_derived_weight_bytes();
+    for (int i = 0; i < 4; ++i) ((b200_context*)backend->context)->stats.ext[9 + i] = b200_boundary_clock::us(i);
     memcpy(out, &((b200_context*)backend->context)->stats, sizeof(*out));
     return 0;
 }

@@ -297,6 +297,7 @@ struct mm_fusion {
     const float* residual = nullptr;   // same [M, N] layout as out, added last
     const ggml_tensor* src1_pre = nullptr;   // activation to read instead of src[1] (same shape): the input of a unary op folded in
     int pre_act = 0;                          // 1: SiLU applied to src1_pre on load (only the few-row GEMV path can do this)
+    int act = 0;                              // activation after the bias, before the residual: 1 SiLU, 2 GELU (tanh form) -- the epilogue's act_fn
 };
 
 static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz = nullptr) {
@@ -314,7 +315,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
     }
 
     // a handful of activation rows against in-place F16/BF16 weights (embedding MLPs): weight-streaming GEMV, no operand packing
-    {
+    if (!(fz && fz->act)) {
         const ggml_tensor* x = fz && fz->src1_pre ? fz->src1_pre : src1;
         if (ctx->opt_gemv && ne02 * ne03 * ne12 * ne13 == 1 && N <= 4 && (src0->type == GGML_TYPE_F16 || src0->type == GGML_TYPE_BF16) &&
             rows_unit_stride(src0) && x->type == GGML_TYPE_F32 && x->nb[0] == 4 && x->nb[1] % 4 == 0 && dst->nb[0] == 4 &&
@@ -330,7 +331,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
         if (fz && fz->src1_pre) return -2;     // only the GEMV can fold the unary op
     }
 
-    if (ct == GGML_TYPE_F32 && ctx->opt_precise_f32 && ctx->opt_tc_gemm) {
+    if (ct == GGML_TYPE_F32 && ctx->opt_precise_f32 && ctx->opt_tc_gemm && !(fz && fz->act)) {
         // F32 x F32 (attention GEMMs of the reference's default graph, F32 Linear weights): the CPU oracle computes true f32 dot products
         // (ggml-cpu.c:1406 with vec_dot_f32); a single TF32 pass would keep 10 mantissa bits of each operand.  3xTF32: x = hi + lo with hi
         // exactly representable in TF32; D = A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, three tensor-core passes chained through the residual
@@ -442,6 +443,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
         g.d_batch_stride = dst->nb[2] / 4;
         if (fz && fz->bias) { g.bias = fz->bias; g.bias_mode = fz->bias_mode; }
         if (fz && fz->residual) { g.residual = fz->residual; g.ldr = g.ldd; }
+        if (fz) g.act = fz->act;
         // model weights read in place are constants of the graph: their first ring-full may be fetched before the PDL wait.  Not for
         // the first kernel of a graph_compute (its stream predecessor belongs to an earlier call, e.g. a weight update).
         if (ctx->opt_early_weights && a.ptr == src0->data && src0->buffer && src0->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS &&
@@ -449,6 +451,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
             g.early = 1;
         int n = launch_tc(ctx, g);
         if (n < 0) {
+            if (fz && fz->act) return -1;      // the reference kernel has no activation epilogue: fail loudly rather than skip it
             // CUDA-core reference kernel (debug option, or shapes the TMA cannot describe)
             n = 0;
             for (int64_t i2 = 0; i2 < nb12; ++i2) {
@@ -1022,6 +1025,25 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
             }
         }
     }
+    // activation: Linear -> GELU / SiLU (the MLPs of the DiT blocks, flux.hpp Mlp; GELU is the tanh form in ggml): applied by the epilogue
+    // on the biased accumulator -- the same f32 expression the unary kernel evaluates -- instead of a separate pass over [features, tokens]
+    if (!src1_pre && ctx->opt_chain_fusion && ctx->opt_tc_gemm && mm->src[0]->type != GGML_TYPE_F32 && mm->ne[1] > 4) {
+        const int ju = chain.empty() ? next_node(g, fs, i) : next_node(g, fs, chain.back());
+        const ggml_tensor* curv = chain.empty() ? (const ggml_tensor*)mm : g->nodes[chain.back()];
+        if (ju >= 0) {
+            ggml_tensor* u = g->nodes[ju];
+            if (u->op == GGML_OP_UNARY && (u->flags & GGML_TENSOR_FLAG_COMPUTE) && u->type == GGML_TYPE_F32 && ggml_is_contiguous(u) && u->src[0] == curv &&
+                ggml_are_same_shape(u, curv) && (u->data == curv->data || single_use(fs, curv)) && !(curv->flags & GGML_TENSOR_FLAG_OUTPUT)) {
+                const ggml_unary_op uo = ggml_get_unary_op(u);
+                const int a = uo == GGML_UNARY_OP_GELU ? 2 : (uo == GGML_UNARY_OP_SILU ? 1 : 0);
+                if (a) {
+                    fz.act = a;
+                    fz.out = (float*)u->data;
+                    chain.push_back(ju);
+                }
+            }
+        }
+    }
     // residual: ... -> ADD(value, r) with r a same-shape tensor that already exists (the ADD is the very next work node, so r was
     // produced before this MUL_MAT).  Read in the epilogue of the element it is added to, so in-place adds onto r are fine.
     {
@@ -1072,6 +1094,25 @@ static std::atomic<uint64_t> g_pw_bytes{0};
 // bumped whenever a derived weight copy is dropped: captured CUDA graphs hold raw pointers to those copies and must not be replayed
 // across such an event (a long-lived backend whose model was reloaded at the same addresses)
 static std::atomic<uint64_t> g_pw_generation{0};
+
+namespace {
+std::atomic<uint64_t> g_bc_us[4];
+std::atomic<int64_t> g_bc_last_leave{0};
+thread_local int64_t t_bc_enter = 0;
+int64_t bc_now() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
+void b200_boundary_clock::enter() {
+    const int64_t now = bc_now();
+    const int64_t last = g_bc_last_leave.load(std::memory_order_relaxed);
+    if (last > 0 && now > last && now - last < 2000000000ll) g_bc_us[3].fetch_add((uint64_t)((now - last) / 1000), std::memory_order_relaxed);
+    t_bc_enter = now;
+}
+void b200_boundary_clock::leave(int category) {
+    const int64_t now = bc_now();
+    if (t_bc_enter > 0) g_bc_us[category & 3].fetch_add((uint64_t)((now - t_bc_enter) / 1000), std::memory_order_relaxed);
+    g_bc_last_leave.store(now, std::memory_order_relaxed);
+}
+uint64_t b200_boundary_clock::us(int what) { return g_bc_us[what & 3].load(std::memory_order_relaxed); }
 
 uint64_t b200_derived_weight_bytes() { return g_pw_bytes.load(std::memory_order_relaxed); }
 
@@ -1308,6 +1349,7 @@ struct conv_prologue {
     const float* gb = nullptr;
     int act = 0;
     const void* ready_nhwc = nullptr;   // the NHWC f16 image already exists (tokens are NHWC): skip the transform
+    const float* addv = nullptr;        // [N][C] vector added to src on the fly: the folded `h + emb` broadcast ADD of a ResBlock
 };
 
 static int emit_conv(b200_context* ctx, const conv_match& m, const conv_prologue& pro) {
@@ -1332,9 +1374,9 @@ static int emit_conv(b200_context* ctx, const conv_match& m, const conv_prologue
             const size_t pb = ctx->gn_counters ? b200_gn_stats_partial_bytes(N, C, H * W, pro.n_groups) : 0;
             void* partial = pb ? ws_alloc(ctx, pb) : nullptr;
             if (pb && !partial) return -1;
-            launches += b200_launch_gn_stats(ctx->stream, (const float*)src->data, stats, N, C, H * W, pro.n_groups, pro.eps, partial, ctx->gn_counters);
+            launches += b200_launch_gn_stats(ctx->stream, (const float*)src->data, stats, N, C, H * W, pro.n_groups, pro.eps, partial, ctx->gn_counters, pro.addv);
         }
-        int n = b200_launch_to_nhwc_f16(ctx->stream, (const float*)src->data, sh, N, C, H, W, pro.up, stats, pro.n_groups, pro.gw, pro.gb, pro.act);
+        int n = b200_launch_to_nhwc_f16(ctx->stream, (const float*)src->data, sh, N, C, H, W, pro.up, stats, pro.n_groups, pro.gw, pro.gb, pro.act, pro.addv);
         if (n < 0) return -1;
         launches += n;
         shadow = sh;
@@ -1442,7 +1484,7 @@ static int try_fuse_modulate(b200_context* ctx, ggml_cgraph* g, fusion_state& fs
 }
 
 // GROUP_NORM -> MUL w -> ADD b [-> SILU]     /     NORM -> MUL w -> ADD b
-static int try_fuse_norm(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
+static int try_fuse_norm(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered, const ggml_tensor* pre_add = nullptr) {
     ggml_tensor* nrm = g->nodes[i];
     const bool group = nrm->op == GGML_OP_GROUP_NORM;
     if (nrm->type != GGML_TYPE_F32 || !ggml_is_contiguous(nrm) || !ggml_is_contiguous(nrm->src[0])) return -2;
@@ -1481,7 +1523,8 @@ static int try_fuse_norm(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, in
         conv_match cm;
         if (ic >= 0 && g->nodes[ic]->op == GGML_OP_IM2COL && g->nodes[ic]->src[1] == last && match_conv(g, fs, ic, &cm)) {
             conv_prologue pro;
-            pro.src = nrm->src[0];
+            pro.src = pre_add ? pre_add->src[0] : nrm->src[0];
+            pro.addv = pre_add ? (const float*)pre_add->src[1]->data : nullptr;
             pro.norm = true;
             pro.n_groups = ggml_get_op_params_i32(nrm, 0);
             memcpy(&pro.eps, (const float*)nrm->op_params + 1, 4);
@@ -1499,6 +1542,7 @@ static int try_fuse_norm(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, in
             if (ctx->capture_overflow) return -1;
         }
     }
+    if (pre_add) return -2;            // only the conv prologue can fold the broadcast ADD: the caller runs the ADD and comes back
     // the fused kernel writes `last` while reading the norm's input: identical placement is fine (each CTA owns its group / row),
     // a partial overlap (recycled memory at another offset) is not
     if (last->data != nrm->src[0]->data && tensors_overlap(last->data, ggml_nbytes(last), nrm->src[0]->data, ggml_nbytes(nrm->src[0]))) return -2;
@@ -1978,6 +2022,22 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
                 if (n == -2 && ctx->opt_chain_fusion) n = try_skip_q_cont(ctx, cgraph, fs, i);
             } else if (t->op == GGML_OP_RMS_NORM && ctx->opt_chain_fusion) n = try_fuse_rms_rope(ctx, cgraph, fs, i, &covered);
             else if (t->op == GGML_OP_UNARY && ctx->opt_chain_fusion) n = try_fuse_silu_gemv(ctx, cgraph, fs, i, &covered);
+            else if (t->op == GGML_OP_ADD && ctx->opt_chain_fusion && ctx->opt_tc_gemm && ctx->opt_implicit_conv) {
+                // ResBlock: h = conv(...) ; h = ADD(h, emb_out [1,1,C,N]) ; GroupNorm(h) -> SiLU -> conv (block.hpp:142-170).  The broadcast ADD has
+                // one consumer, the GroupNorm that the conv prologue absorbs: fold it into the statistics and transform kernels (same f32 add,
+                // same rounding), never materialise it
+                const ggml_tensor* h0 = t->src[0];
+                const ggml_tensor* e0 = t->src[1];
+                const int jn = next_node(cgraph, fs, i);
+                if (jn >= 0 && cgraph->nodes[jn]->op == GGML_OP_GROUP_NORM && cgraph->nodes[jn]->src[0] == t && single_use(fs, t) && t->type == GGML_TYPE_F32 &&
+                    h0->type == GGML_TYPE_F32 && e0->type == GGML_TYPE_F32 && ggml_is_contiguous(h0) && ggml_is_contiguous(e0) && ggml_are_same_shape(t, h0) &&
+                    e0->ne[0] == 1 && e0->ne[1] == 1 && e0->ne[2] == h0->ne[2] && e0->ne[3] == h0->ne[3] && (h0->ne[0] * h0->ne[1]) % 4 == 0) {
+                    int cov = 0;
+                    const int r = try_fuse_norm(ctx, cgraph, fs, jn, &cov, t);
+                    if (r >= 0) { fs.done[jn] = 1; covered = cov + 1; n = r; }
+                    else if (r == -1) n = -1;
+                }
+            }
             else if (t->op == GGML_OP_FLASH_ATTN_EXT && ctx->opt_chain_fusion) n = try_fuse_flash_attn(ctx, cgraph, fs, i, &covered);
             if (n >= 0) {
                 ctx->stats.fused_nodes += (uint64_t)covered;
@@ -2103,9 +2163,13 @@ static void stats_add(b200_stats& dst, const b200_stats& a, const b200_stats& b)
 
 enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
     const auto host_t0 = std::chrono::steady_clock::now();
+    b200_boundary_clock::enter();
     struct host_timer {
         b200_context* c; std::chrono::steady_clock::time_point t0;
-        ~host_timer() { c->stats.ext[1] += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count(); }
+        ~host_timer() {
+            c->stats.ext[1] += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+            b200_boundary_clock::leave(2);
+        }
     } host_timer_guard{ctx, host_t0};
     B200_CUDA_CHECK(cudaSetDevice(ctx->device));
     // the previous graph's device time is finalised here (the host has synchronised in between: it read the result)

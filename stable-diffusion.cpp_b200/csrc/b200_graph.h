@@ -106,6 +106,14 @@ void b200_invalidate_address_range(int device, const void* ptr, size_t size);
 void b200_ingest_weight(int device, const ggml_tensor* w);
 uint64_t b200_derived_weight_bytes();
 
+// Host-time attribution at the plugin boundary (process-wide, microseconds): every vtable entry that moves data or computes is bracketed,
+// and the time BETWEEN two boundary calls is what the host spent outside the backend (the reference's graph rebuild, gallocr, sampler).
+struct b200_boundary_clock {
+    static void enter();
+    static void leave(int category);     // 0 set_tensor, 1 get_tensor (includes waiting for the device), 2 graph_compute (host side)
+    static uint64_t us(int what);        // 0..2 as above, 3 = outside the backend
+};
+
 // CFG-split exchange (kernels/peer.cu)
 int b200_peer_create(b200_context* ctx, size_t bytes, void* ipc_handle_out64);
 int b200_peer_connect(b200_context* ctx, const void* peer_ipc_handle64);   // nullptr: loopback (single-GPU self test)

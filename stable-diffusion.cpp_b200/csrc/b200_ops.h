@@ -129,12 +129,13 @@ int b200_launch_conv_tc2(cudaStream_t s, const b200_device_info& dev, const b200
 // partial / counters (optional): scratch of b200_gn_stats_partial_bytes() and B200_GN_COUNTERS zero-initialised unsigneds owned by the
 // backend instance: large groups are then split over several CTAs (one read of x, deterministic merge by the last CTA)
 #define B200_GN_COUNTERS 4096
+// addv (optional): per-(image, channel) f32 vector [N][C] added to x on the fly (the ResBlock's `h + emb` broadcast ADD, block.hpp:150-160)
 int b200_launch_gn_stats(cudaStream_t s, const float* x, float* stats, int64_t N, int64_t C, int64_t inner, int n_groups, float eps, void* partial = nullptr,
-                         unsigned* counters = nullptr);
+                         unsigned* counters = nullptr, const float* addv = nullptr);
 size_t b200_gn_stats_partial_bytes(int64_t N, int64_t C, int64_t inner, int n_groups);
 // NCHW f32 -> NHWC f16 with optional GroupNorm (stats + per-channel w, b), SiLU (act = 1) and nearest upsampling (up = 1 | 2)
 int b200_launch_to_nhwc_f16(cudaStream_t s, const float* x, void* out, int64_t N, int64_t C, int64_t H, int64_t W, int up, const float* stats,
-                            int n_groups, const float* gw, const float* gb, int act);
+                            int n_groups, const float* gw, const float* gb, int act, const float* addv = nullptr);
 int b200_launch_pack_conv_weight(cudaStream_t s, const void* w, void* out, int KW, int KH, int64_t IC, int64_t OC);
 
 // ---- peer.cu: CFG-split exchange over NVLink peer memory -------------------------------------------------------------------------

@@ -35,7 +35,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 __global__ void __launch_bounds__(1024) k_gn_stats(const float* __restrict__ x, float2* __restrict__ stats, int64_t inner, int C, int cpg, int G,
-                                                   float eps) {
+                                                   float eps, const float* __restrict__ addv) {
     pdl_wait();
     pdl_launch_dependents();
     __shared__ float red[32];
@@ -44,8 +44,11 @@ __global__ void __launch_bounds__(1024) k_gn_stats(const float* __restrict__ x, 
     if (c0 >= c1) return;
     const int64_t len = (int64_t)(c1 - c0) * inner;
     const float* xp = x + ((int64_t)n * C + c0) * inner;
+    const float* av = addv ? addv + (int64_t)n * C + c0 : nullptr;      // per-channel value added on the fly (x + emb broadcast)
     float s = 0.f;
-    if (((uintptr_t)xp % 16 == 0) && (len % 4 == 0)) {
+    if (av) {
+        for (int64_t i = threadIdx.x; i < len; i += blockDim.x) s += xp[i] + av[i / inner];
+    } else if (((uintptr_t)xp % 16 == 0) && (len % 4 == 0)) {
         const float4* x4 = (const float4*)xp;
         for (int64_t i = threadIdx.x; i < len / 4; i += blockDim.x) { float4 v = x4[i]; s += (v.x + v.y) + (v.z + v.w); }
     } else {
@@ -53,7 +56,9 @@ __global__ void __launch_bounds__(1024) k_gn_stats(const float* __restrict__ x, 
     }
     const float mean = block_sum(s, red) / (float)len;
     float s2 = 0.f;
-    if (((uintptr_t)xp % 16 == 0) && (len % 4 == 0)) {
+    if (av) {
+        for (int64_t i = threadIdx.x; i < len; i += blockDim.x) { float v = (xp[i] + av[i / inner]) - mean; s2 += v * v; }
+    } else if (((uintptr_t)xp % 16 == 0) && (len % 4 == 0)) {
         const float4* x4 = (const float4*)xp;
         for (int64_t i = threadIdx.x; i < len / 4; i += blockDim.x) {
             float4 v = x4[i];
@@ -72,9 +77,9 @@ __global__ void __launch_bounds__(1024) k_gn_stats(const float* __restrict__ x, 
 // REGISTERS, computes the chunk mean and the chunk's sum of squared deviations from THAT mean (the oracle's two-pass arithmetic,
 // ops.cpp:4079-4152, per chunk), and the last CTA to finish merges the S partial (mean, M2) pairs in chunk order with the exact
 // pairwise update (Chan et al.) in double -- deterministic, one read of the activation.
-constexpr int GN2_THREADS = 512;
+constexpr int GN2_THREADS = 256;                            // ~100 registers per thread: two or more CTAs per SM, so one's reduction overlaps another's loads
 constexpr int GN2_VEC = 16;                                  // float4 per thread
-constexpr int GN2_CHUNK = GN2_THREADS * GN2_VEC * 4;         // 32768 floats
+constexpr int GN2_CHUNK = GN2_THREADS * GN2_VEC * 4;         // 16384 floats (64 KB in flight per CTA)
 
 __device__ __forceinline__ double block_sum_d(double v, double* red) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -93,9 +98,9 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
     return red[0];
 }
 
-__global__ void __launch_bounds__(GN2_THREADS) k_gn_stats_chunked(const float* __restrict__ x, float2* __restrict__ stats, double2* partial,
+__global__ void __launch_bounds__(GN2_THREADS, 2) k_gn_stats_chunked(const float* __restrict__ x, float2* __restrict__ stats, double2* partial,
                                                                   unsigned* __restrict__ counters, int64_t inner, int C, int cpg, int G, int S,
-                                                                  int64_t chunk, float eps) {
+                                                                  int64_t chunk, float eps, const float* __restrict__ addv) {
     pdl_wait();
     pdl_launch_dependents();
     __shared__ double red[32];
@@ -112,6 +117,10 @@ __global__ void __launch_bounds__(GN2_THREADS) k_gn_stats_chunked(const float* _
     for (int k = 0; k < GN2_VEC; ++k) {
         const int64_t i = (int64_t)k * GN2_THREADS + threadIdx.x;
         r[k] = i < nv ? x4[v0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (addv && i < nv) {       // x + emb broadcast (per channel): inner % 4 == 0, so the four values share a channel
+            const float e = addv[(int64_t)n * C + c0 + (4 * (v0 + i)) / inner];
+            r[k].x += e; r[k].y += e; r[k].z += e; r[k].w += e;
+        }
         s += (r[k].x + r[k].y) + (r[k].z + r[k].w);
     }
     const double cnt = (double)(e1 - e0);
@@ -156,65 +165,88 @@ __global__ void __launch_bounds__(GN2_THREADS) k_gn_stats_chunked(const float* _
     }
 }
 
-// grid (ceil(OH*OW / 64), C / 64, N), block 256: a 64-channel x 64-pixel tile through shared memory.
+// grid (ceil(OH*OW / (64 * NSUB)), C / 64, N), block 256: 64-channel x 64-pixel tiles through shared memory, NSUB of them per CTA.
 // Load: 16 lanes x float4 cover 64 consecutive pixels of one channel (coalesced 256 B), per-channel norm/affine constants are
-// fetched once per channel per thread.  Store: one warp writes one pixel's 64 channels = 128 contiguous bytes of the NHWC row.
-template <int UP>
+// fetched once per channel per thread; with NSUB = 4 a thread issues its 16 loads (1 KB of every channel row, 64 KB per CTA) before the
+// first use -- the 64-pixel version kept only 16 KB per CTA in flight and ran at a third of the HBM rate on the VAE's 512x512 levels.
+// Store: one warp writes one pixel's 64 channels = 128 contiguous bytes of the NHWC row.
+template <int UP, int NSUB>
 __global__ void __launch_bounds__(256) k_to_nhwc_f16(const float* __restrict__ x, __half* __restrict__ out, const float2* __restrict__ stats,
                                                      const float* __restrict__ gw, const float* __restrict__ gb, int C, int H, int W, int OH,
-                                                     int OW, int cpg, int G, int act, int vec_ok) {
+                                                     int OW, int cpg, int G, int act, int vec_ok, const float* __restrict__ addv) {
     pdl_wait();
     pdl_launch_dependents();
     __shared__ float tile[64][65];
     const int n = blockIdx.z;
     const int c0 = blockIdx.y * 64;
     const int64_t OHW = (int64_t)OH * OW;
-    const int64_t p0 = (int64_t)blockIdx.x * 64;
+    const int64_t pbase = (int64_t)blockIdx.x * (64 * NSUB);
     const int t = threadIdx.x;
     const int px4 = (t & 15) * 4;          // first of 4 consecutive output pixels handled by this thread
+    const int warp = t >> 5, lane = t & 31;
+    float v[NSUB][4][4];
+    // ---- all loads first
 #pragma unroll
-    for (int pass = 0; pass < 4; ++pass) {
-        const int cl = pass * 16 + (t >> 4);
-        const int c = c0 + cl;
-        float mean = 0.f, rstd = 1.f, w = 1.f, b = 0.f;
-        if (stats) { const float2 st = stats[(int64_t)n * G + c / cpg]; mean = st.x; rstd = st.y; }
-        if (gw) { w = gw[c]; b = gb ? gb[c] : 0.f; }
-        const float* xc = x + ((int64_t)n * C + c) * H * W;
-        float v[4];
-        const int64_t p = p0 + px4;
-        if (UP == 1 && vec_ok && p + 3 < OHW) {
-            const float4 q = *(const float4*)(xc + p);     // OHW == H*W, 16-byte aligned: p % 4 == 0 and channel planes are multiples of 4 floats
-            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-        } else {
+    for (int sub = 0; sub < NSUB; ++sub) {
+        const int64_t p0 = pbase + sub * 64;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int64_t pp = p + k;
-                if (pp < OHW) {
-                    const int oy = (int)(pp / OW), ox = (int)(pp - (int64_t)oy * OW);
-                    v[k] = xc[(int64_t)(oy / UP) * W + (ox / UP)];
-                } else {
-                    v[k] = 0.f;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int c = c0 + pass * 16 + (t >> 4);
+            const float* xc = x + ((int64_t)n * C + c) * H * W;
+            const int64_t p = p0 + px4;
+            if (UP == 1 && vec_ok && p + 3 < OHW) {
+                const float4 q = *(const float4*)(xc + p);     // OHW == H*W, 16-byte aligned: p % 4 == 0 and channel planes are multiples of 4 floats
+                v[sub][pass][0] = q.x; v[sub][pass][1] = q.y; v[sub][pass][2] = q.z; v[sub][pass][3] = q.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int64_t pp = p + k;
+                    if (pp < OHW) {
+                        const int oy = (int)(pp / OW), ox = (int)(pp - (int64_t)oy * OW);
+                        v[sub][pass][k] = xc[(int64_t)(oy / UP) * W + (ox / UP)];
+                    } else {
+                        v[sub][pass][k] = 0.f;
+                    }
                 }
             }
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float o = (v[k] - mean) * rstd;
-            o = o * w + b;
-            if (act == 1) o = o / (1.0f + expf(-o));
-            tile[cl][px4 + k] = o;
-        }
     }
-    __syncthreads();
-    const int warp = t >> 5, lane = t & 31;
+    // ---- per-channel constants (the same four channels for every sub-tile)
+    float mean[4], rstd[4], w[4], b[4], pre[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int pl = warp * 8 + k;
-        const int64_t p = p0 + pl;
-        if (p < OHW) {
-            const __half2 hv = __floats2half2_rn(tile[2 * lane][pl], tile[2 * lane + 1][pl]);
-            *(__half2*)(out + ((int64_t)n * OHW + p) * C + c0 + 2 * lane) = hv;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int c = c0 + pass * 16 + (t >> 4);
+        mean[pass] = 0.f; rstd[pass] = 1.f; w[pass] = 1.f; b[pass] = 0.f;
+        if (stats) { const float2 st = stats[(int64_t)n * G + c / cpg]; mean[pass] = st.x; rstd[pass] = st.y; }
+        if (gw) { w[pass] = gw[c]; b[pass] = gb ? gb[c] : 0.f; }
+        pre[pass] = addv ? addv[(int64_t)n * C + c] : 0.f;       // x + emb broadcast, added exactly where the unfused ADD rounds
+    }
+#pragma unroll
+    for (int sub = 0; sub < NSUB; ++sub) {
+        const int64_t p0 = pbase + sub * 64;
+        if (p0 >= OHW) break;
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {
+            const int cl = pass * 16 + (t >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float o = ((addv ? v[sub][pass][k] + pre[pass] : v[sub][pass][k]) - mean[pass]) * rstd[pass];
+                o = o * w[pass] + b[pass];
+                if (act == 1) o = o / (1.0f + expf(-o));
+                tile[cl][px4 + k] = o;
+            }
         }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int pl = warp * 8 + k;
+            const int64_t p = p0 + pl;
+            if (p < OHW) {
+                const __half2 hv = __floats2half2_rn(tile[2 * lane][pl], tile[2 * lane + 1][pl]);
+                *(__half2*)(out + ((int64_t)n * OHW + p) * C + c0 + 2 * lane) = hv;
+            }
+        }
+        if (NSUB > 1) __syncthreads();
     }
 }
 
@@ -261,21 +293,21 @@ int b200_launch_dequant_q8_0(cudaStream_t s, const void* blocks, void* out_f16, 
 }
 
 int b200_launch_gn_stats(cudaStream_t s, const float* x, float* stats, int64_t N, int64_t C, int64_t inner, int n_groups, float eps, void* partial,
-                         unsigned* counters) {
+                         unsigned* counters, const float* addv) {
     const int cpg = (int)((C + n_groups - 1) / n_groups);
     const int64_t len = (int64_t)cpg * inner;
     const int64_t S = (len + GN2_CHUNK - 1) / GN2_CHUNK;
     // chunked path: every group complete (C % cpg == 0), float4-aligned chunks, counters available
-    if (partial && counters && S >= 2 && S <= 1024 && C % cpg == 0 && (inner & 3) == 0 && (((uintptr_t)x) & 15) == 0 && N * n_groups <= B200_GN_COUNTERS && N <= 65535) {
+    if (partial && counters && S >= 2 && S <= 4096 && C % cpg == 0 && (inner & 3) == 0 && (((uintptr_t)x) & 15) == 0 && N * n_groups <= B200_GN_COUNTERS && N <= 65535) {
         int64_t chunk = (len + S - 1) / S;
         chunk = (chunk + 3) & ~(int64_t)3;
         dim3 grid((unsigned)S, (unsigned)n_groups, (unsigned)N);
         b200_launch(k_gn_stats_chunked, dim3(grid), dim3(GN2_THREADS), 0, s, x, (float2*)stats, (double2*)partial, counters, inner, (int)C, cpg, n_groups, (int)S,
-                    chunk, eps);
+                    chunk, eps, addv);
         return 1;
     }
     dim3 grid((unsigned)n_groups, (unsigned)N);
-    b200_launch(k_gn_stats, dim3(grid), dim3(1024), 0, s, x, (float2*)stats, inner, (int)C, cpg, n_groups, eps);
+    b200_launch(k_gn_stats, dim3(grid), dim3(1024), 0, s, x, (float2*)stats, inner, (int)C, cpg, n_groups, eps, addv);
     return 1;
 }
 
@@ -286,17 +318,19 @@ size_t b200_gn_stats_partial_bytes(int64_t N, int64_t C, int64_t inner, int n_gr
 }
 
 int b200_launch_to_nhwc_f16(cudaStream_t s, const float* x, void* out, int64_t N, int64_t C, int64_t H, int64_t W, int up, const float* stats,
-                            int n_groups, const float* gw, const float* gb, int act) {
+                            int n_groups, const float* gw, const float* gb, int act, const float* addv) {
     if (C % 64 != 0) return -1;
     const int64_t OH = H * up, OW = W * up;
     const int cpg = n_groups > 0 ? (int)((C + n_groups - 1) / n_groups) : 1;
-    dim3 grid((unsigned)((OH * OW + 63) / 64), (unsigned)(C / 64), (unsigned)N);
+    const int nsub = (up == 1 && OH * OW >= 16384) ? 4 : 1;           // large images: 256 pixels per CTA, 64 KB of loads in flight
+    dim3 grid((unsigned)((OH * OW + 64 * nsub - 1) / (64 * nsub)), (unsigned)(C / 64), (unsigned)N);
     if (grid.y > 65535 || N > 65535 || (up != 1 && up != 2)) return -1;
     const int vec_ok = (((uintptr_t)x & 15) == 0 && ((H * W) & 3) == 0) ? 1 : 0;
-    if (up == 1)
-        b200_launch(k_to_nhwc_f16<1>, dim3(grid), dim3(256), 0, s, x, (__half*)out, (const float2*)stats, gw, gb, (int)C, (int)H, (int)W, (int)OH, (int)OW, cpg, n_groups, act, vec_ok);
-    else
-        b200_launch(k_to_nhwc_f16<2>, dim3(grid), dim3(256), 0, s, x, (__half*)out, (const float2*)stats, gw, gb, (int)C, (int)H, (int)W, (int)OH, (int)OW, cpg, n_groups, act, vec_ok);
+#define NHWC_ARGS x, (__half*)out, (const float2*)stats, gw, gb, (int)C, (int)H, (int)W, (int)OH, (int)OW, cpg, n_groups, act, vec_ok, addv
+    if (up == 1 && nsub == 4) b200_launch(k_to_nhwc_f16<1, 4>, dim3(grid), dim3(256), 0, s, NHWC_ARGS);
+    else if (up == 1) b200_launch(k_to_nhwc_f16<1, 1>, dim3(grid), dim3(256), 0, s, NHWC_ARGS);
+    else b200_launch(k_to_nhwc_f16<2, 1>, dim3(grid), dim3(256), 0, s, NHWC_ARGS);
+#undef NHWC_ARGS
     return 1;
 }
 

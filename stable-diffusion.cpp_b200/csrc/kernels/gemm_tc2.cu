@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                     for (int i = 0; i < 32; ++i)
                         if (c0 + i < p.bn) sred[(c0 + i) * BM + ml] = __uint_as_float(r[i]);
                 }
-            } else if (p.act == 0 && p.vec_epi) {
+            } else if (p.vec_epi) {
                 // Staged stores.  A thread owns one accumulator ROW (TMEM lane), but memory wants a column's 128 consecutive rows in one
                 // piece: the four warps of this column group write a 32-column chunk to shared memory as [column][row], then every warp
                 // streams 8 of the columns with 16 bytes per lane -- one store instruction = 512 contiguous bytes (and the residual is read
@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                             float4 v = *(const float4*)(stage + col * BM + 4 * lane);
                             const float bn = p.bias_mode == 2 ? p.bias[n0 + n] : 0.f;
                             v.x += bm4.x + bn; v.y += bm4.y + bn; v.z += bm4.z + bn; v.w += bm4.w + bn;
+                            if (p.act) { v.x = act_fn(v.x, p.act); v.y = act_fn(v.y, p.act); v.z = act_fn(v.z, p.act); v.w = act_fn(v.w, p.act); }
                             const int64_t off = (int64_t)(n0 + n) * p.ldd + mrow;
                             if (Rp) {
                                 const float4 rr = *(const float4*)(Rp + (int64_t)(n0 + n) * p.ldr + mrow);
@@ -478,7 +479,7 @@ cudaError_t launch2(cudaStream_t s, unsigned ctas, unsigned splits, size_t smem,
 int vec_epilogue_ok(const G2Params& kp, int splits) {
     static int en = -1;
     if (en < 0) { const char* e = getenv("GGML_B200_GEMM2_VEC_EPI"); en = (e && *e) ? atoi(e) : 1; }
-    if (!en || splits != 1 || kp.act != 0) return 0;
+    if (!en || splits != 1) return 0;
     if ((kp.M & 3) || (kp.ldd & 3) || (kp.d_batch_stride & 3) || ((uintptr_t)kp.D & 15)) return 0;
     if (kp.residual && ((kp.ldr & 3) || (kp.r_batch_stride & 3) || ((uintptr_t)kp.residual & 15))) return 0;
     if (kp.bias_mode == 1 && ((uintptr_t)kp.bias & 15)) return 0;

@@ -40,6 +40,18 @@ __global__ void __launch_bounds__(kWarps * 32) k_gemv(const WT* __restrict__ W, 
     extern __shared__ float xs[];    // [N][K], rounded to WT
     pdl_wait();
     pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x * kWarps + warp;
+    const int K8 = K / 8;
+    // the weight stream is what this kernel waits for: put the first 4 x 16 bytes per lane in flight BEFORE the activation rows are staged
+    // (their global reads + SiLU + barrier used to sit in front of the first weight load), then keep 4 loads per lane ahead of the math
+    const uint4* wrow = (const uint4*)(W + (int64_t)min(m, M - 1) * lda);
+    uint4 wreg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = lane + 32 * j;
+        wreg[j] = c < K8 ? wrow[c] : make_uint4(0u, 0u, 0u, 0u);
+    }
     for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
         const int n = i / K, k = i - n * K;
         float v = X[(int64_t)n * ldx + k];
@@ -47,21 +59,32 @@ __global__ void __launch_bounds__(kWarps * 32) k_gemv(const WT* __restrict__ W, 
         xs[i] = round_to<WT>(v);
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m = blockIdx.x * kWarps + warp;
     if (m >= M) return;
-    const uint4* wrow = (const uint4*)(W + (int64_t)m * lda);
     float acc[kMaxN] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = lane; c < K / 8; c += 32) {
-        float w[8];
-        unpack8<WT>(wrow[c], w);
+    for (int c0 = lane; c0 < K8; c0 += 128) {
+        uint4 cur[4];
 #pragma unroll
-        for (int n = 0; n < kMaxN; ++n) {
-            if (n < N) {
-                const float4 x0 = *(const float4*)(xs + n * K + c * 8), x1 = *(const float4*)(xs + n * K + c * 8 + 4);
-                const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        for (int j = 0; j < 4; ++j) cur[j] = wreg[j];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[n] = fmaf(w[i], x[i], acc[n]);
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + 128 + 32 * j;
+            wreg[j] = c < K8 ? wrow[c] : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + 32 * j;
+            if (c < K8) {
+                float w[8];
+                unpack8<WT>(cur[j], w);
+#pragma unroll
+                for (int n = 0; n < kMaxN; ++n) {
+                    if (n < N) {
+                        const float4 x0 = *(const float4*)(xs + n * K + c * 8), x1 = *(const float4*)(xs + n * K + c * 8 + 4);
+                        const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[n] = fmaf(w[i], x[i], acc[n]);
+                    }
+                }
             }
         }
     }

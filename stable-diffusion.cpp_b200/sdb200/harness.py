@@ -43,7 +43,8 @@ EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C
 STAT_KEYS = ("graphs", "kernel_launches", "nodes_executed", "fused_nodes", "last_graph_ms", "total_graph_ms", "tc_gemm_launches",
              "tc_gemm_flops", "tc_gemm_us", "fused_attn_launches", "cuda_graph_replays", "implicit_convs", "q_read_in_place", "gemv_launches", "rope_launches", "_unused",
              "gemm_ref_launches", "host_us", "weight_write_graphs", "per_graph_filter_packs", "persistent_gemm_launches", "cta2_gemm_launches",
-             "derived_weight_bytes", "unfused_attention", "peer_exchanges")
+             "derived_weight_bytes", "unfused_attention", "peer_exchanges",
+             "host_set_us", "host_get_us", "host_compute_us", "host_outside_us")
 
 
 class Harness:
