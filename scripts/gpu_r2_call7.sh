@@ -3,6 +3,11 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 export GGML_BACKEND_PATH=$PWD/stable-diffusion.cpp_b200/lib/libggml-b200.so
+echo "== gemm_bench: bulk-store epilogue on / off"
+GEMM_BENCH_PAIR=1 GEMM_BENCH_FEW=1 timeout 200 stable-diffusion.cpp_b200/lib/gemm_bench 20 2>&1 | cut -c1-160 > gpurun_out/r2c7_bench_tma1.log; echo rc=$?
+GGML_B200_GEMM2_TMA_STORE=0 GEMM_BENCH_PAIR=1 GEMM_BENCH_FEW=1 timeout 200 stable-diffusion.cpp_b200/lib/gemm_bench 20 2>&1 | cut -c1-160 > gpurun_out/r2c7_bench_tma0.log; echo rc=$?
+ok=$(grep -c "mismatches 0 " gpurun_out/r2c7_bench_tma1.log); all=$(grep -c "pair bn" gpurun_out/r2c7_bench_tma1.log); echo "bulk-store epilogue: $ok / $all exact"
+if [ "$ok" != "$all" ] || [ "$all" -lt 50 ]; then echo "!! bulk-store epilogue disabled for the rest of this call"; export GGML_B200_GEMM2_TMA_STORE=0; fi
 echo "== full gpu suite"
 timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -15 | tee gpurun_out/r2c7_pytest.log
 echo "== smoke"

@@ -54,6 +54,7 @@ struct G2Params {
     const float* residual;
     int64_t ldr, r_batch_stride;
     int act;
+    int tma_store;          // staged epilogue whose 32-column x 128-row chunks leave through cp.async.bulk.tensor stores (no residual / peer copy)
     int vec_epi;            // staged epilogue: the 4 warps of a column group transpose 32 columns x 128 rows through shared memory and store 512 B per column
     int stage_off;          // byte offset of the two 16 KB staging tiles behind the operand ring
     int nprod;              // TMA producer threads per CTA: 2 (A and B issued by different warps, default) or 1 (A/B of GGML_B200_GEMM2_NPROD)
@@ -107,7 +108,7 @@ __device__ __forceinline__ float act_fn(float v, int act) {
 // FMT: 0 = f16, 1 = bf16
 template <int FMT>
 __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                         const G2Params p) {
+                                                         const __grid_constant__ CUtensorMap tmD, const G2Params p) {
     constexpr int BK = 64, UMMA_K = 16;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
@@ -259,6 +260,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         if (c0 + i < p.bn) sred[(c0 + i) * BM + ml] = __uint_as_float(r[i]);
+                }
+            } else if (p.tma_store) {
+                // Staged stores through the TMA: the four warps of this column group write bias / activation applied values of a 32-column
+                // chunk to shared memory as [column][row] -- exactly the dense box {128 m, 32 n} of the f32 output map -- and ONE thread hands
+                // the 16 KB to cp.async.bulk.tensor.  The LSU path (st.global from 8 warps) topped out near 10 B/clk per SM, as long as a
+                // 17-k-block main loop per 128 x 128 tile; the bulk store also clips the M / N edges itself.
+                float* stage = (float*)(smem + p.stage_off) + half * (32 * BM);
+                const int wq = (warp - 2) & 3;
+                const float* bias_n = p.bias_mode == 2 ? p.bias + n0 : nullptr;
+#pragma unroll 1
+                for (int c0 = half * 32; c0 < ncols; c0 += 64) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c0, r);
+                    const float bn = (bias_n && c0 + lane < ncols) ? bias_n[c0 + lane] : 0.f;   // lane i carries the bias of column c0 + i
+                    tmem_ld_wait();
+                    // the previous chunk's bulk store has finished READING the staging tile (its issuer waited) before anyone overwrites it
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float v = __uint_as_float(r[i]) + bias_m + __shfl_sync(0xffffffffu, bn, i);
+                        if (p.act) v = act_fn(v, p.act);
+                        stage[i * BM + ml] = v;
+                    }
+                    fence_proxy_async();                                   // generic-proxy writes -> visible to the bulk-copy engine
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                    if (wq == 0 && lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tmD)),
+                                     "r"(smem_u32(stage)), "r"(m0), "r"(n0 + c0), "r"(batch)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
                 }
             } else if (p.vec_epi) {
                 // Staged stores.  A thread owns one accumulator ROW (TMEM lane), but memory wants a column's 128 consecutive rows in one
@@ -419,6 +452,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
             }
         }
     }
+    if (p.tma_store && lane == 0 && (warp == 2 || warp == 6)) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // bulk stores complete
     // nobody may exit while a peer can still read its shared memory (DSMEM reduce, the pair's MMAs) or signal its barriers
     tc_fence_before();
     cluster_sync_all();
@@ -444,7 +478,8 @@ bool encode_rows(CUtensorMap* out, const void* ptr, int type, int64_t K, int64_t
 }
 
 template <int FMT>
-cudaError_t launch2(cudaStream_t s, unsigned ctas, unsigned splits, size_t smem, const CUtensorMap& ta, const CUtensorMap& tb, const G2Params& kp) {
+cudaError_t launch2(cudaStream_t s, unsigned ctas, unsigned splits, size_t smem, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
+                    const G2Params& kp) {
     static size_t configured[B200_MAX_DEVICES] = {};
     int d = 0;
     cudaGetDevice(&d);
@@ -472,7 +507,7 @@ cudaError_t launch2(cudaStream_t s, unsigned ctas, unsigned splits, size_t smem,
     ++n;
     cfg.numAttrs = n;
     cfg.attrs = attr;
-    return cudaLaunchKernelEx(&cfg, k_gemm_tc2<FMT>, ta, tb, kp);
+    return cudaLaunchKernelEx(&cfg, k_gemm_tc2<FMT>, ta, tb, td, kp);
 }
 
 // may the epilogue use 16-byte stores along m?  (GGML_B200_GEMM2_VEC_EPI=0 keeps the per-row path for A/B runs)
@@ -485,6 +520,27 @@ int vec_epilogue_ok(const G2Params& kp, int splits) {
     if (kp.bias_mode == 1 && ((uintptr_t)kp.bias & 15)) return 0;
     if (kp.D2 && (((uintptr_t)kp.D2 & 15) || (kp.d2_slot & 3))) return 0;
     return 1;
+}
+
+// f32 output as a 3-D tensor (m, n, batch) with a dense box {128, 32, 1}: what one bulk store of the staged epilogue writes
+bool encode_output(CUtensorMap* out, G2Params& kp, int64_t batch) {
+    static int en = -1;
+    if (en < 0) { const char* e = getenv("GGML_B200_GEMM2_TMA_STORE"); en = (e && *e) ? atoi(e) : 1; }
+    memset(out, 0, sizeof(*out));
+    kp.tma_store = 0;
+    if (!en || !kp.vec_epi || kp.residual || kp.D2) return true;
+    if ((kp.ldd * 4) % 16 || (kp.d_batch_stride * 4) % 16 || ((uintptr_t)kp.D & 15)) return true;
+    auto enc = b200_get_tensormap_encoder();
+    if (!enc) return true;
+    cuuint64_t dims[3] = {(cuuint64_t)kp.M, (cuuint64_t)kp.N, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)kp.ldd * 4, (cuuint64_t)(batch > 1 ? kp.d_batch_stride : kp.ldd * kp.N) * 4};
+    cuuint32_t box[3] = {128, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, kp.D, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return true;
+    kp.tma_store = 1;
+    return true;
 }
 
 // shared by the GEMM and the conv front end: fills the tile geometry for a chosen (bn, splits)
@@ -579,7 +635,9 @@ int b200_launch_gemm_tc2(cudaStream_t s, const b200_device_info& dev, const b200
     kp.residual = g.residual; kp.ldr = g.ldr; kp.r_batch_stride = g.d_batch_stride;
     kp.act = g.act;
     kp.vec_epi = vec_epilogue_ok(kp, splits);
-    cudaError_t e = g.type == GGML_TYPE_F16 ? launch2<0>(s, ctas, (unsigned)splits, smem, ta, tb, kp) : launch2<1>(s, ctas, (unsigned)splits, smem, ta, tb, kp);
+    CUtensorMap td;
+    encode_output(&td, kp, g.batch);
+    cudaError_t e = g.type == GGML_TYPE_F16 ? launch2<0>(s, ctas, (unsigned)splits, smem, ta, tb, td, kp) : launch2<1>(s, ctas, (unsigned)splits, smem, ta, tb, td, kp);
     if (e != cudaSuccess) {
         fprintf(stderr, "[ggml-b200] CTA-pair GEMM launch failed: %s\n", cudaGetErrorString(e));
         cudaGetLastError();
@@ -624,7 +682,9 @@ int b200_launch_conv_tc2(cudaStream_t s, const b200_device_info& dev, const b200
     kp.D2 = c.D2; kp.d2_seq = c.d2_seq; kp.d2_slot = c.d2_slot_floats;
     kp.vec_epi = vec_epilogue_ok(kp, splits);
     kp.conv = 1; kp.conv_W = (int)c.W; kp.conv_KW = c.KW; kp.conv_cblocks = (int)(c.C / 64); kp.conv_pad = c.pad; kp.conv_dil = c.dil;
-    cudaError_t e = launch2<0>(s, ctas, (unsigned)splits, smem, ta, tb, kp);
+    CUtensorMap td;
+    encode_output(&td, kp, c.N);
+    cudaError_t e = launch2<0>(s, ctas, (unsigned)splits, smem, ta, tb, td, kp);
     if (e != cudaSuccess) {
         fprintf(stderr, "[ggml-b200] CTA-pair conv launch failed: %s\n", cudaGetErrorString(e));
         cudaGetLastError();
