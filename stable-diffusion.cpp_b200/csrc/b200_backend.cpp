@@ -587,6 +587,7 @@ int ggml_backend_b200_get_stats(ggml_backend_t backend, ggml_b200_stats* out) {
     b200_context_finalize_timing((b200_context*)backend->context);
     ((b200_context*)backend->context)->stats.ext[6] = b200_derived_weight_bytes();
     for (int i = 0; i < 4; ++i) ((b200_context*)backend->context)->stats.ext[9 + i] = b200_boundary_clock::us(i);
+    b200_boundary_clock::cut();
     memcpy(out, &((b200_context*)backend->context)->stats, sizeof(*out));
     return 0;
 }

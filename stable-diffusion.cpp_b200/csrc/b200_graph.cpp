@@ -298,6 +298,10 @@ struct mm_fusion {
     const ggml_tensor* src1_pre = nullptr;   // activation to read instead of src[1] (same shape): the input of a unary op folded in
     int pre_act = 0;                          // 1: SiLU applied to src1_pre on load (only the few-row GEMV path can do this)
     int act = 0;                              // activation after the bias, before the residual: 1 SiLU, 2 GELU (tanh form) -- the epilogue's act_fn
+    void* d16 = nullptr;                      // 16-bit copy of the result for the contraction that consumes it (b200_gemm_args::D16)
+    int d16_type = 0;
+    bool skip_f32 = false;
+    int* d16_done = nullptr;
 };
 
 static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz = nullptr) {
@@ -444,6 +448,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
         if (fz && fz->bias) { g.bias = fz->bias; g.bias_mode = fz->bias_mode; }
         if (fz && fz->residual) { g.residual = fz->residual; g.ldr = g.ldd; }
         if (fz) g.act = fz->act;
+        if (fz && fz->d16 && nb13 == 1) { g.D16 = fz->d16; g.d16_type = fz->d16_type; g.skip_f32 = fz->skip_f32 ? 1 : 0; g.d16_done = fz->d16_done; }
         // model weights read in place are constants of the graph: their first ring-full may be fetched before the PDL wait.  Not for
         // the first kernel of a graph_compute (its stream predecessor belongs to an earlier call, e.g. a weight update).
         if (ctx->opt_early_weights && a.ptr == src0->data && src0->buffer && src0->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS &&
@@ -522,7 +527,33 @@ static int op_flash_attn(b200_context* ctx, ggml_tensor* dst, const fa_fusion* f
     const int64_t es = 2;
     const int64_t Lk_pad = (Lk + 7) / 8 * 8;
 
-    // V^T: [Lk, dv, Hkv, NB] view of v, packed to ct with Lk padded
+    // fused single-kernel path first, reading V in place (MN-major operand of the P.V product): no V^T pass, no workspace
+    static int fa_vmn = -1;
+    if (fa_vmn < 0) { const char* e = getenv("GGML_B200_FA_VMN"); fa_vmn = (e && *e) ? atoi(e) : 1; }
+    if (fa_vmn && ctx->opt_tc_gemm && ctx->opt_fused_attn && max_bias == 0.0f && ct == GGML_TYPE_F16 && k->type == GGML_TYPE_F16 && v->type == GGML_TYPE_F16) {
+        b200_td mtd;
+        if (mask) mtd = b200_make_td(mask);
+        void* shadow = nullptr;
+        if (fz && fz->shadow_act) shadow = ws_alloc(ctx, (size_t)ggml_nelements(dst) * 2);
+        int n = b200_launch_flash_attn_fused(ctx->stream, fz && fz->q_td ? *fz->q_td : b200_make_td(q), b200_make_td(k), nullptr, 0, b200_make_td(v),
+                                             mask ? &mtd : nullptr, b200_make_td(dst), scale, shadow);
+        if (n < 0 && shadow) {
+            shadow = nullptr;
+            n = b200_launch_flash_attn_fused(ctx->stream, fz && fz->q_td ? *fz->q_td : b200_make_td(q), b200_make_td(k), nullptr, 0, b200_make_td(v),
+                                             mask ? &mtd : nullptr, b200_make_td(dst), scale, nullptr);
+        }
+        if (n > 0) {
+            ctx->stats.reserved[2] += (uint64_t)n;   // fused attention launches
+            if (shadow) {
+                const ggml_tensor* a = fz->shadow_act;
+                ctx->pack_cache[std::make_pair(a, (int)GGML_TYPE_F16)] = operand{shadow, GGML_TYPE_F16, a->ne[0], a->ne[0] * a->ne[1], a->ne[0] * a->ne[1] * a->ne[2]};
+            }
+            if (fz && fz->q_td) ctx->stats.reserved[5] += 1;   // Q read in place: CONT skipped
+            return launches + n;
+        }
+    }
+
+    // V^T: [Lk, dv, Hkv, NB] view of v, packed to ct with Lk padded (the GEMM + softmax + GEMM path and head sizes outside the fused envelope)
     ggml_tensor vt = *v;
     vt.ne[0] = v->ne[1]; vt.nb[0] = v->nb[1];
     vt.ne[1] = v->ne[0]; vt.nb[1] = v->nb[0];
@@ -1044,6 +1075,28 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
             }
         }
     }
+    // Linear -> GELU -> Linear (flux.hpp Mlp, mmdit, wan FFN): the activated result's ONLY reader is the next contraction, which wants it
+    // rounded to its weight type.  The epilogue writes that 16-bit operand itself and -- nothing else reading the f32 tensor -- skips the
+    // f32 store: the MLP-up projection is bound by output bytes (f32 [12288, 4352] = 214 MB per Flux block at ~2.7 TB/s of write bandwidth)
+    int d16_done = 0;
+    const ggml_tensor* d16_act = nullptr;
+    static int d16_enabled = -1;
+    if (d16_enabled < 0) { const char* e = getenv("GGML_B200_D16"); d16_enabled = (e && *e) ? atoi(e) : 1; }
+    if (d16_enabled && fz.act && !chain.empty()) {
+        const ggml_tensor* curv = g->nodes[chain.back()];
+        const int jm = next_node(g, fs, chain.back());
+        if (jm >= 0 && single_use(fs, curv) && ggml_is_contiguous(curv) && mm->ne[2] * mm->ne[3] == 1) {
+            const ggml_tensor* nm = g->nodes[jm];
+            if (nm->op == GGML_OP_MUL_MAT && nm->src[1] == curv && (nm->src[0]->type == GGML_TYPE_F16 || nm->src[0]->type == GGML_TYPE_BF16) &&
+                (curv->ne[0] * 2) % 16 == 0 && !ctx->pack_cache.count(std::make_pair(curv, (int)nm->src[0]->type))) {
+                void* sh = ws_alloc(ctx, (size_t)ggml_nelements(curv) * 2);
+                if (sh) {
+                    fz.d16 = sh; fz.d16_type = (int)nm->src[0]->type; fz.skip_f32 = true; fz.d16_done = &d16_done;
+                    d16_act = curv;
+                }
+            }
+        }
+    }
     // residual: ... -> ADD(value, r) with r a same-shape tensor that already exists (the ADD is the very next work node, so r was
     // produced before this MUL_MAT).  Read in the epilogue of the element it is added to, so in-place adds onto r are fine.
     {
@@ -1073,8 +1126,11 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
     auto overlaps = [](const void* a, size_t na, const void* b, size_t nb) { return (const char*)a < (const char*)b + nb && (const char*)b < (const char*)a + na; };
     if (overlaps(fz.out, ggml_nbytes(mm), mm->src[0]->data, ggml_nbytes(mm->src[0])) || overlaps(fz.out, ggml_nbytes(mm), mm->src[1]->data, ggml_nbytes(mm->src[1])))
         return -2;
+    if (fz.residual) { fz.d16 = nullptr; fz.skip_f32 = false; d16_act = nullptr; }     // (a residual after the activation: keep the plain path)
     int n = op_mul_mat(ctx, mm, &fz);
     if (n < 0) return n;
+    if (d16_act && d16_done)
+        ctx->pack_cache[std::make_pair(d16_act, fz.d16_type)] = operand{fz.d16, fz.d16_type, d16_act->ne[0], d16_act->ne[0] * d16_act->ne[1], d16_act->ne[0] * d16_act->ne[1] * d16_act->ne[2]};
     for (int c : chain) fs.done[c] = 1;
     *covered = (int)chain.size();
     return n;
@@ -1112,6 +1168,7 @@ void b200_boundary_clock::leave(int category) {
     if (t_bc_enter > 0) g_bc_us[category & 3].fetch_add((uint64_t)((now - t_bc_enter) / 1000), std::memory_order_relaxed);
     g_bc_last_leave.store(now, std::memory_order_relaxed);
 }
+void b200_boundary_clock::cut() { g_bc_last_leave.store(0, std::memory_order_relaxed); }
 uint64_t b200_boundary_clock::us(int what) { return g_bc_us[what & 3].load(std::memory_order_relaxed); }
 
 uint64_t b200_derived_weight_bytes() { return g_pw_bytes.load(std::memory_order_relaxed); }

@@ -112,6 +112,7 @@ struct b200_boundary_clock {
     static void enter();
     static void leave(int category);     // 0 set_tensor, 1 get_tensor (includes waiting for the device), 2 graph_compute (host side)
     static uint64_t us(int what);        // 0..2 as above, 3 = outside the backend
+    static void cut();                   // a gap that spans this point is not attributed (called when the counters are read)
 };
 
 // CFG-split exchange (kernels/peer.cu)

@@ -80,6 +80,14 @@ struct b200_gemm_args {
     int         act;        // 0 none, 1 SiLU, 2 GELU(tanh)
     int         early;      // bit 0: A, bit 1: B is a constant (weight) operand no kernel of this graph writes -> may be fetched before the PDL wait
     void*       trace;      // optional device buffer of 8 uint64: phase timestamps of CTA (0,0,0) (tools/gemm_bench)
+    // optional 16-bit copy of the result (same [N][M] element layout, ldd / d_batch_stride in elements): the K-major operand of the
+    // contraction that consumes it, rounded exactly like its operand pack would.  Honoured by the CTA-pair kernel's staged epilogue only:
+    // *d16_done is set to 1 when it was written.  skip_f32: the f32 tensor has no other reader and need not be stored at all
+    // (f32 output bytes are what bounds the MLP-up projections: ~2.7 TB/s of write bandwidth on this part).
+    void*       D16;
+    int         d16_type;   // GGML_TYPE_F16 | GGML_TYPE_BF16
+    int         skip_f32;
+    int*        d16_done;
 };
 // returns kernels launched, or -1 if the shape/alignment is not supported by the TMA path (caller falls back)
 int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g, void* workspace, size_t workspace_bytes);

@@ -42,6 +42,7 @@ struct FaParams {
     int64_t m_nb1, m_nb2, m_nb3;
     int m_ne2, m_ne3;
     int d, dv16, Lq, Lk, H, rk;    // rk = H / Hkv
+    int v_mn;                      // V is read in its natural [key][dv] layout (MN-major B operand of the P.V product); 0: pre-transposed V^T
     int pos_scale;                 // scale > 0: the row maximum may be taken before scaling
     int q_vec;                     // Q rows are 16-byte aligned and d % 4 == 0: coalesced float4 loads
     float scale_log2;              // scale * log2(e)
@@ -127,15 +128,26 @@ __global__ void __launch_bounds__(192, FaCfg<NATOM, BLOCK_N>::MIN_CTAS) k_flash_
                 for (int a = 0; a < NATOM; ++a)
                     tma_load_4d(sK + s * C::K_STAGE + a * (BLOCK_N * 128), &tmK, &k_full[s], a * 64, j * BLOCK_N, hkv, nb);
                 mbar_wait(&v_empty[s], ph ^ 1);
-                mbar_expect_tx(&v_full[s], (BLOCK_N / 64) * v_atom_bytes);
-                for (int a = 0; a < BLOCK_N / 64; ++a)
-                    tma_load_4d(sV + s * C::V_STAGE + a * v_atom_bytes, &tmV, &v_full[s], j * BLOCK_N + a * 64, 0, hkv, nb);
+                if (p.v_mn) {
+                    // V as stored, [key][dv]: one box {64 dv, BLOCK_N keys} per 64-column block of dv (zero fill beyond dv and beyond Lk)
+                    const int natom_v = (p.dv16 + 63) / 64;
+                    mbar_expect_tx(&v_full[s], natom_v * (BLOCK_N * 128));
+                    for (int a = 0; a < natom_v; ++a)
+                        tma_load_4d(sV + s * C::V_STAGE + a * (BLOCK_N * 128), &tmV, &v_full[s], a * 64, j * BLOCK_N, hkv, nb);
+                } else {
+                    mbar_expect_tx(&v_full[s], (BLOCK_N / 64) * v_atom_bytes);
+                    for (int a = 0; a < BLOCK_N / 64; ++a)
+                        tma_load_4d(sV + s * C::V_STAGE + a * v_atom_bytes, &tmV, &v_full[s], j * BLOCK_N + a * 64, 0, hkv, nb);
+                }
             }
         }
     } else if (warp == 1) {
         // ============================== MMA issuer ==============================
         const uint32_t idesc_qk = make_idesc(0, BLOCK_M, BLOCK_N);
-        const uint32_t idesc_pv = make_idesc(0, BLOCK_M, (uint32_t)p.dv16);
+        // P.V: B = V.  Pre-transposed V^T is K-major like every other operand; V in its natural layout is the MN-major form (bit 16 of the
+        // instruction descriptor): rows of 64 dv values (128 B, swizzled), 8-key groups 1024 B apart (SBO), 64-column blocks of dv
+        // BLOCK_N * 128 B apart (LBO) -- no transposition pass, no V^T workspace
+        const uint32_t idesc_pv = make_idesc(0, BLOCK_M, (uint32_t)p.dv16) | (p.v_mn ? (1u << 16) : 0u);
         const int ksteps_qk = (p.d + 15) / 16;
         auto issue_qk = [&](int j) {
             const int s = j & 1;
@@ -167,7 +179,14 @@ __global__ void __launch_bounds__(192, FaCfg<NATOM, BLOCK_N>::MIN_CTAS) k_flash_
 #pragma unroll
                 for (int kk = 0; kk < BLOCK_N / 16; ++kk) {
                     const uint64_t da = make_smem_desc_sw128(pb + (kk >> 2) * (BLOCK_M * 128) + (kk & 3) * 32);
-                    const uint64_t db = make_smem_desc_sw128(vb + (kk >> 2) * v_atom_bytes + (kk & 3) * 32);
+                    uint64_t db;
+                    if (p.v_mn) {
+                        const uint32_t addr = vb + kk * 2048;                          // 16 keys = two 8-key groups of 1024 B
+                        db = (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((BLOCK_N * 128) >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+                             ((uint64_t)2 << 61);
+                    } else {
+                        db = make_smem_desc_sw128(vb + (kk >> 2) * v_atom_bytes + (kk & 3) * 32);
+                    }
                     mma_f16(tmem_O, da, db, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
                 }
                 mma_commit(&pv_done);
@@ -422,7 +441,9 @@ int b200_launch_flash_attn_fused(cudaStream_t s, const b200_td& q, const b200_td
     if (d != dv || d % 8 || d > 192 || k.type != GGML_TYPE_F16) return -1;
     if (q.nb[0] != 4 || k.nb[0] != 2) return -1;
     if (((uintptr_t)k.data & 15) || (k.nb[1] % 16) || (Hkv > 1 && k.nb[2] % 16) || (NB > 1 && k.nb[3] % 16)) return -1;
-    if (((uintptr_t)vt & 15) || ((uintptr_t)q.data & 3)) return -1;
+    const bool v_mn = vt == nullptr;          // no pre-transposed copy given: read V in place (f16, unit stride along dv, 16-byte aligned strides)
+    if (v_mn && (v.type != GGML_TYPE_F16 || v.nb[0] != 2 || ((uintptr_t)v.data & 15) || (v.nb[1] % 16) || (Hkv > 1 && v.nb[2] % 16) || (NB > 1 && v.nb[3] % 16))) return -1;
+    if ((!v_mn && ((uintptr_t)vt & 15)) || ((uintptr_t)q.data & 3)) return -1;
     if (Lq == 0 || Lk == 0) return -1;
     const int natom = (int)((d + 63) / 64);
     // d <= 64: 64-key tiles keep a CTA at 65 KB of shared memory and 256 TMEM columns, so two CTAs share an SM and one's
@@ -438,8 +459,12 @@ int b200_launch_flash_attn_fused(cudaStream_t s, const b200_td& q, const b200_td
     if (!encode_map(&tk, k.data, (uint64_t)d, (uint64_t)Lk, (uint64_t)Hkv, (uint64_t)NB, (uint64_t)k.nb[1], (uint64_t)k.nb[2], (uint64_t)k.nb[3], 64,
                     (uint32_t)block_n))
         return -1;
-    if (!encode_map(&tv, vt, (uint64_t)Lk, (uint64_t)dv, (uint64_t)Hkv, (uint64_t)NB, (uint64_t)(Lk_pad * 2), (uint64_t)(Lk_pad * dv * 2),
-                    (uint64_t)(Lk_pad * dv * Hkv * 2), 64, (uint32_t)dv16))
+    if (v_mn) {
+        if (!encode_map(&tv, v.data, (uint64_t)dv, (uint64_t)Lk, (uint64_t)Hkv, (uint64_t)NB, (uint64_t)v.nb[1], (uint64_t)v.nb[2], (uint64_t)v.nb[3], 64,
+                        (uint32_t)block_n))
+            return -1;
+    } else if (!encode_map(&tv, vt, (uint64_t)Lk, (uint64_t)dv, (uint64_t)Hkv, (uint64_t)NB, (uint64_t)(Lk_pad * 2), (uint64_t)(Lk_pad * dv * 2),
+                           (uint64_t)(Lk_pad * dv * Hkv * 2), 64, (uint32_t)dv16))
         return -1;
 
     FaParams p;
@@ -459,6 +484,7 @@ int b200_launch_flash_attn_fused(cudaStream_t s, const b200_td& q, const b200_td
         p.m_ne2 = p.m_ne3 = 1;
     }
     p.d = (int)d; p.dv16 = dv16; p.Lq = (int)Lq; p.Lk = (int)Lk; p.H = (int)H; p.rk = (int)(H / Hkv);
+    p.v_mn = v_mn ? 1 : 0;
     p.q_vec = (((uintptr_t)q.data & 15) == 0 && (q.nb[1] & 15) == 0 && (q.nb[2] & 15) == 0 && (q.nb[3] & 15) == 0 && (d & 3) == 0) ? 1 : 0;
     p.pos_scale = scale > 0.f ? 1 : 0;
     p.log2e = 1.4426950408889634f;

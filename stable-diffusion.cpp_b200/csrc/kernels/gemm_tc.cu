@@ -420,12 +420,16 @@ Plan choose_plan(const b200_device_info& dev, const b200_gemm_args& g, int num_k
             const int64_t ctas = tiles * splits;
             const double per_sm = (double)((ctas + sms - 1) / sms);
             const double kb = (double)((num_k_blocks + splits - 1) / splits);
-            // Measured model (tools/gemm_bench, B200; profiles/r02_gemm_model.md): a main loop is bound by the SM's ingest port -- ~43 B/clk
-            // from L2 through TMA per SM, alone or with all 148 busy -- not by the MMA: (128 + bn) x 128 B per k-block
-            const double kb_cycles = std::max(2.0 * bn, (128.0 + bn) * 128.0 / 43.0);
-            // fixed: setup + first data + accumulator hand-off + teardown ~ 5500 clk; epilogue ~ 35 clk per column (four warps, direct) or
-            // smem staging + cluster barriers + DSMEM reduce (~17 B/clk: bn x 512 B per CTA)
-            double cta_cycles = kb * kb_cycles + 5500.0 + (splits > 1 ? 8.0 * bn + 1500.0 + 31.0 * bn : 35.0 * bn);
+            // Measured model (tools/gemm_bench, B200): a 1-CTA main loop is bound by the SM's ingest port (~43-51 B/clk from L2 through TMA,
+            // profiles/r02_gemm_model.md), not by the MMA: (128 + bn) x 128 B per k-block; the shared L2 caps the sum over active SMs.
+            // (Constants as tuned in round 1 against this kernel's own sweep; the round-2 recalibration to a flat 43 B/clk picked worse
+            // split-K plans for the 16x16 / 8x8 levels and was backed out.)
+            const double active = (double)(ctas < sms ? ctas : sms);
+            const double ingest = std::min(64.0 * 0.8, 4700.0 / active);
+            const double kb_cycles = std::max(2.0 * bn, (128.0 + bn) * 128.0 / ingest);
+            // fixed: setup + first data + accumulator hand-off + teardown ~ 3500 clk; epilogue ~ 35 clk per column (direct) or
+            // smem staging + cluster barrier + DSMEM reduce of bn / splits columns
+            double cta_cycles = kb * kb_cycles + 3500.0 + (splits > 1 ? 8.0 * bn + 2500.0 + 80.0 * bn / splits : 35.0 * bn);
             double t = per_sm * cta_cycles;
             if (t < best) { best = t; bestp = Plan{bn, splits}; }
         }

@@ -26,6 +26,7 @@
 #include "sm100_ptx.cuh"
 
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <algorithm>
 #include <cstring>
 
@@ -59,6 +60,8 @@ struct G2Params {
     int stage_off;          // byte offset of the two 16 KB staging tiles behind the operand ring
     int nprod;              // TMA producer threads per CTA: 2 (A and B issued by different warps, default) or 1 (A/B of GGML_B200_GEMM2_NPROD)
     int conv, conv_W, conv_KW, conv_cblocks, conv_pad, conv_dil;
+    void* D16;                // optional 16-bit copy of the result (operand of the next contraction), same element layout as D
+    int d16_bf16, skip_f32;
     float* D2;                // optional mirror of D in the PEER GPU's memory (NVLink mapping, kernels/peer.cu); slot chosen by *d2_seq
     const unsigned* d2_seq;
     int64_t d2_slot;
@@ -325,8 +328,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                                 const float4 rr = *(const float4*)(Rp + (int64_t)(n0 + n) * p.ldr + mrow);
                                 v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
                             }
-                            *(float4*)(Dp + off) = v;
+                            if (!p.skip_f32) *(float4*)(Dp + off) = v;
                             if (p.D2) *(float4*)(Dp + off + d2off) = v;
+                            if (p.D16) {
+                                uint2 h;
+                                if (p.d16_bf16) {
+                                    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+                                    h.x = *(const uint32_t*)&a; h.y = *(const uint32_t*)&b;
+                                } else {
+                                    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+                                    h.x = *(const uint32_t*)&a; h.y = *(const uint32_t*)&b;
+                                }
+                                *(uint2*)((uint16_t*)p.D16 + (int64_t)batch * p.d_batch_stride + off) = h;
+                            }
                         }
                     }
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
@@ -525,11 +539,14 @@ int vec_epilogue_ok(const G2Params& kp, int splits) {
 // f32 output as a 3-D tensor (m, n, batch) with a dense box {128, 32, 1}: what one bulk store of the staged epilogue writes
 bool encode_output(CUtensorMap* out, G2Params& kp, int64_t batch) {
     static int en = -1;
-    if (en < 0) { const char* e = getenv("GGML_B200_GEMM2_TMA_STORE"); en = (e && *e) ? atoi(e) : 1; }
+    if (en < 0) { const char* e = getenv("GGML_B200_GEMM2_TMA_STORE"); en = (e && *e) ? atoi(e) : 0; }     // measured 1-5 us SLOWER than the staged st.global path (profiles/r02_gemm_model.md): off
     memset(out, 0, sizeof(*out));
     kp.tma_store = 0;
     if (!en || !kp.vec_epi || kp.residual || kp.D2) return true;
     if ((kp.ldd * 4) % 16 || (kp.d_batch_stride * 4) % 16 || ((uintptr_t)kp.D & 15)) return true;
+    // batch must be the outermost dimension of the output (the P.V product of the unfused attention interleaves heads INSIDE a row:
+    // d_batch_stride < ldd -- such maps are left to the st.global path)
+    if (batch > 1 && kp.d_batch_stride < kp.ldd * kp.N) return true;
     auto enc = b200_get_tensormap_encoder();
     if (!enc) return true;
     cuuint64_t dims[3] = {(cuuint64_t)kp.M, (cuuint64_t)kp.N, (cuuint64_t)batch};
@@ -635,6 +652,10 @@ int b200_launch_gemm_tc2(cudaStream_t s, const b200_device_info& dev, const b200
     kp.residual = g.residual; kp.ldr = g.ldr; kp.r_batch_stride = g.d_batch_stride;
     kp.act = g.act;
     kp.vec_epi = vec_epilogue_ok(kp, splits);
+    if (g.D16 && kp.vec_epi && !((uintptr_t)g.D16 & 7) && (g.d16_type == GGML_TYPE_F16 || g.d16_type == GGML_TYPE_BF16)) {
+        kp.D16 = g.D16; kp.d16_bf16 = g.d16_type == GGML_TYPE_BF16; kp.skip_f32 = g.skip_f32;
+        if (g.d16_done) *g.d16_done = 1;
+    }
     CUtensorMap td;
     encode_output(&td, kp, g.batch);
     cudaError_t e = g.type == GGML_TYPE_F16 ? launch2<0>(s, ctas, (unsigned)splits, smem, ta, tb, td, kp) : launch2<1>(s, ctas, (unsigned)splits, smem, ta, tb, td, kp);
