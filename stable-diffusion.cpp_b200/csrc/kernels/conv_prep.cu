@@ -45,28 +45,32 @@ __global__ void __launch_bounds__(1024) k_gn_stats(const float* __restrict__ x, 
     const int64_t len = (int64_t)(c1 - c0) * inner;
     const float* xp = x + ((int64_t)n * C + c0) * inner;
     const float* av = addv ? addv + (int64_t)n * C + c0 : nullptr;      // per-channel value added on the fly (x + emb broadcast)
+    // (the folded per-channel add keeps the summation ORDER of the plain path -- pairs inside a float4, then the running sum -- so that
+    //  folding the ResBlock's broadcast ADD changes no bit: tests/test_gpu_models.py::test_producer_side_fusions_are_bit_identical)
+    const bool vec = ((uintptr_t)xp % 16 == 0) && (len % 4 == 0) && (!av || (inner % 4 == 0));
     float s = 0.f;
-    if (av) {
-        for (int64_t i = threadIdx.x; i < len; i += blockDim.x) s += xp[i] + av[i / inner];
-    } else if (((uintptr_t)xp % 16 == 0) && (len % 4 == 0)) {
-        const float4* x4 = (const float4*)xp;
-        for (int64_t i = threadIdx.x; i < len / 4; i += blockDim.x) { float4 v = x4[i]; s += (v.x + v.y) + (v.z + v.w); }
-    } else {
-        for (int64_t i = threadIdx.x; i < len; i += blockDim.x) s += xp[i];
-    }
-    const float mean = block_sum(s, red) / (float)len;
-    float s2 = 0.f;
-    if (av) {
-        for (int64_t i = threadIdx.x; i < len; i += blockDim.x) { float v = (xp[i] + av[i / inner]) - mean; s2 += v * v; }
-    } else if (((uintptr_t)xp % 16 == 0) && (len % 4 == 0)) {
+    if (vec) {
         const float4* x4 = (const float4*)xp;
         for (int64_t i = threadIdx.x; i < len / 4; i += blockDim.x) {
             float4 v = x4[i];
+            if (av) { const float e = av[(4 * i) / inner]; v.x += e; v.y += e; v.z += e; v.w += e; }
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < len; i += blockDim.x) s += av ? xp[i] + av[i / inner] : xp[i];
+    }
+    const float mean = block_sum(s, red) / (float)len;
+    float s2 = 0.f;
+    if (vec) {
+        const float4* x4 = (const float4*)xp;
+        for (int64_t i = threadIdx.x; i < len / 4; i += blockDim.x) {
+            float4 v = x4[i];
+            if (av) { const float e = av[(4 * i) / inner]; v.x += e; v.y += e; v.z += e; v.w += e; }
             float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
             s2 += (a * a + b * b) + (c * c + d * d);
         }
     } else {
-        for (int64_t i = threadIdx.x; i < len; i += blockDim.x) { float v = xp[i] - mean; s2 += v * v; }
+        for (int64_t i = threadIdx.x; i < len; i += blockDim.x) { float v = (av ? xp[i] + av[i / inner] : xp[i]) - mean; s2 += v * v; }
     }
     const float var = block_sum(s2, red) / (float)len;
     if (threadIdx.x == 0) stats[(int64_t)n * G + g] = make_float2(mean, 1.0f / sqrtf(var + eps));
