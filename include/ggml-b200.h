@@ -81,7 +81,10 @@ typedef struct ggml_b200_stats {
                                    [8] graphs that ended with a peer exchange (kernels/peer.cu),
                                    [9..12] host microseconds at the plugin boundary, process-wide: inside set_tensor, inside get_tensor (includes
                                    waiting for the device), inside graph_compute (host side), and OUTSIDE the backend between two boundary
-                                   calls (the host's own work: graph rebuild, gallocr, sampler) */
+                                   calls (the host's own work: graph rebuild, gallocr, sampler),
+                                   [13] K / V projections whose f16 rows the attention kernel read in place (permute + CONT + cast never run),
+                                   [14] attention launches that wrote only the f16 rows of the output projection (no f32 result, no CONT),
+                                   [15] gated residuals (x + gate * Linear(y)) applied by a GEMM epilogue */
 } ggml_b200_stats;
 
 /* copy the backend instance's counters; returns 0 on success.  Counters of kernels that run inside a replayed CUDA graph are

@@ -295,6 +295,7 @@ struct mm_fusion {
     const float* bias = nullptr;  // f32 vector
     int bias_mode = 0;            // 1: per output row m (Linear bias), 2: per n (conv bias: n == output channel)
     const float* residual = nullptr;   // same [M, N] layout as out, added last
+    const float* gate = nullptr;       // f32 [M]: value = residual + gate[m] * value (set together with residual)
     const ggml_tensor* src1_pre = nullptr;   // activation to read instead of src[1] (same shape): the input of a unary op folded in
     int pre_act = 0;                          // 1: SiLU applied to src1_pre on load (only the few-row GEMV path can do this)
     int act = 0;                              // activation after the bias, before the residual: 1 SiLU, 2 GELU (tanh form) -- the epilogue's act_fn
@@ -319,7 +320,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
     }
 
     // a handful of activation rows against in-place F16/BF16 weights (embedding MLPs): weight-streaming GEMV, no operand packing
-    if (!(fz && fz->act)) {
+    if (!(fz && (fz->act || fz->gate))) {
         const ggml_tensor* x = fz && fz->src1_pre ? fz->src1_pre : src1;
         if (ctx->opt_gemv && ne02 * ne03 * ne12 * ne13 == 1 && N <= 4 && (src0->type == GGML_TYPE_F16 || src0->type == GGML_TYPE_BF16) &&
             rows_unit_stride(src0) && x->type == GGML_TYPE_F32 && x->nb[0] == 4 && x->nb[1] % 4 == 0 && dst->nb[0] == 4 &&
@@ -335,7 +336,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
         if (fz && fz->src1_pre) return -2;     // only the GEMV can fold the unary op
     }
 
-    if (ct == GGML_TYPE_F32 && ctx->opt_precise_f32 && ctx->opt_tc_gemm && !(fz && fz->act)) {
+    if (ct == GGML_TYPE_F32 && ctx->opt_precise_f32 && ctx->opt_tc_gemm && !(fz && (fz->act || fz->gate))) {
         // F32 x F32 (attention GEMMs of the reference's default graph, F32 Linear weights): the CPU oracle computes true f32 dot products
         // (ggml-cpu.c:1406 with vec_dot_f32); a single TF32 pass would keep 10 mantissa bits of each operand.  3xTF32: x = hi + lo with hi
         // exactly representable in TF32; D = A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, three tensor-core passes chained through the residual
@@ -447,7 +448,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
         g.d_batch_stride = dst->nb[2] / 4;
         if (fz && fz->bias) { g.bias = fz->bias; g.bias_mode = fz->bias_mode; }
         if (fz && fz->residual) { g.residual = fz->residual; g.ldr = g.ldd; }
-        if (fz) g.act = fz->act;
+        if (fz) { g.act = fz->act; g.gate = fz->gate; }
         if (fz && fz->d16 && nb13 == 1) { g.D16 = fz->d16; g.d16_type = fz->d16_type; g.skip_f32 = fz->skip_f32 ? 1 : 0; g.d16_done = fz->d16_done; }
         // model weights read in place are constants of the graph: their first ring-full may be fetched before the PDL wait.  Not for
         // the first kernel of a graph_compute (its stream predecessor belongs to an earlier call, e.g. a weight update).
@@ -456,7 +457,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
             g.early = 1;
         int n = launch_tc(ctx, g);
         if (n < 0) {
-            if (fz && fz->act) return -1;      // the reference kernel has no activation epilogue: fail loudly rather than skip it
+            if (fz && (fz->act || fz->gate)) return -1;      // the reference kernel has no activation / gate epilogue: fail loudly rather than skip it
             // CUDA-core reference kernel (debug option, or shapes the TMA cannot describe)
             n = 0;
             for (int64_t i2 = 0; i2 < nb12; ++i2) {
@@ -504,13 +505,24 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
 // and an f16 copy of the result for the output projection that follows
 struct fa_fusion {
     const b200_td* q_td = nullptr;
+    int q_split_b = 0;                    // > 0: q_td is [d, Lq, H, q_split_b] (batch apart) instead of ggml's [d, Lq, H * B, 1]
     ggml_tensor* q_cont = nullptr;        // the skipped CONT: executed late if the fused kernel turns the shape down
     const ggml_tensor* shadow_act = nullptr;   // activation operand (f32 view of dst) of the next MUL_MAT
+    // K / V read from the projection GEMM's f16 rows ([d, Lk, H, B] descriptors, see try_fuse_mul_mat); cast_dst: where the graph
+    // expected the contiguous f16 tensor -- filled late if the fused kernel turns the shape down
+    const b200_td* k_td = nullptr;
+    const b200_td* v_td = nullptr;
+    // the result in the layout of the CONT that follows ([d, H, Lq, B] contiguous) as f16 ONLY, for the output projection that is its
+    // single reader (out_act: that projection's activation operand); set by try_fuse_flash_attn, honoured by the fused kernel or not at all
+    const ggml_tensor* out_cont = nullptr;
+    const ggml_tensor* out_act = nullptr;
+    int out_h = 0, out_b = 0;
+    bool out_used = false;
 };
 
 static int run_node(b200_context* ctx, ggml_tensor* t);
 
-static int op_flash_attn(b200_context* ctx, ggml_tensor* dst, const fa_fusion* fz = nullptr) {
+static int op_flash_attn(b200_context* ctx, ggml_tensor* dst, fa_fusion* fz = nullptr) {
     const ggml_tensor* q = dst->src[0];
     const ggml_tensor* k = dst->src[1];
     const ggml_tensor* v = dst->src[2];
@@ -526,6 +538,78 @@ static int op_flash_attn(b200_context* ctx, ggml_tensor* dst, const fa_fusion* f
     const int ct = k->type == GGML_TYPE_BF16 ? GGML_TYPE_BF16 : GGML_TYPE_F16;
     const int64_t es = 2;
     const int64_t Lk_pad = (Lk + 7) / 8 * 8;
+
+    // Operands that never took ggml's [d, L, H * B] form (projection rows read in place, see fa_fusion): every tensor is described with
+    // the batch as its own dimension, [d, L, H, B]; contiguous ones split trivially.  One fused launch; if the kernel turns it down the
+    // skipped copies are produced after all and the generic paths below run.
+    if (fz && (fz->k_td || fz->v_td || fz->q_split_b || fz->out_cont)) {
+        int64_t B = 0;
+        bool ok = ctx->opt_tc_gemm && ctx->opt_fused_attn && max_bias == 0.0f && !mask && NB == 1 && k->ne[3] == 1 && v->ne[3] == 1;
+        auto want_b = [&](int64_t b) { if (b <= 0) return; if (B == 0) B = b; else if (B != b) ok = false; };
+        if (fz->k_td) want_b(fz->k_td->ne[3]);
+        if (fz->v_td) want_b(fz->v_td->ne[3]);
+        if (fz->q_split_b) want_b(fz->q_split_b);
+        if (fz->out_cont) want_b(fz->out_b);
+        if (B == 0) B = 1;
+        auto split = [&](b200_td td) {      // [x, L, H * B, 1] -> [x, L, H, B]
+            if (td.ne[2] % B) { ok = false; return td; }
+            td.ne[2] /= B; td.ne[3] = B; td.nb[3] = td.nb[2] * (size_t)td.ne[2];
+            return td;
+        };
+        if (ok && (H % B || Hkv % B)) ok = false;
+        if (ok) {
+            const b200_td qd = fz->q_td ? (fz->q_split_b ? *fz->q_td : split(*fz->q_td)) : split(b200_make_td(q));
+            const b200_td kd = fz->k_td ? *fz->k_td : split(b200_make_td(k));
+            const b200_td vd = fz->v_td ? *fz->v_td : split(b200_make_td(v));
+            b200_td dd = b200_make_td(dst);            // [dv, H * B, Lq, 1]: head-and-batch index hb = b * H + h
+            const int64_t Hs = H / B;
+            void* shadow = nullptr;
+            const ggml_tensor* shadow_for = nullptr;
+            int skip_f32 = 0;
+            if (fz->out_cont && fz->out_h == Hs) {
+                // write the CONT's layout [dv, H, Lq, B] directly, f16 only
+                dd.ne[1] = Hs; dd.ne[3] = B;
+                dd.nb[1] = (size_t)dv * 4; dd.nb[2] = (size_t)dv * 4 * Hs; dd.nb[3] = (size_t)dv * 4 * Hs * Lq;
+                shadow = ws_alloc(ctx, (size_t)ggml_nelements(dst) * 2);
+                shadow_for = fz->out_act;
+                skip_f32 = 1;
+                if (!shadow) ok = false;
+            } else {
+                dd.ne[1] = Hs; dd.ne[3] = B; dd.nb[3] = dd.nb[1] * (size_t)Hs;
+                if (fz->shadow_act) { shadow = ws_alloc(ctx, (size_t)ggml_nelements(dst) * 2); shadow_for = fz->shadow_act; }
+            }
+            if (ok && kd.ne[2] == vd.ne[2] && kd.ne[3] == B && vd.ne[3] == B && qd.ne[3] == B) {
+                int n = b200_launch_flash_attn_fused(ctx->stream, qd, kd, nullptr, 0, vd, nullptr, dd, scale, shadow, skip_f32);
+                if (n > 0) {
+                    ctx->stats.reserved[2] += (uint64_t)n;
+                    if (shadow && shadow_for)
+                        ctx->pack_cache[std::make_pair(shadow_for, (int)GGML_TYPE_F16)] =
+                            operand{shadow, GGML_TYPE_F16, shadow_for->ne[0], shadow_for->ne[0] * shadow_for->ne[1], shadow_for->ne[0] * shadow_for->ne[1] * shadow_for->ne[2]};
+                    if (fz->q_td) ctx->stats.reserved[5] += 1;
+                    if (skip_f32) { fz->out_used = true; ctx->stats.ext[14] += 1; }
+                    return launches + n;
+                }
+            }
+        }
+        // turned down: materialise what the graph expected (the allocator reserved those tensors until this node)
+        if (fz->k_td) {
+            const int n = b200_launch_pack_rows(ctx->stream, *fz->k_td, k->data, GGML_TYPE_F16, k->ne[0]);
+            if (n < 0) return -1;
+            launches += n;
+        }
+        if (fz->v_td) {
+            const int n = b200_launch_pack_rows(ctx->stream, *fz->v_td, v->data, GGML_TYPE_F16, v->ne[0]);
+            if (n < 0) return -1;
+            launches += n;
+        }
+        if (fz->q_split_b) {
+            if (!fz->q_cont) return -1;
+            const int n = run_node(ctx, fz->q_cont);
+            if (n < 0) return -1;
+            launches += n;
+            fz->q_td = nullptr; fz->q_cont = nullptr; fz->q_split_b = 0;
+        }
+    }
 
     // fused single-kernel path first, reading V in place (MN-major operand of the P.V product): no V^T pass, no workspace
     static int fa_vmn = -1;
@@ -956,8 +1040,12 @@ struct fusion_state {
     std::unordered_map<const ggml_tensor*, int> uses;   // consumer count inside this graph
     std::vector<char> done;                             // node already covered by an earlier fused launch
     // FLASH_ATTN_EXT node index -> (skipped CONT node, strided descriptor the kernel reads Q through instead)
-    struct q_bypass { ggml_tensor* cont; b200_td q; };
+    struct q_bypass { ggml_tensor* cont; b200_td q; int split_b; };     // split_b > 0: q is described as [d, Lq, H, split_b] (batch apart)
     std::unordered_map<int, q_bypass> fa_q;
+    // K / V operand (the CPY node's tensor) of a FLASH_ATTN_EXT -> the f16 projection output the GEMM epilogue wrote, described as
+    // [d, Lk, H, B] over its [B][Lk][H * d] rows: the permute + CONT + cast chain in between was never executed
+    struct kv_direct { b200_td td; const ggml_tensor* cast_dst; };
+    std::unordered_map<const ggml_tensor*, kv_direct> fa_kv;
 };
 
 static void count_uses(const ggml_cgraph* g, fusion_state& fs) {
@@ -1097,9 +1185,110 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
             }
         }
     }
+    // K / V projection of an attention layer (ggml_ext_attention_ext, ggml_extend.hpp:1340-1400): Linear -> reshape [d, H, L, B] ->
+    // permute(0,2,1,3) -> CONT -> reshape [d, L, H*B] -> CPY to F16 -> FLASH_ATTN_EXT.  The fused attention kernel reads K / V through any
+    // 16-byte aligned strides, so the epilogue writes the f16 rows [B][L][H * d] once and the attention reads head h of token l at
+    // (l * H + h) * d: no f32 projection, no permute copy, no cast pass.  Same values: the CONT copies and the CPY rounds f32 -> f16 (RN),
+    // exactly what the epilogue's conversion does.
+    int kv_done = 0, kv_cont = -1, kv_cpy = -1;
+    const ggml_tensor* kv_cp = nullptr;
+    fusion_state::kv_direct kvd;
+    static int kv_enabled = -1;
+    if (kv_enabled < 0) { const char* e = getenv("GGML_B200_KV_DIRECT"); kv_enabled = (e && *e) ? atoi(e) : 1; }
+    if (kv_enabled && !fz.act && !fz.d16 && !src1_pre && ctx->opt_chain_fusion && ctx->opt_tc_gemm && ctx->opt_fused_attn &&
+        mm->src[0]->type == GGML_TYPE_F16 && mm->ne[3] == 1 && mm->ne[1] > 4) {
+        const ggml_tensor* curv = chain.empty() ? (const ggml_tensor*)mm : g->nodes[chain.back()];
+        const int jc = chain.empty() ? next_node(g, fs, i) : next_node(g, fs, chain.back());
+        const int jp = jc >= 0 ? next_node(g, fs, jc) : -1;
+        if (jp >= 0 && g->nodes[jc]->op == GGML_OP_CONT && g->nodes[jp]->op == GGML_OP_CPY && !(curv->flags & GGML_TENSOR_FLAG_OUTPUT)) {
+            const ggml_tensor* c = g->nodes[jc];
+            const ggml_tensor* cp = g->nodes[jp];
+            const ggml_tensor* pv = c->src[0];                      // the permuted view of the projection
+            const int64_t Mf = mm->ne[0], L = mm->ne[1], Bn = mm->ne[2];
+            bool ok = c->type == GGML_TYPE_F32 && ggml_is_contiguous(c) && single_use(fs, c) && (c->flags & GGML_TENSOR_FLAG_COMPUTE) &&
+                      (cp->flags & GGML_TENSOR_FLAG_COMPUTE) && pv->type == GGML_TYPE_F32 && pv->data == curv->data && ggml_are_same_shape(pv, c);
+            // views between the projection and the CONT: one consumer each (nobody else reads the f32 projection)
+            if (ok) {
+                const ggml_tensor* v = pv;
+                int depth = 0;
+                while (v != curv && depth++ < 6) {
+                    if (!is_view_op(v) || !v->src[0] || !single_use(fs, v) || v->data != curv->data) { ok = false; break; }
+                    v = v->src[0];
+                }
+                ok = ok && v == curv && single_use(fs, curv);
+            }
+            // geometry: pv = [d, L, H, B] over rows of Mf = H * d features
+            const int64_t d = ok ? pv->ne[0] : 0, H = ok ? pv->ne[2] : 0;
+            ok = ok && d > 0 && d * H == Mf && pv->ne[1] == L && pv->ne[3] == Bn && pv->nb[0] == 4 && pv->nb[2] == (size_t)d * 4 &&
+                 pv->nb[1] == (size_t)Mf * 4 && (Bn == 1 || pv->nb[3] == (size_t)Mf * L * 4) && d % 8 == 0 && d <= 192;
+            const ggml_tensor* cd = ok ? cp->src[1] : nullptr;     // the cast's destination
+            ok = ok && cd && cd->type == GGML_TYPE_F16 && ggml_is_contiguous(cd) && cd->ne[0] == d && cd->ne[1] == L && ggml_nelements(cd) == ggml_nelements(c) &&
+                 order_preserving_view_of(fs, cp->src[0], c) && (cp->src[0] == c || single_use(fs, cp->src[0])) && single_use(fs, cp);
+            // its one reader: the K or V operand of an attention node the fused kernel will take (no mask, no ALiBi, d == dv)
+            const ggml_tensor* fa = nullptr;
+            if (ok) {
+                for (int j = jp + 1; j < g->n_nodes && j < jp + 32; ++j) {
+                    const ggml_tensor* t = g->nodes[j];
+                    if (t->op == GGML_OP_FLASH_ATTN_EXT && (t->src[1] == cp || t->src[2] == cp)) { fa = t; break; }
+                }
+                ok = fa != nullptr && fa->src[1] != fa->src[2] && !fa->src[3];
+            }
+            if (ok) {
+                float max_bias;
+                memcpy(&max_bias, (const float*)fa->op_params + 1, sizeof(float));
+                const ggml_tensor* fq = fa->src[0];
+                ok = max_bias == 0.0f && fq->type == GGML_TYPE_F32 && fq->ne[0] == d && fa->src[1]->ne[0] == d && fa->src[2]->ne[0] == d &&
+                     fa->src[1]->type == GGML_TYPE_F16 && fa->src[2]->type == GGML_TYPE_F16 && fq->ne[3] == 1 && fq->ne[2] % Bn == 0 &&
+                     (fq->ne[2] / Bn) % H == 0;
+            }
+            if (ok) {
+                void* sh = ws_alloc(ctx, (size_t)ggml_nelements(c) * 2);
+                if (sh) {
+                    fz.d16 = sh; fz.d16_type = GGML_TYPE_F16; fz.skip_f32 = true; fz.d16_done = &kv_done;
+                    kv_cont = jc; kv_cpy = jp; kv_cp = cp;
+                    b200_td td;
+                    td.data = sh; td.type = GGML_TYPE_F16;
+                    td.ne[0] = d; td.ne[1] = L; td.ne[2] = H; td.ne[3] = Bn;
+                    td.nb[0] = 2; td.nb[1] = (size_t)Mf * 2; td.nb[2] = (size_t)d * 2; td.nb[3] = (size_t)Mf * L * 2;
+                    kvd.td = td; kvd.cast_dst = cd;
+                }
+            }
+        }
+    }
+    // gated residual of the DiT blocks: x + gate * Linear(y) (flux.hpp:330-400 DoubleStreamBlock, :470-500 SingleStreamBlock; mmdit, wan):
+    // ... -> MUL(value, gate [M,1,1,1]) -> ADD(x, .).  Both steps in the epilogue, each rounded like the node it replaces.
+    static int gate_enabled = -1;
+    if (gate_enabled < 0) { const char* e = getenv("GGML_B200_GATE_FUSION"); gate_enabled = (e && *e) ? atoi(e) : 1; }
+    if (gate_enabled && !src1_pre && !fz.d16 && ctx->opt_chain_fusion && ctx->opt_tc_gemm && mm->src[0]->type != GGML_TYPE_F32 && mm->ne[1] > 4 && mm->ne[3] == 1) {
+        const int jg = chain.empty() ? next_node(g, fs, i) : next_node(g, fs, chain.back());
+        const ggml_tensor* curv = chain.empty() ? (const ggml_tensor*)mm : g->nodes[chain.back()];
+        const int ja = jg >= 0 ? next_node(g, fs, jg) : -1;
+        if (ja >= 0 && g->nodes[jg]->op == GGML_OP_MUL && g->nodes[ja]->op == GGML_OP_ADD && !(curv->flags & GGML_TENSOR_FLAG_OUTPUT)) {
+            const ggml_tensor* mul = g->nodes[jg];
+            const ggml_tensor* add = g->nodes[ja];
+            const ggml_tensor* val = nullptr;
+            const ggml_tensor* gv = nullptr;
+            if (order_preserving_view_of(fs, mul->src[0], curv)) { val = mul->src[0]; gv = mul->src[1]; }
+            else if (order_preserving_view_of(fs, mul->src[1], curv)) { val = mul->src[1]; gv = mul->src[0]; }
+            const ggml_tensor* r = add->src[0] == mul ? add->src[1] : (add->src[1] == mul ? add->src[0] : nullptr);
+            if (val && gv && r && r != mul && (mul->flags & GGML_TENSOR_FLAG_COMPUTE) && (add->flags & GGML_TENSOR_FLAG_COMPUTE) && mul->type == GGML_TYPE_F32 &&
+                add->type == GGML_TYPE_F32 && ggml_is_contiguous(mul) && ggml_is_contiguous(add) && ggml_are_same_shape(mul, curv) && ggml_are_same_shape(add, mul) &&
+                gv->type == GGML_TYPE_F32 && gv->ne[0] == M && gv->ne[1] * gv->ne[2] * gv->ne[3] == 1 && gv->nb[0] == 4 && !((uintptr_t)gv->data & 3) &&
+                (single_use(fs, val) || mul->data == curv->data) && single_use(fs, mul) && !(mul->flags & GGML_TENSOR_FLAG_OUTPUT) &&
+                r->type == GGML_TYPE_F32 && ggml_is_contiguous(r) && ggml_are_same_shape(r, add) &&
+                // the gate vector is read by every CTA for the whole launch: it must not be where the result goes
+                !overlaps_range(add->data, ggml_nbytes(add), gv->data, (size_t)M * 4)) {
+                fz.gate = (const float*)gv->data;
+                fz.residual = (const float*)r->data;
+                fz.out = (float*)add->data;
+                chain.push_back(jg);
+                chain.push_back(ja);
+            }
+        }
+    }
     // residual: ... -> ADD(value, r) with r a same-shape tensor that already exists (the ADD is the very next work node, so r was
     // produced before this MUL_MAT).  Read in the epilogue of the element it is added to, so in-place adds onto r are fine.
-    {
+    if (!fz.gate) {
         const int jr = chain.empty() ? next_node(g, fs, i) : next_node(g, fs, chain.back());
         const ggml_tensor* curv = chain.empty() ? (const ggml_tensor*)mm : g->nodes[chain.back()];
         if (jr >= 0) {
@@ -1119,16 +1308,23 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
             }
         }
     }
-    if (chain.empty() && !src1_pre) return -2;
+    if (chain.empty() && !src1_pre && !kv_cp) return -2;
     if (src1_pre && overlaps_range(fz.out, ggml_nbytes(mm), src1_pre->data, ggml_nbytes(src1_pre))) return -2;
     // the fused kernel writes `out` while other CTAs may still be reading the operands: `out` must not live in memory gallocr
     // recycled from an operand that is dead in graph order (e.g. the im2col matrix) -- run unfused then
     auto overlaps = [](const void* a, size_t na, const void* b, size_t nb) { return (const char*)a < (const char*)b + nb && (const char*)b < (const char*)a + na; };
     if (overlaps(fz.out, ggml_nbytes(mm), mm->src[0]->data, ggml_nbytes(mm->src[0])) || overlaps(fz.out, ggml_nbytes(mm), mm->src[1]->data, ggml_nbytes(mm->src[1])))
         return -2;
-    if (fz.residual) { fz.d16 = nullptr; fz.skip_f32 = false; d16_act = nullptr; }     // (a residual after the activation: keep the plain path)
+    if (fz.residual) { fz.d16 = nullptr; fz.skip_f32 = false; d16_act = nullptr; kv_cp = nullptr; }     // (a residual after the activation: keep the plain path)
     int n = op_mul_mat(ctx, mm, &fz);
     if (n < 0) return n;
+    if (fz.gate) ctx->stats.ext[15] += 1;      // gated residuals applied by a GEMM epilogue
+    if (kv_cp && kv_done) {
+        fs.fa_kv[kv_cp] = kvd;
+        chain.push_back(kv_cont);
+        chain.push_back(kv_cpy);
+        ctx->stats.ext[13] += 1;       // K / V projections handed to the attention kernel in place
+    }
     if (d16_act && d16_done)
         ctx->pack_cache[std::make_pair(d16_act, fz.d16_type)] = operand{fz.d16, fz.d16_type, d16_act->ne[0], d16_act->ne[0] * d16_act->ne[1], d16_act->ne[0] * d16_act->ne[1] * d16_act->ne[2]};
     for (int c : chain) fs.done[c] = 1;
@@ -1757,12 +1953,19 @@ static int try_skip_q_cont(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, 
     memcpy(&max_bias, (const float*)fa->op_params + 1, sizeof(float));
     if (max_bias != 0.0f) return -2;
     // q is [d, Lq, H(, N)] over c's flat order: express it over src's strides
+    int split_b = 0;
     b200_td qt = b200_make_td(q);
     if (q->ne[0] != c->ne[0] || q->ne[1] != c->ne[1]) return -2;
     if (q->ne[2] == c->ne[2] && q->ne[3] == c->ne[3]) {
         qt.nb[1] = src->nb[1]; qt.nb[2] = src->nb[2]; qt.nb[3] = src->nb[3];
     } else if (q->ne[3] == 1 && q->ne[2] == c->ne[2] * c->ne[3] && (c->ne[3] == 1 || src->nb[3] == src->nb[2] * (size_t)c->ne[2])) {
         qt.nb[1] = src->nb[1]; qt.nb[2] = src->nb[2]; qt.nb[3] = src->nb[2] * (size_t)q->ne[2];
+    } else if (q->ne[3] == 1 && q->ne[2] == c->ne[2] * c->ne[3] && c->ne[3] > 1 && !fa->src[3]) {
+        // heads interleaved inside a token row AND a batch (the CFG-batched UNet: [d, H, L, B] projection rows): no single stride walks
+        // the merged head-and-batch index, so the view is handed over with the batch as its own dimension
+        qt.ne[2] = c->ne[2]; qt.ne[3] = c->ne[3];
+        qt.nb[1] = src->nb[1]; qt.nb[2] = src->nb[2]; qt.nb[3] = src->nb[3];
+        split_b = (int)c->ne[3];
     } else {
         return -2;
     }
@@ -1775,7 +1978,7 @@ static int try_skip_q_cont(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, 
         if (tensors_overlap(t->data, ggml_nbytes(t), lo, nb)) return -2;
         if (t->op == GGML_OP_CPY && t->src[1] && tensors_overlap(t->src[1]->data, ggml_nbytes(t->src[1]), lo, nb)) return -2;
     }
-    fs.fa_q[jf] = fusion_state::q_bypass{c, qt};
+    fs.fa_q[jf] = fusion_state::q_bypass{c, qt, split_b};
     return 0;
 }
 
@@ -1783,10 +1986,45 @@ static int try_fuse_flash_attn(b200_context* ctx, ggml_cgraph* g, fusion_state& 
     ggml_tensor* fa = g->nodes[i];
     fa_fusion fz;
     auto it = fs.fa_q.find(i);
-    if (it != fs.fa_q.end()) { fz.q_td = &it->second.q; fz.q_cont = it->second.cont; }
+    if (it != fs.fa_q.end()) { fz.q_td = &it->second.q; fz.q_cont = it->second.cont; fz.q_split_b = it->second.split_b; }
+    auto ik = fs.fa_kv.find(fa->src[1]);
+    if (ik != fs.fa_kv.end()) fz.k_td = &ik->second.td;
+    auto iv = fs.fa_kv.find(fa->src[2]);
+    if (iv != fs.fa_kv.end()) fz.v_td = &iv->second.td;
     if (!(fa->flags & GGML_TENSOR_FLAG_OUTPUT)) fz.shadow_act = next_mm_activation(ctx, g, fs, i, fa);
+    // FLASH_ATTN_EXT [d, H*B, Lq] -> VIEW [d, H, Lq, B] -> CONT -> reshape [H*d, Lq, B] -> Linear (to_out, ggml_extend.hpp:1400-1416): when that
+    // projection is the only reader and takes its activation as f16 rows anyway, the attention kernel writes exactly those rows and
+    // neither the f32 result nor the CONT's copy of it exists
+    int jcont = -1;
+    static int out_enabled = -1;
+    if (out_enabled < 0) { const char* e = getenv("GGML_B200_FA_OUT16"); out_enabled = (e && *e) ? atoi(e) : 1; }
+    if (out_enabled && !fz.shadow_act && !(fa->flags & GGML_TENSOR_FLAG_OUTPUT) && single_use(fs, fa) && ctx->opt_tc_gemm && ctx->opt_fused_attn) {
+        const int jc = next_node(g, fs, i);
+        if (jc >= 0 && g->nodes[jc]->op == GGML_OP_CONT) {
+            const ggml_tensor* c = g->nodes[jc];
+            const ggml_tensor* vw = c->src[0];
+            const int64_t dv = fa->ne[0], HB = fa->ne[1], Lq = fa->ne[2];
+            bool ok = (c->flags & GGML_TENSOR_FLAG_COMPUTE) && c->type == GGML_TYPE_F32 && ggml_is_contiguous(c) && !(c->flags & GGML_TENSOR_FLAG_OUTPUT) &&
+                      fa->ne[3] == 1 && vw != fa && is_view_op(vw) && vw->src[0] == fa && vw->data == fa->data && single_use(fs, vw) && ggml_are_same_shape(vw, c) &&
+                      vw->ne[0] == dv && vw->ne[2] == Lq && vw->ne[1] * vw->ne[3] == HB && vw->nb[0] == 4 && vw->nb[1] == fa->nb[1] && vw->nb[2] == fa->nb[2] &&
+                      (vw->ne[3] == 1 || vw->nb[3] == fa->nb[1] * (size_t)vw->ne[1]) && (dv * 2) % 16 == 0;
+            if (ok) {
+                const ggml_tensor* act = next_mm_activation(ctx, g, fs, jc, c);
+                const ggml_tensor* mm = act ? g->nodes[next_node(g, fs, jc)] : nullptr;
+                // the projection must be one that reads the packed operand: tensor-core path (more than 4 activation rows, or batched),
+                // and the CONT feeds nothing else
+                if (act && mm && single_use(fs, c) && (act == c || single_use(fs, act)) && order_preserving_view_of(fs, act, c) &&
+                    (act->ne[1] > 4 || act->ne[2] * act->ne[3] > 1) && mm->src[0]->type == GGML_TYPE_F16) {
+                    fz.out_cont = c; fz.out_act = act; fz.out_h = (int)vw->ne[1]; fz.out_b = (int)vw->ne[3];
+                    jcont = jc;
+                }
+            }
+        }
+    }
     *covered = 0;
-    return op_flash_attn(ctx, fa, &fz);
+    const int n = op_flash_attn(ctx, fa, &fz);
+    if (n >= 0 && fz.out_used && jcont >= 0) { fs.done[jcont] = 1; *covered = 1; }
+    return n;
 }
 
 // SILU(emb) -> MUL_MAT(W, .) [-> ADD bias]: the per-ResBlock embedding projection (block.hpp:150-156) as one GEMV that applies

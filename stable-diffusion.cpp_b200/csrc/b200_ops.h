@@ -77,6 +77,8 @@ struct b200_gemm_args {
     int         bias_mode;  // 0 none, 1 per-m (row of A: linear bias), 2 per-n (row of B: conv bias / channel)
     const float* residual;  // optional [N][M] like D (added after bias)
     int64_t     ldr;
+    const float* gate;      // optional per-m f32 vector: D = residual + gate[m] * act(acc + bias) -- the gated residual of the DiT blocks
+                            // (x + gate * Linear(y): flux.hpp DoubleStreamBlock / SingleStreamBlock); product and sum rounded separately
     int         act;        // 0 none, 1 SiLU, 2 GELU(tanh)
     int         early;      // bit 0: A, bit 1: B is a constant (weight) operand no kernel of this graph writes -> may be fetched before the PDL wait
     void*       trace;      // optional device buffer of 8 uint64: phase timestamps of CTA (0,0,0) (tools/gemm_bench)
@@ -153,6 +155,9 @@ int b200_launch_peer_signal_wait(cudaStream_t s, unsigned* my_seq, unsigned* pee
 // ---- attention.cu --------------------------------------------------------------------------------
 // ggml FLASH_ATTN_EXT: q f32 [d, Lq, H, N], k f16 [d, Lk, Hkv, N], v f16 [dv, Lk, Hkv, N], mask f16 [Lk, >=Lq, ...] or null,
 // dst f32 [dv, H, Lq, N]
-// vt = packed V^T f16 [Lk_pad, dv, Hkv, N]; returns -1 when the shape is outside the fused kernel's envelope
+// vt = packed V^T f16 [Lk_pad, dv, Hkv, N]; returns -1 when the shape is outside the fused kernel's envelope.  Only the STRIDES of q / k /
+// v / dst are read besides q's and k's extents, so a caller may describe projections that were never permuted into ggml's layout (heads
+// interleaved inside a token row, the batch as its own dimension).  dst16: f16 copy of the result with dst's element layout;
+// skip_f32: write only that copy (its one reader is the output projection)
 int b200_launch_flash_attn_fused(cudaStream_t s, const b200_td& q, const b200_td& k, const void* vt, int64_t Lk_pad, const b200_td& v,
-                                 const b200_td* mask, const b200_td& dst, float scale, void* dst16 = nullptr);
+                                 const b200_td* mask, const b200_td& dst, float scale, void* dst16 = nullptr, int skip_f32 = 0);

@@ -45,6 +45,7 @@ struct FaParams {
     int v_mn;                      // V is read in its natural [key][dv] layout (MN-major B operand of the P.V product); 0: pre-transposed V^T
     int pos_scale;                 // scale > 0: the row maximum may be taken before scaling
     int q_vec;                     // Q rows are 16-byte aligned and d % 4 == 0: coalesced float4 loads
+    int skip_f32;                  // only the f16 copy is wanted (its single reader is the output projection): no f32 stores
     float scale_log2;              // scale * log2(e)
     float log2e;
 };
@@ -361,8 +362,10 @@ __global__ void __launch_bounds__(192, FaCfg<NATOM, BLOCK_N>::MIN_CTAS) k_flash_
             uint32_t o[32];
             tmem_ld32(tmem_O + lane_off + c0, o);
             tmem_ld_wait();
+            if (!p.skip_f32) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = __uint_as_float(o[i]) * inv;
+                for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = __uint_as_float(o[i]) * inv;
+            }
             if (drow16 && qi < p.Lq) {
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -383,6 +386,7 @@ __global__ void __launch_bounds__(192, FaCfg<NATOM, BLOCK_N>::MIN_CTAS) k_flash_
                     }
                 }
             }
+            if (p.skip_f32) continue;
             __syncwarp();
             if (c0 + lane < dv) {
 #pragma unroll 4
@@ -435,7 +439,7 @@ int launch_fa(cudaStream_t s, dim3 grid, const CUtensorMap& tk, const CUtensorMa
 
 // vt: packed V^T, f16 [Lk_pad, dv, Hkv, N] dense (row stride Lk_pad elements)
 int b200_launch_flash_attn_fused(cudaStream_t s, const b200_td& q, const b200_td& k, const void* vt, int64_t Lk_pad, const b200_td& v,
-                                 const b200_td* mask, const b200_td& dst, float scale, void* dst16) {
+                                 const b200_td* mask, const b200_td& dst, float scale, void* dst16, int skip_f32) {
     const int64_t d = q.ne[0], Lq = q.ne[1], H = q.ne[2], NB = q.ne[3];
     const int64_t Lk = k.ne[1], Hkv = k.ne[2], dv = v.ne[0];
     if (d != dv || d % 8 || d > 192 || k.type != GGML_TYPE_F16) return -1;
@@ -476,6 +480,8 @@ int b200_launch_flash_attn_fused(cudaStream_t s, const b200_td& q, const b200_td
     // the f16 copy needs 16-byte aligned rows for its vector stores
     p.dst16 = (dst16 && !((uintptr_t)dst16 & 15) && !(dst.nb[1] & 31) && !(dst.nb[2] & 31) && !(dst.nb[3] & 31)) ? (__half*)dst16 : nullptr;
     if (dst16 && !p.dst16) return -1;
+    if (skip_f32 && !p.dst16) return -1;
+    p.skip_f32 = skip_f32 ? 1 : 0;
     if (mask) {
         p.mask = (const __half*)mask->data;
         p.m_nb1 = mask->nb[1]; p.m_nb2 = mask->nb[2]; p.m_nb3 = mask->nb[3];

@@ -21,6 +21,7 @@
 #include "sm100_ptx.cuh"
 
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -49,6 +50,7 @@ struct GemmKParams {
     const float* residual;
     int64_t ldr, r_batch_stride;
     int act;           // 0 none, 1 silu, 2 gelu(tanh)
+    const float* gate; // per-m factor after the activation, before the residual (b200_gemm_args::gate; always with a residual)
     // implicit-GEMM convolution (conv != 0): A is an NHWC f16 image read through a 4-D map (C, W, H, N) with halo boxes;
     // k-block kb -> filter tap kb / cblocks and 64-channel block kb % cblocks; rows of the tile are output pixels
     int conv;
@@ -57,6 +59,9 @@ struct GemmKParams {
     int conv_cblocks;  // IC / 64
     int conv_pad, conv_dil;
     int early;         // operands that may be fetched before griddepcontrol.wait (bit 0 = A, bit 1 = B): constant weights
+    // optional 16-bit copy of the result, D's element layout (b200_gemm_args::D16): no residual, no activation on this kernel
+    void* D16;
+    int d16_bf16, skip_f32;
     unsigned long long* trace;   // optional: CTA (0,0,0) writes %globaltimer at its phase boundaries (tools/gemm_bench only)
 };
 
@@ -84,6 +89,12 @@ __device__ __forceinline__ float epilogue_act(float v, int act) {
     if (act == 1) return v / (1.0f + expf(-v));
     if (act == 2) return 0.5f * v * (1.0f + tanhf(0.79788456080286535587989211986876f * v * (1.0f + 0.044715f * v * v)));
     return v;
+}
+
+__device__ __forceinline__ uint16_t round16(float v, int bf16) {
+    if (bf16) { const __nv_bfloat16 h = __float2bfloat16_rn(v); return *(const uint16_t*)&h; }
+    const __half h = __float2half_rn(v);
+    return *(const uint16_t*)&h;
 }
 
 // FMT: 0 = f16, 1 = bf16, 2 = tf32 (operand format field of the instruction descriptor)
@@ -213,6 +224,7 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
         float* Dp = p.D + (int64_t)batch * p.d_batch_stride;
         const float* Rp = p.residual ? p.residual + (int64_t)batch * p.r_batch_stride : nullptr;
         const float bias_m = (p.bias_mode == 1 && m < p.M) ? p.bias[m] : 0.f;
+        const float gate_m = (p.gate && m < p.M) ? p.gate[m] : 1.f;
         float* sred = (float*)smem;   // [BN][BM] f32 partial tile; the operand ring is dead once tmem_full has fired
         const int ncols = (int)min((int64_t)BN, p.N - n0);
         const bool mvalid = m < p.M;
@@ -236,7 +248,17 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
                 tmem_ld32(taddr + c0, r);
                 const float bn = (bias_n && c0 + lane < ncols) ? bias_n[c0 + lane] : 0.f;   // lane j carries the bias of column c0 + j
                 tmem_ld_wait();
-                if (rptr == nullptr) {
+                if (p.D16) {
+                    uint16_t* hptr = (uint16_t*)p.D16 + (int64_t)batch * p.d_batch_stride + (int64_t)n0 * p.ldd + m;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = __uint_as_float(r[j]) + bias_m + __shfl_sync(0xffffffffu, bn, j);
+                        if (mvalid && c0 + j < ncols) {
+                            if (!p.skip_f32) dptr[(int64_t)(c0 + j) * p.ldd] = v;
+                            hptr[(int64_t)(c0 + j) * p.ldd] = round16(v, p.d16_bf16);
+                        }
+                    }
+                } else if (rptr == nullptr) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float v = __uint_as_float(r[j]) + bias_m + __shfl_sync(0xffffffffu, bn, j);
@@ -250,7 +272,9 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
                     for (int j = 0; j < 32; ++j) rr[j] = (mvalid && c0 + j < ncols) ? rptr[(int64_t)(c0 + j) * p.ldr] : 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float v = __uint_as_float(r[j]) + bias_m + __shfl_sync(0xffffffffu, bn, j) + rr[j];
+                        float v = __uint_as_float(r[j]) + bias_m + __shfl_sync(0xffffffffu, bn, j);
+                        if (p.gate) v = __fmul_rn(v, gate_m);
+                        v += rr[j];
                         if (mvalid && c0 + j < ncols) dptr[(int64_t)(c0 + j) * p.ldd] = v;
                     }
                 }
@@ -268,6 +292,7 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
                         float v = __uint_as_float(r[j]) + bias_m;
                         if (p.bias_mode == 2) v += p.bias[n];
                         v = epilogue_act(v, p.act);
+                        if (p.gate) v = __fmul_rn(v, gate_m);
                         if (Rp) v += Rp[n * p.ldr + m];
                         Dp[n * p.ldd + m] = v;
                     }
@@ -299,6 +324,13 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
                 if (mrow + 2 < p.M) bm.z = p.bias[mrow + 2];
                 if (mrow + 3 < p.M) bm.w = p.bias[mrow + 3];
             }
+            float4 gm = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (p.gate) {
+                if (mrow + 0 < p.M) gm.x = p.gate[mrow + 0];
+                if (mrow + 1 < p.M) gm.y = p.gate[mrow + 1];
+                if (mrow + 2 < p.M) gm.z = p.gate[mrow + 2];
+                if (mrow + 3 < p.M) gm.w = p.gate[mrow + 3];
+            }
             const uint32_t sred_local = smem_u32(smem);
             uint32_t peer[8];
 #pragma unroll
@@ -319,8 +351,26 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
                 const float bn = p.bias_mode == 2 ? p.bias[n] : 0.f;
                 v.x += bm.x + bn; v.y += bm.y + bn; v.z += bm.z + bn; v.w += bm.w + bn;
                 if (p.act) { v.x = epilogue_act(v.x, p.act); v.y = epilogue_act(v.y, p.act); v.z = epilogue_act(v.z, p.act); v.w = epilogue_act(v.w, p.act); }
+                if (p.gate) { v.x = __fmul_rn(v.x, gm.x); v.y = __fmul_rn(v.y, gm.y); v.z = __fmul_rn(v.z, gm.z); v.w = __fmul_rn(v.w, gm.w); }
                 float* dst = Dp + n * p.ldd + mrow;
-                if (vec_ok && (Rp == nullptr || (((p.ldr & 3) == 0) && ((((uintptr_t)Rp) & 15) == 0)))) {
+                if (p.D16) {        // (launcher: no residual with a 16-bit copy)
+                    uint16_t* h16 = (uint16_t*)p.D16 + (int64_t)batch * p.d_batch_stride + n * p.ldd + mrow;
+                    if (vec_ok && (((uintptr_t)p.D16 | (uintptr_t)(p.d_batch_stride * 2)) & 7) == 0) {
+                        if (!p.skip_f32) *(float4*)dst = v;
+                        uint2 h;
+                        h.x = (uint32_t)round16(v.x, p.d16_bf16) | ((uint32_t)round16(v.y, p.d16_bf16) << 16);
+                        h.y = (uint32_t)round16(v.z, p.d16_bf16) | ((uint32_t)round16(v.w, p.d16_bf16) << 16);
+                        *(uint2*)h16 = h;
+                    } else {
+                        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (mrow + u < p.M) {
+                                if (!p.skip_f32) dst[u] = vv[u];
+                                h16[u] = round16(vv[u], p.d16_bf16);
+                            }
+                    }
+                } else if (vec_ok && (Rp == nullptr || (((p.ldr & 3) == 0) && ((((uintptr_t)Rp) & 15) == 0)))) {
                     if (Rp) { const float4 rr = *(const float4*)(Rp + n * p.ldr + mrow); v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
                     *(float4*)dst = v;
                 } else {
@@ -514,6 +564,7 @@ int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     if (((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15)) return -1;
     if ((g.lda * es) % 16 || (g.ldb * es) % 16) return -1;
     if (g.K <= 0) return -1;
+    if (g.gate && !g.residual) return -1;       // the gated epilogue exists on the residual paths only
     const int bk = (int)(BK_BYTES / es);
     const int nkb = (int)((g.K + bk - 1) / bk);
     double cycles1 = 0;
@@ -546,8 +597,13 @@ int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     kp.bias = g.bias; kp.bias_mode = g.bias ? g.bias_mode : 0;
     kp.residual = g.residual; kp.ldr = g.ldr; kp.r_batch_stride = g.d_batch_stride;
     kp.act = g.act;
+    kp.gate = g.gate;
     kp.early = g.early & 3;
     kp.trace = (unsigned long long*)g.trace;
+    if (g.D16 && !g.residual && g.act == 0 && (g.d16_type == GGML_TYPE_F16 || g.d16_type == GGML_TYPE_BF16) && !((uintptr_t)g.D16 & 1)) {
+        kp.D16 = g.D16; kp.d16_bf16 = g.d16_type == GGML_TYPE_BF16; kp.skip_f32 = g.skip_f32;
+        if (g.d16_done) *g.d16_done = 1;
+    }
     const int64_t mt = (g.M + BM - 1) / BM, nt = (g.N + pl.bn - 1) / pl.bn;
     if (mt > 0x7fffffff || nt > 65535 || g.batch * pl.splits > 65535) return -1;
     (void)workspace; (void)workspace_bytes;

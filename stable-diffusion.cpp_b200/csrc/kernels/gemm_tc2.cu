@@ -54,6 +54,7 @@ struct G2Params {
     int bias_mode;          // 0 none, 1 per m, 2 per n
     const float* residual;
     int64_t ldr, r_batch_stride;
+    const float* gate;      // per-m factor applied after the activation, before the residual (rounded product, then rounded sum)
     int act;
     int tma_store;          // staged epilogue whose 32-column x 128-row chunks leave through cp.async.bulk.tensor stores (no residual / peer copy)
     int vec_epi;            // staged epilogue: the 4 warps of a column group transpose 32 columns x 128 rows through shared memory and store 512 B per column
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
             const int64_t m = (int64_t)m0 + ml;
             const bool mvalid = m < p.M;
             const float bias_m = (p.bias_mode == 1 && mvalid) ? p.bias[m] : 0.f;
+            const float gate_m = (p.gate && mvalid) ? p.gate[m] : 1.f;
             const int ncols = (int)min((int64_t)p.bn, p.N - n0);
             float* Dp = p.D + (int64_t)batch * p.d_batch_stride;
             const float* Rp = p.residual ? p.residual + (int64_t)batch * p.r_batch_stride : nullptr;
@@ -307,6 +309,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                 const bool rvalid = mrow < p.M;                           // M % 4 == 0 on this path
                 float4 bm4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.bias_mode == 1 && rvalid) bm4 = *(const float4*)(p.bias + mrow);
+                float4 gm4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (p.gate && rvalid) gm4 = *(const float4*)(p.gate + mrow);
 #pragma unroll 1
                 for (int c0 = half * 32; c0 < ncols; c0 += 64) {
                     uint32_t r[32];
@@ -323,6 +327,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                             const float bn = p.bias_mode == 2 ? p.bias[n0 + n] : 0.f;
                             v.x += bm4.x + bn; v.y += bm4.y + bn; v.z += bm4.z + bn; v.w += bm4.w + bn;
                             if (p.act) { v.x = act_fn(v.x, p.act); v.y = act_fn(v.y, p.act); v.z = act_fn(v.z, p.act); v.w = act_fn(v.w, p.act); }
+                            if (p.gate) { v.x = __fmul_rn(v.x, gm4.x); v.y = __fmul_rn(v.y, gm4.y); v.z = __fmul_rn(v.z, gm4.z); v.w = __fmul_rn(v.w, gm4.w); }
                             const int64_t off = (int64_t)(n0 + n) * p.ldd + mrow;
                             if (Rp) {
                                 const float4 rr = *(const float4*)(Rp + (int64_t)(n0 + n) * p.ldr + mrow);
@@ -370,7 +375,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                         for (int i = 0; i < 32; ++i) rr[i] = (mvalid && c0 + i < ncols) ? rptr[(int64_t)(c0 + i) * p.ldr] : 0.f;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const float v = __uint_as_float(r[i]) + bias_m + __shfl_sync(0xffffffffu, bn, i) + rr[i];
+                            float v = __uint_as_float(r[i]) + bias_m + __shfl_sync(0xffffffffu, bn, i);
+                            if (p.gate) v = __fmul_rn(v, gate_m);
+                            v += rr[i];
                             if (mvalid && c0 + i < ncols) {
                                 dptr[(int64_t)(c0 + i) * p.ldd] = v;
                                 if (p.D2) dptr[(int64_t)(c0 + i) * p.ldd + d2off] = v;
@@ -391,6 +398,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                             float v = __uint_as_float(r[i]) + bias_m;
                             if (p.bias_mode == 2) v += p.bias[n];
                             v = act_fn(v, p.act);
+                            if (p.gate) v = __fmul_rn(v, gate_m);
                             if (Rp) v += Rp[n * p.ldr + m];
                             Dp[n * p.ldd + m] = v;
                             if (p.D2) Dp[n * p.ldd + m + d2off] = v;
@@ -424,6 +432,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                 if (mrow + 2 < p.M) bm.z = p.bias[mrow + 2];
                 if (mrow + 3 < p.M) bm.w = p.bias[mrow + 3];
             }
+            float4 gm = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (p.gate) {
+                if (mrow + 0 < p.M) gm.x = p.gate[mrow + 0];
+                if (mrow + 1 < p.M) gm.y = p.gate[mrow + 1];
+                if (mrow + 2 < p.M) gm.z = p.gate[mrow + 2];
+                if (mrow + 3 < p.M) gm.w = p.gate[mrow + 3];
+            }
             const uint32_t sred_local = smem_u32(smem);
             uint32_t peer[8];
 #pragma unroll
@@ -445,10 +460,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                 const float bn = p.bias_mode == 2 ? p.bias[n] : 0.f;
                 v.x += bm.x + bn; v.y += bm.y + bn; v.z += bm.z + bn; v.w += bm.w + bn;
                 if (p.act) { v.x = act_fn(v.x, p.act); v.y = act_fn(v.y, p.act); v.z = act_fn(v.z, p.act); v.w = act_fn(v.w, p.act); }
+                if (p.gate) { v.x = __fmul_rn(v.x, gm.x); v.y = __fmul_rn(v.y, gm.y); v.z = __fmul_rn(v.z, gm.z); v.w = __fmul_rn(v.w, gm.w); }
                 float* dst = Dp + n * p.ldd + mrow;
                 if (vec_ok && (Rp == nullptr || (((p.ldr & 3) == 0) && ((((uintptr_t)Rp) & 15) == 0)))) {
                     if (Rp) { const float4 rr = *(const float4*)(Rp + n * p.ldr + mrow); v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
-                    *(float4*)dst = v;
+                    if (!p.skip_f32) *(float4*)dst = v;
+                    if (p.D16) {        // (launcher: 8-byte aligned 16-bit rows whenever D16 is set with splits > 1)
+                        uint2 h;
+                        if (p.d16_bf16) {
+                            const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+                            h.x = *(const uint32_t*)&a; h.y = *(const uint32_t*)&b;
+                        } else {
+                            const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+                            h.x = *(const uint32_t*)&a; h.y = *(const uint32_t*)&b;
+                        }
+                        *(uint2*)((uint16_t*)p.D16 + (int64_t)batch * p.d_batch_stride + n * p.ldd + mrow) = h;
+                    }
                     if (p.D2) {
                         if ((d2off & 3) == 0) *(float4*)(dst + d2off) = v;
                         else { dst[d2off] = v.x; dst[d2off + 1] = v.y; dst[d2off + 2] = v.z; dst[d2off + 3] = v.w; }
@@ -532,6 +559,7 @@ int vec_epilogue_ok(const G2Params& kp, int splits) {
     if ((kp.M & 3) || (kp.ldd & 3) || (kp.d_batch_stride & 3) || ((uintptr_t)kp.D & 15)) return 0;
     if (kp.residual && ((kp.ldr & 3) || (kp.r_batch_stride & 3) || ((uintptr_t)kp.residual & 15))) return 0;
     if (kp.bias_mode == 1 && ((uintptr_t)kp.bias & 15)) return 0;
+    if (kp.gate && ((uintptr_t)kp.gate & 15)) return 0;
     if (kp.D2 && (((uintptr_t)kp.D2 & 15) || (kp.d2_slot & 3))) return 0;
     return 1;
 }
@@ -542,7 +570,7 @@ bool encode_output(CUtensorMap* out, G2Params& kp, int64_t batch) {
     if (en < 0) { const char* e = getenv("GGML_B200_GEMM2_TMA_STORE"); en = (e && *e) ? atoi(e) : 0; }     // measured 1-5 us SLOWER than the staged st.global path (profiles/r02_gemm_model.md): off
     memset(out, 0, sizeof(*out));
     kp.tma_store = 0;
-    if (!en || !kp.vec_epi || kp.residual || kp.D2) return true;
+    if (!en || !kp.vec_epi || kp.residual || kp.D2 || kp.D16 || kp.gate) return true;
     if ((kp.ldd * 4) % 16 || (kp.d_batch_stride * 4) % 16 || ((uintptr_t)kp.D & 15)) return true;
     // batch must be the outermost dimension of the output (the P.V product of the unfused attention interleaves heads INSIDE a row:
     // d_batch_stride < ldd -- such maps are left to the st.global path)
@@ -633,6 +661,7 @@ int b200_launch_gemm_tc2(cudaStream_t s, const b200_device_info& dev, const b200
     if (g.type != GGML_TYPE_F16 && g.type != GGML_TYPE_BF16) return -1;
     if (((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15) || (g.lda * 2) % 16 || (g.ldb * 2) % 16) return -1;
     if ((g.a_batch_stride * 2) % 16 || (g.b_batch_stride * 2) % 16) return -1;
+    if (g.gate && !g.residual) return -1;       // the gated epilogue exists on the residual paths only
     if (bn < 16 || bn > 256 || (bn & 15) || splits < 1 || splits > 4) return -1;
     const int nkb = (int)((g.K + 63) / 64);
     if (splits > nkb) return -1;
@@ -651,8 +680,11 @@ int b200_launch_gemm_tc2(cudaStream_t s, const b200_device_info& dev, const b200
     kp.bias = g.bias; kp.bias_mode = g.bias ? g.bias_mode : 0;
     kp.residual = g.residual; kp.ldr = g.ldr; kp.r_batch_stride = g.d_batch_stride;
     kp.act = g.act;
+    kp.gate = g.gate;
     kp.vec_epi = vec_epilogue_ok(kp, splits);
-    if (g.D16 && kp.vec_epi && !((uintptr_t)g.D16 & 7) && (g.d16_type == GGML_TYPE_F16 || g.d16_type == GGML_TYPE_BF16)) {
+    // 16-bit copy: the staged epilogue (splits == 1) or the split-K reduce, both with 8-byte stores of four consecutive rows
+    const bool d16_split_ok = splits > 1 && !g.residual && !(kp.M & 3) && !(kp.ldd & 3) && !(kp.d_batch_stride & 3) && !((uintptr_t)kp.D & 15);
+    if (g.D16 && (kp.vec_epi || d16_split_ok) && !((uintptr_t)g.D16 & 7) && (g.d16_type == GGML_TYPE_F16 || g.d16_type == GGML_TYPE_BF16)) {
         kp.D16 = g.D16; kp.d16_bf16 = g.d16_type == GGML_TYPE_BF16; kp.skip_f32 = g.skip_f32;
         if (g.d16_done) *g.d16_done = 1;
     }

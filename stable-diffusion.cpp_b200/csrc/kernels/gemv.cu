@@ -12,6 +12,9 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace {
 
 constexpr int kWarps = 4;
@@ -36,15 +39,19 @@ template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& 
 template <typename WT>
 __global__ void __launch_bounds__(kWarps * 32) k_gemv(const WT* __restrict__ W, int64_t lda, const float* __restrict__ X, int64_t ldx, float* __restrict__ D,
                                                      int64_t ldd, int M, int K, int N, const float* __restrict__ bias, const float* __restrict__ residual,
-                                                     int64_t ldr, int pre_act) {
+                                                     int64_t ldr, int pre_act, int rows_per_warp) {
     extern __shared__ float xs[];    // [N][K], rounded to WT
     pdl_wait();
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m = blockIdx.x * kWarps + warp;
+    // a block owns kWarps * rows_per_warp consecutive output features; warp w takes rows m0 + w, m0 + w + kWarps, ...  The activation rows
+    // are staged (read, SiLU, rounded) ONCE per block: with one row per warp that staging cost as much traffic and more instructions
+    // than the four weight rows it served (Flux modulation: 12 KB of activations per 24 KB of weights).
+    const int m0 = blockIdx.x * kWarps * rows_per_warp;
     const int K8 = K / 8;
     // the weight stream is what this kernel waits for: put the first 4 x 16 bytes per lane in flight BEFORE the activation rows are staged
     // (their global reads + SiLU + barrier used to sit in front of the first weight load), then keep 4 loads per lane ahead of the math
+    int m = m0 + warp;
     const uint4* wrow = (const uint4*)(W + (int64_t)min(m, M - 1) * lda);
     uint4 wreg[4];
 #pragma unroll
@@ -59,46 +66,60 @@ __global__ void __launch_bounds__(kWarps * 32) k_gemv(const WT* __restrict__ W, 
         xs[i] = round_to<WT>(v);
     }
     __syncthreads();
-    if (m >= M) return;
-    float acc[kMaxN] = {0.f, 0.f, 0.f, 0.f};
-    for (int c0 = lane; c0 < K8; c0 += 128) {
-        uint4 cur[4];
+    for (int r = 0; r < rows_per_warp; ++r, m += kWarps) {
+        if (m >= M) return;
+        // the NEXT row of this warp: its first chunks are issued before this row's reduction and store
+        const int mn = m + kWarps;
+        const uint4* wnext = (const uint4*)(W + (int64_t)min(mn, M - 1) * lda);
+        const bool has_next = r + 1 < rows_per_warp && mn < M;
+        float acc[kMaxN] = {0.f, 0.f, 0.f, 0.f};
+        for (int c0 = lane; c0 < K8; c0 += 128) {
+            uint4 cur[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cur[j] = wreg[j];
+            for (int j = 0; j < 4; ++j) cur[j] = wreg[j];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = c0 + 128 + 32 * j;
-            wreg[j] = c < K8 ? wrow[c] : make_uint4(0u, 0u, 0u, 0u);
-        }
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + 128 + 32 * j;
+                wreg[j] = c < K8 ? wrow[c] : make_uint4(0u, 0u, 0u, 0u);
+            }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = c0 + 32 * j;
-            if (c < K8) {
-                float w[8];
-                unpack8<WT>(cur[j], w);
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + 32 * j;
+                if (c < K8) {
+                    float w[8];
+                    unpack8<WT>(cur[j], w);
 #pragma unroll
-                for (int n = 0; n < kMaxN; ++n) {
-                    if (n < N) {
-                        const float4 x0 = *(const float4*)(xs + n * K + c * 8), x1 = *(const float4*)(xs + n * K + c * 8 + 4);
-                        const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                    for (int n = 0; n < kMaxN; ++n) {
+                        if (n < N) {
+                            const float4 x0 = *(const float4*)(xs + n * K + c * 8), x1 = *(const float4*)(xs + n * K + c * 8 + 4);
+                            const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[n] = fmaf(w[i], x[i], acc[n]);
+                            for (int i = 0; i < 8; ++i) acc[n] = fmaf(w[i], x[i], acc[n]);
+                        }
                     }
                 }
             }
         }
-    }
+        if (has_next) {
 #pragma unroll
-    for (int n = 0; n < kMaxN; ++n) {
+            for (int j = 0; j < 4; ++j) {
+                const int c = lane + 32 * j;
+                wreg[j] = c < K8 ? wnext[c] : make_uint4(0u, 0u, 0u, 0u);
+            }
+            wrow = wnext;
+        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
-    }
-    if (lane == 0) {
-        const float b = bias ? bias[m] : 0.f;
-        for (int n = 0; n < N; ++n) {
-            float v = acc[n] + b;
-            if (residual) v += residual[(int64_t)n * ldr + m];
-            D[(int64_t)n * ldd + m] = v;
+        for (int n = 0; n < kMaxN; ++n) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+        }
+        if (lane == 0) {
+            const float b = bias ? bias[m] : 0.f;
+            for (int n = 0; n < N; ++n) {
+                float v = acc[n] + b;
+                if (residual) v += residual[(int64_t)n * ldr + m];
+                D[(int64_t)n * ldd + m] = v;
+            }
         }
     }
 }
@@ -116,12 +137,17 @@ bool b200_gemv_supported(int wtype, int64_t M, int64_t N, int64_t K, const void*
 int b200_launch_gemv(cudaStream_t s, int wtype, const void* W, int64_t lda, const float* X, int64_t ldx, float* D, int64_t ldd, int64_t M, int64_t N,
                      int64_t K, const float* bias, const float* residual, int64_t ldr, int pre_act) {
     if (!b200_gemv_supported(wtype, M, N, K, W, lda, X)) return -1;
-    const dim3 grid((unsigned)((M + kWarps - 1) / kWarps));
+    // rows per warp: as many as keep >= 4 blocks per SM (the UNet's 320..1280-feature embeddings stay at one row per warp; the Flux / SD3
+    // modulation Linears with 9216..18432 features take 4..8)
+    static int rpw_env = -1;
+    if (rpw_env < 0) { const char* e = getenv("GGML_B200_GEMV_RPW"); rpw_env = (e && *e) ? atoi(e) : 0; }
+    int rpw = rpw_env > 0 ? rpw_env : (int)std::min<int64_t>(8, std::max<int64_t>(1, M / (kWarps * 148 * 4)));
+    const dim3 grid((unsigned)((M + kWarps * rpw - 1) / (kWarps * rpw)));
     const size_t smem = (size_t)(N * K * 4);
     if (wtype == GGML_TYPE_F16)
-        b200_launch(k_gemv<__half>, grid, dim3(kWarps * 32), smem, s, (const __half*)W, lda, X, ldx, D, ldd, (int)M, (int)K, (int)N, bias, residual, ldr, pre_act);
+        b200_launch(k_gemv<__half>, grid, dim3(kWarps * 32), smem, s, (const __half*)W, lda, X, ldx, D, ldd, (int)M, (int)K, (int)N, bias, residual, ldr, pre_act, rpw);
     else
         b200_launch(k_gemv<__nv_bfloat16>, grid, dim3(kWarps * 32), smem, s, (const __nv_bfloat16*)W, lda, X, ldx, D, ldd, (int)M, (int)K, (int)N, bias,
-                    residual, ldr, pre_act);
+                    residual, ldr, pre_act, rpw);
     return 1;
 }

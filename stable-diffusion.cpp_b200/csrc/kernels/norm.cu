@@ -198,6 +198,78 @@ __global__ void k_row_norm(b200_td a, b200_td d, float eps, const float* __restr
     }
 }
 
+// Vectorised row norm: rows of up to 4096 floats live in registers as float4 (one 16-byte load per lane and slot, coalesced 4 KB per
+// CTA-wide instruction), f32 result stored as float4 and the optional 16-bit operand copy as 8 bytes per lane.  The scalar kernel above
+// re-read rows longer than 2048 floats three times with 4-byte accesses: 0.5-1.4 TB/s on the DiT blocks' [3072, 4352] LayerNorms.
+template <int KIND>
+__global__ void __launch_bounds__(256) k_row_norm_vec(b200_td a, b200_td d, float eps, const float* __restrict__ rw, const float* __restrict__ rb, void* out16,
+                                                      int out16_bf16, int modulate) {
+    pdl_wait();
+    pdl_launch_dependents();
+    __shared__ float red[32];
+    const int64_t row = blockIdx.x;
+    const int64_t i1 = row % a.ne[1], r = row / a.ne[1];
+    const int64_t i2 = r % a.ne[2], i3 = r / a.ne[2];
+    const float4* x = (const float4*)((const char*)a.data + i1 * a.nb[1] + i2 * a.nb[2] + i3 * a.nb[3]);
+    float4* y = (float4*)((char*)d.data + i1 * d.nb[1] + i2 * d.nb[2] + i3 * d.nb[3]);
+    const int n4 = (int)(a.ne[0] >> 2);
+    const float n = (float)a.ne[0];
+    float4 v[4];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = threadIdx.x + k * 256;
+        v[k] = i < n4 ? x[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (KIND == B200_NORM_LAYER) ? (v[k].x + v[k].y) + (v[k].z + v[k].w) : (v[k].x * v[k].x + v[k].y * v[k].y) + (v[k].z * v[k].z + v[k].w * v[k].w);
+    }
+    s = block_sum(s, red);
+    float mean = 0.f, scale;
+    if (KIND == B200_NORM_LAYER) {
+        mean = s / n;
+        float s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = threadIdx.x + k * 256;
+            if (i < n4) {
+                const float t0 = v[k].x - mean, t1 = v[k].y - mean, t2 = v[k].z - mean, t3 = v[k].w - mean;
+                s2 += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
+            }
+        }
+        s2 = block_sum(s2, red);
+        scale = 1.0f / sqrtf(s2 / n + eps);
+    } else if (KIND == B200_NORM_RMS) {
+        scale = 1.0f / sqrtf(s / n + eps);
+    } else {
+        scale = 1.0f / fmaxf(sqrtf(s), eps);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = threadIdx.x + k * 256;
+        if (i < n4) {
+            float o[4] = {(v[k].x - mean) * scale, (v[k].y - mean) * scale, (v[k].z - mean) * scale, (v[k].w - mean) * scale};
+            if (rw) {
+                const float4 w4 = ((const float4*)rw)[i];
+                const float4 b4 = rb ? ((const float4*)rb)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float ww[4] = {w4.x, w4.y, w4.z, w4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = modulate ? __fadd_rn(__fadd_rn(o[e], __fmul_rn(o[e], ww[e])), bb[e]) : o[e] * ww[e] + bb[e];
+            }
+            y[i] = make_float4(o[0], o[1], o[2], o[3]);
+            if (out16) {
+                uint2 h;
+                if (out16_bf16) {
+                    const __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+                    h.x = *(const uint32_t*)&p0; h.y = *(const uint32_t*)&p1;
+                } else {
+                    const __half2 p0 = __floats2half2_rn(o[0], o[1]), p1 = __floats2half2_rn(o[2], o[3]);
+                    h.x = *(const uint32_t*)&p0; h.y = *(const uint32_t*)&p1;
+                }
+                ((uint2*)out16)[row * n4 + i] = h;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // SOFT_MAX: one CTA per row; the scaled+masked row lives in shared memory (ne0 floats).
 // ------------------------------------------------------------------------------------------
@@ -272,6 +344,18 @@ int b200_launch_norm(cudaStream_t s, int kind, const b200_td& src, const b200_td
     if (nrows == 0 || src.ne[0] == 0) return 0;
     int threads = src.ne[0] >= 4096 ? 1024 : (src.ne[0] >= 1024 ? 256 : 128);
     if (nrows > 0x7fffffff) return -1;
+    // float4 path: rows of 512 .. 4096 floats, 16-byte aligned rows / affine vectors / 8-byte aligned 16-bit copy
+    const bool vec = src.ne[0] % 4 == 0 && src.ne[0] >= 512 && src.ne[0] <= 4096 && src.nb[0] == 4 && dst.nb[0] == 4 && !((uintptr_t)src.data & 15) && !((uintptr_t)dst.data & 15) &&
+                     !(src.nb[1] & 15) && !(src.nb[2] & 15) && !(src.nb[3] & 15) && !(dst.nb[1] & 15) && !(dst.nb[2] & 15) && !(dst.nb[3] & 15) &&
+                     !((uintptr_t)w & 15) && !((uintptr_t)b & 15) && !((uintptr_t)out16 & 7);
+    if (vec) {
+        switch (kind) {
+            case B200_NORM_LAYER: b200_launch(k_row_norm_vec<B200_NORM_LAYER>, dim3((unsigned)nrows), dim3(256), 0, s, src, dst, eps, w, b, out16, bf, modulate); break;
+            case B200_NORM_RMS: b200_launch(k_row_norm_vec<B200_NORM_RMS>, dim3((unsigned)nrows), dim3(256), 0, s, src, dst, eps, w, b, out16, bf, modulate); break;
+            default: b200_launch(k_row_norm_vec<B200_NORM_L2>, dim3((unsigned)nrows), dim3(256), 0, s, src, dst, eps, w, b, out16, bf, modulate); break;
+        }
+        return 1;
+    }
     switch (kind) {
         case B200_NORM_LAYER: b200_launch(k_row_norm<B200_NORM_LAYER>, dim3((unsigned)nrows), dim3(threads), 0, s, src, dst, eps, w, b, out16, bf, modulate); break;
         case B200_NORM_RMS: b200_launch(k_row_norm<B200_NORM_RMS>, dim3((unsigned)nrows), dim3(threads), 0, s, src, dst, eps, w, b, out16, bf, modulate); break;

@@ -128,16 +128,22 @@ def test_flux_tiny_vs_live_cpu(b200):
     assert rel(outs[dev], outs["CPU"]) < 3e-2, f"rel_l2 {rel(outs[dev], outs['CPU']):.2e}"
 
 
-@pytest.mark.parametrize("arch,shape,cshape", [("unet_tiny", (1, 4, 16, 16), (1, 77, 768)), ("sd15_unet", (1, 4, 64, 64), (1, 77, 768))])
+@pytest.mark.parametrize("arch,shape,cshape", [("unet_tiny", (1, 4, 16, 16), (1, 77, 768)), ("unet_tiny", (2, 4, 32, 32), (2, 77, 768)),
+                                               ("sd15_unet", (1, 4, 64, 64), (1, 77, 768)), ("sd15_unet", (2, 4, 64, 64), (2, 77, 768))])
 def test_producer_side_fusions_are_bit_identical(b200, arch, shape, cshape):
-    """GEGLU tail, Q read in place by the attention kernel, f16 operand copies written by their producers and the early weight fetch
-    move work between kernels without changing one rounding: outputs must equal the unfused execution bit for bit (also across the
-    eager first call, the CUDA-graph capture and its replays)."""
+    """GEGLU tail, Q / K / V read in place by the attention kernel (projection rows, heads interleaved, the CFG batch as its own
+    dimension), f16 operand copies written by their producers (K / V by the projection GEMM, the attention result for its output
+    projection) and the early weight fetch move work between kernels without changing one rounding: outputs must equal the unfused
+    execution bit for bit (also across the eager first call, the CUDA-graph capture and its replays)."""
     h, dev = b200
-    x = h.randn(42, shape); ctx = h.randn(43, cshape); t = np.array([999.0], np.float32)
+    x = h.randn(42, shape); ctx = h.randn(43, cshape); t = np.full((shape[0],), 999.0, np.float32)
     m = h.model(dev, arch, "f16", 1, 1234, 0)
     outs = [m.forward(x, t, ctx)[0] for _ in range(3)]            # eager, capture, replay
     st = m.stats()
+    # every attention layer of the flash-attention graph takes the in-place path (2 projections each) and hands f16 rows to to_out
+    assert st["kv_in_place"] > 0 and st["attn_out_f16_only"] > 0 and st["q_read_in_place"] > 0, st
+    if arch == "sd15_unet":
+        assert st["kv_in_place"] == 2 * st["fused_attn_launches"] and st["attn_out_f16_only"] == st["fused_attn_launches"], st
     m.set_option("chain_fusion", 0)
     m.set_option("early_weights", 0)
     plain = [m.forward(x, t, ctx)[0] for _ in range(2)]
