@@ -85,6 +85,8 @@ typedef struct ggml_b200_stats {
                                    [13] K / V projections whose f16 rows the attention kernel read in place (permute + CONT + cast never run),
                                    [14] attention launches that wrote only the f16 rows of the output projection (no f32 result, no CONT),
                                    [15] gated residuals (x + gate * Linear(y)) applied by a GEMM epilogue */
+    uint64_t side_launches;     /* in-place K / V projections launched on a side stream: beside the Q projection of their layer, or -- for
+                                   projections of graph inputs (the text context) -- hoisted to the start of the graph */
 } ggml_b200_stats;
 
 /* copy the backend instance's counters; returns 0 on success.  Counters of kernels that run inside a replayed CUDA graph are

@@ -60,6 +60,7 @@ struct b200_stats {
     uint64_t tc_gemm_launches;  // tcgen05 GEMM launches (subset of kernel_launches)
     uint64_t reserved[8];
     uint64_t ext[16];           // see include/ggml-b200.h
+    uint64_t side_launches;     // projections launched on a side stream (beside the main stream's kernels)
 };
 
 struct b200_device_info {

@@ -38,6 +38,8 @@ b200_context* b200_context_create(const b200_device_info& info) {
         delete ctx;
         return nullptr;
     }
+    for (int k = 0; k < 3; ++k)
+        if (cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ctx->side[k] = nullptr; }
     cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming);
     cudaEventCreate(&ctx->ev_start);
     cudaEventCreate(&ctx->ev_stop);
@@ -55,6 +57,7 @@ b200_context* b200_context_create(const b200_device_info& info) {
     ctx->opt_precise_f32 = env_flag("GGML_B200_PRECISE_F32", 1) != 0;
     ctx->opt_q8_activations = env_flag("GGML_B200_Q8_ACT", 1) != 0;
     ctx->opt_persistent_gemm = env_flag("GGML_B200_PERSISTENT", 0) != 0;   // experimental persistent GEMM (gemm_tc_persist.cu), never run on hardware yet
+    ctx->opt_side_streams = env_flag("GGML_B200_SIDE_STREAMS", 1) != 0;
     ctx->opt_fold_batch = env_flag("GGML_B200_FOLD_BATCH", 0) != 0;   // written at the end of round 1, not yet measured: off by default
     return ctx;
 }
@@ -62,6 +65,8 @@ b200_context* b200_context_create(const b200_device_info& info) {
 b200_context::~b200_context() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
+    for (int k = 0; k < 3; ++k) if (side[k]) { cudaStreamSynchronize(side[k]); cudaStreamDestroy(side[k]); }
+    for (auto e : ev_pool) cudaEventDestroy(e);
     for (auto& c : ws.chunks) cudaFree(c.base);
     if (gn_counters) cudaFree(gn_counters);
     b200_peer_close(this);
@@ -85,6 +90,7 @@ int b200_context_set_option(b200_context* ctx, const char* key, int value) {
     else if (!strcmp(key, "cuda_graphs")) ctx->opt_cuda_graphs = value != 0;
     else if (!strcmp(key, "kernel_timing")) ctx->opt_kernel_timing = value != 0;
     else if (!strcmp(key, "fused_attn")) ctx->opt_fused_attn = value != 0;
+    else if (!strcmp(key, "side_streams")) ctx->opt_side_streams = value != 0;
     else if (!strcmp(key, "implicit_conv")) ctx->opt_implicit_conv = value != 0;
     else if (!strcmp(key, "early_weights")) ctx->opt_early_weights = value != 0;
     else if (!strcmp(key, "chain_fusion")) ctx->opt_chain_fusion = value != 0;
@@ -186,6 +192,17 @@ using operand = b200_operand;
 // otherwise packed (converted, K padded to 16 bytes) into workspace.  Returns false on allocation failure.
 static const void* get_dequantised_weight(b200_context* ctx, const ggml_tensor* w, int* launches);
 
+// events for the fork / join edges between the main stream and the side streams; none is created while a capture is running
+static cudaEvent_t side_event(b200_context* ctx) {
+    if (ctx->ev_next < ctx->ev_pool.size()) return ctx->ev_pool[ctx->ev_next++];
+    if (ctx->capturing) return nullptr;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ctx->ev_pool.push_back(e);
+    ctx->ev_next++;
+    return e;
+}
+
 static bool prepare_operand(b200_context* ctx, const ggml_tensor* t, int want, operand* out, int* launches) {
     if (t->type == GGML_TYPE_Q8_0) {
         if (want != GGML_TYPE_F16) return false;
@@ -203,6 +220,10 @@ static bool prepare_operand(b200_context* ctx, const ggml_tensor* t, int want, o
     // once per graph execution: a ggml tensor node is a value, its buffer is not overwritten before its last consumer has run
     auto hit = ctx->pack_cache.find(std::make_pair(t, want));
     if (hit != ctx->pack_cache.end()) {
+        if (!ctx->pack_origins.empty()) {      // packed on another stream: this stream waits for that pack kernel
+            auto o = ctx->pack_origins.find(std::make_pair(t, want));
+            if (o != ctx->pack_origins.end() && o->second.stream != ctx->stream) cudaStreamWaitEvent(ctx->stream, o->second.ready, 0);
+        }
         *out = hit->second;
         return true;
     }
@@ -216,6 +237,12 @@ static bool prepare_operand(b200_context* ctx, const ggml_tensor* t, int want, o
     if (n < 0) return false;
     *launches += n;
     *out = operand{buf, want, kpad, kpad * t->ne[1], kpad * t->ne[1] * t->ne[2]};
+    if (ctx->on_side) {
+        cudaEvent_t e = side_event(ctx);
+        if (!e) return true;                   // (no event left inside a capture: usable by this launch, not shared)
+        cudaEventRecord(e, ctx->stream);
+        ctx->pack_origins[std::make_pair(t, want)] = b200_context::pack_origin{ctx->stream, e};
+    }
     ctx->pack_cache[std::make_pair(t, want)] = *out;
     return true;
 }
@@ -303,6 +330,7 @@ struct mm_fusion {
     int d16_type = 0;
     bool skip_f32 = false;
     int* d16_done = nullptr;
+    bool d16_strict = false;                  // decline (-2, nothing written) rather than run without the 16-bit copy
 };
 
 static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz = nullptr) {
@@ -320,7 +348,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
     }
 
     // a handful of activation rows against in-place F16/BF16 weights (embedding MLPs): weight-streaming GEMV, no operand packing
-    if (!(fz && (fz->act || fz->gate))) {
+    if (!(fz && (fz->act || fz->gate || fz->d16_strict))) {
         const ggml_tensor* x = fz && fz->src1_pre ? fz->src1_pre : src1;
         if (ctx->opt_gemv && ne02 * ne03 * ne12 * ne13 == 1 && N <= 4 && (src0->type == GGML_TYPE_F16 || src0->type == GGML_TYPE_BF16) &&
             rows_unit_stride(src0) && x->type == GGML_TYPE_F32 && x->nb[0] == 4 && x->nb[1] % 4 == 0 && dst->nb[0] == 4 &&
@@ -449,7 +477,8 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
         if (fz && fz->bias) { g.bias = fz->bias; g.bias_mode = fz->bias_mode; }
         if (fz && fz->residual) { g.residual = fz->residual; g.ldr = g.ldd; }
         if (fz) { g.act = fz->act; g.gate = fz->gate; }
-        if (fz && fz->d16 && nb13 == 1) { g.D16 = fz->d16; g.d16_type = fz->d16_type; g.skip_f32 = fz->skip_f32 ? 1 : 0; g.d16_done = fz->d16_done; }
+        if (fz && fz->d16 && nb13 == 1) { g.D16 = fz->d16; g.d16_type = fz->d16_type; g.skip_f32 = fz->skip_f32 ? 1 : 0; g.d16_done = fz->d16_done; g.d16_strict = fz->d16_strict ? 1 : 0; }
+        else if (fz && fz->d16_strict) return -2;
         // model weights read in place are constants of the graph: their first ring-full may be fetched before the PDL wait.  Not for
         // the first kernel of a graph_compute (its stream predecessor belongs to an earlier call, e.g. a weight update).
         if (ctx->opt_early_weights && a.ptr == src0->data && src0->buffer && src0->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS &&
@@ -457,6 +486,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
             g.early = 1;
         int n = launch_tc(ctx, g);
         if (n < 0) {
+            if (fz && fz->d16_strict) return -2;             // declined before anything was launched: the caller runs the node in its turn
             if (fz && (fz->act || fz->gate)) return -1;      // the reference kernel has no activation / gate epilogue: fail loudly rather than skip it
             // CUDA-core reference kernel (debug option, or shapes the TMA cannot describe)
             n = 0;
@@ -1046,6 +1076,10 @@ struct fusion_state {
     // [d, Lk, H, B] over its [B][Lk][H * d] rows: the permute + CONT + cast chain in between was never executed
     struct kv_direct { b200_td td; const ggml_tensor* cast_dst; };
     std::unordered_map<const ggml_tensor*, kv_direct> fa_kv;
+    // projections running on a side stream: `done` must have fired before the main stream executes any node after position `pos`
+    // (the allocator's lifetimes are those of in-order execution)
+    struct side_job { int pos; cudaEvent_t done; };
+    std::vector<side_job> pend;
 };
 
 static void count_uses(const ggml_cgraph* g, fusion_state& fs) {
@@ -1101,9 +1135,72 @@ static inline bool overlaps_range(const void* a, size_t na, const void* b, size_
     return (const char*)a < (const char*)b + nb && (const char*)b < (const char*)a + na;
 }
 
+// K / V projection of an attention layer (ggml_ext_attention_ext, ggml_extend.hpp:1340-1400): Linear -> reshape [d, H, L, B] ->
+// permute(0,2,1,3) -> CONT -> reshape [d, L, H*B] -> CPY to F16 -> FLASH_ATTN_EXT.  The fused attention kernel reads K / V through any
+// 16-byte aligned strides, so the epilogue writes the f16 rows [B][L][H * d] once and the attention reads head h of token l at
+// (l * H + h) * d: no f32 projection, no permute copy, no cast pass.  Same values: the CONT copies and the CPY rounds f32 -> f16 (RN),
+// exactly what the epilogue's conversion does.  `curv`: tensor holding the projection's value (mm, or its bias ADD); `after`: its node index.
+struct kv_match { int jc, jp; const ggml_tensor* cp; const ggml_tensor* cast_dst; int64_t d, L, H, B; };
+static bool match_kv_projection(const b200_context* ctx, const ggml_cgraph* g, const fusion_state& fs, const ggml_tensor* mm, const ggml_tensor* curv, int after,
+                                kv_match* out) {
+    static int kv_enabled = -1;
+    if (kv_enabled < 0) { const char* e = getenv("GGML_B200_KV_DIRECT"); kv_enabled = (e && *e) ? atoi(e) : 1; }
+    if (!kv_enabled || !ctx->opt_chain_fusion || !ctx->opt_tc_gemm || !ctx->opt_fused_attn) return false;
+    if (mm->src[0]->type != GGML_TYPE_F16 || mm->ne[3] != 1 || mm->ne[1] <= 4 || !ggml_is_contiguous(mm) || mm->src[1]->ne[3] != 1) return false;
+    const int jc = next_node(g, fs, after);
+    const int jp = jc >= 0 ? next_node(g, fs, jc) : -1;
+    if (jp < 0 || g->nodes[jc]->op != GGML_OP_CONT || g->nodes[jp]->op != GGML_OP_CPY || (curv->flags & GGML_TENSOR_FLAG_OUTPUT)) return false;
+    const ggml_tensor* c = g->nodes[jc];
+    const ggml_tensor* cp = g->nodes[jp];
+    const ggml_tensor* pv = c->src[0];                      // the permuted view of the projection
+    const int64_t Mf = mm->ne[0], L = mm->ne[1], Bn = mm->ne[2];
+    if (!(c->type == GGML_TYPE_F32 && ggml_is_contiguous(c) && single_use(fs, c) && (c->flags & GGML_TENSOR_FLAG_COMPUTE) && (cp->flags & GGML_TENSOR_FLAG_COMPUTE) &&
+          pv->type == GGML_TYPE_F32 && pv->data == curv->data && ggml_are_same_shape(pv, c)))
+        return false;
+    // views between the projection and the CONT: one consumer each (nobody else reads the f32 projection)
+    {
+        const ggml_tensor* v = pv;
+        int depth = 0;
+        while (v != curv && depth++ < 6) {
+            if (!is_view_op(v) || !v->src[0] || !single_use(fs, v) || v->data != curv->data) return false;
+            v = v->src[0];
+        }
+        if (v != curv || !single_use(fs, curv)) return false;
+    }
+    // geometry: pv = [d, L, H, B] over rows of Mf = H * d features
+    const int64_t d = pv->ne[0], H = pv->ne[2];
+    if (!(d > 0 && d * H == Mf && pv->ne[1] == L && pv->ne[3] == Bn && pv->nb[0] == 4 && pv->nb[2] == (size_t)d * 4 && pv->nb[1] == (size_t)Mf * 4 &&
+          (Bn == 1 || pv->nb[3] == (size_t)Mf * L * 4) && d % 8 == 0 && d <= 192))
+        return false;
+    const ggml_tensor* cd = cp->src[1];     // the cast's destination
+    if (!(cd && cd->type == GGML_TYPE_F16 && ggml_is_contiguous(cd) && cd->ne[0] == d && cd->ne[1] == L && ggml_nelements(cd) == ggml_nelements(c) &&
+          order_preserving_view_of(fs, cp->src[0], c) && (cp->src[0] == c || single_use(fs, cp->src[0]))))
+        return false;
+    {   // one reader of the cast.  ggml_cast makes the node its own src[1] (ggml.c: result->src[1] = result), which counts as a use
+        auto it = fs.uses.find(cp);
+        const int self = cp->src[1] == cp ? 1 : 0;
+        if ((cp->flags & GGML_TENSOR_FLAG_OUTPUT) || it == fs.uses.end() || it->second != 1 + self) return false;
+    }
+    // its one reader: the K or V operand of an attention node the fused kernel will take (no mask, no ALiBi, d == dv)
+    const ggml_tensor* fa = nullptr;
+    for (int j = jp + 1; j < g->n_nodes && j < jp + 32; ++j) {
+        const ggml_tensor* t = g->nodes[j];
+        if (t->op == GGML_OP_FLASH_ATTN_EXT && (t->src[1] == cp || t->src[2] == cp)) { fa = t; break; }
+    }
+    if (!fa || fa->src[1] == fa->src[2] || fa->src[3]) return false;
+    float max_bias;
+    memcpy(&max_bias, (const float*)fa->op_params + 1, sizeof(float));
+    const ggml_tensor* fq = fa->src[0];
+    if (!(max_bias == 0.0f && fq->type == GGML_TYPE_F32 && fq->ne[0] == d && fa->src[1]->ne[0] == d && fa->src[2]->ne[0] == d && fa->src[1]->type == GGML_TYPE_F16 &&
+          fa->src[2]->type == GGML_TYPE_F16 && fq->ne[3] == 1 && fq->ne[2] % Bn == 0 && (fq->ne[2] / Bn) % H == 0))
+        return false;
+    *out = kv_match{jc, jp, cp, cd, d, L, H, Bn};
+    return true;
+}
+
 // MUL_MAT [-> views] [-> CONT of an order-preserving view] [-> views] [-> ADD bias]
 static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered, const ggml_tensor* src1_pre = nullptr,
-                            int pre_act = 0) {
+                            int pre_act = 0, bool side_only = false) {
     ggml_tensor* mm = g->nodes[i];
     if (!ggml_is_contiguous(mm) || (mm->flags & GGML_TENSOR_FLAG_OUTPUT)) return -2;
     std::vector<int> chain;
@@ -1185,76 +1282,28 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
             }
         }
     }
-    // K / V projection of an attention layer (ggml_ext_attention_ext, ggml_extend.hpp:1340-1400): Linear -> reshape [d, H, L, B] ->
-    // permute(0,2,1,3) -> CONT -> reshape [d, L, H*B] -> CPY to F16 -> FLASH_ATTN_EXT.  The fused attention kernel reads K / V through any
-    // 16-byte aligned strides, so the epilogue writes the f16 rows [B][L][H * d] once and the attention reads head h of token l at
-    // (l * H + h) * d: no f32 projection, no permute copy, no cast pass.  Same values: the CONT copies and the CPY rounds f32 -> f16 (RN),
-    // exactly what the epilogue's conversion does.
+    // K / V projection of an attention layer: see match_kv_projection
     int kv_done = 0, kv_cont = -1, kv_cpy = -1;
     const ggml_tensor* kv_cp = nullptr;
     fusion_state::kv_direct kvd;
-    static int kv_enabled = -1;
-    if (kv_enabled < 0) { const char* e = getenv("GGML_B200_KV_DIRECT"); kv_enabled = (e && *e) ? atoi(e) : 1; }
-    if (kv_enabled && !fz.act && !fz.d16 && !src1_pre && ctx->opt_chain_fusion && ctx->opt_tc_gemm && ctx->opt_fused_attn &&
-        mm->src[0]->type == GGML_TYPE_F16 && mm->ne[3] == 1 && mm->ne[1] > 4) {
+    if (!fz.act && !fz.d16 && !src1_pre) {
         const ggml_tensor* curv = chain.empty() ? (const ggml_tensor*)mm : g->nodes[chain.back()];
-        const int jc = chain.empty() ? next_node(g, fs, i) : next_node(g, fs, chain.back());
-        const int jp = jc >= 0 ? next_node(g, fs, jc) : -1;
-        if (jp >= 0 && g->nodes[jc]->op == GGML_OP_CONT && g->nodes[jp]->op == GGML_OP_CPY && !(curv->flags & GGML_TENSOR_FLAG_OUTPUT)) {
-            const ggml_tensor* c = g->nodes[jc];
-            const ggml_tensor* cp = g->nodes[jp];
-            const ggml_tensor* pv = c->src[0];                      // the permuted view of the projection
-            const int64_t Mf = mm->ne[0], L = mm->ne[1], Bn = mm->ne[2];
-            bool ok = c->type == GGML_TYPE_F32 && ggml_is_contiguous(c) && single_use(fs, c) && (c->flags & GGML_TENSOR_FLAG_COMPUTE) &&
-                      (cp->flags & GGML_TENSOR_FLAG_COMPUTE) && pv->type == GGML_TYPE_F32 && pv->data == curv->data && ggml_are_same_shape(pv, c);
-            // views between the projection and the CONT: one consumer each (nobody else reads the f32 projection)
-            if (ok) {
-                const ggml_tensor* v = pv;
-                int depth = 0;
-                while (v != curv && depth++ < 6) {
-                    if (!is_view_op(v) || !v->src[0] || !single_use(fs, v) || v->data != curv->data) { ok = false; break; }
-                    v = v->src[0];
-                }
-                ok = ok && v == curv && single_use(fs, curv);
-            }
-            // geometry: pv = [d, L, H, B] over rows of Mf = H * d features
-            const int64_t d = ok ? pv->ne[0] : 0, H = ok ? pv->ne[2] : 0;
-            ok = ok && d > 0 && d * H == Mf && pv->ne[1] == L && pv->ne[3] == Bn && pv->nb[0] == 4 && pv->nb[2] == (size_t)d * 4 &&
-                 pv->nb[1] == (size_t)Mf * 4 && (Bn == 1 || pv->nb[3] == (size_t)Mf * L * 4) && d % 8 == 0 && d <= 192;
-            const ggml_tensor* cd = ok ? cp->src[1] : nullptr;     // the cast's destination
-            ok = ok && cd && cd->type == GGML_TYPE_F16 && ggml_is_contiguous(cd) && cd->ne[0] == d && cd->ne[1] == L && ggml_nelements(cd) == ggml_nelements(c) &&
-                 order_preserving_view_of(fs, cp->src[0], c) && (cp->src[0] == c || single_use(fs, cp->src[0])) && single_use(fs, cp);
-            // its one reader: the K or V operand of an attention node the fused kernel will take (no mask, no ALiBi, d == dv)
-            const ggml_tensor* fa = nullptr;
-            if (ok) {
-                for (int j = jp + 1; j < g->n_nodes && j < jp + 32; ++j) {
-                    const ggml_tensor* t = g->nodes[j];
-                    if (t->op == GGML_OP_FLASH_ATTN_EXT && (t->src[1] == cp || t->src[2] == cp)) { fa = t; break; }
-                }
-                ok = fa != nullptr && fa->src[1] != fa->src[2] && !fa->src[3];
-            }
-            if (ok) {
-                float max_bias;
-                memcpy(&max_bias, (const float*)fa->op_params + 1, sizeof(float));
-                const ggml_tensor* fq = fa->src[0];
-                ok = max_bias == 0.0f && fq->type == GGML_TYPE_F32 && fq->ne[0] == d && fa->src[1]->ne[0] == d && fa->src[2]->ne[0] == d &&
-                     fa->src[1]->type == GGML_TYPE_F16 && fa->src[2]->type == GGML_TYPE_F16 && fq->ne[3] == 1 && fq->ne[2] % Bn == 0 &&
-                     (fq->ne[2] / Bn) % H == 0;
-            }
-            if (ok) {
-                void* sh = ws_alloc(ctx, (size_t)ggml_nelements(c) * 2);
-                if (sh) {
-                    fz.d16 = sh; fz.d16_type = GGML_TYPE_F16; fz.skip_f32 = true; fz.d16_done = &kv_done;
-                    kv_cont = jc; kv_cpy = jp; kv_cp = cp;
-                    b200_td td;
-                    td.data = sh; td.type = GGML_TYPE_F16;
-                    td.ne[0] = d; td.ne[1] = L; td.ne[2] = H; td.ne[3] = Bn;
-                    td.nb[0] = 2; td.nb[1] = (size_t)Mf * 2; td.nb[2] = (size_t)d * 2; td.nb[3] = (size_t)Mf * L * 2;
-                    kvd.td = td; kvd.cast_dst = cd;
-                }
+        kv_match km;
+        if (match_kv_projection(ctx, g, fs, mm, curv, chain.empty() ? i : chain.back(), &km)) {
+            void* sh = ws_alloc(ctx, (size_t)ggml_nelements(mm) * 2);
+            if (sh) {
+                fz.d16 = sh; fz.d16_type = GGML_TYPE_F16; fz.skip_f32 = true; fz.d16_done = &kv_done;
+                kv_cont = km.jc; kv_cpy = km.jp; kv_cp = km.cp;
+                b200_td td;
+                td.data = sh; td.type = GGML_TYPE_F16;
+                td.ne[0] = km.d; td.ne[1] = km.L; td.ne[2] = km.H; td.ne[3] = km.B;
+                td.nb[0] = 2; td.nb[1] = km.d * km.H * 2; td.nb[2] = km.d * 2; td.nb[3] = km.d * km.H * km.L * 2;
+                kvd.td = td; kvd.cast_dst = km.cast_dst;
             }
         }
     }
+    if (side_only && !kv_cp) return -2;          // launched ahead of its turn on a side stream: only as an in-place K / V projection
+    fz.d16_strict = side_only;
     // gated residual of the DiT blocks: x + gate * Linear(y) (flux.hpp:330-400 DoubleStreamBlock, :470-500 SingleStreamBlock; mmdit, wan):
     // ... -> MUL(value, gate [M,1,1,1]) -> ADD(x, .).  Both steps in the epilogue, each rounded like the node it replaces.
     static int gate_enabled = -1;
@@ -1975,6 +2024,9 @@ static int try_skip_q_cont(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, 
     for (int j = i + 1; j <= jf; ++j) {
         const ggml_tensor* t = g->nodes[j];
         if (is_view_op(t) || ggml_is_empty(t)) continue;
+        // nodes ahead of this one that are already done are the layer's in-place K / V projections (launched on the side streams beside
+        // the Q projection) and their CONT / CPY chains: they wrote workspace only, the allocator's placement of their tensors is moot
+        if (fs.done[j]) continue;
         if (tensors_overlap(t->data, ggml_nbytes(t), lo, nb)) return -2;
         if (t->op == GGML_OP_CPY && t->src[1] && tensors_overlap(t->src[1]->data, ggml_nbytes(t->src[1]), lo, nb)) return -2;
     }
@@ -2277,9 +2329,73 @@ static int try_fuse_conv(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, in
     return n;
 }
 
+// ------------------------------------------------------------------------------------------------
+// side streams.  An in-place K / V projection (match_kv_projection) writes nothing but workspace, so it may run as soon as its input
+// exists -- beside the Q projection of its attention layer, or, when its input is an INPUT of the graph (the text context), at the
+// very start of the graph beside conv_in and the first ResBlocks.  These GEMMs are fixed-cost bound (7 us for 0.04 GFLOP: 154 context
+// rows) and use a handful of SMs; in line they cost the UNet 64 x 4..7 us per forward.
+// ------------------------------------------------------------------------------------------------
+static int launch_kv_on_side(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int j, int which, uint64_t* nodes) {
+    cudaStream_t main_stream = ctx->stream, ss = ctx->side[which];
+    if (!ss) return -2;
+    if (ctx->capturing && ctx->ev_pool.size() - ctx->ev_next < 4) return -2;
+    cudaEvent_t ef = side_event(ctx), ed = side_event(ctx);
+    if (!ef || !ed) return -2;
+    cudaEventRecord(ef, main_stream);
+    cudaStreamWaitEvent(ss, ef, 0);
+    ctx->stream = ss;
+    ctx->on_side = true;
+    int cov = 0;
+    const int n = try_fuse_mul_mat(ctx, g, fs, j, &cov, nullptr, 0, true);
+    ctx->stream = main_stream;
+    ctx->on_side = false;
+    cudaEventRecord(ed, ss);
+    if (n < 0) {                                   // declined: nothing of the node itself was launched; it runs in its turn
+        cudaStreamWaitEvent(main_stream, ed, 0);
+        return -2;
+    }
+    fs.done[j] = 1;
+    fs.pend.push_back(fusion_state::side_job{j, ed});
+    ctx->stats.fused_nodes += (uint64_t)cov;
+    ctx->stats.side_launches += 1;
+    *nodes += (uint64_t)cov + 1;
+    return n;
+}
+
+static inline const ggml_tensor* base_tensor(const ggml_tensor* t) {
+    while (t->view_src) t = t->view_src;
+    return t;
+}
+
+// projections of graph inputs: every MUL_MAT whose activation is (a view of) a leaf that no node of this graph writes
+static void hoist_input_projections(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, uint64_t* launches, uint64_t* nodes) {
+    std::unordered_map<const ggml_tensor*, char> written;
+    bool scanned = false;
+    for (int j = 0; j < g->n_nodes; ++j) {
+        ggml_tensor* mm = g->nodes[j];
+        if (mm->op != GGML_OP_MUL_MAT || fs.done[j] || !(mm->flags & GGML_TENSOR_FLAG_COMPUTE) || !mm->src[1]) continue;
+        const ggml_tensor* root = base_tensor(mm->src[1]);
+        if (root->op != GGML_OP_NONE || !root->data || root->type != GGML_TYPE_F32) continue;
+        kv_match km;
+        if (!match_kv_projection(ctx, g, fs, mm, mm, j, &km)) continue;
+        if (!scanned) {
+            for (int k = 0; k < g->n_nodes; ++k) {
+                const ggml_tensor* t = g->nodes[k];
+                if (t->view_src && !is_view_op(t)) written[base_tensor(t)] = 1;         // CPY destinations, in-place ops
+            }
+            scanned = true;
+        }
+        if (written.count(root)) continue;
+        const int n = launch_kv_on_side(ctx, g, fs, j, 2, nodes);
+        if (n > 0) *launches += (uint64_t)n;
+    }
+}
+
 static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, uint64_t* launches, uint64_t* nodes) {
     fusion_state fs;
     ctx->pack_cache.clear();
+    ctx->pack_origins.clear();
+    ctx->ev_next = 0;
     ctx->launched_any = false;
     ctx->peer_out = nullptr;
     ctx->peer_fused = false;
@@ -2295,14 +2411,43 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
     const bool fuse = ctx->opt_fusion && cgraph->n_nodes > 1;
     if (fuse) count_uses(cgraph, fs);
     else fs.done.assign((size_t)cgraph->n_nodes, 0);
+    const bool side_on = fuse && ctx->opt_side_streams && ctx->opt_chain_fusion && !ctx->opt_kernel_timing && ctx->side[0] && ctx->side[1] && ctx->side[2];
+    if (side_on) hoist_input_projections(ctx, cgraph, fs, launches, nodes);
     for (int i = 0; i < cgraph->n_nodes; ++i) {
         ggml_tensor* t = cgraph->nodes[i];
         if (fs.done[i]) continue;
         if (node_is_noop(t)) continue;
         if ((t->flags & GGML_TENSOR_FLAG_COMPUTE) == 0) continue;
+        // side-stream work whose position in the graph lies before this node must be complete: from here on the allocator may have
+        // handed its inputs' memory to somebody else, and its consumer (the attention node) comes after it
+        for (size_t k = 0; k < fs.pend.size();) {
+            if (fs.pend[k].pos < i) { cudaStreamWaitEvent(ctx->stream, fs.pend[k].done, 0); fs.pend[k] = fs.pend.back(); fs.pend.pop_back(); }
+            else ++k;
+        }
         int n = -2;
         if (fuse) {
             int covered = 0;
+            if (t->op == GGML_OP_MUL_MAT && side_on) {
+                // Q projection at hand: its sibling K / V projections (same activation operand, in-place candidates) start now on the side streams
+                int which = 0;
+                bool packed = false;
+                for (int j = i + 1; j < cgraph->n_nodes && j <= i + 24 && which < 2; ++j) {
+                    ggml_tensor* nj = cgraph->nodes[j];
+                    if (nj->op == GGML_OP_FLASH_ATTN_EXT) break;
+                    if (fs.done[j] || nj->op != GGML_OP_MUL_MAT || nj->src[1] != t->src[1] || !(nj->flags & GGML_TENSOR_FLAG_COMPUTE)) continue;
+                    kv_match km;
+                    if (!match_kv_projection(ctx, cgraph, fs, nj, nj, j, &km)) continue;
+                    if (!packed) {             // the shared activation operand is packed once, on the main stream, before the fork
+                        operand tmp;
+                        int l = 0;
+                        if (!prepare_operand(ctx, nj->src[1], GGML_TYPE_F16, &tmp, &l)) break;
+                        *launches += (uint64_t)l;
+                        packed = true;
+                    }
+                    const int r = launch_kv_on_side(ctx, cgraph, fs, j, which, nodes);
+                    if (r >= 0) { *launches += (uint64_t)r; ++which; }
+                }
+            }
             if (t->op == GGML_OP_MUL_MAT) n = try_fuse_mul_mat(ctx, cgraph, fs, i, &covered);
             else if (t->op == GGML_OP_GROUP_NORM || t->op == GGML_OP_NORM) {
                 n = try_fuse_norm(ctx, cgraph, fs, i, &covered);
@@ -2342,6 +2487,7 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
         if (n == -2) n = run_node(ctx, t);
         if (n < 0) {
             GGML_LOG_ERROR("ggml-b200: node %d (%s, %s) is not executable on this backend\n", i, ggml_op_name(t->op), t->name);
+            for (auto& pj : fs.pend) cudaStreamWaitEvent(ctx->stream, pj.done, 0);
             return GGML_STATUS_FAILED;
         }
         *launches += (uint64_t)n;
@@ -2356,6 +2502,15 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
             }
         }
 #endif
+    }
+    for (auto& pj : fs.pend) cudaStreamWaitEvent(ctx->stream, pj.done, 0);      // every side branch joins before the graph ends
+    fs.pend.clear();
+    if (!ctx->capturing && side_on) {       // head-room for the capture of this same graph (no event may be created while capturing)
+        while (ctx->ev_pool.size() < ctx->ev_next + 8) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); break; }
+            ctx->ev_pool.push_back(e);
+        }
     }
     if (ctx->peer_out) {
         auto& pr = ctx->peer;
@@ -2454,6 +2609,7 @@ static void stats_add(b200_stats& dst, const b200_stats& a, const b200_stats& b)
     dst.tc_gemm_launches += a.tc_gemm_launches - b.tc_gemm_launches;
     for (int i = 2; i < 8; ++i) if (i != 3) dst.reserved[i] += a.reserved[i] - b.reserved[i];
     for (int i = 0; i < 16; ++i) if (i != 1 && i != 2 && i != 6) dst.ext[i] += a.ext[i] - b.ext[i];
+    dst.side_launches += a.side_launches - b.side_launches;
 }
 
 enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {

@@ -86,6 +86,16 @@ struct b200_context {
     bool peer_fused = false;            // ... and its producer has already stored it there (fused epilogue)
     bool graph_pushed = false;          // the graph executed last contained a push
     unsigned* gn_counters = nullptr;   // B200_GN_COUNTERS zeroed counters of the chunked GroupNorm statistics (self-resetting)
+    // side streams: in-place K / V projections (workspace-only results) run beside the main stream -- [0], [1] the two projections of the
+    // attention layer at hand while the main stream computes Q, [2] projections of graph INPUTS (the text context: 2 x 16 cross-attention
+    // layers of the SD1.5 UNet) hoisted to the start of the graph.  Fork / join by events; inside a capture they become graph branches.
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_next = 0;
+    bool opt_side_streams = true;
+    bool on_side = false;              // launches currently go to a side stream (ctx->stream is swapped)
+    struct pack_origin { cudaStream_t stream; cudaEvent_t ready; };
+    std::unordered_map<std::pair<const ggml_tensor*, int>, pack_origin, b200_pack_key_hash> pack_origins;   // packed operands produced on a side stream
     bool capturing = false, capture_overflow = false;
     bool launched_any = false;        // a kernel of the current graph execution has been launched
 

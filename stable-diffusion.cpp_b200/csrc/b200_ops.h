@@ -90,6 +90,8 @@ struct b200_gemm_args {
     int         d16_type;   // GGML_TYPE_F16 | GGML_TYPE_BF16
     int         skip_f32;
     int*        d16_done;
+    int         d16_strict; // return -1 WITHOUT launching when the 16-bit copy cannot be written (the caller depends on it: a projection run ahead
+                            // of its turn on a side stream must not touch its f32 tensor, whose memory still belongs to somebody else)
 };
 // returns kernels launched, or -1 if the shape/alignment is not supported by the TMA path (caller falls back)
 int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g, void* workspace, size_t workspace_bytes);

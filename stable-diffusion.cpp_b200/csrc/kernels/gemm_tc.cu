@@ -602,7 +602,8 @@ int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     kp.trace = (unsigned long long*)g.trace;
     if (g.D16 && !g.residual && g.act == 0 && (g.d16_type == GGML_TYPE_F16 || g.d16_type == GGML_TYPE_BF16) && !((uintptr_t)g.D16 & 1)) {
         kp.D16 = g.D16; kp.d16_bf16 = g.d16_type == GGML_TYPE_BF16; kp.skip_f32 = g.skip_f32;
-        if (g.d16_done) *g.d16_done = 1;
+    } else if (g.D16 && g.d16_strict) {
+        return -1;
     }
     const int64_t mt = (g.M + BM - 1) / BM, nt = (g.N + pl.bn - 1) / pl.bn;
     if (mt > 0x7fffffff || nt > 65535 || g.batch * pl.splits > 65535) return -1;
@@ -625,6 +626,7 @@ int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_
         fprintf(stderr, "[ggml-b200] tcgen05 GEMM launch failed: %s\n", cudaGetErrorString(e));
         return -1;
     }
+    if (kp.D16 && g.d16_done) *g.d16_done = 1;
     return 1;
 }
 

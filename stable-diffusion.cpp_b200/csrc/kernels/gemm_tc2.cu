@@ -686,7 +686,8 @@ int b200_launch_gemm_tc2(cudaStream_t s, const b200_device_info& dev, const b200
     const bool d16_split_ok = splits > 1 && !g.residual && !(kp.M & 3) && !(kp.ldd & 3) && !(kp.d_batch_stride & 3) && !((uintptr_t)kp.D & 15);
     if (g.D16 && (kp.vec_epi || d16_split_ok) && !((uintptr_t)g.D16 & 7) && (g.d16_type == GGML_TYPE_F16 || g.d16_type == GGML_TYPE_BF16)) {
         kp.D16 = g.D16; kp.d16_bf16 = g.d16_type == GGML_TYPE_BF16; kp.skip_f32 = g.skip_f32;
-        if (g.d16_done) *g.d16_done = 1;
+    } else if (g.D16 && g.d16_strict) {
+        return -1;          // the one-CTA kernel may still take it
     }
     CUtensorMap td;
     encode_output(&td, kp, g.batch);
@@ -696,6 +697,7 @@ int b200_launch_gemm_tc2(cudaStream_t s, const b200_device_info& dev, const b200
         cudaGetLastError();
         return -1;
     }
+    if (kp.D16 && g.d16_done) *g.d16_done = 1;
     return 1;
 }
 

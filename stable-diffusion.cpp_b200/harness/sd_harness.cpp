@@ -852,11 +852,12 @@ int sdh_model_backend_stats(sdh_model* m, double* out, int n) {
     typedef int (*get_stats_t)(ggml_backend_t, void*);
     get_stats_t fn = reg ? (get_stats_t)ggml_backend_reg_get_proc_address(reg, "ggml_backend_b200_get_stats") : nullptr;
     if (!fn) return fail("backend has no ggml_backend_b200_get_stats");
-    struct { uint64_t graphs, launches, nodes, fused; double last_ms, total_ms; uint64_t tc, reserved[8], ext[16]; } s;
+    struct { uint64_t graphs, launches, nodes, fused; double last_ms, total_ms; uint64_t tc, reserved[8], ext[16], side; } s;
     if (fn(m->backend, &s) != 0) return fail("get_stats failed");
     double v[32] = {(double)s.graphs, (double)s.launches, (double)s.nodes, (double)s.fused, s.last_ms, s.total_ms, (double)s.tc,
                     (double)s.reserved[0], (double)s.reserved[1], (double)s.reserved[2], (double)s.reserved[3], (double)s.reserved[4],
                     (double)s.reserved[5], (double)s.reserved[6], (double)s.reserved[7], 0};
+    v[15] = (double)s.side;
     for (int i = 0; i < 16; ++i) v[16 + i] = (double)s.ext[i];
     for (int i = 0; i < n && i < 32; ++i) out[i] = v[i];
     return 0;

@@ -141,9 +141,13 @@ def test_producer_side_fusions_are_bit_identical(b200, arch, shape, cshape):
     outs = [m.forward(x, t, ctx)[0] for _ in range(3)]            # eager, capture, replay
     st = m.stats()
     # every attention layer of the flash-attention graph takes the in-place path (2 projections each) and hands f16 rows to to_out
-    assert st["kv_in_place"] > 0 and st["attn_out_f16_only"] > 0 and st["q_read_in_place"] > 0, st
+    key = {k: st[k] for k in ("fused_attn_launches", "kv_in_place", "attn_out_f16_only", "q_read_in_place", "side_stream_launches")}
+    assert st["kv_in_place"] > 0 and st["attn_out_f16_only"] > 0 and st["q_read_in_place"] > 0, key
     if arch == "sd15_unet":
-        assert st["kv_in_place"] == 2 * st["fused_attn_launches"] and st["attn_out_f16_only"] == st["fused_attn_launches"], st
+        assert st["kv_in_place"] == 2 * st["fused_attn_launches"] and st["attn_out_f16_only"] == st["fused_attn_launches"], key
+        # ... and every one of those projections ran on a side stream (context K / V hoisted to the start of the graph, self-attention
+        # K / V beside the Q projection): inside the captured CUDA graph they are parallel branches
+        assert st["side_stream_launches"] == st["kv_in_place"], key
     m.set_option("chain_fusion", 0)
     m.set_option("early_weights", 0)
     plain = [m.forward(x, t, ctx)[0] for _ in range(2)]
