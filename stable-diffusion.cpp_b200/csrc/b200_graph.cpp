@@ -58,6 +58,7 @@ b200_context* b200_context_create(const b200_device_info& info) {
     ctx->opt_q8_activations = env_flag("GGML_B200_Q8_ACT", 1) != 0;
     ctx->opt_persistent_gemm = env_flag("GGML_B200_PERSISTENT", 0) != 0;   // experimental persistent GEMM (gemm_tc_persist.cu), never run on hardware yet
     ctx->opt_side_streams = env_flag("GGML_B200_SIDE_STREAMS", 1) != 0;
+    ctx->opt_wprefetch = env_flag("GGML_B200_WPREFETCH", 0) != 0;
     ctx->opt_fold_batch = env_flag("GGML_B200_FOLD_BATCH", 0) != 0;   // written at the end of round 1, not yet measured: off by default
     return ctx;
 }
@@ -91,6 +92,7 @@ int b200_context_set_option(b200_context* ctx, const char* key, int value) {
     else if (!strcmp(key, "kernel_timing")) ctx->opt_kernel_timing = value != 0;
     else if (!strcmp(key, "fused_attn")) ctx->opt_fused_attn = value != 0;
     else if (!strcmp(key, "side_streams")) ctx->opt_side_streams = value != 0;
+    else if (!strcmp(key, "wprefetch")) ctx->opt_wprefetch = value != 0;
     else if (!strcmp(key, "implicit_conv")) ctx->opt_implicit_conv = value != 0;
     else if (!strcmp(key, "early_weights")) ctx->opt_early_weights = value != 0;
     else if (!strcmp(key, "chain_fusion")) ctx->opt_chain_fusion = value != 0;
@@ -484,6 +486,10 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
         if (ctx->opt_early_weights && a.ptr == src0->data && src0->buffer && src0->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS &&
             (ctx->launched_any || launches > 0))
             g.early = 1;
+        // (in place or a derived copy made at upload: constant either way, unless this very graph stores into weights -- LoRA apply)
+        if (ctx->opt_wprefetch && !ctx->graph_writes_weights && src0->buffer && src0->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS &&
+            (a.ptr == src0->data || src0->type == GGML_TYPE_Q8_0) && ne02 * ne03 == 1)
+            g.wprefetch = 1;
         int n = launch_tc(ctx, g);
         if (n < 0) {
             if (fz && fz->d16_strict) return -2;             // declined before anything was launched: the caller runs the node in its turn
@@ -1707,6 +1713,7 @@ static int emit_conv(b200_context* ctx, const conv_match& m, const conv_prologue
     c.dil = m.dil; c.pad = c.dil * (c.KH - 1) / 2;
     c.D = m.out; c.bias = m.bias; c.residual = m.residual;
     c.w_const = (ctx->opt_early_weights && !w_fresh) ? 1 : 0;     // at least the NHWC transform precedes this launch in the graph
+    c.w_prefetch = (ctx->opt_wprefetch && !w_fresh && !ctx->graph_writes_weights && m.w->buffer && m.w->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS) ? 1 : 0;
     const bool want_peer = ctx->peer.connected && ctx->peer_out && (const void*)m.out == ctx->peer_out && N == 1;
     if (want_peer) {       // compute + collective in one kernel: the epilogue also stores into the peer GPU's mailbox
         c.D2 = (float*)ctx->peer.remote;
@@ -2637,6 +2644,7 @@ enum ggml_status b200_graph_compute(b200_context* ctx, ggml_cgraph* cgraph) {
     std::vector<weight_write> writes;
     std::vector<uint64_t>& sig = ctx->sig_scratch;
     const uint64_t key = graph_signature(cgraph, sig, &writes);
+    ctx->graph_writes_weights = !writes.empty();
     if (!writes.empty()) {
         // this graph modifies model weights in place: derived copies (packed conv filters, dequantised Q8_0) of those ranges are stale
         // after it -- and, for consumers later in this same graph, from the write on.  Drop them now (consumers repack in stream order)

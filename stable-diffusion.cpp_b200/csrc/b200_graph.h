@@ -93,6 +93,8 @@ struct b200_context {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_next = 0;
     bool opt_side_streams = true;
+    bool opt_wprefetch = false;        // GEMM / conv CTAs request their constant weight slab from L2 before the PDL wait (b200_gemm_args::wprefetch)
+    bool graph_writes_weights = false; // the graph being executed stores into a WEIGHTS buffer: nothing in it is treated as a constant
     bool on_side = false;              // launches currently go to a side stream (ctx->stream is swapped)
     struct pack_origin { cudaStream_t stream; cudaEvent_t ready; };
     std::unordered_map<std::pair<const ggml_tensor*, int>, pack_origin, b200_pack_key_hash> pack_origins;   // packed operands produced on a side stream

@@ -81,6 +81,9 @@ struct b200_gemm_args {
                             // (x + gate * Linear(y): flux.hpp DoubleStreamBlock / SingleStreamBlock); product and sum rounded separately
     int         act;        // 0 none, 1 SiLU, 2 GELU(tanh)
     int         early;      // bit 0: A, bit 1: B is a constant (weight) operand no kernel of this graph writes -> may be fetched before the PDL wait
+    int         wprefetch;  // bit 0: A, bit 1: B is a constant weight operand (batch 1): every CTA requests the whole slab of weight rows it will
+                            // stage (its rows x its K range) from L2 with cp.async.bulk.prefetch.L2 BEFORE the PDL wait, so the HBM latency of a
+                            // weight stream that is read exactly once per forward is paid up front instead of per ring slot (option wprefetch)
     void*       trace;      // optional device buffer of 8 uint64: phase timestamps of CTA (0,0,0) (tools/gemm_bench)
     // optional 16-bit copy of the result (same [N][M] element layout, ldd / d_batch_stride in elements): the K-major operand of the
     // contraction that consumes it, rounded exactly like its operand pack would.  Honoured by the CTA-pair kernel's staged epilogue only:
@@ -127,6 +130,7 @@ struct b200_conv_args {
     const float* bias;      // per OC or null
     const float* residual;  // same layout as D or null
     int w_const;            // w_packed was not produced by a kernel of this graph execution (may be fetched before the PDL wait)
+    int w_prefetch;         // request each CTA's filter slab from L2 up front (see b200_gemm_args::wprefetch); implies w_const
     // optional second destination over NVLink (kernels/peer.cu): every output element is also stored at
     // D2 + ((*d2_seq + 1) & 1) * d2_slot_floats + (its offset in D).  Honoured by the CTA-pair kernel only (launcher returns 2).
     float* D2;

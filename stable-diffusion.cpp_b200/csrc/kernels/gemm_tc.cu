@@ -59,6 +59,9 @@ struct GemmKParams {
     int conv_cblocks;  // IC / 64
     int conv_pad, conv_dil;
     int early;         // operands that may be fetched before griddepcontrol.wait (bit 0 = A, bit 1 = B): constant weights
+    const char* wpf;   // weight operand to request from L2 up front (b200_gemm_args::wprefetch), null: off
+    int64_t wpf_ld, wpf_rows, wpf_kbytes;
+    int wpf_is_a;
     // optional 16-bit copy of the result, D's element layout (b200_gemm_args::D16): no residual, no activation on this kernel
     void* D16;
     int d16_bf16, skip_f32;
@@ -164,6 +167,16 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(const __grid_constant__ CUte
             if (which & 2) tma_load_4d(sb, &tmB, &full_bar[s], k, n0, i2, i3);
         }
     };
+    if (p.wpf) {
+        // constant weights: request this CTA's slab (its rows, its K range) from L2 before the predecessor kernel has finished
+        const int row0 = p.wpf_is_a ? m0 : n0;
+        const int nrows = p.wpf_is_a ? BM : BN;
+        const int64_t koff = (int64_t)kb0 * BK_BYTES;
+        const int64_t kbytes = min((int64_t)nkb * BK_BYTES, p.wpf_kbytes - koff) & ~(int64_t)15;
+        if (kbytes > 0)
+            for (int r = threadIdx.x; r < nrows; r += 192)
+                if (row0 + r < p.wpf_rows) l2_prefetch_bulk(p.wpf + (int64_t)(row0 + r) * p.wpf_ld + koff, (unsigned)kbytes);
+    }
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
         const int pre = p.early ? min(nkb, C::STAGES) : 0;
@@ -598,6 +611,8 @@ int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     kp.residual = g.residual; kp.ldr = g.ldr; kp.r_batch_stride = g.d_batch_stride;
     kp.act = g.act;
     kp.gate = g.gate;
+    if ((g.wprefetch & 1) && a_batches == 1) { kp.wpf = (const char*)g.A; kp.wpf_ld = g.lda * es; kp.wpf_rows = g.M; kp.wpf_kbytes = g.K * es; kp.wpf_is_a = 1; }
+    else if ((g.wprefetch & 2) && g.batch == 1) { kp.wpf = (const char*)g.B; kp.wpf_ld = g.ldb * es; kp.wpf_rows = g.N; kp.wpf_kbytes = g.K * es; kp.wpf_is_a = 0; }
     kp.early = g.early & 3;
     kp.trace = (unsigned long long*)g.trace;
     if (g.D16 && !g.residual && g.act == 0 && (g.d16_type == GGML_TYPE_F16 || g.d16_type == GGML_TYPE_BF16) && !((uintptr_t)g.D16 & 1)) {
@@ -695,6 +710,7 @@ int b200_launch_conv_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     kp.num_k_blocks = nkb;
     kp.splits = pl.splits;
     kp.ne12 = (int)c.N; kp.r2 = 1; kp.r3 = 1;
+    if (c.w_prefetch) { kp.wpf = (const char*)c.w_packed; kp.wpf_ld = g.K * 2; kp.wpf_rows = c.OC; kp.wpf_kbytes = g.K * 2; kp.wpf_is_a = 0; }
     kp.bias = c.bias; kp.bias_mode = c.bias ? 2 : 0;
     kp.residual = c.residual; kp.ldr = c.H * c.W; kp.r_batch_stride = c.OC * c.H * c.W;
     kp.act = 0;

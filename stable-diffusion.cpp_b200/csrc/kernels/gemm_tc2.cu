@@ -63,6 +63,9 @@ struct G2Params {
     int conv, conv_W, conv_KW, conv_cblocks, conv_pad, conv_dil;
     void* D16;                // optional 16-bit copy of the result (operand of the next contraction), same element layout as D
     int d16_bf16, skip_f32;
+    const char* wpf;          // weight operand to request from L2 up front (null: off): row-major [wpf_rows][wpf_kbytes], stride wpf_ld bytes
+    int64_t wpf_ld, wpf_rows, wpf_kbytes;
+    int wpf_is_a;             // the weights are the A operand (Linear) / the B operand (conv filter)
     float* D2;                // optional mirror of D in the PEER GPU's memory (NVLink mapping, kernels/peer.cu); slot chosen by *d2_seq
     const unsigned* d2_seq;
     int64_t d2_slot;
@@ -154,8 +157,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
     cluster_sync_all();           // barriers of every CTA of the cluster are initialised before anyone signals them remotely
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
-    pdl_wait();
-    pdl_launch_dependents();
 
     // tile -> (pair m tile, n tile, batch): m fastest, so the pairs running at one time share the B tile in L2
     auto decode = [&](int t, int& m0, int& n0, int& batch) {
@@ -166,6 +167,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
         m0 = mt * (2 * BM) + (int)prank * BM;      // this CTA's 128 rows
         n0 = nt * p.bn;                            // first column of the pair's tile
     };
+    if (p.wpf && pair < p.total_tiles) {
+        // constant weights: the slab this CTA stages for its first tile (its rows, its K range) is requested from L2 now, before the
+        // predecessor kernel has finished -- one bulk prefetch per row segment, spread over the CTA's threads
+        int m0, n0, batch;
+        decode(pair, m0, n0, batch);
+        const int row0 = p.wpf_is_a ? m0 : n0 + (int)prank * half_bn;
+        const int nrows = p.wpf_is_a ? BM : half_bn;
+        const int64_t koff = (int64_t)kb0 * BK_BYTES;
+        const int64_t kbytes = min((int64_t)nkb * BK_BYTES, p.wpf_kbytes - koff) & ~(int64_t)15;
+        if (kbytes > 0)
+            for (int r = threadIdx.x; r < nrows; r += NTHREADS)
+                if (row0 + r < p.wpf_rows) l2_prefetch_bulk(p.wpf + (int64_t)(row0 + r) * p.wpf_ld + koff, (unsigned)kbytes);
+    }
+    pdl_wait();
+    pdl_launch_dependents();
 
     if (warp == 0 || warp == 10) {
         if (lane == 0 && (warp == 0 || p.nprod == 2)) {
@@ -681,6 +697,8 @@ int b200_launch_gemm_tc2(cudaStream_t s, const b200_device_info& dev, const b200
     kp.residual = g.residual; kp.ldr = g.ldr; kp.r_batch_stride = g.d_batch_stride;
     kp.act = g.act;
     kp.gate = g.gate;
+    if ((g.wprefetch & 1) && a_batches == 1) { kp.wpf = (const char*)g.A; kp.wpf_ld = g.lda * 2; kp.wpf_rows = g.M; kp.wpf_kbytes = g.K * 2; kp.wpf_is_a = 1; }
+    else if ((g.wprefetch & 2) && g.batch == 1) { kp.wpf = (const char*)g.B; kp.wpf_ld = g.ldb * 2; kp.wpf_rows = g.N; kp.wpf_kbytes = g.K * 2; kp.wpf_is_a = 0; }
     kp.vec_epi = vec_epilogue_ok(kp, splits);
     // 16-bit copy: the staged epilogue (splits == 1) or the split-K reduce, both with 8-byte stores of four consecutive rows
     const bool d16_split_ok = splits > 1 && !g.residual && !(kp.M & 3) && !(kp.ldd & 3) && !(kp.d_batch_stride & 3) && !((uintptr_t)kp.D & 15);
@@ -732,6 +750,7 @@ int b200_launch_conv_tc2(cudaStream_t s, const b200_device_info& dev, const b200
     kp.D = c.D; kp.ldd = M; kp.d_batch_stride = c.OC * M;
     kp.M = M; kp.N = c.OC;
     kp.ne12 = (int)c.N; kp.r2 = 1;
+    if (c.w_prefetch) { kp.wpf = (const char*)c.w_packed; kp.wpf_ld = K * 2; kp.wpf_rows = c.OC; kp.wpf_kbytes = K * 2; kp.wpf_is_a = 0; }
     kp.bias = c.bias; kp.bias_mode = c.bias ? 2 : 0;
     kp.residual = c.residual; kp.ldr = M; kp.r_batch_stride = c.OC * M;
     kp.D2 = c.D2; kp.d2_seq = c.d2_seq; kp.d2_slot = c.d2_slot_floats;

@@ -4,6 +4,7 @@
 #include "../csrc/b200_ops.h"
 #include <cuda_fp16.h>
 #include <vector>
+#include <string>
 #include <cstring>
 #include <cmath>
 
@@ -41,6 +42,18 @@ int main(int argc, char** argv) {
         for (auto& v : hb) { x = x * 1664525u + 1013904223u; v = ((int)(x >> 20) % 9 - 4) / 8.0f; }
         cudaMemcpy(bias, hb.data(), 1 << 20, cudaMemcpyHostToDevice);
     }
+    // GEMM_BENCH_COLD=1: the WEIGHT operand of every launch comes from a different copy in a 1 GB pool, so it is read from HBM like the
+    // weights of a real forward (1.7 GB per SD1.5 step, each byte once); activations stay warm.  GEMM_BENCH_PF=1: with the up-front L2
+    // request of each CTA's weight slab (b200_gemm_args::wprefetch).
+    const bool cold = getenv("GEMM_BENCH_COLD") != nullptr;
+    const bool pf = getenv("GEMM_BENCH_PF") != nullptr;
+    const size_t pool_bytes = (size_t)1 << 30;
+    __half* pool = nullptr;
+    if (cold) {
+        if (cudaMalloc(&pool, pool_bytes) != cudaSuccess) { printf("no memory for the cold pool\n"); return 1; }
+        const size_t chunk = std::max(maxA, maxB) * 2;
+        for (size_t off = 0; off < pool_bytes; off += chunk) cudaMemcpy((char*)pool + off, A, std::min(chunk, pool_bytes - off), cudaMemcpyDeviceToDevice);
+    }
     unsigned long long* trace; cudaMalloc(&trace, 64);
     cudaStream_t st; cudaStreamCreate(&st);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -69,7 +82,19 @@ int main(int argc, char** argv) {
     printf("%-34s %8s %8s %8s | %9s %9s\n", "shape", "M", "N", "K", "us", "TFLOP/s");
     const char* only = getenv("GEMM_BENCH_ONLY");      // substring filter on the shape name
     for (auto& s : shapes) {
-        if (only && !strstr(s.name, only)) continue;
+        if (only) {                                    // comma-separated substrings
+            bool hit = false;
+            std::string list(only);
+            size_t pos = 0;
+            while (pos <= list.size()) {
+                const size_t c = list.find(',', pos);
+                const std::string tok = list.substr(pos, c == std::string::npos ? std::string::npos : c - pos);
+                if (!tok.empty() && strstr(s.name, tok.c_str())) hit = true;
+                if (c == std::string::npos) break;
+                pos = c + 1;
+            }
+            if (!hit) continue;
+        }
         b200_gemm_args g; memset(&g, 0, sizeof(g));
         g.A = A; g.B = B; g.type = GGML_TYPE_F16; g.M = s.M; g.N = s.N; g.K = s.K; g.lda = s.K; g.ldb = s.K; g.batch = 1; g.a_bcast = 1;
         g.a_batch_stride = s.M * s.K; g.b_batch_stride = s.N * s.K; g.d_batch_stride = s.M * s.N; g.D = D; g.ldd = s.M; g.bias = bias; g.bias_mode = 1;
@@ -78,6 +103,58 @@ int main(int argc, char** argv) {
         float ms = 0;
         double us = time_graph([&] { b200_launch_gemm_tc(st, dev, g, nullptr, 0); });
         printf("%-34s %8lld %8lld %8lld | %9.2f %9.1f", s.name, (long long)s.M, (long long)s.N, (long long)s.K, us, 2.0 * s.M * s.N * s.K / us * 1e-6);
+        if (cold) {
+            // which operand is the weight matrix: the filter (B) of a conv, the [features][K] matrix (A) of a Linear
+            const bool w_is_b = strstr(s.name, "conv") != nullptr;
+            const size_t wbytes = (size_t)(w_is_b ? s.N : s.M) * s.K * 2;
+            const size_t stride = (wbytes + 4095) & ~(size_t)4095;
+            const int ncopies = (int)std::min<size_t>(pool_bytes / stride, 64);
+            {
+                for (int with_pf = 0; with_pf <= (pf ? 1 : 0); ++with_pf) {
+                    int it = 0;
+                    b200_gemm_args gc = g;
+                    gc.wprefetch = with_pf ? (w_is_b ? 2 : 1) : 0;
+                    const double t = time_graph([&] {
+                        const char* w = (const char*)pool + (size_t)(it++ % ncopies) * stride;
+                        if (w_is_b) gc.B = w; else gc.A = w;
+                        b200_launch_gemm_tc(st, dev, gc, nullptr, 0);
+                    });
+                    printf("\n   one-CTA cold weights%s (%d copies of %.1f MB): %8.2f us %7.1f TFLOP/s  weights at %.0f GB/s", with_pf ? " + L2 slab prefetch" : "", ncopies,
+                           wbytes / 1e6, t, 2.0 * s.M * s.N * s.K / t * 1e-6, wbytes / t * 1e-3);
+                }
+            }
+            // the pair kernel at the plan the dispatcher's model picks for this shape
+            {
+                const int nkb = (int)((s.K + 63) / 64);
+                double bestc = 1e30; int bbn = 0, bsp = 1;
+                const int bns[] = {256, 224, 192, 160, 128, 96, 64, 48, 32};
+                for (int bn : bns) {
+                    if (bn > 32 && s.N <= bn / 2) continue;
+                    const int64_t tiles = ((s.M + 255) / 256) * ((s.N + bn - 1) / bn);
+                    for (int sp = 1; sp <= 4; sp *= 2) {
+                        if (sp > 1 && (tiles * 2 * sp > 148 || nkb / sp < 4)) break;
+                        const double c = b200_gemm_tc2_model(dev, s.M, s.N, 1, nkb, bn, sp);
+                        if (c < bestc) { bestc = c; bbn = bn; bsp = sp; }
+                    }
+                }
+                if (bbn && s.M > 128) {
+                    for (int with_pf = 0; with_pf <= (pf ? 1 : 0); ++with_pf) {
+                        int it = 0;
+                        b200_gemm_args gc = g;
+                        gc.wprefetch = with_pf ? (w_is_b ? 2 : 1) : 0;
+                        const double tw = with_pf ? 0.0 : time_graph([&] { b200_launch_gemm_tc2(st, dev, g, bbn, bsp); });
+                        const double t = time_graph([&] {
+                            const char* w = (const char*)pool + (size_t)(it++ % ncopies) * stride;
+                            if (w_is_b) gc.B = w; else gc.A = w;
+                            b200_launch_gemm_tc2(st, dev, gc, bbn, bsp);
+                        });
+                        if (!with_pf) printf("\n   pair bn %d splits %d warm: %8.2f us", bbn, bsp, tw);
+                        printf("\n   pair bn %d splits %d cold weights%s: %8.2f us %7.1f TFLOP/s  weights at %.0f GB/s", bbn, bsp, with_pf ? " + L2 slab prefetch" : "", t,
+                               2.0 * s.M * s.N * s.K / t * 1e-6, wbytes / t * 1e-3);
+                    }
+                }
+            }
+        }
         // CTA-pair kernel (gemm_tc2.cu) on the same problem: a sweep over (tile N, split-K), each checked element by element against the
         // one-CTA kernel's result
         if (getenv("GEMM_BENCH_PAIR")) {
