@@ -554,6 +554,9 @@ struct fa_fusion {
     const ggml_tensor* out_act = nullptr;
     int out_h = 0, out_b = 0;
     bool out_used = false;
+    // no CONT in between (batch 1: FLASH_ATTN_EXT -> views -> to_out): shadow_act is the projection's operand; out_skip: that projection
+    // is the ONLY reader of the result, so the f32 tensor is not stored
+    bool out_skip = false;
 };
 
 static int run_node(b200_context* ctx, ggml_tensor* t);
@@ -612,7 +615,11 @@ static int op_flash_attn(b200_context* ctx, ggml_tensor* dst, fa_fusion* fz = nu
                 if (!shadow) ok = false;
             } else {
                 dd.ne[1] = Hs; dd.ne[3] = B; dd.nb[3] = dd.nb[1] * (size_t)Hs;
-                if (fz->shadow_act) { shadow = ws_alloc(ctx, (size_t)ggml_nelements(dst) * 2); shadow_for = fz->shadow_act; }
+                if (fz->shadow_act) {
+                    shadow = ws_alloc(ctx, (size_t)ggml_nelements(dst) * 2);
+                    shadow_for = fz->shadow_act;
+                    if (shadow && fz->out_skip) skip_f32 = 1;
+                }
             }
             if (ok && kd.ne[2] == vd.ne[2] && kd.ne[3] == B && vd.ne[3] == B && qd.ne[3] == B) {
                 int n = b200_launch_flash_attn_fused(ctx->stream, qd, kd, nullptr, 0, vd, nullptr, dd, scale, shadow, skip_f32);
@@ -622,7 +629,7 @@ static int op_flash_attn(b200_context* ctx, ggml_tensor* dst, fa_fusion* fz = nu
                         ctx->pack_cache[std::make_pair(shadow_for, (int)GGML_TYPE_F16)] =
                             operand{shadow, GGML_TYPE_F16, shadow_for->ne[0], shadow_for->ne[0] * shadow_for->ne[1], shadow_for->ne[0] * shadow_for->ne[1] * shadow_for->ne[2]};
                     if (fz->q_td) ctx->stats.reserved[5] += 1;
-                    if (skip_f32) { fz->out_used = true; ctx->stats.ext[14] += 1; }
+                    if (skip_f32) { fz->out_used = fz->out_cont != nullptr; ctx->stats.ext[14] += 1; }
                     return launches + n;
                 }
             }
@@ -655,8 +662,10 @@ static int op_flash_attn(b200_context* ctx, ggml_tensor* dst, fa_fusion* fz = nu
         if (mask) mtd = b200_make_td(mask);
         void* shadow = nullptr;
         if (fz && fz->shadow_act) shadow = ws_alloc(ctx, (size_t)ggml_nelements(dst) * 2);
+        const int skip = (shadow && fz->out_skip) ? 1 : 0;
         int n = b200_launch_flash_attn_fused(ctx->stream, fz && fz->q_td ? *fz->q_td : b200_make_td(q), b200_make_td(k), nullptr, 0, b200_make_td(v),
-                                             mask ? &mtd : nullptr, b200_make_td(dst), scale, shadow);
+                                             mask ? &mtd : nullptr, b200_make_td(dst), scale, shadow, skip);
+        if (n > 0 && skip) ctx->stats.ext[14] += 1;
         if (n < 0 && shadow) {
             shadow = nullptr;
             n = b200_launch_flash_attn_fused(ctx->stream, fz && fz->q_td ? *fz->q_td : b200_make_td(q), b200_make_td(k), nullptr, 0, b200_make_td(v),
@@ -2051,12 +2060,22 @@ static int try_fuse_flash_attn(b200_context* ctx, ggml_cgraph* g, fusion_state& 
     auto iv = fs.fa_kv.find(fa->src[2]);
     if (iv != fs.fa_kv.end()) fz.v_td = &iv->second.td;
     if (!(fa->flags & GGML_TENSOR_FLAG_OUTPUT)) fz.shadow_act = next_mm_activation(ctx, g, fs, i, fa);
+    static int out_enabled = -1;
+    if (out_enabled < 0) { const char* e = getenv("GGML_B200_FA_OUT16"); out_enabled = (e && *e) ? atoi(e) : 1; }
+    if (out_enabled && fz.shadow_act && single_use(fs, fa)) {
+        // to_out reads the result directly (through views): when nobody else does and the projection takes the packed f16 rows
+        // (tensor-core path: more than 4 activation rows or batched), the f32 result is never stored
+        const ggml_tensor* act = fz.shadow_act;
+        const int jm = next_node(g, fs, i);
+        const ggml_tensor* mm = jm >= 0 ? g->nodes[jm] : nullptr;
+        if (mm && mm->op == GGML_OP_MUL_MAT && mm->src[1] == act && mm->src[0]->type == GGML_TYPE_F16 && ctx->opt_tc_gemm && ctx->opt_fused_attn &&
+            (act->ne[1] > 4 || act->ne[2] * act->ne[3] > 1) && (act == fa || (single_use(fs, act) && order_preserving_view_of(fs, act, fa))))
+            fz.out_skip = true;
+    }
     // FLASH_ATTN_EXT [d, H*B, Lq] -> VIEW [d, H, Lq, B] -> CONT -> reshape [H*d, Lq, B] -> Linear (to_out, ggml_extend.hpp:1400-1416): when that
     // projection is the only reader and takes its activation as f16 rows anyway, the attention kernel writes exactly those rows and
     // neither the f32 result nor the CONT's copy of it exists
     int jcont = -1;
-    static int out_enabled = -1;
-    if (out_enabled < 0) { const char* e = getenv("GGML_B200_FA_OUT16"); out_enabled = (e && *e) ? atoi(e) : 1; }
     if (out_enabled && !fz.shadow_act && !(fa->flags & GGML_TENSOR_FLAG_OUTPUT) && single_use(fs, fa) && ctx->opt_tc_gemm && ctx->opt_fused_attn) {
         const int jc = next_node(g, fs, i);
         if (jc >= 0 && g->nodes[jc]->op == GGML_OP_CONT) {
