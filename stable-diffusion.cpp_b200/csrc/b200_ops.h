@@ -106,7 +106,8 @@ int b200_launch_gemm_tc_persistent(cudaStream_t s, const b200_device_info& dev, 
 // bn: tile N of the pair (multiple of 16, <= 256), splits: split-K factor inside the cluster (1..4).  1 when launched, -1 when the
 // problem is outside the envelope.  The conv front end is declared after b200_conv_args below.
 int b200_launch_gemm_tc2(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g, int bn, int splits);
-double b200_gemm_tc2_model(const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int nkb, int bn, int splits);
+// a_bytes: bytes of A one CTA stages per 64-wide k-block (16 KB; 20 KB / 3 or 22.5 KB / 9 for the halo-reuse convolution)
+double b200_gemm_tc2_model(const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int nkb, int bn, int splits, double a_bytes = 16384.0);
 
 // Q8_0 blocks (34 bytes: f16 scale + 32 int8, ggml-common.h:251-255) -> f16 rows [rows][K] (K % 32 == 0): the derived weight layout the
 // tensor-core GEMM reads; value = round_f16(float(d) * q), the reference's own dequantisation (ggml-quants.c dequantize_row_q8_0)
@@ -140,7 +141,9 @@ struct b200_conv_args {
 bool b200_conv_tc_supported(int64_t N, int64_t H, int64_t W, int64_t C, int64_t OC, int KH, int KW, int s0, int s1, int p0, int p1, int d0, int d1);
 size_t b200_conv_tc_workspace_bytes(const b200_device_info& dev, const b200_conv_args& c);
 int b200_launch_conv_tc(cudaStream_t s, const b200_device_info& dev, const b200_conv_args& c, void* workspace, size_t workspace_bytes);
-int b200_launch_conv_tc2(cudaStream_t s, const b200_device_info& dev, const b200_conv_args& c, int bn, int splits);
+// halo_taps 3 | 9: 3x3 convolution with the image box staged once per 3 | 9 taps (16 x 8 pixel patches; see gemm_tc2.cu), 0: per-tap boxes
+int b200_launch_conv_tc2(cudaStream_t s, const b200_device_info& dev, const b200_conv_args& c, int bn, int splits, int halo_taps = 0);
+int b200_conv_tc2_halo_taps(int bn, int splits);
 // stats: float2 {mean, rstd} per (image, group)
 // partial / counters (optional): scratch of b200_gn_stats_partial_bytes() and B200_GN_COUNTERS zero-initialised unsigneds owned by the
 // backend instance: large groups are then split over several CTAs (one read of x, deterministic merge by the last CTA)

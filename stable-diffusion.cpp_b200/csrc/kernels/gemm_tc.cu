@@ -541,6 +541,29 @@ Plan2 choose_plan2(const b200_device_info& dev, int64_t M, int64_t N, int64_t ba
     return best;
 }
 
+// halo-reuse convolution (gemm_tc2.cu): same candidates, the image bytes per k-block shrink with the taps a ring stage serves
+struct Plan2H { int bn; int splits; int taps; double cycles; };
+Plan2H choose_plan2_halo(const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int cblocks) {
+    const int sms = dev.sm_count > 0 ? dev.sm_count : 148;
+    Plan2H best{0, 1, 0, 1e30};
+    const int bns[] = {256, 224, 192, 160, 128, 96, 64, 48, 32};
+    const int nkb = 9 * cblocks;
+    for (int bn : bns) {
+        if (bn > 32 && N <= bn / 2) continue;
+        const int64_t tiles = ((M + 255) / 256) * ((N + bn - 1) / bn) * batch;
+        for (int splits = 1; splits <= 4; splits *= 2) {
+            const int taps = b200_conv_tc2_halo_taps(bn, splits);
+            if (!taps) continue;
+            const int nst = taps == 9 ? cblocks : 3 * cblocks;          // ring stages per tile: what split-K divides
+            if (splits > 1 && (tiles * 2 * splits > sms || nst / splits < 2)) break;
+            const double a_bytes = taps == 9 ? 23040.0 / 9.0 : 20480.0 / 3.0;
+            const double t = b200_gemm_tc2_model(dev, M, N, batch, nkb, bn, splits, a_bytes);
+            if (t < best.cycles) best = Plan2H{bn, splits, taps, t};
+        }
+    }
+    return best;
+}
+
 template <int BN, int FMT>
 cudaError_t launch_cfg(cudaStream_t s, dim3 grid, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp) {
     using C = Cfg<BN>;
@@ -677,11 +700,23 @@ int b200_launch_conv_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     // (a peer destination c.D2 does not influence the choice: the serial and the split sampler must run the very same plans to stay
     //  bit-identical; when this launch ends up on the one-CTA kernel the executor pushes the tensor with kernels/peer.cu instead)
     if (gemm2_mode() && g.M > BM && g.M % 128 == 0) {
-        const Plan2 p2 = choose_plan2(dev, g.M, g.N, g.batch, nkb);
+        Plan2 p2 = choose_plan2(dev, g.M, g.N, g.batch, nkb);
+        int taps = 0;
+        static int halo_en = -1;
+        if (halo_en < 0) { const char* e = getenv("GGML_B200_CONV_HALO"); halo_en = (e && *e) ? atoi(e) : 1; }
+        if (halo_en && c.KH == 3 && c.KW == 3 && c.pad == 1 && c.dil == 1 && c.W % 8 == 0 && c.H % 16 == 0) {
+            const Plan2H ph = choose_plan2_halo(dev, g.M, g.N, g.batch, (int)(c.C / 64));
+            if (ph.bn > 0 && (p2.bn <= 0 || ph.cycles < p2.cycles)) { p2 = Plan2{ph.bn, ph.splits, ph.cycles}; taps = ph.taps; }
+        }
         if (p2.bn > 0 && (gemm2_mode() >= 2 || p2.cycles < cycles1)) {
-            const int r = b200_launch_conv_tc2(s, dev, c, p2.bn, p2.splits);
+            int r = b200_launch_conv_tc2(s, dev, c, p2.bn, p2.splits, taps);
+            if (r <= 0 && taps) {          // (outside the halo envelope after all: the per-tap plan)
+                p2 = choose_plan2(dev, g.M, g.N, g.batch, nkb);
+                taps = 0;
+                if (p2.bn > 0 && (gemm2_mode() >= 2 || p2.cycles < cycles1)) r = b200_launch_conv_tc2(s, dev, c, p2.bn, p2.splits, 0);
+            }
             if (r > 0) {
-                if (gemm_log()) fprintf(stderr, "GEMMLOG pair conv M %lld N %lld K %lld batch %lld bn %d splits %d model1 %.0f model2 %.0f\n", (long long)g.M, (long long)g.N, (long long)g.K, (long long)g.batch, p2.bn, p2.splits, cycles1, p2.cycles);
+                if (gemm_log()) fprintf(stderr, "GEMMLOG pair conv M %lld N %lld K %lld batch %lld bn %d splits %d taps %d model1 %.0f model2 %.0f\n", (long long)g.M, (long long)g.N, (long long)g.K, (long long)g.batch, p2.bn, p2.splits, taps, cycles1, p2.cycles);
                 return 2;
             }
         }

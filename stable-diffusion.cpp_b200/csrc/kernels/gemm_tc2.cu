@@ -19,6 +19,13 @@
 //     are reduced through DSMEM in split order (deterministic), as in gemm_tc.cu
 //   * convolution mode: A is the NHWC f16 image read as halo boxes {64 ch, BW, BH} (zero fill = the conv's padding), B the packed
 //     filter; k-block = (tap, 64-channel block)
+//   * convolution with HALO REUSE (3x3, stride 1, pad 1; W % 8 == 0, H % 16 == 0): the per-tap mode above re-stages the image tile nine
+//     times, and the main loop is bound by exactly those bytes (43 B/clk per SM).  Here a CTA's 128 output pixels are a 16 x 8 patch;
+//     ONE box {64 ch, 10, 16 | 18} lands in shared memory as rows of 128 bytes (pixel-major, 128B swizzle) and the MMAs of tap (kh, kw)
+//     read it through a descriptor that starts kw (+ 10 kh) rows into the box with a stride of 10 rows between 8-row groups -- the swizzle
+//     is a function of the shared-memory address, so any 128-byte row may start a group (measured: tools/desc_probe.cu, all 56 variants
+//     exact).  A ring stage holds the box and the filter tiles of its 3 (one kh) or 9 taps; A bytes per k-block drop from 16 KB to
+//     6.7 / 2.5 KB and the loop becomes MMA bound for tile N >= 128
 //
 // Roofline: tensor pipe.  2 * M * N * K flop per launch; algorithmic bytes (M + N) * K * 2 + M * N * 4.
 #include "../b200_ops.h"
@@ -61,6 +68,8 @@ struct G2Params {
     int stage_off;          // byte offset of the two 16 KB staging tiles behind the operand ring
     int nprod;              // TMA producer threads per CTA: 2 (A and B issued by different warps, default) or 1 (A/B of GGML_B200_GEMM2_NPROD)
     int conv, conv_W, conv_KW, conv_cblocks, conv_pad, conv_dil;
+    int halo_taps;          // 0: per-tap boxes; 3 | 9: halo reuse, taps per ring stage (num_k_blocks then counts STAGES: 3 * cblocks | cblocks)
+    int halo_a_bytes;       // bytes of the image box region at the head of a stage (1024-byte multiple); filter tiles follow
     void* D16;                // optional 16-bit copy of the result (operand of the next contraction), same element layout as D
     int d16_bf16, skip_f32;
     const char* wpf;          // weight operand to request from L2 up front (null: off): row-major [wpf_rows][wpf_kbytes], stride wpf_ld bytes
@@ -198,7 +207,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                 decode(t, m0, n0, batch);
                 const int i2 = batch % p.ne12, i3 = batch / p.ne12;
                 const int nb = n0 + (int)prank * half_bn;          // this CTA's half of the B tile
-                const int y0 = p.conv ? m0 / p.conv_W : 0, x0 = p.conv ? m0 - y0 * p.conv_W : 0;
+                int y0 = p.conv ? m0 / p.conv_W : 0, x0 = p.conv ? m0 - y0 * p.conv_W : 0;
+                if (p.halo_taps) {
+                    // 16 x 8 pixel patches in row-major patch order: patch index = m0 / 128
+                    const int tw = p.conv_W >> 3, ti = m0 >> 7;
+                    y0 = (ti / tw) * 16; x0 = (ti % tw) * 8;
+                    const int T = p.halo_taps;
+                    const uint32_t a_bytes = (uint32_t)(10 * (T == 9 ? 18 : 16) * 128), b_bytes = (uint32_t)(T * half_bn * BK_BYTES);
+                    const uint32_t mine = both ? a_bytes + b_bytes : (is_a ? a_bytes : b_bytes);
+                    for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                        const int s = (int)(it % (uint32_t)p.stages);
+                        const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
+                        mbar_wait(&empty_bar[s], ph ^ 1u);
+                        const uint32_t fb = full0 + 8u * (uint32_t)s;
+                        mbar_expect_tx_cluster(fb, mine);
+                        uint8_t* sa = smem + (size_t)s * p.stage_bytes;
+                        const int kh = T == 9 ? 0 : kb / p.conv_cblocks, cb = T == 9 ? kb : kb - kh * p.conv_cblocks;
+                        if (is_a) tma_load_4d_2cta(sa, &tmA, fb, cb * 64, x0 - 1, y0 + (T == 9 ? 0 : kh) - 1, i2);
+                        if (!is_a || both) {
+                            for (int tp = 0; tp < T; ++tp) {
+                                const int tap = T == 9 ? tp : kh * 3 + tp;
+                                tma_load_4d_2cta(sa + p.halo_a_bytes + (size_t)tp * half_bn * BK_BYTES, &tmB, fb, (tap * p.conv_cblocks + cb) * BK, nb, 0, 0);
+                            }
+                        }
+                    }
+                    continue;
+                }
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = (int)(it % (uint32_t)p.stages);
                     const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
@@ -236,10 +270,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t sa = smem_u32(smem + (size_t)s * p.stage_bytes);
-                        const uint64_t da = make_smem_desc_sw128(sa);
-                        const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES);
+                        if (p.halo_taps) {
+                            // the image box is in shared memory once; tap (kh, kw) = the same pixels kw (+ 10 kh) rows further in
+                            const int T = p.halo_taps;
+                            for (int tp = 0; tp < T; ++tp) {
+                                const uint32_t arow = (uint32_t)((T == 9 ? (tp / 3) * 10 : 0) + tp % 3);
+                                const uint64_t da = make_smem_desc_sw128_sbo(sa + arow * 128u, 10u * 128u);
+                                const uint64_t db = make_smem_desc_sw128(sa + (uint32_t)p.halo_a_bytes + (uint32_t)(tp * half_bn * BK_BYTES));
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) mma_f16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                                for (int k = 0; k < BK / UMMA_K; ++k) mma_f16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || tp > 0 || k > 0) ? 1u : 0u);
+                            }
+                        } else {
+                            const uint64_t da = make_smem_desc_sw128(sa);
+                            const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k) mma_f16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        }
                         mma_commit_mc(&empty_bar[s], pair_mask);                       // ring slot reusable in BOTH CTAs
                         if (kb == nkb - 1) mma_commit_mc(&acc_full[buf], pair_mask);   // accumulator complete (both CTAs' epilogues)
                     }
@@ -323,6 +369,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                 const int wq = (warp - 2) & 3;
                 const int64_t mrow = (int64_t)m0 + 4 * lane;
                 const bool rvalid = mrow < p.M;                           // M % 4 == 0 on this path
+                // where this lane's four consecutive rows live inside an image plane: m itself, or -- halo mode, 16 x 8 pixel patches --
+                // four neighbours of one image row
+                int64_t prow = mrow;
+                if (p.halo_taps) {
+                    const int tw = p.conv_W >> 3, ti = m0 >> 7;
+                    prow = (int64_t)((ti / tw) * 16 + (lane >> 1)) * p.conv_W + (ti % tw) * 8 + (lane & 1) * 4;
+                }
                 float4 bm4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.bias_mode == 1 && rvalid) bm4 = *(const float4*)(p.bias + mrow);
                 float4 gm4 = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -344,9 +397,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                             v.x += bm4.x + bn; v.y += bm4.y + bn; v.z += bm4.z + bn; v.w += bm4.w + bn;
                             if (p.act) { v.x = act_fn(v.x, p.act); v.y = act_fn(v.y, p.act); v.z = act_fn(v.z, p.act); v.w = act_fn(v.w, p.act); }
                             if (p.gate) { v.x = __fmul_rn(v.x, gm4.x); v.y = __fmul_rn(v.y, gm4.y); v.z = __fmul_rn(v.z, gm4.z); v.w = __fmul_rn(v.w, gm4.w); }
-                            const int64_t off = (int64_t)(n0 + n) * p.ldd + mrow;
+                            const int64_t off = (int64_t)(n0 + n) * p.ldd + prow;
                             if (Rp) {
-                                const float4 rr = *(const float4*)(Rp + (int64_t)(n0 + n) * p.ldr + mrow);
+                                const float4 rr = *(const float4*)(Rp + (int64_t)(n0 + n) * p.ldr + prow);
                                 v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
                             }
                             if (!p.skip_f32) *(float4*)(Dp + off) = v;
@@ -439,6 +492,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
             decode(pair, m0, n0, batch);
             const int w8 = warp - 2;
             const int64_t mrow = (int64_t)m0 + 4 * lane;
+            int64_t prow = mrow;                  // offset inside the image plane (see the staged epilogue)
+            if (p.halo_taps) {
+                const int tw = p.conv_W >> 3, ti = m0 >> 7;
+                prow = (int64_t)((ti / tw) * 16 + (lane >> 1)) * p.conv_W + (ti % tw) * 8 + (lane & 1) * 4;
+            }
             float* Dp = p.D + (int64_t)batch * p.d_batch_stride;
             const float* Rp = p.residual ? p.residual + (int64_t)batch * p.r_batch_stride : nullptr;
             float4 bm = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -477,9 +535,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                 v.x += bm.x + bn; v.y += bm.y + bn; v.z += bm.z + bn; v.w += bm.w + bn;
                 if (p.act) { v.x = act_fn(v.x, p.act); v.y = act_fn(v.y, p.act); v.z = act_fn(v.z, p.act); v.w = act_fn(v.w, p.act); }
                 if (p.gate) { v.x = __fmul_rn(v.x, gm.x); v.y = __fmul_rn(v.y, gm.y); v.z = __fmul_rn(v.z, gm.z); v.w = __fmul_rn(v.w, gm.w); }
-                float* dst = Dp + n * p.ldd + mrow;
+                float* dst = Dp + n * p.ldd + prow;
                 if (vec_ok && (Rp == nullptr || (((p.ldr & 3) == 0) && ((((uintptr_t)Rp) & 15) == 0)))) {
-                    if (Rp) { const float4 rr = *(const float4*)(Rp + n * p.ldr + mrow); v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
+                    if (Rp) { const float4 rr = *(const float4*)(Rp + n * p.ldr + prow); v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
                     if (!p.skip_f32) *(float4*)dst = v;
                     if (p.D16) {        // (launcher: 8-byte aligned 16-bit rows whenever D16 is set with splits > 1)
                         uint2 h;
@@ -490,7 +548,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                             const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
                             h.x = *(const uint32_t*)&a; h.y = *(const uint32_t*)&b;
                         }
-                        *(uint2*)((uint16_t*)p.D16 + (int64_t)batch * p.d_batch_stride + n * p.ldd + mrow) = h;
+                        *(uint2*)((uint16_t*)p.D16 + (int64_t)batch * p.d_batch_stride + n * p.ldd + prow) = h;
                     }
                     if (p.D2) {
                         if ((d2off & 3) == 0) *(float4*)(dst + d2off) = v;
@@ -501,7 +559,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                         if (mrow + u < p.M) {
-                            const float o = vv[u] + (Rp ? Rp[n * p.ldr + mrow + u] : 0.f);
+                            const float o = vv[u] + (Rp ? Rp[n * p.ldr + prow + u] : 0.f);
                             dst[u] = o;
                             if (p.D2) dst[u + d2off] = o;
                         }
@@ -605,7 +663,10 @@ bool encode_output(CUtensorMap* out, G2Params& kp, int64_t batch) {
 }
 
 // shared by the GEMM and the conv front end: fills the tile geometry for a chosen (bn, splits)
-bool fill_geometry(G2Params& kp, const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int nkb, int bn, int splits, unsigned* ctas, size_t* smem) {
+// halo_taps: 0 = one (A tile, B tile) pair per stage; 3 | 9 = halo-reuse convolution, a stage = the image box + that many filter tiles
+// (nkb then counts stages)
+bool fill_geometry(G2Params& kp, const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int nkb, int bn, int splits, unsigned* ctas, size_t* smem,
+                   int halo_taps = 0) {
     static int nprod = -1;
     if (nprod < 0) { const char* e = getenv("GGML_B200_GEMM2_NPROD"); nprod = (e && *e && atoi(e) == 1) ? 1 : 2; }
     kp.nprod = nprod;
@@ -613,7 +674,9 @@ bool fill_geometry(G2Params& kp, const b200_device_info& dev, int64_t M, int64_t
     kp.bn = bn;
     kp.splits = splits;
     kp.num_k_blocks = nkb;
-    kp.stage_bytes = A_STAGE_BYTES + (bn / 2) * BK_BYTES;
+    kp.halo_taps = halo_taps;
+    kp.halo_a_bytes = halo_taps == 9 ? 23 * 1024 : (halo_taps == 3 ? 20 * 1024 : 0);       // 10 x 18 | 10 x 16 rows of 128 B, rounded to 1 KB
+    kp.stage_bytes = halo_taps ? kp.halo_a_bytes + halo_taps * (bn / 2) * BK_BYTES : A_STAGE_BYTES + (bn / 2) * BK_BYTES;
     const int stage_tiles = splits == 1 ? 2 * 32 * BM * 4 : 0;        // two 16 KB staging tiles of the vectorised epilogue
     int stages = (int)((227 * 1024 - 4096 - stage_tiles) / kp.stage_bytes);
     stages = std::min(stages, MAX_STAGES);
@@ -622,7 +685,7 @@ bool fill_geometry(G2Params& kp, const b200_device_info& dev, int64_t M, int64_t
         while ((size_t)stages * kp.stage_bytes < (size_t)bn * BM * 4) ++stages;
         if ((size_t)stages * kp.stage_bytes + 2048 > 227 * 1024 - 2048 || stages > MAX_STAGES) return false;
     }
-    if (stages < 3) return false;
+    if (stages < (halo_taps == 9 ? 2 : 3)) return false;
     kp.stages = stages;
     int cols = 32;
     while (cols < 2 * bn) cols <<= 1;
@@ -649,13 +712,13 @@ bool fill_geometry(G2Params& kp, const b200_device_info& dev, int64_t M, int64_t
 // the SM's ingest port: one SM takes ~43 B/clk from L2 through TMA whether it runs alone or with 147 others (the "6300 B/clk chip
 // cap" is 148 such ports), so a CTA's main loop costs (bytes it stages) / 43 clk and small problems are won by spreading the operand
 // bytes over as many SMs as possible -- not by bigger tiles.
-double b200_gemm_tc2_model(const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int nkb, int bn, int splits) {
+double b200_gemm_tc2_model(const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int nkb, int bn, int splits, double a_bytes) {
     const int sms = dev.sm_count > 0 ? dev.sm_count : 148;
     const int64_t tm = (M + 255) / 256, tn = (N + bn - 1) / bn;
     const int64_t tiles = tm * tn * batch;
     const double kb = (double)((nkb + splits - 1) / splits);
     const double ingest = 43.0;                                            // B/clk per SM
-    const double bytes = (128.0 + bn / 2.0) * 128.0;
+    const double bytes = a_bytes + bn / 2.0 * 128.0;                       // per k-block and CTA: its A rows (16 KB, less with halo reuse) + half the B tile
     const double kb_cycles = std::max(2.0 * bn, bytes / ingest);           // cta_group::2: bn / 2 clk per K = 16 MMA, four per k-block
     const double epi = 18.0 * bn + 600.0;                                  // eight epilogue warps: TMEM -> registers -> coalesced f32 stores
     if (splits == 1) {
@@ -719,21 +782,46 @@ int b200_launch_gemm_tc2(cudaStream_t s, const b200_device_info& dev, const b200
     return 1;
 }
 
-int b200_launch_conv_tc2(cudaStream_t s, const b200_device_info& dev, const b200_conv_args& c, int bn, int splits) {
+// taps per ring stage the halo-reuse convolution would use for (bn, splits): 9 (whole 3x3 neighbourhood from one box) when two such
+// stages fit the shared memory, else 3 (one filter row per box), 0 when neither fits
+int b200_conv_tc2_halo_taps(int bn, int splits) {
+    if (bn < 16 || bn > 256 || (bn & 15)) return 0;
+    const int stage_tiles = splits == 1 ? 2 * 32 * BM * 4 : 0;
+    const int avail = 227 * 1024 - 4096 - stage_tiles;
+    auto fits = [&](int taps, int min_stages) {
+        const int sb = (taps == 9 ? 23 * 1024 : 20 * 1024) + taps * (bn / 2) * BK_BYTES;
+        int stages = std::min(avail / sb, MAX_STAGES);
+        if (splits > 1) {
+            while ((size_t)stages * sb < (size_t)bn * BM * 4) ++stages;
+            if ((size_t)stages * sb + 2048 > 227 * 1024 - 2048 || stages > MAX_STAGES) return false;
+        }
+        return stages >= min_stages;
+    };
+    if (fits(9, 2)) return 9;
+    if (fits(3, 3)) return 3;
+    return 0;
+}
+
+int b200_launch_conv_tc2(cudaStream_t s, const b200_device_info& dev, const b200_conv_args& c, int bn, int splits, int halo_taps) {
     if (!b200_conv_tc_supported(c.N, c.H, c.W, c.C, c.OC, c.KH, c.KW, 1, 1, c.pad, c.pad, c.dil, c.dil)) return -1;
     if (((uintptr_t)c.x_nhwc & 15) || ((uintptr_t)c.w_packed & 15)) return -1;
     if (bn < 16 || bn > 256 || (bn & 15) || splits < 1 || splits > 4) return -1;
     const int64_t M = c.H * c.W, K = (int64_t)c.KH * c.KW * c.C;
     // a pair tile is 256 consecutive output pixels of one image: the image must split into whole 128-pixel boxes
     if (M % 128 != 0) return -1;
-    const int nkb = (int)(K / 64);
+    if (halo_taps) {
+        // 3x3, stride 1, pad 1; 16 x 8 pixel patches tile the image
+        if ((halo_taps != 3 && halo_taps != 9) || c.KH != 3 || c.KW != 3 || c.pad != 1 || c.dil != 1 || c.W % 8 || c.H % 16) return -1;
+    }
+    const int cblocks = (int)(c.C / 64);
+    const int nkb = halo_taps ? (halo_taps == 9 ? cblocks : 3 * cblocks) : (int)(K / 64);      // ring stages per tile
     if (splits > nkb) return -1;
     G2Params kp;
     memset(&kp, 0, sizeof(kp));
     unsigned ctas = 0;
     size_t smem = 0;
-    if (!fill_geometry(kp, dev, M, c.OC, c.N, nkb, bn, splits, &ctas, &smem)) return -1;
-    const uint32_t BW = (uint32_t)(c.W < 128 ? c.W : 128), BH = 128 / BW;
+    if (!fill_geometry(kp, dev, M, c.OC, c.N, nkb, bn, splits, &ctas, &smem, halo_taps)) return -1;
+    const uint32_t BW = halo_taps ? 10u : (uint32_t)(c.W < 128 ? c.W : 128), BH = halo_taps ? (halo_taps == 9 ? 18u : 16u) : 128 / BW;
     CUtensorMap ta, tb;
     {
         auto enc = b200_get_tensormap_encoder();
@@ -755,9 +843,12 @@ int b200_launch_conv_tc2(cudaStream_t s, const b200_device_info& dev, const b200
     kp.residual = c.residual; kp.ldr = M; kp.r_batch_stride = c.OC * M;
     kp.D2 = c.D2; kp.d2_seq = c.d2_seq; kp.d2_slot = c.d2_slot_floats;
     kp.vec_epi = vec_epilogue_ok(kp, splits);
+    if (halo_taps && !kp.vec_epi && splits == 1) return -1;        // the per-row epilogues do not know the 16 x 8 patch layout
+    if (halo_taps) { kp.wpf = nullptr; }                            // (the up-front L2 request counts k-blocks of 128 bytes, not stages)
     kp.conv = 1; kp.conv_W = (int)c.W; kp.conv_KW = c.KW; kp.conv_cblocks = (int)(c.C / 64); kp.conv_pad = c.pad; kp.conv_dil = c.dil;
     CUtensorMap td;
     encode_output(&td, kp, c.N);
+    if (halo_taps) kp.tma_store = 0;
     cudaError_t e = launch2<0>(s, ctas, (unsigned)splits, smem, ta, tb, td, kp);
     if (e != cudaSuccess) {
         fprintf(stderr, "[ggml-b200] CTA-pair conv launch failed: %s\n", cudaGetErrorString(e));

@@ -128,6 +128,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// same, with the stride between 8-row groups given (any multiple of 128 bytes: the swizzle is applied to the shared-memory ADDRESS, so a
+// group may start at any 128-byte row of a swizzled region -- tools/desc_probe.cu)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 // Instruction descriptor for kind::f16 / kind::tf32 with f32 accumulate, both operands K-major.
 //   bits [4,6) c_format = 1 (F32); [7,10) a_format; [10,13) b_format (0 F16, 1 BF16, 2 TF32);
 //   bit 15 a_major = 0 (K); bit 16 b_major = 0 (K); [17,23) N >> 3; [24,29) M >> 4

@@ -127,6 +127,17 @@ def test_conv_2d(b200, IC, OC, H, s):
     assert rel(g, c) < 2e-4, f"rel {rel(g, c):.2e}"
 
 
+@pytest.mark.parametrize("N,IC,OC,H,W", [(2, 320, 320, 32, 64), (1, 128, 128, 48, 24), (2, 1280, 1280, 16, 16), (1, 640, 320, 32, 32), (1, 64, 128, 16, 8),
+                                         (1, 1920, 640, 32, 32), (1, 256, 256, 64, 64)])
+def test_conv_2d_3x3_patch_tiles(b200, N, IC, OC, H, W):
+    """3x3 / stride 1 / pad 1 convolutions inside the halo-reuse envelope of the CTA-pair kernel (W % 8 == 0, H % 16 == 0: one image box in
+    shared memory serves 3 or 9 taps, 16 x 8 pixel patches): batch > 1, an odd number of patches, one patch pair per image, split-K
+    (few patches, long K), 3 and 9 taps per ring stage."""
+    w, x, b = f(OC, IC, 3, 3) / np.sqrt(9 * IC), f(N, IC, H, W), 0.1 * f(1, OC, 1, 1)
+    g, c = both(b200, "conv_2d", [w, x, b], ["f16", "f32", "f32"], ip=[1, 1, 1, 1, 1, 1])
+    assert g.shape == c.shape and rel(g, c) < 2e-4, f"rel {rel(g, c):.2e}"
+
+
 def test_conv_1x1(b200):
     w, x = f(640, 320, 1, 1) / 18, f(1, 320, 32, 32)
     g, c = both(b200, "conv_2d", [w, x], ["f16", "f32"], ip=[1, 1, 0, 0, 1, 1])
