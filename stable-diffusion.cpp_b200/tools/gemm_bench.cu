@@ -79,8 +79,58 @@ int main(int argc, char** argv) {
         cudaGraphDestroy(graph);
         return ms * 1e3 / reps;
     };
-    printf("%-34s %8s %8s %8s | %9s %9s\n", "shape", "M", "N", "K", "us", "TFLOP/s");
     const char* only = getenv("GEMM_BENCH_ONLY");      // substring filter on the shape name
+    // GEMM_BENCH_CONV=1: the 3x3 convolutions of the UNet / VAE on the CTA-pair kernel, per-tap boxes against halo reuse (3 / 9 taps per
+    // ring stage), over tile widths and split-K factors; the halo result is compared with the per-tap one (same products, other order)
+    if (getenv("GEMM_BENCH_CONV")) {
+        struct Conv { const char* name; int64_t N, H, W, C, OC; };
+        const Conv convs[] = {{"sd15 64x64 320->320 x2", 2, 64, 64, 320, 320}, {"sd15 32x32 640->640 x2", 2, 32, 32, 640, 640}, {"sd15 16x16 1280->1280 x2", 2, 16, 16, 1280, 1280},
+                              {"sd15 64x64 640->320 x2", 2, 64, 64, 640, 320}, {"sd15 32x32 1280->640 x2", 2, 32, 32, 1280, 640},
+                              {"vae 512x512 128->128", 1, 512, 512, 128, 128}, {"vae 256x256 256->256", 1, 256, 256, 256, 256}, {"vae 128x128 512->512", 1, 128, 128, 512, 512},
+                              {"sdxl 128x128 320->320", 1, 128, 128, 320, 320}, {"sdxl 64x64 640->640", 1, 64, 64, 640, 640}};
+        printf("%-28s %4s %6s %5s | %9s %9s %s\n", "conv", "bn", "splits", "taps", "us", "TFLOP/s", "max |halo - per-tap|");
+        for (const Conv& cv : convs) {
+            if (only && !strstr(cv.name, only)) continue;
+            const int64_t M = cv.H * cv.W, K = 9 * cv.C;
+            if ((size_t)cv.N * M * cv.C > maxA || (size_t)cv.OC * K > maxB || (size_t)cv.N * M * cv.OC > maxD) { printf("%s: buffers too small\n", cv.name); continue; }
+            b200_conv_args c; memset(&c, 0, sizeof(c));
+            c.x_nhwc = A; c.w_packed = B; c.N = cv.N; c.H = cv.H; c.W = cv.W; c.C = cv.C; c.OC = cv.OC; c.KH = 3; c.KW = 3; c.pad = 1; c.dil = 1; c.D = D; c.bias = bias;
+            const double flop = 2.0 * cv.N * M * cv.OC * K;
+            std::vector<float> ref, got((size_t)cv.N * M * cv.OC);
+            {   // the dispatcher's own choice (what the backend runs)
+                const double t = time_graph([&] { b200_launch_conv_tc(st, dev, c, nullptr, 0); });
+                printf("%-28s %4s %6s %5s | %9.2f %9.1f   <- dispatcher\n", cv.name, "-", "-", "-", t, flop / t * 1e-6);
+            }
+            const int bns[] = {256, 192, 160, 128, 96, 64};
+            for (int bn : bns) {
+                if (bn > 64 && cv.OC <= bn / 2) continue;
+                for (int sp = 1; sp <= 4; sp *= 2) {
+                    const int64_t tiles = ((M + 255) / 256) * ((cv.OC + bn - 1) / bn) * cv.N;
+                    if (sp > 1 && tiles * 2 * sp > 148) continue;
+                    const int auto_taps = b200_conv_tc2_halo_taps(bn, sp);
+                    const int modes[3] = {0, auto_taps, auto_taps == 9 ? 3 : -1};
+                    bool have_ref = false;
+                    for (int mi = 0; mi < 3; ++mi) {
+                        const int taps = modes[mi];
+                        if (taps < 0 || (mi > 0 && taps == 0)) continue;
+                        cudaMemsetAsync(D, 0xff, got.size() * 4, st);
+                        if (b200_launch_conv_tc2(st, dev, c, bn, sp, taps) <= 0) continue;
+                        if (cudaStreamSynchronize(st) != cudaSuccess) { printf("   bn %d splits %d taps %d: FAILED %s\n", bn, sp, taps, cudaGetErrorString(cudaGetLastError())); return 1; }
+                        cudaMemcpy(got.data(), D, got.size() * 4, cudaMemcpyDeviceToHost);
+                        double maxd = 0;
+                        if (taps == 0) { ref = got; have_ref = true; }
+                        else if (have_ref) for (size_t i = 0; i < got.size(); ++i) { const double d = fabs((double)got[i] - ref[i]); if (!(d <= maxd)) maxd = d; }
+                        const double t = time_graph([&] { b200_launch_conv_tc2(st, dev, c, bn, sp, taps); });
+                        printf("%-28s %4d %6d %5d | %9.2f %9.1f   %.3g\n", cv.name, bn, sp, taps, t, flop / t * 1e-6, taps ? maxd : 0.0);
+                        fflush(stdout);
+                    }
+                }
+            }
+        }
+        printf("status: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
+    printf("%-34s %8s %8s %8s | %9s %9s\n", "shape", "M", "N", "K", "us", "TFLOP/s");
     for (auto& s : shapes) {
         if (only) {                                    // comma-separated substrings
             bool hit = false;
