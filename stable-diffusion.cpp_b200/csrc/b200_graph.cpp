@@ -56,7 +56,6 @@ b200_context* b200_context_create(const b200_device_info& info) {
     ctx->opt_gemv = env_flag("GGML_B200_GEMV", 1) != 0;
     ctx->opt_precise_f32 = env_flag("GGML_B200_PRECISE_F32", 1) != 0;
     ctx->opt_q8_activations = env_flag("GGML_B200_Q8_ACT", 1) != 0;
-    ctx->opt_persistent_gemm = env_flag("GGML_B200_PERSISTENT", 0) != 0;   // experimental persistent GEMM (gemm_tc_persist.cu), never run on hardware yet
     ctx->opt_side_streams = env_flag("GGML_B200_SIDE_STREAMS", 1) != 0;
     ctx->opt_wprefetch = env_flag("GGML_B200_WPREFETCH", 0) != 0;
     ctx->opt_fold_batch = env_flag("GGML_B200_FOLD_BATCH", 0) != 0;   // written at the end of round 1, not yet measured: off by default
@@ -81,6 +80,7 @@ b200_context::~b200_context() {
 }
 
 static void drop_cuda_graphs(b200_context* ctx);
+static void b200_debug_refuse_op(int op);
 
 int b200_context_set_option(b200_context* ctx, const char* key, int value) {
     // captured plans embody the options they were recorded under
@@ -98,9 +98,9 @@ int b200_context_set_option(b200_context* ctx, const char* key, int value) {
     else if (!strcmp(key, "chain_fusion")) ctx->opt_chain_fusion = value != 0;
     else if (!strcmp(key, "gemv")) ctx->opt_gemv = value != 0;
     else if (!strcmp(key, "fold_batch")) ctx->opt_fold_batch = value != 0;
-    else if (!strcmp(key, "persistent_gemm")) ctx->opt_persistent_gemm = value != 0;
     else if (!strcmp(key, "precise_f32")) ctx->opt_precise_f32 = value != 0;
     else if (!strcmp(key, "q8_activations")) ctx->opt_q8_activations = value != 0;
+    else if (!strcmp(key, "debug_refuse_op")) b200_debug_refuse_op(value);
     else return -1;
     return 0;
 }
@@ -289,10 +289,7 @@ static int launch_tc(b200_context* ctx, const b200_gemm_args& g) {
         e1 = kt_event(ctx);
         cudaEventRecord(e0, ctx->stream);
     }
-    int n = -1;
-    if (ctx->opt_persistent_gemm) n = b200_launch_gemm_tc_persistent(ctx->stream, ctx->info, g);   // experimental, off by default
-    if (n < 0) n = b200_launch_gemm_tc(ctx->stream, ctx->info, g, w, w ? wsb : 0);
-    else ctx->stats.ext[4] += 1;           // persistent one-CTA variant
+    int n = b200_launch_gemm_tc(ctx->stream, ctx->info, g, w, w ? wsb : 0);
     if (n == 2) { n = 1; ctx->stats.ext[5] += 1; }   // CTA-pair kernel (gemm_tc2.cu)
     if (ctx->opt_kernel_timing) {
         if (n > 0) {
@@ -804,7 +801,14 @@ static int op_flash_attn(b200_context* ctx, ggml_tensor* dst, fa_fusion* fz = nu
 // ------------------------------------------------------------------------------------------------
 // supports_op
 // ------------------------------------------------------------------------------------------------
+// test knob (option "debug_refuse_op"): report one ggml op as unsupported, so that the host's own ggml_backend_sched fallback
+// (src/core/ggml_extend.hpp:2198-2225: B200 -> CPU -> B200 splits with cross-backend copies) can be exercised against this backend
+static std::atomic<int> g_refuse_op{-1};
+
+static void b200_debug_refuse_op(int op) { g_refuse_op.store(op, std::memory_order_relaxed); }
+
 bool b200_supports_op(const b200_device_info&, const ggml_tensor* op) {
+    if ((int)op->op == g_refuse_op.load(std::memory_order_relaxed)) return false;
     const ggml_tensor* s0 = op->src[0];
     const ggml_tensor* s1 = op->src[1];
     switch (op->op) {

@@ -50,7 +50,6 @@ struct b200_context {
     bool opt_chain_fusion = true;     // GEGLU tail, Q read in place by attention, f16 operand copies written by their producers
     bool opt_gemv = true;             // MUL_MAT with <= 4 activation rows as a weight-streaming GEMV instead of a tcgen05 tile
     bool opt_fold_batch = false;      // MUL_MAT of one weight matrix against a contiguous batch of activations runs as one GEMM with N * batch rows
-    bool opt_persistent_gemm = false; // EXPERIMENTAL persistent GEMM with double-buffered TMEM accumulators (not validated on hardware)
     bool opt_precise_f32 = true;      // F32 x F32 MUL_MAT as 3xTF32 (hi/lo operand split, three tensor-core passes): f32-class accuracy like the CPU oracle's f32 dot
     bool opt_q8_activations = true;   // Q8_0-weight contractions quantise the activation rows to Q8_0 like the CPU oracle does (q8_0 x q8_0 dot)
     bool opt_kernel_timing = false;   // per-launch CUDA events around every tcgen05 GEMM (roofline pass only)

@@ -99,8 +99,6 @@ struct b200_gemm_args {
 // returns kernels launched, or -1 if the shape/alignment is not supported by the TMA path (caller falls back)
 int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g, void* workspace, size_t workspace_bytes);
 size_t b200_gemm_tc_workspace_bytes(const b200_device_info& dev, const b200_gemm_args& g);
-// EXPERIMENTAL persistent variant (gemm_tc_persist.cu; option "persistent_gemm", off by default): 1 when launched, -1 when not applicable
-int b200_launch_gemm_tc_persistent(cudaStream_t s, const b200_device_info& dev, const b200_gemm_args& g);
 
 // gemm_tc2.cu: CTA-pair (tcgen05 cta_group::2, M = 256) persistent GEMM / implicit conv with two TMEM accumulators; F16 / BF16 only.
 // bn: tile N of the pair (multiple of 16, <= 256), splits: split-K factor inside the cluster (1..4).  1 when launched, -1 when the

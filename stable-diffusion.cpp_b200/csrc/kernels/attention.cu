@@ -293,9 +293,11 @@ __global__ void __launch_bounds__(192, FaCfg<NATOM, BLOCK_N>::MIN_CTAS) k_flash_
             }
             float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             if (plain) mx *= p.scale_log2;                       // scale > 0: the maximum commutes with it
-            float m_new = fmaxf(m_ref, mx);
-            if (m_new == -INFINITY) m_new = 0.f;                  // fully masked row so far
-            bool grow = (j == 0) || (m_new - m_ref > kLazyThreshold);
+            const float m_new = fmaxf(m_ref, mx);
+            // A row whose keys so far are ALL masked keeps m_ref = -inf (its probabilities are exact zeros); the first finite maximum then
+            // forces a rescale with alpha = exp2(-inf) = 0.  (Forcing the reference to 0 here would exponentiate later, much smaller scores
+            // against 0 and flush them to f16 zeros: rows of a left-padded mask came out as zeros.)
+            bool grow = m_new > -INFINITY && (m_ref == -INFINITY || m_new - m_ref > kLazyThreshold);
             // previous P.V must have retired before P is overwritten or O is rescaled; the (rare) rescale needs it now,
             // otherwise the wait is deferred until the new probabilities sit in registers so the exps overlap that MMA
             bool waited = j == 0;
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(192, FaCfg<NATOM, BLOCK_N>::MIN_CTAS) k_flash_
             // ---- pass 2: P = exp2(s - m_ref), row sum, f16 into swizzled shared memory
             float ls4[4] = {0.f, 0.f, 0.f, 0.f};
             uint32_t ph[BLOCK_N / 2];   // the whole P row as packed half2, kept in registers until the P buffer is free
-            const float neg_m = -m_ref;
+            const float neg_m = m_ref == -INFINITY ? 0.f : -m_ref;       // all keys masked so far: exp2(-inf + 0) = 0
 #pragma unroll
             for (int i = 0; i < BLOCK_N; i += 2) {
                 // exp2(s * scale - m): one FMA feeding the MUFU (mul == 1 when the scale was applied above); exp2(-inf) == 0 for masked / tail keys

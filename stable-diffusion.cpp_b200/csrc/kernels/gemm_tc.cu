@@ -541,23 +541,45 @@ Plan2 choose_plan2(const b200_device_info& dev, int64_t M, int64_t N, int64_t ba
     return best;
 }
 
-// halo-reuse convolution (gemm_tc2.cu): same candidates, the image bytes per k-block shrink with the taps a ring stage serves
+// halo-reuse convolution (gemm_tc2.cu).  Its own cost model, fitted to the hardware sweep of tools/gemm_bench (GEMM_BENCH_CONV=1: ten
+// UNet / VAE / SDXL 3x3 convolutions x tile width x split-K x taps per stage, profiles/r02_conv_halo_sweep.log; 12 % rms, picks within
+// 0-14 % of the best measured plan for every shape).  What the sweep showed and the GEMM model above does not capture:
+//   * a k-block costs max(2.64 bn, staged bytes / 31.8, (operand reads + staged bytes) / 97.8) clk: besides the MMA issue rate and the
+//     L2 -> SM fill, the SHARED-MEMORY port is a limit of its own -- every K = 16 MMA of the pair re-reads 128 rows of A and bn / 2 rows of
+//     B (32 B each) per CTA, the TMA fill writes through the same port (narrow tiles re-read A per few columns: bn = 64 is port bound)
+//   * the epilogue of a tile (~2800 clk) is NOT hidden behind the next tile's main loop in practice (it shares that port), and the
+//     fixed cost of a launch (prologue, first fill, last drain) is ~13.9 k clk
+// Halo plans beat every per-tap plan of the same shape in the sweep, so when the halo envelope holds the per-tap plan is not considered.
 struct Plan2H { int bn; int splits; int taps; double cycles; };
+double conv_halo_model(const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int cblocks, int bn, int splits, int taps) {
+    const int sms = dev.sm_count > 0 ? dev.sm_count : 148;
+    const int64_t tiles = ((M + 255) / 256) * ((N + bn - 1) / bn) * batch;
+    const int nkb = 9 * cblocks;
+    const double kb = (double)((nkb + splits - 1) / splits);
+    const double staged = (taps == 9 ? 23040.0 / 9.0 : 20480.0 / 3.0) + bn / 2.0 * 128.0;     // bytes per 64-wide k-block and CTA
+    const double kb_cycles = std::max(std::max(2.64 * bn, staged / 31.8), (4.0 * (4096.0 + 16.0 * bn) + staged) / 97.8);
+    if (splits == 1) {
+        const int64_t pairs = std::min<int64_t>(tiles, sms / 2);
+        return 13870.0 + (double)((tiles + pairs - 1) / pairs) * (kb * kb_cycles + 2800.0);
+    }
+    const int csize = 2 * splits;
+    const int64_t max_clusters = csize == 4 ? 36 : (csize == 6 ? 20 : 13);   // concurrent clusters the GPCs (16-20 SMs each) can host
+    return (double)((tiles + max_clusters - 1) / max_clusters) * (13870.0 + kb * kb_cycles);
+}
 Plan2H choose_plan2_halo(const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int cblocks) {
     const int sms = dev.sm_count > 0 ? dev.sm_count : 148;
     Plan2H best{0, 1, 0, 1e30};
-    const int bns[] = {256, 224, 192, 160, 128, 96, 64, 48, 32};
-    const int nkb = 9 * cblocks;
+    const int bns[] = {256, 192, 160, 128, 96, 64, 48, 32};      // (the widths the sweep covered; 48 / 32 only ever for N <= 32)
     for (int bn : bns) {
         if (bn > 32 && N <= bn / 2) continue;
+        if (bn < 64 && N > 32) continue;
         const int64_t tiles = ((M + 255) / 256) * ((N + bn - 1) / bn) * batch;
         for (int splits = 1; splits <= 4; splits *= 2) {
             const int taps = b200_conv_tc2_halo_taps(bn, splits);
             if (!taps) continue;
             const int nst = taps == 9 ? cblocks : 3 * cblocks;          // ring stages per tile: what split-K divides
             if (splits > 1 && (tiles * 2 * splits > sms || nst / splits < 2)) break;
-            const double a_bytes = taps == 9 ? 23040.0 / 9.0 : 20480.0 / 3.0;
-            const double t = b200_gemm_tc2_model(dev, M, N, batch, nkb, bn, splits, a_bytes);
+            const double t = conv_halo_model(dev, M, N, batch, cblocks, bn, splits, taps);
             if (t < best.cycles) best = Plan2H{bn, splits, taps, t};
         }
     }
@@ -706,7 +728,7 @@ int b200_launch_conv_tc(cudaStream_t s, const b200_device_info& dev, const b200_
         if (halo_en < 0) { const char* e = getenv("GGML_B200_CONV_HALO"); halo_en = (e && *e) ? atoi(e) : 1; }
         if (halo_en && c.KH == 3 && c.KW == 3 && c.pad == 1 && c.dil == 1 && c.W % 8 == 0 && c.H % 16 == 0) {
             const Plan2H ph = choose_plan2_halo(dev, g.M, g.N, g.batch, (int)(c.C / 64));
-            if (ph.bn > 0 && (p2.bn <= 0 || ph.cycles < p2.cycles)) { p2 = Plan2{ph.bn, ph.splits, ph.cycles}; taps = ph.taps; }
+            if (ph.bn > 0) { p2 = Plan2{ph.bn, ph.splits, std::min(ph.cycles, p2.bn > 0 ? p2.cycles : ph.cycles)}; taps = ph.taps; }
         }
         if (p2.bn > 0 && (gemm2_mode() >= 2 || p2.cycles < cycles1)) {
             int r = b200_launch_conv_tc2(s, dev, c, p2.bn, p2.splits, taps);

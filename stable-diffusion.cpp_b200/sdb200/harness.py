@@ -116,6 +116,13 @@ class Harness:
     def last_error(self) -> str:
         return (self.lib.sdh_last_error() or b"").decode()
 
+    def op_name(self, op: int) -> str:
+        """ggml_op_name of the reference's ggml (libggml-base.so, already loaded globally by the harness)."""
+        fn = self.lib.ggml_op_name
+        fn.argtypes = [C.c_int]
+        fn.restype = C.c_char_p
+        return (fn(int(op)) or b"").decode(errors="replace")
+
     # ------------------------------------------------------------------ host-side reference math
     def schedule(self, steps: int):
         s = np.zeros(steps + 1, np.float32)

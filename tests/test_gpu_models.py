@@ -297,3 +297,34 @@ def test_wan_vae_decoder_vs_committed_cpu_fixture(b200):
     m.close()
     assert out.shape == gold.shape and np.isfinite(out).all()
     assert rel(out, gold) < 3e-3, f"rel_l2 {rel(out, gold):.2e}"
+
+
+def test_reference_sched_fallback_splits_run_clean(b200):
+    """SURVEY.md 8f-4 (sched-clean): when supports_op rejects a node, the reference's GGMLRunner replaces gallocr by a ggml_backend_sched
+    over [B200, CPU] (src/core/ggml_extend.hpp:2083-2136, 2198-2225) -- the graph is split B200 -> CPU -> B200, inputs of a split are
+    copied across backends through the buffer vtable, and every split is one graph_compute.  The debug knob makes this backend refuse
+    UPSCALE (3 nodes of the tiny UNet): the result must match the all-B200 run and a later all-B200 forward must still be right."""
+    h, dev = b200
+    GGML_OP_UPSCALE = next(i for i in range(102) if h.op_name(i) == "UPSCALE")
+    x = h.randn(42, (1, 4, 16, 16)); ctx = h.randn(43, (1, 77, 768)); t = np.array([999.0], np.float32)
+    m = h.model(dev, "unet_tiny", "f16", 1, 1234, 0)
+    ref, _ = m.forward(x, t, ctx)
+    s0 = m.stats()
+    m.forward(x, t, ctx)
+    s1 = m.stats()
+    assert s1["graphs"] - s0["graphs"] == 1
+    try:
+        m.set_option("debug_refuse_op", GGML_OP_UPSCALE)
+        out, _ = m.forward(x, t, ctx)
+        s2 = m.stats()
+        out2, _ = m.forward(x, t, ctx)
+    finally:
+        m.set_option("debug_refuse_op", -1)
+    assert s2["graphs"] - s1["graphs"] >= 2, "the refused nodes must have split the graph into several B200 graph_compute calls"
+    assert s2["gemm_ref_launches"] == s0["gemm_ref_launches"]
+    assert np.isfinite(out).all()
+    assert rel(out, ref) < 1e-5, f"sched split run vs single-graph run: {rel(out, ref):.2e}"
+    assert np.array_equal(out, out2)
+    back, _ = m.forward(x, t, ctx)          # the runner keeps its sched; with nothing refused the whole graph is one B200 split again
+    m.close()
+    assert rel(back, ref) < 1e-5

@@ -154,6 +154,21 @@ def test_flash_attn_ext(b200, H, d, Lq, Lk):
     assert rel(g, c) < 2.3e-2, f"vs CPU oracle {rel(g, c):.2e}"  # sqrt(5e-4): test-backend-ops' FLASH_ATTN_EXT limit
 
 
+def test_flash_attn_ext_left_padded_mask(b200):
+    """A mask whose LEADING key tiles are fully -inf and whose open keys carry a large negative bias: the running maximum must stay
+    -inf until the first open key (a reference of 0 would flush the later probabilities to f16 zeros and write zero rows)."""
+    H, d, Lq, Lk = 4, 64, 130, 320
+    q, k, v = f(1, H, Lq, d), f(1, H, Lk, d), f(1, H, Lk, d)
+    mask = np.full((1, 1, Lq, Lk), -30.0, np.float32)
+    mask[..., :160] = -np.inf
+    mask[:, :, 7, 160:200] = -np.inf                              # one row opens even later
+    g, c = both(b200, "flash_attn", [q, k, v, mask], ["f32", "f16", "f16", "f16"], fp=[d ** -0.5])
+    ref = R.flash_attn_ext(q, k, v, mask, d ** -0.5)
+    assert np.abs(ref).max() > 0.1
+    assert rel(g, ref) < 2e-3, f"vs restatement {rel(g, ref):.2e}"
+    assert rel(g, c) < 2.3e-2, f"vs CPU oracle {rel(g, c):.2e}"
+
+
 @pytest.mark.parametrize("fa", [0, 1])
 def test_attention_wrapper_both_graph_variants(b200, fa):
     """ggml_ext_attention_ext (ggml_extend.hpp:1349): reshape/permute/cont + (FLASH_ATTN_EXT | MUL_MAT+SOFT_MAX+MUL_MAT)."""
