@@ -76,7 +76,7 @@ typedef struct ggml_b200_stats {
     uint64_t ext[16];           /* [0] CUDA-core reference GEMM launches (gemm_ref.cu: must stay 0 on every model path; the parity tests assert it),
                                    [1] host microseconds spent inside graph_compute (signature, fusion planning, launches / cudaGraphLaunch),
                                    [2] graphs that wrote into a WEIGHTS buffer (derived weight copies dropped), [3] conv filters packed per graph
-                                   (filter computed inside the graph: no persistent copy), [4] unused, [5] 2-CTA GEMM launches,
+                                   (filter computed inside the graph: no persistent copy), [4] GEGLU projections run in the pair kernel's GEGLU mode (only output: the next Linear's 16-bit operand), [5] 2-CTA GEMM launches,
                                    [6] bytes of derived weight copies alive, [7] unfused (GEMM + softmax + GEMM) attention executions,
                                    [8] graphs that ended with a peer exchange (kernels/peer.cu),
                                    [9..12] host microseconds at the plugin boundary, process-wide: inside set_tensor, inside get_tensor (includes

@@ -330,6 +330,7 @@ struct mm_fusion {
     bool skip_f32 = false;
     int* d16_done = nullptr;
     bool d16_strict = false;                  // decline (-2, nothing written) rather than run without the 16-bit copy
+    int64_t geglu = 0;                        // > 0: GEGLU projection (b200_gemm_args::geglu): d16 = x * gelu(gate) [tokens][geglu] is the only output
 };
 
 static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz = nullptr) {
@@ -347,7 +348,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
     }
 
     // a handful of activation rows against in-place F16/BF16 weights (embedding MLPs): weight-streaming GEMV, no operand packing
-    if (!(fz && (fz->act || fz->gate || fz->d16_strict))) {
+    if (!(fz && (fz->act || fz->gate || fz->d16_strict || fz->geglu))) {
         const ggml_tensor* x = fz && fz->src1_pre ? fz->src1_pre : src1;
         if (ctx->opt_gemv && ne02 * ne03 * ne12 * ne13 == 1 && N <= 4 && (src0->type == GGML_TYPE_F16 || src0->type == GGML_TYPE_BF16) &&
             rows_unit_stride(src0) && x->type == GGML_TYPE_F32 && x->nb[0] == 4 && x->nb[1] % 4 == 0 && dst->nb[0] == 4 &&
@@ -363,6 +364,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
         if (fz && fz->src1_pre) return -2;     // only the GEMV can fold the unary op
     }
 
+    if (fz && fz->geglu && (ct == GGML_TYPE_F32 || !ctx->opt_tc_gemm)) return -2;
     if (ct == GGML_TYPE_F32 && ctx->opt_precise_f32 && ctx->opt_tc_gemm && !(fz && (fz->act || fz->gate))) {
         // F32 x F32 (attention GEMMs of the reference's default graph, F32 Linear weights): the CPU oracle computes true f32 dot products
         // (ggml-cpu.c:1406 with vec_dot_f32); a single TF32 pass would keep 10 mantissa bits of each operand.  3xTF32: x = hi + lo with hi
@@ -477,7 +479,8 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
         if (fz && fz->residual) { g.residual = fz->residual; g.ldr = g.ldd; }
         if (fz) { g.act = fz->act; g.gate = fz->gate; }
         if (fz && fz->d16 && nb13 == 1) { g.D16 = fz->d16; g.d16_type = fz->d16_type; g.skip_f32 = fz->skip_f32 ? 1 : 0; g.d16_done = fz->d16_done; g.d16_strict = fz->d16_strict ? 1 : 0; }
-        else if (fz && fz->d16_strict) return -2;
+        else if (fz && (fz->d16_strict || fz->geglu)) return -2;
+        if (fz && fz->geglu) g.geglu = fz->geglu;
         // model weights read in place are constants of the graph: their first ring-full may be fetched before the PDL wait.  Not for
         // the first kernel of a graph_compute (its stream predecessor belongs to an earlier call, e.g. a weight update).
         if (ctx->opt_early_weights && a.ptr == src0->data && src0->buffer && src0->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS &&
@@ -489,7 +492,7 @@ static int op_mul_mat(b200_context* ctx, ggml_tensor* dst, const mm_fusion* fz =
             g.wprefetch = 1;
         int n = launch_tc(ctx, g);
         if (n < 0) {
-            if (fz && fz->d16_strict) return -2;             // declined before anything was launched: the caller runs the node in its turn
+            if (fz && (fz->d16_strict || fz->geglu)) return -2;   // declined before anything was launched: the caller runs the node in its turn / unfused
             if (fz && (fz->act || fz->gate)) return -1;      // the reference kernel has no activation / gate epilogue: fail loudly rather than skip it
             // CUDA-core reference kernel (debug option, or shapes the TMA cannot describe)
             n = 0;
@@ -1217,9 +1220,11 @@ static bool match_kv_projection(const b200_context* ctx, const ggml_cgraph* g, c
     return true;
 }
 
+static bool same_order_view_of(const ggml_tensor* v, const ggml_tensor* root);
+
 // MUL_MAT [-> views] [-> CONT of an order-preserving view] [-> views] [-> ADD bias]
 static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered, const ggml_tensor* src1_pre = nullptr,
-                            int pre_act = 0, bool side_only = false) {
+                            int pre_act = 0, bool side_only = false, bool allow_geglu = true) {
     ggml_tensor* mm = g->nodes[i];
     if (!ggml_is_contiguous(mm) || (mm->flags & GGML_TENSOR_FLAG_OUTPUT)) return -2;
     std::vector<int> chain;
@@ -1260,9 +1265,62 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
             }
         }
     }
+    // GEGLU (FeedForward of the UNet transformer blocks, block.hpp:182-210): proj [+ bias] -> chunk views x | gate -> CONT(gate) -> GELU ->
+    // MUL(x, .) -> net.2.  The projection is bound by its OUTPUT bytes (f32 [2 inner, tokens]: 84 MB at 8192 tokens x 2560, written, read
+    // back by the GEGLU pass, 42 MB of products written and packed to 16 bits again).  In GEGLU mode the pair kernel pairs each x feature
+    // with its gate feature inside one accumulator tile and its epilogue writes ONLY the 16-bit operand of net.2.
+    static int geglu_enabled = -1;
+    if (geglu_enabled < 0) { const char* e = getenv("GGML_B200_GEGLU_EPI"); geglu_enabled = (e && *e) ? atoi(e) : 1; }
+    const ggml_tensor* geglu_act = nullptr;
+    int geglu_done = 0;
+    if (geglu_enabled && allow_geglu && !src1_pre && !side_only && ctx->opt_chain_fusion && ctx->opt_tc_gemm && ctx->opt_fusion &&
+        (mm->src[0]->type == GGML_TYPE_F16 || mm->src[0]->type == GGML_TYPE_BF16) && mm->ne[1] > 4 && mm->ne[3] == 1 && M % 128 == 0 && fz.bias_mode != 2) {
+        const ggml_tensor* curv = chain.empty() ? (const ggml_tensor*)mm : g->nodes[chain.back()];
+        const int64_t inner = M / 2;
+        const int jc = next_node(g, fs, chain.empty() ? i : chain.back());
+        const int jg = jc >= 0 ? next_node(g, fs, jc) : -1;
+        const int jm = jg >= 0 ? next_node(g, fs, jg) : -1;
+        const int jn = jm >= 0 ? next_node(g, fs, jm) : -1;
+        if (jn >= 0 && !(curv->flags & GGML_TENSOR_FLAG_OUTPUT) && ggml_is_contiguous(curv)) {
+            const ggml_tensor* c = g->nodes[jc];
+            const ggml_tensor* ge = g->nodes[jg];
+            const ggml_tensor* mul = g->nodes[jm];
+            const ggml_tensor* nm = g->nodes[jn];
+            const ggml_tensor* gate = c->op == GGML_OP_CONT ? c->src[0] : nullptr;
+            const ggml_tensor* xv = (mul->op == GGML_OP_MUL) ? (mul->src[0] == ge ? mul->src[1] : (mul->src[1] == ge ? mul->src[0] : nullptr)) : nullptr;
+            auto half_view = [&](const ggml_tensor* v, int64_t off_elems) {
+                // a chunk view [inner, tokens..] of curv's rows, `off_elems` floats into each row, read by one node only
+                if (!v || v->op != GGML_OP_VIEW || v->type != GGML_TYPE_F32 || !v->src[0] || !single_use(fs, v)) return false;
+                const ggml_tensor* base = v->src[0];
+                if (base != curv && !(is_view_op(base) && base->op != GGML_OP_NONE && base->data == curv->data && ggml_is_contiguous(base) &&
+                                      ggml_nelements(base) == ggml_nelements(curv) && base->ne[0] == curv->ne[0]))
+                    return false;
+                return v->data == (const char*)curv->data + off_elems * 4 && v->ne[0] == inner && v->nb[0] == 4 && v->nb[1] == (size_t)M * 4 &&
+                       ggml_nelements(v) * 2 == ggml_nelements(curv);
+            };
+            const bool views_ok = half_view(gate, inner) && half_view(xv, 0) && gate->src[0] == xv->src[0] &&
+                                  fs.uses.count(gate->src[0]) && fs.uses.at(gate->src[0]) == 2 && (gate->src[0] == curv || single_use(fs, curv));
+            if (views_ok && (c->flags & GGML_TENSOR_FLAG_COMPUTE) && c->type == GGML_TYPE_F32 && ggml_is_contiguous(c) && single_use(fs, c) &&
+                ge->op == GGML_OP_UNARY && ggml_get_unary_op(ge) == GGML_UNARY_OP_GELU && ge->src[0] == c && single_use(fs, ge) &&
+                (ge->flags & GGML_TENSOR_FLAG_COMPUTE) && ge->type == GGML_TYPE_F32 && ggml_is_contiguous(ge) &&
+                (mul->flags & GGML_TENSOR_FLAG_COMPUTE) && mul->type == GGML_TYPE_F32 && ggml_is_contiguous(mul) && single_use(fs, mul) &&
+                ggml_are_same_shape(mul, ge) && mul->ne[0] == inner &&
+                nm->op == GGML_OP_MUL_MAT && nm->src[1] && (nm->src[0]->type == GGML_TYPE_F16 || nm->src[0]->type == GGML_TYPE_BF16) &&
+                nm->src[1]->type == GGML_TYPE_F32 && same_order_view_of(nm->src[1], mul) && (nm->src[1] == mul || single_use(fs, nm->src[1])) &&
+                !ctx->pack_cache.count(std::make_pair(nm->src[1], (int)nm->src[0]->type))) {
+                void* sh = ws_alloc(ctx, (size_t)ggml_nelements(mul) * 2);
+                if (sh) {
+                    fz.geglu = inner;
+                    fz.d16 = sh; fz.d16_type = (int)nm->src[0]->type; fz.skip_f32 = true; fz.d16_done = &geglu_done;
+                    geglu_act = nm->src[1];
+                    chain.push_back(jc); chain.push_back(jg); chain.push_back(jm);
+                }
+            }
+        }
+    }
     // activation: Linear -> GELU / SiLU (the MLPs of the DiT blocks, flux.hpp Mlp; GELU is the tanh form in ggml): applied by the epilogue
     // on the biased accumulator -- the same f32 expression the unary kernel evaluates -- instead of a separate pass over [features, tokens]
-    if (!src1_pre && ctx->opt_chain_fusion && ctx->opt_tc_gemm && mm->src[0]->type != GGML_TYPE_F32 && mm->ne[1] > 4) {
+    if (!fz.geglu && !src1_pre && ctx->opt_chain_fusion && ctx->opt_tc_gemm && mm->src[0]->type != GGML_TYPE_F32 && mm->ne[1] > 4) {
         const int ju = chain.empty() ? next_node(g, fs, i) : next_node(g, fs, chain.back());
         const ggml_tensor* curv = chain.empty() ? (const ggml_tensor*)mm : g->nodes[chain.back()];
         if (ju >= 0) {
@@ -1286,7 +1344,7 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
     const ggml_tensor* d16_act = nullptr;
     static int d16_enabled = -1;
     if (d16_enabled < 0) { const char* e = getenv("GGML_B200_D16"); d16_enabled = (e && *e) ? atoi(e) : 1; }
-    if (d16_enabled && fz.act && !chain.empty()) {
+    if (d16_enabled && fz.act && !fz.geglu && !chain.empty()) {
         const ggml_tensor* curv = g->nodes[chain.back()];
         const int jm = next_node(g, fs, chain.back());
         if (jm >= 0 && single_use(fs, curv) && ggml_is_contiguous(curv) && mm->ne[2] * mm->ne[3] == 1) {
@@ -1305,7 +1363,7 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
     int kv_done = 0, kv_cont = -1, kv_cpy = -1;
     const ggml_tensor* kv_cp = nullptr;
     fusion_state::kv_direct kvd;
-    if (!fz.act && !fz.d16 && !src1_pre) {
+    if (!fz.act && !fz.d16 && !src1_pre && !fz.geglu) {
         const ggml_tensor* curv = chain.empty() ? (const ggml_tensor*)mm : g->nodes[chain.back()];
         kv_match km;
         if (match_kv_projection(ctx, g, fs, mm, curv, chain.empty() ? i : chain.back(), &km)) {
@@ -1356,7 +1414,7 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
     }
     // residual: ... -> ADD(value, r) with r a same-shape tensor that already exists (the ADD is the very next work node, so r was
     // produced before this MUL_MAT).  Read in the epilogue of the element it is added to, so in-place adds onto r are fine.
-    if (!fz.gate) {
+    if (!fz.gate && !fz.geglu) {
         const int jr = chain.empty() ? next_node(g, fs, i) : next_node(g, fs, chain.back());
         const ggml_tensor* curv = chain.empty() ? (const ggml_tensor*)mm : g->nodes[chain.back()];
         if (jr >= 0) {
@@ -1385,6 +1443,16 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
         return -2;
     if (fz.residual) { fz.d16 = nullptr; fz.skip_f32 = false; d16_act = nullptr; kv_cp = nullptr; }     // (a residual after the activation: keep the plain path)
     int n = op_mul_mat(ctx, mm, &fz);
+    if (fz.geglu) {
+        // the pair kernel declined (nothing launched) or did not confirm the operand: run the chain the plain way
+        if (n < 0 || !geglu_done) {
+            if (n >= 0) return -1;                        // launched without the operand: cannot be undone -- report
+            return try_fuse_mul_mat(ctx, g, fs, i, covered, src1_pre, pre_act, side_only, false);
+        }
+        const ggml_tensor* a = geglu_act;
+        ctx->pack_cache[std::make_pair(a, fz.d16_type)] = operand{fz.d16, fz.d16_type, a->ne[0], a->ne[0] * a->ne[1], a->ne[0] * a->ne[1] * a->ne[2]};
+        ctx->stats.ext[4] += 1;        // GEGLU projections whose only output is the next Linear's 16-bit operand
+    }
     if (n < 0) return n;
     if (fz.gate) ctx->stats.ext[15] += 1;      // gated residuals applied by a GEMM epilogue
     if (kv_cp && kv_done) {

@@ -93,6 +93,9 @@ struct b200_gemm_args {
     int         d16_type;   // GGML_TYPE_F16 | GGML_TYPE_BF16
     int         skip_f32;
     int*        d16_done;
+    int64_t     geglu;      // > 0: GEGLU mode of the CTA-pair kernel (block.hpp:182-210).  A = [2 * geglu rows][K]: x-half features then gate-half; the
+                            // ONLY output is D16 = x * gelu_tanh(gate) as [N tokens][geglu] 16-bit rows (batch stride N * geglu); M == 2 * geglu,
+                            // geglu % 64 == 0, bias per row or none, skip_f32 set.  The launcher returns -1 when it cannot run it (nothing launched)
     int         d16_strict; // return -1 WITHOUT launching when the 16-bit copy cannot be written (the caller depends on it: a projection run ahead
                             // of its turn on a side stream must not touch its f32 tensor, whose memory still belongs to somebody else)
 };

@@ -625,6 +625,21 @@ int b200_launch_gemm_tc(cudaStream_t s, const b200_device_info& dev, const b200_
     if (g.gate && !g.residual) return -1;       // the gated epilogue exists on the residual paths only
     const int bk = (int)(BK_BYTES / es);
     const int nkb = (int)((g.K + bk - 1) / bk);
+    if (g.geglu) {
+        // GEGLU projection: exists on the CTA-pair kernel only (one tile per pair step, no split-K); widest-to-narrowest tile by the model
+        if (!gemm2_mode() || g.type == GGML_TYPE_F32) return -1;
+        int best_bn = 0;
+        double best = 1e30;
+        const int bns[] = {256, 192, 160, 128, 96, 64};
+        for (int bn : bns) {
+            if (bn > 64 && g.N <= bn / 2) continue;
+            const double t = b200_gemm_tc2_model(dev, g.M, g.N, g.batch, nkb, bn, 1);
+            if (t < best) { best = t; best_bn = bn; }
+        }
+        if (!best_bn || b200_launch_gemm_tc2(s, dev, g, best_bn, 1) <= 0) return -1;
+        if (gemm_log()) fprintf(stderr, "GEMMLOG pair geglu M %lld N %lld K %lld batch %lld bn %d\n", (long long)g.M, (long long)g.N, (long long)g.K, (long long)g.batch, best_bn);
+        return 2;
+    }
     double cycles1 = 0;
     Plan pl = choose_plan(dev, g, nkb, &cycles1);
     if (gemm2_mode() && g.type != GGML_TYPE_F32 && !g.trace && !g.early && g.M > BM) {

@@ -78,6 +78,12 @@ struct G2Params {
     float* D2;                // optional mirror of D in the PEER GPU's memory (NVLink mapping, kernels/peer.cu); slot chosen by *d2_seq
     const unsigned* d2_seq;
     int64_t d2_slot;
+    // GEGLU mode (> 0: the width `inner` of the gated unit): A holds 2 * inner rows, x-half features [0, inner) then gate-half
+    // [inner, 2 inner).  A CTA stages 64 x rows and the 64 gate rows of the SAME features as one 128-row A tile, so TMEM lanes 0..63 / 64..127
+    // hold x / gate of features j0 .. j0 + 63 and the epilogue emits x * gelu(gate) as the 16-bit operand [token][inner] of the next
+    // Linear -- the f32 projection [2 inner, tokens], the CONT + GELU + MUL passes over it and the operand pack never exist.
+    int64_t geglu;
+    int res_pf;               // request the residual tile from L2 while the epilogue warps wait for the accumulator (GGML_B200_RES_PREFETCH, default on)
 };
 
 // ---- cta_group::2 flavours of the primitives in sm100_ptx.cuh
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
         const int r = t / p.tiles_m;
         const int nt = r % p.tiles_n;
         batch = r / p.tiles_n;
-        m0 = mt * (2 * BM) + (int)prank * BM;      // this CTA's 128 rows
+        m0 = p.geglu ? mt * BM + (int)prank * (BM / 2) : mt * (2 * BM) + (int)prank * BM;      // this CTA's 128 rows (GEGLU: its 64 features)
         n0 = nt * p.bn;                            // first column of the pair's tile
     };
     if (p.wpf && pair < p.total_tiles) {
@@ -246,6 +252,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                         const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
                         const int kh = tap / p.conv_KW, kw = tap - kh * p.conv_KW;
                         tma_load_4d_2cta(sa, &tmA, fb, cb * 64, x0 + kw * p.conv_dil - p.conv_pad, y0 + kh * p.conv_dil - p.conv_pad, i2);
+                    } else if (p.geglu) {
+                        // two 64-row boxes: the x rows of this CTA's features, then the gate rows of the same features
+                        tma_load_4d_2cta(sa, &tmA, fb, kb * BK, m0, i2 / p.r2, i3);
+                        tma_load_4d_2cta(sa + (BM / 2) * BK_BYTES, &tmA, fb, kb * BK, (int)p.geglu + m0, i2 / p.r2, i3);
                     } else {
                         tma_load_4d_2cta(sa, &tmA, fb, kb * BK, m0, i2 / p.r2, i3);
                     }
@@ -313,6 +323,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
             const float* Rp = p.residual ? p.residual + (int64_t)batch * p.r_batch_stride : nullptr;
             // fused collective: the same element also goes to the peer GPU (offset of D's element inside the mailbox slot)
             const int64_t d2off = p.D2 ? (p.D2 - p.D) + (int64_t)((*p.d2_seq + 1u) & 1u) * p.d2_slot : 0;
+            if (Rp && p.res_pf && p.splits == 1 && p.vec_epi) {
+                // the main loop of this tile is still running and these eight warps have nothing to do: ask L2 for the residual values the
+                // epilogue will add (this CTA's 128 rows of every column of the tile) -- a hint, bounded to rows < M and columns < N
+                const int et = (int)threadIdx.x - 64;                  // 0 .. 255
+                if (p.halo_taps) {
+                    const int tw = p.conv_W >> 3, ti = m0 >> 7;
+                    const int64_t base_row = (int64_t)((ti / tw) * 16) * p.conv_W + (ti % tw) * 8;
+                    if ((int64_t)m0 < p.M)
+                        for (int u = et; u < ncols * 16; u += 256) {
+                            const int n = u >> 4, py = u & 15;
+                            l2_prefetch_bulk(Rp + (int64_t)(n0 + n) * p.ldr + base_row + (int64_t)py * p.conv_W, 32u);
+                        }
+                } else {
+                    const int64_t rows = min((int64_t)BM, p.M - m0);
+                    if (rows > 0)
+                        for (int n = et; n < ncols; n += 256) l2_prefetch_bulk(Rp + (int64_t)(n0 + n) * p.ldr + m0, (unsigned)(rows * 4));
+                }
+            }
             mbar_wait(&acc_full[buf], aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.acc_stride;
@@ -327,6 +355,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         if (c0 + i < p.bn) sred[(c0 + i) * BM + ml] = __uint_as_float(r[i]);
+                }
+            } else if (p.geglu) {
+                // GEGLU: staged like the vectorised epilogue below.  After the transpose through shared memory lane l holds rows 4l .. 4l + 3 of a
+                // column (token): lanes 0..15 the x values of features j0 + 4l .., lanes 16..31 the gate values of features j0 + 4 (l - 16) ..:
+                // the gate lanes apply bias + GELU and hand their four values to the x lanes 16 below, which multiply and store 8 bytes.
+                // Arithmetic is the unfused chain's: (acc + bias) per half, gelu_tanh in f32, one multiply, one rounding to the 16-bit operand.
+                float* stage = (float*)(smem + p.stage_off) + half * (32 * BM);
+                const int wq = (warp - 2) & 3;
+                const bool is_gate = lane >= 16;
+                const int64_t feat = (int64_t)m0 + 4 * (lane & 15);
+                const bool fvalid = feat < p.geglu;                       // inner % 4 == 0: the four features are valid together
+                float4 bm4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias_mode == 1 && fvalid) bm4 = *(const float4*)(p.bias + (is_gate ? p.geglu : 0) + feat);
+                uint16_t* out16 = (uint16_t*)p.D16 + (int64_t)batch * p.N * p.geglu + feat;
+#pragma unroll 1
+                for (int c0 = half * 32; c0 < ncols; c0 += 64) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) stage[i * BM + ml] = __uint_as_float(r[i]);
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int col = wq * 8 + jj, n = c0 + col;
+                        float4 v = *(const float4*)(stage + col * BM + 4 * lane);
+                        v.x += bm4.x + 0.f; v.y += bm4.y + 0.f; v.z += bm4.z + 0.f; v.w += bm4.w + 0.f;      // (the plain epilogue's acc + (bias_m + bias_n))
+                        if (is_gate) { v.x = act_fn(v.x, 2); v.y = act_fn(v.y, 2); v.z = act_fn(v.z, 2); v.w = act_fn(v.w, 2); }
+                        const float gx = __shfl_down_sync(0xffffffffu, v.x, 16), gy = __shfl_down_sync(0xffffffffu, v.y, 16);
+                        const float gz = __shfl_down_sync(0xffffffffu, v.z, 16), gw = __shfl_down_sync(0xffffffffu, v.w, 16);
+                        if (!is_gate && fvalid && n < ncols) {
+                            const float ox = __fmul_rn(v.x, gx), oy = __fmul_rn(v.y, gy), oz = __fmul_rn(v.z, gz), ow = __fmul_rn(v.w, gw);
+                            uint2 h;
+                            if (p.d16_bf16) {
+                                const __nv_bfloat162 a = __floats2bfloat162_rn(ox, oy), b = __floats2bfloat162_rn(oz, ow);
+                                h.x = *(const uint32_t*)&a; h.y = *(const uint32_t*)&b;
+                            } else {
+                                const __half2 a = __floats2half2_rn(ox, oy), b = __floats2half2_rn(oz, ow);
+                                h.x = *(const uint32_t*)&a; h.y = *(const uint32_t*)&b;
+                            }
+                            *(uint2*)(out16 + (int64_t)(n0 + n) * p.geglu) = h;
+                        }
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
                 }
             } else if (p.tma_store) {
                 // Staged stores through the TMA: the four warps of this column group write bias / activation applied values of a 32-column
@@ -387,19 +459,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) stage[i * BM + ml] = __uint_as_float(r[i]);
+                    // The residual values of this warp's eight columns are requested together and BEFORE the barrier (the accumulator registers
+                    // are dead by now, so this costs no registers): one memory latency per chunk instead of eight in a row -- D and the residual
+                    // may alias (in-place add), which kept the compiler from hoisting the loads itself, and a conv with a residual ran at
+                    // 240 us where the same conv without one took 107 us (512 x 512 x 128 VAE level).  A thread reads exactly the elements it
+                    // writes, and all eight reads precede the eight writes, so the in-place case stays correct.
+                    float4 rr8[8];
+                    float bn8[8];
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int n = c0 + wq * 8 + jj;
+                        rr8[jj] = (Rp && n < ncols && rvalid) ? *(const float4*)(Rp + (int64_t)(n0 + n) * p.ldr + prow) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        bn8[jj] = (p.bias_mode == 2 && n < ncols) ? p.bias[n0 + n] : 0.f;
+                    }
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
 #pragma unroll
                     for (int jj = 0; jj < 8; ++jj) {
                         const int col = wq * 8 + jj, n = c0 + col;
                         if (n < ncols && rvalid) {
                             float4 v = *(const float4*)(stage + col * BM + 4 * lane);
-                            const float bn = p.bias_mode == 2 ? p.bias[n0 + n] : 0.f;
+                            const float bn = bn8[jj];
                             v.x += bm4.x + bn; v.y += bm4.y + bn; v.z += bm4.z + bn; v.w += bm4.w + bn;
                             if (p.act) { v.x = act_fn(v.x, p.act); v.y = act_fn(v.y, p.act); v.z = act_fn(v.z, p.act); v.w = act_fn(v.w, p.act); }
                             if (p.gate) { v.x = __fmul_rn(v.x, gm4.x); v.y = __fmul_rn(v.y, gm4.y); v.z = __fmul_rn(v.z, gm4.z); v.w = __fmul_rn(v.w, gm4.w); }
                             const int64_t off = (int64_t)(n0 + n) * p.ldd + prow;
                             if (Rp) {
-                                const float4 rr = *(const float4*)(Rp + (int64_t)(n0 + n) * p.ldr + prow);
+                                const float4 rr = rr8[jj];
                                 v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
                             }
                             if (!p.skip_f32) *(float4*)(Dp + off) = v;
@@ -521,8 +606,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
             const int cbeg = (split * p.bn) / p.splits, cend = min(((split + 1) * p.bn) / p.splits, ncols);
             const bool vec_ok = (mrow + 3 < p.M) && ((p.ldd & 3) == 0) && ((((uintptr_t)Dp) & 15) == 0) && ((m0 & 3) == 0);
             const int64_t d2off = p.D2 ? (p.D2 - p.D) + (int64_t)((*p.d2_seq + 1u) & 1u) * p.d2_slot : 0;
+            // the residual of the NEXT column is requested before the partial tiles of this one are summed (same aliasing argument as the
+            // staged epilogue: a thread reads only elements it writes itself, one iteration ahead of the write of a different column)
+            const bool res_vec = vec_ok && Rp != nullptr && ((p.ldr & 3) == 0) && ((((uintptr_t)Rp) & 15) == 0);
+            float4 rnext = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (res_vec && cbeg + w8 < cend) rnext = *(const float4*)(Rp + ((int64_t)n0 + cbeg + w8) * p.ldr + prow);
 #pragma unroll 1
             for (int c = cbeg + w8; c < cend; c += 8) {
+                const float4 rcur = rnext;
+                if (res_vec && c + 8 < cend) rnext = *(const float4*)(Rp + ((int64_t)n0 + c + 8) * p.ldr + prow);
                 const uint32_t off = (uint32_t)(c * BM + 4 * lane) * 4u;
                 float4 part[8];
 #pragma unroll
@@ -537,7 +629,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc2(const __grid_constant_
                 if (p.gate) { v.x = __fmul_rn(v.x, gm.x); v.y = __fmul_rn(v.y, gm.y); v.z = __fmul_rn(v.z, gm.z); v.w = __fmul_rn(v.w, gm.w); }
                 float* dst = Dp + n * p.ldd + prow;
                 if (vec_ok && (Rp == nullptr || (((p.ldr & 3) == 0) && ((((uintptr_t)Rp) & 15) == 0)))) {
-                    if (Rp) { const float4 rr = *(const float4*)(Rp + n * p.ldr + prow); v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
+                    if (Rp) { const float4 rr = rcur; v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
                     if (!p.skip_f32) *(float4*)dst = v;
                     if (p.D16) {        // (launcher: 8-byte aligned 16-bit rows whenever D16 is set with splits > 1)
                         uint2 h;
@@ -667,6 +759,9 @@ bool encode_output(CUtensorMap* out, G2Params& kp, int64_t batch) {
 // (nkb then counts stages)
 bool fill_geometry(G2Params& kp, const b200_device_info& dev, int64_t M, int64_t N, int64_t batch, int nkb, int bn, int splits, unsigned* ctas, size_t* smem,
                    int halo_taps = 0) {
+    static int res_pf = -1;
+    if (res_pf < 0) { const char* e = getenv("GGML_B200_RES_PREFETCH"); res_pf = (e && *e) ? atoi(e) : 1; }
+    kp.res_pf = res_pf;
     static int nprod = -1;
     if (nprod < 0) { const char* e = getenv("GGML_B200_GEMM2_NPROD"); nprod = (e && *e && atoi(e) == 1) ? 1 : 2; }
     kp.nprod = nprod;
@@ -751,7 +846,12 @@ int b200_launch_gemm_tc2(cudaStream_t s, const b200_device_info& dev, const b200
     if (!fill_geometry(kp, dev, g.M, g.N, g.batch, nkb, bn, splits, &ctas, &smem)) return -1;
     CUtensorMap ta, tb;
     const int64_t a_batches = (g.batch + g.a_bcast - 1) / g.a_bcast;
-    if (!encode_rows(&ta, g.A, g.type, g.K, g.M, g.lda, a_batches, g.a_batch_stride, BM)) return -1;
+    if (g.geglu) {
+        // GEGLU mode: whole 64-feature slabs, the 16-bit operand as the only output, bias per feature or none, no other epilogue work
+        if (g.M != 2 * g.geglu || g.geglu % 64 || splits != 1 || !g.D16 || !g.skip_f32 || g.residual || g.gate || g.act || (g.bias && g.bias_mode != 1)) return -1;
+        if (((uintptr_t)g.D16 & 15) || (g.bias && ((uintptr_t)g.bias & 15)) || (g.d16_type != GGML_TYPE_F16 && g.d16_type != GGML_TYPE_BF16)) return -1;
+    }
+    if (!encode_rows(&ta, g.A, g.type, g.K, g.M, g.lda, a_batches, g.a_batch_stride, g.geglu ? BM / 2 : BM)) return -1;
     if (!encode_rows(&tb, g.B, g.type, g.K, g.N, g.ldb, g.batch, g.b_batch_stride, (uint32_t)(bn / 2))) return -1;
     kp.D = g.D; kp.ldd = g.ldd; kp.d_batch_stride = g.d_batch_stride;
     kp.M = g.M; kp.N = g.N;
@@ -762,10 +862,14 @@ int b200_launch_gemm_tc2(cudaStream_t s, const b200_device_info& dev, const b200
     kp.gate = g.gate;
     if ((g.wprefetch & 1) && a_batches == 1) { kp.wpf = (const char*)g.A; kp.wpf_ld = g.lda * 2; kp.wpf_rows = g.M; kp.wpf_kbytes = g.K * 2; kp.wpf_is_a = 1; }
     else if ((g.wprefetch & 2) && g.batch == 1) { kp.wpf = (const char*)g.B; kp.wpf_ld = g.ldb * 2; kp.wpf_rows = g.N; kp.wpf_kbytes = g.K * 2; kp.wpf_is_a = 0; }
-    kp.vec_epi = vec_epilogue_ok(kp, splits);
+    kp.geglu = g.geglu;
+    if (g.geglu) kp.wpf = nullptr;            // (the up-front L2 request assumes 128 consecutive A rows per CTA)
+    kp.vec_epi = g.geglu ? 0 : vec_epilogue_ok(kp, splits);
     // 16-bit copy: the staged epilogue (splits == 1) or the split-K reduce, both with 8-byte stores of four consecutive rows
     const bool d16_split_ok = splits > 1 && !g.residual && !(kp.M & 3) && !(kp.ldd & 3) && !(kp.d_batch_stride & 3) && !((uintptr_t)kp.D & 15);
-    if (g.D16 && (kp.vec_epi || d16_split_ok) && !((uintptr_t)g.D16 & 7) && (g.d16_type == GGML_TYPE_F16 || g.d16_type == GGML_TYPE_BF16)) {
+    if (g.geglu) {
+        kp.D16 = g.D16; kp.d16_bf16 = g.d16_type == GGML_TYPE_BF16; kp.skip_f32 = 1;
+    } else if (g.D16 && (kp.vec_epi || d16_split_ok) && !((uintptr_t)g.D16 & 7) && (g.d16_type == GGML_TYPE_F16 || g.d16_type == GGML_TYPE_BF16)) {
         kp.D16 = g.D16; kp.d16_bf16 = g.d16_type == GGML_TYPE_BF16; kp.skip_f32 = g.skip_f32;
     } else if (g.D16 && g.d16_strict) {
         return -1;          // the one-CTA kernel may still take it

@@ -42,7 +42,7 @@ EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C
 
 STAT_KEYS = ("graphs", "kernel_launches", "nodes_executed", "fused_nodes", "last_graph_ms", "total_graph_ms", "tc_gemm_launches",
              "tc_gemm_flops", "tc_gemm_us", "fused_attn_launches", "cuda_graph_replays", "implicit_convs", "q_read_in_place", "gemv_launches", "rope_launches", "side_stream_launches",
-             "gemm_ref_launches", "host_us", "weight_write_graphs", "per_graph_filter_packs", "persistent_gemm_launches", "cta2_gemm_launches",
+             "gemm_ref_launches", "host_us", "weight_write_graphs", "per_graph_filter_packs", "geglu_epilogues", "cta2_gemm_launches",
              "derived_weight_bytes", "unfused_attention", "peer_exchanges",
              "host_set_us", "host_get_us", "host_compute_us", "host_outside_us", "kv_in_place", "attn_out_f16_only", "gated_residual_epilogues")
 
