@@ -81,9 +81,12 @@ __global__ void __launch_bounds__(1024) k_gn_stats(const float* __restrict__ x, 
 // REGISTERS, computes the chunk mean and the chunk's sum of squared deviations from THAT mean (the oracle's two-pass arithmetic,
 // ops.cpp:4079-4152, per chunk), and the last CTA to finish merges the S partial (mean, M2) pairs in chunk order with the exact
 // pairwise update (Chan et al.) in double -- deterministic, one read of the activation.
-constexpr int GN2_THREADS = 256;                            // ~100 registers per thread: two or more CTAs per SM, so one's reduction overlaps another's loads
-constexpr int GN2_VEC = 16;                                  // float4 per thread
-constexpr int GN2_CHUNK = GN2_THREADS * GN2_VEC * 4;         // 16384 floats (64 KB in flight per CTA)
+// A CTA's life is load phase -> two block reductions -> partial + fence + atomic round trip; with two 64 KB CTAs per SM the second half
+// of that (no loads in flight) cost half the bandwidth (2.4 TB/s measured on the VAE levels).  32 KB chunks and four CTAs per SM: the same
+// bytes in flight, four phases that overlap.
+constexpr int GN2_THREADS = 256;
+constexpr int GN2_VEC = 8;                                   // float4 per thread
+constexpr int GN2_CHUNK = GN2_THREADS * GN2_VEC * 4;         // 8192 floats (32 KB in flight per CTA)
 
 __device__ __forceinline__ double block_sum_d(double v, double* red) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -102,7 +105,7 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
     return red[0];
 }
 
-__global__ void __launch_bounds__(GN2_THREADS, 2) k_gn_stats_chunked(const float* __restrict__ x, float2* __restrict__ stats, double2* partial,
+__global__ void __launch_bounds__(GN2_THREADS, 4) k_gn_stats_chunked(const float* __restrict__ x, float2* __restrict__ stats, double2* partial,
                                                                   unsigned* __restrict__ counters, int64_t inner, int C, int cpg, int G, int S,
                                                                   int64_t chunk, float eps, const float* __restrict__ addv) {
     pdl_wait();
@@ -201,6 +204,12 @@ __global__ void __launch_bounds__(256) k_to_nhwc_f16(const float* __restrict__ x
             if (UP == 1 && vec_ok && p + 3 < OHW) {
                 const float4 q = *(const float4*)(xc + p);     // OHW == H*W, 16-byte aligned: p % 4 == 0 and channel planes are multiples of 4 floats
                 v[sub][pass][0] = q.x; v[sub][pass][1] = q.y; v[sub][pass][2] = q.z; v[sub][pass][3] = q.w;
+            } else if (UP == 2 && vec_ok && (OW & 3) == 0 && p + 3 < OHW) {
+                // nearest x2: four consecutive output pixels of one row (p % 4 == 0, OW % 4 == 0) are two source pixels, each twice -- one
+                // 32-bit division and one 8-byte load instead of four 64-bit divisions and four loads (the pass was instruction bound)
+                const unsigned pu = (unsigned)p, oy = pu / (unsigned)OW, ox = pu - oy * (unsigned)OW;
+                const float2 q = *(const float2*)(xc + (int64_t)(oy >> 1) * W + (ox >> 1));
+                v[sub][pass][0] = q.x; v[sub][pass][1] = q.x; v[sub][pass][2] = q.y; v[sub][pass][3] = q.y;
             } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -236,7 +245,10 @@ __global__ void __launch_bounds__(256) k_to_nhwc_f16(const float* __restrict__ x
             for (int k = 0; k < 4; ++k) {
                 float o = ((addv ? v[sub][pass][k] + pre[pass] : v[sub][pass][k]) - mean[pass]) * rstd[pass];
                 o = o * w[pass] + b[pass];
-                if (act == 1) o = o / (1.0f + expf(-o));
+                // SiLU with the fast exponential / division (MUFU.EX2, MUFU.RCP): the IEEE division and expf expanded to ~35 instructions per
+                // element and made this pass INSTRUCTION bound (96 us for the 201 MB of a 512 x 512 x 128 VAE level, 2.1 TB/s); a few f32 ulp
+                // of difference disappear in the rounding to f16 that follows (the CPU oracle's vectorised SiLU is a polynomial itself)
+                if (act == 1) o = __fdividef(o, 1.0f + __expf(-o));
                 tile[cl][px4 + k] = o;
             }
         }

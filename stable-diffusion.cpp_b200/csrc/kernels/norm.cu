@@ -270,6 +270,79 @@ __global__ void __launch_bounds__(256) k_row_norm_vec(b200_td a, b200_td d, floa
     }
 }
 
+// Short rows (< 512 floats: the C = 320 LayerNorms of the 64 x 64 UNet level, 8192 rows per batched forward): ONE WARP per row, eight rows
+// per CTA, the row in registers as float4, shuffle reductions, no block barrier.  The CTA-per-row kernel above spent 19 us on 26 MB
+// (8192 CTAs of 128 threads, two block reductions each: 1.4 TB/s).
+template <int KIND>
+__global__ void __launch_bounds__(256) k_row_norm_warp(b200_td a, b200_td d, float eps, const float* __restrict__ rw, const float* __restrict__ rb, void* out16,
+                                                       int out16_bf16, int modulate, int64_t nrows) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const int64_t i1 = row % a.ne[1], r = row / a.ne[1];
+    const int64_t i2 = r % a.ne[2], i3 = r / a.ne[2];
+    const float4* x = (const float4*)((const char*)a.data + i1 * a.nb[1] + i2 * a.nb[2] + i3 * a.nb[3]);
+    float4* y = (float4*)((char*)d.data + i1 * d.nb[1] + i2 * d.nb[2] + i3 * d.nb[3]);
+    const int n4 = (int)(a.ne[0] >> 2);
+    const float n = (float)a.ne[0];
+    float4 v[4];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = lane + k * 32;
+        v[k] = i < n4 ? x[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (KIND == B200_NORM_LAYER) ? (v[k].x + v[k].y) + (v[k].z + v[k].w) : (v[k].x * v[k].x + v[k].y * v[k].y) + (v[k].z * v[k].z + v[k].w * v[k].w);
+    }
+    s = warp_sum(s);
+    float mean = 0.f, scale;
+    if (KIND == B200_NORM_LAYER) {
+        mean = s / n;
+        float s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = lane + k * 32;
+            if (i < n4) {
+                const float t0 = v[k].x - mean, t1 = v[k].y - mean, t2 = v[k].z - mean, t3 = v[k].w - mean;
+                s2 += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
+            }
+        }
+        s2 = warp_sum(s2);
+        scale = 1.0f / sqrtf(s2 / n + eps);
+    } else if (KIND == B200_NORM_RMS) {
+        scale = 1.0f / sqrtf(s / n + eps);
+    } else {
+        scale = 1.0f / fmaxf(sqrtf(s), eps);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = lane + k * 32;
+        if (i < n4) {
+            float o[4] = {(v[k].x - mean) * scale, (v[k].y - mean) * scale, (v[k].z - mean) * scale, (v[k].w - mean) * scale};
+            if (rw) {
+                const float4 w4 = ((const float4*)rw)[i];
+                const float4 b4 = rb ? ((const float4*)rb)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float ww[4] = {w4.x, w4.y, w4.z, w4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = modulate ? __fadd_rn(__fadd_rn(o[e], __fmul_rn(o[e], ww[e])), bb[e]) : o[e] * ww[e] + bb[e];
+            }
+            y[i] = make_float4(o[0], o[1], o[2], o[3]);
+            if (out16) {
+                uint2 h;
+                if (out16_bf16) {
+                    const __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+                    h.x = *(const uint32_t*)&p0; h.y = *(const uint32_t*)&p1;
+                } else {
+                    const __half2 p0 = __floats2half2_rn(o[0], o[1]), p1 = __floats2half2_rn(o[2], o[3]);
+                    h.x = *(const uint32_t*)&p0; h.y = *(const uint32_t*)&p1;
+                }
+                ((uint2*)out16)[row * n4 + i] = h;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // SOFT_MAX: one CTA per row; the scaled+masked row lives in shared memory (ne0 floats).
 // ------------------------------------------------------------------------------------------
@@ -348,6 +421,21 @@ int b200_launch_norm(cudaStream_t s, int kind, const b200_td& src, const b200_td
     const bool vec = src.ne[0] % 4 == 0 && src.ne[0] >= 512 && src.ne[0] <= 4096 && src.nb[0] == 4 && dst.nb[0] == 4 && !((uintptr_t)src.data & 15) && !((uintptr_t)dst.data & 15) &&
                      !(src.nb[1] & 15) && !(src.nb[2] & 15) && !(src.nb[3] & 15) && !(dst.nb[1] & 15) && !(dst.nb[2] & 15) && !(dst.nb[3] & 15) &&
                      !((uintptr_t)w & 15) && !((uintptr_t)b & 15) && !((uintptr_t)out16 & 7);
+    // short rows: a warp per row (same alignment conditions as the float4 path)
+    static int warp_rows = -1;
+    if (warp_rows < 0) { const char* e = getenv("GGML_B200_NORM_WARP"); warp_rows = (e && *e) ? atoi(e) : 1; }
+    const bool vec_small = warp_rows && src.ne[0] % 4 == 0 && src.ne[0] >= 64 && src.ne[0] < 512 && nrows >= 64 && src.nb[0] == 4 && dst.nb[0] == 4 && !((uintptr_t)src.data & 15) &&
+                           !((uintptr_t)dst.data & 15) && !(src.nb[1] & 15) && !(src.nb[2] & 15) && !(src.nb[3] & 15) && !(dst.nb[1] & 15) && !(dst.nb[2] & 15) && !(dst.nb[3] & 15) &&
+                           !((uintptr_t)w & 15) && !((uintptr_t)b & 15) && !((uintptr_t)out16 & 7);
+    if (vec_small) {
+        const unsigned grid = (unsigned)((nrows + 7) / 8);
+        switch (kind) {
+            case B200_NORM_LAYER: b200_launch(k_row_norm_warp<B200_NORM_LAYER>, dim3(grid), dim3(256), 0, s, src, dst, eps, w, b, out16, bf, modulate, nrows); break;
+            case B200_NORM_RMS: b200_launch(k_row_norm_warp<B200_NORM_RMS>, dim3(grid), dim3(256), 0, s, src, dst, eps, w, b, out16, bf, modulate, nrows); break;
+            default: b200_launch(k_row_norm_warp<B200_NORM_L2>, dim3(grid), dim3(256), 0, s, src, dst, eps, w, b, out16, bf, modulate, nrows); break;
+        }
+        return 1;
+    }
     if (vec) {
         switch (kind) {
             case B200_NORM_LAYER: b200_launch(k_row_norm_vec<B200_NORM_LAYER>, dim3((unsigned)nrows), dim3(256), 0, s, src, dst, eps, w, b, out16, bf, modulate); break;
