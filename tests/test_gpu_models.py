@@ -143,6 +143,9 @@ def test_producer_side_fusions_are_bit_identical(b200, arch, shape, cshape):
     # every attention layer of the flash-attention graph takes the in-place path (2 projections each) and hands f16 rows to to_out
     key = {k: st[k] for k in ("fused_attn_launches", "kv_in_place", "attn_out_f16_only", "q_read_in_place", "side_stream_launches")}
     assert st["kv_in_place"] > 0 and st["attn_out_f16_only"] > 0 and st["q_read_in_place"] > 0, key
+    # every FeedForward's GEGLU projection ran in the pair kernel's GEGLU mode (x | gate paired in one accumulator tile, only the 16-bit
+    # operand of net.2 written): no CONT / GELU / MUL pass, and -- asserted below -- not one bit of difference
+    assert st["geglu_epilogues"] > 0 and st["geglu_epilogues"] % 3 == 0, st["geglu_epilogues"]
     if arch == "sd15_unet":
         assert st["kv_in_place"] == 2 * st["fused_attn_launches"] and st["attn_out_f16_only"] == st["fused_attn_launches"], key
         # ... and every one of those projections ran on a side stream (context K / V hoisted to the start of the graph, self-attention
