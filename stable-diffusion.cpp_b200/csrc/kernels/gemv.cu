@@ -59,11 +59,39 @@ __global__ void __launch_bounds__(kWarps * 32) k_gemv(const WT* __restrict__ W, 
         const int c = lane + 32 * j;
         wreg[j] = c < K8 ? wrow[c] : make_uint4(0u, 0u, 0u, 0u);
     }
-    for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
-        const int n = i / K, k = i - n * K;
-        float v = X[(int64_t)n * ldx + k];
-        if (pre_act == 1) v = v / (1.0f + expf(-v));     // SiLU, the unary kernel's own expression
-        xs[i] = round_to<WT>(v);
+    if ((((uintptr_t)X) & 15) == 0 && (ldx & 3) == 0) {
+        // 16-byte loads, four per thread in flight: the scalar loop below is a chain of dependent-latency iterations (load, SiLU, store)
+        // and cost more than streaming the block's weight rows (K % 8 == 0: a float4 never straddles two activation rows)
+        const int K4 = K >> 2, total4 = N * K4;
+        for (int i0 = threadIdx.x; i0 < total4; i0 += 4 * blockDim.x) {
+            float4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < total4) { const int n = i / K4, k4 = i - n * K4; q[u] = *(const float4*)(X + (int64_t)n * ldx + 4 * k4); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < total4) {
+                    float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float v = e[c];
+                        if (pre_act == 1) v = v / (1.0f + expf(-v));     // SiLU, the unary kernel's own expression
+                        e[c] = round_to<WT>(v);
+                    }
+                    *(float4*)(xs + 4 * i) = make_float4(e[0], e[1], e[2], e[3]);
+                }
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
+            const int n = i / K, k = i - n * K;
+            float v = X[(int64_t)n * ldx + k];
+            if (pre_act == 1) v = v / (1.0f + expf(-v));     // SiLU, the unary kernel's own expression
+            xs[i] = round_to<WT>(v);
+        }
     }
     __syncthreads();
     for (int r = 0; r < rows_per_warp; ++r, m += kWarps) {
