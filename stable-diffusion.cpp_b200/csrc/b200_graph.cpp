@@ -1102,6 +1102,9 @@ struct fusion_state {
     // (the allocator's lifetimes are those of in-order execution)
     struct side_job { int pos; cudaEvent_t done; };
     std::vector<side_job> pend;
+    // adaLN modulation whose scale / shift vectors are produced BETWEEN the NORM and its MUL in graph order (the first use of a block's
+    // Modulation output): MUL node index -> the NORM node that was held back; the fused launch happens at the MUL's turn
+    std::unordered_map<int, int> deferred_norm;
 };
 
 static void count_uses(const ggml_cgraph* g, fusion_state& fs) {
@@ -1221,6 +1224,7 @@ static bool match_kv_projection(const b200_context* ctx, const ggml_cgraph* g, c
 }
 
 static bool same_order_view_of(const ggml_tensor* v, const ggml_tensor* root);
+static inline void base_range(const ggml_tensor* t, const char** lo, size_t* n);
 
 // MUL_MAT [-> views] [-> CONT of an order-preserving view] [-> views] [-> ADD bias]
 static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered, const ggml_tensor* src1_pre = nullptr,
@@ -1439,7 +1443,13 @@ static int try_fuse_mul_mat(b200_context* ctx, ggml_cgraph* g, fusion_state& fs,
     // the fused kernel writes `out` while other CTAs may still be reading the operands: `out` must not live in memory gallocr
     // recycled from an operand that is dead in graph order (e.g. the im2col matrix) -- run unfused then
     auto overlaps = [](const void* a, size_t na, const void* b, size_t nb) { return (const char*)a < (const char*)b + nb && (const char*)b < (const char*)a + na; };
-    if (overlaps(fz.out, ggml_nbytes(mm), mm->src[0]->data, ggml_nbytes(mm->src[0])) || overlaps(fz.out, ggml_nbytes(mm), mm->src[1]->data, ggml_nbytes(mm->src[1])))
+    // (an f32 activation against 16-bit / Q8_0 weights is read by the GEMM from its PACKED copy in workspace, written by a kernel that runs
+    //  before the GEMM on the same stream: the f32 tensor's memory may then be where the result goes -- gallocr does exactly that with the
+    //  attention output of a DiT block, which used to throw the whole projection + bias + gate + residual chain back to five kernels.
+    //  Few-row problems are the exception: the GEMV reads the f32 rows in place.)
+    const bool src1_packed = mm->src[1]->type == GGML_TYPE_F32 && mm->src[0]->type != GGML_TYPE_F32 && mm->ne[1] > 4 && !src1_pre;
+    if (overlaps(fz.out, ggml_nbytes(mm), mm->src[0]->data, ggml_nbytes(mm->src[0])) ||
+        (!src1_packed && overlaps(fz.out, ggml_nbytes(mm), mm->src[1]->data, ggml_nbytes(mm->src[1]))))
         return -2;
     if (fz.residual) { fz.d16 = nullptr; fz.skip_f32 = false; d16_act = nullptr; kv_cp = nullptr; }     // (a residual after the activation: keep the plain path)
     int n = op_mul_mat(ctx, mm, &fz);
@@ -1822,11 +1832,12 @@ static int emit_conv(b200_context* ctx, const conv_match& m, const conv_prologue
 // adaLN modulation of the DiT blocks (Flux::modulate flux.hpp:413-428, MMDiT, Wan):  n = NORM(x);  m = MUL(n, scale);  a = ADD(n, m);
 // y = ADD(a, shift)  with scale / shift rows of the modulation Linear.  One row-norm launch that also writes the f16 / bf16 operand of
 // the projection that consumes y.
-static int try_fuse_modulate(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
+// j1_given >= 0: the MUL's index when the NORM was held back (see try_defer_modulate); dry_run: check the pattern only, launch nothing
+static int try_fuse_modulate(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered, int j1_given = -1, bool dry_run = false) {
     ggml_tensor* nrm = g->nodes[i];
     if (nrm->op != GGML_OP_NORM || nrm->type != GGML_TYPE_F32 || !ggml_is_contiguous(nrm) || nrm->src[0]->type != GGML_TYPE_F32 || nrm->src[0]->nb[0] != 4) return -2;
     const int64_t C = nrm->ne[0];
-    const int j1 = next_node(g, fs, i);
+    const int j1 = j1_given >= 0 ? j1_given : next_node(g, fs, i);
     if (j1 < 0) return -2;
     const ggml_tensor* mul = g->nodes[j1];
     if (mul->op != GGML_OP_MUL || !(mul->flags & GGML_TENSOR_FLAG_COMPUTE) || mul->src[0] != nrm || !is_f32_vec(mul->src[1], C) || mul->src[1]->ne[0] != C ||
@@ -1851,6 +1862,7 @@ static int try_fuse_modulate(b200_context* ctx, ggml_cgraph* g, fusion_state& fs
     // the modulation vectors are produced earlier in the graph: their memory must not be where we write
     if (tensors_overlap(add2->data, ggml_nbytes(add2), mul->src[1]->data, (size_t)C * 4) || tensors_overlap(add2->data, ggml_nbytes(add2), add2->src[1]->data, (size_t)C * 4))
         return -2;
+    if (dry_run) return 0;
     float eps;
     memcpy(&eps, nrm->op_params, 4);
     int want = -1;
@@ -1868,9 +1880,42 @@ static int try_fuse_modulate(b200_context* ctx, ggml_cgraph* g, fusion_state& fs
                              (const float*)add2->src[1]->data, shadow, want, 1);
     if (n < 0) return -2;
     if (shadow) ctx->pack_cache[std::make_pair((const ggml_tensor*)add2, want)] = operand{shadow, want, add2->ne[0], add2->ne[0] * add2->ne[1], add2->ne[0] * add2->ne[1] * add2->ne[2]};
-    fs.done[j1] = 1; fs.done[j2] = 1; fs.done[j3] = 1;
-    *covered = 3;
+    if (j1_given < 0) fs.done[j1] = 1;          // (held-back form: j1 is the node being executed)
+    fs.done[j2] = 1; fs.done[j3] = 1;
+    *covered = j1_given < 0 ? 3 : 2;
     return n;
+}
+
+// NORM whose first reader comes a few nodes later: in the reference's graphs the scale / shift vectors of a block's FIRST modulate are
+// emitted between the NORM and the MUL (depth-first node order: ADD(x, MUL(x, scale)) visits the norm, then the Modulation Linear).
+// The NORM is held back -- nothing is launched at its turn -- and the fused norm + modulate kernel runs at the MUL's turn, when the
+// vectors exist.  Safe because the kernel then reads the NORM's INPUT: no node in between may write into that memory (gallocr may
+// have recycled it for one of them once the NORM, its last reader in graph order, has run), and none may read the NORM's output.
+static int try_defer_modulate(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i) {
+    static int en = -1;
+    if (en < 0) { const char* e = getenv("GGML_B200_DEFER_MODULATE"); en = (e && *e) ? atoi(e) : 1; }
+    if (!en) return -2;
+    ggml_tensor* nrm = g->nodes[i];
+    if (nrm->op != GGML_OP_NORM || (nrm->flags & GGML_TENSOR_FLAG_OUTPUT)) return -2;
+    const ggml_tensor* x = nrm->src[0];
+    const char* xlo; size_t xn;
+    base_range(x, &xlo, &xn);
+    int j1 = -1, work = 0;
+    for (int j = i + 1; j < g->n_nodes && j < i + 48; ++j) {
+        const ggml_tensor* t = g->nodes[j];
+        bool reads = false;
+        for (int sidx = 0; sidx < GGML_MAX_SRC && t->src[sidx]; ++sidx) reads |= t->src[sidx] == nrm;
+        if (reads) { j1 = j; break; }
+        if (fs.done[j] || is_view_op(t) || ggml_is_empty(t)) continue;
+        if (++work > 12) return -2;
+        if (tensors_overlap(t->data, ggml_nbytes(t), xlo, xn)) return -2;          // would overwrite the input before the held-back read
+        if (t->op == GGML_OP_CPY && t->src[1] && tensors_overlap(t->src[1]->data, ggml_nbytes(t->src[1]), xlo, xn)) return -2;
+    }
+    if (j1 < 0 || work == 0 || g->nodes[j1]->op != GGML_OP_MUL || is_view_op(g->nodes[j1])) return -2;
+    int cov = 0;
+    if (try_fuse_modulate(ctx, g, fs, i, &cov, j1, true) != 0) return -2;          // the MUL / ADD / ADD pattern must hold from j1 on
+    fs.deferred_norm[j1] = i;
+    return 0;                                                                      // nothing launched now
 }
 
 // GROUP_NORM -> MUL w -> ADD b [-> SILU]     /     NORM -> MUL w -> ADD b
@@ -2397,6 +2442,35 @@ static int try_fuse_rms_rope(b200_context* ctx, ggml_cgraph* g, fusion_state& fs
     return n;
 }
 
+// RMS_NORM(v) -> MUL(., w[d]) with nothing to absorb behind it (the QKNorm of a DiT double block, whose q / k are concatenated with the
+// other stream before the rotation: flux.hpp SelfAttention::pre_attention): one row-norm launch, product rounded like the MUL node
+static int try_fuse_rms_mul(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
+    static int en = -1;
+    if (en < 0) { const char* e = getenv("GGML_B200_RMS_MUL"); en = (e && *e) ? atoi(e) : 1; }
+    if (!en) return -2;
+    ggml_tensor* rms = g->nodes[i];
+    const ggml_tensor* v = rms->src[0];
+    if (rms->type != GGML_TYPE_F32 || v->type != GGML_TYPE_F32 || v->nb[0] != 4 || !ggml_is_contiguous(rms) || (rms->flags & GGML_TENSOR_FLAG_OUTPUT)) return -2;
+    const int j1 = next_node(g, fs, i);
+    if (j1 < 0) return -2;
+    ggml_tensor* mul = g->nodes[j1];
+    if (mul->op != GGML_OP_MUL || !(mul->flags & GGML_TENSOR_FLAG_COMPUTE) || mul->type != GGML_TYPE_F32 || !ggml_is_contiguous(mul) || !ggml_are_same_shape(mul, rms)) return -2;
+    if (mul->src[0] != rms) return -2;                          // value * weight, in the node's own operand order
+    const ggml_tensor* w = mul->src[1];
+    if (w == rms || w->type != GGML_TYPE_F32 || !ggml_is_contiguous(w) || ggml_nelements(w) != rms->ne[0] || w->ne[0] != rms->ne[0]) return -2;
+    if (!(mul->data == rms->data || single_use(fs, rms))) return -2;
+    // one pass reads v while it writes mul: identical placement is fine (a row is read completely before it is written), partial overlap is not
+    if (mul->data != v->data && tensors_overlap(mul->data, ggml_nbytes(mul), v->data, ggml_nbytes(v))) return -2;
+    if (tensors_overlap(mul->data, ggml_nbytes(mul), w->data, ggml_nbytes(w))) return -2;
+    float eps;
+    memcpy(&eps, rms->op_params, 4);
+    const int n = b200_launch_norm(ctx->stream, B200_NORM_RMS, b200_make_td(v), b200_make_td(mul), eps, (const float*)w->data, nullptr, nullptr, -1, 0);
+    if (n < 0) return -2;
+    fs.done[j1] = 1;
+    *covered = 1;
+    return n;
+}
+
 // IM2COL -> ...   or   UPSCALE(nearest x2) -> IM2COL -> ...
 static int try_fuse_conv(b200_context* ctx, ggml_cgraph* g, fusion_state& fs, int i, int* covered) {
     ggml_tensor* t = g->nodes[i];
@@ -2550,6 +2624,18 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
             else if (t->op == GGML_OP_GROUP_NORM || t->op == GGML_OP_NORM) {
                 n = try_fuse_norm(ctx, cgraph, fs, i, &covered);
                 if (n == -2 && t->op == GGML_OP_NORM && ctx->opt_chain_fusion) n = try_fuse_modulate(ctx, cgraph, fs, i, &covered);
+                if (n == -2 && t->op == GGML_OP_NORM && ctx->opt_chain_fusion) n = try_defer_modulate(ctx, cgraph, fs, i);
+            }
+            else if (t->op == GGML_OP_MUL && !fs.deferred_norm.empty() && fs.deferred_norm.count(i)) {
+                // the held-back NORM of this modulate: fused launch now; if the kernel declines, the NORM runs here (late) and the chain unfused
+                const int in = fs.deferred_norm[i];
+                fs.deferred_norm.erase(i);
+                n = try_fuse_modulate(ctx, cgraph, fs, in, &covered, i);
+                if (n < 0) {
+                    const int r = run_node(ctx, cgraph->nodes[in]);
+                    if (r < 0) n = -1;
+                    else { *launches += (uint64_t)r; n = -2; }
+                }
             }
             else if ((t->op == GGML_OP_IM2COL || t->op == GGML_OP_UPSCALE) && ctx->opt_tc_gemm && ctx->opt_implicit_conv) n = try_fuse_conv(ctx, cgraph, fs, i, &covered);
             else if (t->op == GGML_OP_CONT) {
@@ -2558,7 +2644,10 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
                 if (n == -2 && ctx->opt_chain_fusion) n = try_fuse_tokens_conv(ctx, cgraph, fs, i, &covered);
                 if (n == -2 && ctx->opt_chain_fusion) n = try_fuse_rope(ctx, cgraph, fs, i, &covered);
                 if (n == -2 && ctx->opt_chain_fusion) n = try_skip_q_cont(ctx, cgraph, fs, i);
-            } else if (t->op == GGML_OP_RMS_NORM && ctx->opt_chain_fusion) n = try_fuse_rms_rope(ctx, cgraph, fs, i, &covered);
+            } else if (t->op == GGML_OP_RMS_NORM && ctx->opt_chain_fusion) {
+                n = try_fuse_rms_rope(ctx, cgraph, fs, i, &covered);
+                if (n == -2) n = try_fuse_rms_mul(ctx, cgraph, fs, i, &covered);
+            }
             else if (t->op == GGML_OP_UNARY && ctx->opt_chain_fusion) n = try_fuse_silu_gemv(ctx, cgraph, fs, i, &covered);
             else if (t->op == GGML_OP_ADD && ctx->opt_chain_fusion && ctx->opt_tc_gemm && ctx->opt_implicit_conv) {
                 // ResBlock: h = conv(...) ; h = ADD(h, emb_out [1,1,C,N]) ; GroupNorm(h) -> SiLU -> conv (block.hpp:142-170).  The broadcast ADD has

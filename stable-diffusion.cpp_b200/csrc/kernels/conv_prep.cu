@@ -81,12 +81,11 @@ __global__ void __launch_bounds__(1024) k_gn_stats(const float* __restrict__ x, 
 // REGISTERS, computes the chunk mean and the chunk's sum of squared deviations from THAT mean (the oracle's two-pass arithmetic,
 // ops.cpp:4079-4152, per chunk), and the last CTA to finish merges the S partial (mean, M2) pairs in chunk order with the exact
 // pairwise update (Chan et al.) in double -- deterministic, one read of the activation.
-// A CTA's life is load phase -> two block reductions -> partial + fence + atomic round trip; with two 64 KB CTAs per SM the second half
-// of that (no loads in flight) cost half the bandwidth (2.4 TB/s measured on the VAE levels).  32 KB chunks and four CTAs per SM: the same
-// bytes in flight, four phases that overlap.
-constexpr int GN2_THREADS = 256;
-constexpr int GN2_VEC = 8;                                   // float4 per thread
-constexpr int GN2_CHUNK = GN2_THREADS * GN2_VEC * 4;         // 8192 floats (32 KB in flight per CTA)
+constexpr int GN2_THREADS = 256;                            // ~100 registers per thread: two CTAs per SM
+constexpr int GN2_VEC = 16;                                  // float4 per thread
+constexpr int GN2_CHUNK = GN2_THREADS * GN2_VEC * 4;         // 16384 floats (64 KB in flight per CTA)
+// (32 KB chunks with four CTAs per SM were tried on hardware: the 512 x 512 x 128 VAE level went from 55 us to 72 us -- twice the partial
+//  merges and atomics; profiles/r02_summary.md)
 
 __device__ __forceinline__ double block_sum_d(double v, double* red) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -105,7 +104,7 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
     return red[0];
 }
 
-__global__ void __launch_bounds__(GN2_THREADS, 4) k_gn_stats_chunked(const float* __restrict__ x, float2* __restrict__ stats, double2* partial,
+__global__ void __launch_bounds__(GN2_THREADS, 2) k_gn_stats_chunked(const float* __restrict__ x, float2* __restrict__ stats, double2* partial,
                                                                   unsigned* __restrict__ counters, int64_t inner, int C, int cpg, int G, int S,
                                                                   int64_t chunk, float eps, const float* __restrict__ addv) {
     pdl_wait();
