@@ -1560,6 +1560,16 @@ static const void* derived_weight(int device, cudaStream_t stream, const ggml_te
         g_pw_generation.fetch_add(1, std::memory_order_relaxed);
     }
     const size_t bytes = kind == 0 ? ggml_nbytes(w) : (size_t)ggml_nelements(w) * 2;
+    // byte cap on the derived copies (GGML_B200_DERIVED_CAP_MB, default 96 GB of the 180 GB): past it every copy is dropped -- they are
+    // re-derived on demand, and the generation bump keeps captured plans from replaying against freed memory (cudaFree synchronises)
+    static int64_t cap = -1;
+    if (cap < 0) { const char* e = getenv("GGML_B200_DERIVED_CAP_MB"); cap = ((e && *e) ? (int64_t)atoll(e) : (int64_t)96 * 1024) * 1048576; }
+    if ((int64_t)(g_pw_bytes.load(std::memory_order_relaxed) + bytes) > cap && !g_packed_weights.empty()) {
+        for (auto& kv : g_packed_weights) cudaFree(kv.second.ptr);
+        g_packed_weights.clear();
+        g_pw_bytes.store(0, std::memory_order_relaxed);
+        g_pw_generation.fetch_add(1, std::memory_order_relaxed);
+    }
     void* p = nullptr;
     if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     int n = kind == 0 ? b200_launch_pack_conv_weight(stream, w->data, p, (int)w->ne[0], (int)w->ne[1], w->ne[2], w->ne[3])

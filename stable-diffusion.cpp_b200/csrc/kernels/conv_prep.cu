@@ -13,6 +13,7 @@
 #include "b200_launch.cuh"
 
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace {
 
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(GN2_THREADS, 2) k_gn_stats_chunked(const float
 // first use -- the 64-pixel version kept only 16 KB per CTA in flight and ran at a third of the HBM rate on the VAE's 512x512 levels.
 // Store: one warp writes one pixel's 64 channels = 128 contiguous bytes of the NHWC row.
 template <int UP, int NSUB>
-__global__ void __launch_bounds__(256) k_to_nhwc_f16(const float* __restrict__ x, __half* __restrict__ out, const float2* __restrict__ stats,
+__global__ void __launch_bounds__(256, NSUB == 2 ? 4 : 1) k_to_nhwc_f16(const float* __restrict__ x, __half* __restrict__ out, const float2* __restrict__ stats,
                                                      const float* __restrict__ gw, const float* __restrict__ gb, int C, int H, int W, int OH,
                                                      int OW, int cpg, int G, int act, int vec_ok, const float* __restrict__ addv) {
     pdl_wait();
@@ -337,12 +338,16 @@ int b200_launch_to_nhwc_f16(cudaStream_t s, const float* x, void* out, int64_t N
     if (C % 64 != 0) return -1;
     const int64_t OH = H * up, OW = W * up;
     const int cpg = n_groups > 0 ? (int)((C + n_groups - 1) / n_groups) : 1;
-    const int nsub = (up == 1 && OH * OW >= 16384) ? 4 : 1;           // large images: 256 pixels per CTA, 64 KB of loads in flight
+    // large images: 256 pixels per CTA, 64 KB of loads in flight (two CTAs per SM); GGML_B200_NHWC_NSUB=2: 128 pixels, four CTAs per SM (A/B option)
+    static int nsub_big = -1;
+    if (nsub_big < 0) { const char* e = getenv("GGML_B200_NHWC_NSUB"); nsub_big = (e && atoi(e) == 2) ? 2 : 4; }
+    const int nsub = (up == 1 && OH * OW >= 16384) ? nsub_big : 1;
     dim3 grid((unsigned)((OH * OW + 64 * nsub - 1) / (64 * nsub)), (unsigned)(C / 64), (unsigned)N);
     if (grid.y > 65535 || N > 65535 || (up != 1 && up != 2)) return -1;
     const int vec_ok = (((uintptr_t)x & 15) == 0 && ((H * W) & 3) == 0) ? 1 : 0;
 #define NHWC_ARGS x, (__half*)out, (const float2*)stats, gw, gb, (int)C, (int)H, (int)W, (int)OH, (int)OW, cpg, n_groups, act, vec_ok, addv
     if (up == 1 && nsub == 4) b200_launch(k_to_nhwc_f16<1, 4>, dim3(grid), dim3(256), 0, s, NHWC_ARGS);
+    else if (up == 1 && nsub == 2) b200_launch(k_to_nhwc_f16<1, 2>, dim3(grid), dim3(256), 0, s, NHWC_ARGS);
     else if (up == 1) b200_launch(k_to_nhwc_f16<1, 1>, dim3(grid), dim3(256), 0, s, NHWC_ARGS);
     else b200_launch(k_to_nhwc_f16<2, 1>, dim3(grid), dim3(256), 0, s, NHWC_ARGS);
 #undef NHWC_ARGS
