@@ -108,6 +108,14 @@ void ggml_backend_b200_reset_stats(ggml_backend_t backend);
  * returns 0 on success, -1 for an unknown key. */
 int ggml_backend_b200_set_option(ggml_backend_t backend, const char* key, int value);
 
+/* Diagnostic, host-only (no reference counterpart; the reference's CUDA backend keeps its kernel selection internal,
+ * ggml/src/ggml-cuda/ggml-cuda.cu:1825-2038): the plan -- tile width of the CTA pair, split-K factor, filter taps served per image box --
+ * the halo-reuse 3x3 convolution would run for `batch` images of H x W x C -> OC on `sm_count` SMs, and its modelled time in microseconds.
+ * Returns 1, or 0 when the shape is outside the halo envelope (W % 8, H % 16, C % 64).  tests/test_cabi.py pins it against the committed
+ * hardware sweep. */
+int ggml_backend_b200_debug_conv_plan(int64_t batch, int64_t H, int64_t W, int64_t C, int64_t OC, int sm_count, int* bn, int* splits, int* taps,
+                                      double* model_us);
+
 /* ---- CFG-batch split over a pair of GPUs, one process per GPU (kernels/peer.cu).  The reference offers nothing here
  * (its sample() is serial, stable-diffusion.cpp:2811-2836); the closest reference interface is the meta backend's
  * "ggml_backend_comm_init / _allreduce_tensor" extension pair (ggml/src/ggml-backend-meta.cpp:2207-2220), found the same way:

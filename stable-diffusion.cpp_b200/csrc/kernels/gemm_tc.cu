@@ -610,6 +610,24 @@ cudaError_t launch_cfg(cudaStream_t s, dim3 grid, const CUtensorMap& ta, const C
 
 }  // namespace
 
+// Diagnostic C-ABI (include/ggml-b200.h): the plan the halo-reuse convolution front end would choose for a 3x3 convolution of `batch`
+// images of H x W x C -> OC on a device with `sm_count` SMs.  Pure host code: lets a CPU test pin the fitted cost model against the
+// committed hardware sweep (profiles/r02_conv_halo_sweep.log).  Returns 0 when the shape is outside the halo envelope.
+extern "C" int ggml_backend_b200_debug_conv_plan(int64_t batch, int64_t H, int64_t W, int64_t C, int64_t OC, int sm_count, int* bn, int* splits, int* taps,
+                                                 double* model_us) {
+    if (batch < 1 || H < 1 || W < 1 || C % 64 || C < 64 || OC < 1 || W % 8 || H % 16 || (H * W) % 128) return 0;
+    b200_device_info dev;
+    memset(&dev, 0, sizeof(dev));
+    dev.sm_count = sm_count;
+    const Plan2H ph = choose_plan2_halo(dev, H * W, OC, batch, (int)(C / 64));
+    if (ph.bn <= 0) return 0;
+    if (bn) *bn = ph.bn;
+    if (splits) *splits = ph.splits;
+    if (taps) *taps = ph.taps;
+    if (model_us) *model_us = ph.cycles / 1965.0;
+    return 1;
+}
+
 size_t b200_gemm_tc_workspace_bytes(const b200_device_info&, const b200_gemm_args&) {
     return 0;   // split-K partials live in distributed shared memory
 }

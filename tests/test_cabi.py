@@ -134,3 +134,34 @@ def test_t5_text_encoder_graph_is_claimed_by_the_plugin(harness):
     m.close()
     assert out.shape[-2:] == (32, 4096) and np.isfinite(out).all()
     assert bad == 0, f"{bad} node(s) would fall back to the CPU, first: {first}"
+
+
+def test_halo_conv_plan_model_against_committed_hardware_sweep():
+    """The fitted cost model of the halo-reuse convolution (gemm_tc.cu conv_halo_model) must keep choosing plans within 15 % of the best
+    plan MEASURED on B200 for every shape of the committed sweep (profiles/r02_conv_halo_sweep.log: tile width x split-K x taps per box,
+    each line element-exact against the per-tap kernel), and its predicted time within 35 % of the measured one."""
+    from sdb200 import B200_SO
+    lib = ctypes.CDLL(str(B200_SO))
+    fn = lib.ggml_backend_b200_debug_conv_plan
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int64] * 5 + [ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 3 + [ctypes.POINTER(ctypes.c_double)]
+    shapes = {"sd15 64x64 320->320 x2": (2, 64, 64, 320, 320), "sd15 32x32 640->640 x2": (2, 32, 32, 640, 640),
+              "sd15 16x16 1280->1280 x2": (2, 16, 16, 1280, 1280), "sd15 64x64 640->320 x2": (2, 64, 64, 640, 320),
+              "sd15 32x32 1280->640 x2": (2, 32, 32, 1280, 640), "vae 512x512 128->128": (1, 512, 512, 128, 128),
+              "vae 256x256 256->256": (1, 256, 256, 256, 256), "vae 128x128 512->512": (1, 128, 128, 512, 512),
+              "sdxl 128x128 320->320": (1, 128, 128, 320, 320), "sdxl 64x64 640->640": (1, 64, 64, 640, 640)}
+    meas = {}
+    for line in (REPO / "profiles" / "r02_conv_halo_sweep.log").read_text().splitlines():
+        m = re.match(r"(\S+ \S+ \S+(?: x2)?)\s+(\d+)\s+(\d+)\s+(\d+) \|\s+([\d.]+)", line)
+        if m:
+            meas[(m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(4)))] = float(m.group(5))
+    assert len(meas) > 150
+    for name, (n, H, W, C, OC) in shapes.items():
+        bn, sp, taps, us = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+        assert fn(n, H, W, C, OC, 148, ctypes.byref(bn), ctypes.byref(sp), ctypes.byref(taps), ctypes.byref(us)) == 1, name
+        key = (name, bn.value, sp.value, taps.value)
+        assert key in meas, f"{name}: chosen plan {key[1:]} was not part of the hardware sweep"
+        best = min(v for k, v in meas.items() if k[0] == name and k[3] > 0)
+        assert meas[key] <= 1.15 * best, f"{name}: chosen {key[1:]} measured {meas[key]} us, best halo plan {best} us"
+        assert abs(us.value - meas[key]) <= 0.35 * meas[key], f"{name}: model {us.value:.1f} us vs measured {meas[key]} us"
+    assert fn(1, 8, 8, 1280, 1280, 148, None, None, None, None) == 0      # 8 x 8 level: outside the 16 x 8 patch envelope
