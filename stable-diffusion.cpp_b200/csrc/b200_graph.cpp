@@ -2702,6 +2702,11 @@ static enum ggml_status execute_nodes(b200_context* ctx, ggml_cgraph* cgraph, ui
     }
     for (auto& pj : fs.pend) cudaStreamWaitEvent(ctx->stream, pj.done, 0);      // every side branch joins before the graph ends
     fs.pend.clear();
+    if (!fs.deferred_norm.empty()) {
+        // a held-back NORM whose MUL was never reached (covered by another fusion): its value was never produced -- fail loudly
+        GGML_LOG_ERROR("ggml-b200: %zu held-back NORM node(s) were never executed\n", fs.deferred_norm.size());
+        return GGML_STATUS_FAILED;
+    }
     if (!ctx->capturing && side_on) {       // head-room for the capture of this same graph (no event may be created while capturing)
         while (ctx->ev_pool.size() < ctx->ev_next + 8) {
             cudaEvent_t e = nullptr;
