@@ -116,6 +116,12 @@ int ggml_backend_b200_set_option(ggml_backend_t backend, const char* key, int va
 int ggml_backend_b200_debug_conv_plan(int64_t batch, int64_t H, int64_t W, int64_t C, int64_t OC, int sm_count, int* bn, int* splits, int* taps,
                                       double* model_us);
 
+/* Diagnostic, host-only: launch geometry of the CTA-pair tcgen05 kernel for a problem of `batch` x [M rows of A, N rows of B, nkb 64-wide k-blocks
+ * (halo modes: ring stages)] with tile width bn, split-K factor `splits` and `halo_taps` (0 | 3 | 9) filter taps per image box: ring stages, bytes
+ * per stage, dynamic shared memory, TMEM columns, CTAs.  Returns 0 when the plan is outside the kernel's envelope. */
+int ggml_backend_b200_debug_pair_geometry(int64_t M, int64_t N, int64_t batch, int nkb, int bn, int splits, int halo_taps, int sm_count, int* stages,
+                                          int* stage_bytes, int64_t* smem_bytes, int* tmem_cols, int* ctas);
+
 /* ---- CFG-batch split over a pair of GPUs, one process per GPU (kernels/peer.cu).  The reference offers nothing here
  * (its sample() is serial, stable-diffusion.cpp:2811-2836); the closest reference interface is the meta backend's
  * "ggml_backend_comm_init / _allreduce_tensor" extension pair (ggml/src/ggml-backend-meta.cpp:2207-2220), found the same way:

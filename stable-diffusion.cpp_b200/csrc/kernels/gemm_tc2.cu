@@ -886,6 +886,28 @@ int b200_launch_gemm_tc2(cudaStream_t s, const b200_device_info& dev, const b200
     return 1;
 }
 
+// Diagnostic C-ABI (include/ggml-b200.h), host only: the launch geometry of the pair kernel for a tile width / split-K factor / taps per
+// image box -- ring stages, bytes per stage, dynamic shared memory, TMEM columns, CTAs.  tests/test_cabi.py sweeps every legal plan and
+// checks the invariants the kernel relies on (1024-byte aligned swizzle atoms, shared-memory and TMEM budgets, split-K partial tile fits the ring).
+extern "C" int ggml_backend_b200_debug_pair_geometry(int64_t M, int64_t N, int64_t batch, int nkb, int bn, int splits, int halo_taps, int sm_count, int* stages,
+                                                     int* stage_bytes, int64_t* smem_bytes, int* tmem_cols, int* ctas) {
+    if (bn < 16 || bn > 256 || (bn & 15) || splits < 1 || splits > 4 || (halo_taps != 0 && halo_taps != 3 && halo_taps != 9)) return 0;
+    b200_device_info dev;
+    memset(&dev, 0, sizeof(dev));
+    dev.sm_count = sm_count;
+    G2Params kp;
+    memset(&kp, 0, sizeof(kp));
+    unsigned c = 0;
+    size_t smem = 0;
+    if (!fill_geometry(kp, dev, M, N, batch, nkb, bn, splits, &c, &smem, halo_taps)) return 0;
+    if (stages) *stages = kp.stages;
+    if (stage_bytes) *stage_bytes = kp.stage_bytes;
+    if (smem_bytes) *smem_bytes = (int64_t)smem;
+    if (tmem_cols) *tmem_cols = kp.tmem_cols;
+    if (ctas) *ctas = (int)c;
+    return 1;
+}
+
 // taps per ring stage the halo-reuse convolution would use for (bn, splits): 9 (whole 3x3 neighbourhood from one box) when two such
 // stages fit the shared memory, else 3 (one filter row per box), 0 when neither fits
 int b200_conv_tc2_halo_taps(int bn, int splits) {

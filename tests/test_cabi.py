@@ -165,3 +165,43 @@ def test_halo_conv_plan_model_against_committed_hardware_sweep():
         assert meas[key] <= 1.15 * best, f"{name}: chosen {key[1:]} measured {meas[key]} us, best halo plan {best} us"
         assert abs(us.value - meas[key]) <= 0.35 * meas[key], f"{name}: model {us.value:.1f} us vs measured {meas[key]} us"
     assert fn(1, 8, 8, 1280, 1280, 148, None, None, None, None) == 0      # 8 x 8 level: outside the 16 x 8 patch envelope
+
+
+def test_pair_kernel_geometry_invariants_over_every_legal_plan():
+    """fill_geometry (gemm_tc2.cu) for every tile width x split-K x taps-per-box the dispatchers can ask for: the invariants the kernel's
+    addressing relies on -- stages of whole 1024-byte swizzle atoms, the ring + the two 16 KB staging tiles inside the 227 KB of dynamic shared
+    memory, a split-K partial tile [bn][128] f32 that fits the ring it reuses, two accumulators of bn columns inside a power-of-two TMEM
+    allocation of at most 512 columns, and a grid of whole CTA pairs that never exceeds the SM count in the persistent (split 1) form."""
+    from sdb200 import B200_SO
+    lib = ctypes.CDLL(str(B200_SO))
+    fn = lib.ggml_backend_b200_debug_pair_geometry
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int64] * 3 + [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_int)] * 2 + [ctypes.POINTER(ctypes.c_int64)] + [ctypes.POINTER(ctypes.c_int)] * 2
+    legal = 0
+    for taps in (0, 3, 9):
+        for bn in range(16, 257, 16):
+            for splits in (1, 2, 4):
+                for (M, N, batch, nkb) in ((262144, 128, 1, 18), (4096, 320, 2, 45), (256, 1280, 2, 180), (1024, 640, 2, 90), (320, 4096, 2, 5)):
+                    st, sb, tm, ct = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+                    sm = ctypes.c_int64()
+                    if splits > nkb:
+                        continue
+                    if not fn(M, N, batch, nkb, bn, splits, taps, 148, ctypes.byref(st), ctypes.byref(sb), ctypes.byref(sm), ctypes.byref(tm), ctypes.byref(ct)):
+                        continue
+                    legal += 1
+                    tag = (taps, bn, splits, M, N)
+                    assert sb.value % 1024 == 0, tag
+                    a_bytes = {0: 16384, 3: 20 * 1024, 9: 23 * 1024}[taps]
+                    assert sb.value == a_bytes + max(taps, 1) * (bn // 2) * 128, tag
+                    assert 2 <= st.value <= 10 and (taps != 3 or st.value >= 3), tag
+                    assert sm.value <= 227 * 1024 - 2048, tag
+                    assert sm.value >= st.value * sb.value + (32768 if splits == 1 else 0), tag
+                    if splits > 1:
+                        assert st.value * sb.value >= bn * 128 * 4, tag
+                    assert tm.value in (32, 64, 128, 256, 512) and tm.value >= 2 * bn, tag
+                    assert ct.value % 2 == 0 and ct.value >= 2, tag
+                    if splits == 1:
+                        assert ct.value <= 148, tag
+    assert legal > 300
+    assert fn(4096, 320, 2, 45, 24, 1, 0, 148, None, None, None, None, None) == 0          # tile width must be a multiple of 16
+    assert fn(4096, 320, 2, 45, 256, 1, 9, 148, None, None, None, None, None) == 0         # nine 16 KB filter tiles + the image box: no two stages fit
