@@ -48,7 +48,8 @@ const char* sdh_last_error(void);
  *          single-graph decode returns NaN from the second frame on, on its own CPU backend too, so parity is pinned on one frame)
  * wtype:   "f32" | "f16" | "bf16" | "q8_0"  (dtype of Linear weights; conv weights are always F16 as
  *           in the reference, ggml_extend.hpp:3600-3603; norm/bias are F32)
- * flags:   bit0 = flash attention graph variant (--diffusion-fa), bit1 = conv2d direct
+ * flags:   bit0 = flash attention graph variant (--diffusion-fa), bit1 = conv2d direct, bit2 = place the parameters without filling them
+ *          (graph / supports_op walks that never run the model: a multi-GB synthetic checkpoint is not generated)
  * seed:    weight seed -- the same seed gives byte-identical weights on every backend
  * n_threads: threads for the CPU backend (ignored by GPU backends)                           */
 sdh_model* sdh_model_create(const char* device, const char* arch, const char* wtype,

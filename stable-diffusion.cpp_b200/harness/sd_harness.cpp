@@ -129,7 +129,8 @@ struct SyntheticWeights : public RunnerWeightManager {
     void release_compute_backend_params(const std::vector<ggml_tensor*>&) override {}
     void release_params_backend_params(const std::vector<ggml_tensor*>&) override {}
 
-    bool materialise(ggml_backend_t backend, const std::map<std::string, ggml_tensor*>& tensors, uint64_t seed) {
+    // fill == false: tensors are placed in the buffer but keep whatever the allocation holds (graph / claim walks that never run the model)
+    bool materialise(ggml_backend_t backend, const std::map<std::string, ggml_tensor*>& tensors, uint64_t seed, bool fill = true) {
         ggml_backend_buffer_type_t buft = ggml_backend_get_default_buffer_type(backend);
         size_t align = ggml_backend_buft_get_alignment(buft);
         size_t total = 0;
@@ -149,6 +150,7 @@ struct SyntheticWeights : public RunnerWeightManager {
             size_t sz = ggml_backend_buft_get_alloc_size(buft, t);
             if (ggml_backend_tensor_alloc(buffer, t, base + off) != GGML_STATUS_SUCCESS) return false;
             off += (sz + align - 1) / align * align;
+            if (!fill) { bytes += ggml_nbytes(t); count++; continue; }
 
             const std::string& name = kv.first;
             int64_t n = ggml_nelements(t);
@@ -514,7 +516,7 @@ sdh_model* sdh_model_create(const char* device, const char* arch, const char* wt
         fail("unknown arch: " + a);
         return nullptr;
     }
-    if (!m->weights->materialise(m->backend, tensors, seed)) {
+    if (!m->weights->materialise(m->backend, tensors, seed, (flags & 4) == 0)) {
         fail("weight allocation failed");
         return nullptr;
     }

@@ -19,6 +19,7 @@ B200_SO = Path(os.environ.get("SDB200_PLUGIN", str(REPO / "stable-diffusion.cpp_
 
 FLAG_FLASH_ATTN = 1
 FLAG_CONV_DIRECT = 2
+FLAG_NO_WEIGHT_VALUES = 4      # place the parameters but do not fill them: graph / claim walks that never run the model
 
 
 class SdhTensor(C.Structure):

@@ -92,7 +92,7 @@ def test_every_graph_node_is_claimed_by_the_plugin(harness, arch, wtype, flags, 
     from sdb200 import B200_SO
     from oracle.cpu_ref import load_cpu_oracle
     load_cpu_oracle(harness)
-    m = harness.model("CPU", arch, wtype, flags, 1234, 2)
+    m = harness.model("CPU", arch, wtype, flags | 4, 1234, 2)          # bit 2: parameters placed, not filled -- nothing is computed here
     x = harness.randn(42, xs)
     t = np.full((xs[0] if arch == "unet_tiny" else 1,), 999.0, np.float32) if cs is not None or arch != "vae_decoder" else None
     ctx = harness.randn(43, cs) if cs else None
